@@ -1,0 +1,256 @@
+/*
+ * mctsb200.h -- C ABI of libmctsb200.so: the B200 (sm_100a) search loop behind MCTS.jl's
+ * MCTSSolver/DPWSolver -> solve -> action/action_info API.
+ *
+ * What this boundary replaces in the reference (all paths relative to /root/reference):
+ *   - the body of build_tree                      src/vanilla.jl:209-237   (vanilla UCT)
+ *   - the search block of DPW action_info         src/dpw.jl:29-67         (double progressive widening)
+ *   - everything those call downward: simulate (src/vanilla.jl:240-276, src/dpw.jl:80-154),
+ *     insert_node! (src/vanilla.jl:292-307), insert_state_node!/insert_action_node!
+ *     (src/dpw_types.jl:162-186), best_sanode_UCB (src/vanilla.jl:354-386, src/dpw.jl:179-199),
+ *     best_sanode_Q / best_sanode (src/vanilla.jl:339-349, src/dpw.jl:163-173),
+ *     estimate_value(::SolvedRolloutEstimator) (src/domain_knowledge.jl:65-73) with the POMDPTools
+ *     RolloutSimulator loop, numeric init_Q/init_N/estimate_value (src/domain_knowledge.jl:10,82,91),
+ *     RandomActionGenerator (src/action_gen.jl:11-13) and the model's gen/isterminal/actions.
+ * The solver structs, solve(), action()/action_info() wrappers, default_action handling and tree
+ * visualisation stay on the host (Julia glue: mcts.jl_b200/julia/MCTSB200.jl; Python mirror used by the
+ * tests: mcts.jl_b200/solvers.py).  INTEGRATION.md shows the ccall stubs.
+ *
+ * Conventions
+ *   - every entry point is extern "C", takes plain pointers and sizes, never throws, never aborts;
+ *   - return value: 0 = MCTSB200_OK, negative = error; text via mctsb200_last_error() (thread local);
+ *   - the caller owns every host buffer; the library owns all device memory inside a ctx;
+ *   - a ctx is bound to ONE CUDA device (one process per GPU; multi-GPU = several processes, roots
+ *     sharded by the host with `root_index_base`, see mcts.jl_b200/distributed.py) and is not re-entrant,
+ *     exactly like a reference planner (src/vanilla.jl:129-135);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call fails.
+ *   - actions are returned as 0-based indices into actions(mdp) iteration order
+ *     (SimpleGridWorld: up, down, left, right; MountainCar: -1.0, 0.0, 1.0); node ids in exported
+ *     trees are 1-based in insertion order, as in MCTSTree/DPWTree.
+ */
+#ifndef MCTSB200_H
+#define MCTSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCTSB200_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------------------------- */
+enum {
+    MCTSB200_OK = 0,
+    MCTSB200_ERR_INVALID_ARG = -1,
+    MCTSB200_ERR_UNSUPPORTED = -2,   /* option not expressible on the device (host closures etc.)    */
+    MCTSB200_ERR_TERMINAL_ROOT = -3, /* DPW called on a terminal state (src/dpw.jl:22-27)             */
+    MCTSB200_ERR_CAPACITY = -4,      /* a per-tree table overflowed                                    */
+    MCTSB200_ERR_CUDA = -5,          /* CUDA runtime error or no device                                */
+    MCTSB200_ERR_STATE = -6          /* call sequence error (e.g. tree query before plan)              */
+};
+
+/* ---- built-in MDP plugins ------------------------------------------------------------------- */
+enum { MCTSB200_MDP_GRIDWORLD = 0, MCTSB200_MDP_MOUNTAINCAR = 1, MCTSB200_MDP_COUNT = 2 };
+
+#define MCTSB200_GW_MAX_SPECIAL 32
+
+/* SimpleGridWorld (POMDPModels.jl; restated in SURVEY.md 8c). State = two int64 (x, y), 1-based;
+ * the terminal state is (-1,-1). */
+typedef struct {
+    int32_t nx, ny;         /* size, default (10,10); nx*ny + 1 <= 65535                          */
+    double tprob;           /* default 0.7                                                        */
+    double discount;        /* default 0.95                                                       */
+    int32_t n_rewards;      /* rewards Dict entries                                               */
+    int32_t n_terminate;    /* terminate_from Set entries (default: the reward cells)             */
+    int32_t reward_x[MCTSB200_GW_MAX_SPECIAL], reward_y[MCTSB200_GW_MAX_SPECIAL];
+    double reward_v[MCTSB200_GW_MAX_SPECIAL];
+    int32_t term_x[MCTSB200_GW_MAX_SPECIAL], term_y[MCTSB200_GW_MAX_SPECIAL];
+} mctsb200_gridworld_params;
+
+/* MountainCar (POMDPModels.jl). State = two float64 (x, v). */
+typedef struct {
+    double discount; /* 0.99  */
+    double cost;     /* -1.0  */
+    double jackpot;  /* 100.0 */
+} mctsb200_mountaincar_params;
+
+/* ---- solver configuration -------------------------------------------------------------------- */
+enum { MCTSB200_KIND_UCT = 0, MCTSB200_KIND_DPW = 1 };
+enum { MCTSB200_EST_ROLLOUT = 0, MCTSB200_EST_CONSTANT = 1, MCTSB200_EST_TABLE = 2 };
+enum {
+    MCTSB200_POLICY_RANDOM = 0,    /* RandomPolicy: rand(rng, actions(mdp, s))                      */
+    MCTSB200_POLICY_CONSTANT = 1,  /* FunctionPolicy(s -> actions[param[0]])  (test/options.jl:29)  */
+    MCTSB200_POLICY_GW_SEEK = 2,   /* notebook SeekTarget(GWPos(param[0], param[1]))                */
+    MCTSB200_POLICY_MC_ENERGY = 3  /* MountainCar: push in the direction of motion (v<0 ? -1 : +1)  */
+};
+
+/* Flat mirror of MCTSSolver (src/vanilla.jl:28-62) and DPWSolver (src/dpw_types.jl:45-100).
+ * Fields that hold host closures in the reference (callback, timer, reset_callback, show_progress,
+ * Function/object-valued init_Q/init_N/estimate_value/next_action) have no representation here: the
+ * host glue must refuse them (MCTSB200_ERR_UNSUPPORTED) -- there is no CPU fallback. */
+typedef struct {
+    int32_t struct_size;          /* = sizeof(mctsb200_solver_cfg), ABI guard                      */
+    int32_t kind;                 /* MCTSB200_KIND_*                                               */
+    int64_t n_iterations;
+    int32_t depth;
+    int32_t rollouts_per_leaf;    /* 1 = reference semantics; K>1 averages K rollouts per leaf     */
+    double exploration_constant;  /* >= 0                                                          */
+    double max_time;              /* seconds; +inf = off. Checked between iteration chunks.        */
+    /* DPW only */
+    double k_action, alpha_action, k_state, alpha_state;
+    int32_t enable_action_pw, enable_state_pw, check_repeat_state, check_repeat_action;
+    int32_t keep_tree;            /* DPW keep_tree / vanilla reuse_tree                            */
+    int32_t lanes_per_tree;       /* 0 = auto; else 1,2,4,8,16,32 lanes cooperate on one tree      */
+    /* node initialisers and leaf estimator */
+    double init_Q;
+    int64_t init_N;
+    int32_t estimate_kind;        /* MCTSB200_EST_*                                                */
+    int32_t rollout_policy;       /* MCTSB200_POLICY_*                                             */
+    double estimate_const;
+    int32_t rollout_policy_param[4];
+    int32_t rollout_max_depth;    /* RolloutEstimator.max_depth; -1 = remaining depth              */
+    int32_t reserved0;
+    double rollout_eps;
+    uint64_t seed;                /* Philox key                                                    */
+    /* Optional dense tables (host pointers, may be NULL; only for MDPs with a dense state index):
+     * device-expressible stand-ins for Function-valued hooks. Index = state_index*n_actions + a,
+     * resp. state_index. When non-NULL they override init_Q / init_N / estimate_const. */
+    const double* init_q_table;
+    const int64_t* init_n_table;
+    const double* value_table;    /* used when estimate_kind == MCTSB200_EST_TABLE                 */
+} mctsb200_solver_cfg;
+
+/* Work counters of one plan call (sums over all trees of the call). "Simulation" = one iteration of
+ * src/vanilla.jl:229-235 / src/dpw.jl:48-56; "rollout step" = one iteration of the RolloutSimulator
+ * loop. algorithmic_bytes applies SURVEY.md 8(d): UCT 144 B/level + 112 B/inserted state node;
+ * DPW (144 + 24*C) B/level + 56 B/state node + 72 B/action node. */
+typedef struct {
+    int64_t n_trees;
+    int64_t n_simulations;
+    int64_t n_tree_levels;       /* selection steps (levels that reach best_sanode_UCB)            */
+    int64_t n_dpw_children_seen; /* sum over DPW levels of C = children present at selection       */
+    int64_t n_state_inserts;
+    int64_t n_action_inserts;
+    int64_t n_rollouts;
+    int64_t n_rollout_steps;
+    int64_t n_transition_samples; /* DPW: draws from transitions[sanode] (src/dpw.jl:140)          */
+    int64_t algorithmic_bytes;
+    double kernel_ms;            /* device time of the search kernels (CUDA events)                */
+    double total_ms;             /* host wall time of the call incl. copies                         */
+    int64_t h2d_bytes, d2h_bytes;
+    int32_t lanes_per_tree;      /* the value actually used                                         */
+    int32_t n_kernel_launches;
+    int32_t iterations_done;     /* < n_iterations only when max_time stopped the search           */
+    int32_t reserved0;
+} mctsb200_plan_stats;
+
+typedef struct mctsb200_ctx mctsb200_ctx;
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+int32_t mctsb200_abi_version(void);
+const char* mctsb200_last_error(void);
+/* device_id: CUDA ordinal. stream: a cudaStream_t to launch on (e.g. torch's current stream), or NULL
+ * for a stream owned by the ctx. */
+int32_t mctsb200_ctx_create(int32_t device_id, void* stream, mctsb200_ctx** out);
+int32_t mctsb200_ctx_destroy(mctsb200_ctx* ctx);
+
+/* ---- MDP plugins ------------------------------------------------------------------------------- */
+int32_t mctsb200_mdp_lookup(const char* name, int32_t* mdp_id); /* "SimpleGridWorld", "MountainCar" */
+int32_t mctsb200_mdp_info(int32_t mdp_id, int32_t* n_actions, int64_t* state_bytes);
+int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* pod_params, size_t bytes);
+
+/* ---- planning: replaces build_tree (src/vanilla.jl:209-237) / the DPW loop (src/dpw.jl:29-67) ---- */
+/* Plans for n_roots independent root states (one tree each). roots: n_roots*state_bytes host bytes.
+ * root_index_base: global index of roots[0] -- Philox streams are keyed by global root index so a
+ * sharded run returns the same trees as an unsharded one. Outputs (host): action_idx_out[n_roots]
+ * = index of best_sanode_Q's action, best_q_out[n_roots] = its Q. status_out (may be NULL): per-root
+ * status (MCTSB200_OK / MCTSB200_ERR_TERMINAL_ROOT / MCTSB200_ERR_CAPACITY). Trees stay resident in the ctx until the
+ * next plan call or ctx_destroy. */
+int32_t mctsb200_plan(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* roots,
+                      int64_t n_roots, size_t state_bytes, int64_t root_index_base, int32_t* action_idx_out,
+                      double* best_q_out, int32_t* status_out, mctsb200_plan_stats* stats_out);
+
+/* Same, but roots/action/best_q/status are DEVICE pointers (e.g. torch tensors); nothing is copied and
+ * the call returns after the kernels are enqueued and counters read back. */
+int32_t mctsb200_plan_device(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id,
+                             const void* d_roots, int64_t n_roots, size_t state_bytes, int64_t root_index_base,
+                             int32_t* d_action_idx_out, double* d_best_q_out, int32_t* d_status_out,
+                             mctsb200_plan_stats* stats_out);
+
+/* Root-parallel search of ONE root (BASELINE config 5): n_trees independent trees of the same root
+ * (Philox tree index = tree_index_base + t), n_iterations each. Writes the per-ctx partial sums
+ * sum_n[a] = sum_t N_t(a), sum_nq[a] = sum_t N_t(a)*Q_t(a) (host, n_actions each; summed in fixed
+ * tree order). The host all-reduces them across GPUs (one NCCL allreduce) and calls
+ * mctsb200_root_parallel_decide. d_sums_out: optional DEVICE buffer of 2*n_actions doubles that receives
+ * [sum_n | sum_nq] for an in-place NCCL allreduce. */
+int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id,
+                                    const void* root_state, size_t state_bytes, int64_t n_trees,
+                                    int64_t tree_index_base, double* sum_n_out, double* sum_nq_out,
+                                    double* d_sums_out, mctsb200_plan_stats* stats_out);
+/* Q_a = sum_nq/sum_n (a with sum_n == 0 keeps init_Q); action = first argmax, as best_sanode_Q. */
+int32_t mctsb200_root_parallel_decide(const double* sum_n, const double* sum_nq, int32_t n_actions,
+                                      double init_q, int32_t* action_idx_out, double* best_q_out, double* q_out);
+
+/* ---- tree queries (info[:tree], value(), ranked_actions) ------------------------------------------ */
+/* Children of the root of tree root_i, in child order. Buffers hold >= n_actions entries. */
+int32_t mctsb200_root_stats(mctsb200_ctx* ctx, int64_t root_i, int32_t* n_children, int32_t* action_idx,
+                            int64_t* n, double* q, int64_t* total_n);
+
+typedef struct {
+    int64_t n_state_nodes;
+    int64_t n_action_nodes;
+    int64_t n_transitions;   /* DPW: distinct (sanode, spnode) records; 0 for UCT */
+    int64_t state_bytes;
+} mctsb200_tree_sizes;
+
+/* Caller-allocated arrays sized from mctsb200_tree_sizes (two-call pattern). Field names follow
+ * MCTSTree (src/vanilla.jl:64-94) and DPWTree (src/dpw_types.jl:123-159). Any pointer may be NULL. */
+typedef struct {
+    /* per state node */
+    int64_t* total_n;        /* [n_state_nodes]                                                    */
+    void* s_labels;          /* [n_state_nodes * state_bytes]                                      */
+    int64_t* child_offsets;  /* [n_state_nodes + 1] CSR into child_ids                             */
+    int64_t* child_ids;      /* [n_action_nodes] 1-based action-node ids                           */
+    /* per action node, 1-based id = position + 1 */
+    int64_t* n;              /* [n_action_nodes]                                                   */
+    double* q;               /* [n_action_nodes]                                                   */
+    int32_t* a_labels;       /* [n_action_nodes] action index                                      */
+    /* DPW only */
+    int64_t* n_a_children;   /* [n_action_nodes]                                                   */
+    int64_t* trans_offsets;  /* [n_action_nodes + 1] CSR into the arrays below                     */
+    int64_t* trans_spnode;   /* [n_transitions] 1-based state-node id                              */
+    double* trans_r;         /* [n_transitions]                                                    */
+    int64_t* trans_count;    /* [n_transitions] multiplicity in transitions[sanode]                */
+} mctsb200_tree_buffers;
+
+int32_t mctsb200_tree_sizes_query(mctsb200_ctx* ctx, int64_t root_i, mctsb200_tree_sizes* sizes);
+int32_t mctsb200_tree_export(mctsb200_ctx* ctx, int64_t root_i, const mctsb200_tree_buffers* buffers);
+int32_t mctsb200_clear_trees(mctsb200_ctx* ctx); /* clear_tree! (src/vanilla.jl:148, src/dpw.jl:6-8) */
+
+/* ---- numerical contract helpers (exposed so hosts/tests can check device == host bit-for-bit) ---- */
+/* Evaluates det_log / det_cos (mctsb200_detmath.h) ON THE DEVICE for n host inputs. */
+int32_t mctsb200_device_log(mctsb200_ctx* ctx, const double* x, int64_t n, double* out);
+int32_t mctsb200_device_cos(mctsb200_ctx* ctx, const double* x, int64_t n, double* out);
+/* First 4*n_blocks Philox4x32-10 words of stream (seed, tree, iteration, stream_id), from the device. */
+int32_t mctsb200_device_philox(mctsb200_ctx* ctx, uint64_t seed, uint64_t tree, uint32_t iteration,
+                               uint32_t stream_id, int32_t n_blocks, uint32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+
+/*
+ * Random-number contract (shared by the library and the test oracle; the reference's single
+ * MersenneTwister stream -- src/vanilla.jl:53,141, src/domain_knowledge.jl:53 -- is replaced by
+ * counter-based Philox4x32-10 streams, so stochastic runs compare with Julia only statistically):
+ *   key     = (seed lo32, seed hi32)
+ *   counter = (block, iteration, tree lo32, (tree hi16 << 16) | stream_id)
+ *   stream 0          : tree descent of that iteration (next_action, gen, transition sampling)
+ *   stream 1 + k      : k-th rollout of that iteration (k = 0 for the reference's single rollout)
+ *   words are consumed in order x0,x1,x2,x3 of block 0, then block 1, ...
+ *   uniform_int(n)    = (word * n) >> 32           (rand(rng, 1:n) stand-in)
+ *   uniform01()       = word * 2^-32               (rand(rng) stand-in)
+ */
+#endif /* MCTSB200_H */

@@ -1,0 +1,220 @@
+"""Loader and thin object wrapper for libmctsb200.so (the C ABI of include/mctsb200.h).
+
+There is no CPU fallback: if the CUDA library has not been built, or no B200 is visible, every
+compute entry point raises.  (The CPU-only test-suite links a host emulation of the same sources,
+tests/emu, and hands its path to `load_library` explicitly; nothing in this package looks for it.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from . import _abi as abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(_HERE, "csrc")
+DEFAULT_LIB = os.path.join(CSRC_DIR, "libmctsb200.so")
+
+_lib_cache: dict[str, C.CDLL] = {}
+
+
+class MCTSB200Error(RuntimeError):
+    """Raised for every non-zero status of the C ABI (the Julia glue calls error() the same way)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libmctsb200 [{abi.STATUS_NAMES.get(status, status)}]: {message}")
+        self.status = status
+        self.message = message
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a with nvcc (in-tree, so the .so travels with the repo snapshot)."""
+    cmd = ["make", "-C", CSRC_DIR, "-j", str(os.cpu_count() or 4)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libmctsb200.so failed")
+    return DEFAULT_LIB
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if path in _lib_cache:
+        return _lib_cache[path]
+    if not os.path.exists(path):
+        raise MCTSB200Error(
+            abi.ERR_CUDA,
+            f"{path} not found: the CUDA extension has not been built (run `python __graft_entry__.py` or "
+            f"`make -C {CSRC_DIR}`). There is no CPU fallback.",
+        )
+    lib = abi.declare(C.CDLL(path))
+    got = lib.mctsb200_abi_version()
+    if got != abi.ABI_VERSION:
+        raise MCTSB200Error(abi.ERR_INVALID_ARG, f"ABI version {got} != {abi.ABI_VERSION}")
+    _lib_cache[path] = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One mctsb200_ctx: bound to one CUDA device, not re-entrant (like a reference planner)."""
+
+    def __init__(self, device: int = 0, stream: int = 0, lib_path: Optional[str] = None):
+        self.lib = load_library(lib_path)
+        self._h = C.c_void_p()
+        self._check(self.lib.mctsb200_ctx_create(int(device), C.c_void_p(stream or None), C.byref(self._h)))
+        self.device = int(device)
+        self._configured: dict[int, bytes] = {}
+
+    # -- plumbing --
+    def _check(self, status: int) -> None:
+        if status != abi.OK:
+            raise MCTSB200Error(status, self.lib.mctsb200_last_error().decode("utf-8", "replace"))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.mctsb200_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- MDP plugins --
+    def mdp_lookup(self, name: str) -> int:
+        out = C.c_int32()
+        self._check(self.lib.mctsb200_mdp_lookup(name.encode(), C.byref(out)))
+        return out.value
+
+    def mdp_info(self, mdp_id: int) -> tuple[int, int]:
+        na, sb = C.c_int32(), C.c_int64()
+        self._check(self.lib.mctsb200_mdp_info(mdp_id, C.byref(na), C.byref(sb)))
+        return na.value, sb.value
+
+    def configure(self, mdp_id: int, params: C.Structure) -> None:
+        raw = bytes(params)
+        if self._configured.get(mdp_id) == raw:
+            return
+        self._check(self.lib.mctsb200_mdp_configure(self._h, mdp_id, C.byref(params), C.sizeof(params)))
+        self._configured[mdp_id] = raw
+
+    # -- planning --
+    def plan(self, cfg: abi.SolverCfg, mdp_id: int, roots: np.ndarray, root_index_base: int = 0,
+             want_status: bool = False):
+        """roots: C-contiguous array whose rows are statetype(mdp) values. Returns (actions, best_q, status, stats).
+        With want_status=False a terminal DPW root raises (like src/dpw.jl:22-27); with True it is reported per root."""
+        roots = np.ascontiguousarray(roots)
+        n = roots.shape[0]
+        state_bytes = roots.dtype.itemsize * int(np.prod(roots.shape[1:], dtype=np.int64)) if n else 0
+        actions = np.empty(n, dtype=np.int32)
+        best_q = np.empty(n, dtype=np.float64)
+        status = np.zeros(n, dtype=np.int32) if want_status else None
+        stats = abi.PlanStats()
+        self._check(self.lib.mctsb200_plan(self._h, C.byref(cfg), mdp_id, _ptr(roots), n, state_bytes, int(root_index_base),
+                                           _ptr(actions), _ptr(best_q), _ptr(status), C.byref(stats)))
+        return actions, best_q, status, stats
+
+    def plan_device(self, cfg: abi.SolverCfg, mdp_id: int, d_roots: int, n_roots: int, state_bytes: int,
+                    d_actions: int, d_best_q: int, d_status: int = 0, root_index_base: int = 0) -> abi.PlanStats:
+        """Device-pointer variant (e.g. torch tensors' data_ptr())."""
+        stats = abi.PlanStats()
+        self._check(self.lib.mctsb200_plan_device(self._h, C.byref(cfg), mdp_id, C.c_void_p(d_roots), int(n_roots), int(state_bytes),
+                                                  int(root_index_base), C.c_void_p(d_actions or None), C.c_void_p(d_best_q or None),
+                                                  C.c_void_p(d_status or None), C.byref(stats)))
+        return stats
+
+    def plan_root_parallel(self, cfg: abi.SolverCfg, mdp_id: int, root: np.ndarray, n_trees: int, tree_index_base: int = 0,
+                           d_sums: int = 0):
+        root = np.ascontiguousarray(root)
+        na, _ = self.mdp_info(mdp_id)
+        sum_n = np.zeros(na, dtype=np.float64)
+        sum_nq = np.zeros(na, dtype=np.float64)
+        stats = abi.PlanStats()
+        self._check(self.lib.mctsb200_plan_root_parallel(self._h, C.byref(cfg), mdp_id, _ptr(root), root.nbytes, int(n_trees),
+                                                         int(tree_index_base), _ptr(sum_n), _ptr(sum_nq), C.c_void_p(d_sums or None),
+                                                         C.byref(stats)))
+        return sum_n, sum_nq, stats
+
+    def root_parallel_decide(self, sum_n: np.ndarray, sum_nq: np.ndarray, init_q: float = 0.0):
+        sum_n = np.ascontiguousarray(sum_n, dtype=np.float64)
+        sum_nq = np.ascontiguousarray(sum_nq, dtype=np.float64)
+        q = np.zeros_like(sum_n)
+        a, bq = C.c_int32(), C.c_double()
+        self._check(self.lib.mctsb200_root_parallel_decide(_ptr(sum_n), _ptr(sum_nq), len(sum_n), float(init_q), C.byref(a), C.byref(bq), _ptr(q)))
+        return a.value, bq.value, q
+
+    # -- tree queries --
+    def root_stats(self, root_i: int, n_actions: int = 16) -> dict:
+        nch, tot = C.c_int32(), C.c_int64()
+        act = np.zeros(n_actions, dtype=np.int32)
+        n = np.zeros(n_actions, dtype=np.int64)
+        q = np.zeros(n_actions, dtype=np.float64)
+        self._check(self.lib.mctsb200_root_stats(self._h, int(root_i), C.byref(nch), _ptr(act), _ptr(n), _ptr(q), C.byref(tot)))
+        k = nch.value
+        return {"action_idx": act[:k].copy(), "n": n[:k].copy(), "q": q[:k].copy(), "total_n": tot.value}
+
+    def tree_export(self, root_i: int, state_dtype=np.int64, state_width: int = 2) -> dict:
+        """Two-call export into numpy arrays named after MCTSTree / DPWTree fields (ids are 1-based)."""
+        sz = abi.TreeSizes()
+        self._check(self.lib.mctsb200_tree_sizes_query(self._h, int(root_i), C.byref(sz)))
+        return export_into_numpy(lambda b: self._check(self.lib.mctsb200_tree_export(self._h, int(root_i), C.byref(b))), sz,
+                                 state_dtype, state_width)
+
+    def clear_trees(self) -> None:
+        self._check(self.lib.mctsb200_clear_trees(self._h))
+
+    # -- numerical-contract probes --
+    def device_log(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        self._check(self.lib.mctsb200_device_log(self._h, _ptr(x), x.size, _ptr(out)))
+        return out
+
+    def device_cos(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        self._check(self.lib.mctsb200_device_cos(self._h, _ptr(x), x.size, _ptr(out)))
+        return out
+
+    def device_philox(self, seed: int, tree: int, iteration: int, stream_id: int, n_blocks: int) -> np.ndarray:
+        out = np.empty(4 * n_blocks, dtype=np.uint32)
+        self._check(self.lib.mctsb200_device_philox(self._h, seed, tree, iteration, stream_id, n_blocks, _ptr(out)))
+        return out
+
+
+def export_into_numpy(call, sz: abi.TreeSizes, state_dtype, state_width: int) -> dict:
+    ns, na, nt = sz.n_state_nodes, sz.n_action_nodes, sz.n_transitions
+    t = {
+        "total_n": np.zeros(ns, dtype=np.int64),
+        "s_labels": np.zeros((ns, state_width), dtype=state_dtype),
+        "child_offsets": np.zeros(ns + 1, dtype=np.int64),
+        "child_ids": np.zeros(na, dtype=np.int64),
+        "n": np.zeros(na, dtype=np.int64),
+        "q": np.zeros(na, dtype=np.float64),
+        "a_labels": np.zeros(na, dtype=np.int32),
+        "n_a_children": np.zeros(na, dtype=np.int64),
+        "trans_offsets": np.zeros(na + 1, dtype=np.int64),
+        "trans_spnode": np.zeros(nt, dtype=np.int64),
+        "trans_r": np.zeros(nt, dtype=np.float64),
+        "trans_count": np.zeros(nt, dtype=np.int64),
+    }
+    b = abi.TreeBuffers(**{k: v.ctypes.data for k, v in t.items()})
+    call(b)
+    return t

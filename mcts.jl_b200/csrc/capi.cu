@@ -1,0 +1,961 @@
+// capi.cu -- host side of libmctsb200.so: the C ABI of include/mctsb200.h.
+//
+// Owns device memory (node tables, lookup tables, counters), validates solver options the way the Julia
+// glue needs them (unsupported -> error, never a CPU fallback), sizes the per-tree tables, picks the tile
+// width, launches the search kernels (search.cuh) in iteration chunks (max_time), runs the root
+// decision kernel and exports trees in the reference's MCTSTree / DPWTree vector layout.
+#ifndef MCTSB200_HOST_EMU
+#include <cuda_runtime.h>
+#endif
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "search.cuh"
+
+using namespace mctsb200;
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) return fail(MCTSB200_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));  \
+    } while (0)
+
+// device buffer that only grows
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Storage {
+    bool valid = false;
+    int kind = 0, mdp_id = 0;
+    long long n_trees = 0;
+    Geometry geo{};
+    size_t row_bytes = 0, aux_bytes = 0, map_entry_bytes = 0;
+    DevBuf hdr, rows, aux, trans, map, path;
+};
+
+}  // namespace
+
+struct mctsb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    bool gw_ok = false, mc_ok = false;
+    mctsb200_gridworld_params gw_host{};
+    GridWorldDev::Params gw_dev{};
+    DevBuf gw_reward, gw_term;
+    MountainCarDev::Params mc_dev{};
+
+    Storage st;
+    DevBuf counters, log_tab, nmin_state, init_q, init_n, value_tab, io_roots, io_action, io_bestq, io_status, sums;
+    int log_tab_n = 0;
+};
+
+namespace {
+
+template <class M>
+struct MdpAccess;
+template <>
+struct MdpAccess<GridWorldDev> {
+    static bool ready(const mctsb200_ctx* c) { return c->gw_ok; }
+    static const GridWorldDev::Params& params(const mctsb200_ctx* c) { return c->gw_dev; }
+    static int dense_count(const mctsb200_ctx* c) { return c->gw_dev.nx * c->gw_dev.ny + 1; }
+    static int32_t check_root(const mctsb200_ctx* c, const GridWorldDev::AbiState& s) {
+        const bool inb = s.x >= 1 && s.x <= c->gw_dev.nx && s.y >= 1 && s.y <= c->gw_dev.ny;
+        const bool term = s.x == -1 && s.y == -1;
+        return (inb || term) ? 0 : -1;
+    }
+    static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_GW_SEEK; }
+};
+template <>
+struct MdpAccess<MountainCarDev> {
+    static bool ready(const mctsb200_ctx* c) { return c->mc_ok; }
+    static const MountainCarDev::Params& params(const mctsb200_ctx* c) { return c->mc_dev; }
+    static int dense_count(const mctsb200_ctx*) { return 0; }
+    static int32_t check_root(const mctsb200_ctx*, const MountainCarDev::AbiState& s) {
+        return (std::isfinite(s.x) && std::isfinite(s.v) && std::fabs(s.x) < 1e5) ? 0 : -1;
+    }
+    static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_MC_ENERGY; }
+};
+
+// min N in [0, bound] with  len <= k * N^alpha  (the reference's widening test, src/dpw.jl:95,121,
+// evaluated with the host's pow exactly as written there); INT_MAX if none.
+int nmin_for(double k, double alpha, int len, long long bound) {
+    auto pred = [&](long long N) { return (double)len <= k * std::pow((double)N, alpha); };
+    if (pred(0)) return 0;
+    if (!pred(bound)) return 0x7fffffff;
+    long long lo = 0, hi = bound;  // pred(lo) false, pred(hi) true; pow is monotone in N for alpha >= 0
+    while (hi - lo > 1) {
+        const long long mid = lo + (hi - lo) / 2;
+        if (pred(mid)) hi = mid;
+        else lo = mid;
+    }
+    while (hi > 1 && pred(hi - 1)) --hi;  // guard against a non-monotone last ulp
+    return (int)hi;
+}
+
+int next_pow2(long long v) {
+    long long p = 1;
+    while (p < v) p <<= 1;
+    return (int)p;
+}
+
+int32_t validate_cfg(const mctsb200_solver_cfg* cfg, int n_actions, bool dense, bool (*policy_ok)(int)) {
+    if (!cfg) return fail(MCTSB200_ERR_INVALID_ARG, "cfg is NULL");
+    if (cfg->struct_size != (int32_t)sizeof(mctsb200_solver_cfg))
+        return fail(MCTSB200_ERR_INVALID_ARG, "solver_cfg.struct_size %d != %zu (ABI mismatch)", cfg->struct_size, sizeof(mctsb200_solver_cfg));
+    if (cfg->kind != MCTSB200_KIND_UCT && cfg->kind != MCTSB200_KIND_DPW) return fail(MCTSB200_ERR_INVALID_ARG, "unknown solver kind %d", cfg->kind);
+    if (cfg->n_iterations < 0 || cfg->n_iterations > 2000000000LL) return fail(MCTSB200_ERR_INVALID_ARG, "n_iterations out of range");
+    if (cfg->depth < 0 || cfg->depth > 100000) return fail(MCTSB200_ERR_INVALID_ARG, "depth out of range");
+    if ((double)cfg->n_iterations * (double)std::max(cfg->depth, 1) > 2.0e9)
+        return fail(MCTSB200_ERR_CAPACITY, "n_iterations*depth exceeds the 32-bit visit counters");
+    if (!(cfg->exploration_constant >= 0.0) || !std::isfinite(cfg->exploration_constant))
+        return fail(MCTSB200_ERR_INVALID_ARG, "exploration_constant must be finite and >= 0");
+    if (cfg->rollouts_per_leaf < 1 || cfg->rollouts_per_leaf > 1024) return fail(MCTSB200_ERR_INVALID_ARG, "rollouts_per_leaf must be in [1,1024]");
+    const int g = cfg->lanes_per_tree;
+    if (!(g == 0 || g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32)) return fail(MCTSB200_ERR_INVALID_ARG, "lanes_per_tree must be 0,1,2,4,8,16,32");
+    if (cfg->init_N < 0 || cfg->init_N > 1000000000LL) return fail(MCTSB200_ERR_INVALID_ARG, "init_N out of range");
+    if (std::isnan(cfg->max_time) || cfg->max_time < 0) return fail(MCTSB200_ERR_INVALID_ARG, "max_time must be >= 0");
+    if (cfg->estimate_kind < MCTSB200_EST_ROLLOUT || cfg->estimate_kind > MCTSB200_EST_TABLE) return fail(MCTSB200_ERR_INVALID_ARG, "unknown estimate_kind");
+    if (cfg->estimate_kind == MCTSB200_EST_TABLE && (!dense || !cfg->value_table))
+        return fail(MCTSB200_ERR_UNSUPPORTED, "table-valued estimate_value needs a dense-state MDP and a value_table");
+    if ((cfg->init_q_table || cfg->init_n_table) && !dense) return fail(MCTSB200_ERR_UNSUPPORTED, "init tables need a dense-state MDP");
+    if (cfg->estimate_kind == MCTSB200_EST_ROLLOUT) {
+        if (!policy_ok(cfg->rollout_policy)) return fail(MCTSB200_ERR_UNSUPPORTED, "rollout policy %d is not available for this MDP", cfg->rollout_policy);
+        if (cfg->rollout_policy == MCTSB200_POLICY_CONSTANT && (cfg->rollout_policy_param[0] < 0 || cfg->rollout_policy_param[0] >= n_actions))
+            return fail(MCTSB200_ERR_INVALID_ARG, "constant rollout action out of range");
+        if (cfg->rollout_max_depth < -1) return fail(MCTSB200_ERR_INVALID_ARG, "rollout max_depth must be >= -1");
+        if (std::isnan(cfg->rollout_eps)) return fail(MCTSB200_ERR_INVALID_ARG, "rollout eps is NaN");
+    }
+    if (cfg->kind == MCTSB200_KIND_DPW) {
+        const double v[4] = {cfg->k_action, cfg->alpha_action, cfg->k_state, cfg->alpha_state};
+        for (double x : v)
+            if (!(x >= 0.0) || !std::isfinite(x)) return fail(MCTSB200_ERR_UNSUPPORTED, "DPW k/alpha must be finite and >= 0");
+        if (cfg->enable_action_pw && !cfg->check_repeat_action)
+            return fail(MCTSB200_ERR_UNSUPPORTED, "action widening with check_repeat_action=false (duplicate action nodes) is not supported on the device");
+    }
+    return MCTSB200_OK;
+}
+
+template <class M>
+int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_trees) {
+    constexpr int A = M::kActions;
+    const bool dpw = cfg->kind == MCTSB200_KIND_DPW;
+    const long long n_iter = cfg->n_iterations;
+    const int dense = MdpAccess<M>::dense_count(ctx);
+    const bool merge_states = !dpw || cfg->check_repeat_state;
+    long long NS = n_iter + 1;
+    if (M::kDense && merge_states) NS = std::min<long long>(NS, dense);
+    const bool maintain_lookup = !dpw || cfg->keep_tree || cfg->check_repeat_state;
+    if (M::kDense && maintain_lookup && NS > 65535) return fail(MCTSB200_ERR_CAPACITY, "dense state map limited to 65535 nodes per tree");
+    long long NT = 0;
+    if (dpw) {
+        const long long by_iter = std::max<long long>(1, n_iter * std::max(cfg->depth, 1));
+        const long long by_pairs = NS * A * std::min<long long>(M::kMaxBranch, NS);
+        NT = cfg->check_repeat_state ? std::min(by_iter, by_pairs) : std::max<long long>(1, n_iter);
+    }
+    long long MAP = 0;
+    size_t map_entry = 0;
+    if (M::kDense) {
+        MAP = (dense + 63) / 64 * 64;
+        map_entry = sizeof(uint16_t);
+    } else {
+        MAP = next_pow2(2 * NS);
+        map_entry = sizeof(HashSlot);
+    }
+    Geometry g;
+    g.NS = (int)NS;
+    g.NT = (int)std::max<long long>(NT, 1);
+    g.MAP = (int)MAP;
+    g.depth = std::max(cfg->depth, 1);
+
+    const size_t b_hdr = sizeof(TreeHeader) * (size_t)n_trees;
+    const size_t b_rows = sizeof(Row<M>) * (size_t)NS * (size_t)n_trees;
+    const size_t b_aux = dpw ? sizeof(Aux<M>) * (size_t)NS * (size_t)n_trees : 0;
+    const size_t b_trans = dpw ? sizeof(TransRec) * (size_t)g.NT * (size_t)n_trees : 0;
+    const size_t b_map = map_entry * (size_t)MAP * (size_t)n_trees;
+    const size_t b_path = sizeof(PathEntry) * (size_t)g.depth * (size_t)n_trees;
+    const size_t total = b_hdr + b_rows + b_aux + b_trans + b_map + b_path;
+
+    Storage& st = ctx->st;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t have = st.hdr.cap + st.rows.cap + st.aux.cap + st.trans.cap + st.map.cap + st.path.cap;
+    if (total > free_b + have)
+        return fail(MCTSB200_ERR_CAPACITY, "node tables need %.2f GB but only %.2f GB of HBM are free; plan fewer roots per call", total / 1e9,
+                    (free_b + have) / 1e9);
+    st.valid = false;
+    CUDA_TRY(st.hdr.ensure(b_hdr));
+    CUDA_TRY(st.rows.ensure(b_rows));
+    CUDA_TRY(st.aux.ensure(b_aux));
+    CUDA_TRY(st.trans.ensure(b_trans));
+    CUDA_TRY(st.map.ensure(b_map));
+    CUDA_TRY(st.path.ensure(b_path));
+    st.kind = cfg->kind;
+    st.mdp_id = M::kMdpId;
+    st.n_trees = n_trees;
+    st.geo = g;
+    st.row_bytes = sizeof(Row<M>);
+    st.aux_bytes = sizeof(Aux<M>);
+    st.map_entry_bytes = map_entry;
+    CUDA_TRY(cudaMemsetAsync(st.hdr.p, 0, b_hdr, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(st.map.p, 0, b_map, ctx->stream));
+    return MCTSB200_OK;
+}
+
+template <class M>
+int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg& d) {
+    constexpr int A = M::kActions;
+    std::memset(&d, 0, sizeof d);
+    d.n_iterations = cfg->n_iterations;
+    d.c = cfg->exploration_constant;
+    d.init_Q = cfg->init_Q;
+    d.estimate_const = cfg->estimate_const;
+    d.rollout_eps = cfg->rollout_eps;
+    d.seed = cfg->seed;
+    d.depth = cfg->depth;
+    d.K = cfg->rollouts_per_leaf;
+    d.init_N = (int)cfg->init_N;
+    d.estimate_kind = cfg->estimate_kind;
+    d.policy = cfg->rollout_policy;
+    for (int i = 0; i < 4; ++i) d.pparam[i] = cfg->rollout_policy_param[i];
+    d.rollout_max_depth = cfg->rollout_max_depth;
+    d.enable_action_pw = cfg->enable_action_pw;
+    d.enable_state_pw = cfg->enable_state_pw;
+    d.check_repeat_state = cfg->check_repeat_state;
+    d.maintain_lookup = (cfg->keep_tree || cfg->check_repeat_state) ? 1 : 0;
+
+    long long max_init_n = cfg->init_N;
+    const int dense = MdpAccess<M>::dense_count(ctx);
+    if (cfg->init_q_table) {
+        const size_t bytes = sizeof(double) * (size_t)dense * A;
+        CUDA_TRY(ctx->init_q.ensure(bytes));
+        CUDA_TRY(cudaMemcpyAsync(ctx->init_q.p, cfg->init_q_table, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d.init_q_table = (const double*)ctx->init_q.p;
+    }
+    if (cfg->init_n_table) {
+        std::vector<int> tmp((size_t)dense * A);
+        max_init_n = 0;
+        for (size_t i = 0; i < tmp.size(); ++i) {
+            const int64_t v = cfg->init_n_table[i];
+            if (v < 0 || v > 1000000000LL) return fail(MCTSB200_ERR_INVALID_ARG, "init_n_table entry out of range");
+            tmp[i] = (int)v;
+            max_init_n = std::max<long long>(max_init_n, v);
+        }
+        CUDA_TRY(ctx->init_n.ensure(tmp.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(ctx->init_n.p, tmp.data(), tmp.size() * sizeof(int), cudaMemcpyHostToDevice));
+        d.init_n_table = (const int*)ctx->init_n.p;
+    }
+    if (cfg->value_table && cfg->estimate_kind == MCTSB200_EST_TABLE) {
+        const size_t bytes = sizeof(double) * (size_t)dense;
+        CUDA_TRY(ctx->value_tab.ensure(bytes));
+        CUDA_TRY(cudaMemcpyAsync(ctx->value_tab.p, cfg->value_table, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d.value_table = (const double*)ctx->value_tab.p;
+    }
+
+    // visit-count bound: every backup adds one visit; at most depth backups per simulation
+    const long long bound = std::min<long long>(2000000000LL, max_init_n * A + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1);
+    if (max_init_n * A + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1 > 2000000000LL)
+        return fail(MCTSB200_ERR_CAPACITY, "visit counts may exceed 32 bits");
+
+    // log table: det_log(N), N < log_tab_n (grown lazily, shared by all configurations)
+    const int want = (int)std::min<long long>(bound + 1, 1 << 20);
+    if (want > ctx->log_tab_n) {
+        std::vector<double> tab((size_t)want);
+        for (int i = 0; i < want; ++i) tab[(size_t)i] = det_log((double)i);
+        CUDA_TRY(ctx->log_tab.ensure(sizeof(double) * (size_t)want));
+        CUDA_TRY(cudaMemcpy(ctx->log_tab.p, tab.data(), sizeof(double) * (size_t)want, cudaMemcpyHostToDevice));
+        ctx->log_tab_n = want;
+    }
+    d.log_tab = (const double*)ctx->log_tab.p;
+    d.log_tab_n = ctx->log_tab_n;
+
+    if (cfg->kind == MCTSB200_KIND_DPW) {
+        for (int len = 0; len < 16; ++len) d.nmin_action[len] = len <= A ? nmin_for(cfg->k_action, cfg->alpha_action, len, bound) : 0x7fffffff;
+        std::vector<int> ns;
+        const long long max_len = cfg->check_repeat_state ? (long long)M::kMaxBranch : std::min<long long>(cfg->n_iterations + 1, (1 << 20) - 2);
+        for (long long len = 0; len <= max_len; ++len) {
+            const int v = nmin_for(cfg->k_state, cfg->alpha_state, (int)len, bound);
+            ns.push_back(v);
+            if (v == 0x7fffffff) break;
+        }
+        if (!cfg->check_repeat_state && ns.back() != 0x7fffffff && (long long)ns.size() - 1 < cfg->n_iterations + 1)
+            return fail(MCTSB200_ERR_UNSUPPORTED, "state-widening table would exceed 2^20 entries");
+        CUDA_TRY(ctx->nmin_state.ensure(ns.size() * sizeof(int)));
+        CUDA_TRY(cudaMemcpy(ctx->nmin_state.p, ns.data(), ns.size() * sizeof(int), cudaMemcpyHostToDevice));
+        d.nmin_state = (const int*)ctx->nmin_state.p;
+        d.nmin_state_n = (int)ns.size();
+    }
+    return MCTSB200_OK;
+}
+
+template <class M, int KIND>
+int pick_lanes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_trees) {
+#ifdef MCTSB200_HOST_EMU
+    return 1;  // the host emulator runs one lane at a time
+#endif
+    if (cfg->lanes_per_tree) return cfg->lanes_per_tree;
+    // widest tile that still lets every tree be resident at once (one wave)
+    int best = 1;
+    for (int G = 2; G <= 32; G *= 2) {
+        const long long resident = (long long)search_occupancy<M, KIND>(G) * kBlockThreads * ctx->sm_count;
+        if (n_trees * G <= resident) best = G;
+    }
+    // a tile wider than the work it can share only idles lanes
+    const int useful = std::max(next_pow2(M::kActions), next_pow2(cfg->rollouts_per_leaf));
+    return std::min(best, std::min(32, useful));
+}
+
+void fill_stats(mctsb200_plan_stats* s, const mctsb200_solver_cfg* cfg, const unsigned long long* c, int n_actions) {
+    s->n_simulations = (int64_t)c[CNT_SIMULATIONS];
+    s->n_tree_levels = (int64_t)c[CNT_LEVELS];
+    s->n_dpw_children_seen = (int64_t)c[CNT_CHILDREN_SEEN];
+    s->n_state_inserts = (int64_t)c[CNT_STATE_INSERTS];
+    s->n_action_inserts = (int64_t)c[CNT_ACTION_INSERTS];
+    s->n_rollouts = (int64_t)c[CNT_ROLLOUTS];
+    s->n_rollout_steps = (int64_t)c[CNT_ROLLOUT_STEPS];
+    s->n_transition_samples = (int64_t)c[CNT_TRANS_SAMPLES];
+    if (cfg->kind == MCTSB200_KIND_UCT)
+        s->algorithmic_bytes = (80 + 16 * (int64_t)n_actions) * s->n_tree_levels + (48 + 16 * (int64_t)n_actions) * s->n_state_inserts;
+    else
+        s->algorithmic_bytes = 144 * s->n_tree_levels + 24 * s->n_dpw_children_seen + 56 * s->n_state_inserts + 72 * s->n_action_inserts;
+}
+
+// Runs the search for trees whose roots are already on the device. d_* outputs may be null.
+template <class M, int KIND>
+int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const typename M::AbiState* d_roots, long long n_trees,
+                   long long root_stride, long long tree_index_base, int* d_action, double* d_bestq, int* d_status,
+                   mctsb200_plan_stats* stats) {
+    DevCfg dcfg;
+    int32_t rc = build_dev_cfg<M>(ctx, cfg, dcfg);
+    if (rc) return rc;
+    rc = setup_storage<M>(ctx, cfg, n_trees);
+    if (rc) return rc;
+    Storage& st = ctx->st;
+    CUDA_TRY(ctx->counters.ensure(sizeof(unsigned long long) * CNT_COUNT));
+    CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * CNT_COUNT, ctx->stream));
+
+    KernelArgs<M> args;
+    std::memset(&args, 0, sizeof args);
+    args.mdp = MdpAccess<M>::params(ctx);
+    args.cfg = dcfg;
+    args.geo = st.geo;
+    args.hdr = (TreeHeader*)st.hdr.p;
+    args.rows = (Row<M>*)st.rows.p;
+    args.aux = KIND == MCTSB200_KIND_DPW ? (Aux<M>*)st.aux.p : nullptr;
+    args.trans = KIND == MCTSB200_KIND_DPW ? (TransRec*)st.trans.p : nullptr;
+    args.map = st.map.p;
+    args.path = (PathEntry*)st.path.p;
+    args.roots = d_roots;
+    args.counters = (unsigned long long*)ctx->counters.p;
+    args.n_trees = n_trees;
+    args.tree_index_base = tree_index_base;
+    args.root_stride = root_stride;
+
+    const int G = pick_lanes<M, KIND>(ctx, cfg, n_trees);
+    const int n_iter = (int)cfg->n_iterations;
+    int launches = 0, done = 0;
+    float kernel_ms = 0.f;
+    const auto t_start = std::chrono::steady_clock::now();
+    if (!std::isfinite(cfg->max_time)) {
+        args.iter_begin = 0;
+        args.iter_end = n_iter;
+        CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+        launch_search<M, KIND>(args, G, ctx->stream);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        launches = 1;
+        done = n_iter;
+    } else {
+        // max_time (src/vanilla.jl:232, src/dpw.jl:52): the timer is read after each chunk of iterations;
+        // at least one iteration always runs. Chunks grow until one takes ~1/16 of the budget.
+        int chunk = 1;
+        CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+        while (done < n_iter || (n_iter == 0 && launches == 0)) {
+            args.iter_begin = done;
+            args.iter_end = std::min(n_iter, done + chunk);
+            const auto c0 = std::chrono::steady_clock::now();
+            launch_search<M, KIND>(args, G, ctx->stream);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            ++launches;
+            done = args.iter_end;
+            const auto now = std::chrono::steady_clock::now();
+            const double elapsed = std::chrono::duration<double>(now - t_start).count();
+            if (elapsed >= cfg->max_time || n_iter == 0) break;
+            const double chunk_s = std::chrono::duration<double>(now - c0).count();
+            if (chunk_s < cfg->max_time / 16.0) chunk = std::min(chunk * 2, 1 << 20);
+            const double per_iter = chunk_s / (double)(args.iter_end - args.iter_begin);
+            const double left = cfg->max_time - elapsed;
+            if (per_iter > 0 && chunk * per_iter > left) chunk = std::max(1, (int)(left / per_iter));
+        }
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    }
+    {
+        const unsigned grid = (unsigned)((n_trees + 127) / 128);
+        auto kernel = decide_kernel<M>;
+        MCTSB200_LAUNCH(kernel, grid, 128, ctx->stream, (const TreeHeader*)st.hdr.p, (const Row<M>*)st.rows.p, st.geo.NS, n_trees, d_action, d_bestq,
+                        d_status);
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+    }
+    unsigned long long h_cnt[CNT_COUNT];
+    CUDA_TRY(cudaMemcpyAsync(h_cnt, ctx->counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaEventElapsedTime(&kernel_ms, ctx->ev0, ctx->ev1));
+    st.valid = true;
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        stats->n_trees = n_trees;
+        fill_stats(stats, cfg, h_cnt, M::kActions);
+        stats->kernel_ms = kernel_ms;
+        stats->lanes_per_tree = G;
+        stats->n_kernel_launches = launches;
+        stats->iterations_done = done;
+    }
+    return MCTSB200_OK;
+}
+
+template <class M>
+int32_t plan_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const void* roots, bool roots_on_device, long long n_roots,
+                      size_t state_bytes, long long base, int* action_out, double* bestq_out, int* status_out, bool out_on_device,
+                      mctsb200_plan_stats* stats) {
+    using Abi = typename M::AbiState;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
+    int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok);
+    if (rc) return rc;
+    if (state_bytes != sizeof(Abi)) return fail(MCTSB200_ERR_INVALID_ARG, "state_bytes %zu != %zu", state_bytes, sizeof(Abi));
+    if (n_roots <= 0 || !roots) return fail(MCTSB200_ERR_INVALID_ARG, "need at least one root state");
+    if (base < 0) return fail(MCTSB200_ERR_INVALID_ARG, "root_index_base must be >= 0");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+
+    const Abi* d_roots = nullptr;
+    int64_t h2d = 0, d2h = 0;
+    if (roots_on_device) {
+        d_roots = (const Abi*)roots;
+    } else {
+        const Abi* h = (const Abi*)roots;
+        for (long long i = 0; i < n_roots; ++i)
+            if (MdpAccess<M>::check_root(ctx, h[i])) return fail(MCTSB200_ERR_INVALID_ARG, "root state %lld is not a valid state of this MDP", i);
+        CUDA_TRY(ctx->io_roots.ensure(sizeof(Abi) * (size_t)n_roots));
+        CUDA_TRY(cudaMemcpyAsync(ctx->io_roots.p, roots, sizeof(Abi) * (size_t)n_roots, cudaMemcpyHostToDevice, ctx->stream));
+        h2d += (int64_t)(sizeof(Abi) * (size_t)n_roots);
+        d_roots = (const Abi*)ctx->io_roots.p;
+    }
+    int* d_action = action_out;
+    double* d_bestq = bestq_out;
+    int* d_status = status_out;
+    if (!out_on_device) {
+        CUDA_TRY(ctx->io_action.ensure(sizeof(int) * (size_t)n_roots));
+        CUDA_TRY(ctx->io_bestq.ensure(sizeof(double) * (size_t)n_roots));
+        CUDA_TRY(ctx->io_status.ensure(sizeof(int) * (size_t)n_roots));
+        d_action = (int*)ctx->io_action.p;
+        d_bestq = (double*)ctx->io_bestq.p;
+        d_status = (int*)ctx->io_status.p;
+    }
+    if (cfg->kind == MCTSB200_KIND_UCT) rc = run_search<M, MCTSB200_KIND_UCT>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats);
+    else rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats);
+    if (rc) return rc;
+    int32_t worst = MCTSB200_OK;
+    if (!out_on_device) {
+        std::vector<int> h_status((size_t)n_roots);
+        if (action_out) CUDA_TRY(cudaMemcpyAsync(action_out, d_action, sizeof(int) * (size_t)n_roots, cudaMemcpyDeviceToHost, ctx->stream));
+        if (bestq_out) CUDA_TRY(cudaMemcpyAsync(bestq_out, d_bestq, sizeof(double) * (size_t)n_roots, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * (size_t)n_roots, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        d2h += (int64_t)((action_out ? sizeof(int) : 0) + (bestq_out ? sizeof(double) : 0) + sizeof(int)) * n_roots;
+        for (long long i = 0; i < n_roots; ++i) {
+            if (status_out) status_out[i] = h_status[(size_t)i];
+            if (h_status[(size_t)i] != MCTSB200_OK && worst == MCTSB200_OK) worst = h_status[(size_t)i];
+        }
+    }
+    if (stats) {
+        stats->h2d_bytes = h2d;
+        stats->d2h_bytes = d2h;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (worst == MCTSB200_ERR_TERMINAL_ROOT && !status_out)
+        return fail(worst, "MCTS cannot handle terminal states: a root state is terminal (src/dpw.jl:22-27)");
+    if (worst == MCTSB200_ERR_CAPACITY) return fail(worst, "a per-tree table overflowed");
+    return MCTSB200_OK;
+}
+
+template <class M>
+int32_t root_parallel_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const void* root_state, size_t state_bytes,
+                               long long n_trees, long long base, double* sum_n_out, double* sum_nq_out, double* d_sums_out,
+                               mctsb200_plan_stats* stats) {
+    using Abi = typename M::AbiState;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
+    int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok);
+    if (rc) return rc;
+    if (state_bytes != sizeof(Abi) || !root_state || n_trees <= 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad root_parallel arguments");
+    if (MdpAccess<M>::check_root(ctx, *(const Abi*)root_state)) return fail(MCTSB200_ERR_INVALID_ARG, "root state is not a valid state of this MDP");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx->io_roots.ensure(sizeof(Abi)));
+    CUDA_TRY(cudaMemcpyAsync(ctx->io_roots.p, root_state, sizeof(Abi), cudaMemcpyHostToDevice, ctx->stream));
+    if (cfg->kind == MCTSB200_KIND_UCT)
+        rc = run_search<M, MCTSB200_KIND_UCT>(ctx, cfg, (const Abi*)ctx->io_roots.p, n_trees, 0, base, nullptr, nullptr, nullptr, stats);
+    else
+        rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, (const Abi*)ctx->io_roots.p, n_trees, 0, base, nullptr, nullptr, nullptr, stats);
+    if (rc) return rc;
+    double* d_sums = d_sums_out;
+    if (!d_sums) {
+        CUDA_TRY(ctx->sums.ensure(sizeof(double) * 2 * M::kActions));
+        d_sums = (double*)ctx->sums.p;
+    }
+    auto kernel = root_sums_kernel<M>;
+    MCTSB200_LAUNCH(kernel, 1, 32, ctx->stream, (const TreeHeader*)ctx->st.hdr.p, (const Row<M>*)ctx->st.rows.p, ctx->st.geo.NS, n_trees, d_sums);
+    CUDA_TRY(cudaGetLastError());
+    double h[2 * M::kActions];
+    CUDA_TRY(cudaMemcpyAsync(h, d_sums, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < M::kActions; ++i) {
+        if (sum_n_out) sum_n_out[i] = h[i];
+        if (sum_nq_out) sum_nq_out[i] = h[M::kActions + i];
+    }
+    if (stats) {
+        stats->n_kernel_launches += 1;
+        stats->h2d_bytes = sizeof(Abi);
+        stats->d2h_bytes = sizeof h;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return MCTSB200_OK;
+}
+
+// ---- tree export --------------------------------------------------------------------------------
+template <class M>
+struct HostTree {
+    TreeHeader h;
+    std::vector<Row<M>> rows;
+    std::vector<Aux<M>> aux;
+    std::vector<TransRec> trans;
+};
+
+template <class M>
+int32_t fetch_tree(mctsb200_ctx* ctx, long long i, HostTree<M>& t) {
+    Storage& st = ctx->st;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpy(&t.h, (const TreeHeader*)st.hdr.p + i, sizeof(TreeHeader), cudaMemcpyDeviceToHost));
+    t.rows.resize((size_t)t.h.n_state);
+    if (t.h.n_state) CUDA_TRY(cudaMemcpy(t.rows.data(), (const Row<M>*)st.rows.p + i * st.geo.NS, sizeof(Row<M>) * (size_t)t.h.n_state, cudaMemcpyDeviceToHost));
+    if (st.kind == MCTSB200_KIND_DPW) {
+        t.aux.resize((size_t)t.h.n_state);
+        t.trans.resize((size_t)t.h.n_trans);
+        if (t.h.n_state) CUDA_TRY(cudaMemcpy(t.aux.data(), (const Aux<M>*)st.aux.p + i * st.geo.NS, sizeof(Aux<M>) * (size_t)t.h.n_state, cudaMemcpyDeviceToHost));
+        if (t.h.n_trans) CUDA_TRY(cudaMemcpy(t.trans.data(), (const TransRec*)st.trans.p + i * st.geo.NT, sizeof(TransRec) * (size_t)t.h.n_trans, cudaMemcpyDeviceToHost));
+    }
+    return MCTSB200_OK;
+}
+
+template <class M>
+int32_t tree_sizes_impl(mctsb200_ctx* ctx, long long i, mctsb200_tree_sizes* out) {
+    TreeHeader h;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpy(&h, (const TreeHeader*)ctx->st.hdr.p + i, sizeof h, cudaMemcpyDeviceToHost));
+    out->n_state_nodes = h.n_state;
+    out->n_action_nodes = h.n_action;
+    out->n_transitions = ctx->st.kind == MCTSB200_KIND_DPW ? h.n_trans : 0;
+    out->state_bytes = (int64_t)sizeof(typename M::AbiState);
+    return MCTSB200_OK;
+}
+
+template <class M>
+int32_t tree_export_impl(mctsb200_ctx* ctx, long long i, const mctsb200_tree_buffers* b) {
+    constexpr int A = M::kActions;
+    HostTree<M> t;
+    int32_t rc = fetch_tree<M>(ctx, i, t);
+    if (rc) return rc;
+    const auto& P = MdpAccess<M>::params(ctx);
+    const bool dpw = ctx->st.kind == MCTSB200_KIND_DPW;
+    const int ns = t.h.n_state;
+    using Abi = typename M::AbiState;
+    int64_t child_pos = 0;
+    // reference action-node id (1-based) of child `slot` of state node `s`
+    auto said = [&](int s, int slot) -> int64_t { return dpw ? (int64_t)t.aux[(size_t)s].seq[slot] : (int64_t)s * A + slot + 1; };
+    if (b->child_offsets) b->child_offsets[0] = 0;
+    for (int s = 0; s < ns; ++s) {
+        const Row<M>& rw = t.rows[(size_t)s];
+        if (b->total_n) b->total_n[s] = rw.total_n;
+        if (b->s_labels) {
+            const Abi lab = M::store(M::state_of(P, rw.key));
+            std::memcpy((char*)b->s_labels + sizeof(Abi) * (size_t)s, &lab, sizeof lab);
+        }
+        for (int slot = 0; slot < rw.nchild; ++slot) {
+            const int64_t id = said(s, slot);
+            if (b->child_ids) b->child_ids[child_pos] = id;
+            ++child_pos;
+            if (b->n) b->n[id - 1] = rw.n[slot];
+            if (b->q) b->q[id - 1] = rw.q[slot];
+            if (b->a_labels) b->a_labels[id - 1] = rw.alabel[slot];
+            if (dpw && b->n_a_children) b->n_a_children[id - 1] = t.aux[(size_t)s].nac[slot];
+        }
+        if (b->child_offsets) b->child_offsets[s + 1] = child_pos;
+    }
+    if (dpw && (b->trans_offsets || b->trans_spnode || b->trans_r || b->trans_count)) {
+        // CSR over action nodes in id order; records oldest-first (first-occurrence order)
+        const int na = t.h.n_action;
+        std::vector<int> owner_s((size_t)na, -1), owner_slot((size_t)na, 0);
+        for (int s = 0; s < ns; ++s)
+            for (int slot = 0; slot < t.rows[(size_t)s].nchild; ++slot) {
+                const int64_t id = said(s, slot);
+                owner_s[(size_t)(id - 1)] = s;
+                owner_slot[(size_t)(id - 1)] = slot;
+            }
+        int64_t pos = 0;
+        if (b->trans_offsets) b->trans_offsets[0] = 0;
+        std::vector<int> chain;
+        for (int id = 0; id < na; ++id) {
+            chain.clear();
+            if (owner_s[(size_t)id] >= 0)
+                for (int rec = t.aux[(size_t)owner_s[(size_t)id]].thead[owner_slot[(size_t)id]]; rec >= 0; rec = t.trans[(size_t)rec].next) chain.push_back(rec);
+            for (auto it = chain.rbegin(); it != chain.rend(); ++it) {
+                const TransRec& tr = t.trans[(size_t)*it];
+                if (b->trans_spnode) b->trans_spnode[pos] = tr.sp + 1;
+                if (b->trans_r) b->trans_r[pos] = tr.r;
+                if (b->trans_count) b->trans_count[pos] = tr.count;
+                ++pos;
+            }
+            if (b->trans_offsets) b->trans_offsets[id + 1] = pos;
+        }
+    }
+    return MCTSB200_OK;
+}
+
+template <class M>
+int32_t root_stats_impl(mctsb200_ctx* ctx, long long i, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q, int64_t* total_n) {
+    TreeHeader h;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpy(&h, (const TreeHeader*)ctx->st.hdr.p + i, sizeof h, cudaMemcpyDeviceToHost));
+    if (h.n_state == 0) {
+        if (n_children) *n_children = 0;
+        if (total_n) *total_n = 0;
+        return MCTSB200_OK;
+    }
+    Row<M> rw;
+    CUDA_TRY(cudaMemcpy(&rw, (const Row<M>*)ctx->st.rows.p + i * ctx->st.geo.NS + h.root, sizeof rw, cudaMemcpyDeviceToHost));
+    if (n_children) *n_children = rw.nchild;
+    if (total_n) *total_n = rw.total_n;
+    for (int j = 0; j < rw.nchild; ++j) {
+        if (action_idx) action_idx[j] = rw.alabel[j];
+        if (n) n[j] = rw.n[j];
+        if (q) q[j] = rw.q[j];
+    }
+    return MCTSB200_OK;
+}
+
+__global__ void probe_log_kernel(const double* x, long long n, double* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = det_log(x[i]);
+}
+__global__ void probe_cos_kernel(const double* x, long long n, double* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = det_cos(x[i]);
+}
+__global__ void probe_philox_kernel(uint64_t seed, uint64_t tree, uint32_t iteration, uint32_t stream_id, int n_words, uint32_t* out) {
+    if (threadIdx.x || blockIdx.x) return;
+    Stream s;
+    s.init(seed, tree, iteration, stream_id);
+    for (int i = 0; i < n_words; ++i) out[i] = s.next();
+}
+
+int32_t check_tree_query(mctsb200_ctx* ctx, long long i) {
+    if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (!ctx->st.valid) return fail(MCTSB200_ERR_STATE, "no tree: call mctsb200_plan first");
+    if (i < 0 || i >= ctx->st.n_trees) return fail(MCTSB200_ERR_INVALID_ARG, "root index %lld out of range [0,%lld)", i, ctx->st.n_trees);
+    return MCTSB200_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// extern "C" surface
+// =====================================================================================================
+extern "C" {
+
+int32_t mctsb200_abi_version(void) { return MCTSB200_ABI_VERSION; }
+const char* mctsb200_last_error(void) { return g_err.c_str(); }
+
+int32_t mctsb200_ctx_create(int32_t device_id, void* stream, mctsb200_ctx** out) {
+    if (!out) return fail(MCTSB200_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(MCTSB200_ERR_CUDA, "no CUDA device available (%s); libmctsb200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device_id < 0 || device_id >= n_dev) return fail(MCTSB200_ERR_INVALID_ARG, "device %d out of range [0,%d)", device_id, n_dev);
+    CUDA_TRY(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major != 10) return fail(MCTSB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device_id, prop.major, prop.minor);
+    mctsb200_ctx* c = new mctsb200_ctx();
+    c->device = device_id;
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return fail(MCTSB200_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
+    if (!c) return MCTSB200_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->counters,
+                      &c->log_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
+                      &c->sums};
+    for (DevBuf* b : bufs) b->release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_mdp_lookup(const char* name, int32_t* mdp_id) {
+    if (!name || !mdp_id) return fail(MCTSB200_ERR_INVALID_ARG, "NULL argument");
+    if (!std::strcmp(name, "SimpleGridWorld")) *mdp_id = MCTSB200_MDP_GRIDWORLD;
+    else if (!std::strcmp(name, "MountainCar")) *mdp_id = MCTSB200_MDP_MOUNTAINCAR;
+    else return fail(MCTSB200_ERR_UNSUPPORTED, "no device plugin registered for MDP '%s' (built in: SimpleGridWorld, MountainCar)", name);
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_mdp_info(int32_t mdp_id, int32_t* n_actions, int64_t* state_bytes) {
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD) {
+        if (n_actions) *n_actions = GridWorldDev::kActions;
+        if (state_bytes) *state_bytes = sizeof(GridWorldDev::AbiState);
+    } else if (mdp_id == MCTSB200_MDP_MOUNTAINCAR) {
+        if (n_actions) *n_actions = MountainCarDev::kActions;
+        if (state_bytes) *state_bytes = sizeof(MountainCarDev::AbiState);
+    } else {
+        return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+    }
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* pod, size_t bytes) {
+    if (!ctx || !pod) return fail(MCTSB200_ERR_INVALID_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD) {
+        if (bytes != sizeof(mctsb200_gridworld_params)) return fail(MCTSB200_ERR_INVALID_ARG, "gridworld params: %zu bytes, expected %zu", bytes, sizeof(mctsb200_gridworld_params));
+        const mctsb200_gridworld_params& p = *(const mctsb200_gridworld_params*)pod;
+        if (p.nx < 1 || p.ny < 1 || (long long)p.nx * p.ny + 1 > 65535) return fail(MCTSB200_ERR_INVALID_ARG, "grid size out of range");
+        if (!(p.tprob >= 0.0 && p.tprob <= 1.0)) return fail(MCTSB200_ERR_INVALID_ARG, "tprob must be in [0,1]");
+        if (!(p.discount >= 0.0 && p.discount <= 1.0)) return fail(MCTSB200_ERR_INVALID_ARG, "discount must be in [0,1]");
+        if (p.n_rewards < 0 || p.n_rewards > MCTSB200_GW_MAX_SPECIAL || p.n_terminate < 0 || p.n_terminate > MCTSB200_GW_MAX_SPECIAL)
+            return fail(MCTSB200_ERR_INVALID_ARG, "too many reward / terminate_from cells (max %d)", MCTSB200_GW_MAX_SPECIAL);
+        const int cells = p.nx * p.ny;
+        std::vector<double> rew((size_t)cells + 1, 0.0);
+        std::vector<uint8_t> term((size_t)cells + 1, 0);
+        auto inb = [&](int x, int y) { return x >= 1 && x <= p.nx && y >= 1 && y <= p.ny; };
+        for (int i = 0; i < p.n_rewards; ++i) {
+            // a Dict key outside the grid can only ever be matched by the terminal state (-1,-1)
+            if (inb(p.reward_x[i], p.reward_y[i])) rew[(size_t)((p.reward_x[i] - 1) + (p.reward_y[i] - 1) * p.nx)] = p.reward_v[i];
+            else if (p.reward_x[i] == -1 && p.reward_y[i] == -1) rew[(size_t)cells] = p.reward_v[i];
+        }
+        for (int i = 0; i < p.n_terminate; ++i)
+            if (inb(p.term_x[i], p.term_y[i])) term[(size_t)((p.term_x[i] - 1) + (p.term_y[i] - 1) * p.nx)] = 1;
+        term[(size_t)cells] = 1;
+        CUDA_TRY(ctx->gw_reward.ensure(rew.size() * sizeof(double)));
+        CUDA_TRY(ctx->gw_term.ensure(term.size()));
+        CUDA_TRY(cudaMemcpy(ctx->gw_reward.p, rew.data(), rew.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(ctx->gw_term.p, term.data(), term.size(), cudaMemcpyHostToDevice));
+        ctx->gw_host = p;
+        ctx->gw_dev.nx = p.nx;
+        ctx->gw_dev.ny = p.ny;
+        ctx->gw_dev.tprob = p.tprob;
+        ctx->gw_dev.p_other = (1.0 - p.tprob) / (double)(GridWorldDev::kActions - 1);
+        ctx->gw_dev.discount = p.discount;
+        ctx->gw_dev.cell_reward = (const double*)ctx->gw_reward.p;
+        ctx->gw_dev.cell_term_from = (const uint8_t*)ctx->gw_term.p;
+        ctx->gw_ok = true;
+        ctx->st.valid = false;
+        return MCTSB200_OK;
+    }
+    if (mdp_id == MCTSB200_MDP_MOUNTAINCAR) {
+        if (bytes != sizeof(mctsb200_mountaincar_params)) return fail(MCTSB200_ERR_INVALID_ARG, "mountaincar params: %zu bytes, expected %zu", bytes, sizeof(mctsb200_mountaincar_params));
+        const mctsb200_mountaincar_params& p = *(const mctsb200_mountaincar_params*)pod;
+        if (!(p.discount >= 0.0 && p.discount <= 1.0)) return fail(MCTSB200_ERR_INVALID_ARG, "discount must be in [0,1]");
+        ctx->mc_dev.discount = p.discount;
+        ctx->mc_dev.cost = p.cost;
+        ctx->mc_dev.jackpot = p.jackpot;
+        ctx->mc_ok = true;
+        ctx->st.valid = false;
+        return MCTSB200_OK;
+    }
+    return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+}
+
+int32_t mctsb200_plan(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* roots, int64_t n_roots, size_t state_bytes,
+                      int64_t root_index_base, int32_t* action_idx_out, double* best_q_out, int32_t* status_out, mctsb200_plan_stats* stats_out) {
+    if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD)
+        return plan_dispatch<GridWorldDev>(ctx, cfg, roots, false, n_roots, state_bytes, root_index_base, action_idx_out, best_q_out, status_out, false, stats_out);
+    if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
+        return plan_dispatch<MountainCarDev>(ctx, cfg, roots, false, n_roots, state_bytes, root_index_base, action_idx_out, best_q_out, status_out, false, stats_out);
+    return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+}
+
+int32_t mctsb200_plan_device(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* d_roots, int64_t n_roots,
+                             size_t state_bytes, int64_t root_index_base, int32_t* d_action_idx_out, double* d_best_q_out, int32_t* d_status_out,
+                             mctsb200_plan_stats* stats_out) {
+    if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD)
+        return plan_dispatch<GridWorldDev>(ctx, cfg, d_roots, true, n_roots, state_bytes, root_index_base, d_action_idx_out, d_best_q_out, d_status_out, true, stats_out);
+    if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
+        return plan_dispatch<MountainCarDev>(ctx, cfg, d_roots, true, n_roots, state_bytes, root_index_base, d_action_idx_out, d_best_q_out, d_status_out, true, stats_out);
+    return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+}
+
+int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* root_state, size_t state_bytes,
+                                    int64_t n_trees, int64_t tree_index_base, double* sum_n_out, double* sum_nq_out, double* d_sums_out,
+                                    mctsb200_plan_stats* stats_out) {
+    if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD)
+        return root_parallel_dispatch<GridWorldDev>(ctx, cfg, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out);
+    if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
+        return root_parallel_dispatch<MountainCarDev>(ctx, cfg, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out);
+    return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+}
+
+int32_t mctsb200_root_parallel_decide(const double* sum_n, const double* sum_nq, int32_t n_actions, double init_q, int32_t* action_idx_out,
+                                      double* best_q_out, double* q_out) {
+    if (!sum_n || !sum_nq || n_actions < 1) return fail(MCTSB200_ERR_INVALID_ARG, "bad arguments");
+    double best = -INFINITY;
+    int act = 0;
+    for (int a = 0; a < n_actions; ++a) {
+        const double q = sum_n[a] > 0.0 ? sum_nq[a] / sum_n[a] : init_q;
+        if (q_out) q_out[a] = q;
+        if (q > best) {
+            best = q;
+            act = a;
+        }
+    }
+    if (action_idx_out) *action_idx_out = act;
+    if (best_q_out) *best_q_out = best;
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_root_stats(mctsb200_ctx* ctx, int64_t root_i, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q, int64_t* total_n) {
+    int32_t rc = check_tree_query(ctx, root_i);
+    if (rc) return rc;
+    if (ctx->st.mdp_id == MCTSB200_MDP_GRIDWORLD) return root_stats_impl<GridWorldDev>(ctx, root_i, n_children, action_idx, n, q, total_n);
+    return root_stats_impl<MountainCarDev>(ctx, root_i, n_children, action_idx, n, q, total_n);
+}
+
+int32_t mctsb200_tree_sizes_query(mctsb200_ctx* ctx, int64_t root_i, mctsb200_tree_sizes* sizes) {
+    int32_t rc = check_tree_query(ctx, root_i);
+    if (rc) return rc;
+    if (!sizes) return fail(MCTSB200_ERR_INVALID_ARG, "sizes is NULL");
+    if (ctx->st.mdp_id == MCTSB200_MDP_GRIDWORLD) return tree_sizes_impl<GridWorldDev>(ctx, root_i, sizes);
+    return tree_sizes_impl<MountainCarDev>(ctx, root_i, sizes);
+}
+
+int32_t mctsb200_tree_export(mctsb200_ctx* ctx, int64_t root_i, const mctsb200_tree_buffers* buffers) {
+    int32_t rc = check_tree_query(ctx, root_i);
+    if (rc) return rc;
+    if (!buffers) return fail(MCTSB200_ERR_INVALID_ARG, "buffers is NULL");
+    if (ctx->st.mdp_id == MCTSB200_MDP_GRIDWORLD) return tree_export_impl<GridWorldDev>(ctx, root_i, buffers);
+    return tree_export_impl<MountainCarDev>(ctx, root_i, buffers);
+}
+
+int32_t mctsb200_clear_trees(mctsb200_ctx* ctx) {
+    if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    ctx->st.valid = false;
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_device_log(mctsb200_ctx* ctx, const double* x, int64_t n, double* out) {
+    if (!ctx || !x || !out || n < 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return MCTSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    DevBuf in, o;
+    CUDA_TRY(in.ensure(sizeof(double) * (size_t)n));
+    CUDA_TRY(o.ensure(sizeof(double) * (size_t)n));
+    CUDA_TRY(cudaMemcpyAsync(in.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    MCTSB200_LAUNCH(probe_log_kernel, (unsigned)((n + 255) / 256), 256, ctx->stream, (const double*)in.p, (long long)n, (double*)o.p);
+    CUDA_TRY(cudaMemcpyAsync(out, o.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    in.release();
+    o.release();
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_device_cos(mctsb200_ctx* ctx, const double* x, int64_t n, double* out) {
+    if (!ctx || !x || !out || n < 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad arguments");
+    if (n == 0) return MCTSB200_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    DevBuf in, o;
+    CUDA_TRY(in.ensure(sizeof(double) * (size_t)n));
+    CUDA_TRY(o.ensure(sizeof(double) * (size_t)n));
+    CUDA_TRY(cudaMemcpyAsync(in.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    MCTSB200_LAUNCH(probe_cos_kernel, (unsigned)((n + 255) / 256), 256, ctx->stream, (const double*)in.p, (long long)n, (double*)o.p);
+    CUDA_TRY(cudaMemcpyAsync(out, o.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    in.release();
+    o.release();
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_device_philox(mctsb200_ctx* ctx, uint64_t seed, uint64_t tree, uint32_t iteration, uint32_t stream_id, int32_t n_blocks, uint32_t* out) {
+    if (!ctx || !out || n_blocks < 1 || n_blocks > 4096) return fail(MCTSB200_ERR_INVALID_ARG, "bad arguments");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    DevBuf o;
+    CUDA_TRY(o.ensure(sizeof(uint32_t) * 4 * (size_t)n_blocks));
+    MCTSB200_LAUNCH(probe_philox_kernel, 1, 32, ctx->stream, seed, tree, iteration, stream_id, 4 * n_blocks, (uint32_t*)o.p);
+    CUDA_TRY(cudaMemcpyAsync(out, o.p, sizeof(uint32_t) * 4 * (size_t)n_blocks, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    o.release();
+    return MCTSB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+// common.cuh -- shared device/host PODs of libmctsb200: Philox streams, per-tree tables, kernel arguments.
+//
+// Storage model ("node tables", one set per ctx, all in HBM):
+//   for each component X there is ONE array covering all trees of the plan call, indexed
+//   [tree][entry] (struct-of-arrays at the table level):
+//     hdr   [n_trees]                 TreeHeader   counters, root id, status
+//     rows  [n_trees][NS]             Row<M>       one 64 B row per state node: q[A], key, n[A], total_n,
+//                                                  child count + child action labels (2 sectors, read with
+//                                                  16 B vector loads)
+//     aux   [n_trees][NS]             Aux<M>       DPW only: n_a_children, transition list head, push
+//                                                  count and insertion sequence number per child
+//     trans [n_trees][NT]             TransRec     DPW only: distinct (spnode, r) records with counts
+//     map   [n_trees][MAP]            u16 / HashSlot   state -> node id (dense index or open addressing)
+//     path  [n_trees][depth]          PathEntry    the explicit recursion stack of one simulation
+// Node ids on the device are 0-based; the ABI export converts to the reference's 1-based ids.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/mctsb200.h"
+#include "../../include/mctsb200_detmath.h"
+
+// Kernel launch. MCTSB200_HOST_EMU is defined only by tests/emu (a single-threaded host build of this
+// library used to exercise the host logic without a GPU); the shipped library never defines it.
+#ifdef MCTSB200_HOST_EMU
+#define MCTSB200_LAUNCH(kernel, grid, block, stream, ...) mctsb200_emu::run((grid), (block), [&] { kernel(__VA_ARGS__); })
+#else
+#define MCTSB200_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace mctsb200 {
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 streams (contract: include/mctsb200.h)
+// ---------------------------------------------------------------------------------------------
+struct Stream {
+    uint32_t k0, k1;
+    uint32_t c0, c1, c2, c3;
+    uint32_t b0, b1, b2, b3;
+    int have;
+
+    __host__ __device__ __forceinline__ void init(uint64_t seed, uint64_t tree, uint32_t iteration, uint32_t stream_id) {
+        k0 = (uint32_t)seed;
+        k1 = (uint32_t)(seed >> 32);
+        c0 = 0;
+        c1 = iteration;
+        c2 = (uint32_t)tree;
+        c3 = (uint32_t)(((tree >> 32) & 0xffffu) << 16) | (stream_id & 0xffffu);
+        have = 0;
+    }
+    __host__ __device__ __forceinline__ void refill() {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, ka = k0, kb = k1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int round = 0; round < 10; ++round) {
+#if defined(__CUDA_ARCH__)
+            const uint32_t lo0 = 0xD2511F53u * x0, hi0 = __umulhi(0xD2511F53u, x0);
+            const uint32_t lo1 = 0xCD9E8D57u * x2, hi1 = __umulhi(0xCD9E8D57u, x2);
+#else
+            const uint64_t p0 = (uint64_t)0xD2511F53u * x0, p1 = (uint64_t)0xCD9E8D57u * x2;
+            const uint32_t lo0 = (uint32_t)p0, hi0 = (uint32_t)(p0 >> 32), lo1 = (uint32_t)p1, hi1 = (uint32_t)(p1 >> 32);
+#endif
+            const uint32_t n0 = hi1 ^ x1 ^ ka, n2 = hi0 ^ x3 ^ kb;
+            x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
+            ka += 0x9E3779B9u;
+            kb += 0xBB67AE85u;
+        }
+        b0 = x0; b1 = x1; b2 = x2; b3 = x3;
+        c0 += 1;
+        have = 4;
+    }
+    __host__ __device__ __forceinline__ uint32_t next() {
+        if (have == 0) refill();
+        const uint32_t w = have == 4 ? b0 : have == 3 ? b1 : have == 2 ? b2 : b3;
+        --have;
+        return w;
+    }
+    __host__ __device__ __forceinline__ int uniform_int(int n) {
+#if defined(__CUDA_ARCH__)
+        return (int)__umulhi(next(), (uint32_t)n);
+#else
+        return (int)(((uint64_t)next() * (uint64_t)n) >> 32);
+#endif
+    }
+    __host__ __device__ __forceinline__ double uniform01() { return (double)next() * (1.0 / 4294967296.0); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Per-tree tables
+// ---------------------------------------------------------------------------------------------
+struct TreeHeader {
+    int n_state;     // state nodes in use
+    int n_action;    // action nodes inserted so far (DPW insertion sequence; UCT: A * n_state)
+    int n_trans;     // transition records in use
+    int root;        // 0-based root node id
+    int status;      // MCTSB200_OK / ERR_TERMINAL_ROOT / ERR_CAPACITY
+    int iterations;  // iterations completed
+    int pad[2];
+};
+
+struct __align__(16) PathEntry {
+    int node;
+    int slot;
+    double r;
+};
+
+struct __align__(32) TransRec {
+    double r;
+    int sp;     // 0-based state node
+    int next;   // next (older) record of the same action node, -1 = end
+    int count;  // multiplicity in the reference's transitions[sanode] vector
+    int pad[3];
+};
+
+struct __align__(8) HashSlot {
+    uint32_t tag;  // 0 = empty; else (hash | 1)
+    int node;
+};
+
+// One state node. UCT: children are all A actions in actions(mdp) order (child k = action k; reference
+// action-node id = A*node + k + 1). DPW: children live in slots [0, nchild) in insertion order with
+// their action index in alabel[].
+template <class M>
+struct __align__(32) Row {
+    double q[M::kActions];
+    typename M::Key key;
+    int n[M::kActions];
+    int total_n;
+    uint8_t nchild;
+    uint8_t alabel[M::kActions];
+};
+
+template <class M>
+struct __align__(32) Aux {
+    int nac[M::kActions];    // n_a_children
+    int thead[M::kActions];  // newest transition record, -1 = none
+    int tpush[M::kActions];  // length of the reference's transitions[sanode] (pushes)
+    int seq[M::kActions];    // 1-based insertion sequence of the action node (reference id)
+};
+
+// geometry of the tables of one plan call
+struct Geometry {
+    int NS;         // state-node capacity per tree
+    int NT;         // transition-record capacity per tree
+    int MAP;        // map entries per tree (dense: n_dense u16; hash: power-of-two HashSlots)
+    int depth;      // path entries per tree
+};
+
+enum CounterId {
+    CNT_SIMULATIONS = 0, CNT_LEVELS, CNT_CHILDREN_SEEN, CNT_STATE_INSERTS, CNT_ACTION_INSERTS, CNT_ROLLOUTS, CNT_ROLLOUT_STEPS,
+    CNT_TRANS_SAMPLES, CNT_COUNT
+};
+
+// device view of the solver configuration
+struct DevCfg {
+    long long n_iterations;
+    double c;
+    double init_Q;
+    double estimate_const;
+    double rollout_eps;
+    unsigned long long seed;
+    const double* init_q_table;  // device, may be null
+    const int* init_n_table;     // device, may be null
+    const double* value_table;   // device, may be null
+    const double* log_tab;       // device: det_log(N) for N < log_tab_n
+    const int* nmin_state;       // device: min n[sanode] for which n_a_children == len may widen
+    int log_tab_n;
+    int nmin_state_n;
+    int nmin_action[16];         // min total_n for which a state node with len children may widen
+    int depth;
+    int K;
+    int init_N;
+    int estimate_kind;
+    int policy;
+    int pparam[4];
+    int rollout_max_depth;
+    int enable_action_pw, enable_state_pw, check_repeat_state, maintain_lookup;
+};
+
+template <class M>
+struct KernelArgs {
+    typename M::Params mdp;
+    DevCfg cfg;
+    Geometry geo;
+    TreeHeader* hdr;
+    Row<M>* rows;
+    Aux<M>* aux;
+    TransRec* trans;
+    void* map;
+    PathEntry* path;
+    const typename M::AbiState* roots;  // device
+    unsigned long long* counters;       // device, CNT_COUNT entries
+    long long n_trees;
+    long long tree_index_base;
+    long long root_stride;              // 1 = one root per tree, 0 = every tree plans roots[0]
+    int iter_begin, iter_end;
+};
+
+}  // namespace mctsb200

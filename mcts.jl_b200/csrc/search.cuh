@@ -1,0 +1,655 @@
+// search.cuh -- the search loop on the device: UCT (src/vanilla.jl:229-276, 292-307, 354-386),
+// DPW (src/dpw.jl:48-56, 80-154, 179-199; src/dpw_types.jl:162-186) and leaf evaluation
+// (src/domain_knowledge.jl:65-73 + the POMDPTools RolloutSimulator loop).  Paths are relative to
+// /root/reference; the code is a from-scratch design, not a translation:
+//
+//   * one TILE of G lanes (G = 1,2,4,...,32; G = 32 with 32-thread blocks is "one CTA per tree")
+//     owns one tree for the whole launch; every lane of the tile carries the same control state
+//     (node, depth, state, Philox stream), so shared decisions cost no communication;
+//   * selection: lane j scores child j, the tile arg-maxes with warp shuffles (ties -> lowest index,
+//     exactly the reference's strict '>' scan);
+//   * the reference's recursion is an explicit path stack; backup runs deepest-first after the
+//     descent, which reproduces the stale-statistics behaviour of re-entered nodes;
+//   * leaf rollouts: K = rollouts_per_leaf independent Philox streams, one lane per rollout, summed
+//     in stream order (so K>1 is still bit-reproducible); K = 1 is the reference's estimator;
+//   * no transcendental is evaluated per child: log(total_n) is one table load per level, and the
+//     widening tests k*N^alpha are integer compares against host-built threshold tables.
+#pragma once
+#ifndef MCTSB200_HOST_EMU
+#include <math_constants.h>
+#endif
+
+#include "common.cuh"
+#include "models.cuh"
+
+namespace mctsb200 {
+
+constexpr int kBlockThreads = 128;
+
+template <int G>
+struct Tile {
+    static_assert(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "tile width");
+    unsigned mask;
+    int lane;
+    __device__ __forceinline__ Tile() {
+        lane = threadIdx.x & (G - 1);
+        if constexpr (G == 32) mask = 0xffffffffu;
+        else mask = ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
+    }
+    __device__ __forceinline__ void sync() const {
+        if constexpr (G > 1) __syncwarp(mask);
+    }
+    __device__ __forceinline__ double bcast(double v, int src) const {
+        if constexpr (G > 1) return __shfl_sync(mask, v, src, G);
+        else return v;
+    }
+    __device__ __forceinline__ int min_int(int v) const {
+        if constexpr (G > 1) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o, G));
+        }
+        return v;
+    }
+    // arg-max of (score, idx): larger score wins, equal scores -> smaller idx
+    __device__ __forceinline__ void argmax(double& score, int& idx) const {
+        if constexpr (G > 1) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const double os = __shfl_xor_sync(mask, score, o, G);
+                const int oi = __shfl_xor_sync(mask, idx, o, G);
+                if (os > score || (os == score && oi < idx)) {
+                    score = os;
+                    idx = oi;
+                }
+            }
+        }
+    }
+};
+
+template <class M, int G>
+struct Search {
+    using State = typename M::State;
+    using Key = typename M::Key;
+    static constexpr int A = M::kActions;
+
+    const KernelArgs<M>& a;
+    Tile<G> tile;
+    // this tile's tables
+    Row<M>* rows;
+    Aux<M>* aux;
+    TransRec* trans;
+    PathEntry* path;
+    uint16_t* dmap;
+    HashSlot* hmap;
+    uint64_t tree_index;
+    // header mirror (registers, tile-uniform)
+    int n_state, n_action, n_trans, status;
+    // per-lane work counters
+    unsigned long long cnt[CNT_COUNT];
+
+    __device__ __forceinline__ Search(const KernelArgs<M>& args, long long tree) : a(args) {
+        rows = args.rows + tree * args.geo.NS;
+        aux = args.aux ? args.aux + tree * args.geo.NS : nullptr;
+        trans = args.trans ? args.trans + tree * args.geo.NT : nullptr;
+        path = args.path + tree * args.geo.depth;
+        dmap = M::kDense ? (uint16_t*)args.map + tree * args.geo.MAP : nullptr;
+        hmap = M::kDense ? nullptr : (HashSlot*)args.map + tree * args.geo.MAP;
+        tree_index = (uint64_t)(args.tree_index_base + tree);
+#pragma unroll
+        for (int i = 0; i < CNT_COUNT; ++i) cnt[i] = 0;
+    }
+
+    __device__ __forceinline__ bool lead() const { return tile.lane == 0; }
+
+    // ---- numeric hooks (src/domain_knowledge.jl:10,82,91 + table stand-ins) ----
+    __device__ __forceinline__ double init_Q(const State& s, int act) const {
+        if (M::kDense && a.cfg.init_q_table) return __ldg(a.cfg.init_q_table + M::dense_index(a.mdp, s) * A + act);
+        return a.cfg.init_Q;
+    }
+    __device__ __forceinline__ int init_N(const State& s, int act) const {
+        if (M::kDense && a.cfg.init_n_table) return __ldg(a.cfg.init_n_table + M::dense_index(a.mdp, s) * A + act);
+        return a.cfg.init_N;
+    }
+    __device__ __forceinline__ double log_n(int N) const {
+        if (N < a.cfg.log_tab_n) return __ldg(a.cfg.log_tab + N);
+        return det_log((double)N);
+    }
+
+    // ---- state -> node map -----------------------------------------------------------------
+    __device__ __forceinline__ int map_lookup(const State& s) const {
+        if (M::kDense) {
+            return (int)dmap[M::dense_index(a.mdp, s)] - 1;
+        } else {
+            const uint32_t tag = hash_of(s) | 1u;
+            const int msk = a.geo.MAP - 1;
+            const Key key = M::key_of(a.mdp, s);
+            for (int i = (int)(tag >> 1) & msk;; i = (i + 1) & msk) {
+                const HashSlot sl = hmap[i];
+                if (sl.tag == 0) return -1;
+                if (sl.tag == tag && M::key_equal(rows[sl.node].key, key)) return sl.node;
+            }
+        }
+    }
+    __device__ __forceinline__ void map_insert(const State& s, int node) const {  // leader only
+        if (M::kDense) {
+            dmap[M::dense_index(a.mdp, s)] = (uint16_t)(node + 1);
+        } else {
+            const uint32_t tag = hash_of(s) | 1u;
+            const int msk = a.geo.MAP - 1;
+            int i = (int)(tag >> 1) & msk;
+            while (hmap[i].tag != 0) i = (i + 1) & msk;
+            hmap[i] = HashSlot{tag, node};
+        }
+    }
+    __device__ __forceinline__ static uint32_t hash_of(const State& s) {
+        if constexpr (M::kDense) return 0u;
+        else return M::hash(s);
+    }
+
+    // ---- leaf evaluation ---------------------------------------------------------------------
+    // POMDPTools simulate(::RolloutSimulator, mdp, policy, s0)
+    __device__ __forceinline__ double rollout(State s, int max_steps, Stream& rs, unsigned long long& steps) const {
+        const double eps = a.cfg.rollout_eps;
+        const double gamma = M::discount(a.mdp);
+        double disc = 1.0, r_total = 0.0;
+        int step = 1;
+        while (disc > eps && !M::is_terminal(a.mdp, s) && step <= max_steps) {
+            const int act = M::policy_action(a.mdp, a.cfg.policy, a.cfg.pparam, s, rs);
+            State sp;
+            double r;
+            M::gen(a.mdp, s, act, rs, sp, r);
+            r_total = DM_ADD(r_total, DM_MUL(disc, r));
+            s = sp;
+            disc = DM_MUL(disc, gamma);
+            ++step;
+            ++steps;
+        }
+        return r_total;
+    }
+
+    // estimate_value(estimator, mdp, s, remaining_depth)
+    __device__ __forceinline__ double estimate(const State& s, int remaining_depth, uint32_t it) {
+        if (a.cfg.estimate_kind == MCTSB200_EST_CONSTANT) return a.cfg.estimate_const;
+        if (a.cfg.estimate_kind == MCTSB200_EST_TABLE) {
+            if constexpr (M::kDense) return __ldg(a.cfg.value_table + M::dense_index(a.mdp, s));
+            else return 0.0;
+        }
+        const int max_steps = a.cfg.rollout_max_depth == -1 ? remaining_depth : a.cfg.rollout_max_depth;
+        const int K = a.cfg.K;
+        if (K == 1) {  // every lane runs the same stream: no divergence, no shuffle
+            Stream rs;
+            rs.init(a.cfg.seed, tree_index, it, 1u);
+            unsigned long long steps = 0;
+            const double v = rollout(s, max_steps, rs, steps);
+            if (lead()) {
+                cnt[CNT_ROLLOUTS] += 1;
+                cnt[CNT_ROLLOUT_STEPS] += steps;
+            }
+            return v;
+        }
+        // leaf-parallel: lane l runs rollouts l, l+G, ...; summed in stream order 0..K-1
+        double sum = 0.0;
+        for (int base = 0; base < K; base += G) {
+            const int k = base + tile.lane;
+            double mine = 0.0;
+            if (k < K) {
+                Stream rs;
+                rs.init(a.cfg.seed, tree_index, it, 1u + (uint32_t)k);
+                unsigned long long steps = 0;
+                mine = rollout(s, max_steps, rs, steps);
+                cnt[CNT_ROLLOUTS] += 1;
+                cnt[CNT_ROLLOUT_STEPS] += steps;
+            }
+            const int m = min(G, K - base);
+            for (int j = 0; j < m; ++j) sum = DM_ADD(sum, tile.bcast(mine, j));
+        }
+        return DM_DIV(sum, (double)K);
+    }
+
+    // ---- backup (src/vanilla.jl:272-274, src/dpw.jl:149-151), deepest level first ---------------
+    __device__ __forceinline__ void backup(int top, double v) {
+        tile.sync();
+        const double gamma = M::discount(a.mdp);
+        for (int lvl = top - 1; lvl >= 0; --lvl) {
+            const PathEntry e = path[lvl];
+            const double qv = DM_ADD(e.r, DM_MUL(gamma, v));
+            if (lead()) {
+                Row<M>* rw = rows + e.node;
+                const int nn = rw->n[e.slot] + 1;
+                rw->n[e.slot] = nn;
+                rw->total_n += 1;
+                const double qo = rw->q[e.slot];
+                rw->q[e.slot] = DM_ADD(qo, DM_DIV(DM_SUB(qv, qo), (double)nn));
+            }
+            v = qv;
+        }
+        tile.sync();
+    }
+
+    // =====================================================================================
+    // Vanilla UCT
+    // =====================================================================================
+    // insert_node! (src/vanilla.jl:292-307); returns the new 0-based node id or -1 on overflow
+    __device__ __forceinline__ int uct_insert(const State& s) {
+        const int id = n_state;
+        if (id >= a.geo.NS) {
+            status = MCTSB200_ERR_CAPACITY;
+            return -1;
+        }
+        if (lead()) {
+            Row<M>* rw = rows + id;
+            int tot = 0;
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                const int n0 = init_N(s, k);
+                tot += n0;
+                rw->n[k] = n0;
+                rw->q[k] = init_Q(s, k);
+                rw->alabel[k] = (uint8_t)k;
+            }
+            rw->total_n = tot;
+            rw->nchild = (uint8_t)A;
+            rw->key = M::key_of(a.mdp, s);
+            map_insert(s, id);
+            cnt[CNT_STATE_INSERTS] += 1;
+            cnt[CNT_ACTION_INSERTS] += A;
+        }
+        n_state = id + 1;
+        n_action += A;
+        return id;
+    }
+
+    // best_sanode_UCB (src/vanilla.jl:354-386); returns the child slot (= action index)
+    __device__ __forceinline__ int uct_select(const Row<M>* rw) const {
+        const double c = a.cfg.c;
+        double best = -CUDART_INF;
+        int best_i = 0x7fffffff;
+        if (c == 0.0) {  // argmax(q, children)
+            for (int j = tile.lane; j < A; j += G) {
+                const double qj = rw->q[j];
+                if (qj > best) {
+                    best = qj;
+                    best_i = j;
+                }
+            }
+            tile.argmax(best, best_i);
+            return best_i == 0x7fffffff ? 0 : best_i;
+        }
+        const int sn = rw->total_n;
+        int first_zero = 0x7fffffff;
+        int nj[(A + G - 1) / G];
+#pragma unroll
+        for (int t = 0; t < (A + G - 1) / G; ++t) {
+            const int j = tile.lane + t * G;
+            nj[t] = j < A ? rw->n[j] : 1;
+            if (j < A && nj[t] == 0) first_zero = min(first_zero, j);
+        }
+        first_zero = tile.min_int(first_zero);
+        if (first_zero != 0x7fffffff) return first_zero;  // "if action was not used, use it"
+        const double lsn = log_n(sn);
+#pragma unroll
+        for (int t = 0; t < (A + G - 1) / G; ++t) {
+            const int j = tile.lane + t * G;
+            if (j < A) {
+                const double ucb = DM_ADD(rw->q[j], DM_MUL(c, DM_SQRT(DM_DIV(lsn, (double)nj[t]))));
+                if (ucb > best) {
+                    best = ucb;
+                    best_i = j;
+                }
+            }
+        }
+        tile.argmax(best, best_i);
+        return best_i == 0x7fffffff ? 0 : best_i;
+    }
+
+    // one iteration of src/vanilla.jl:229-235: simulate(root, depth) unrolled into descent + backup
+    __device__ __forceinline__ void uct_iteration(int root, uint32_t it) {
+        Stream rng;
+        rng.init(a.cfg.seed, tree_index, it, 0u);
+        int node = root, d = a.cfg.depth, top = 0;
+        State s = M::state_of(a.mdp, rows[node].key);
+        double v;
+        for (;;) {
+            if (M::is_terminal(a.mdp, s)) {
+                v = 0.0;
+                break;
+            }
+            if (d == 0) {
+                v = estimate(s, 0, it);
+                break;
+            }
+            if (lead()) cnt[CNT_LEVELS] += 1;
+            const int slot = uct_select(rows + node);
+            State sp;
+            double r;
+            M::gen(a.mdp, s, slot, rng, sp, r);
+            if (lead()) path[top] = PathEntry{node, slot, r};
+            ++top;
+            int spid = map_lookup(sp);
+            if (spid < 0) {
+                spid = uct_insert(sp);
+                if (spid < 0) return;  // capacity error: abandon this simulation
+                v = estimate(sp, d - 1, it);
+                break;
+            }
+            node = spid;
+            s = sp;
+            --d;
+        }
+        backup(top, v);
+        if (lead()) cnt[CNT_SIMULATIONS] += 1;
+    }
+
+    // =====================================================================================
+    // DPW
+    // =====================================================================================
+    // insert_state_node! (src/dpw_types.jl:162-171)
+    __device__ __forceinline__ int dpw_insert_state(const State& s, bool maintain_lookup) {
+        const int id = n_state;
+        if (id >= a.geo.NS) {
+            status = MCTSB200_ERR_CAPACITY;
+            return -1;
+        }
+        if (lead()) {
+            Row<M>* rw = rows + id;
+            rw->total_n = 0;
+            rw->nchild = 0;
+            rw->key = M::key_of(a.mdp, s);
+            if (maintain_lookup) map_insert(s, id);
+            cnt[CNT_STATE_INSERTS] += 1;
+        }
+        n_state = id + 1;
+        return id;
+    }
+
+    // insert_action_node! (src/dpw_types.jl:174-186) into the next free slot of the row
+    __device__ __forceinline__ void dpw_insert_action(int node, int slot, const State& s, int act) {
+        if (lead()) {
+            Row<M>* rw = rows + node;
+            Aux<M>* ax = aux + node;
+            const int n0 = init_N(s, act);
+            rw->n[slot] = n0;
+            rw->q[slot] = init_Q(s, act);
+            rw->alabel[slot] = (uint8_t)act;
+            rw->nchild = (uint8_t)(slot + 1);
+            rw->total_n += n0;  // tree.total_n[snode] += n0
+            ax->nac[slot] = 0;
+            ax->thead[slot] = -1;
+            ax->tpush[slot] = 0;
+            ax->seq[slot] = n_action + 1;
+            cnt[CNT_ACTION_INSERTS] += 1;
+        }
+        n_action += 1;
+    }
+
+    // best_sanode_UCB (src/dpw.jl:179-199); returns the child slot
+    __device__ __forceinline__ int dpw_select(const Row<M>* rw, int nchild) const {
+        const double c = a.cfg.c;
+        const double ltn = log_n(rw->total_n);
+        double best = -CUDART_INF;
+        int best_i = 0x7fffffff;
+        for (int j = tile.lane; j < nchild; j += G) {
+            const int nn = rw->n[j];
+            const double qq = rw->q[j];
+            double ucb;
+            if ((ltn <= 0.0 && nn == 0) || c == 0.0) ucb = qq;
+            else ucb = DM_ADD(qq, DM_MUL(c, DM_SQRT(DM_DIV(ltn, (double)nn))));
+            if (ucb > best) {
+                best = ucb;
+                best_i = j;
+            }
+        }
+        tile.argmax(best, best_i);
+        return best_i == 0x7fffffff ? 0 : best_i;
+    }
+
+    // one iteration of src/dpw.jl:48-56: simulate(dpw, snode, depth) as descent + backup
+    __device__ __forceinline__ void dpw_iteration(int root, uint32_t it) {
+        Stream rng;
+        rng.init(a.cfg.seed, tree_index, it, 0u);
+        int node = root, d = a.cfg.depth, top = 0;
+        State s = M::state_of(a.mdp, rows[node].key);
+        double v;
+        for (;;) {
+            if (M::is_terminal(a.mdp, s)) {
+                v = 0.0;
+                break;
+            }
+            if (d == 0) {
+                v = estimate(s, 0, it);
+                break;
+            }
+            Row<M>* rw = rows + node;
+            int nchild = rw->nchild;
+            // ---- action progressive widening (src/dpw.jl:94-114) ----
+            if (a.cfg.enable_action_pw) {
+                // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action[len]
+                if (rw->total_n >= a.cfg.nmin_action[nchild]) {
+                    const int act = rng.uniform_int(A);  // next_action(::RandomActionGenerator)
+                    bool present = false;
+                    for (int j = 0; j < nchild; ++j) present |= (rw->alabel[j] == act);
+                    if (!present) {  // check_repeat_action (always on; see capi.cu)
+                        dpw_insert_action(node, nchild, s, act);
+                        ++nchild;
+                        tile.sync();
+                    }
+                }
+            } else if (nchild == 0) {
+                for (int act = 0; act < A; ++act) dpw_insert_action(node, act, s, act);
+                nchild = A;
+                tile.sync();
+            }
+            if (lead()) {
+                cnt[CNT_LEVELS] += 1;
+                cnt[CNT_CHILDREN_SEEN] += (unsigned long long)nchild;
+            }
+            const int slot = dpw_select(rw, nchild);
+            const int act = rw->alabel[slot];
+            Aux<M>* ax = aux + node;
+
+            // ---- state progressive widening (src/dpw.jl:119-141) ----
+            bool new_node = false;
+            int spnode;
+            double r;
+            State sp;
+            const int nac = ax->nac[slot];
+            bool widen = nac == 0;
+            if (!widen && a.cfg.enable_state_pw) {
+                // n_a_children <= k_state * n^alpha_state  <=>  n >= nmin_state[n_a_children]
+                const int need = nac < a.cfg.nmin_state_n ? __ldg(a.cfg.nmin_state + nac) : 0x7fffffff;
+                widen = rw->n[slot] >= need;
+            }
+            if (widen) {
+                M::gen(a.mdp, s, act, rng, sp, r);
+                spnode = a.cfg.check_repeat_state ? map_lookup(sp) : -1;
+                if (spnode < 0) {
+                    spnode = dpw_insert_state(sp, a.cfg.maintain_lookup != 0);
+                    if (spnode < 0) return;
+                    new_node = true;
+                }
+                // push!(transitions[sanode], (spnode, r)) in multiset form; unique_transitions bookkeeping
+                int rec = -1;
+                if (!new_node) {
+                    for (rec = ax->thead[slot]; rec >= 0; rec = trans[rec].next)
+                        if (trans[rec].sp == spnode) break;
+                }
+                if (rec < 0 && n_trans >= a.geo.NT) {
+                    status = MCTSB200_ERR_CAPACITY;
+                    return;
+                }
+                if (lead()) {
+                    if (rec >= 0) {
+                        trans[rec].count += 1;
+                    } else {
+                        TransRec t;
+                        t.r = r;
+                        t.sp = spnode;
+                        t.next = ax->thead[slot];
+                        t.count = 1;
+                        t.pad[0] = t.pad[1] = t.pad[2] = 0;
+                        trans[n_trans] = t;
+                        ax->thead[slot] = n_trans;
+                        ax->nac[slot] = nac + 1;
+                    }
+                    ax->tpush[slot] += 1;
+                }
+                if (rec < 0) n_trans += 1;
+            } else {
+                // rand(rng, transitions[sanode]): index j of the push-ordered multiset; records are chained
+                // newest-first, so walk with the mirrored index
+                const int pushes = ax->tpush[slot];
+                const int j = rng.uniform_int(pushes);
+                int jm = pushes - 1 - j, cum = 0, rec = ax->thead[slot];
+                for (;;) {
+                    const int cnt_r = trans[rec].count;
+                    if (jm < cum + cnt_r || trans[rec].next < 0) break;
+                    cum += cnt_r;
+                    rec = trans[rec].next;
+                }
+                spnode = trans[rec].sp;
+                r = trans[rec].r;
+                sp = M::state_of(a.mdp, rows[spnode].key);
+                if (lead()) cnt[CNT_TRANS_SAMPLES] += 1;
+            }
+            if (lead()) path[top] = PathEntry{node, slot, r};
+            ++top;
+            tile.sync();
+            if (new_node) {
+                v = estimate(sp, d - 1, it);
+                break;
+            }
+            node = spnode;
+            s = sp;
+            --d;
+        }
+        backup(top, v);
+        if (lead()) cnt[CNT_SIMULATIONS] += 1;
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// The search kernel: iterations [iter_begin, iter_end) of every tree of the call.
+// -------------------------------------------------------------------------------------------------
+template <class M, int KIND, int G>
+__global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_constant__ KernelArgs<M> args) {
+    __shared__ unsigned long long s_cnt[CNT_COUNT];
+#ifndef MCTSB200_HOST_EMU
+    if (threadIdx.x < CNT_COUNT) s_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+#endif
+
+    const long long tree = ((long long)blockIdx.x * kBlockThreads + threadIdx.x) / G;
+    if (tree < args.n_trees) {
+        Search<M, G> S(args, tree);
+        TreeHeader* hd = args.hdr + tree;
+        TreeHeader h = *hd;
+        S.n_state = h.n_state;
+        S.n_action = h.n_action;
+        S.n_trans = h.n_trans;
+        S.status = h.status;
+        int root = h.root;
+
+        if (args.iter_begin == 0 && h.iterations == 0 && h.status == MCTSB200_OK) {
+            // root lookup / insertion (src/vanilla.jl:219-224, src/dpw.jl:22-42)
+            const typename M::State s0 = M::load(args.roots[tree * args.root_stride]);
+            if (KIND == MCTSB200_KIND_DPW && M::is_terminal(args.mdp, s0)) {
+                S.status = MCTSB200_ERR_TERMINAL_ROOT;
+            } else {
+                int id = S.n_state > 0 ? S.map_lookup(s0) : -1;
+                if (id < 0) {
+                    if (KIND == MCTSB200_KIND_UCT) id = S.uct_insert(s0);
+                    else id = S.dpw_insert_state(s0, S.n_state > 0 ? true : args.cfg.check_repeat_state != 0);
+                }
+                root = id < 0 ? 0 : id;
+            }
+            S.tile.sync();
+        }
+
+        int it = args.iter_begin;
+        for (; it < args.iter_end && S.status == MCTSB200_OK; ++it) {
+            if (KIND == MCTSB200_KIND_UCT) S.uct_iteration(root, (uint32_t)it);
+            else S.dpw_iteration(root, (uint32_t)it);
+        }
+
+        if (S.lead()) {
+            h.n_state = S.n_state;
+            h.n_action = S.n_action;
+            h.n_trans = S.n_trans;
+            h.status = S.status;
+            h.root = root;
+            h.iterations = S.status == MCTSB200_OK ? args.iter_end : it;
+            *hd = h;
+        }
+#pragma unroll
+        for (int i = 0; i < CNT_COUNT; ++i)
+            if (S.cnt[i]) atomicAdd(&s_cnt[i], S.cnt[i]);
+    }
+#ifdef MCTSB200_HOST_EMU
+    for (int i = 0; i < CNT_COUNT; ++i) {  // the emulator runs one thread at a time
+        args.counters[i] += s_cnt[i];
+        s_cnt[i] = 0;
+    }
+#else
+    __syncthreads();
+    if (threadIdx.x < CNT_COUNT && s_cnt[threadIdx.x]) atomicAdd(args.counters + threadIdx.x, s_cnt[threadIdx.x]);
+#endif
+}
+
+// Root decision: best_sanode_Q (src/vanilla.jl:339-349) / best_sanode (src/dpw.jl:163-173).
+template <class M>
+__global__ void decide_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS, long long n_trees, int* action_out,
+                              double* best_q_out, int* status_out) {
+    const long long tree = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= n_trees) return;
+    const TreeHeader h = hdr[tree];
+    int act = 0;
+    double bq = 0.0;
+    if (h.status != MCTSB200_ERR_TERMINAL_ROOT && h.n_state > 0) {
+        const Row<M>* rw = rows + tree * NS + h.root;
+        double best = -CUDART_INF;
+        int slot = rw->nchild > 0 ? 0 : -1;  // vanilla default: first child; DPW: 0 children -> none
+        for (int j = 0; j < rw->nchild; ++j) {
+            if (rw->q[j] > best) {
+                best = rw->q[j];
+                slot = j;
+            }
+        }
+        if (slot >= 0) {
+            act = rw->alabel[slot];
+            bq = rw->q[slot];
+        }
+    }
+    if (action_out) action_out[tree] = act;
+    if (best_q_out) best_q_out[tree] = bq;
+    if (status_out) status_out[tree] = h.status;
+}
+
+// Root-parallel partial sums (BASELINE config 5): lane a sums action a over all trees in tree order, so
+// the result is bit-identical to a sequential host loop. out = [sum_n[0..A) | sum_nq[0..A)].
+template <class M>
+__global__ void root_sums_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS, long long n_trees, double* out) {
+    const int act = threadIdx.x;
+    if (act >= M::kActions) return;
+    double sn = 0.0, snq = 0.0;
+    for (long long t = 0; t < n_trees; ++t) {
+        const TreeHeader h = hdr[t];
+        if (h.n_state == 0) continue;
+        const Row<M>* rw = rows + t * NS + h.root;
+        for (int j = 0; j < rw->nchild; ++j) {
+            if (rw->alabel[j] == act) {
+                const double nn = (double)rw->n[j];
+                sn = DM_ADD(sn, nn);
+                snq = DM_ADD(snq, DM_MUL(nn, rw->q[j]));
+            }
+        }
+    }
+    out[act] = sn;
+    out[M::kActions + act] = snq;
+}
+
+template <class M, int KIND>
+void launch_search(const KernelArgs<M>& args, int G, cudaStream_t stream);
+template <class M, int KIND>
+int search_occupancy(int G);  // resident blocks per SM of the G variant
+
+}  // namespace mctsb200

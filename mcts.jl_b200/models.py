@@ -1,0 +1,119 @@
+"""Host-side descriptions of the MDPs that have a device plugin (mcts.jl_b200/csrc/models.cuh).
+
+These mirror the POMDPModels.jl constructors the reference's tests and benches use
+(`SimpleGridWorld()` everywhere in /root/reference/test, `GWPos`; MountainCar per BASELINE.json) and
+only carry parameters: all model arithmetic runs on the device.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, Optional, Sequence, Set, Tuple
+
+import numpy as np
+
+from . import _abi as abi
+
+
+def GWPos(x: int, y: int) -> Tuple[int, int]:
+    """SVector{2,Int} stand-in."""
+    return (int(x), int(y))
+
+
+_DEFAULT_REWARDS = {(4, 3): -10.0, (4, 6): -5.0, (9, 3): 10.0, (8, 8): 3.0}
+
+
+@dataclass
+class SimpleGridWorld:
+    """POMDPModels.SimpleGridWorld: size, rewards, terminate_from, tprob, discount."""
+
+    size: Tuple[int, int] = (10, 10)
+    rewards: Dict[Tuple[int, int], float] = field(default_factory=lambda: dict(_DEFAULT_REWARDS))
+    terminate_from: Optional[Set[Tuple[int, int]]] = None  # default: the reward cells
+    tprob: float = 0.7
+    discount: float = 0.95
+
+    name = "SimpleGridWorld"
+    mdp_id = abi.MDP_GRIDWORLD
+    actions: Tuple[str, ...] = ("up", "down", "left", "right")
+    state_dtype = np.int64
+    state_width = 2
+    dense = True
+
+    def __post_init__(self):
+        if self.terminate_from is None:
+            self.terminate_from = set(self.rewards.keys())
+
+    # -- POMDPs.jl-style accessors used by host code --
+    def isterminal(self, s) -> bool:
+        return s[0] < 0 or s[1] < 0
+
+    def n_states(self) -> int:
+        return self.size[0] * self.size[1] + 1
+
+    def state_index(self, s) -> int:
+        if self.isterminal(s):
+            return self.size[0] * self.size[1]
+        return (s[0] - 1) + (s[1] - 1) * self.size[0]
+
+    def state_from_index(self, i: int) -> Tuple[int, int]:
+        if i == self.size[0] * self.size[1]:
+            return (-1, -1)
+        return (i % self.size[0] + 1, i // self.size[0] + 1)
+
+    def states(self) -> Iterable[Tuple[int, int]]:
+        return (self.state_from_index(i) for i in range(self.n_states()))
+
+    def action_index(self, a) -> int:
+        return self.actions.index(a)
+
+    def encode_states(self, states: Sequence) -> np.ndarray:
+        arr = np.asarray(states, dtype=np.int64).reshape(-1, 2)
+        return np.ascontiguousarray(arr)
+
+    def decode_state(self, row) -> Tuple[int, int]:
+        return (int(row[0]), int(row[1]))
+
+    def params(self) -> abi.GridWorldParams:
+        p = abi.GridWorldParams()
+        p.nx, p.ny = int(self.size[0]), int(self.size[1])
+        p.tprob, p.discount = float(self.tprob), float(self.discount)
+        if len(self.rewards) > abi.GW_MAX_SPECIAL or len(self.terminate_from) > abi.GW_MAX_SPECIAL:
+            raise ValueError(f"at most {abi.GW_MAX_SPECIAL} reward / terminate_from cells are supported")
+        p.n_rewards = len(self.rewards)
+        for i, ((x, y), v) in enumerate(self.rewards.items()):
+            p.reward_x[i], p.reward_y[i], p.reward_v[i] = int(x), int(y), float(v)
+        p.n_terminate = len(self.terminate_from)
+        for i, (x, y) in enumerate(sorted(self.terminate_from)):
+            p.term_x[i], p.term_y[i] = int(x), int(y)
+        return p
+
+
+@dataclass
+class MountainCar:
+    """POMDPModels.MountainCar: state (x, v), actions [-1., 0., 1.]."""
+
+    discount: float = 0.99
+    cost: float = -1.0
+    jackpot: float = 100.0
+
+    name = "MountainCar"
+    mdp_id = abi.MDP_MOUNTAINCAR
+    actions: Tuple[float, ...] = (-1.0, 0.0, 1.0)
+    state_dtype = np.float64
+    state_width = 2
+    dense = False
+
+    def isterminal(self, s) -> bool:
+        return s[0] >= 0.5
+
+    def action_index(self, a) -> int:
+        return self.actions.index(float(a))
+
+    def encode_states(self, states: Sequence) -> np.ndarray:
+        return np.ascontiguousarray(np.asarray(states, dtype=np.float64).reshape(-1, 2))
+
+    def decode_state(self, row) -> Tuple[float, float]:
+        return (float(row[0]), float(row[1]))
+
+    def params(self) -> abi.MountainCarParams:
+        return abi.MountainCarParams(float(self.discount), float(self.cost), float(self.jackpot))

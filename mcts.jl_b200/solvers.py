@@ -1,0 +1,459 @@
+"""Host mirror of MCTS.jl's public API for the hot path, on top of the C ABI.
+
+This is what the Julia glue (mcts.jl_b200/julia/MCTSB200.jl) does in Julia, written in Python because
+Julia is not installed in the build image: solver structs with the reference's field names and
+defaults (src/vanilla.jl:28-62, src/dpw_types.jl:45-100), `solve` (src/vanilla.jl:152, src/dpw.jl:1),
+`action` / `action_info` (src/vanilla.jl:158-164, src/dpw.jl:13-74), `value` (src/vanilla.jl:169-197),
+`clear_tree!` (src/vanilla.jl:148, src/dpw.jl:6-8), `ranked_actions` (src/util.jl:8-24), the
+`default_action` handling around the DPW search (src/dpw.jl:68-71, src/default_action.jl) -- plus the
+batch extension `action_batch` / `action_info_batch` (one tree per root state, all on the device).
+
+Everything that iterates (the bodies of build_tree and of the DPW search block) happens inside
+`mctsb200_plan`; nothing here computes a search step on the host.
+"""
+from __future__ import annotations
+
+import math
+import time
+import warnings
+from dataclasses import dataclass, field
+from typing import Any, Callable, Optional, Sequence
+
+import numpy as np
+
+from . import _abi as abi
+from ._lib import Context, MCTSB200Error
+
+_INF = float("inf")
+
+
+# ----------------------------------------------------------------------------------------------
+# rollout policies / estimators (src/domain_knowledge.jl:27-57)
+# ----------------------------------------------------------------------------------------------
+class RandomSolver:
+    """POMDPTools.RandomSolver: solve() gives a RandomPolicy."""
+
+
+class RandomPolicy:
+    """POMDPTools.RandomPolicy: rand(rng, actions(mdp, s))."""
+
+
+@dataclass
+class ConstantPolicy:
+    """FunctionPolicy(s -> a) for a fixed action `a` (e.g. `RolloutEstimator(x->:up)`, test/options.jl:29)."""
+
+    action: Any
+
+
+@dataclass
+class SeekTarget:
+    """notebooks/Domain_Knowledge_Example.ipynb cell 12-13: move towards `target` (x first, then y)."""
+
+    target: tuple
+
+
+class EnergyPolicy:
+    """MountainCar heuristic: accelerate in the direction of motion (v < 0 ? -1 : +1)."""
+
+
+@dataclass
+class RolloutEstimator:
+    """src/domain_knowledge.jl:27-37."""
+
+    solver: Any = field(default_factory=RandomSolver)
+    max_depth: int = 50
+    eps: float = 0.0
+
+
+class ExceptionRethrow:
+    """src/default_action.jl: rethrow the search exception (the DPWSolver default)."""
+
+
+# ----------------------------------------------------------------------------------------------
+# solver structs
+# ----------------------------------------------------------------------------------------------
+def _seed_of(rng) -> int:
+    if rng is None:
+        return 0
+    if isinstance(rng, (int, np.integer)):
+        return int(rng) & 0xFFFFFFFFFFFFFFFF
+    if isinstance(rng, np.random.Generator):
+        return int(rng.integers(0, 2**63 - 1))
+    raise TypeError(f"rng must be an int seed or numpy Generator, got {type(rng).__name__}")
+
+
+@dataclass
+class MCTSSolver:
+    """Mirror of MCTSSolver (src/vanilla.jl:28-62); same keyword names and defaults."""
+
+    n_iterations: int = 100
+    max_time: float = _INF
+    depth: int = 10
+    exploration_constant: float = 1.0
+    rng: Any = None
+    estimate_value: Any = field(default_factory=RolloutEstimator)
+    init_Q: Any = 0.0
+    init_N: Any = 0
+    reuse_tree: bool = False
+    enable_tree_vis: bool = False
+    timer: Optional[Callable] = None
+    callback: Optional[Callable] = None
+    # device extensions (not in the reference)
+    rollouts_per_leaf: int = 1
+    lanes_per_tree: int = 0
+
+
+@dataclass
+class DPWSolver:
+    """Mirror of DPWSolver (src/dpw_types.jl:45-100); same keyword names and defaults."""
+
+    depth: int = 10
+    exploration_constant: float = 1.0
+    n_iterations: int = 100
+    max_time: float = _INF
+    k_action: float = 10.0
+    alpha_action: float = 0.5
+    k_state: float = 10.0
+    alpha_state: float = 0.5
+    keep_tree: bool = False
+    enable_action_pw: bool = True
+    enable_state_pw: bool = True
+    check_repeat_state: bool = True
+    check_repeat_action: bool = True
+    tree_in_info: bool = False
+    rng: Any = None
+    estimate_value: Any = field(default_factory=RolloutEstimator)
+    init_Q: Any = 0.0
+    init_N: Any = 0
+    next_action: Any = None  # None = RandomActionGenerator(rng)
+    default_action: Any = field(default_factory=ExceptionRethrow)
+    reset_callback: Optional[Callable] = None
+    show_progress: bool = False
+    timer: Optional[Callable] = None
+    rollouts_per_leaf: int = 1
+    lanes_per_tree: int = 0
+
+
+def _unsupported(what: str) -> MCTSB200Error:
+    return MCTSB200Error(abi.ERR_UNSUPPORTED, f"{what} cannot run on the device and there is no CPU fallback")
+
+
+def _tabulate(f: Callable, mdp, per_action: bool, dtype) -> np.ndarray:
+    """Evaluate a pure host function over the dense state space once (device-expressible stand-in for the
+    Function/object forms of init_Q / init_N / estimate_value, src/domain_knowledge.jl:9,81,90)."""
+    n = mdp.n_states()
+    if per_action:
+        out = np.zeros((n, len(mdp.actions)), dtype=dtype)
+        for i in range(n):
+            s = mdp.state_from_index(i)
+            for j, a in enumerate(mdp.actions):
+                out[i, j] = f(mdp, s, a)
+    else:
+        out = np.zeros(n, dtype=dtype)
+        for i in range(n):
+            out[i] = f(mdp, mdp.state_from_index(i), 0)
+    return np.ascontiguousarray(out)
+
+
+def build_cfg(solver, mdp) -> tuple[abi.SolverCfg, list]:
+    """Flatten a solver struct into mctsb200_solver_cfg; raises for options that need host closures.
+    Returns (cfg, keepalive) where keepalive holds the numpy tables the cfg points into."""
+    import ctypes as C
+
+    cfg = abi.SolverCfg()
+    keep: list = []
+    cfg.struct_size = C.sizeof(abi.SolverCfg)
+    is_dpw = isinstance(solver, DPWSolver)
+    cfg.kind = abi.KIND_DPW if is_dpw else abi.KIND_UCT
+    for name in ("n_iterations", "depth"):
+        if not isinstance(getattr(solver, name), (int, np.integer)):
+            raise TypeError(f"{name} must be an Int")
+    cfg.n_iterations = int(solver.n_iterations)
+    cfg.depth = int(solver.depth)
+    cfg.exploration_constant = float(solver.exploration_constant)
+    cfg.max_time = float(solver.max_time)
+    cfg.rollouts_per_leaf = int(solver.rollouts_per_leaf)
+    cfg.lanes_per_tree = int(solver.lanes_per_tree)
+    cfg.seed = _seed_of(solver.rng)
+
+    # host callbacks have no device form
+    if solver.timer is not None:
+        raise _unsupported("a custom `timer`")
+    if not is_dpw and solver.callback is not None:
+        raise _unsupported("a per-iteration `callback`")
+    if is_dpw:
+        if solver.reset_callback is not None:
+            raise _unsupported("`reset_callback`")
+        if solver.show_progress:
+            raise _unsupported("`show_progress`")
+        if solver.next_action is not None:
+            raise _unsupported("a custom `next_action` (only RandomActionGenerator)")
+        cfg.k_action, cfg.alpha_action = float(solver.k_action), float(solver.alpha_action)
+        cfg.k_state, cfg.alpha_state = float(solver.k_state), float(solver.alpha_state)
+        cfg.enable_action_pw = int(bool(solver.enable_action_pw))
+        cfg.enable_state_pw = int(bool(solver.enable_state_pw))
+        cfg.check_repeat_state = int(bool(solver.check_repeat_state))
+        cfg.check_repeat_action = int(bool(solver.check_repeat_action))
+        cfg.keep_tree = int(bool(solver.keep_tree))
+    else:
+        cfg.keep_tree = int(bool(solver.reuse_tree))
+        if solver.enable_tree_vis:
+            raise _unsupported("`enable_tree_vis` (_vis_stats recording)")
+
+    # init_Q / init_N: Number, ndarray table, or (dense MDPs) a pure function tabulated once
+    def table_or_const(val, name, dtype, ctype):
+        if isinstance(val, bool) or isinstance(val, str):
+            raise TypeError(f"no method matching {name}(::{type(val).__name__}, ...)")  # MethodError parity (test/options.jl:18)
+        if isinstance(val, (int, float, np.integer, np.floating)):
+            return val, None
+        if isinstance(val, np.ndarray) or callable(val):
+            if not mdp.dense:
+                raise _unsupported(f"a table/function-valued `{name}` on a non-dense MDP")
+            tab = val if isinstance(val, np.ndarray) else _tabulate(val, mdp, True, dtype)
+            tab = np.ascontiguousarray(tab, dtype=dtype).reshape(mdp.n_states(), len(mdp.actions))
+            keep.append(tab)
+            return None, tab.ctypes.data_as(C.POINTER(ctype))
+        raise TypeError(f"no method matching {name}(::{type(val).__name__}, ...)")
+
+    qc, qt = table_or_const(solver.init_Q, "init_Q", np.float64, C.c_double)
+    nc, nt = table_or_const(solver.init_N, "init_N", np.int64, C.c_int64)
+    cfg.init_Q = float(qc) if qc is not None else 0.0
+    if nc is not None and int(nc) != nc:
+        raise TypeError("init_N must be an Int (InexactError)")
+    cfg.init_N = int(nc) if nc is not None else 0
+    if qt is not None:
+        cfg.init_q_table = qt
+    if nt is not None:
+        cfg.init_n_table = nt
+
+    ev = solver.estimate_value
+    cfg.rollout_max_depth = 50
+    if isinstance(ev, bool) or isinstance(ev, str):
+        raise TypeError(f"no method matching estimate_value(::{type(ev).__name__}, ...)")
+    if isinstance(ev, (int, float, np.integer, np.floating)):
+        cfg.estimate_kind = abi.EST_CONSTANT
+        cfg.estimate_const = float(ev)
+    elif isinstance(ev, RolloutEstimator):
+        cfg.estimate_kind = abi.EST_ROLLOUT
+        cfg.rollout_max_depth = int(ev.max_depth)
+        cfg.rollout_eps = float(ev.eps)
+        pol = ev.solver
+        if isinstance(pol, type):
+            pol = pol()
+        if isinstance(pol, (RandomSolver, RandomPolicy)):
+            cfg.rollout_policy = abi.POLICY_RANDOM
+        elif isinstance(pol, ConstantPolicy):
+            cfg.rollout_policy = abi.POLICY_CONSTANT
+            cfg.rollout_policy_param[0] = mdp.action_index(pol.action)
+        elif isinstance(pol, SeekTarget):
+            cfg.rollout_policy = abi.POLICY_GW_SEEK
+            cfg.rollout_policy_param[0], cfg.rollout_policy_param[1] = int(pol.target[0]), int(pol.target[1])
+        elif isinstance(pol, EnergyPolicy):
+            cfg.rollout_policy = abi.POLICY_MC_ENERGY
+        elif callable(pol):
+            raise _unsupported("a Function-valued rollout policy (use ConstantPolicy / SeekTarget / EnergyPolicy)")
+        else:
+            raise TypeError(f"RolloutEstimator: unsupported policy {type(pol).__name__}")
+    elif isinstance(ev, np.ndarray) or callable(ev):
+        if not mdp.dense:
+            raise _unsupported("a table/function-valued `estimate_value` on a non-dense MDP")
+        tab = ev if isinstance(ev, np.ndarray) else _tabulate(lambda m, s, _a: ev(m, s, 0), mdp, False, np.float64)
+        tab = np.ascontiguousarray(tab, dtype=np.float64).reshape(mdp.n_states())
+        keep.append(tab)
+        cfg.estimate_kind = abi.EST_TABLE
+        cfg.value_table = tab.ctypes.data_as(C.POINTER(C.c_double))
+    else:
+        raise TypeError(f"no method matching estimate_value(::{type(ev).__name__}, ...)")
+    return cfg, keep
+
+
+# ----------------------------------------------------------------------------------------------
+# tree views
+# ----------------------------------------------------------------------------------------------
+class TreeView:
+    """info[:tree]: the arrays of MCTSTree (src/vanilla.jl:64-94) / DPWTree (src/dpw_types.jl:123-159),
+    exported from the device on first access. Node ids are 1-based like in Julia."""
+
+    def __init__(self, planner, root_i: int):
+        self._planner, self._root_i, self._data = planner, root_i, None
+
+    def _load(self) -> dict:
+        if self._data is None:
+            m = self._planner.mdp
+            self._data = self._planner.ctx.tree_export(self._root_i, m.state_dtype, m.state_width)
+        return self._data
+
+    def __getattr__(self, name):
+        d = self._load()
+        if name in d:
+            return d[name]
+        raise AttributeError(name)
+
+    @property
+    def state_map(self) -> dict:
+        """state => state-node id (first occurrence; DPW without check_repeat_state may repeat states)."""
+        d = self._load()
+        m = self._planner.mdp
+        out = {}
+        for i, row in enumerate(d["s_labels"]):
+            out.setdefault(m.decode_state(row), i + 1)
+        return out
+
+    s_lookup = state_map
+
+    def children(self, snode: int) -> np.ndarray:
+        d = self._load()
+        return d["child_ids"][d["child_offsets"][snode - 1]:d["child_offsets"][snode]]
+
+
+# ----------------------------------------------------------------------------------------------
+# planners
+# ----------------------------------------------------------------------------------------------
+class _Planner:
+    def __init__(self, solver, mdp, ctx: Optional[Context] = None, device: int = 0):
+        self.solver, self.mdp = solver, mdp
+        self.ctx = ctx if ctx is not None else Context(device)
+        self.ctx.configure(mdp.mdp_id, mdp.params())
+        self.tree = None
+        self._roots = None
+        self._calls = 0
+        self.last_stats = None
+
+    # one plan call over a batch of root states
+    def _plan(self, states: Sequence, root_index_base: int = 0, want_status: bool = False):
+        cfg, keep = build_cfg(self.solver, self.mdp)
+        cfg.seed = (cfg.seed + self._calls) & 0xFFFFFFFFFFFFFFFF  # successive calls see fresh randomness
+        self.ctx.configure(self.mdp.mdp_id, self.mdp.params())
+        roots = self.mdp.encode_states(states)
+        actions, best_q, status, stats = self.ctx.plan(cfg, self.mdp.mdp_id, roots, root_index_base, want_status)
+        del keep
+        self._calls += 1
+        self._roots = [self.mdp.decode_state(r) for r in roots]
+        self.last_stats = stats
+        return actions, best_q, status, stats
+
+    def _label(self, idx: int):
+        return self.mdp.actions[int(idx)]
+
+    def clear_tree(self):
+        """clear_tree!(planner)"""
+        self.tree = None
+        self._roots = None
+        self.ctx.clear_trees()
+
+    def ranked_actions(self, state):
+        """src/util.jl:8-24: children of the root sorted by Q, best first -> [(action, Q)]."""
+        i = self._root_index(state)
+        rs = self.ctx.root_stats(i, len(self.mdp.actions))
+        order = sorted(range(len(rs["q"])), key=lambda j: -rs["q"][j])
+        return [(self._label(rs["action_idx"][j]), float(rs["q"][j])) for j in order]
+
+    def _root_index(self, state) -> int:
+        if self._roots is None:
+            self.action(state)
+        st = self.mdp.decode_state(self.mdp.encode_states([state])[0])
+        try:
+            return self._roots.index(st)
+        except ValueError:
+            raise KeyError(f"State {state} was not a root of the last plan call.")
+
+
+class MCTSPlanner(_Planner):
+    """solve(::MCTSSolver, mdp) (src/vanilla.jl:137-152)."""
+
+    def action_info_batch(self, states: Sequence, root_index_base: int = 0):
+        actions, best_q, _, stats = self._plan(states, root_index_base)
+        infos = [{"tree": TreeView(self, i), "best_Q": float(best_q[i])} for i in range(len(actions))]
+        self.tree = infos[0]["tree"] if infos else None
+        return [self._label(a) for a in actions], infos
+
+    def action_batch(self, states: Sequence):
+        return self.action_info_batch(states)[0]
+
+    def action_info(self, state):
+        acts, infos = self.action_info_batch([state])
+        return acts[0], infos[0]
+
+    def action(self, state):
+        return self.action_info(state)[0]
+
+    def value(self, state, a=None):
+        """value(planner, s[, a]) (src/vanilla.jl:169-197)."""
+        if self.tree is None:
+            self.action(state)
+        tree = self.tree
+        sid = tree.state_map.get(self.mdp.decode_state(self.mdp.encode_states([state])[0]), 0)
+        if sid == 0:
+            raise KeyError(f"State {state} not present in MCTS tree.")
+        ch = tree.children(sid)
+        if a is None:
+            return float(max(tree.q[c - 1] for c in ch))
+        ai = self.mdp.action_index(a)
+        for c in ch:
+            if tree.a_labels[c - 1] == ai:
+                return float(tree.q[c - 1])
+        return None
+
+
+class DPWPlanner(_Planner):
+    """solve(::DPWSolver, mdp) (src/dpw_types.jl:211-227, src/dpw.jl:1)."""
+
+    def action_info_batch(self, states: Sequence, tree_in_info: bool = False, root_index_base: int = 0):
+        t0 = time.perf_counter()
+        infos = []
+        try:
+            for s in states:
+                if self.mdp.isterminal(s):
+                    raise MCTSB200Error(abi.ERR_TERMINAL_ROOT, f"MCTS cannot handle terminal states. action was called with\ns = {s}")
+            actions, best_q, _, stats = self._plan(states, root_index_base)
+            dt = time.perf_counter() - t0
+            out = []
+            for i, a in enumerate(actions):
+                info = {"search_time": dt, "search_time_us": dt * 1e6, "tree_queries": int(stats.iterations_done), "best_Q": float(best_q[i])}
+                if self.solver.tree_in_info or tree_in_info:
+                    info["tree"] = TreeView(self, i)
+                infos.append(info)
+                out.append(self._label(a))
+            self.tree = TreeView(self, 0)
+            return out, infos
+        except MCTSB200Error as ex:
+            # src/dpw.jl:68-71 + src/default_action.jl
+            da = self.solver.default_action
+            if isinstance(da, ExceptionRethrow):
+                raise
+            out = []
+            for s in states:
+                a = da(self.mdp, s, ex) if callable(da) else da
+                warnings.warn(f"Using default action {a} because of the following error:\n{ex}")
+                out.append(a)
+                infos.append({"exception": ex})
+            return out, infos
+
+    def action_batch(self, states: Sequence):
+        return self.action_info_batch(states)[0]
+
+    def action_info(self, state, tree_in_info: bool = False):
+        acts, infos = self.action_info_batch([state], tree_in_info=tree_in_info)
+        return acts[0], infos[0]
+
+    def action(self, state):
+        return self.action_info(state)[0]
+
+
+def solve(solver, mdp, ctx: Optional[Context] = None, device: int = 0):
+    """POMDPs.solve: no computation, just binds solver and model (src/vanilla.jl:151-152)."""
+    if isinstance(solver, DPWSolver):
+        build_cfg(solver, mdp)  # reject unsupported options up front
+        return DPWPlanner(solver, mdp, ctx, device)
+    if isinstance(solver, MCTSSolver):
+        build_cfg(solver, mdp)
+        return MCTSPlanner(solver, mdp, ctx, device)
+    raise TypeError(f"solve: unknown solver type {type(solver).__name__}")
+
+
+def clear_tree(planner: _Planner) -> None:
+    planner.clear_tree()
+
+
+def ranked_actions(planner: _Planner, state):
+    return planner.ranked_actions(state)

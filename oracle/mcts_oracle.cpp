@@ -1,0 +1,1037 @@
+// mcts_oracle.cpp -- CPU restatement of MCTS.jl's search loop.  TEST INFRASTRUCTURE ONLY.
+//
+// Nothing in the product path (libmctsb200.so, mcts.jl_b200/) may link, import or execute this file.
+// It exists so that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// leg can check and time the CUDA path against an independent statement of the reference algorithm.
+//
+// It deliberately keeps the reference's own shape -- recursive simulate, Vector-of-Vectors trees,
+// Dict/Set lookups, 1-based node ids -- so each function can be read against the Julia it follows
+// (paths relative to /root/reference):
+//   VanillaPlanner::build_tree        src/vanilla.jl:209-237
+//   VanillaPlanner::simulate          src/vanilla.jl:240-276
+//   VanillaPlanner::insert_node       src/vanilla.jl:292-307
+//   VanillaPlanner::best_sanode_UCB   src/vanilla.jl:354-386
+//   VanillaPlanner::best_sanode_Q     src/vanilla.jl:339-349
+//   DPWPlanner::action_info           src/dpw.jl:18-74
+//   DPWPlanner::simulate              src/dpw.jl:80-154
+//   DPWPlanner::best_sanode           src/dpw.jl:163-173
+//   DPWPlanner::best_sanode_UCB       src/dpw.jl:179-199
+//   DPWTree / insert_state_node / insert_action_node   src/dpw_types.jl:123-186
+//   Estimator::estimate_value         src/domain_knowledge.jl:10,65-73
+//   init_Q / init_N                   src/domain_knowledge.jl:80-91
+//   next_action                       src/action_gen.jl:11-13
+//
+// Third-party arithmetic that is NOT under /root/reference (Project.toml:6-27 lists the packages,
+// no Manifest.toml pins them) is restated from the published sources of
+//   POMDPTools.jl  (compat "0.1, 1"):  RolloutSimulator loop, RandomPolicy, FunctionPolicy, SparseCat sampling
+//   POMDPModels.jl (compat "0.4"):     SimpleGridWorld, MountainCar
+// and anchored on the reference's call sites (src/domain_knowledge.jl:71-72, src/vanilla.jl:258,
+// src/dpw.jl:122) and stored notebook outputs (tests/test_oracle_golden.py).
+//
+// Parity status: the search-loop arithmetic is pinned by the golden vectors of SURVEY.md 8(c)
+// (notebook Q/N values, DAG/self-loop invariants, root id, VI action table).  No reference test pins
+// a full seeded search bit-for-bit (they all depend on Julia's MersenneTwister), and Julia is not
+// available in the build image, so stochastic parity with Julia is statistical; MountainCar parity is
+// UNPINNED by the reference (the model is never imported by it).
+//
+// Deliberate, documented deviations from a literal Julia run:
+//   * RNG: counter-based Philox4x32-10 streams (include/mctsb200.h "Random-number contract").
+//   * log/cos: include/mctsb200_detmath.h (Julia's are not correctly rounded either; see that header).
+//     Build with -DORACLE_LIBM to use glibc's instead (used by a test that shows actions agree).
+//   * transitions[sanode] sampling has two modes: literal (vector indexed by push order, the default
+//     restatement of src/dpw.jl:131,140) and multiset (distinct (spnode,r) records with counts,
+//     sampled by cumulative count in first-occurrence order) -- distribution-identical;
+//     the device uses the multiset form.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../include/mctsb200.h"
+#include "../include/mctsb200_detmath.h"
+
+namespace oracle {
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) and the stream contract of include/mctsb200.h
+// ---------------------------------------------------------------------------------------------
+static inline void philox4x32_10(const uint32_t key_in[2], const uint32_t ctr_in[4], uint32_t out[4]) {
+    uint32_t k0 = key_in[0], k1 = key_in[1];
+    uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct Stream {
+    uint32_t key[2];
+    uint32_t ctr[4];
+    uint32_t buf[4];
+    int have = 0;  // unread words left in buf
+    Stream(uint64_t seed, uint64_t tree, uint32_t iteration, uint32_t stream_id) {
+        key[0] = (uint32_t)seed;
+        key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = 0;
+        ctr[1] = iteration;
+        ctr[2] = (uint32_t)tree;
+        ctr[3] = (uint32_t)(((tree >> 32) & 0xffffu) << 16) | (stream_id & 0xffffu);
+    }
+    uint32_t next() {
+        if (have == 0) {
+            philox4x32_10(key, ctr, buf);
+            ctr[0] += 1;
+            have = 4;
+        }
+        const uint32_t w = buf[4 - have];
+        --have;
+        return w;
+    }
+    int uniform_int(int n) { return (int)(((uint64_t)next() * (uint64_t)n) >> 32); }
+    double uniform01() { return (double)next() * (1.0 / 4294967296.0); }
+};
+
+static inline double o_log(double x) {
+#ifdef ORACLE_LIBM
+    return std::log(x);
+#else
+    return det_log(x);
+#endif
+}
+static inline double o_cos(double x) {
+#ifdef ORACLE_LIBM
+    return std::cos(x);
+#else
+    return det_cos(x);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Models (POMDPModels.jl restatements)
+// ---------------------------------------------------------------------------------------------
+struct GWPos {
+    int64_t x, y;
+    bool operator==(const GWPos& o) const { return x == o.x && y == o.y; }
+    bool operator<(const GWPos& o) const { return x != o.x ? x < o.x : y < o.y; }
+};
+struct GWPosHash {
+    size_t operator()(const GWPos& s) const { return std::hash<int64_t>()(s.x * 1000003 + s.y); }
+};
+
+// SimpleGridWorld: actions (:up,:down,:left,:right); dir up(0,1) down(0,-1) left(-1,0) right(1,0).
+struct GridWorld {
+    using State = GWPos;
+    static constexpr int kActions = 4;
+    int nx = 10, ny = 10;
+    double tprob = 0.7, gamma = 0.95;
+    std::map<GWPos, double> rewards;
+    std::set<GWPos> terminate_from;
+
+    explicit GridWorld(const mctsb200_gridworld_params& p) : nx(p.nx), ny(p.ny), tprob(p.tprob), gamma(p.discount) {
+        for (int i = 0; i < p.n_rewards; ++i) rewards[GWPos{p.reward_x[i], p.reward_y[i]}] = p.reward_v[i];
+        for (int i = 0; i < p.n_terminate; ++i) terminate_from.insert(GWPos{p.term_x[i], p.term_y[i]});
+    }
+    double discount() const { return gamma; }
+    int n_actions(const State&) const { return kActions; }
+    bool isterminal(const State& s) const { return s.x < 0 || s.y < 0; }  // any(x->x<0, s)
+    bool inbounds(const State& s) const { return 1 <= s.x && s.x <= nx && 1 <= s.y && s.y <= ny; }
+    double reward(const State& s) const {  // reward(mdp, s, a) = get(mdp.rewards, s, 0.0)
+        auto it = rewards.find(s);
+        return it == rewards.end() ? 0.0 : it->second;
+    }
+    // dense index used only for the optional init/value tables: cells row-major in x, terminal last
+    int64_t state_index(const State& s) const { return isterminal(s) ? (int64_t)nx * ny : (s.x - 1) + (s.y - 1) * (int64_t)nx; }
+    int64_t n_states() const { return (int64_t)nx * ny + 1; }
+
+    // transition(mdp, s, a) followed by rand(rng, dist); reward from the source state.
+    void gen(const State& s, int a, Stream& rng, State& sp, double& r) const {
+        r = reward(s);
+        if (terminate_from.count(s) || isterminal(s)) {  // Deterministic(GWPos(-1,-1)): no draw
+            sp = GWPos{-1, -1};
+            return;
+        }
+        static const int dx[4] = {0, 0, -1, 1}, dy[4] = {1, -1, 0, 0};
+        State destinations[5];
+        double probs[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        destinations[0] = s;
+        for (int i = 0; i < 4; ++i) {
+            double prob;
+            if (i == a) prob = tprob;
+            else prob = (1.0 - tprob) / (double)(kActions - 1);
+            State dest{s.x + dx[i], s.y + dy[i]};
+            destinations[i + 1] = dest;
+            if (!inbounds(dest)) {  // hit an edge and come back
+                probs[0] += prob;
+                destinations[i + 1] = GWPos{-1, -1};
+            } else {
+                probs[i + 1] += prob;
+            }
+        }
+        // rand(rng, ::SparseCat): r = sum(probs)*rand(rng); first index with r < running total
+        double total = 0.0;
+        for (int i = 0; i < 5; ++i) total += probs[i];
+        const double u = total * rng.uniform01();
+        double tot = 0.0;
+        for (int i = 0; i < 5; ++i) {
+            tot += probs[i];
+            if (u < tot) {
+                sp = destinations[i];
+                return;
+            }
+        }
+        sp = destinations[4];  // unreachable for u < 1 (Julia raises an error here)
+    }
+};
+
+struct MCState {
+    double x, v;
+    // isequal semantics on Float64 pairs: bitwise (so -0.0 != 0.0, NaN == NaN)
+    bool operator==(const MCState& o) const { return dm_bits(x) == dm_bits(o.x) && dm_bits(v) == dm_bits(o.v); }
+};
+struct MCStateHash {
+    size_t operator()(const MCState& s) const { return std::hash<uint64_t>()(dm_bits(s.x) * 0x9E3779B97F4A7C15ull ^ dm_bits(s.v)); }
+};
+
+// MountainCar: actions [-1., 0., 1.]; gen is deterministic.
+struct MountainCar {
+    using State = MCState;
+    static constexpr int kActions = 3;
+    double gamma, cost, jackpot;
+    explicit MountainCar(const mctsb200_mountaincar_params& p) : gamma(p.discount), cost(p.cost), jackpot(p.jackpot) {}
+    double discount() const { return gamma; }
+    int n_actions(const State&) const { return kActions; }
+    bool isterminal(const State& s) const { return s.x >= 0.5; }
+    int64_t state_index(const State&) const { return -1; }
+    int64_t n_states() const { return 0; }
+    void gen(const State& s, int ai, Stream&, State& sp, double& r) const {
+        const double a = (double)(ai - 1);
+        // v_ = v + a*0.001 + cos(3*x)*-0.0025
+        double v_ = (s.v + a * 0.001) + o_cos(3.0 * s.x) * -0.0025;
+        v_ = std::max(std::min(0.07, v_), -0.07);
+        double x_ = s.x + v_;
+        if (x_ < -1.2) {  // inelastic boundary
+            x_ = -1.2;
+            v_ = 0.0;
+        }
+        sp = MCState{x_, v_};
+        r = isterminal(sp) ? jackpot : cost;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Work counters (same definitions as mctsb200_plan_stats)
+// ---------------------------------------------------------------------------------------------
+struct Counters {
+    int64_t n_simulations = 0, n_tree_levels = 0, n_dpw_children_seen = 0, n_state_inserts = 0, n_action_inserts = 0,
+            n_rollouts = 0, n_rollout_steps = 0, n_transition_samples = 0;
+    void add(const Counters& o) {
+        n_simulations += o.n_simulations; n_tree_levels += o.n_tree_levels; n_dpw_children_seen += o.n_dpw_children_seen;
+        n_state_inserts += o.n_state_inserts; n_action_inserts += o.n_action_inserts; n_rollouts += o.n_rollouts;
+        n_rollout_steps += o.n_rollout_steps; n_transition_samples += o.n_transition_samples;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Leaf evaluation and node initialisers
+// ---------------------------------------------------------------------------------------------
+template <class M>
+struct Hooks {
+    const M& mdp;
+    const mctsb200_solver_cfg& cfg;
+    uint64_t tree_index;
+    uint32_t iteration = 0;
+    Counters* cnt;
+
+    // action(policy, s) for the rollout policy
+    int policy_action(const typename M::State& s, Stream& rng) const {
+        switch (cfg.rollout_policy) {
+            case MCTSB200_POLICY_RANDOM:  // rand(rng, actions(problem, s))
+                return rng.uniform_int(mdp.n_actions(s));
+            case MCTSB200_POLICY_CONSTANT:
+                return cfg.rollout_policy_param[0];
+            case MCTSB200_POLICY_GW_SEEK: {  // notebooks/Domain_Knowledge_Example.ipynb cell 13
+                const int64_t tx = cfg.rollout_policy_param[0], ty = cfg.rollout_policy_param[1];
+                const int64_t sx = state_x(s), sy = state_y(s);
+                if (tx > sx) return 3;       // :right
+                else if (tx < sx) return 2;  // :left
+                else if (ty > sy) return 0;  // :up
+                else return 1;               // :down
+            }
+            case MCTSB200_POLICY_MC_ENERGY:
+                return state_v(s) < 0.0 ? 0 : 2;
+        }
+        return 0;
+    }
+    static int64_t state_x(const GWPos& s) { return s.x; }
+    static int64_t state_y(const GWPos& s) { return s.y; }
+    static int64_t state_x(const MCState&) { return 0; }
+    static int64_t state_y(const MCState&) { return 0; }
+    static double state_v(const GWPos&) { return 0.0; }
+    static double state_v(const MCState& s) { return s.v; }
+
+    // POMDPTools simulate(::RolloutSimulator, mdp, policy, s0)
+    double rollout(typename M::State s, int64_t max_steps, Stream& rng) const {
+        const double eps = cfg.rollout_eps;
+        double disc = 1.0;
+        double r_total = 0.0;
+        int64_t step = 1;
+        while (disc > eps && !mdp.isterminal(s) && step <= max_steps) {
+            const int a = policy_action(s, rng);
+            typename M::State sp;
+            double r;
+            mdp.gen(s, a, rng, sp, r);
+            r_total += disc * r;
+            s = sp;
+            disc *= mdp.discount();
+            step += 1;
+            cnt->n_rollout_steps += 1;
+        }
+        return r_total;
+    }
+
+    // estimate_value(estimator, mdp, state, remaining_depth)
+    double estimate_value(const typename M::State& s, int64_t remaining_depth) const {
+        switch (cfg.estimate_kind) {
+            case MCTSB200_EST_CONSTANT:
+                return cfg.estimate_const;  // convert(Float64, estimator): also for terminal states
+            case MCTSB200_EST_TABLE:
+                return cfg.value_table[mdp.state_index(s)];
+            default: {
+                const int64_t max_steps = cfg.rollout_max_depth == -1 ? remaining_depth : cfg.rollout_max_depth;
+                const int K = cfg.rollouts_per_leaf < 1 ? 1 : cfg.rollouts_per_leaf;
+                double sum = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    Stream rs(cfg.seed, tree_index, iteration, 1u + (uint32_t)k);
+                    const double v = rollout(s, max_steps, rs);
+                    cnt->n_rollouts += 1;
+                    if (K == 1) return v;
+                    sum += v;
+                }
+                return sum / (double)K;
+            }
+        }
+    }
+    double init_Q(const typename M::State& s, int a) const {
+        if (cfg.init_q_table) return cfg.init_q_table[mdp.state_index(s) * M::kActions + a];
+        return cfg.init_Q;
+    }
+    int64_t init_N(const typename M::State& s, int a) const {
+        if (cfg.init_n_table) return cfg.init_n_table[mdp.state_index(s) * M::kActions + a];
+        return cfg.init_N;
+    }
+};
+
+// Export container shared by both planners (mirrors mctsb200_tree_buffers)
+struct ExportedTree {
+    int64_t state_bytes = 0;
+    std::vector<int64_t> total_n;
+    std::vector<uint8_t> s_labels;
+    std::vector<int64_t> child_offsets, child_ids;
+    std::vector<int64_t> n;
+    std::vector<double> q;
+    std::vector<int32_t> a_labels;
+    std::vector<int64_t> n_a_children, trans_offsets, trans_spnode, trans_count;
+    std::vector<double> trans_r;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Vanilla UCT  (src/vanilla.jl)
+// ---------------------------------------------------------------------------------------------
+template <class M, class H>
+struct VanillaPlanner {
+    using S = typename M::State;
+    const M& mdp;
+    const mctsb200_solver_cfg& cfg;
+    Hooks<M> hooks;
+    Counters cnt;
+    Stream* rng = nullptr;
+
+    // MCTSTree (src/vanilla.jl:64-94); ids are 1-based, index i-1 in the vectors
+    std::unordered_map<S, int64_t, H> state_map;
+    std::vector<std::vector<int64_t>> child_ids;
+    std::vector<int64_t> total_n;
+    std::vector<S> s_labels;
+    std::vector<int64_t> n;
+    std::vector<double> q;
+    std::vector<int32_t> a_labels;
+
+    VanillaPlanner(const M& m, const mctsb200_solver_cfg& c, uint64_t tree_index)
+        : mdp(m), cfg(c), hooks{m, c, tree_index, 0, &cnt} {}
+
+    int64_t insert_node(const S& s) {
+        s_labels.push_back(s);
+        state_map[s] = (int64_t)s_labels.size();
+        child_ids.emplace_back();
+        int64_t tot = 0;
+        for (int a = 0; a < mdp.n_actions(s); ++a) {
+            const int64_t n0 = hooks.init_N(s, a);
+            tot += n0;
+            n.push_back(n0);
+            q.push_back(hooks.init_Q(s, a));
+            a_labels.push_back(a);
+            child_ids.back().push_back((int64_t)n.size());
+            cnt.n_action_inserts += 1;
+        }
+        total_n.push_back(tot);
+        cnt.n_state_inserts += 1;
+        return (int64_t)total_n.size();
+    }
+
+    int64_t best_sanode_Q(int64_t snode) const {
+        double best_Q = -std::numeric_limits<double>::infinity();
+        int64_t best = child_ids[snode - 1].front();
+        for (int64_t sa : child_ids[snode - 1]) {
+            if (q[sa - 1] > best_Q) {
+                best_Q = q[sa - 1];
+                best = sa;
+            }
+        }
+        return best;
+    }
+
+    int64_t best_sanode_UCB(int64_t snode, double c) const {
+        const auto& ch = child_ids[snode - 1];
+        if (c == 0) {  // argmax(q, children): first maximal element
+            int64_t best = ch.front();
+            for (int64_t sa : ch)
+                if (q[sa - 1] > q[best - 1]) best = sa;
+            return best;
+        }
+        double best_UCB = -std::numeric_limits<double>::infinity();
+        int64_t best = ch.front();
+        const int64_t sn = total_n[snode - 1];
+        for (int64_t sa : ch) {
+            double UCB;
+            if (n[sa - 1] == 0) {
+                return sa;
+            } else {
+                UCB = q[sa - 1] + c * std::sqrt(o_log((double)sn) / (double)n[sa - 1]);
+            }
+            if (UCB > best_UCB) {
+                best_UCB = UCB;
+                best = sa;
+            }
+        }
+        return best;
+    }
+
+    double simulate(int64_t node, int64_t depth) {
+        const S s = s_labels[node - 1];
+        if (mdp.isterminal(s)) {
+            return 0.0;
+        } else if (depth == 0) {
+            return hooks.estimate_value(s, depth);
+        }
+        cnt.n_tree_levels += 1;
+        const int64_t said = best_sanode_UCB(node, cfg.exploration_constant);
+        S sp;
+        double r;
+        mdp.gen(s, a_labels[said - 1], *rng, sp, r);
+        double qv;
+        auto it = state_map.find(sp);
+        if (it == state_map.end()) {
+            insert_node(sp);
+            qv = r + mdp.discount() * hooks.estimate_value(sp, depth - 1);
+        } else {
+            qv = r + mdp.discount() * simulate(it->second, depth - 1);
+        }
+        total_n[node - 1] += 1;
+        n[said - 1] += 1;
+        q[said - 1] += (qv - q[said - 1]) / (double)n[said - 1];
+        return qv;
+    }
+
+    // returns iterations done
+    int64_t build_tree(const S& s, int64_t& root_out) {
+        auto it = state_map.find(s);
+        int64_t root = it == state_map.end() ? insert_node(s) : it->second;
+        root_out = root;
+        const auto start = std::chrono::steady_clock::now();
+        int64_t done = 0;
+        for (int64_t i = 0; i < cfg.n_iterations; ++i) {
+            Stream descent(cfg.seed, hooks.tree_index, (uint32_t)i, 0);
+            rng = &descent;
+            hooks.iteration = (uint32_t)i;
+            simulate(root, cfg.depth);
+            cnt.n_simulations += 1;
+            done = i + 1;
+            if (std::isfinite(cfg.max_time)) {
+                const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+                if (el >= cfg.max_time) break;
+            }
+        }
+        return done;
+    }
+
+    void export_tree(ExportedTree& t) const {
+        t.state_bytes = sizeof(S);
+        t.total_n = total_n;
+        t.s_labels.resize(s_labels.size() * sizeof(S));
+        if (!s_labels.empty()) std::memcpy(t.s_labels.data(), s_labels.data(), t.s_labels.size());
+        t.child_offsets.assign(1, 0);
+        for (const auto& ch : child_ids) {
+            for (int64_t c : ch) t.child_ids.push_back(c);
+            t.child_offsets.push_back((int64_t)t.child_ids.size());
+        }
+        t.n = n;
+        t.q = q;
+        t.a_labels = a_labels;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// DPW (src/dpw.jl, src/dpw_types.jl)
+// ---------------------------------------------------------------------------------------------
+template <class M, class H>
+struct DPWPlanner {
+    using S = typename M::State;
+    const M& mdp;
+    const mctsb200_solver_cfg& cfg;
+    const bool literal_transitions;
+    Hooks<M> hooks;
+    Counters cnt;
+    Stream* rng = nullptr;
+
+    // DPWTree (src/dpw_types.jl:123-159)
+    std::vector<int64_t> total_n;
+    std::vector<std::vector<int64_t>> children;
+    std::vector<S> s_labels;
+    std::unordered_map<S, int64_t, H> s_lookup;
+    std::vector<int64_t> n;
+    std::vector<double> q;
+    std::vector<std::vector<std::pair<int64_t, double>>> transitions;
+    std::vector<int32_t> a_labels;
+    std::map<std::pair<int64_t, int32_t>, int64_t> a_lookup;
+    std::vector<int64_t> n_a_children;
+    std::set<std::pair<int64_t, int64_t>> unique_transitions;
+
+    DPWPlanner(const M& m, const mctsb200_solver_cfg& c, uint64_t tree_index, bool literal)
+        : mdp(m), cfg(c), literal_transitions(literal), hooks{m, c, tree_index, 0, &cnt} {}
+
+    int64_t insert_state_node(const S& s, bool maintain_s_lookup) {
+        total_n.push_back(0);
+        children.emplace_back();
+        s_labels.push_back(s);
+        const int64_t snode = (int64_t)total_n.size();
+        if (maintain_s_lookup) s_lookup[s] = snode;
+        cnt.n_state_inserts += 1;
+        return snode;
+    }
+
+    int64_t insert_action_node(int64_t snode, int32_t a, int64_t n0, double q0, bool maintain_a_lookup) {
+        n.push_back(n0);
+        q.push_back(q0);
+        a_labels.push_back(a);
+        transitions.emplace_back();
+        const int64_t sanode = (int64_t)n.size();
+        children[snode - 1].push_back(sanode);
+        n_a_children.push_back(0);
+        if (maintain_a_lookup) a_lookup[{snode, a}] = sanode;
+        cnt.n_action_inserts += 1;
+        return sanode;
+    }
+
+    int64_t best_sanode(int64_t snode) const {
+        double best_Q = -std::numeric_limits<double>::infinity();
+        int64_t sanode = 0;
+        for (int64_t child : children[snode - 1]) {
+            if (q[child - 1] > best_Q) {
+                best_Q = q[child - 1];
+                sanode = child;
+            }
+        }
+        return sanode;
+    }
+
+    int64_t best_sanode_UCB(int64_t snode, double c) const {
+        double best_UCB = -std::numeric_limits<double>::infinity();
+        int64_t sanode = 0;
+        const double ltn = o_log((double)total_n[snode - 1]);
+        for (int64_t child : children[snode - 1]) {
+            const int64_t nn = n[child - 1];
+            const double qq = q[child - 1];
+            double UCB;
+            if ((ltn <= 0 && nn == 0) || c == 0.0) {
+                UCB = qq;
+            } else {
+                UCB = qq + c * std::sqrt(ltn / (double)nn);
+            }
+            if (UCB > best_UCB) {
+                best_UCB = UCB;
+                sanode = child;
+            }
+        }
+        return sanode;
+    }
+
+    // rand(rng, transitions[sanode])
+    std::pair<int64_t, double> sample_transition(int64_t sanode) {
+        const auto& tr = transitions[sanode - 1];
+        const int j = rng->uniform_int((int)tr.size());
+        cnt.n_transition_samples += 1;
+        if (literal_transitions) return tr[j];
+        // multiset form: distinct spnodes in first-occurrence order, selected by cumulative count
+        std::vector<std::pair<int64_t, double>> uniq;
+        std::vector<int64_t> count;
+        for (const auto& e : tr) {
+            size_t k = 0;
+            for (; k < uniq.size(); ++k)
+                if (uniq[k].first == e.first) break;
+            if (k == uniq.size()) {
+                uniq.push_back(e);
+                count.push_back(1);
+            } else {
+                count[k] += 1;
+            }
+        }
+        int64_t cum = 0;
+        for (size_t k = 0; k < uniq.size(); ++k) {
+            cum += count[k];
+            if (j < cum) return uniq[k];
+        }
+        return uniq.back();
+    }
+
+    double simulate(int64_t snode, int64_t d) {
+        const S s = s_labels[snode - 1];
+        if (mdp.isterminal(s)) {
+            return 0.0;
+        } else if (d == 0) {
+            return hooks.estimate_value(s, d);
+        }
+
+        // action progressive widening
+        if (cfg.enable_action_pw) {
+            if ((double)children[snode - 1].size() <= cfg.k_action * std::pow((double)total_n[snode - 1], cfg.alpha_action)) {
+                const int32_t a = rng->uniform_int(mdp.n_actions(s));  // next_action(::RandomActionGenerator)
+                if (!cfg.check_repeat_action || !a_lookup.count({snode, a})) {
+                    const int64_t n0 = hooks.init_N(s, a);
+                    insert_action_node(snode, a, n0, hooks.init_Q(s, a), cfg.check_repeat_action != 0);
+                    total_n[snode - 1] += n0;
+                }
+            }
+        } else if (children[snode - 1].empty()) {
+            for (int32_t a = 0; a < mdp.n_actions(s); ++a) {
+                const int64_t n0 = hooks.init_N(s, a);
+                insert_action_node(snode, a, n0, hooks.init_Q(s, a), false);
+                total_n[snode - 1] += n0;
+            }
+        }
+
+        cnt.n_tree_levels += 1;
+        cnt.n_dpw_children_seen += (int64_t)children[snode - 1].size();
+        const int64_t sanode = best_sanode_UCB(snode, cfg.exploration_constant);
+        const int32_t a = a_labels[sanode - 1];
+
+        // state progressive widening
+        bool new_node = false;
+        int64_t spnode;
+        double r;
+        S sp{};
+        if ((cfg.enable_state_pw &&
+             (double)n_a_children[sanode - 1] <= cfg.k_state * std::pow((double)n[sanode - 1], cfg.alpha_state)) ||
+            n_a_children[sanode - 1] == 0) {
+            mdp.gen(s, a, *rng, sp, r);
+            auto it = s_lookup.end();
+            if (cfg.check_repeat_state && (it = s_lookup.find(sp)) != s_lookup.end()) {
+                spnode = it->second;
+            } else {
+                spnode = insert_state_node(sp, cfg.keep_tree || cfg.check_repeat_state);
+                new_node = true;
+            }
+            transitions[sanode - 1].push_back({spnode, r});
+            if (!cfg.check_repeat_state) {
+                n_a_children[sanode - 1] += 1;
+            } else if (!unique_transitions.count({sanode, spnode})) {
+                unique_transitions.insert({sanode, spnode});
+                n_a_children[sanode - 1] += 1;
+            }
+        } else {
+            auto pr = sample_transition(sanode);
+            spnode = pr.first;
+            r = pr.second;
+        }
+
+        double qv;
+        if (new_node) {
+            qv = r + mdp.discount() * hooks.estimate_value(sp, d - 1);
+        } else {
+            qv = r + mdp.discount() * simulate(spnode, d - 1);
+        }
+
+        n[sanode - 1] += 1;
+        total_n[snode - 1] += 1;
+        q[sanode - 1] += (qv - q[sanode - 1]) / (double)n[sanode - 1];
+        return qv;
+    }
+
+    // the search block of action_info; returns status
+    int32_t search(const S& s, int64_t& root_out, int64_t& done_out) {
+        if (mdp.isterminal(s)) return MCTSB200_ERR_TERMINAL_ROOT;
+        int64_t snode;
+        auto it = s_lookup.find(s);
+        if (cfg.keep_tree && !total_n.empty()) {
+            snode = it != s_lookup.end() ? it->second : insert_state_node(s, true);
+        } else {
+            snode = insert_state_node(s, cfg.check_repeat_state != 0);
+        }
+        root_out = snode;
+        const auto start = std::chrono::steady_clock::now();
+        done_out = 0;
+        for (int64_t i = 0; i < cfg.n_iterations; ++i) {
+            Stream descent(cfg.seed, hooks.tree_index, (uint32_t)i, 0);
+            rng = &descent;
+            hooks.iteration = (uint32_t)i;
+            simulate(snode, cfg.depth);
+            cnt.n_simulations += 1;
+            done_out = i + 1;
+            if (std::isfinite(cfg.max_time)) {
+                const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+                if (el >= cfg.max_time) break;
+            }
+        }
+        return MCTSB200_OK;
+    }
+
+    void export_tree(ExportedTree& t) const {
+        t.state_bytes = sizeof(S);
+        t.total_n = total_n;
+        t.s_labels.resize(s_labels.size() * sizeof(S));
+        if (!s_labels.empty()) std::memcpy(t.s_labels.data(), s_labels.data(), t.s_labels.size());
+        t.child_offsets.assign(1, 0);
+        for (const auto& ch : children) {
+            for (int64_t c : ch) t.child_ids.push_back(c);
+            t.child_offsets.push_back((int64_t)t.child_ids.size());
+        }
+        t.n = n;
+        t.q = q;
+        t.a_labels = a_labels;
+        t.n_a_children = n_a_children;
+        t.trans_offsets.assign(1, 0);
+        for (const auto& tr : transitions) {  // distinct spnodes, first-occurrence order, with counts
+            const size_t base = t.trans_spnode.size();
+            for (const auto& e : tr) {
+                size_t k = base;
+                for (; k < t.trans_spnode.size(); ++k)
+                    if (t.trans_spnode[k] == e.first) break;
+                if (k == t.trans_spnode.size()) {
+                    t.trans_spnode.push_back(e.first);
+                    t.trans_r.push_back(e.second);
+                    t.trans_count.push_back(1);
+                } else {
+                    t.trans_count[k] += 1;
+                }
+            }
+            t.trans_offsets.push_back((int64_t)t.trans_spnode.size());
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Batch driver
+// ---------------------------------------------------------------------------------------------
+struct RootResult {
+    int32_t action = 0;
+    double best_q = 0.0;
+    int32_t status = 0;
+    int32_t n_children = 0;
+    int64_t total_n = 0;
+    std::vector<int32_t> child_action;
+    std::vector<int64_t> child_n;
+    std::vector<double> child_q;
+};
+
+static std::vector<std::unique_ptr<ExportedTree>> g_trees;
+static std::vector<RootResult> g_roots;
+static std::mutex g_mu;
+
+template <class M, class H>
+static void plan_one(const M& mdp, const mctsb200_solver_cfg& cfg, const typename M::State& root, uint64_t tree_index,
+                     bool literal, bool keep, RootResult& res, Counters& cnt, std::unique_ptr<ExportedTree>& tree_out,
+                     int64_t& iterations_done) {
+    if (cfg.kind == MCTSB200_KIND_UCT) {
+        VanillaPlanner<M, H> p(mdp, cfg, tree_index);
+        int64_t rootid = 0;
+        iterations_done = p.build_tree(root, rootid);
+        const int64_t best = p.best_sanode_Q(rootid);
+        res.action = p.a_labels[best - 1];
+        res.best_q = p.q[best - 1];
+        res.status = MCTSB200_OK;
+        res.total_n = p.total_n[rootid - 1];
+        for (int64_t sa : p.child_ids[rootid - 1]) {
+            res.child_action.push_back(p.a_labels[sa - 1]);
+            res.child_n.push_back(p.n[sa - 1]);
+            res.child_q.push_back(p.q[sa - 1]);
+        }
+        res.n_children = (int32_t)res.child_action.size();
+        cnt = p.cnt;
+        if (keep) {
+            tree_out.reset(new ExportedTree());
+            p.export_tree(*tree_out);
+        }
+    } else {
+        DPWPlanner<M, H> p(mdp, cfg, tree_index, literal);
+        int64_t rootid = 0;
+        res.status = p.search(root, rootid, iterations_done);
+        if (res.status == MCTSB200_OK) {
+            const int64_t best = p.best_sanode(rootid);
+            if (best > 0) {
+                res.action = p.a_labels[best - 1];
+                res.best_q = p.q[best - 1];
+            }
+            res.total_n = p.total_n[rootid - 1];
+            for (int64_t sa : p.children[rootid - 1]) {
+                res.child_action.push_back(p.a_labels[sa - 1]);
+                res.child_n.push_back(p.n[sa - 1]);
+                res.child_q.push_back(p.q[sa - 1]);
+            }
+            res.n_children = (int32_t)res.child_action.size();
+        }
+        cnt = p.cnt;
+        if (keep) {
+            tree_out.reset(new ExportedTree());
+            p.export_tree(*tree_out);
+        }
+    }
+}
+
+static int64_t algorithmic_bytes(const mctsb200_solver_cfg& cfg, const Counters& c, int n_actions) {
+    if (cfg.kind == MCTSB200_KIND_UCT) return (80 + 16 * (int64_t)n_actions) * c.n_tree_levels + (48 + 16 * (int64_t)n_actions) * c.n_state_inserts;
+    return 144 * c.n_tree_levels + 24 * c.n_dpw_children_seen + 56 * c.n_state_inserts + 72 * c.n_action_inserts;
+}
+
+template <class M, class H>
+static int32_t plan_batch(const M& mdp, const mctsb200_solver_cfg& cfg, const typename M::State* roots, int64_t n_roots,
+                          int64_t base, int n_threads, bool keep, bool literal, bool same_root, int32_t* action_out,
+                          double* bestq_out, int32_t* status_out, mctsb200_plan_stats* stats) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<RootResult> results((size_t)n_roots);
+    std::vector<std::unique_ptr<ExportedTree>> trees((size_t)n_roots);
+    std::vector<Counters> per_thread((size_t)std::max(1, n_threads));
+    std::atomic<int64_t> next{0};
+    std::atomic<int64_t> min_done{std::numeric_limits<int64_t>::max()};
+    auto worker = [&](int tid) {
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n_roots) break;
+            Counters c;
+            int64_t done = 0;
+            plan_one<M, H>(mdp, cfg, roots[same_root ? 0 : i], (uint64_t)(base + i), literal, keep, results[(size_t)i], c,
+                           trees[(size_t)i], done);
+            per_thread[(size_t)tid].add(c);
+            int64_t cur = min_done.load();
+            while (done < cur && !min_done.compare_exchange_weak(cur, done)) {
+            }
+        }
+    };
+    if (n_threads <= 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; ++t) th.emplace_back(worker, t);
+        for (auto& t : th) t.join();
+    }
+    Counters tot;
+    for (const auto& c : per_thread) tot.add(c);
+    for (int64_t i = 0; i < n_roots; ++i) {
+        if (action_out) action_out[i] = results[(size_t)i].action;
+        if (bestq_out) bestq_out[i] = results[(size_t)i].best_q;
+        if (status_out) status_out[i] = results[(size_t)i].status;
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        stats->n_trees = n_roots;
+        stats->n_simulations = tot.n_simulations;
+        stats->n_tree_levels = tot.n_tree_levels;
+        stats->n_dpw_children_seen = tot.n_dpw_children_seen;
+        stats->n_state_inserts = tot.n_state_inserts;
+        stats->n_action_inserts = tot.n_action_inserts;
+        stats->n_rollouts = tot.n_rollouts;
+        stats->n_rollout_steps = tot.n_rollout_steps;
+        stats->n_transition_samples = tot.n_transition_samples;
+        stats->algorithmic_bytes = algorithmic_bytes(cfg, tot, M::kActions);
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        stats->lanes_per_tree = 1;
+        stats->iterations_done = n_roots ? (int32_t)std::min<int64_t>(min_done.load(), INT32_MAX) : 0;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_trees = std::move(trees);
+    g_roots = std::move(results);
+    return MCTSB200_OK;
+}
+
+}  // namespace oracle
+
+// ---------------------------------------------------------------------------------------------
+// C interface for ctypes (tests / bench cpu_baseline only)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+static void copy_out(T* dst, const std::vector<T>& src) {
+    if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(T));
+}
+
+extern "C" {
+
+int32_t oracle_plan(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* params, const void* roots, int64_t n_roots,
+                    int64_t root_index_base, int32_t n_threads, int32_t keep_trees, int32_t literal_transitions,
+                    int32_t same_root, int32_t* action_out, double* bestq_out, int32_t* status_out,
+                    mctsb200_plan_stats* stats) {
+    using namespace oracle;
+    if (!cfg || cfg->struct_size != (int32_t)sizeof(mctsb200_solver_cfg) || !params || (!roots && n_roots > 0)) return MCTSB200_ERR_INVALID_ARG;
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD) {
+        GridWorld m(*(const mctsb200_gridworld_params*)params);
+        return plan_batch<GridWorld, GWPosHash>(m, *cfg, (const GWPos*)roots, n_roots, root_index_base, n_threads, keep_trees != 0,
+                                                literal_transitions != 0, same_root != 0, action_out, bestq_out, status_out, stats);
+    } else if (mdp_id == MCTSB200_MDP_MOUNTAINCAR) {
+        MountainCar m(*(const mctsb200_mountaincar_params*)params);
+        return plan_batch<MountainCar, MCStateHash>(m, *cfg, (const MCState*)roots, n_roots, root_index_base, n_threads,
+                                                    keep_trees != 0, literal_transitions != 0, same_root != 0, action_out, bestq_out,
+                                                    status_out, stats);
+    }
+    return MCTSB200_ERR_INVALID_ARG;
+}
+
+int32_t oracle_root_stats(int64_t root_i, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q, int64_t* total_n) {
+    using namespace oracle;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (root_i < 0 || root_i >= (int64_t)g_roots.size()) return MCTSB200_ERR_INVALID_ARG;
+    const RootResult& r = g_roots[(size_t)root_i];
+    if (n_children) *n_children = r.n_children;
+    if (total_n) *total_n = r.total_n;
+    for (int i = 0; i < r.n_children; ++i) {
+        if (action_idx) action_idx[i] = r.child_action[(size_t)i];
+        if (n) n[i] = r.child_n[(size_t)i];
+        if (q) q[i] = r.child_q[(size_t)i];
+    }
+    return MCTSB200_OK;
+}
+
+int32_t oracle_tree_sizes_query(int64_t root_i, mctsb200_tree_sizes* sizes) {
+    using namespace oracle;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (root_i < 0 || root_i >= (int64_t)g_trees.size() || !g_trees[(size_t)root_i]) return MCTSB200_ERR_STATE;
+    const ExportedTree& t = *g_trees[(size_t)root_i];
+    sizes->n_state_nodes = (int64_t)t.total_n.size();
+    sizes->n_action_nodes = (int64_t)t.n.size();
+    sizes->n_transitions = (int64_t)t.trans_spnode.size();
+    sizes->state_bytes = t.state_bytes;
+    return MCTSB200_OK;
+}
+
+int32_t oracle_tree_export(int64_t root_i, const mctsb200_tree_buffers* b) {
+    using namespace oracle;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (root_i < 0 || root_i >= (int64_t)g_trees.size() || !g_trees[(size_t)root_i]) return MCTSB200_ERR_STATE;
+    const ExportedTree& t = *g_trees[(size_t)root_i];
+    copy_out(b->total_n, t.total_n);
+    if (b->s_labels && !t.s_labels.empty()) std::memcpy(b->s_labels, t.s_labels.data(), t.s_labels.size());
+    copy_out(b->child_offsets, t.child_offsets);
+    copy_out(b->child_ids, t.child_ids);
+    copy_out(b->n, t.n);
+    copy_out(b->q, t.q);
+    copy_out(b->a_labels, t.a_labels);
+    copy_out(b->n_a_children, t.n_a_children);
+    copy_out(b->trans_offsets, t.trans_offsets);
+    copy_out(b->trans_spnode, t.trans_spnode);
+    copy_out(b->trans_r, t.trans_r);
+    copy_out(b->trans_count, t.trans_count);
+    return MCTSB200_OK;
+}
+
+// Root-parallel ensemble of one root (BASELINE config 5): per-action sums over trees in tree order.
+int32_t oracle_plan_root_parallel(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* params, const void* root_state,
+                                  int64_t n_trees, int64_t tree_index_base, int32_t n_threads, double* sum_n_out,
+                                  double* sum_nq_out, mctsb200_plan_stats* stats) {
+    using namespace oracle;
+    int32_t rc = oracle_plan(cfg, mdp_id, params, root_state, n_trees, tree_index_base, n_threads, 0, 1, 1, nullptr, nullptr,
+                             nullptr, stats);
+    if (rc != MCTSB200_OK) return rc;
+    const int nA = mdp_id == MCTSB200_MDP_GRIDWORLD ? 4 : 3;
+    for (int a = 0; a < nA; ++a) sum_n_out[a] = sum_nq_out[a] = 0.0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (const RootResult& r : g_roots) {
+        for (int i = 0; i < r.n_children; ++i) {
+            const int a = r.child_action[(size_t)i];
+            sum_n_out[a] += (double)r.child_n[(size_t)i];
+            sum_nq_out[a] += (double)r.child_n[(size_t)i] * r.child_q[(size_t)i];
+        }
+    }
+    return MCTSB200_OK;
+}
+
+// ---- small probes used by the unit tests ----
+int32_t oracle_philox(uint64_t seed, uint64_t tree, uint32_t iteration, uint32_t stream_id, int32_t n_blocks, uint32_t* out) {
+    oracle::Stream s(seed, tree, iteration, stream_id);
+    for (int i = 0; i < 4 * n_blocks; ++i) out[i] = s.next();
+    return 0;
+}
+int32_t oracle_philox_raw(const uint32_t* key, const uint32_t* ctr, uint32_t* out) {
+    oracle::philox4x32_10(key, ctr, out);
+    return 0;
+}
+double oracle_log(double x) { return oracle::o_log(x); }
+double oracle_cos(double x) { return oracle::o_cos(x); }
+double oracle_libm_log(double x) { return std::log(x); }
+double oracle_libm_cos(double x) { return std::cos(x); }
+
+// one gen() call with a fresh stream (seed, tree, iteration, stream_id); returns words consumed
+int32_t oracle_gen(int32_t mdp_id, const void* params, const void* s, int32_t a, uint64_t seed, uint64_t tree,
+                   uint32_t iteration, uint32_t stream_id, void* sp_out, double* r_out) {
+    using namespace oracle;
+    Stream rng(seed, tree, iteration, stream_id);
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD) {
+        GridWorld m(*(const mctsb200_gridworld_params*)params);
+        GWPos sp;
+        m.gen(*(const GWPos*)s, a, rng, sp, *r_out);
+        std::memcpy(sp_out, &sp, sizeof sp);
+    } else {
+        MountainCar m(*(const mctsb200_mountaincar_params*)params);
+        MCState sp;
+        m.gen(*(const MCState*)s, a, rng, sp, *r_out);
+        std::memcpy(sp_out, &sp, sizeof sp);
+    }
+    return (int32_t)rng.ctr[0] * 4 - rng.have;
+}
+
+// one rollout (estimate_value with the configured policy) from s; iteration selects the stream
+double oracle_rollout(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* params, const void* s, uint64_t tree,
+                      uint32_t iteration, int64_t remaining_depth, int64_t* steps_out) {
+    using namespace oracle;
+    Counters cnt;
+    double v;
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD) {
+        GridWorld m(*(const mctsb200_gridworld_params*)params);
+        Hooks<GridWorld> h{m, *cfg, tree, iteration, &cnt};
+        v = h.estimate_value(*(const GWPos*)s, remaining_depth);
+    } else {
+        MountainCar m(*(const mctsb200_mountaincar_params*)params);
+        Hooks<MountainCar> h{m, *cfg, tree, iteration, &cnt};
+        v = h.estimate_value(*(const MCState*)s, remaining_depth);
+    }
+    if (steps_out) *steps_out = cnt.n_rollout_steps;
+    return v;
+}
+
+int32_t oracle_hardware_threads(void) { return (int32_t)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

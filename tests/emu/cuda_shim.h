@@ -1,0 +1,80 @@
+// cuda_shim.h -- TEST INFRASTRUCTURE. Lets g++ compile mcts.jl_b200/csrc/*.cu as a single-threaded host
+// program (libmctsb200_emu.so) so that the CPU-only test suite can exercise the library's HOST logic
+// (option validation, table sizing, widening thresholds, export, sharding) and the G = 1 kernel logic
+// without a GPU. The shipped package never loads this build: mcts.jl_b200/_lib.py only ever opens
+// csrc/libmctsb200.so and raises if it (or a CUDA device) is missing.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __shared__ static
+#define __grid_constant__
+#define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+#define CUDART_INF (std::numeric_limits<double>::infinity())
+
+struct EmuDim3 { unsigned x = 0, y = 0, z = 0; };
+static thread_local EmuDim3 threadIdx, blockIdx, blockDim;
+
+using std::max;
+using std::min;
+
+static inline void __syncthreads() {}
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+template <class T> static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline long long __double_as_longlong(double x) { long long u; std::memcpy(&u, &x, 8); return u; }
+static inline double __longlong_as_double(long long u) { double x; std::memcpy(&x, &u, 8); return x; }
+template <class T, class U> static inline T atomicAdd(T* p, U v) { T old = *p; *p += (T)v; return old; }
+
+namespace mctsb200_emu {
+template <class F>
+static inline void run(unsigned grid, unsigned block, F&& f) {
+    blockDim.x = block;
+    for (unsigned b = 0; b < grid; ++b)
+        for (unsigned t = 0; t < block; ++t) {
+            blockIdx.x = b;
+            threadIdx.x = t;
+            f();
+        }
+}
+}  // namespace mctsb200_emu
+
+// ---- a pretend CUDA runtime: device memory is host memory, everything is synchronous ----
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+typedef std::chrono::steady_clock::time_point* cudaEvent_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaStreamNonBlocking = 1 };
+struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 148; };
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA error"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
+static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)8 << 30; return cudaSuccess; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new std::chrono::steady_clock::time_point(); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { *e = std::chrono::steady_clock::now(); return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = std::chrono::duration<float, std::milli>(*b - *a).count(); return cudaSuccess; }
+template <class K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 4; return cudaSuccess; }
