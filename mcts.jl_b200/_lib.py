@@ -117,15 +117,20 @@ class Context:
 
     # -- planning --
     def plan(self, cfg: abi.SolverCfg, mdp_id: int, roots: np.ndarray, root_index_base: int = 0,
-             want_status: bool = False):
+             want_status: bool = False, out=None):
         """roots: C-contiguous array whose rows are statetype(mdp) values. Returns (actions, best_q, status, stats).
-        With want_status=False a terminal DPW root raises (like src/dpw.jl:22-27); with True it is reported per root."""
+        With want_status=False a terminal DPW root raises (like src/dpw.jl:22-27); with True it is reported per root.
+        out: optional preallocated (actions int32[n], best_q float64[n], status int32[n]) host arrays (e.g. pinned)."""
         roots = np.ascontiguousarray(roots)
         n = roots.shape[0]
         state_bytes = roots.dtype.itemsize * int(np.prod(roots.shape[1:], dtype=np.int64)) if n else 0
-        actions = np.empty(n, dtype=np.int32)
-        best_q = np.empty(n, dtype=np.float64)
-        status = np.zeros(n, dtype=np.int32) if want_status else None
+        if out is not None:
+            actions, best_q, status = out
+            assert actions.dtype == np.int32 and best_q.dtype == np.float64 and len(actions) == n and len(best_q) == n
+        else:
+            actions = np.empty(n, dtype=np.int32)
+            best_q = np.empty(n, dtype=np.float64)
+            status = np.zeros(n, dtype=np.int32) if want_status else None
         stats = abi.PlanStats()
         self._check(self.lib.mctsb200_plan(self._h, C.byref(cfg), mdp_id, _ptr(roots), n, state_bytes, int(root_index_base),
                                            _ptr(actions), _ptr(best_q), _ptr(status), C.byref(stats)))

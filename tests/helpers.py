@@ -1,0 +1,64 @@
+"""Shared helpers for the parity tests: drive the library and the oracle with identical bytes and
+compare actions, Q, per-root status, work counters and whole exported trees bit-for-bit."""
+import numpy as np
+
+import mcts_jl_b200 as m
+
+COUNTER_KEYS = ["n_simulations", "n_tree_levels", "n_dpw_children_seen", "n_state_inserts", "n_action_inserts", "n_rollouts",
+                "n_rollout_steps", "n_transition_samples", "algorithmic_bytes"]
+
+
+def bits(a: np.ndarray) -> np.ndarray:
+    return a.view(np.int64) if a.dtype == np.float64 else a
+
+
+def assert_trees_equal(t1: dict, t2: dict, what: str = "") -> None:
+    assert set(t1) == set(t2)
+    for k in t1:
+        assert t1[k].shape == t2[k].shape, f"{what}: field {k} shape {t1[k].shape} != {t2[k].shape}"
+        assert np.array_equal(bits(t1[k]), bits(t2[k])), f"{what}: field {k} differs"
+
+
+def gridworld_roots(n: int):
+    """BASELINE config 2/3 root formula: root i = GWPos(1 + i mod 10, 1 + (i div 10) mod 10)."""
+    return [(1 + i % 10, 1 + (i // 10) % 10) for i in range(n)]
+
+
+def mountaincar_roots(n: int, seed: int = 0):
+    """Config 4 roots: x = -1.2 + 1.7 u1 (rejecting x >= 0.5), v = -0.07 + 0.14 u2."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        x, v = -1.2 + 1.7 * rng.random(), -0.07 + 0.14 * rng.random()
+        if x < 0.5:
+            out.append((x, v))
+    return out
+
+
+def run_both(ctx, orc, solver, mdp, roots, base: int = 0, compare_trees="all", lanes=None, literal=False):
+    """Plan with the library (ctx) and with the oracle; assert bit-exact agreement; return library outputs."""
+    cfg, keep = m.build_cfg(solver, mdp)
+    if lanes is not None:
+        cfg.lanes_per_tree = lanes
+    ctx.configure(mdp.mdp_id, mdp.params())
+    orc.configure(mdp.mdp_id, mdp.params())
+    r = mdp.encode_states(roots)
+    a1, q1, s1, st1 = ctx.plan(cfg, mdp.mdp_id, r, base, want_status=True)
+    a2, q2, s2, st2 = orc.plan(cfg, mdp.mdp_id, r, base, literal_transitions=literal, n_threads=4)
+    assert np.array_equal(s1, s2), "per-root status differs"
+    assert np.array_equal(a1, a2), f"actions differ at {np.nonzero(a1 != a2)[0][:10]}"
+    assert np.array_equal(bits(q1), bits(q2)), "best_Q differs"
+    d1, d2 = st1.as_dict(), st2.as_dict()
+    for k in COUNTER_KEYS:
+        assert d1[k] == d2[k], f"counter {k}: {d1[k]} != {d2[k]}"
+    idx = range(len(roots)) if compare_trees == "all" else compare_trees
+    for i in idx:
+        t1 = ctx.tree_export(i, mdp.state_dtype, mdp.state_width)
+        t2 = orc.tree_export(i, mdp.state_dtype, mdp.state_width)
+        assert_trees_equal(t1, t2, f"tree {i}")
+        rs1, rs2 = ctx.root_stats(i), orc.root_stats(i)
+        for k in ("action_idx", "n", "q"):
+            assert np.array_equal(bits(rs1[k]), bits(rs2[k]))
+        assert rs1["total_n"] == rs2["total_n"]
+    del keep
+    return a1, q1, s1, st1

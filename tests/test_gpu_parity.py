@@ -1,0 +1,106 @@
+"""GPU parity proper: the shipped CUDA library, called through the C ABI, against the CPU oracle on the
+same seeded inputs -- actions, best Q, status, work counters and every field of every exported tree
+bit-for-bit, for every tile width."""
+import numpy as np
+import pytest
+
+import mcts_jl_b200 as m
+from helpers import gridworld_roots, mountaincar_roots, run_both
+
+pytestmark = pytest.mark.gpu
+
+GW = m.SimpleGridWorld()
+GW_DET = m.SimpleGridWorld(tprob=1.0)
+MC = m.MountainCar()
+ALL_LANES = [1, 2, 4, 8, 16, 32]
+
+
+def test_device_math_matches_host_bit_for_bit(gpu_ctx, oracle):
+    n = np.arange(0, 1 << 20, dtype=np.float64)
+    host = np.array([oracle.lib.oracle_log(float(x)) for x in n[:50000]])
+    dev = gpu_ctx.device_log(n)
+    assert np.array_equal(dev[:50000].view(np.int64), host.view(np.int64))
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-3.7, 1.8, 50000), rng.uniform(-1e5, 1e5, 20000), [0.0, -0.0, 0.5235987755982988]])
+    hostc = np.array([oracle.lib.oracle_cos(float(v)) for v in x])
+    assert np.array_equal(gpu_ctx.device_cos(x).view(np.int64), hostc.view(np.int64))
+    xl = np.exp(rng.uniform(-700, 700, 50000))
+    hostl = np.array([oracle.lib.oracle_log(float(v)) for v in xl])
+    assert np.array_equal(gpu_ctx.device_log(xl).view(np.int64), hostl.view(np.int64))
+
+
+def test_device_philox_matches_oracle(gpu_ctx, oracle):
+    for seed, tree, it, sid in [(0, 0, 0, 0), (12345678901234567, 65535, 999, 1), (2**64 - 1, 2**40 + 17, 2**32 - 1, 33)]:
+        assert np.array_equal(gpu_ctx.device_philox(seed, tree, it, sid, 8), oracle.philox(seed, tree, it, sid, 8))
+
+
+@pytest.mark.parametrize("lanes", ALL_LANES)
+def test_uct_gridworld_deterministic_bit_exact(gpu_ctx, oracle, lanes):
+    """Config 2, deterministic variant (tprob=1, FunctionPolicy(s->:up) / SeekTarget rollouts), reduced size."""
+    roots = gridworld_roots(200)
+    for est in (m.RolloutEstimator(m.ConstantPolicy("up")), m.RolloutEstimator(m.SeekTarget((9, 3)))):
+        s = m.MCTSSolver(n_iterations=300, depth=20, exploration_constant=5.0, estimate_value=est)
+        run_both(gpu_ctx, oracle, s, GW_DET, roots, lanes=lanes, compare_trees=range(0, 200, 7))
+
+
+@pytest.mark.parametrize("lanes", ALL_LANES)
+def test_uct_gridworld_stochastic_bit_exact(gpu_ctx, oracle, lanes):
+    s = m.MCTSSolver(n_iterations=250, depth=20, exploration_constant=5.0, rng=7)
+    run_both(gpu_ctx, oracle, s, GW, gridworld_roots(128), base=1000, lanes=lanes, compare_trees=range(0, 128, 5))
+
+
+@pytest.mark.parametrize("lanes", ALL_LANES)
+def test_dpw_gridworld_bit_exact(gpu_ctx, oracle, lanes):
+    """Config 3 solver (bench/non-terminal_gw_dpw.jl), reduced size."""
+    s = m.DPWSolver(n_iterations=300, depth=20, exploration_constant=10.0, k_state=4.0, alpha_state=1 / 8, k_action=4.0, alpha_action=1 / 8, rng=3)
+    run_both(gpu_ctx, oracle, s, GW, gridworld_roots(100), lanes=lanes, compare_trees=range(0, 100, 9))
+
+
+@pytest.mark.parametrize("lanes", [1, 4, 32])
+@pytest.mark.parametrize("opts", [
+    dict(),
+    dict(enable_action_pw=False),
+    dict(k_state=1.0, alpha_state=0.1),
+    dict(check_repeat_state=False, k_state=2.0, alpha_state=0.3),
+    dict(enable_state_pw=False),
+    dict(init_N=2, init_Q=-1.0, estimate_value=4.0),
+    dict(exploration_constant=0.0),
+])
+def test_dpw_option_matrix_bit_exact(gpu_ctx, oracle, lanes, opts):
+    kw = dict(n_iterations=200, depth=10, rng=11)
+    kw.update(opts)
+    run_both(gpu_ctx, oracle, m.DPWSolver(**kw), GW, gridworld_roots(40), lanes=lanes)
+
+
+@pytest.mark.parametrize("lanes", [1, 4, 32])
+@pytest.mark.parametrize("opts", [
+    dict(exploration_constant=0.0),
+    dict(init_N=3, init_Q=11.73, estimate_value=0.0),
+    dict(estimate_value=m.RolloutEstimator(m.RandomSolver(), max_depth=-1)),
+    dict(estimate_value=m.RolloutEstimator(m.ConstantPolicy("up"), max_depth=-1)),
+    dict(estimate_value=m.RolloutEstimator(m.RandomSolver(), eps=0.2)),
+    dict(rollouts_per_leaf=8),
+    dict(rollouts_per_leaf=40),
+])
+def test_uct_option_matrix_bit_exact(gpu_ctx, oracle, lanes, opts):
+    kw = dict(n_iterations=150, depth=8, exploration_constant=3.0, rng=5)
+    kw.update(opts)
+    run_both(gpu_ctx, oracle, m.MCTSSolver(**kw), GW, gridworld_roots(40), lanes=lanes)
+
+
+@pytest.mark.parametrize("lanes", [1, 4, 32])
+def test_mountaincar_bit_exact(gpu_ctx, oracle, lanes):
+    """Config 4 solver (defaults, depth 50), reduced size; plus vanilla UCT and a heuristic rollout policy."""
+    roots = mountaincar_roots(24)
+    run_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=400, depth=50, rng=8), MC, roots, lanes=lanes)
+    run_both(gpu_ctx, oracle, m.MCTSSolver(n_iterations=300, depth=30, exploration_constant=10.0, rng=9), MC, roots, lanes=lanes)
+    run_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=300, depth=50, rng=8, estimate_value=m.RolloutEstimator(m.EnergyPolicy(), max_depth=100)),
+             MC, roots, lanes=lanes)
+
+
+def test_auto_lanes_and_terminal_roots(gpu_ctx, oracle):
+    roots = gridworld_roots(30) + [(-1, -1)]
+    a, q, st, stats = run_both(gpu_ctx, oracle, m.MCTSSolver(n_iterations=50, depth=20, exploration_constant=5.0, rng=2), GW, roots)
+    assert stats.lanes_per_tree in (1, 2, 4, 8, 16, 32)
+    a, q, st, stats = run_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=50, depth=10, rng=2), GW, roots)
+    assert st[-1] == m.abi.ERR_TERMINAL_ROOT and (st[:-1] == 0).all()
