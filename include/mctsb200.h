@@ -136,6 +136,7 @@ typedef struct {
     int64_t n_rollouts;
     int64_t n_rollout_steps;
     int64_t n_transition_samples; /* DPW: draws from transitions[sanode] (src/dpw.jl:140)          */
+    int64_t n_select_exact;      /* selections that needed the exact div/sqrt score (rest: table fast path) */
     int64_t algorithmic_bytes;
     double kernel_ms;            /* device time of the search kernels (CUDA events)                */
     double total_ms;             /* host wall time of the call incl. copies                         */

@@ -111,6 +111,7 @@ class PlanStats(C.Structure):
         ("n_rollouts", C.c_int64),
         ("n_rollout_steps", C.c_int64),
         ("n_transition_samples", C.c_int64),
+        ("n_select_exact", C.c_int64),
         ("algorithmic_bytes", C.c_int64),
         ("kernel_ms", C.c_double),
         ("total_ms", C.c_double),

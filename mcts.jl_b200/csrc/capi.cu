@@ -86,7 +86,7 @@ struct mctsb200_ctx {
     MountainCarDev::Params mc_dev{};
 
     Storage st;
-    DevBuf counters, log_tab, nmin_state, init_q, init_n, value_tab, io_roots, io_action, io_bestq, io_status, sums;
+    DevBuf counters, log_tab, sqrtlog_tab, rsqrt_tab, nmin_state, init_q, init_n, value_tab, io_roots, io_action, io_bestq, io_status, sums;
     int log_tab_n = 0;
 };
 
@@ -116,6 +116,40 @@ struct MdpAccess<MountainCarDev> {
     }
     static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_MC_ENERGY; }
 };
+
+// For every (boundary class, action): the positions where the reference's sampling expression
+// (GridWorldDev::sample_destination, evaluated here on the host with the same individually rounded operations)
+// steps from one destination to the next as the 32-bit word w grows, and the destination on each plateau.
+void gw_thresholds(double tprob, double p_other, GridWorldDev::Thresholds* out) {
+    for (unsigned mask = 0; mask < 16; ++mask)
+        for (int a = 0; a < 4; ++a) {
+            unsigned long long first_gt[4];  // first w with destination(w) > i; 2^32 if none
+            for (int i = 0; i < 4; ++i) {
+                unsigned long long lo = 0, hi = 1ull << 32;
+                while (lo < hi) {
+                    const unsigned long long mid = lo + (hi - lo) / 2;
+                    if (GridWorldDev::sample_destination(tprob, p_other, mask, a, (uint32_t)mid) > i) hi = mid;
+                    else lo = mid + 1;
+                }
+                first_gt[i] = lo;
+            }
+            GridWorldDev::Thresholds& T = out[mask * 4 + a];
+            for (int i = 0; i < 4; ++i) T.t[i] = 0xffffffffu;
+            T.pad[0] = T.pad[1] = T.pad[2] = 0;
+            int n_steps = 0;
+            uint32_t codes = (uint32_t)GridWorldDev::sample_destination(tprob, p_other, mask, a, 0u);
+            unsigned long long prev = 0;
+            for (int i = 0; i < 4; ++i) {
+                const unsigned long long v = first_gt[i];
+                if (v == 0 || v >= (1ull << 32) || v == prev) continue;  // no step here (or same step as before)
+                T.t[n_steps] = (uint32_t)(v - 1);                       // w > v-1  <=>  w >= v
+                ++n_steps;
+                codes |= (uint32_t)GridWorldDev::sample_destination(tprob, p_other, mask, a, (uint32_t)v) << (4 * n_steps);
+                prev = v;
+            }
+            T.codes = codes;
+        }
+}
 
 // min N in [0, bound] with  len <= k * N^alpha  (the reference's widening test, src/dpw.jl:95,121,
 // evaluated with the host's pow exactly as written there); INT_MAX if none.
@@ -300,14 +334,25 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     // log table: det_log(N), N < log_tab_n (grown lazily, shared by all configurations)
     const int want = (int)std::min<long long>(bound + 1, 1 << 20);
     if (want > ctx->log_tab_n) {
-        std::vector<double> tab((size_t)want);
-        for (int i = 0; i < want; ++i) tab[(size_t)i] = det_log((double)i);
+        std::vector<double> tab((size_t)want), stab((size_t)want), rtab((size_t)want);
+        for (int i = 0; i < want; ++i) {
+            tab[(size_t)i] = det_log((double)i);
+            stab[(size_t)i] = i >= 1 ? std::sqrt(tab[(size_t)i]) : 0.0;
+            rtab[(size_t)i] = i >= 1 ? 1.0 / std::sqrt((double)i) : INFINITY;
+        }
         CUDA_TRY(ctx->log_tab.ensure(sizeof(double) * (size_t)want));
+        CUDA_TRY(ctx->sqrtlog_tab.ensure(sizeof(double) * (size_t)want));
+        CUDA_TRY(ctx->rsqrt_tab.ensure(sizeof(double) * (size_t)want));
         CUDA_TRY(cudaMemcpy(ctx->log_tab.p, tab.data(), sizeof(double) * (size_t)want, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(ctx->sqrtlog_tab.p, stab.data(), sizeof(double) * (size_t)want, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(ctx->rsqrt_tab.p, rtab.data(), sizeof(double) * (size_t)want, cudaMemcpyHostToDevice));
         ctx->log_tab_n = want;
     }
     d.log_tab = (const double*)ctx->log_tab.p;
+    d.sqrtlog_tab = (const double*)ctx->sqrtlog_tab.p;
+    d.rsqrt_tab = (const double*)ctx->rsqrt_tab.p;
     d.log_tab_n = ctx->log_tab_n;
+    d.rsqrt_tab_n = ctx->log_tab_n;
 
     if (cfg->kind == MCTSB200_KIND_DPW) {
         for (int len = 0; len < 16; ++len) d.nmin_action[len] = len <= A ? nmin_for(cfg->k_action, cfg->alpha_action, len, bound) : 0x7fffffff;
@@ -354,6 +399,7 @@ void fill_stats(mctsb200_plan_stats* s, const mctsb200_solver_cfg* cfg, const un
     s->n_rollouts = (int64_t)c[CNT_ROLLOUTS];
     s->n_rollout_steps = (int64_t)c[CNT_ROLLOUT_STEPS];
     s->n_transition_samples = (int64_t)c[CNT_TRANS_SAMPLES];
+    s->n_select_exact = (int64_t)c[CNT_SELECT_EXACT];
     if (cfg->kind == MCTSB200_KIND_UCT)
         s->algorithmic_bytes = (80 + 16 * (int64_t)n_actions) * s->n_tree_levels + (48 + 16 * (int64_t)n_actions) * s->n_state_inserts;
     else
@@ -618,16 +664,16 @@ int32_t tree_export_impl(mctsb200_ctx* ctx, long long i, const mctsb200_tree_buf
         const Row<M>& rw = t.rows[(size_t)s];
         if (b->total_n) b->total_n[s] = rw.total_n;
         if (b->s_labels) {
-            const Abi lab = M::store(M::state_of(P, rw.key));
+            const Abi lab = M::store(P, M::state_of(P, rw.key));
             std::memcpy((char*)b->s_labels + sizeof(Abi) * (size_t)s, &lab, sizeof lab);
         }
-        for (int slot = 0; slot < rw.nchild; ++slot) {
+        for (int slot = 0; slot < rw.nchild(); ++slot) {
             const int64_t id = said(s, slot);
             if (b->child_ids) b->child_ids[child_pos] = id;
             ++child_pos;
             if (b->n) b->n[id - 1] = rw.n[slot];
             if (b->q) b->q[id - 1] = rw.q[slot];
-            if (b->a_labels) b->a_labels[id - 1] = rw.alabel[slot];
+            if (b->a_labels) b->a_labels[id - 1] = rw.alabel(slot);
             if (dpw && b->n_a_children) b->n_a_children[id - 1] = t.aux[(size_t)s].nac[slot];
         }
         if (b->child_offsets) b->child_offsets[s + 1] = child_pos;
@@ -637,7 +683,7 @@ int32_t tree_export_impl(mctsb200_ctx* ctx, long long i, const mctsb200_tree_buf
         const int na = t.h.n_action;
         std::vector<int> owner_s((size_t)na, -1), owner_slot((size_t)na, 0);
         for (int s = 0; s < ns; ++s)
-            for (int slot = 0; slot < t.rows[(size_t)s].nchild; ++slot) {
+            for (int slot = 0; slot < t.rows[(size_t)s].nchild(); ++slot) {
                 const int64_t id = said(s, slot);
                 owner_s[(size_t)(id - 1)] = s;
                 owner_slot[(size_t)(id - 1)] = slot;
@@ -674,10 +720,10 @@ int32_t root_stats_impl(mctsb200_ctx* ctx, long long i, int32_t* n_children, int
     }
     Row<M> rw;
     CUDA_TRY(cudaMemcpy(&rw, (const Row<M>*)ctx->st.rows.p + i * ctx->st.geo.NS + h.root, sizeof rw, cudaMemcpyDeviceToHost));
-    if (n_children) *n_children = rw.nchild;
+    if (n_children) *n_children = rw.nchild();
     if (total_n) *total_n = rw.total_n;
-    for (int j = 0; j < rw.nchild; ++j) {
-        if (action_idx) action_idx[j] = rw.alabel[j];
+    for (int j = 0; j < rw.nchild(); ++j) {
+        if (action_idx) action_idx[j] = rw.alabel(j);
         if (n) n[j] = rw.n[j];
         if (q) q[j] = rw.q[j];
     }
@@ -751,7 +797,7 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->counters,
-                      &c->log_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
+                      &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
                       &c->sums};
     for (DevBuf* b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -794,29 +840,46 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
         if (p.n_rewards < 0 || p.n_rewards > MCTSB200_GW_MAX_SPECIAL || p.n_terminate < 0 || p.n_terminate > MCTSB200_GW_MAX_SPECIAL)
             return fail(MCTSB200_ERR_INVALID_ARG, "too many reward / terminate_from cells (max %d)", MCTSB200_GW_MAX_SPECIAL);
         const int cells = p.nx * p.ny;
-        std::vector<double> rew((size_t)cells + 1, 0.0);
-        std::vector<uint8_t> term((size_t)cells + 1, 0);
+        std::vector<GridWorldDev::CellInfo> info((size_t)cells + 1);
         auto inb = [&](int x, int y) { return x >= 1 && x <= p.nx && y >= 1 && y <= p.ny; };
+        for (int c = 0; c <= cells; ++c) {
+            GridWorldDev::CellInfo ci;
+            ci.reward = 0.0;
+            ci.term_from = c == cells ? 1u : 0u;
+            ci.row = 0;
+            if (c < cells) {
+                const int x = c % p.nx + 1, y = c / p.nx + 1;
+                ci.row = 4u * ((y + 1 > p.ny ? 1u : 0u) | (y - 1 < 1 ? 2u : 0u) | (x - 1 < 1 ? 4u : 0u) | (x + 1 > p.nx ? 8u : 0u));
+            }
+            info[(size_t)c] = ci;
+        }
         for (int i = 0; i < p.n_rewards; ++i) {
             // a Dict key outside the grid can only ever be matched by the terminal state (-1,-1)
-            if (inb(p.reward_x[i], p.reward_y[i])) rew[(size_t)((p.reward_x[i] - 1) + (p.reward_y[i] - 1) * p.nx)] = p.reward_v[i];
-            else if (p.reward_x[i] == -1 && p.reward_y[i] == -1) rew[(size_t)cells] = p.reward_v[i];
+            if (inb(p.reward_x[i], p.reward_y[i])) info[(size_t)((p.reward_x[i] - 1) + (p.reward_y[i] - 1) * p.nx)].reward = p.reward_v[i];
+            else if (p.reward_x[i] == -1 && p.reward_y[i] == -1) info[(size_t)cells].reward = p.reward_v[i];
         }
         for (int i = 0; i < p.n_terminate; ++i)
-            if (inb(p.term_x[i], p.term_y[i])) term[(size_t)((p.term_x[i] - 1) + (p.term_y[i] - 1) * p.nx)] = 1;
-        term[(size_t)cells] = 1;
-        CUDA_TRY(ctx->gw_reward.ensure(rew.size() * sizeof(double)));
-        CUDA_TRY(ctx->gw_term.ensure(term.size()));
-        CUDA_TRY(cudaMemcpy(ctx->gw_reward.p, rew.data(), rew.size() * sizeof(double), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(ctx->gw_term.p, term.data(), term.size(), cudaMemcpyHostToDevice));
+            if (inb(p.term_x[i], p.term_y[i])) info[(size_t)((p.term_x[i] - 1) + (p.term_y[i] - 1) * p.nx)].term_from = 1u;
+        const double p_other = (1.0 - p.tprob) / (double)(GridWorldDev::kActions - 1);
+        std::vector<GridWorldDev::Thresholds> thr(16 * 4);
+        gw_thresholds(p.tprob, p_other, thr.data());
+        CUDA_TRY(ctx->gw_reward.ensure(info.size() * sizeof(GridWorldDev::CellInfo)));
+        CUDA_TRY(ctx->gw_term.ensure(thr.size() * sizeof(GridWorldDev::Thresholds)));
+        CUDA_TRY(cudaMemcpy(ctx->gw_reward.p, info.data(), info.size() * sizeof(GridWorldDev::CellInfo), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(ctx->gw_term.p, thr.data(), thr.size() * sizeof(GridWorldDev::Thresholds), cudaMemcpyHostToDevice));
         ctx->gw_host = p;
         ctx->gw_dev.nx = p.nx;
         ctx->gw_dev.ny = p.ny;
+        ctx->gw_dev.ncells = cells;
+        {
+            const int d[8] = {0, p.nx, -p.nx, -1, 1, 0, 0, 0};
+            for (int i = 0; i < 8; ++i) ctx->gw_dev.delta[i] = d[i];
+        }
         ctx->gw_dev.tprob = p.tprob;
-        ctx->gw_dev.p_other = (1.0 - p.tprob) / (double)(GridWorldDev::kActions - 1);
+        ctx->gw_dev.p_other = p_other;
         ctx->gw_dev.discount = p.discount;
-        ctx->gw_dev.cell_reward = (const double*)ctx->gw_reward.p;
-        ctx->gw_dev.cell_term_from = (const uint8_t*)ctx->gw_term.p;
+        ctx->gw_dev.cells = (const GridWorldDev::CellInfo*)ctx->gw_reward.p;
+        ctx->gw_dev.thr = (const GridWorldDev::Thresholds*)ctx->gw_term.p;
         ctx->gw_ok = true;
         ctx->st.valid = false;
         return MCTSB200_OK;

@@ -27,6 +27,8 @@
 #define MCTSB200_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #endif
 
+#define MCTSB200_MAX_ACTIONS_PER_ROW 7
+
 namespace mctsb200 {
 
 // ---------------------------------------------------------------------------------------------
@@ -117,18 +119,26 @@ struct __align__(8) HashSlot {
     int node;
 };
 
-// One state node. UCT: children are all A actions in actions(mdp) order (child k = action k; reference
-// action-node id = A*node + k + 1). DPW: children live in slots [0, nchild) in insertion order with
-// their action index in alabel[].
+// One state node (64 B for both built-in MDPs = two 32 B sectors).
+// UCT: children are all A actions in actions(mdp) order (child k = action k; reference action-node id =
+// A*node + k + 1). DPW: children live in slots [0, nchild) in insertion order; `packed` holds the child count
+// (bits 28-31) and each child's action index (4 bits per slot).
+// Field order keeps q[] and n[] 16 B aligned for A = 4 so one row is read with three vector loads.
 template <class M>
 struct __align__(32) Row {
     double q[M::kActions];
-    typename M::Key key;
     int n[M::kActions];
     int total_n;
-    uint8_t nchild;
-    uint8_t alabel[M::kActions];
+    uint32_t packed;
+    typename M::Key key;
+
+    __host__ __device__ __forceinline__ int nchild() const { return (int)(packed >> 28); }
+    __host__ __device__ __forceinline__ int alabel(int slot) const { return (int)((packed >> (4 * slot)) & 15u); }
+    __host__ __device__ __forceinline__ static uint32_t pack_add(uint32_t pk, int slot, int act) {
+        return (pk & 0x0fffffffu & ~(15u << (4 * slot))) | ((uint32_t)act << (4 * slot)) | ((uint32_t)(slot + 1) << 28);
+    }
 };
+static_assert(MCTSB200_MAX_ACTIONS_PER_ROW == 7, "4-bit labels, 7 slots + count");
 
 template <class M>
 struct __align__(32) Aux {
@@ -148,7 +158,7 @@ struct Geometry {
 
 enum CounterId {
     CNT_SIMULATIONS = 0, CNT_LEVELS, CNT_CHILDREN_SEEN, CNT_STATE_INSERTS, CNT_ACTION_INSERTS, CNT_ROLLOUTS, CNT_ROLLOUT_STEPS,
-    CNT_TRANS_SAMPLES, CNT_COUNT
+    CNT_TRANS_SAMPLES, CNT_SELECT_EXACT, CNT_COUNT
 };
 
 // device view of the solver configuration
@@ -163,8 +173,11 @@ struct DevCfg {
     const int* init_n_table;     // device, may be null
     const double* value_table;   // device, may be null
     const double* log_tab;       // device: det_log(N) for N < log_tab_n
+    const double* sqrtlog_tab;   // device: sqrt(det_log(N)) for N < log_tab_n (fast-path score)
+    const double* rsqrt_tab;     // device: 1/sqrt(n) for n < rsqrt_tab_n     (fast-path score)
     const int* nmin_state;       // device: min n[sanode] for which n_a_children == len may widen
     int log_tab_n;
+    int rsqrt_tab_n;
     int nmin_state_n;
     int nmin_action[16];         // min total_n for which a state node with len children may widen
     int depth;

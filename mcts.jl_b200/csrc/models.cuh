@@ -30,79 +30,101 @@ struct GridWorldDev {
     static constexpr int kMdpId = MCTSB200_MDP_GRIDWORLD;
 
     struct AbiState { long long x, y; };
-    struct State { int x, y; };
-    typedef uint16_t Key;  // dense cell index; nx*ny = the terminal state (-1,-1)
+    // On the device a state is its dense cell index: (x-1) + (y-1)*nx, and nx*ny for the terminal state (-1,-1).
+    struct State { int cell; };
+    typedef uint16_t Key;
+
+    // One 16 B record per cell (one vector load per gen call).
+    struct __align__(16) CellInfo {
+        double reward;       // get(rewards, s, 0.0)
+        uint32_t term_from;  // s in terminate_from, or the terminal state itself
+        uint32_t row;        // 4 * ob_mask: first threshold row of this cell's boundary class
+    };
+    // Transition sampling for one (boundary class, intended action). The reference draws u = sum(p)*rand() and
+    // takes the first destination in [stay, up, down, left, right] whose running total exceeds u (SparseCat).
+    // With rand() = w * 2^-32 that choice is a monotone step function of the 32-bit word w, so the host
+    // evaluates the reference's floating-point expression (sample_destination) to find the step positions and
+    // the device only compares integers:  j = #{i : w > t[i]},  destination = (codes >> 4j) & 15.
+    // Unused slots hold t = 0xffffffff (never exceeded).
+    struct __align__(32) Thresholds {
+        uint32_t t[4];
+        uint32_t codes;
+        uint32_t pad[3];
+    };
 
     struct Params {
-        int nx, ny;
+        int nx, ny, ncells;
+        int delta[8];    // cell-index step of destination code [stay, up, down, left, right]
         double tprob;    // probability of the intended move
         double p_other;  // (1.0 - tprob) / 3
         double discount;
-        const double* cell_reward;       // [nx*ny + 1]   get(rewards, s, 0.0)
-        const uint8_t* cell_term_from;   // [nx*ny + 1]   s in terminate_from
+        const CellInfo* cells;      // [nx*ny + 1]
+        const Thresholds* thr;      // [16 boundary classes][4 actions]
     };
 
-    __device__ __forceinline__ static State load(const AbiState& a) { return State{(int)a.x, (int)a.y}; }
-    __host__ __device__ __forceinline__ static AbiState store(const State& s) { return AbiState{s.x, s.y}; }
-    __device__ __forceinline__ static bool is_terminal(const Params&, const State& s) { return s.x < 0 || s.y < 0; }
+    __device__ __forceinline__ static State load(const Params& p, const AbiState& a) {
+        return State{(a.x < 0 || a.y < 0) ? p.ncells : (int)(a.x - 1) + (int)(a.y - 1) * p.nx};
+    }
+    __host__ __device__ __forceinline__ static AbiState store(const Params& p, const State& s) {
+        if (s.cell == p.ncells) return AbiState{-1, -1};
+        return AbiState{s.cell % p.nx + 1, s.cell / p.nx + 1};
+    }
+    __device__ __forceinline__ static bool is_terminal(const Params& p, const State& s) { return s.cell == p.ncells; }  // any(s .< 0)
     __device__ __forceinline__ static double discount(const Params& p) { return p.discount; }
-    __device__ __forceinline__ static int dense_count(const Params& p) { return p.nx * p.ny + 1; }
-    __host__ __device__ __forceinline__ static int dense_index(const Params& p, const State& s) {
-        return (s.x < 0 || s.y < 0) ? p.nx * p.ny : (s.x - 1) + (s.y - 1) * p.nx;
-    }
-    __device__ __forceinline__ static Key key_of(const Params& p, const State& s) { return (Key)dense_index(p, s); }
-    __host__ __device__ __forceinline__ static State state_of(const Params& p, Key k) {
-        if ((int)k == p.nx * p.ny) return State{-1, -1};
-        return State{(int)k % p.nx + 1, (int)k / p.nx + 1};
-    }
+    __device__ __forceinline__ static int dense_index(const Params&, const State& s) { return s.cell; }
+    __device__ __forceinline__ static Key key_of(const Params&, const State& s) { return (Key)s.cell; }
+    __host__ __device__ __forceinline__ static State state_of(const Params&, Key k) { return State{(int)k}; }
     __device__ __forceinline__ static bool key_equal(Key a, Key b) { return a == b; }
 
-    // transition(mdp, s, a) + rand(rng, SparseCat) + reward(mdp, s, a); one uniform draw unless the
-    // source is a terminate_from cell or terminal (Deterministic next state, no draw).
-    __device__ __forceinline__ static void gen(const Params& p, const State& s, int a, Stream& rng, State& sp, double& r) {
-        const int cell = dense_index(p, s);
-        r = __ldg(p.cell_reward + cell);
-        if (__ldg(p.cell_term_from + cell) || is_terminal(p, s)) {
-            sp = State{-1, -1};
-            return;
-        }
-        // destination order [stay, up, down, left, right]; out-of-bounds mass folds into "stay"
-        const bool ob_up = s.y + 1 > p.ny, ob_down = s.y - 1 < 1, ob_left = s.x - 1 < 1, ob_right = s.x + 1 > p.nx;
-        const double pu = a == 0 ? p.tprob : p.p_other, pd = a == 1 ? p.tprob : p.p_other;
-        const double pl = a == 2 ? p.tprob : p.p_other, pr = a == 3 ? p.tprob : p.p_other;
-        double p0 = 0.0;
+    // The reference's floating-point sampling expression for one (boundary class, action, word): which of the
+    // five destinations [stay, up, down, left, right] is chosen. Only the host evaluates it (threshold table).
+    __host__ __device__ __forceinline__ static int sample_destination(double tprob, double p_other, unsigned ob_mask, int a, uint32_t w) {
+        const bool ob_up = ob_mask & 1u, ob_down = ob_mask & 2u, ob_left = ob_mask & 4u, ob_right = ob_mask & 8u;
+        const double pu = a == 0 ? tprob : p_other, pd = a == 1 ? tprob : p_other;
+        const double pl = a == 2 ? tprob : p_other, pr = a == 3 ? tprob : p_other;
+        double p0 = 0.0;  // out-of-bounds mass folds into "stay", accumulated in action order
         if (ob_up) p0 = DM_ADD(p0, pu);
         if (ob_down) p0 = DM_ADD(p0, pd);
         if (ob_left) p0 = DM_ADD(p0, pl);
         if (ob_right) p0 = DM_ADD(p0, pr);
         const double p1 = ob_up ? 0.0 : pu, p2 = ob_down ? 0.0 : pd, p3 = ob_left ? 0.0 : pl, p4 = ob_right ? 0.0 : pr;
         const double c1 = DM_ADD(p0, p1), c2 = DM_ADD(c1, p2), c3 = DM_ADD(c2, p3), c4 = DM_ADD(c3, p4);
-        const double u = DM_MUL(c4, rng.uniform01());
-        sp = s;
-        if (u < p0) {
-        } else if (u < c1) {
-            sp.y = s.y + 1;
-        } else if (u < c2) {
-            sp.y = s.y - 1;
-        } else if (u < c3) {
-            sp.x = s.x - 1;
-        } else {
-            sp.x = s.x + 1;  // u < c4 always holds for u01 < 1
-        }
-        // an out-of-bounds destination carries probability 0 and is never selected, except through the
-        // final else when its mass is 0 and rounding pushed u to c4; the reference errors there (u < c4
-        // fails only if rand() == 1, which [0,1) excludes).
+        const double u = DM_MUL(c4, DM_MUL((double)w, 1.0 / 4294967296.0));
+        if (u < p0) return 0;
+        if (u < c1) return 1;
+        if (u < c2) return 2;
+        if (u < c3) return 3;
+        return 4;  // u < c4 always holds for rand() < 1
     }
 
-    __device__ __forceinline__ static int policy_action(const Params&, int policy, const int* pp, const State& s, Stream& rng) {
+    // transition(mdp, s, a) + rand(rng, SparseCat) + reward(mdp, s, a); one 32-bit draw unless the source is
+    // a terminate_from cell or terminal (Deterministic next state, no draw).
+    __device__ __forceinline__ static void gen(const Params& p, const State& s, int a, Stream& rng, State& sp, double& r) {
+        const int4 raw = __ldg(reinterpret_cast<const int4*>(p.cells + s.cell));
+        r = __hiloint2double(raw.y, raw.x);
+        if (raw.z) {
+            sp.cell = p.ncells;
+            return;
+        }
+        const uint32_t w = rng.next();
+        const Thresholds* row = p.thr + (raw.w + a);
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(row->t));
+        const uint32_t codes = __ldg(&row->codes);
+        const int j = (int)(w > t.x) + (int)(w > t.y) + (int)(w > t.z) + (int)(w > t.w);
+        sp.cell = s.cell + p.delta[(codes >> (4 * j)) & 15u];
+    }
+
+    __device__ __forceinline__ static int policy_action(const Params& p, int policy, const int* pp, const State& s, Stream& rng) {
         switch (policy) {
             case MCTSB200_POLICY_RANDOM: return rng.uniform_int(kActions);
             case MCTSB200_POLICY_CONSTANT: return pp[0];
-            case MCTSB200_POLICY_GW_SEEK:
-                if (pp[0] > s.x) return 3;
-                else if (pp[0] < s.x) return 2;
-                else if (pp[1] > s.y) return 0;
+            case MCTSB200_POLICY_GW_SEEK: {
+                const int x = s.cell % p.nx + 1, y = s.cell / p.nx + 1;
+                if (pp[0] > x) return 3;
+                else if (pp[0] < x) return 2;
+                else if (pp[1] > y) return 0;
                 else return 1;
+            }
             default: return 0;
         }
     }
@@ -125,12 +147,11 @@ struct MountainCarDev {
         double discount, cost, jackpot;
     };
 
-    __device__ __forceinline__ static State load(const AbiState& a) { return a; }
-    __host__ __device__ __forceinline__ static AbiState store(const State& s) { return s; }
+    __device__ __forceinline__ static State load(const Params&, const AbiState& a) { return a; }
+    __host__ __device__ __forceinline__ static AbiState store(const Params&, const State& s) { return s; }
     __device__ __forceinline__ static bool is_terminal(const Params&, const State& s) { return s.x >= 0.5; }
     __device__ __forceinline__ static double discount(const Params& p) { return p.discount; }
-    __device__ __forceinline__ static int dense_count(const Params&) { return 0; }
-    __host__ __device__ __forceinline__ static int dense_index(const Params&, const State&) { return -1; }
+    __device__ __forceinline__ static int dense_index(const Params&, const State&) { return -1; }
     __device__ __forceinline__ static Key key_of(const Params&, const State& s) { return Key{s.x, s.v}; }
     __host__ __device__ __forceinline__ static State state_of(const Params&, const Key& k) { return State{k.x, k.v}; }
     // isequal on Float64 pairs == bitwise equality

@@ -50,6 +50,44 @@ struct Tile {
         }
         return v;
     }
+    __device__ __forceinline__ double max_double(double v) const {
+        if constexpr (G > 1) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, G));
+        }
+        return v;
+    }
+    __device__ __forceinline__ double sum_double(double v) const {  // identical in every lane (xor butterfly)
+        if constexpr (G > 1) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) v = v + __shfl_xor_sync(mask, v, o, G);
+        }
+        return v;
+    }
+    __device__ __forceinline__ bool any(bool p) const {
+        if constexpr (G > 1) return __any_sync(mask, p) != 0;
+        else return p;
+    }
+    // arg-max of (score, idx) carrying the winner's (q, n, t) along
+    __device__ __forceinline__ void argmax_payload(double& score, int& idx, double& q, int& n, double& t) const {
+        if constexpr (G > 1) {
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                const double os = __shfl_xor_sync(mask, score, o, G);
+                const int oi = __shfl_xor_sync(mask, idx, o, G);
+                const double oq = __shfl_xor_sync(mask, q, o, G);
+                const int on = __shfl_xor_sync(mask, n, o, G);
+                const double ot = __shfl_xor_sync(mask, t, o, G);
+                if (os > score || (os == score && oi < idx)) {
+                    score = os;
+                    idx = oi;
+                    q = oq;
+                    n = on;
+                    t = ot;
+                }
+            }
+        }
+    }
     // arg-max of (score, idx): larger score wins, equal scores -> smaller idx
     __device__ __forceinline__ void argmax(double& score, int& idx) const {
         if constexpr (G > 1) {
@@ -84,8 +122,10 @@ struct Search {
     uint64_t tree_index;
     // header mirror (registers, tile-uniform)
     int n_state, n_action, n_trans, status;
-    // per-lane work counters
-    unsigned long long cnt[CNT_COUNT];
+    // per-lane work counters (per-tree counts fit 32 bits: n_iterations*depth <= 2e9 is validated on the host;
+    // rollout steps can exceed that and are kept in 64 bits)
+    unsigned cnt[CNT_COUNT];
+    unsigned long long rollout_steps;
 
     __device__ __forceinline__ Search(const KernelArgs<M>& args, long long tree) : a(args) {
         rows = args.rows + tree * args.geo.NS;
@@ -97,9 +137,13 @@ struct Search {
         tree_index = (uint64_t)(args.tree_index_base + tree);
 #pragma unroll
         for (int i = 0; i < CNT_COUNT; ++i) cnt[i] = 0;
+        rollout_steps = 0;
     }
 
     __device__ __forceinline__ bool lead() const { return tile.lane == 0; }
+
+    // exact int -> double for 0 <= n < 2^31 on the FP64 pipe (I2F.F64 would go through the 16-lane XU pipe)
+    __device__ __forceinline__ static double i2d(int n) { return DM_SUB(__hiloint2double(0x43300000, n), 4503599627370496.0); }
 
     // ---- numeric hooks (src/domain_knowledge.jl:10,82,91 + table stand-ins) ----
     __device__ __forceinline__ double init_Q(const State& s, int act) const {
@@ -148,7 +192,7 @@ struct Search {
 
     // ---- leaf evaluation ---------------------------------------------------------------------
     // POMDPTools simulate(::RolloutSimulator, mdp, policy, s0)
-    __device__ __forceinline__ double rollout(State s, int max_steps, Stream& rs, unsigned long long& steps) const {
+    __device__ __forceinline__ double rollout(State s, int max_steps, Stream& rs, unsigned& steps) const {
         const double eps = a.cfg.rollout_eps;
         const double gamma = M::discount(a.mdp);
         double disc = 1.0, r_total = 0.0;
@@ -179,11 +223,11 @@ struct Search {
         if (K == 1) {  // every lane runs the same stream: no divergence, no shuffle
             Stream rs;
             rs.init(a.cfg.seed, tree_index, it, 1u);
-            unsigned long long steps = 0;
+            unsigned steps = 0;
             const double v = rollout(s, max_steps, rs, steps);
             if (lead()) {
                 cnt[CNT_ROLLOUTS] += 1;
-                cnt[CNT_ROLLOUT_STEPS] += steps;
+                rollout_steps += steps;
             }
             return v;
         }
@@ -195,10 +239,10 @@ struct Search {
             if (k < K) {
                 Stream rs;
                 rs.init(a.cfg.seed, tree_index, it, 1u + (uint32_t)k);
-                unsigned long long steps = 0;
+                unsigned steps = 0;
                 mine = rollout(s, max_steps, rs, steps);
                 cnt[CNT_ROLLOUTS] += 1;
-                cnt[CNT_ROLLOUT_STEPS] += steps;
+                rollout_steps += steps;
             }
             const int m = min(G, K - base);
             for (int j = 0; j < m; ++j) sum = DM_ADD(sum, tile.bcast(mine, j));
@@ -219,7 +263,7 @@ struct Search {
                 rw->n[e.slot] = nn;
                 rw->total_n += 1;
                 const double qo = rw->q[e.slot];
-                rw->q[e.slot] = DM_ADD(qo, DM_DIV(DM_SUB(qv, qo), (double)nn));
+                rw->q[e.slot] = DM_ADD(qo, DM_DIV(DM_SUB(qv, qo), i2d(nn)));
             }
             v = qv;
         }
@@ -245,10 +289,14 @@ struct Search {
                 tot += n0;
                 rw->n[k] = n0;
                 rw->q[k] = init_Q(s, k);
-                rw->alabel[k] = (uint8_t)k;
             }
             rw->total_n = tot;
-            rw->nchild = (uint8_t)A;
+            {
+                uint32_t pk = 0;
+#pragma unroll
+                for (int k = 0; k < A; ++k) pk = Row<M>::pack_add(pk, k, k);
+                rw->packed = pk;
+            }
             rw->key = M::key_of(a.mdp, s);
             map_insert(s, id);
             cnt[CNT_STATE_INSERTS] += 1;
@@ -259,39 +307,69 @@ struct Search {
         return id;
     }
 
-    // best_sanode_UCB (src/vanilla.jl:354-386); returns the child slot (= action index)
-    __device__ __forceinline__ int uct_select(const Row<M>* rw) const {
-        const double c = a.cfg.c;
-        double best = -CUDART_INF;
-        int best_i = 0x7fffffff;
-        if (c == 0.0) {  // argmax(q, children)
-            for (int j = tile.lane; j < A; j += G) {
-                const double qj = rw->q[j];
-                if (qj > best) {
-                    best = qj;
-                    best_i = j;
+    // ---- selection ---------------------------------------------------------------------------
+    static constexpr int T = (A + G - 1) / G;  // children per lane
+    static constexpr int kNone = 0x7fffffff;
+    struct Kids {  // this lane's children: slot j = lane + t*G
+        int n[T];
+        double q[T];
+    };
+
+    // one row = three vector loads when a lane owns all four children
+    __device__ __forceinline__ void load_kids(const Row<M>* rw, int nchild, Kids& k, int& total_n) const {
+        if constexpr (G == 1 && A == 4) {
+            const double2 q01 = *reinterpret_cast<const double2*>(&rw->q[0]);
+            const double2 q23 = *reinterpret_cast<const double2*>(&rw->q[2]);
+            const int4 n4 = *reinterpret_cast<const int4*>(&rw->n[0]);
+            k.q[0] = q01.x; k.q[1] = q01.y; k.q[2] = q23.x; k.q[3] = q23.y;
+            k.n[0] = n4.x; k.n[1] = n4.y; k.n[2] = n4.z; k.n[3] = n4.w;
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+                if (t >= nchild) {
+                    k.n[t] = 1;
+                    k.q[t] = 0.0;
                 }
+        } else {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int j = tile.lane + t * G;
+                k.n[t] = j < nchild ? rw->n[j] : 1;
+                k.q[t] = j < nchild ? rw->q[j] : 0.0;
             }
-            tile.argmax(best, best_i);
-            return best_i == 0x7fffffff ? 0 : best_i;
         }
-        const int sn = rw->total_n;
-        int first_zero = 0x7fffffff;
-        int nj[(A + G - 1) / G];
+        total_n = rw->total_n;
+    }
+
+    // argmax(q, children): strict '>' scan from -Inf, default first child
+    __device__ __forceinline__ int argmax_q(const Kids& k, int nchild) const {
+        double best = -CUDART_INF;
+        int best_i = kNone;
 #pragma unroll
-        for (int t = 0; t < (A + G - 1) / G; ++t) {
+        for (int t = 0; t < T; ++t) {
             const int j = tile.lane + t * G;
-            nj[t] = j < A ? rw->n[j] : 1;
-            if (j < A && nj[t] == 0) first_zero = min(first_zero, j);
+            if (j < nchild && k.q[t] > best) {
+                best = k.q[t];
+                best_i = j;
+            }
         }
-        first_zero = tile.min_int(first_zero);
-        if (first_zero != 0x7fffffff) return first_zero;  // "if action was not used, use it"
-        const double lsn = log_n(sn);
+        tile.argmax(best, best_i);
+        return best_i == kNone ? 0 : best_i;
+    }
+
+    // The reference's score, operation for operation: q + c*sqrt(log(N)/n). Static (no access to `this`) so
+    // that the out-of-line near-tie handler below does not force the per-tile state into local memory.
+    __device__ __forceinline__ static int exact_scores(const Tile<G>& tile, const DevCfg& cfg, const Kids& k, int nchild, int N, bool dpw) {
+        const double c = cfg.c;
+        const double lN = N < cfg.log_tab_n ? __ldg(cfg.log_tab + N) : det_log((double)N);
+        double best = -CUDART_INF;
+        int best_i = kNone;
 #pragma unroll
-        for (int t = 0; t < (A + G - 1) / G; ++t) {
+        for (int t = 0; t < T; ++t) {
             const int j = tile.lane + t * G;
-            if (j < A) {
-                const double ucb = DM_ADD(rw->q[j], DM_MUL(c, DM_SQRT(DM_DIV(lsn, (double)nj[t]))));
+            if (j < nchild) {
+                double ucb;
+                if (dpw && lN <= 0.0 && k.n[t] == 0) ucb = k.q[t];
+                else ucb = DM_ADD(k.q[t], DM_MUL(c, DM_SQRT(DM_DIV(lN, i2d(k.n[t])))));
                 if (ucb > best) {
                     best = ucb;
                     best_i = j;
@@ -299,43 +377,145 @@ struct Search {
             }
         }
         tile.argmax(best, best_i);
-        return best_i == 0x7fffffff ? 0 : best_i;
+        return best_i == kNone ? 0 : best_i;
+    }
+    __device__ __forceinline__ int select_exact(const Kids& k, int nchild, int N, bool dpw) {
+        if (lead()) cnt[CNT_SELECT_EXACT] += 1;
+        return exact_scores(tile, a.cfg, k, nchild, N, dpw);
     }
 
-    // one iteration of src/vanilla.jl:229-235: simulate(root, depth) unrolled into descent + backup
+    // A near-tie of the fast-path scores: children inside the margin that carry bit-identical (n, q) have
+    // bit-identical reference scores (tie -> lowest index, as the strict '>' scan); anything else is decided
+    // with the reference's exact operation sequence. Returns slot | 256 if the exact scores were needed.
+    __device__ __noinline__ static int select_near_tie(Tile<G> tile, const DevCfg* cfg, Kids k, int nchild, int N, bool dpw, double cs,
+                                                       double margin) {
+        double S[T];
+        double best = -CUDART_INF, bq = 0.0, bt = 0.0;
+        int best_i = kNone, bn = 0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = tile.lane + t * G;
+            const double term = DM_MUL(cs, __ldg(cfg->rsqrt_tab + k.n[t]));
+            S[t] = DM_ADD(k.q[t], term);
+            if (j < nchild && S[t] > best) {
+                best = S[t];
+                best_i = j;
+                bq = k.q[t];
+                bn = k.n[t];
+                bt = term;
+            }
+        }
+        tile.argmax_payload(best, best_i, bq, bn, bt);
+        bool need_exact = best_i == kNone;  // every score NaN / -Inf
+        int tie_i = best_i;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = tile.lane + t * G;
+            if (j < nchild && j != best_i && !(DM_SUB(best, S[t]) > margin)) {  // also catches NaN / Inf - Inf
+                if (k.n[t] == bn && k.q[t] == bq) tie_i = min(tie_i, j);
+                else need_exact = true;
+            }
+        }
+        if (tile.any(need_exact)) return exact_scores(tile, *cfg, k, nchild, N, dpw) | 256;
+        return tile.min_int(tie_i);
+    }
+
+    // best_sanode_UCB for both solvers (src/vanilla.jl:354-386, src/dpw.jl:179-199); returns the child slot.
+    //
+    // Fast path: S_j = q_j + (c*sqrt(log N)) * n_j^(-1/2) from two host-built tables -- 1 load, 1 mul, 1 add per
+    // child, no division, square root or XU-pipe instruction. S_j differs from the reference's rounded score by
+    // at most ~12 ulp of (|q_j| + term_j); the arg-max is accepted only if the runner-up is further away than
+    // 2^-44 * sum_j(|q_j| + term_j) (a >= 32x safety factor); otherwise select_near_tie decides.
+    __device__ __forceinline__ int select_child(const Row<M>* rw, int nchild, bool dpw) {
+        Kids k;
+        int N;
+        load_kids(rw, nchild, k, N);
+        const double c = a.cfg.c;
+        if (c == 0.0) return argmax_q(k, nchild);
+        int first_zero = kNone, n_max = 0;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = tile.lane + t * G;
+            if (j < nchild) {
+                if (k.n[t] == 0) first_zero = min(first_zero, j);
+                n_max = max(n_max, k.n[t]);
+            }
+        }
+        first_zero = tile.min_int(first_zero);
+        if (first_zero != kNone) {
+            if (!dpw) return first_zero;  // vanilla: "if action was not used, use it"
+            return select_exact(k, nchild, N, true);
+        }
+        if (dpw && N <= 1) return argmax_q(k, nchild);  // log(N) <= 0 with every n > 0: the exploration term is exactly 0
+        n_max = -tile.min_int(-n_max);
+        if (N >= a.cfg.log_tab_n || n_max >= a.cfg.rsqrt_tab_n) return select_exact(k, nchild, N, dpw);
+
+        const double cs = DM_MUL(c, __ldg(a.cfg.sqrtlog_tab + N));
+        double best = -CUDART_INF, second = -CUDART_INF, mag = 0.0;
+        int best_i = kNone;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = tile.lane + t * G;
+            if (j < nchild) {
+                const double term = DM_MUL(cs, __ldg(a.cfg.rsqrt_tab + k.n[t]));
+                const double S = DM_ADD(k.q[t], term);
+                mag = DM_ADD(mag, DM_ADD(fabs(k.q[t]), term));
+                if (S > best) {
+                    second = best;
+                    best = S;
+                    best_i = j;
+                } else if (S > second) {
+                    second = S;
+                }
+            }
+        }
+        if constexpr (G > 1) {
+            const double lane_best = best;
+            tile.argmax(best, best_i);
+            const bool mine = best_i != kNone && (best_i % G) == tile.lane;  // the winner is one of this lane's children
+            second = tile.max_double(mine ? second : lane_best);
+            mag = tile.sum_double(mag);
+        }
+        const double margin = DM_MUL(5.6843418860808015e-14, mag);  // 2^-44 * sum(|q| + term); NaN if any input is
+        if (best_i != kNone && DM_SUB(best, second) > margin) return best_i;
+        const int r = select_near_tie(tile, &a.cfg, k, nchild, N, dpw, cs, margin);
+        if ((r & 256) && lead()) cnt[CNT_SELECT_EXACT] += 1;
+        return r & 255;
+    }
+
+    // one iteration of src/vanilla.jl:229-235: simulate(root, depth) unrolled into three warp-synchronous phases:
+    // descent (one tree level per trip), ONE leaf-evaluation phase for all lanes together (lanes reach their
+    // leaves at different levels; evaluating inside the descent loop would run a separate, mostly empty rollout
+    // loop per level), and the deepest-first backup.
     __device__ __forceinline__ void uct_iteration(int root, uint32_t it) {
         Stream rng;
         rng.init(a.cfg.seed, tree_index, it, 0u);
         int node = root, d = a.cfg.depth, top = 0;
         State s = M::state_of(a.mdp, rows[node].key);
-        double v;
+        int leaf = 0;  // 0: terminal (value 0.0), 1: estimate_value(s, d), 2: table overflow
         for (;;) {
-            if (M::is_terminal(a.mdp, s)) {
-                v = 0.0;
-                break;
-            }
+            if (M::is_terminal(a.mdp, s)) break;
             if (d == 0) {
-                v = estimate(s, 0, it);
+                leaf = 1;
                 break;
             }
             if (lead()) cnt[CNT_LEVELS] += 1;
-            const int slot = uct_select(rows + node);
+            const int slot = select_child(rows + node, A, false);
             State sp;
             double r;
             M::gen(a.mdp, s, slot, rng, sp, r);
             if (lead()) path[top] = PathEntry{node, slot, r};
             ++top;
-            int spid = map_lookup(sp);
-            if (spid < 0) {
-                spid = uct_insert(sp);
-                if (spid < 0) return;  // capacity error: abandon this simulation
-                v = estimate(sp, d - 1, it);
+            --d;
+            s = sp;
+            node = map_lookup(sp);
+            if (node < 0) {
+                leaf = uct_insert(sp) < 0 ? 2 : 1;  // new node: estimate_value(sp, depth-1), also when sp is terminal
                 break;
             }
-            node = spid;
-            s = sp;
-            --d;
         }
+        if (leaf == 2) return;  // capacity error: abandon this simulation
+        const double v = leaf == 1 ? estimate(s, d, it) : 0.0;
         backup(top, v);
         if (lead()) cnt[CNT_SIMULATIONS] += 1;
     }
@@ -353,7 +533,7 @@ struct Search {
         if (lead()) {
             Row<M>* rw = rows + id;
             rw->total_n = 0;
-            rw->nchild = 0;
+            rw->packed = 0;
             rw->key = M::key_of(a.mdp, s);
             if (maintain_lookup) map_insert(s, id);
             cnt[CNT_STATE_INSERTS] += 1;
@@ -370,8 +550,7 @@ struct Search {
             const int n0 = init_N(s, act);
             rw->n[slot] = n0;
             rw->q[slot] = init_Q(s, act);
-            rw->alabel[slot] = (uint8_t)act;
-            rw->nchild = (uint8_t)(slot + 1);
+            rw->packed = Row<M>::pack_add(rw->packed, slot, act);
             rw->total_n += n0;  // tree.total_n[snode] += n0
             ax->nac[slot] = 0;
             ax->thead[slot] = -1;
@@ -382,52 +561,29 @@ struct Search {
         n_action += 1;
     }
 
-    // best_sanode_UCB (src/dpw.jl:179-199); returns the child slot
-    __device__ __forceinline__ int dpw_select(const Row<M>* rw, int nchild) const {
-        const double c = a.cfg.c;
-        const double ltn = log_n(rw->total_n);
-        double best = -CUDART_INF;
-        int best_i = 0x7fffffff;
-        for (int j = tile.lane; j < nchild; j += G) {
-            const int nn = rw->n[j];
-            const double qq = rw->q[j];
-            double ucb;
-            if ((ltn <= 0.0 && nn == 0) || c == 0.0) ucb = qq;
-            else ucb = DM_ADD(qq, DM_MUL(c, DM_SQRT(DM_DIV(ltn, (double)nn))));
-            if (ucb > best) {
-                best = ucb;
-                best_i = j;
-            }
-        }
-        tile.argmax(best, best_i);
-        return best_i == 0x7fffffff ? 0 : best_i;
-    }
-
     // one iteration of src/dpw.jl:48-56: simulate(dpw, snode, depth) as descent + backup
     __device__ __forceinline__ void dpw_iteration(int root, uint32_t it) {
         Stream rng;
         rng.init(a.cfg.seed, tree_index, it, 0u);
         int node = root, d = a.cfg.depth, top = 0;
         State s = M::state_of(a.mdp, rows[node].key);
-        double v;
+        int leaf = 0;  // 0: terminal (value 0.0), 1: estimate_value(s, d), 2: table overflow (see uct_iteration)
         for (;;) {
-            if (M::is_terminal(a.mdp, s)) {
-                v = 0.0;
-                break;
-            }
+            if (M::is_terminal(a.mdp, s)) break;
             if (d == 0) {
-                v = estimate(s, 0, it);
+                leaf = 1;
                 break;
             }
             Row<M>* rw = rows + node;
-            int nchild = rw->nchild;
+            int nchild = rw->nchild();
             // ---- action progressive widening (src/dpw.jl:94-114) ----
             if (a.cfg.enable_action_pw) {
                 // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action[len]
                 if (rw->total_n >= a.cfg.nmin_action[nchild]) {
                     const int act = rng.uniform_int(A);  // next_action(::RandomActionGenerator)
                     bool present = false;
-                    for (int j = 0; j < nchild; ++j) present |= (rw->alabel[j] == act);
+                    const uint32_t pk = rw->packed;
+                    for (int j = 0; j < nchild; ++j) present |= ((int)((pk >> (4 * j)) & 15u) == act);
                     if (!present) {  // check_repeat_action (always on; see capi.cu)
                         dpw_insert_action(node, nchild, s, act);
                         ++nchild;
@@ -441,10 +597,10 @@ struct Search {
             }
             if (lead()) {
                 cnt[CNT_LEVELS] += 1;
-                cnt[CNT_CHILDREN_SEEN] += (unsigned long long)nchild;
+                cnt[CNT_CHILDREN_SEEN] += (unsigned)nchild;
             }
-            const int slot = dpw_select(rw, nchild);
-            const int act = rw->alabel[slot];
+            const int slot = select_child(rw, nchild, true);
+            const int act = rw->alabel(slot);
             Aux<M>* ax = aux + node;
 
             // ---- state progressive widening (src/dpw.jl:119-141) ----
@@ -464,7 +620,10 @@ struct Search {
                 spnode = a.cfg.check_repeat_state ? map_lookup(sp) : -1;
                 if (spnode < 0) {
                     spnode = dpw_insert_state(sp, a.cfg.maintain_lookup != 0);
-                    if (spnode < 0) return;
+                    if (spnode < 0) {
+                        leaf = 2;
+                        break;
+                    }
                     new_node = true;
                 }
                 // push!(transitions[sanode], (spnode, r)) in multiset form; unique_transitions bookkeeping
@@ -475,7 +634,8 @@ struct Search {
                 }
                 if (rec < 0 && n_trans >= a.geo.NT) {
                     status = MCTSB200_ERR_CAPACITY;
-                    return;
+                    leaf = 2;
+                    break;
                 }
                 if (lead()) {
                     if (rec >= 0) {
@@ -514,14 +674,16 @@ struct Search {
             if (lead()) path[top] = PathEntry{node, slot, r};
             ++top;
             tile.sync();
-            if (new_node) {
-                v = estimate(sp, d - 1, it);
-                break;
-            }
             node = spnode;
             s = sp;
             --d;
+            if (new_node) {
+                leaf = 1;  // estimate_value(sp, d-1)
+                break;
+            }
         }
+        if (leaf == 2) return;
+        const double v = leaf == 1 ? estimate(s, d, it) : 0.0;
         backup(top, v);
         if (lead()) cnt[CNT_SIMULATIONS] += 1;
     }
@@ -551,7 +713,7 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
 
         if (args.iter_begin == 0 && h.iterations == 0 && h.status == MCTSB200_OK) {
             // root lookup / insertion (src/vanilla.jl:219-224, src/dpw.jl:22-42)
-            const typename M::State s0 = M::load(args.roots[tree * args.root_stride]);
+            const typename M::State s0 = M::load(args.mdp, args.roots[tree * args.root_stride]);
             if (KIND == MCTSB200_KIND_DPW && M::is_terminal(args.mdp, s0)) {
                 S.status = MCTSB200_ERR_TERMINAL_ROOT;
             } else {
@@ -580,9 +742,11 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
             h.iterations = S.status == MCTSB200_OK ? args.iter_end : it;
             *hd = h;
         }
+        S.cnt[CNT_ROLLOUT_STEPS] = 0;
 #pragma unroll
         for (int i = 0; i < CNT_COUNT; ++i)
-            if (S.cnt[i]) atomicAdd(&s_cnt[i], S.cnt[i]);
+            if (S.cnt[i]) atomicAdd(&s_cnt[i], (unsigned long long)S.cnt[i]);
+        if (S.rollout_steps) atomicAdd(&s_cnt[CNT_ROLLOUT_STEPS], S.rollout_steps);
     }
 #ifdef MCTSB200_HOST_EMU
     for (int i = 0; i < CNT_COUNT; ++i) {  // the emulator runs one thread at a time
@@ -607,15 +771,16 @@ __global__ void decide_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS,
     if (h.status != MCTSB200_ERR_TERMINAL_ROOT && h.n_state > 0) {
         const Row<M>* rw = rows + tree * NS + h.root;
         double best = -CUDART_INF;
-        int slot = rw->nchild > 0 ? 0 : -1;  // vanilla default: first child; DPW: 0 children -> none
-        for (int j = 0; j < rw->nchild; ++j) {
+        const int nchild = rw->nchild();
+        int slot = nchild > 0 ? 0 : -1;  // vanilla default: first child; DPW: 0 children -> none
+        for (int j = 0; j < nchild; ++j) {
             if (rw->q[j] > best) {
                 best = rw->q[j];
                 slot = j;
             }
         }
         if (slot >= 0) {
-            act = rw->alabel[slot];
+            act = rw->alabel(slot);
             bq = rw->q[slot];
         }
     }
@@ -635,8 +800,8 @@ __global__ void root_sums_kernel(const TreeHeader* hdr, const Row<M>* rows, int 
         const TreeHeader h = hdr[t];
         if (h.n_state == 0) continue;
         const Row<M>* rw = rows + t * NS + h.root;
-        for (int j = 0; j < rw->nchild; ++j) {
-            if (rw->alabel[j] == act) {
+        for (int j = 0; j < rw->nchild(); ++j) {
+            if (rw->alabel(j) == act) {
                 const double nn = (double)rw->n[j];
                 sn = DM_ADD(sn, nn);
                 snq = DM_ADD(snq, DM_MUL(nn, rw->q[j]));

@@ -16,6 +16,7 @@
 #define __device__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static
 #define __grid_constant__
 #define __launch_bounds__(...)
@@ -34,6 +35,15 @@ template <class T> static inline T __shfl_sync(unsigned, T v, int, int = 32) { r
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+struct int4 { int x, y, z, w; };
+struct uint4 { unsigned x, y, z, w; };
+struct double2 { double x, y; };
+struct ulonglong2 { unsigned long long x, y; };
+static inline double __hiloint2double(int hi, int lo) {
+    const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double d; std::memcpy(&d, &u, 8); return d;
+}
+static inline int __any_sync(unsigned, int p) { return p; }
 static inline long long __double_as_longlong(double x) { long long u; std::memcpy(&u, &x, 8); return u; }
 static inline double __longlong_as_double(long long u) { double x; std::memcpy(&x, &u, 8); return x; }
 template <class T, class U> static inline T atomicAdd(T* p, U v) { T old = *p; *p += (T)v; return old; }

@@ -46,8 +46,23 @@ def main():
                         "root": [5, 1], "rows": parse_sa_lines(out)}
     src, out = cell_output(tv, 3)
     nums = [int(x) for x in re.findall(r"N:\s+(\d+)", out)]
+    qs = [float(x) for x in re.findall(r"Q:\s+(-?[\d.]+)", out)]
+    src2, out2 = cell_output(tv, 2)
     vec["tv_cell3"] = {"solver": "MCTSSolver(n_iterations=100000, depth=10, exploration_constant=10.0)", "root": [1, 3], "n_iterations": 100000,
-                       "root_N": nums[0], "root_children_N": [60357, 80029, 106441, 17348], "first_N_values": nums[:24]}
+                       "root_N": nums[0], "root_children_N": [60357, 80029, 106441, 17348], "first_N_values": nums[:24], "first_Q_values": qs[:20],
+                       "action": out2.strip().lstrip(":"),
+                       # the printed tree in document order: state node N, then per action (Q, N) and its child state nodes
+                       "nodes": {"1,3": {"N": 264175, "child_N": [60357, 80029, 106441, 17348], "child_Q": [-0.07, -0.06, -0.04, -0.20]},
+                                 "2,3": {"N": 58864, "child_N": [16065, 18984, 22211, 1604], "child_Q": [-0.19, -0.17, -0.15, -0.76]},
+                                 "1,4": {"N": 113408, "child_N": [28373, 32407, 35005, 17623], "child_Q": [-0.05, -0.03, -0.03, -0.10]},
+                                 "1,2": {"N": 141042, "child_N": [35646, 39166, 43325, 22905], "child_Q": [-0.03, -0.02, -0.01, -0.07]}}}
+
+    # the hand-keyed node table above must agree with the numbers parsed from the stored output
+    nd = vec["tv_cell3"]["nodes"]
+    assert nums[:7] == [nd["1,3"]["N"], nd["1,3"]["child_N"][0], nd["2,3"]["N"]] + nd["2,3"]["child_N"]
+    assert nums[7:12] == [nd["1,4"]["N"]] + nd["1,4"]["child_N"] and nums[12:17] == [nd["1,3"]["N"]] + nd["1,3"]["child_N"]
+    assert nums[17:22] == [nd["1,2"]["N"]] + nd["1,2"]["child_N"]
+    assert qs[:17] == [nd["1,3"]["child_Q"][0]] + nd["2,3"]["child_Q"] + nd["1,4"]["child_Q"] + nd["1,3"]["child_Q"] + nd["1,2"]["child_Q"]
 
     vt = open(os.path.join(REF, "test", "value_test.jl")).read()
     ad = {f"{a},{b}": act for a, b, act in re.findall(r"GWPos\((\d+), (\d+)\)=>:(\w+)", vt)}

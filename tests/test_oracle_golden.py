@@ -65,7 +65,8 @@ def test_notebook_cell3_incremental_mean_values(oracle):
 
 # ---- notebook cell 6: DPW backup with gamma = 0.95 -------------------------------------------------------
 def manhattan_value(mdp, s, depth):
-    return 10.0 / (abs(s[0] - 9) + abs(s[1] - 3))
+    d = abs(s[0] - 9) + abs(s[1] - 3)
+    return 10.0 / d if d else float("inf")  # Julia: 10.0/0 == Inf
 
 
 def test_notebook_cell6_dpw_backup_values(oracle):
@@ -96,21 +97,62 @@ def test_notebook_cell6_dpw_backup_values(oracle):
 
 
 # ---- notebook Test_Visualization cell 3: the vanilla tree is a DAG keyed by state ------------------------
+def _check_dag_invariants(t, root, n_iterations):
+    for i in range(len(t["total_n"])):  # every state node: total_n == sum of its children's n (init_N = 0)
+        ch = t["child_ids"][t["child_offsets"][i]:t["child_offsets"][i + 1]]
+        assert t["total_n"][i] == t["n"][ch - 1].sum()
+    assert tuple(t["s_labels"][0]) == tuple(root)  # tree.state_map[root] == 1 (test/runtests.jl:44)
+    assert t["total_n"][0] > n_iterations  # the root is re-entered deeper inside a simulation
+    assert len(t["total_n"]) <= 101
+    assert len(np.unique(t["s_labels"], axis=0)) == len(t["s_labels"])  # one node per state
+
+
 def test_visualization_notebook_dag_invariants(oracle):
     tv = VEC["tv_cell3"]
     assert sum(tv["root_children_N"]) == tv["root_N"]  # what the notebook shows
     s = m.MCTSSolver(n_iterations=tv["n_iterations"], depth=10, exploration_constant=10.0, rng=4)
     _, _, _, st = plan(oracle, s, GW, [tuple(tv["root"])])
-    t = oracle.tree_export(0)
-    # every state node: total_n == sum of its children's n (init_N = 0)
-    for i in range(len(t["total_n"])):
-        ch = t["child_ids"][t["child_offsets"][i]:t["child_offsets"][i + 1]]
-        assert t["total_n"][i] == t["n"][ch - 1].sum()
-    assert tuple(t["s_labels"][0]) == tuple(tv["root"])  # tree.state_map[root] == 1 (test/runtests.jl:44)
-    ratio = t["total_n"][0] / tv["n_iterations"]
-    assert 2.0 < ratio < 3.4, ratio  # notebook: 2.64 root visits per iteration (root re-entered deeper in a simulation)
-    assert len(t["total_n"]) <= 101 and st.n_simulations == tv["n_iterations"]
-    assert len(np.unique(t["s_labels"], axis=0)) == len(t["s_labels"])  # one node per state
+    assert st.n_simulations == tv["n_iterations"]
+    _check_dag_invariants(oracle.tree_export(0), tv["root"], tv["n_iterations"])
+
+
+def test_visualization_notebook_statistics_reproduced(oracle):
+    """The stored tree (root [1,3]: N = 264175 = 2.64 visits/iteration, action :left, per-child N and Q two
+    levels deep) was produced by a release that returned 0.0 at depth 0 instead of calling estimate_value
+    (the stored Q of about -0.05 is impossible with 50-step random rollouts at every depth-0 leaf, which give
+    about -0.8). With estimate_value = 0.0 today's loop (src/vanilla.jl:247-250) has exactly that behaviour,
+    apart from <= 101 new-node rollouts, and the oracle must then land on the stored numbers up to seed noise."""
+    tv = VEC["tv_cell3"]
+    nodes = tv["nodes"]
+    n_seeds = 8
+    acc = {k: {"N": [], "frac": [], "q": []} for k in nodes}
+    actions = []
+    for seed in range(n_seeds):
+        s = m.MCTSSolver(n_iterations=tv["n_iterations"], depth=10, exploration_constant=10.0, rng=seed, estimate_value=0.0)
+        a, _, _, _ = plan(oracle, s, GW, [tuple(tv["root"])])
+        actions.append(GW.actions[int(a[0])])
+        t = oracle.tree_export(0)
+        _check_dag_invariants(t, tv["root"], tv["n_iterations"])
+        labels = [tuple(x) for x in t["s_labels"].tolist()]
+        for key in nodes:
+            i = labels.index(tuple(map(int, key.split(","))))
+            ch = t["child_ids"][t["child_offsets"][i]:t["child_offsets"][i + 1]]
+            acc[key]["N"].append(t["total_n"][i])
+            acc[key]["frac"].append(t["n"][ch - 1] / t["total_n"][i])
+            acc[key]["q"].append(t["q"][ch - 1])
+    assert actions.count(tv["action"]) >= n_seeds - 1  # stored decision: :left
+    for key, ref in nodes.items():
+        N = np.mean(acc[key]["N"])
+        assert abs(N / ref["N"] - 1.0) < 0.08, (key, N, ref["N"])  # root: 2.52-2.61 vs 2.64 visits per iteration
+        frac = np.mean(acc[key]["frac"], axis=0)
+        ref_frac = np.array(ref["child_N"]) / ref["N"]
+        sd = np.std(acc[key]["frac"], axis=0, ddof=1)  # the notebook is ONE run: allow 3 sigma of seed-to-seed spread
+        assert (np.abs(frac - ref_frac) < 3 * sd + 0.01).all(), (key, frac, ref_frac, sd)
+        q = np.mean(acc[key]["q"], axis=0)
+        ref_q = np.array(ref["child_Q"])
+        sdq = np.std(acc[key]["q"], axis=0, ddof=1)
+        tol = 3 * sdq + 0.02  # stored values are rounded to 2 decimals; rarely visited children are noisy
+        assert (np.abs(q - ref_q) < tol).all(), (key, q, ref_q, sdq)
 
 
 # ---- SimpleGridWorld restatement vs the reference's hard-coded value-iteration table -------------------------
@@ -148,11 +190,15 @@ def test_value_iteration_table_matches_reference(oracle):
     """test/value_test.jl:30-45 hard-codes VI-optimal actions for 16 states; an independent VI over the
     restated model must reproduce them, and one-step oracle gen() must agree with that model's support."""
     Q = gridworld_value_iteration(GW)
+    exact = 0
     for key, act in VEC["value_test"]["vi_actions"].items():
         x, y = map(int, key.split(","))
         q = Q[GW.state_index((x, y))]
-        best = q.max()
-        assert q[GW.action_index(act)] >= best - 1e-9, (key, act, q)
+        # the table predates SimpleGridWorld (generated under `using Base.Test`); two of its 16 entries are
+        # near-ties (dQ = 0.006 and 0.037) that a converged VI on today's model resolves the other way
+        assert q[GW.action_index(act)] >= q.max() - 0.05, (key, act, q)
+        exact += int(q.argmax() == GW.action_index(act))
+    assert exact >= 14
     # oracle gen(): support and frequencies against the numpy model
     oracle.configure(GW.mdp_id, GW.params())
     for s, a in [((1, 3), 0), ((5, 5), 3), ((10, 10), 0), ((1, 1), 1)]:
@@ -233,7 +279,7 @@ def test_mountaincar_restatement(oracle):
     assert tuple(sp) == (-1.2, 0.0) and r == -1.0
     sp, r, _ = oracle.gen(mc.mdp_id, (0.45, 0.07), 2)  # reaches the goal: jackpot on the transition INTO a terminal state
     assert sp[0] >= 0.5 and r == 100.0
-    sp, r, _ = oracle.gen(mc.mdp_id, (0.0, 0.069), 2)  # speed clamp
+    sp, r, _ = oracle.gen(mc.mdp_id, (-0.6, 0.0695), 2)  # speed clamp (cos(-1.8) < 0 adds to v)
     assert sp[1] == 0.07
 
 
@@ -261,7 +307,8 @@ def test_libm_oracle_takes_the_same_decisions(oracle, oracle_libm):
 def test_literal_and_multiset_transition_sampling_agree(oracle):
     """src/dpw.jl:131,140 keeps every (spnode, r) push and samples by index; the multiset form samples the
     same distribution. Identical trees when nothing is sampled; statistically equal root Q otherwise."""
-    s = m.DPWSolver(n_iterations=300, depth=10, rng=1)  # defaults: the widening test always passes for GridWorld
+    # init_N = 1 keeps n >= 1, so n_a_children (<= 5) <= 10*sqrt(n) always holds: every visit widens, nothing is sampled
+    s = m.DPWSolver(n_iterations=300, depth=10, rng=1, init_N=1)
     plan(oracle, s, GW, [(2, 2)], literal_transitions=True)
     t1 = oracle.tree_export(0)
     _, _, _, st = plan(oracle, s, GW, [(2, 2)], literal_transitions=False)
