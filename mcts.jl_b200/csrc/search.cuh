@@ -126,6 +126,14 @@ struct Search {
     // rollout steps can exceed that and are kept in 64 bits)
     unsigned cnt[CNT_COUNT];
     unsigned long long rollout_steps;
+#ifdef MCTSB200_PHASE_TIMING
+    long long cyc[4] = {0, 0, 0, 0};  // descent, leaf evaluation, backup, trips
+#define PT_CLOCK(var) const long long var = clock64()
+#define PT_ADD(i, v) cyc[i] += (v)
+#else
+#define PT_CLOCK(var)
+#define PT_ADD(i, v)
+#endif
 
     __device__ __forceinline__ Search(const KernelArgs<M>& args, long long tree) : a(args) {
         rows = args.rows + tree * args.geo.NS;
@@ -493,7 +501,9 @@ struct Search {
         int node = root, d = a.cfg.depth, top = 0;
         State s = M::state_of(a.mdp, rows[node].key);
         int leaf = 0;  // 0: terminal (value 0.0), 1: estimate_value(s, d), 2: table overflow
+        PT_CLOCK(t0);
         for (;;) {
+            PT_ADD(3, 1);
             if (M::is_terminal(a.mdp, s)) break;
             if (d == 0) {
                 leaf = 1;
@@ -515,8 +525,16 @@ struct Search {
             }
         }
         if (leaf == 2) return;  // capacity error: abandon this simulation
+        tile.sync();
+        PT_CLOCK(t1);
         const double v = leaf == 1 ? estimate(s, d, it) : 0.0;
+        tile.sync();
+        PT_CLOCK(t2);
         backup(top, v);
+        PT_CLOCK(t3);
+        PT_ADD(0, t1 - t0);
+        PT_ADD(1, t2 - t1);
+        PT_ADD(2, t3 - t2);
         if (lead()) cnt[CNT_SIMULATIONS] += 1;
     }
 
@@ -733,6 +751,12 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
             else S.dpw_iteration(root, (uint32_t)it);
         }
 
+#ifdef MCTSB200_PHASE_TIMING
+        if ((threadIdx.x & 31) == 0 && (blockIdx.x % 97) == 0 && threadIdx.x < 64)
+            printf("PT block %d warp %d: iters %d descent %lld leaf %lld backup %lld (cycles/iter) trips/iter %.2f\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
+                   args.iter_end - args.iter_begin, S.cyc[0] / (args.iter_end - args.iter_begin), S.cyc[1] / (args.iter_end - args.iter_begin),
+                   S.cyc[2] / (args.iter_end - args.iter_begin), (double)S.cyc[3] / (args.iter_end - args.iter_begin));
+#endif
         if (S.lead()) {
             h.n_state = S.n_state;
             h.n_action = S.n_action;
