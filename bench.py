@@ -47,7 +47,7 @@ WORKLOADS = {
 }
 
 
-def make_workload(name, n_roots=None, lanes=0, n_iterations=None):
+def make_workload(name, n_roots=None, lanes=0, n_iterations=None, same_root=None):
     import mcts_jl_b200 as m
     from helpers import gridworld_roots, mountaincar_roots
 
@@ -62,6 +62,8 @@ def make_workload(name, n_roots=None, lanes=0, n_iterations=None):
     kw["lanes_per_tree"] = lanes
     solver = (m.MCTSSolver if w["kind"] == "uct" else m.DPWSolver)(rng=0, **kw)
     roots = gridworld_roots(n) if w["mdp"] == "gw" else mountaincar_roots(n)
+    if same_root:  # experiment: every tree plans from the same root state
+        roots = [tuple(int(v) for v in same_root.split(","))] * n
     return mdp, solver, mdp.encode_states(roots)
 
 
@@ -187,6 +189,7 @@ def main():
     ap.add_argument("--iterations", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--same-root", default="", help="experiment: x,y of a GridWorld root used for every tree")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -214,7 +217,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    mdp, solver, roots_np = make_workload(args.workload, args.roots or None, args.lanes, args.iterations or None)
+    mdp, solver, roots_np = make_workload(args.workload, args.roots or None, args.lanes, args.iterations or None, args.same_root or None)
     n_roots = roots_np.shape[0]
     base = rank * n_roots  # global root index of this rank's shard
     cfg, keep = m.build_cfg(solver, mdp)

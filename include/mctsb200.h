@@ -144,7 +144,7 @@ typedef struct {
     int32_t lanes_per_tree;      /* the value actually used                                         */
     int32_t n_kernel_launches;
     int32_t iterations_done;     /* < n_iterations only when max_time stopped the search           */
-    int32_t reserved0;
+    int32_t kernel_variant;      /* 0 = tile kernel (search.cuh), 1 = shared-memory lane-per-tree UCT kernel (uct_fast.cuh) */
 } mctsb200_plan_stats;
 
 typedef struct mctsb200_ctx mctsb200_ctx;

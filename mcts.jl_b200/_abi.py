@@ -120,7 +120,7 @@ class PlanStats(C.Structure):
         ("lanes_per_tree", C.c_int32),
         ("n_kernel_launches", C.c_int32),
         ("iterations_done", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("kernel_variant", C.c_int32),
     ]
 
     def as_dict(self) -> dict:

@@ -13,11 +13,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "search.cuh"
+#include "uct_fast.cuh"
 
 using namespace mctsb200;
 
@@ -63,6 +65,7 @@ struct DevBuf {
 
 struct Storage {
     bool valid = false;
+    bool direct = false;  // rows indexed by the state's dense index (uct_fast.cuh); Row::key holds the insertion sequence number
     int kind = 0, mdp_id = 0;
     long long n_trees = 0;
     Geometry geo{};
@@ -82,11 +85,12 @@ struct mctsb200_ctx {
     bool gw_ok = false, mc_ok = false;
     mctsb200_gridworld_params gw_host{};
     GridWorldDev::Params gw_dev{};
-    DevBuf gw_reward, gw_term;
+    DevBuf gw_reward, gw_term, gw_fast;
     MountainCarDev::Params mc_dev{};
 
     Storage st;
     DevBuf counters, log_tab, sqrtlog_tab, rsqrt_tab, nmin_state, init_q, init_n, value_tab, io_roots, io_action, io_bestq, io_status, sums;
+    DevBuf order, order_bins, policy_tab;
     int log_tab_n = 0;
 };
 
@@ -105,6 +109,17 @@ struct MdpAccess<GridWorldDev> {
         return (inb || term) ? 0 : -1;
     }
     static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_GW_SEEK; }
+    // a state-only deterministic rollout policy as a table over dense state indices (GridWorldDev::policy_action restated on the host)
+    static bool tabulate_policy(const mctsb200_ctx* c, const mctsb200_solver_cfg* cfg, std::vector<unsigned char>& out) {
+        if (cfg->rollout_policy != MCTSB200_POLICY_GW_SEEK) return false;
+        const int nx = c->gw_dev.nx, n = c->gw_dev.ncells;
+        out.assign((size_t)n + 1, 0);
+        for (int cell = 0; cell <= n; ++cell) {
+            const int x = cell % nx + 1, y = cell / nx + 1, tx = cfg->rollout_policy_param[0], ty = cfg->rollout_policy_param[1];
+            out[(size_t)cell] = (unsigned char)(tx > x ? 3 : tx < x ? 2 : ty > y ? 0 : 1);
+        }
+        return true;
+    }
 };
 template <>
 struct MdpAccess<MountainCarDev> {
@@ -211,7 +226,7 @@ int32_t validate_cfg(const mctsb200_solver_cfg* cfg, int n_actions, bool dense, 
 }
 
 template <class M>
-int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_trees) {
+int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_trees, bool direct) {
     constexpr int A = M::kActions;
     const bool dpw = cfg->kind == MCTSB200_KIND_DPW;
     const long long n_iter = cfg->n_iterations;
@@ -219,6 +234,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     const bool merge_states = !dpw || cfg->check_repeat_state;
     long long NS = n_iter + 1;
     if (M::kDense && merge_states) NS = std::min<long long>(NS, dense);
+    if (direct) NS = dense;
     const bool maintain_lookup = !dpw || cfg->keep_tree || cfg->check_repeat_state;
     if (M::kDense && maintain_lookup && NS > 65535) return fail(MCTSB200_ERR_CAPACITY, "dense state map limited to 65535 nodes per tree");
     long long NT = 0;
@@ -229,7 +245,10 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     }
     long long MAP = 0;
     size_t map_entry = 0;
-    if (M::kDense) {
+    if (direct) {
+        MAP = 0;
+        map_entry = sizeof(uint16_t);
+    } else if (M::kDense) {
         MAP = (dense + 63) / 64 * 64;
         map_entry = sizeof(uint16_t);
     } else {
@@ -247,7 +266,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     const size_t b_aux = dpw ? sizeof(Aux<M>) * (size_t)NS * (size_t)n_trees : 0;
     const size_t b_trans = dpw ? sizeof(TransRec) * (size_t)g.NT * (size_t)n_trees : 0;
     const size_t b_map = map_entry * (size_t)MAP * (size_t)n_trees;
-    const size_t b_path = sizeof(PathEntry) * (size_t)g.depth * (size_t)n_trees;
+    const size_t b_path = direct ? 0 : sizeof(PathEntry) * (size_t)g.depth * (size_t)n_trees;
     const size_t total = b_hdr + b_rows + b_aux + b_trans + b_map + b_path;
 
     Storage& st = ctx->st;
@@ -265,6 +284,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     CUDA_TRY(st.map.ensure(b_map));
     CUDA_TRY(st.path.ensure(b_path));
     st.kind = cfg->kind;
+    st.direct = direct;
     st.mdp_id = M::kMdpId;
     st.n_trees = n_trees;
     st.geo = g;
@@ -272,7 +292,8 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     st.aux_bytes = sizeof(Aux<M>);
     st.map_entry_bytes = map_entry;
     CUDA_TRY(cudaMemsetAsync(st.hdr.p, 0, b_hdr, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync(st.map.p, 0, b_map, ctx->stream));
+    if (b_map) CUDA_TRY(cudaMemsetAsync(st.map.p, 0, b_map, ctx->stream));
+    if (direct) CUDA_TRY(cudaMemsetAsync(st.rows.p, 0, b_rows, ctx->stream));  // Row::packed == 0 <=> state not in the tree
     return MCTSB200_OK;
 }
 
@@ -300,6 +321,14 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
 
     long long max_init_n = cfg->init_N;
     const int dense = MdpAccess<M>::dense_count(ctx);
+    if constexpr (M::kFast) {
+        std::vector<unsigned char> pol;
+        if (cfg->estimate_kind == MCTSB200_EST_ROLLOUT && MdpAccess<M>::tabulate_policy(ctx, cfg, pol)) {
+            CUDA_TRY(ctx->policy_tab.ensure(pol.size()));
+            CUDA_TRY(cudaMemcpy(ctx->policy_tab.p, pol.data(), pol.size(), cudaMemcpyHostToDevice));
+            d.policy_table = (const unsigned char*)ctx->policy_tab.p;
+        }
+    }
     if (cfg->init_q_table) {
         const size_t bytes = sizeof(double) * (size_t)dense * A;
         CUDA_TRY(ctx->init_q.ensure(bytes));
@@ -373,6 +402,22 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     return MCTSB200_OK;
 }
 
+// debugging / tuning switches (environment): MCTSB200_PATH_SMEM=0 keeps the tile kernel's path stacks in HBM,
+// MCTSB200_FAST=0 disables the shared-memory lane-per-tree UCT kernel, MCTSB200_LANE_ORDER=1 groups trees with
+// equal root states into the same warps (off by default: measured slower)
+bool env_enabled(const char* name, bool dflt = true) {
+    const char* v = std::getenv(name);
+    if (!v || !v[0]) return dflt;
+    return v[0] != '0';
+}
+
+bool use_path_smem(int depth, int G) {
+#ifdef MCTSB200_HOST_EMU
+    return false;
+#endif
+    return env_enabled("MCTSB200_PATH_SMEM") && path_smem_bytes(depth, G) <= kPathSmemLimit;
+}
+
 template <class M, int KIND>
 int pick_lanes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_trees) {
 #ifdef MCTSB200_HOST_EMU
@@ -381,8 +426,10 @@ int pick_lanes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_tr
     if (cfg->lanes_per_tree) return cfg->lanes_per_tree;
     // widest tile that still lets every tree be resident at once (one wave)
     int best = 1;
+    const int depth = std::max(cfg->depth, 1);
     for (int G = 2; G <= 32; G *= 2) {
-        const long long resident = (long long)search_occupancy<M, KIND>(G) * kBlockThreads * ctx->sm_count;
+        const size_t smem = use_path_smem(depth, G) ? path_smem_bytes(depth, G) : 0;
+        const long long resident = (long long)search_occupancy<M, KIND>(G, smem) * kBlockThreads * ctx->sm_count;
         if (n_trees * G <= resident) best = G;
     }
     // a tile wider than the work it can share only idles lanes
@@ -406,6 +453,32 @@ void fill_stats(mctsb200_plan_stats* s, const mctsb200_solver_cfg* cfg, const un
         s->algorithmic_bytes = 144 * s->n_tree_levels + 24 * s->n_dpw_children_seen + 56 * s->n_state_inserts + 72 * s->n_action_inserts;
 }
 
+constexpr size_t kFastSmemLimit = 220 * 1024;
+
+// The shared-memory lane-per-tree kernel (uct_fast.cuh) applies to vanilla UCT with one rollout per leaf on a
+// dense-state MDP whose tables fit in shared memory. Returns the policy variant or -1.
+template <class M, int KIND>
+int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg) {
+    if constexpr (!M::kFast || KIND != MCTSB200_KIND_UCT) {
+        return -1;
+    } else {
+        if (!env_enabled("MCTSB200_FAST")) return -1;
+        if (cfg->estimate_kind != MCTSB200_EST_ROLLOUT || cfg->rollouts_per_leaf != 1 || cfg->lanes_per_tree > 1) return -1;
+        if (cfg->init_q_table || cfg->init_n_table) return -1;
+        const int dense = MdpAccess<M>::dense_count(ctx);
+        // direct-indexed rows cost dense*64 B per tree: only when the tree can actually grow to that order of size
+        if (dense > 256 && (long long)dense > 4 * (cfg->n_iterations + 1)) return -1;
+        if (cfg->depth > 254) return -1;  // level bytes in the row stamps
+        if (fast_smem_bytes<M>(MdpAccess<M>::params(ctx), std::max(cfg->depth, 1), 64) > kFastSmemLimit) return -1;
+        switch (cfg->rollout_policy) {
+            case MCTSB200_POLICY_RANDOM: return FAST_POLICY_RANDOM;
+            case MCTSB200_POLICY_CONSTANT: return FAST_POLICY_CONSTANT;
+            case MCTSB200_POLICY_GW_SEEK: return FAST_POLICY_TABLE;
+            default: return -1;
+        }
+    }
+}
+
 // Runs the search for trees whose roots are already on the device. d_* outputs may be null.
 template <class M, int KIND>
 int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const typename M::AbiState* d_roots, long long n_trees,
@@ -414,7 +487,8 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     DevCfg dcfg;
     int32_t rc = build_dev_cfg<M>(ctx, cfg, dcfg);
     if (rc) return rc;
-    rc = setup_storage<M>(ctx, cfg, n_trees);
+    const int fast = fast_variant<M, KIND>(ctx, cfg);
+    rc = setup_storage<M>(ctx, cfg, n_trees, fast >= 0);
     if (rc) return rc;
     Storage& st = ctx->st;
     CUDA_TRY(ctx->counters.ensure(sizeof(unsigned long long) * CNT_COUNT));
@@ -437,19 +511,64 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.tree_index_base = tree_index_base;
     args.root_stride = root_stride;
 
-    const int G = pick_lanes<M, KIND>(ctx, cfg, n_trees);
+    const int G = fast >= 0 ? 1 : pick_lanes<M, KIND>(ctx, cfg, n_trees);
     const int n_iter = (int)cfg->n_iterations;
     int launches = 0, done = 0;
+    args.path_smem = fast < 0 && use_path_smem(st.geo.depth, G) ? 1 : 0;
+    args.n_slots = n_trees;
+    if constexpr (M::kDense) {
+        if (root_stride == 1 && n_trees > 32 && n_trees < (1LL << 30) && env_enabled("MCTSB200_LANE_ORDER", false)) {
+            const int n_bins = MdpAccess<M>::dense_count(ctx);
+            const int tpw = 32 / G;  // tiles per warp
+            // upper bound of the padded slot count (the exact one is only known on the device): every non-empty
+            // group wastes at most tpw-1 slots
+            const long long bound = n_trees + std::min<long long>(n_bins, n_trees) * (tpw - 1);
+            const long long n_warps = (bound + tpw - 1) / tpw;
+            long long mul = (long long)((double)n_warps * 0.6180339887498949) | 1;
+            auto gcd = [](long long x, long long y) { while (y) { const long long t = x % y; x = y; y = t; } return x; };
+            while (gcd(mul, n_warps) != 1) mul += 2;
+            if (n_warps < 8) mul = 1;
+            const unsigned grid = (unsigned)((n_trees + 255) / 256);
+            CUDA_TRY(ctx->order.ensure(sizeof(int) * (size_t)(n_warps * tpw)));
+            CUDA_TRY(ctx->order_bins.ensure(sizeof(int) * (size_t)n_bins));
+            CUDA_TRY(cudaMemsetAsync(ctx->order_bins.p, 0, sizeof(int) * (size_t)n_bins, ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(ctx->order.p, 0xff, sizeof(int) * (size_t)(n_warps * tpw), ctx->stream));
+            auto hist = order_hist_kernel<M>;
+            auto scatter = order_scatter_kernel<M>;
+            MCTSB200_LAUNCH(hist, grid, 256, 0, ctx->stream, args.mdp, d_roots, n_trees, (int*)ctx->order_bins.p);
+            MCTSB200_LAUNCH(order_scan_kernel, 1, 1024, 0, ctx->stream, (int*)ctx->order_bins.p, n_bins, tpw);
+            MCTSB200_LAUNCH(scatter, grid, 256, 0, ctx->stream, args.mdp, d_roots, n_trees, (int*)ctx->order_bins.p, (int*)ctx->order.p, tpw, n_warps, mul);
+            CUDA_TRY(cudaGetLastError());
+            args.order = (const int*)ctx->order.p;
+            args.n_slots = n_warps * tpw;
+            launches += 3;
+        }
+    }
+    // one search launch over iterations [args.iter_begin, args.iter_end)
+    auto launch = [&]() -> int32_t {
+        if constexpr (M::kFast && KIND == MCTSB200_KIND_UCT) {
+            if (fast >= 0) {
+                // one block per SM, as many lanes as the batch needs and the per-level records in shared memory allow
+                const long long per_sm = (args.n_slots + ctx->sm_count - 1) / ctx->sm_count;
+                int block = (int)std::min<long long>(kFastMaxThreads, std::max<long long>(32, (per_sm + 31) / 32 * 32));
+                while (block > 32 && fast_smem_bytes<M>(args.mdp, args.geo.depth, block) > kFastSmemLimit) block -= 32;
+                const int grid = (int)((args.n_slots + block - 1) / block);
+                return launch_uct_fast<M>(args, fast, grid, block, fast_smem_bytes<M>(args.mdp, args.geo.depth, block), ctx->stream);
+            }
+        }
+        launch_search<M, KIND>(args, G, ctx->stream);
+        return MCTSB200_OK;
+    };
     float kernel_ms = 0.f;
     const auto t_start = std::chrono::steady_clock::now();
     if (!std::isfinite(cfg->max_time)) {
         args.iter_begin = 0;
         args.iter_end = n_iter;
         CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-        launch_search<M, KIND>(args, G, ctx->stream);
+        if (launch()) return fail(MCTSB200_ERR_CUDA, "launching the search kernel failed");
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
-        launches = 1;
+        launches += 1;
         done = n_iter;
     } else {
         // max_time (src/vanilla.jl:232, src/dpw.jl:52): the timer is read after each chunk of iterations;
@@ -460,7 +579,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             args.iter_begin = done;
             args.iter_end = std::min(n_iter, done + chunk);
             const auto c0 = std::chrono::steady_clock::now();
-            launch_search<M, KIND>(args, G, ctx->stream);
+            if (launch()) return fail(MCTSB200_ERR_CUDA, "launching the search kernel failed");
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             ++launches;
@@ -476,10 +595,17 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         }
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     }
+    if (fast >= 0) {
+        const long long n_rows = n_trees * st.geo.NS;
+        auto kernel = total_n_kernel<M>;
+        MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (Row<M>*)st.rows.p, n_rows);
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+    }
     {
         const unsigned grid = (unsigned)((n_trees + 127) / 128);
         auto kernel = decide_kernel<M>;
-        MCTSB200_LAUNCH(kernel, grid, 128, ctx->stream, (const TreeHeader*)st.hdr.p, (const Row<M>*)st.rows.p, st.geo.NS, n_trees, d_action, d_bestq,
+        MCTSB200_LAUNCH(kernel, grid, 128, 0, ctx->stream, (const TreeHeader*)st.hdr.p, (const Row<M>*)st.rows.p, st.geo.NS, n_trees, d_action, d_bestq,
                         d_status);
         CUDA_TRY(cudaGetLastError());
         ++launches;
@@ -497,6 +623,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         stats->lanes_per_tree = G;
         stats->n_kernel_launches = launches;
         stats->iterations_done = done;
+        stats->kernel_variant = fast >= 0 ? 1 : 0;
     }
     return MCTSB200_OK;
 }
@@ -591,7 +718,7 @@ int32_t root_parallel_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg
         d_sums = (double*)ctx->sums.p;
     }
     auto kernel = root_sums_kernel<M>;
-    MCTSB200_LAUNCH(kernel, 1, 32, ctx->stream, (const TreeHeader*)ctx->st.hdr.p, (const Row<M>*)ctx->st.rows.p, ctx->st.geo.NS, n_trees, d_sums);
+    MCTSB200_LAUNCH(kernel, 1, 32, 0, ctx->stream, (const TreeHeader*)ctx->st.hdr.p, (const Row<M>*)ctx->st.rows.p, ctx->st.geo.NS, n_trees, d_sums);
     CUDA_TRY(cudaGetLastError());
     double h[2 * M::kActions];
     CUDA_TRY(cudaMemcpyAsync(h, d_sums, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
@@ -624,7 +751,21 @@ int32_t fetch_tree(mctsb200_ctx* ctx, long long i, HostTree<M>& t) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemcpy(&t.h, (const TreeHeader*)st.hdr.p + i, sizeof(TreeHeader), cudaMemcpyDeviceToHost));
     t.rows.resize((size_t)t.h.n_state);
-    if (t.h.n_state) CUDA_TRY(cudaMemcpy(t.rows.data(), (const Row<M>*)st.rows.p + i * st.geo.NS, sizeof(Row<M>) * (size_t)t.h.n_state, cudaMemcpyDeviceToHost));
+    if (st.direct) {
+        // rows are stored by dense state index; bring them into insertion order and restore the key
+        if constexpr (M::kDense) {
+            std::vector<Row<M>> all((size_t)st.geo.NS);
+            CUDA_TRY(cudaMemcpy(all.data(), (const Row<M>*)st.rows.p + i * st.geo.NS, sizeof(Row<M>) * all.size(), cudaMemcpyDeviceToHost));
+            for (size_t cell = 0; cell < all.size(); ++cell) {
+                if (all[cell].packed == 0) continue;
+                const size_t seq = (size_t)all[cell].key;
+                if (seq == 0 || seq > t.rows.size()) return fail(MCTSB200_ERR_STATE, "corrupt direct-indexed node table");
+                t.rows[seq - 1] = all[cell];
+                t.rows[seq - 1].key = (typename M::Key)cell;
+            }
+        }
+    } else if (t.h.n_state)
+        CUDA_TRY(cudaMemcpy(t.rows.data(), (const Row<M>*)st.rows.p + i * st.geo.NS, sizeof(Row<M>) * (size_t)t.h.n_state, cudaMemcpyDeviceToHost));
     if (st.kind == MCTSB200_KIND_DPW) {
         t.aux.resize((size_t)t.h.n_state);
         t.trans.resize((size_t)t.h.n_trans);
@@ -798,7 +939,7 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->counters,
                       &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
-                      &c->sums};
+                      &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->gw_fast};
     for (DevBuf* b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -863,6 +1004,25 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
         const double p_other = (1.0 - p.tprob) / (double)(GridWorldDev::kActions - 1);
         std::vector<GridWorldDev::Thresholds> thr(16 * 4);
         gw_thresholds(p.tprob, p_other, thr.data());
+        // per-(cell, action) fused entries for uct_fast.cuh
+        std::vector<GridWorldDev::FastEntry> fast(((size_t)cells + 1) * 4);
+        {
+            const int dlt[5] = {0, p.nx, -p.nx, -1, 1};
+            for (int c = 0; c <= cells; ++c)
+                for (int a = 0; a < 4; ++a) {
+                    GridWorldDev::FastEntry& e = fast[(size_t)c * 4 + a];
+                    for (int i = 0; i < 4; ++i) e.t[i] = 0xffffffffu;
+                    for (int i = 0; i < 5; ++i) e.next[i] = (uint32_t)cells;
+                    e.pad[0] = e.pad[1] = e.pad[2] = 0;
+                    if (info[(size_t)c].term_from) continue;  // Deterministic(terminal state)
+                    const GridWorldDev::Thresholds& T = thr[info[(size_t)c].row + a];
+                    for (int i = 0; i < 4; ++i) e.t[i] = T.t[i];
+                    for (int i = 0; i < 5; ++i) e.next[i] = (uint32_t)(c + dlt[(T.codes >> (4 * i)) & 15u]);
+                }
+        }
+        CUDA_TRY(ctx->gw_fast.ensure(fast.size() * sizeof(GridWorldDev::FastEntry)));
+        CUDA_TRY(cudaMemcpy(ctx->gw_fast.p, fast.data(), fast.size() * sizeof(GridWorldDev::FastEntry), cudaMemcpyHostToDevice));
+        ctx->gw_dev.fast_tt = (const GridWorldDev::FastEntry*)ctx->gw_fast.p;
         CUDA_TRY(ctx->gw_reward.ensure(info.size() * sizeof(GridWorldDev::CellInfo)));
         CUDA_TRY(ctx->gw_term.ensure(thr.size() * sizeof(GridWorldDev::Thresholds)));
         CUDA_TRY(cudaMemcpy(ctx->gw_reward.p, info.data(), info.size() * sizeof(GridWorldDev::CellInfo), cudaMemcpyHostToDevice));
@@ -985,7 +1145,7 @@ int32_t mctsb200_device_log(mctsb200_ctx* ctx, const double* x, int64_t n, doubl
     CUDA_TRY(in.ensure(sizeof(double) * (size_t)n));
     CUDA_TRY(o.ensure(sizeof(double) * (size_t)n));
     CUDA_TRY(cudaMemcpyAsync(in.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    MCTSB200_LAUNCH(probe_log_kernel, (unsigned)((n + 255) / 256), 256, ctx->stream, (const double*)in.p, (long long)n, (double*)o.p);
+    MCTSB200_LAUNCH(probe_log_kernel, (unsigned)((n + 255) / 256), 256, 0, ctx->stream, (const double*)in.p, (long long)n, (double*)o.p);
     CUDA_TRY(cudaMemcpyAsync(out, o.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     in.release();
@@ -1001,7 +1161,7 @@ int32_t mctsb200_device_cos(mctsb200_ctx* ctx, const double* x, int64_t n, doubl
     CUDA_TRY(in.ensure(sizeof(double) * (size_t)n));
     CUDA_TRY(o.ensure(sizeof(double) * (size_t)n));
     CUDA_TRY(cudaMemcpyAsync(in.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    MCTSB200_LAUNCH(probe_cos_kernel, (unsigned)((n + 255) / 256), 256, ctx->stream, (const double*)in.p, (long long)n, (double*)o.p);
+    MCTSB200_LAUNCH(probe_cos_kernel, (unsigned)((n + 255) / 256), 256, 0, ctx->stream, (const double*)in.p, (long long)n, (double*)o.p);
     CUDA_TRY(cudaMemcpyAsync(out, o.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     in.release();
@@ -1014,7 +1174,7 @@ int32_t mctsb200_device_philox(mctsb200_ctx* ctx, uint64_t seed, uint64_t tree, 
     CUDA_TRY(cudaSetDevice(ctx->device));
     DevBuf o;
     CUDA_TRY(o.ensure(sizeof(uint32_t) * 4 * (size_t)n_blocks));
-    MCTSB200_LAUNCH(probe_philox_kernel, 1, 32, ctx->stream, seed, tree, iteration, stream_id, 4 * n_blocks, (uint32_t*)o.p);
+    MCTSB200_LAUNCH(probe_philox_kernel, 1, 32, 0, ctx->stream, seed, tree, iteration, stream_id, 4 * n_blocks, (uint32_t*)o.p);
     CUDA_TRY(cudaMemcpyAsync(out, o.p, sizeof(uint32_t) * 4 * (size_t)n_blocks, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     o.release();

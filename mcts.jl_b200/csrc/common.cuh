@@ -11,7 +11,8 @@
 //                                                  count and insertion sequence number per child
 //     trans [n_trees][NT]             TransRec     DPW only: distinct (spnode, r) records with counts
 //     map   [n_trees][MAP]            u16 / HashSlot   state -> node id (dense index or open addressing)
-//     path  [n_trees][depth]          PathEntry    the explicit recursion stack of one simulation
+//     path  [n_trees][depth]          PathEntry    the explicit recursion stack of one simulation (only used when
+//                                                  the stacks of a block do not fit in shared memory)
 // Node ids on the device are 0-based; the ABI export converts to the reference's 1-based ids.
 #pragma once
 #include <stdint.h>
@@ -22,9 +23,9 @@
 // Kernel launch. MCTSB200_HOST_EMU is defined only by tests/emu (a single-threaded host build of this
 // library used to exercise the host logic without a GPU); the shipped library never defines it.
 #ifdef MCTSB200_HOST_EMU
-#define MCTSB200_LAUNCH(kernel, grid, block, stream, ...) mctsb200_emu::run((grid), (block), [&] { kernel(__VA_ARGS__); })
+#define MCTSB200_LAUNCH(kernel, grid, block, smem, stream, ...) mctsb200_emu::run((grid), (block), [&] { kernel(__VA_ARGS__); })
 #else
-#define MCTSB200_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define MCTSB200_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
 #define MCTSB200_MAX_ACTIONS_PER_ROW 7
@@ -176,6 +177,7 @@ struct DevCfg {
     const double* sqrtlog_tab;   // device: sqrt(det_log(N)) for N < log_tab_n (fast-path score)
     const double* rsqrt_tab;     // device: 1/sqrt(n) for n < rsqrt_tab_n     (fast-path score)
     const int* nmin_state;       // device: min n[sanode] for which n_a_children == len may widen
+    const unsigned char* policy_table;  // device, may be null: tabulated state-only rollout policy [dense index] (uct_fast.cuh)
     int log_tab_n;
     int rsqrt_tab_n;
     int nmin_state_n;
@@ -206,6 +208,9 @@ struct KernelArgs {
     long long n_trees;
     long long tree_index_base;
     long long root_stride;              // 1 = one root per tree, 0 = every tree plans roots[0]
+    const int* order;                   // device, may be null: tile slot -> tree or -1 (see order_*_kernel in search.cuh)
+    long long n_slots;                  // tile slots of the launch (= n_trees without an order)
+    int path_smem;                      // 1: the path stacks of a block live in dynamic shared memory, [level][tile]
     int iter_begin, iter_end;
 };
 

@@ -6,16 +6,17 @@ namespace mctsb200 {
 
 template <class M, int KIND, int G>
 static void launch_one(const KernelArgs<M>& args, cudaStream_t stream) {
-    const long long threads = args.n_trees * G;
+    const long long threads = args.n_slots * G;
     const unsigned grid = (unsigned)((threads + kBlockThreads - 1) / kBlockThreads);
     auto kernel = search_kernel<M, KIND, G>;
-    MCTSB200_LAUNCH(kernel, grid, kBlockThreads, stream, args);
+    const size_t smem = args.path_smem ? path_smem_bytes(args.geo.depth, G) : 0;
+    MCTSB200_LAUNCH(kernel, grid, kBlockThreads, smem, stream, args);
 }
 
 template <class M, int KIND, int G>
-static int occupancy_one() {
+static int occupancy_one(size_t smem) {
     int blocks = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, search_kernel<M, KIND, G>, kBlockThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, search_kernel<M, KIND, G>, kBlockThreads, smem);
     return blocks;
 }
 
@@ -32,14 +33,14 @@ static int occupancy_one() {
         }                                                                                           \
     }                                                                                               \
     template <>                                                                                     \
-    int search_occupancy<M, KIND>(int G) {                                                          \
+    int search_occupancy<M, KIND>(int G, size_t smem) {                                                          \
         switch (G) {                                                                                \
-            case 1: return occupancy_one<M, KIND, 1>();                                             \
-            case 2: return occupancy_one<M, KIND, 2>();                                             \
-            case 4: return occupancy_one<M, KIND, 4>();                                             \
-            case 8: return occupancy_one<M, KIND, 8>();                                             \
-            case 16: return occupancy_one<M, KIND, 16>();                                           \
-            default: return occupancy_one<M, KIND, 32>();                                           \
+            case 1: return occupancy_one<M, KIND, 1>(smem);                                             \
+            case 2: return occupancy_one<M, KIND, 2>(smem);                                             \
+            case 4: return occupancy_one<M, KIND, 4>(smem);                                             \
+            case 8: return occupancy_one<M, KIND, 8>(smem);                                             \
+            case 16: return occupancy_one<M, KIND, 16>(smem);                                           \
+            default: return occupancy_one<M, KIND, 32>(smem);                                           \
         }                                                                                           \
     }
 

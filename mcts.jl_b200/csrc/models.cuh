@@ -52,6 +52,20 @@ struct GridWorldDev {
         uint32_t pad[3];
     };
 
+    // The same sampling table fused per (cell, action) for the shared-memory kernel (uct_fast.cuh): thresholds
+    // ascending (unused = 0xffffffff) and the successor CELL on each plateau, so one entry answers gen(s, a, w):
+    //   sp = next[#{i : w > t[i]}].  terminate_from cells and the terminal state have no step and next[0] = terminal.
+    struct __align__(16) FastEntry {
+        uint32_t t[4];
+        uint32_t next[5];
+        uint32_t pad[3];
+    };
+    struct FastTables {
+        const FastEntry* tt;   // shared memory, [ncells + 1][4]
+        const double* reward;  // shared memory, [ncells + 1]
+        int term;              // dense index of the terminal state
+    };
+
     struct Params {
         int nx, ny, ncells;
         int delta[8];    // cell-index step of destination code [stay, up, down, left, right]
@@ -60,7 +74,47 @@ struct GridWorldDev {
         double discount;
         const CellInfo* cells;      // [nx*ny + 1]
         const Thresholds* thr;      // [16 boundary classes][4 actions]
+        const FastEntry* fast_tt;   // [nx*ny + 1][4]
     };
+
+    static constexpr bool kFast = true;
+    __host__ __device__ __forceinline__ static int fast_states(const Params& p) { return p.ncells + 1; }
+    __host__ __device__ __forceinline__ static size_t fast_table_bytes(const Params& p) {
+        return (sizeof(FastEntry) * 4 + sizeof(double)) * (size_t)(p.ncells + 1) + 8;
+    }
+    // copies the tables into shared memory (all threads of the block; the caller synchronises); returns the
+    // first free 16-byte aligned address
+    __device__ __forceinline__ static unsigned char* fast_stage(const Params& p, unsigned char* smem, FastTables& ft) {
+        const int n = p.ncells + 1;
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        const uint4* src = reinterpret_cast<const uint4*>(p.fast_tt);
+        const int n16 = n * 4 * (int)(sizeof(FastEntry) / 16);
+        double* rew = reinterpret_cast<double*>(smem + sizeof(FastEntry) * 4 * (size_t)n);
+#ifdef MCTSB200_HOST_EMU
+        const int i0 = 0, di = 1;
+#else
+        const int i0 = (int)threadIdx.x, di = (int)blockDim.x;
+#endif
+        for (int i = i0; i < n16; i += di) dst[i] = src[i];
+        for (int i = i0; i < n; i += di) rew[i] = p.cells[i].reward;
+        ft.tt = reinterpret_cast<const FastEntry*>(smem);
+        ft.reward = rew;
+        ft.term = p.ncells;
+        return smem + (fast_table_bytes(p) + 15) / 16 * 16;
+    }
+    __device__ __forceinline__ static double fast_reward(const FastTables& ft, int cell) { return ft.reward[cell]; }
+    __device__ __forceinline__ static int fast_gen(const FastTables& ft, int cell, int a, uint32_t w) {
+        const FastEntry* e = ft.tt + (cell * 4 + a);
+        const uint4 t = *reinterpret_cast<const uint4*>(e->t);
+        const uint4 nx = *reinterpret_cast<const uint4*>(e->next);
+        const uint32_t n4 = e->next[4];
+        uint32_t sp = nx.x;
+        sp = w > t.x ? nx.y : sp;
+        sp = w > t.y ? nx.z : sp;
+        sp = w > t.z ? nx.w : sp;
+        sp = w > t.w ? n4 : sp;
+        return (int)sp;
+    }
 
     __device__ __forceinline__ static State load(const Params& p, const AbiState& a) {
         return State{(a.x < 0 || a.y < 0) ? p.ncells : (int)(a.x - 1) + (int)(a.y - 1) * p.nx};
@@ -138,6 +192,7 @@ struct MountainCarDev {
     static constexpr bool kDense = false;
     static constexpr int kMaxBranch = 1;
     static constexpr int kMdpId = MCTSB200_MDP_MOUNTAINCAR;
+    static constexpr bool kFast = false;
 
     struct AbiState { double x, v; };
     typedef AbiState State;

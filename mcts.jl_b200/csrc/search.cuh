@@ -126,6 +126,7 @@ struct Search {
     // rollout steps can exceed that and are kept in 64 bits)
     unsigned cnt[CNT_COUNT];
     unsigned long long rollout_steps;
+    int path_stride;  // entries between consecutive levels of this tile's path
 #ifdef MCTSB200_PHASE_TIMING
     long long cyc[4] = {0, 0, 0, 0};  // descent, leaf evaluation, backup, trips
 #define PT_CLOCK(var) const long long var = clock64()
@@ -140,6 +141,7 @@ struct Search {
         aux = args.aux ? args.aux + tree * args.geo.NS : nullptr;
         trans = args.trans ? args.trans + tree * args.geo.NT : nullptr;
         path = args.path + tree * args.geo.depth;
+        path_stride = 1;
         dmap = M::kDense ? (uint16_t*)args.map + tree * args.geo.MAP : nullptr;
         hmap = M::kDense ? nullptr : (HashSlot*)args.map + tree * args.geo.MAP;
         tree_index = (uint64_t)(args.tree_index_base + tree);
@@ -263,7 +265,7 @@ struct Search {
         tile.sync();
         const double gamma = M::discount(a.mdp);
         for (int lvl = top - 1; lvl >= 0; --lvl) {
-            const PathEntry e = path[lvl];
+            const PathEntry e = path[lvl * path_stride];
             const double qv = DM_ADD(e.r, DM_MUL(gamma, v));
             if (lead()) {
                 Row<M>* rw = rows + e.node;
@@ -514,7 +516,7 @@ struct Search {
             State sp;
             double r;
             M::gen(a.mdp, s, slot, rng, sp, r);
-            if (lead()) path[top] = PathEntry{node, slot, r};
+            if (lead()) path[top * path_stride] = PathEntry{node, slot, r};
             ++top;
             --d;
             s = sp;
@@ -689,7 +691,7 @@ struct Search {
                 sp = M::state_of(a.mdp, rows[spnode].key);
                 if (lead()) cnt[CNT_TRANS_SAMPLES] += 1;
             }
-            if (lead()) path[top] = PathEntry{node, slot, r};
+            if (lead()) path[top * path_stride] = PathEntry{node, slot, r};
             ++top;
             tile.sync();
             node = spnode;
@@ -718,9 +720,17 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
     __syncthreads();
 #endif
 
-    const long long tree = ((long long)blockIdx.x * kBlockThreads + threadIdx.x) / G;
-    if (tree < args.n_trees) {
+    const long long slot = ((long long)blockIdx.x * kBlockThreads + threadIdx.x) / G;
+    const long long tree = slot >= args.n_slots ? -1 : args.order ? (long long)args.order[slot] : slot;
+    if (tree >= 0) {
         Search<M, G> S(args, tree);
+#ifndef MCTSB200_HOST_EMU
+        if (args.path_smem) {  // [level][tile]: tiles at the same level touch consecutive 16 B entries
+            extern __shared__ __align__(16) unsigned char dyn_smem[];
+            S.path = reinterpret_cast<PathEntry*>(dyn_smem) + threadIdx.x / G;
+            S.path_stride = kBlockThreads / G;
+        }
+#endif
         TreeHeader* hd = args.hdr + tree;
         TreeHeader h = *hd;
         S.n_state = h.n_state;
@@ -836,9 +846,71 @@ __global__ void root_sums_kernel(const TreeHeader* hdr, const Row<M>* rows, int 
     out[M::kActions + act] = snq;
 }
 
+// Lane ordering for dense-state MDPs: a counting sort of the trees by root state, so that trees planning from
+// equal roots (statistically alike, and for deterministic models identical, amounts of work per iteration) run
+// in the same warps and a warp's lanes stay converged. Every group of equal roots is padded to whole warps
+// (idle slots hold -1), and the warps are then spread over the grid by a multiplicative permutation so that no
+// SM ends up with all the long-running groups. The order only decides which lane works on which tree; results do
+// not depend on it.
+template <class M>
+__global__ void order_hist_kernel(const typename M::Params mdp, const typename M::AbiState* roots, long long n_trees, int* bins) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_trees) atomicAdd(bins + M::dense_index(mdp, M::load(mdp, roots[t])), 1);
+}
+// bins[0..n): group sizes -> first slot of each group, every group rounded up to a multiple of `tpw` slots (one block)
+static __global__ void order_scan_kernel(int* bins, int n, int tpw) {
+#ifdef MCTSB200_HOST_EMU
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < n; ++i) {
+            const int c = (bins[i] + tpw - 1) / tpw * tpw;
+            bins[i] = run;
+            run += c;
+        }
+    }
+#else
+    __shared__ int part[1024];
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int lo = min(n, (int)threadIdx.x * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += (bins[i] + tpw - 1) / tpw * tpw;
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) {
+            const int c = part[i];
+            part[i] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    int run = part[threadIdx.x];
+    for (int i = lo; i < hi; ++i) {
+        const int c = (bins[i] + tpw - 1) / tpw * tpw;
+        bins[i] = run;
+        run += c;
+    }
+#endif
+}
+// slot = group start + arrival rank; its warp w moves to (w * warp_mul) mod n_warps
+template <class M>
+__global__ void order_scatter_kernel(const typename M::Params mdp, const typename M::AbiState* roots, long long n_trees, int* bins, int* order,
+                                     int tpw, long long n_warps, long long warp_mul) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    const int slot = atomicAdd(bins + M::dense_index(mdp, M::load(mdp, roots[t])), 1);
+    const long long w = slot / tpw;
+    order[((w * warp_mul) % n_warps) * tpw + slot % tpw] = (int)t;
+}
+
+// dynamic shared memory of one block of the G variant: the path stacks, if they fit
+static inline size_t path_smem_bytes(int depth, int G) { return sizeof(PathEntry) * (size_t)depth * (size_t)(kBlockThreads / G); }
+constexpr size_t kPathSmemLimit = 48 * 1024;
+
 template <class M, int KIND>
 void launch_search(const KernelArgs<M>& args, int G, cudaStream_t stream);
 template <class M, int KIND>
-int search_occupancy(int G);  // resident blocks per SM of the G variant
+int search_occupancy(int G, size_t smem_bytes);  // resident blocks per SM of the G variant
 
 }  // namespace mctsb200

@@ -1,5 +1,5 @@
 import json, sys
-for l in open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/bench_all.log"):
+for l in (open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin):
     if not l.startswith("{"):
         print(l.strip()[:200]); continue
     d = json.loads(l)

@@ -43,6 +43,8 @@ static inline double __hiloint2double(int hi, int lo) {
     const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
     double d; std::memcpy(&d, &u, 8); return d;
 }
+static inline int __double2loint(double x) { uint64_t u; std::memcpy(&u, &x, 8); return (int)(uint32_t)u; }
+static inline int __double2hiint(double x) { uint64_t u; std::memcpy(&u, &x, 8); return (int)(uint32_t)(u >> 32); }
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline long long __double_as_longlong(double x) { long long u; std::memcpy(&u, &x, 8); return u; }
 static inline double __longlong_as_double(long long u) { double x; std::memcpy(&x, &u, 8); return x; }

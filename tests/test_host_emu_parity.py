@@ -1,0 +1,124 @@
+"""CPU-only checks of the shipped library's sources:
+
+* the host-emulation build of mcts.jl_b200/csrc (tests/emu: the same .cu files compiled by g++ as a
+  single-threaded program, one lane per tree) against the CPU oracle, bit-for-bit -- this exercises the host logic
+  (validation, table sizing, widening thresholds, lane ordering, export) and the kernel's control flow without
+  a GPU;
+* the real libmctsb200.so loads and exports every symbol include/mctsb200.h declares (no compute call).
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mcts_jl_b200 as m
+from helpers import gridworld_roots, mountaincar_roots, run_both
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GW = m.SimpleGridWorld()
+GW_DET = m.SimpleGridWorld(tprob=1.0)
+MC = m.MountainCar()
+
+
+def test_shipped_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mctsb200.h")).read()
+    declared = set(re.findall(r"^(?:int32_t|const char\*)\s+(mctsb200_[a-z_]+)\s*\(", hdr, flags=re.M))
+    assert declared >= set(m.abi.EXPORTED_SYMBOLS) and len(declared) >= 15
+    m.build_library()
+    lib = C.CDLL(m._lib.DEFAULT_LIB)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"libmctsb200.so does not export {sym}"
+    assert lib.mctsb200_abi_version() == m.abi.ABI_VERSION
+
+
+def test_no_device_means_error_not_fallback():
+    """Without a CUDA device ctx_create fails loudly (there is no CPU path in the shipped library)."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(m.MCTSB200Error) as ei:
+        m.Context(0)
+    assert ei.value.status == m.abi.ERR_CUDA
+
+
+def test_emu_uct_deterministic(emu_ctx, oracle):
+    roots = gridworld_roots(100)
+    for est in (m.RolloutEstimator(m.ConstantPolicy("up")), m.RolloutEstimator(m.SeekTarget((9, 3)))):
+        s = m.MCTSSolver(n_iterations=200, depth=20, exploration_constant=5.0, estimate_value=est)
+        run_both(emu_ctx, oracle, s, GW_DET, roots, compare_trees=range(0, 100, 3))
+
+
+def test_emu_uct_stochastic(emu_ctx, oracle):
+    s = m.MCTSSolver(n_iterations=250, depth=20, exploration_constant=5.0, rng=7)
+    _, _, _, st = run_both(emu_ctx, oracle, s, GW, gridworld_roots(64), base=1000, compare_trees=range(0, 64, 5))
+    assert st.kernel_variant == 1  # the shared-memory lane-per-tree kernel
+
+
+def test_emu_generic_uct_kernel_still_matches(emu_ctx, oracle, monkeypatch):
+    """MCTSB200_FAST=0 forces the tile kernel on the configurations the lean kernel normally takes."""
+    monkeypatch.setenv("MCTSB200_FAST", "0")
+    s = m.MCTSSolver(n_iterations=200, depth=20, exploration_constant=5.0, rng=7)
+    _, _, _, st = run_both(emu_ctx, oracle, s, GW, gridworld_roots(40), compare_trees=range(0, 40, 5))
+    assert st.kernel_variant == 0
+    s = m.MCTSSolver(n_iterations=150, depth=20, exploration_constant=5.0, estimate_value=m.RolloutEstimator(m.SeekTarget((9, 3))))
+    run_both(emu_ctx, oracle, s, GW_DET, gridworld_roots(40), compare_trees=range(0, 40, 5))
+
+
+@pytest.mark.parametrize("opts", [
+    dict(exploration_constant=0.0),
+    dict(init_N=3, init_Q=11.73, estimate_value=0.0),
+    dict(estimate_value=m.RolloutEstimator(m.RandomSolver(), max_depth=-1)),
+    dict(estimate_value=m.RolloutEstimator(m.ConstantPolicy("up"), max_depth=-1)),
+    dict(estimate_value=m.RolloutEstimator(m.RandomSolver(), eps=0.2)),
+    dict(rollouts_per_leaf=5),
+    dict(depth=0),
+    dict(n_iterations=1),
+])
+def test_emu_uct_options(emu_ctx, oracle, opts):
+    kw = dict(n_iterations=150, depth=8, exploration_constant=3.0, rng=5)
+    kw.update(opts)
+    run_both(emu_ctx, oracle, m.MCTSSolver(**kw), GW, gridworld_roots(30) + [(-1, -1)])
+
+
+def test_emu_dpw_gridworld(emu_ctx, oracle):
+    s = m.DPWSolver(n_iterations=300, depth=20, exploration_constant=10.0, k_state=4.0, alpha_state=1 / 8, k_action=4.0, alpha_action=1 / 8, rng=3)
+    run_both(emu_ctx, oracle, s, GW, gridworld_roots(50), compare_trees=range(0, 50, 4))
+
+
+@pytest.mark.parametrize("opts", [
+    dict(),
+    dict(enable_action_pw=False),
+    dict(k_state=1.0, alpha_state=0.1),
+    dict(check_repeat_state=False, k_state=2.0, alpha_state=0.3),
+    dict(enable_state_pw=False),
+    dict(init_N=2, init_Q=-1.0, estimate_value=4.0),
+    dict(exploration_constant=0.0),
+    dict(rollouts_per_leaf=3),
+])
+def test_emu_dpw_options(emu_ctx, oracle, opts):
+    kw = dict(n_iterations=200, depth=10, rng=11)
+    kw.update(opts)
+    run_both(emu_ctx, oracle, m.DPWSolver(**kw), GW, gridworld_roots(24))
+
+
+def test_emu_mountaincar(emu_ctx, oracle):
+    roots = mountaincar_roots(8)
+    run_both(emu_ctx, oracle, m.DPWSolver(n_iterations=300, depth=50, rng=8), MC, roots)
+    run_both(emu_ctx, oracle, m.MCTSSolver(n_iterations=200, depth=30, exploration_constant=10.0, rng=9), MC, roots)
+
+
+def test_emu_large_grid_uses_map_layout(emu_ctx, oracle):
+    """A grid with far more cells than iterations (node table sized by n_iterations, not by the grid)."""
+    big = m.SimpleGridWorld(size=(60, 50), rewards={(30, 20): 5.0, (7, 9): -3.0})
+    roots = [(1 + (7 * i) % 60, 1 + (11 * i) % 50) for i in range(20)]
+    run_both(emu_ctx, oracle, m.MCTSSolver(n_iterations=80, depth=12, exploration_constant=2.0, rng=4), big, roots)
+    run_both(emu_ctx, oracle, m.DPWSolver(n_iterations=80, depth=12, rng=4), big, roots)
+
+
+def test_emu_terminal_dpw_root_reports_status(emu_ctx, oracle):
+    roots = gridworld_roots(10) + [(-1, -1)]
+    a, q, st, stats = run_both(emu_ctx, oracle, m.DPWSolver(n_iterations=50, depth=10, rng=2), GW, roots)
+    assert st[-1] == m.abi.ERR_TERMINAL_ROOT and (st[:-1] == 0).all()
