@@ -1,0 +1,138 @@
+"""The host-side mirror of the reference's public API for this path (mcts.jl_b200/solvers.py), exercised the way
+the reference's own tests exercise MCTS.jl -- test/runtests.jl, test/options.jl, test/dpw_test.jl, test/other.jl --
+on the host-emulation build (CPU suite) and, marked gpu, on the shipped CUDA library."""
+import warnings
+
+import numpy as np
+import pytest
+
+import mcts_jl_b200 as m
+
+GW = m.SimpleGridWorld()
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def ctx(request):
+    if request.param == "emu":
+        return request.getfixturevalue("emu_ctx")
+    return request.getfixturevalue("gpu_ctx")
+
+
+def test_vanilla_smoke_like_runtests(ctx):
+    """test/runtests.jl:17-49: action(policy, GWPos(1,1)), root has id 1, info[:tree], clear_tree!."""
+    solver = m.MCTSSolver(n_iterations=100, depth=20, exploration_constant=5.0, rng=1)
+    policy = m.solve(solver, GW, ctx=ctx)
+    state = (1, 1)
+    a = policy.action(state)
+    assert a in GW.actions
+    a2, info = policy.action_info(state)
+    assert a2 in GW.actions and "tree" in info and "best_Q" in info
+    tree = info["tree"]
+    assert tree.state_map[state] == 1  # test/runtests.jl:44-45
+    assert len(tree.total_n) <= 101 and len(tree.n) == 4 * len(tree.total_n)
+    assert int(tree.total_n[0]) == int(tree.n[:4].sum()) >= 100
+    m.clear_tree(policy)
+    assert policy.tree is None
+
+
+def test_readme_usage(ctx):
+    """README.md:37-40: MCTSSolver(n_iterations=50, depth=20, exploration_constant=5.0), root SA[1,2]."""
+    planner = m.solve(m.MCTSSolver(n_iterations=50, depth=20, exploration_constant=5.0), GW, ctx=ctx)
+    assert planner.action((1, 2)) in ("up", "down", "left", "right")
+
+
+def test_option_matrix_like_options_jl(ctx):
+    """test/options.jl: every device-expressible form of init_Q / init_N / estimate_value runs for both solvers;
+    a String is a MethodError (TypeError here); host closures without a device form are refused."""
+    for S in (m.MCTSSolver, m.DPWSolver):
+        base = dict(n_iterations=20, depth=5)
+        for kw in (dict(init_Q=1.0), dict(init_N=3), dict(estimate_value=2.5),
+                   dict(init_Q=lambda mdp, s, a: 1.5), dict(init_N=lambda mdp, s, a: 2),
+                   dict(estimate_value=lambda mdp, s, d: 0.25),
+                   dict(estimate_value=m.RolloutEstimator(m.RandomPolicy())),
+                   dict(estimate_value=m.RolloutEstimator(m.ConstantPolicy("up"))),
+                   dict(estimate_value=m.RolloutEstimator(m.RandomSolver(), max_depth=-1))):
+            assert m.solve(S(**base, **kw), GW, ctx=ctx).action((1, 1)) in GW.actions
+        for bad in (dict(init_Q="bad"), dict(init_N="bad"), dict(estimate_value="bad")):
+            with pytest.raises(TypeError):
+                m.solve(S(**base, **bad), GW, ctx=ctx)
+    for kw in (dict(callback=lambda p, n: None), dict(timer=lambda: 0.0), dict(enable_tree_vis=True)):
+        with pytest.raises(m.MCTSB200Error) as ei:
+            m.solve(m.MCTSSolver(**kw), GW, ctx=ctx)
+        assert ei.value.status == m.abi.ERR_UNSUPPORTED
+    for kw in (dict(reset_callback=lambda mdp, s: None), dict(show_progress=True), dict(next_action=lambda *a: "up")):
+        with pytest.raises(m.MCTSB200Error):
+            m.solve(m.DPWSolver(**kw), GW, ctx=ctx)
+    with pytest.raises(m.MCTSB200Error):
+        m.solve(m.MCTSSolver(estimate_value=m.RolloutEstimator(lambda s: "up")), GW, ctx=ctx)
+
+
+def test_dpw_smoke_like_dpw_test(ctx):
+    """test/dpw_test.jl: default, keep_tree + enable_action_pw=false; info keys of src/dpw.jl:58-67."""
+    for kw in (dict(), dict(keep_tree=True, enable_action_pw=False), dict(tree_in_info=True)):
+        p = m.solve(m.DPWSolver(n_iterations=50, depth=20, exploration_constant=5.0, **kw), GW, ctx=ctx)
+        a, info = p.action_info((1, 1), tree_in_info=True)
+        assert a in GW.actions
+        assert {"search_time", "search_time_us", "tree_queries", "best_Q", "tree"} <= set(info)
+        assert info["tree_queries"] == 50
+
+
+def test_ranked_actions_like_other_jl(ctx):
+    """test/other.jl:15,29: the top-ranked action is the chosen action, for both solvers."""
+    for S in (m.MCTSSolver, m.DPWSolver):
+        p = m.solve(S(n_iterations=200, depth=10, exploration_constant=5.0, rng=3), GW, ctx=ctx)
+        a = p.action((3, 3))
+        ranked = m.ranked_actions(p, (3, 3))
+        assert ranked[0][0] == a
+        assert [q for _, q in ranked] == sorted((q for _, q in ranked), reverse=True)
+
+
+def test_zero_exploration_like_runtests(ctx):
+    """test/runtests.jl:136-153: c = 0 runs without NaN for both solvers."""
+    for S in (m.MCTSSolver, m.DPWSolver):
+        p = m.solve(S(n_iterations=100, depth=10, exploration_constant=0.0), GW, ctx=ctx)
+        a, info = p.action_info((2, 2))
+        assert a in GW.actions and np.isfinite(info["best_Q"])
+
+
+def test_dpw_terminal_root_and_default_action(ctx):
+    """src/dpw.jl:22-27 raises on a terminal root; with a default_action the exception is captured (src/dpw.jl:68-71,
+    test/runtests.jl:155-163)."""
+    p = m.solve(m.DPWSolver(n_iterations=10, depth=5), GW, ctx=ctx)
+    with pytest.raises(m.MCTSB200Error) as ei:
+        p.action((-1, -1))
+    assert ei.value.status == m.abi.ERR_TERMINAL_ROOT
+    p = m.solve(m.DPWSolver(n_iterations=10, depth=5, default_action="up"), GW, ctx=ctx)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        a, info = p.action_info((-1, -1))
+    assert a == "up" and "exception" in info and len(w) == 1
+
+
+def test_value_like_vanilla_jl(ctx):
+    """value(planner, s) = max_a Q(s,a), value(planner, s, a) = Q(s,a) (src/vanilla.jl:169-197)."""
+    p = m.solve(m.MCTSSolver(n_iterations=300, depth=10, exploration_constant=5.0, rng=2), GW, ctx=ctx)
+    a, info = p.action_info((8, 3))
+    v = p.value((8, 3))
+    assert v == pytest.approx(info["best_Q"])
+    assert p.value((8, 3), a) == pytest.approx(v)
+    with pytest.raises(KeyError):
+        p.value((1, 10) if (1, 10) not in p.tree.state_map else (-5, -5))
+
+
+def test_batch_extension_equals_single_calls(ctx):
+    """action_batch plans every state in one call; with the same global root indices the trees are the same."""
+    solver = m.MCTSSolver(n_iterations=80, depth=10, exploration_constant=5.0, rng=9)
+    states = [(1, 1), (5, 5), (9, 2), (4, 6)]
+    acts, infos = m.solve(solver, GW, ctx=ctx).action_info_batch(states)
+    for i, s in enumerate(states):
+        a1, info1 = m.solve(solver, GW, ctx=ctx).action_info_batch([s], root_index_base=i)
+        assert a1[0] == acts[i] and info1[0]["best_Q"] == infos[i]["best_Q"]
+
+
+def test_max_time_runs_at_least_one_iteration(ctx):
+    """src/vanilla.jl:229-235: the timer is read after an iteration, so max_time = 0 still runs one."""
+    p = m.solve(m.MCTSSolver(n_iterations=10**6, depth=5, max_time=0.0), GW, ctx=ctx)
+    p.action((1, 1))
+    assert 1 <= p.last_stats.iterations_done < 10**6
+    assert int(p.last_stats.n_simulations) == p.last_stats.iterations_done
