@@ -109,6 +109,7 @@ struct MdpAccess<GridWorldDev> {
         return (inb || term) ? 0 : -1;
     }
     static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_GW_SEEK; }
+    static bool fast_ready(const mctsb200_ctx* c) { return c->gw_dev.fast_tt != nullptr; }
     // a state-only deterministic rollout policy as a table over dense state indices (GridWorldDev::policy_action restated on the host)
     static bool tabulate_policy(const mctsb200_ctx* c, const mctsb200_solver_cfg* cfg, std::vector<unsigned char>& out) {
         if (cfg->rollout_policy != MCTSB200_POLICY_GW_SEEK) return false;
@@ -246,7 +247,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     long long MAP = 0;
     size_t map_entry = 0;
     if (direct) {
-        MAP = 0;
+        MAP = NS;  // insertion sequence number per state (uct_fast.cuh)
         map_entry = sizeof(uint16_t);
     } else if (M::kDense) {
         MAP = (dense + 63) / 64 * 64;
@@ -462,13 +463,14 @@ int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg) {
     if constexpr (!M::kFast || KIND != MCTSB200_KIND_UCT) {
         return -1;
     } else {
-        if (!env_enabled("MCTSB200_FAST")) return -1;
+        if (!env_enabled("MCTSB200_FAST") || !MdpAccess<M>::fast_ready(ctx)) return -1;
         if (cfg->estimate_kind != MCTSB200_EST_ROLLOUT || cfg->rollouts_per_leaf != 1 || cfg->lanes_per_tree > 1) return -1;
         if (cfg->init_q_table || cfg->init_n_table) return -1;
-        const int dense = MdpAccess<M>::dense_count(ctx);
-        // direct-indexed rows cost dense*64 B per tree: only when the tree can actually grow to that order of size
-        if (dense > 256 && (long long)dense > 4 * (cfg->n_iterations + 1)) return -1;
-        if (cfg->depth > 254) return -1;  // level bytes in the row stamps
+        if (cfg->exploration_constant == 0.0) return -1;  // argmax-Q selection: the tile kernel has that path
+        if (cfg->depth > 254 || cfg->n_iterations >= (1LL << 24) - 1) return -1;  // (iteration, level) tags of the children
+        // the kernel indexes the UCB tables without a range check: every visit count must be inside them
+        const long long bound = 4LL * std::max<long long>(cfg->init_N, 0) + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1;
+        if (bound + 1 > (1LL << 20)) return -1;
         if (fast_smem_bytes<M>(MdpAccess<M>::params(ctx), std::max(cfg->depth, 1), 64) > kFastSmemLimit) return -1;
         switch (cfg->rollout_policy) {
             case MCTSB200_POLICY_RANDOM: return FAST_POLICY_RANDOM;
@@ -477,6 +479,16 @@ int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg) {
             default: return -1;
         }
     }
+}
+
+// threads per block of the fast kernel: one block per SM, as many lanes as the batch needs and the per-level records
+// in shared memory allow
+template <class M>
+int fast_block_threads(mctsb200_ctx* ctx, long long slots_per_sm, int depth) {
+    int block = (int)std::min<long long>(kFastMaxThreads, std::max<long long>(32, (slots_per_sm + 31) / 32 * 32));
+    if constexpr (M::kFast)
+        while (block > 32 && fast_smem_bytes<M>(MdpAccess<M>::params(ctx), depth, block) > kFastSmemLimit) block -= 32;
+    return block;
 }
 
 // Runs the search for trees whose roots are already on the device. d_* outputs may be null.
@@ -516,6 +528,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     int launches = 0, done = 0;
     args.path_smem = fast < 0 && use_path_smem(st.geo.depth, G) ? 1 : 0;
     args.n_slots = n_trees;
+    int fast_block = 0;  // block size the lane order was dealt for
     if constexpr (M::kDense) {
         if (root_stride == 1 && n_trees > 32 && n_trees < (1LL << 30) && env_enabled("MCTSB200_LANE_ORDER", false)) {
             const int n_bins = MdpAccess<M>::dense_count(ctx);
@@ -523,11 +536,16 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             // upper bound of the padded slot count (the exact one is only known on the device): every non-empty
             // group wastes at most tpw-1 slots
             const long long bound = n_trees + std::min<long long>(n_bins, n_trees) * (tpw - 1);
-            const long long n_warps = (bound + tpw - 1) / tpw;
-            long long mul = (long long)((double)n_warps * 0.6180339887498949) | 1;
-            auto gcd = [](long long x, long long y) { while (y) { const long long t = x % y; x = y; y = t; } return x; };
-            while (gcd(mul, n_warps) != 1) mul += 2;
-            if (n_warps < 8) mul = 1;
+            long long n_warps = (bound + tpw - 1) / tpw;
+            // thread-block shape of the launch that will consume the order
+            long long wpb = kBlockThreads / 32;
+            if (fast >= 0) {
+                const long long per_sm = (n_warps * tpw + ctx->sm_count - 1) / ctx->sm_count;
+                fast_block = fast_block_threads<M>(ctx, per_sm, st.geo.depth);
+                wpb = fast_block / 32;
+            }
+            const long long n_blocks = (n_warps + wpb - 1) / wpb;
+            n_warps = n_blocks * wpb;
             const unsigned grid = (unsigned)((n_trees + 255) / 256);
             CUDA_TRY(ctx->order.ensure(sizeof(int) * (size_t)(n_warps * tpw)));
             CUDA_TRY(ctx->order_bins.ensure(sizeof(int) * (size_t)n_bins));
@@ -537,7 +555,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             auto scatter = order_scatter_kernel<M>;
             MCTSB200_LAUNCH(hist, grid, 256, 0, ctx->stream, args.mdp, d_roots, n_trees, (int*)ctx->order_bins.p);
             MCTSB200_LAUNCH(order_scan_kernel, 1, 1024, 0, ctx->stream, (int*)ctx->order_bins.p, n_bins, tpw);
-            MCTSB200_LAUNCH(scatter, grid, 256, 0, ctx->stream, args.mdp, d_roots, n_trees, (int*)ctx->order_bins.p, (int*)ctx->order.p, tpw, n_warps, mul);
+            MCTSB200_LAUNCH(scatter, grid, 256, 0, ctx->stream, args.mdp, d_roots, n_trees, (int*)ctx->order_bins.p, (int*)ctx->order.p, tpw, n_blocks, wpb);
             CUDA_TRY(cudaGetLastError());
             args.order = (const int*)ctx->order.p;
             args.n_slots = n_warps * tpw;
@@ -548,10 +566,8 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     auto launch = [&]() -> int32_t {
         if constexpr (M::kFast && KIND == MCTSB200_KIND_UCT) {
             if (fast >= 0) {
-                // one block per SM, as many lanes as the batch needs and the per-level records in shared memory allow
                 const long long per_sm = (args.n_slots + ctx->sm_count - 1) / ctx->sm_count;
-                int block = (int)std::min<long long>(kFastMaxThreads, std::max<long long>(32, (per_sm + 31) / 32 * 32));
-                while (block > 32 && fast_smem_bytes<M>(args.mdp, args.geo.depth, block) > kFastSmemLimit) block -= 32;
+                const int block = fast_block ? fast_block : fast_block_threads<M>(ctx, per_sm, args.geo.depth);
                 const int grid = (int)((args.n_slots + block - 1) / block);
                 return launch_uct_fast<M>(args, fast, grid, block, fast_smem_bytes<M>(args.mdp, args.geo.depth, block), ctx->stream);
             }
@@ -595,10 +611,10 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         }
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     }
-    if (fast >= 0) {
+    if constexpr (M::kFast) if (fast >= 0) {
         const long long n_rows = n_trees * st.geo.NS;
-        auto kernel = total_n_kernel<M>;
-        MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (Row<M>*)st.rows.p, n_rows);
+        auto kernel = finalize_rows_kernel<M>;
+        MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (Row<M>*)st.rows.p, (const uint16_t*)st.map.p, n_rows);
         CUDA_TRY(cudaGetLastError());
         ++launches;
     }
@@ -1004,25 +1020,40 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
         const double p_other = (1.0 - p.tprob) / (double)(GridWorldDev::kActions - 1);
         std::vector<GridWorldDev::Thresholds> thr(16 * 4);
         gw_thresholds(p.tprob, p_other, thr.data());
-        // per-(cell, action) fused entries for uct_fast.cuh
-        std::vector<GridWorldDev::FastEntry> fast(((size_t)cells + 1) * 4);
-        {
+        // per-(cell, action) 16-byte entries for uct_fast.cuh; only for grids whose successor deltas fit in 8 bits
+        ctx->gw_dev.fast_tt = nullptr;
+        for (int i = 0; i < 4; ++i) ctx->gw_dev.fast_rbits[i] = 0;
+        if (cells <= 127) {
+            std::vector<GridWorldDev::FastEntry> fast(((size_t)cells + 1) * 4);
             const int dlt[5] = {0, p.nx, -p.nx, -1, 1};
-            for (int c = 0; c <= cells; ++c)
+            bool ok = true, neg_zero = false;
+            for (int c = 0; c <= cells; ++c) {
+                const double rw = info[(size_t)c].reward;
+                uint64_t bits;
+                std::memcpy(&bits, &rw, 8);
+                if (bits != 0) ctx->gw_dev.fast_rbits[c >> 5] |= 1u << (c & 31);
+                if (bits == 0x8000000000000000ull) neg_zero = true;
                 for (int a = 0; a < 4; ++a) {
                     GridWorldDev::FastEntry& e = fast[(size_t)c * 4 + a];
-                    for (int i = 0; i < 4; ++i) e.t[i] = 0xffffffffu;
-                    for (int i = 0; i < 5; ++i) e.next[i] = (uint32_t)cells;
-                    e.pad[0] = e.pad[1] = e.pad[2] = 0;
+                    e.t[0] = e.t[1] = e.t[2] = 0xffffffffu;
+                    e.d = (uint32_t)((cells - c) & 0xff);  // plateau 0 -> terminal state
                     if (info[(size_t)c].term_from) continue;  // Deterministic(terminal state)
                     const GridWorldDev::Thresholds& T = thr[info[(size_t)c].row + a];
-                    for (int i = 0; i < 4; ++i) e.t[i] = T.t[i];
-                    for (int i = 0; i < 5; ++i) e.next[i] = (uint32_t)(c + dlt[(T.codes >> (4 * i)) & 15u]);
+                    if (T.t[3] != 0xffffffffu) ok = false;
+                    e.d = 0;
+                    for (int i = 0; i < 3; ++i) e.t[i] = T.t[i];
+                    for (int i = 0; i < 4; ++i) e.d |= (uint32_t)(dlt[(T.codes >> (4 * i)) & 15u] & 0xff) << (8 * i);
                 }
+            }
+            // a reward of -0.0 could make a running sum -0.0, for which adding +0.0 is not the identity: always add then
+            if (neg_zero)
+                for (int i = 0; i < 4; ++i) ctx->gw_dev.fast_rbits[i] = 0xffffffffu;
+            if (ok) {
+                CUDA_TRY(ctx->gw_fast.ensure(fast.size() * sizeof(GridWorldDev::FastEntry)));
+                CUDA_TRY(cudaMemcpy(ctx->gw_fast.p, fast.data(), fast.size() * sizeof(GridWorldDev::FastEntry), cudaMemcpyHostToDevice));
+                ctx->gw_dev.fast_tt = (const GridWorldDev::FastEntry*)ctx->gw_fast.p;
+            }
         }
-        CUDA_TRY(ctx->gw_fast.ensure(fast.size() * sizeof(GridWorldDev::FastEntry)));
-        CUDA_TRY(cudaMemcpy(ctx->gw_fast.p, fast.data(), fast.size() * sizeof(GridWorldDev::FastEntry), cudaMemcpyHostToDevice));
-        ctx->gw_dev.fast_tt = (const GridWorldDev::FastEntry*)ctx->gw_fast.p;
         CUDA_TRY(ctx->gw_reward.ensure(info.size() * sizeof(GridWorldDev::CellInfo)));
         CUDA_TRY(ctx->gw_term.ensure(thr.size() * sizeof(GridWorldDev::Thresholds)));
         CUDA_TRY(cudaMemcpy(ctx->gw_reward.p, info.data(), info.size() * sizeof(GridWorldDev::CellInfo), cudaMemcpyHostToDevice));

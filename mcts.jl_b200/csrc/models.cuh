@@ -52,17 +52,19 @@ struct GridWorldDev {
         uint32_t pad[3];
     };
 
-    // The same sampling table fused per (cell, action) for the shared-memory kernel (uct_fast.cuh): thresholds
-    // ascending (unused = 0xffffffff) and the successor CELL on each plateau, so one entry answers gen(s, a, w):
-    //   sp = next[#{i : w > t[i]}].  terminate_from cells and the terminal state have no step and next[0] = terminal.
+    // The same sampling table fused per (cell, action) for the shared-memory kernel (uct_fast.cuh), 16 bytes per
+    // entry: a GridWorld move has at most 4 outcomes with non-zero probability (stay only at the border, where at
+    // least one direction is folded into it), i.e. at most 3 steps, and on grids of up to 127 cells every successor
+    // is within +-127 of the source index:  sp = cell + d[#{i : w > t[i]}].  terminate_from cells and the terminal
+    // state have no step and d[0] = terminal - cell.
     struct __align__(16) FastEntry {
-        uint32_t t[4];
-        uint32_t next[5];
-        uint32_t pad[3];
+        uint32_t t[3];  // ascending, unused = 0xffffffff
+        uint32_t d;     // four signed 8-bit successor deltas, plateau 0 in the low byte
     };
     struct FastTables {
         const FastEntry* tt;   // shared memory, [ncells + 1][4]
         const double* reward;  // shared memory, [ncells + 1]
+        uint32_t rbits[4];     // bit c: reward(c) is not +0.0 (adding +0.0 is exact identity, so those cells skip the arithmetic)
         int term;              // dense index of the terminal state
     };
 
@@ -74,13 +76,14 @@ struct GridWorldDev {
         double discount;
         const CellInfo* cells;      // [nx*ny + 1]
         const Thresholds* thr;      // [16 boundary classes][4 actions]
-        const FastEntry* fast_tt;   // [nx*ny + 1][4]
+        const FastEntry* fast_tt;   // [nx*ny + 1][4], null if the grid does not qualify for the 16-byte entries
+        uint32_t fast_rbits[4];
     };
 
     static constexpr bool kFast = true;
     __host__ __device__ __forceinline__ static int fast_states(const Params& p) { return p.ncells + 1; }
     __host__ __device__ __forceinline__ static size_t fast_table_bytes(const Params& p) {
-        return (sizeof(FastEntry) * 4 + sizeof(double)) * (size_t)(p.ncells + 1) + 8;
+        return ((sizeof(FastEntry) * 4 + sizeof(double)) * (size_t)(p.ncells + 1) + 15) / 16 * 16;
     }
     // copies the tables into shared memory (all threads of the block; the caller synchronises); returns the
     // first free 16-byte aligned address
@@ -88,32 +91,30 @@ struct GridWorldDev {
         const int n = p.ncells + 1;
         uint4* dst = reinterpret_cast<uint4*>(smem);
         const uint4* src = reinterpret_cast<const uint4*>(p.fast_tt);
-        const int n16 = n * 4 * (int)(sizeof(FastEntry) / 16);
         double* rew = reinterpret_cast<double*>(smem + sizeof(FastEntry) * 4 * (size_t)n);
 #ifdef MCTSB200_HOST_EMU
         const int i0 = 0, di = 1;
 #else
         const int i0 = (int)threadIdx.x, di = (int)blockDim.x;
 #endif
-        for (int i = i0; i < n16; i += di) dst[i] = src[i];
+        for (int i = i0; i < n * 4; i += di) dst[i] = src[i];
         for (int i = i0; i < n; i += di) rew[i] = p.cells[i].reward;
         ft.tt = reinterpret_cast<const FastEntry*>(smem);
         ft.reward = rew;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ft.rbits[i] = p.fast_rbits[i];
         ft.term = p.ncells;
-        return smem + (fast_table_bytes(p) + 15) / 16 * 16;
+        return smem + fast_table_bytes(p);
+    }
+    __device__ __forceinline__ static bool fast_has_reward(const FastTables& ft, int cell) {
+        const uint32_t lo = (cell & 32) ? ft.rbits[1] : ft.rbits[0], hi = (cell & 32) ? ft.rbits[3] : ft.rbits[2];
+        return (((cell & 64) ? hi : lo) >> (cell & 31)) & 1u;
     }
     __device__ __forceinline__ static double fast_reward(const FastTables& ft, int cell) { return ft.reward[cell]; }
     __device__ __forceinline__ static int fast_gen(const FastTables& ft, int cell, int a, uint32_t w) {
-        const FastEntry* e = ft.tt + (cell * 4 + a);
-        const uint4 t = *reinterpret_cast<const uint4*>(e->t);
-        const uint4 nx = *reinterpret_cast<const uint4*>(e->next);
-        const uint32_t n4 = e->next[4];
-        uint32_t sp = nx.x;
-        sp = w > t.x ? nx.y : sp;
-        sp = w > t.y ? nx.z : sp;
-        sp = w > t.z ? nx.w : sp;
-        sp = w > t.w ? n4 : sp;
-        return (int)sp;
+        const uint4 e = *reinterpret_cast<const uint4*>(ft.tt + (cell * 4 + a));
+        const int j = (int)(w > e.x) + (int)(w > e.y) + (int)(w > e.z);
+        return cell + (int)(signed char)(e.w >> (8 * j));
     }
 
     __device__ __forceinline__ static State load(const Params& p, const AbiState& a) {

@@ -104,6 +104,10 @@ struct Tile {
     }
 };
 
+// x / n for a visit count n >= 1. An exactly zero numerator (every backup level inside a zero-reward region) would
+// send CUDA's IEEE division to its ~150-instruction slow path; 0 / n is the numerator itself, sign included.
+__device__ __forceinline__ double div_by_count(double x, double n) { return x == 0.0 ? x : DM_DIV(x, n); }
+
 template <class M, int G>
 struct Search {
     using State = typename M::State;
@@ -273,7 +277,7 @@ struct Search {
                 rw->n[e.slot] = nn;
                 rw->total_n += 1;
                 const double qo = rw->q[e.slot];
-                rw->q[e.slot] = DM_ADD(qo, DM_DIV(DM_SUB(qv, qo), i2d(nn)));
+                rw->q[e.slot] = DM_ADD(qo, div_by_count(DM_SUB(qv, qo), i2d(nn)));
             }
             v = qv;
         }
@@ -849,9 +853,9 @@ __global__ void root_sums_kernel(const TreeHeader* hdr, const Row<M>* rows, int 
 // Lane ordering for dense-state MDPs: a counting sort of the trees by root state, so that trees planning from
 // equal roots (statistically alike, and for deterministic models identical, amounts of work per iteration) run
 // in the same warps and a warp's lanes stay converged. Every group of equal roots is padded to whole warps
-// (idle slots hold -1), and the warps are then spread over the grid by a multiplicative permutation so that no
-// SM ends up with all the long-running groups. The order only decides which lane works on which tree; results do
-// not depend on it.
+// (idle slots hold -1), and the warps are then dealt round-robin to the thread blocks, so that every block (and
+// SM) receives an evenly spaced sample of the groups instead of a run of warps with the same, possibly
+// long-running, root. The order only decides which lane works on which tree; results do not depend on it.
 template <class M>
 __global__ void order_hist_kernel(const typename M::Params mdp, const typename M::AbiState* roots, long long n_trees, int* bins) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -893,15 +897,15 @@ static __global__ void order_scan_kernel(int* bins, int n, int tpw) {
     }
 #endif
 }
-// slot = group start + arrival rank; its warp w moves to (w * warp_mul) mod n_warps
+// slot = group start + arrival rank; its warp w goes to block w mod n_blocks, position w / n_blocks in that block
 template <class M>
 __global__ void order_scatter_kernel(const typename M::Params mdp, const typename M::AbiState* roots, long long n_trees, int* bins, int* order,
-                                     int tpw, long long n_warps, long long warp_mul) {
+                                     int tpw, long long n_blocks, long long warps_per_block) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_trees) return;
     const int slot = atomicAdd(bins + M::dense_index(mdp, M::load(mdp, roots[t])), 1);
     const long long w = slot / tpw;
-    order[((w * warp_mul) % n_warps) * tpw + slot % tpw] = (int)t;
+    order[((w % n_blocks) * warps_per_block + w / n_blocks) * tpw + slot % tpw] = (int)t;
 }
 
 // dynamic shared memory of one block of the G variant: the path stacks, if they fit

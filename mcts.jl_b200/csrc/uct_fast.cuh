@@ -1,28 +1,31 @@
-// uct_fast.cuh -- the lean vanilla-UCT kernel for dense-state MDPs whose model tables fit in shared memory
-// (SimpleGridWorld). Same algorithm, same arithmetic and same results as search_kernel<M, UCT, 1> (search.cuh);
-// what differs is the machine mapping, chosen after profiling the generic kernel (profiles/):
+// uct_fast.cuh -- the lean vanilla-UCT kernel for small dense-state MDPs whose model tables fit in shared memory
+// (SimpleGridWorld up to 127 cells). Same algorithm, same arithmetic and same results as
+// search_kernel<M, UCT, 1> (search.cuh); what differs is the machine mapping, chosen after profiling the tile
+// kernel (profiles/):
 //
 //   The search of one tree is a strictly serial chain of dependent steps (iteration n+1 reads the statistics
-//   iteration n wrote; src/vanilla.jl:229-235), and a batch has far fewer trees than a B200 has lanes, so the
-//   cost that matters is the LATENCY of one step of one tree, not instruction throughput. This kernel shortens
-//   that chain:
-//     * one lane per tree, one block per SM; every model table (fused per-(cell, action) transition entries,
-//       rewards, tabulated rollout policy) and the head of the two UCB tables are staged in shared memory once
-//       per block, so a rollout step touches no global memory at all and its critical path is one 29-cycle LDS
-//       plus a handful of integer selects;
-//     * rows are indexed directly by the state's dense index (no state -> node map probe between two levels);
-//       the row of the next level is fetched as soon as the successor state is known;
+//   iteration n wrote; src/vanilla.jl:229-235) and a batch has far fewer trees than a B200 has lanes, so what
+//   counts is the LATENCY of one step of one tree and the number of LSU wavefronts it costs (ncu: the L1/shared
+//   data pipe is the busiest unit). This kernel shortens the chain and the traffic:
+//     * one lane per tree, one block per SM; the model (one 16-byte entry per (state, action): three sampling
+//       thresholds + four successor deltas; rewards; a tabulated rollout policy) and the heads of the two UCB
+//       tables live in shared memory, so a rollout step is ONE 128-bit LDS and a few integer selects and touches
+//       no global memory;
+//     * a state node is 64 bytes = 4 children x {q f64, n i32, tag u32}, indexed directly by the state's dense
+//       index (no state -> node map) and read with two 256-bit loads; the successor's row is requested as soon as
+//       the successor is known;
 //     * a global store evicts its line from L1, so in a read-modify-write backup every load pays an L2 round trip
-//       (~350 cycles measured, scripts/microbench/lat.cu). The backup here loads nothing: the descent leaves a
-//       16-byte record per level in shared memory ([level][lane], conflict-free) with the visited (node, child) and
-//       that child's (n, q) as it was read for selection, and the backup only computes and stores. A (node, child)
-//       pair that occurs twice on one path (self-loops at walls, cycles) is handled exactly: the descent stamps each
-//       row it passes with the iteration and the level per child, so a repeated pair finds its previous level
-//       and the backup forwards the new (n, q) into that level's record; total_n is not kept during the search
-//       (it is always the sum of the children's n) and is written once by total_n_kernel afterwards;
-//     * random words come from whole Philox blocks generated once per 4 levels / 2-4 rollout steps, with no
-//       per-word buffer bookkeeping; every run-time option that the generic kernel tests per step (rollout
-//       policy kind, estimator kind, leaf-parallel count) is a template parameter or an applicability rule here.
+//       (~350 cycles, scripts/microbench/lat.cu). The backup here loads nothing: the descent leaves a 16-byte
+//       record per level in shared memory ([level][lane], conflict-free) with the visited (node, child) and that
+//       child's (n, q) as read for selection; the backup computes and issues one 128-bit store per level. A
+//       (node, child) pair that occurs twice on one path (self-loops at walls, cycles) is handled exactly: the
+//       descent tags the child with (iteration, level), a repeated pair finds its previous level in the tag and the
+//       backup forwards the new (n, q) into that level's record;
+//     * random words come from whole Philox blocks (one per 4 levels / 2-4 rollout steps); UCB arg-max is a
+//       two-round tournament on table-based scores with an error-margin test, exact ties (bit-identical (n, q))
+//       resolved inline to the lowest index and the reference's exact expression as the last resort.
+//   After the last launch finalize_rows_kernel rewrites the rows in place into the Row<M> layout (total_n = sum of
+//   the children's n; key = insertion sequence number) that the decision / query / export code reads.
 //
 // Reference lines restated: simulate src/vanilla.jl:240-276, insert_node! :292-307, best_sanode_UCB :354-386,
 // estimate_value(::SolvedRolloutEstimator) src/domain_knowledge.jl:65-73 + the POMDPTools RolloutSimulator loop.
@@ -34,8 +37,16 @@
 
 namespace mctsb200 {
 
+#ifdef MCTSB200_PHASE_TIMING
+__device__ __forceinline__ unsigned __smid() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+#endif
+
 constexpr int kFastMaxThreads = 512;
-constexpr int kFastTab = 1024;  // entries of sqrt(log N) and 1/sqrt(n) staged in shared memory
+constexpr int kFastTab = 2048;  // entries of sqrt(log N) and 1/sqrt(n) staged in shared memory
 enum { FAST_POLICY_RANDOM = 0, FAST_POLICY_CONSTANT = 1, FAST_POLICY_TABLE = 2 };
 
 // words b0..b3 of block `blk` of stream (seed, tree, iteration, stream_id) -- the contract of include/mctsb200.h
@@ -51,6 +62,43 @@ __device__ __forceinline__ void philox_block(uint64_t seed, uint64_t tree, uint3
     b3 = st.b3;
 }
 
+// One state node of the fast kernel: child k = action k.
+//   tag == 0             the state is not in the tree (rows are zero-filled before the search)
+//   tag = stamp<<8|lvl   stamp = (iteration+1) mod 2^24 of the last descent that took this child, lvl = its level
+//                        on that path (0xff = none; a fresh node carries stamp 0)
+struct __align__(16) FastChild {
+    double q;
+    int n;
+    uint32_t tag;
+};
+struct __align__(32) FastRow {
+    FastChild c[4];
+};
+static_assert(sizeof(FastRow) == 64, "one row = two 32-byte sectors");
+
+__device__ __forceinline__ void load_row(const FastRow* rw, FastChild (&k)[4]) {
+#ifdef MCTSB200_HOST_EMU
+    for (int j = 0; j < 4; ++j) k[j] = rw->c[j];
+#else
+    unsigned long long a0, a1, a2, a3, b0, b1, b2, b3;
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(rw) : "memory");
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b0), "=l"(b1), "=l"(b2), "=l"(b3) : "l"(&rw->c[2]) : "memory");
+    k[0].q = __longlong_as_double((long long)a0); k[0].n = (int)(uint32_t)a1; k[0].tag = (uint32_t)(a1 >> 32);
+    k[1].q = __longlong_as_double((long long)a2); k[1].n = (int)(uint32_t)a3; k[1].tag = (uint32_t)(a3 >> 32);
+    k[2].q = __longlong_as_double((long long)b0); k[2].n = (int)(uint32_t)b1; k[2].tag = (uint32_t)(b1 >> 32);
+    k[3].q = __longlong_as_double((long long)b2); k[3].n = (int)(uint32_t)b3; k[3].tag = (uint32_t)(b3 >> 32);
+#endif
+}
+__device__ __forceinline__ void store_child(FastChild* c, double q, int n, uint32_t tag) {
+    *reinterpret_cast<int4*>(c) = int4{__double2loint(q), __double2hiint(q), n, (int)tag};
+}
+
+// the reference's exact scores, out of line: needed for ~0.1 % of the selections
+template <class M>
+__device__ __noinline__ int exact_scores_cold(const DevCfg* cfg, typename Search<M, 1>::Kids k, int N) {
+    return Search<M, 1>::exact_scores(Tile<1>(), *cfg, k, M::kActions, N, false);
+}
+
 // bytes of dynamic shared memory of one block
 template <class M>
 static inline size_t fast_smem_bytes(const typename M::Params& p, int depth, int block_threads) {
@@ -61,7 +109,7 @@ static inline size_t fast_smem_bytes(const typename M::Params& p, int depth, int
 template <class M, int POLICY>
 __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __grid_constant__ KernelArgs<M> args) {
     constexpr int A = M::kActions;
-    static_assert(A == 4, "rows are read with 16-byte vector loads of four children");
+    static_assert(A == 4, "a row holds exactly four children");
     using SG = Search<M, 1>;
 #ifdef MCTSB200_HOST_EMU
     static unsigned char fast_smem[256 * 1024];
@@ -99,7 +147,8 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
     const long long slot_id = (long long)blockIdx.x * BD + threadIdx.x;
     const long long tree = slot_id >= args.n_slots ? -1 : args.order ? (long long)args.order[slot_id] : slot_id;
     if (tree >= 0) {
-        Row<M>* const rows = args.rows + tree * args.geo.NS;
+        FastRow* const rows = reinterpret_cast<FastRow*>(args.rows) + tree * args.geo.NS;
+        uint16_t* const seq = reinterpret_cast<uint16_t*>(args.map) + tree * args.geo.MAP;  // insertion sequence number per state
         TreeHeader* const hd = args.hdr + tree;
         TreeHeader h = *hd;
         int n_state = h.n_state, root = h.root;
@@ -107,31 +156,22 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
         const uint64_t tree_index = (uint64_t)(args.tree_index_base + tree);
         const uint64_t seed = cfg.seed;
         const int TERM = ft.term;
-        const double gamma = M::discount(args.mdp), eps = cfg.rollout_eps;
+        const double gamma = M::discount(args.mdp), eps = cfg.rollout_eps, c_ucb = cfg.c;
         unsigned n_levels = 0, n_inserts = 0, n_rollouts = 0, n_sims = 0, n_exact = 0;
         unsigned long long n_steps = 0;
 
-        // insert_node! (src/vanilla.jl:292-307): all A children at once; the row's key field holds the 1-based
-        // insertion sequence number (= the reference's state-node id)
+        // insert_node! (src/vanilla.jl:292-307): all A children at once
         auto insert = [&](int cell) {
-            Row<M>* rw = rows + cell;
-            const double iq = cfg.init_Q;
-            const int in = cfg.init_N;
-            *reinterpret_cast<double2*>(&rw->q[0]) = double2{iq, iq};
-            *reinterpret_cast<double2*>(&rw->q[2]) = double2{iq, iq};
-            *reinterpret_cast<int4*>(&rw->n[0]) = int4{in, in, in, in};
-            uint32_t pk = 0;
+            FastRow* rw = rows + cell;
 #pragma unroll
-            for (int k = 0; k < A; ++k) pk = Row<M>::pack_add(pk, k, k);
-            ++n_state;
-            // tail: [stamp (total_n's slot) | packed | seq (key) + level bytes of children 0,1 | children 2,3]
-            *reinterpret_cast<int4*>(&rw->total_n) = int4{0, (int)pk, n_state, 0};
+            for (int k = 0; k < A; ++k) store_child(&rw->c[k], cfg.init_Q, cfg.init_N, 0xffu);
+            seq[cell] = (uint16_t)(++n_state);
             ++n_inserts;
         };
 
         if (args.iter_begin == 0 && h.iterations == 0 && status == MCTSB200_OK) {  // root lookup / insertion (src/vanilla.jl:219-224)
             root = M::dense_index(args.mdp, M::load(args.mdp, args.roots[tree * args.root_stride]));
-            if (rows[root].packed == 0) insert(root);
+            if (rows[root].c[0].tag == 0) insert(root);
         }
 
 #ifdef MCTSB200_PHASE_TIMING
@@ -149,14 +189,13 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
         if (status == MCTSB200_OK) {
             for (; it < args.iter_end; ++it) {
                 PT_CLOCK(t0);
+                const uint32_t stamp = ((uint32_t)it + 1u) & 0xffffffu;
                 // ---- descent: simulate(planner, node, depth), one level per trip --------------------------------
                 int cell = root, d = cfg.depth, top = 0;
                 bool leaf = false;
                 uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-                double2 q01 = *reinterpret_cast<const double2*>(&rows[root].q[0]);
-                double2 q23 = *reinterpret_cast<const double2*>(&rows[root].q[2]);
-                int4 n4 = *reinterpret_cast<const int4*>(&rows[root].n[0]);
-                int4 tail = *reinterpret_cast<const int4*>(&rows[root].total_n);
+                FastChild k[A];
+                load_row(rows + root, k);
                 for (;;) {
                     if (cell == TERM) break;  // isterminal: value 0.0, no statistics update at this node
                     if (d == 0) {
@@ -166,93 +205,94 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     ++n_levels;
                     if ((top & 3) == 0) philox_block(seed, tree_index, (uint32_t)it, 0u, (uint32_t)(top >> 2), b0, b1, b2, b3);
                     const uint32_t w = (top & 2) ? ((top & 1) ? b3 : b2) : ((top & 1) ? b1 : b0);
-                    // best_sanode_UCB
-                    typename SG::Kids k;
-                    k.q[0] = q01.x; k.q[1] = q01.y; k.q[2] = q23.x; k.q[3] = q23.y;
-                    k.n[0] = n4.x; k.n[1] = n4.y; k.n[2] = n4.z; k.n[3] = n4.w;
-                    const int N = k.n[0] + k.n[1] + k.n[2] + k.n[3];  // total_n(snode): always the sum over its children
+
+                    // ---- best_sanode_UCB (src/vanilla.jl:354-386) ----
                     int slot;
-                    if (cfg.c == 0.0) {
-                        slot = 0;
-                        double best = k.q[0];
-#pragma unroll
-                        for (int j = 1; j < A; ++j)
-                            if (k.q[j] > best) {
-                                best = k.q[j];
-                                slot = j;
-                            }
-                    } else if (k.n[0] == 0 || k.n[1] == 0 || k.n[2] == 0 || k.n[3] == 0) {
-                        slot = k.n[0] == 0 ? 0 : k.n[1] == 0 ? 1 : k.n[2] == 0 ? 2 : 3;  // "if action was not used, use it"
+                    if (k[0].n == 0 || k[1].n == 0 || k[2].n == 0 || k[3].n == 0) {
+                        slot = k[0].n == 0 ? 0 : k[1].n == 0 ? 1 : k[2].n == 0 ? 2 : 3;  // "if action was not used, use it"
                     } else {
-                        const int n_max = max(max(k.n[0], k.n[1]), max(k.n[2], k.n[3]));
-                        if (N >= cfg.log_tab_n || n_max >= cfg.rsqrt_tab_n) {
-                            ++n_exact;
-                            slot = SG::exact_scores(Tile<1>(), cfg, k, A, N, false);
+                        // fast-path scores S_j = q_j + (c*sqrt(log N)) * n_j^(-1/2) from the two tables (see
+                        // Search::select_child for the error bound behind the margin)
+                        const int N = (k[0].n + k[1].n) + (k[2].n + k[3].n);  // total_n(snode): always the sum over its children
+                        double S[A], T[A], cs;
+                        if (N < kFastTab) {  // then every n_j is below kFastTab too: all five factors come from shared memory
+                            cs = DM_MUL(c_ucb, s_sqrtlog[N]);
+#pragma unroll
+                            for (int j = 0; j < A; ++j) T[j] = DM_MUL(cs, s_rsqrt[k[j].n]);
                         } else {
-                            // fast-path scores S_j = q_j + (c*sqrt(log N)) * n_j^(-1/2) (see Search::select_child)
-                            const double cs = DM_MUL(cfg.c, N < kFastTab ? s_sqrtlog[N] : __ldg(cfg.sqrtlog_tab + N));
-                            double S[A], mag = 0.0;
+                            cs = DM_MUL(c_ucb, __ldg(cfg.sqrtlog_tab + N));
 #pragma unroll
-                            for (int j = 0; j < A; ++j) {
-                                const double term = DM_MUL(cs, k.n[j] < kFastTab ? s_rsqrt[k.n[j]] : __ldg(cfg.rsqrt_tab + k.n[j]));
-                                S[j] = DM_ADD(k.q[j], term);
-                                mag = DM_ADD(mag, DM_ADD(fabs(k.q[j]), term));
-                            }
-                            double best = -CUDART_INF, second = -CUDART_INF;
-                            int best_i = SG::kNone;
+                            for (int j = 0; j < A; ++j) T[j] = DM_MUL(cs, __ldg(cfg.rsqrt_tab + k[j].n));
+                        }
 #pragma unroll
-                            for (int j = 0; j < A; ++j) {
-                                if (S[j] > best) {
-                                    second = best;
-                                    best = S[j];
-                                    best_i = j;
-                                } else if (S[j] > second) {
-                                    second = S[j];
+                        for (int j = 0; j < A; ++j) S[j] = DM_ADD(k[j].q, T[j]);
+                        const double mag = DM_ADD(DM_ADD(DM_ADD(fabs(k[0].q), T[0]), DM_ADD(fabs(k[1].q), T[1])),
+                                                  DM_ADD(DM_ADD(fabs(k[2].q), T[2]), DM_ADD(fabs(k[3].q), T[3])));
+                        const double margin = DM_MUL(5.6843418860808015e-14, mag);  // 2^-44 * sum(|q| + term); NaN if any input is
+                        // two-round tournament; equal scores keep the lower index, like the reference's strict '>' scan
+                        const bool m01 = S[1] > S[0], m23 = S[3] > S[2];
+                        const double w01 = m01 ? S[1] : S[0], l01 = m01 ? S[0] : S[1];
+                        const double w23 = m23 ? S[3] : S[2], l23 = m23 ? S[2] : S[3];
+                        const bool mf = w23 > w01;
+                        const double best = mf ? w23 : w01;
+                        const double second = fmax(mf ? w01 : w23, mf ? l23 : l01);
+                        const int best_i = mf ? (m23 ? 3 : 2) : (m01 ? 1 : 0);
+                        if (DM_SUB(best, second) > margin) {
+                            slot = best_i;
+                        } else {
+                            // near-tie: children inside the margin with bit-identical (n, q) have bit-identical reference
+                            // scores (tie -> lowest index); anything else is decided by the reference's exact expression
+                            const int nb = best_i == 0 ? k[0].n : best_i == 1 ? k[1].n : best_i == 2 ? k[2].n : k[3].n;
+                            const double qb = best_i == 0 ? k[0].q : best_i == 1 ? k[1].q : best_i == 2 ? k[2].q : k[3].q;
+                            bool need_exact = !(best == best);
+                            int tie_i = best_i;
+#pragma unroll
+                            for (int j = A - 1; j >= 0; --j) {
+                                if (j != best_i && !(DM_SUB(best, S[j]) > margin)) {
+                                    if (k[j].n == nb && k[j].q == qb) tie_i = min(tie_i, j);
+                                    else need_exact = true;
                                 }
                             }
-                            const double margin = DM_MUL(5.6843418860808015e-14, mag);
-                            if (best_i != SG::kNone && DM_SUB(best, second) > margin) {
-                                slot = best_i;
+                            if (need_exact) {
+                                ++n_exact;
+                                typename SG::Kids kk;
+#pragma unroll
+                                for (int j = 0; j < A; ++j) {
+                                    kk.q[j] = k[j].q;
+                                    kk.n[j] = k[j].n;
+                                }
+                                slot = exact_scores_cold<M>(&cfg, kk, N);
                             } else {
-                                const int r = SG::select_near_tie(Tile<1>(), &cfg, k, A, N, false, cs, margin);
-                                if (r & 256) ++n_exact;
-                                slot = r & 255;
+                                slot = tie_i;
                             }
                         }
                     }
+
                     // sp, r = @gen(:sp,:r)(mdp, s, a, rng); the reward is re-read from the table during backup
                     const int sp = M::fast_gen(ft, cell, slot, w);
                     {
-                        // record the level; stamp the row so that a later level of this path on the same (node, child) finds this one
-                        const uint32_t stamp = (uint32_t)it + 1u;
-                        uint32_t lv = ((uint32_t)tail.z >> 16) | ((uint32_t)tail.w << 16);  // level byte per child
-                        if ((uint32_t)tail.x != stamp) lv = 0xffffffffu;
-                        const uint32_t link = (lv >> (8 * slot)) & 0xffu;
-                        lv = (lv & ~(0xffu << (8 * slot))) | ((uint32_t)top << (8 * slot));
-                        const int ns = slot == 0 ? k.n[0] : slot == 1 ? k.n[1] : slot == 2 ? k.n[2] : k.n[3];
-                        const double qs = slot == 0 ? k.q[0] : slot == 1 ? k.q[1] : slot == 2 ? k.q[2] : k.q[3];
+                        // record the level; tag the child so that a later level of this path on the same (node, child) finds this one
+                        const int ns = slot == 0 ? k[0].n : slot == 1 ? k[1].n : slot == 2 ? k[2].n : k[3].n;
+                        const double qs = slot == 0 ? k[0].q : slot == 1 ? k[1].q : slot == 2 ? k[2].q : k[3].q;
+                        const uint32_t tg = slot == 0 ? k[0].tag : slot == 1 ? k[1].tag : slot == 2 ? k[2].tag : k[3].tag;
+                        const uint32_t link = (tg >> 8) == stamp ? (tg & 0xffu) : 0xffu;
                         s_path[top * BD] = uint4{(uint32_t)cell | ((uint32_t)slot << 16) | (link << 24), (uint32_t)ns, (uint32_t)__double2loint(qs),
                                                  (uint32_t)__double2hiint(qs)};
-                        *reinterpret_cast<int4*>(&rows[cell].total_n) =
-                            int4{(int)stamp, tail.y, (int)(((uint32_t)tail.z & 0xffffu) | (lv << 16)), (int)(lv >> 16)};
+                        rows[cell].c[slot].tag = (stamp << 8) | (uint32_t)top;
                     }
                     ++top;
                     --d;
                     cell = sp;
-                    const Row<M>* rw = rows + cell;
-                    q01 = *reinterpret_cast<const double2*>(&rw->q[0]);
-                    q23 = *reinterpret_cast<const double2*>(&rw->q[2]);
-                    n4 = *reinterpret_cast<const int4*>(&rw->n[0]);
-                    tail = *reinterpret_cast<const int4*>(&rw->total_n);
-                    if (tail.y == 0) {  // new node: estimate_value(sp, depth-1), also when sp is terminal
+                    load_row(rows + cell, k);
+                    if (k[0].tag == 0) {  // new node: estimate_value(sp, depth-1), also when sp is terminal
                         insert(cell);
                         leaf = true;
                         break;
                     }
                 }
-
                 PT_CLOCK(t1);
                 PT_TRIP(0, top);
+
                 // ---- leaf evaluation: one rollout (POMDPTools RolloutSimulator loop) --------------------------------
                 double v = 0.0;
                 if (leaf) {
@@ -279,9 +319,8 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                                 act = POLICY == FAST_POLICY_CONSTANT ? cfg.pparam[0] : (int)s_pol[cc];
                                 wg = w[u];
                             }
-                            const double r = M::fast_reward(ft, cc);
+                            if (M::fast_has_reward(ft, cc)) r_total = DM_ADD(r_total, DM_MUL(disc, M::fast_reward(ft, cc)));
                             cc = M::fast_gen(ft, cc, act, wg);
-                            r_total = DM_ADD(r_total, DM_MUL(disc, r));
                             disc = DM_MUL(disc, gamma);
                             ++step;
                             ++steps_here;
@@ -298,13 +337,12 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     const uint4 e = s_path[lvl * BD];
                     const int node = (int)(e.x & 0xffffu), slot = (int)((e.x >> 16) & 0xffu);
                     const uint32_t link = e.x >> 24;
-                    const double qv = DM_ADD(M::fast_reward(ft, node), DM_MUL(gamma, v));
+                    double qv = DM_MUL(gamma, v);
+                    if (M::fast_has_reward(ft, node)) qv = DM_ADD(M::fast_reward(ft, node), qv);
                     const int nn = (int)e.y + 1;
                     const double qo = __hiloint2double((int)e.w, (int)e.z);
-                    const double qn = DM_ADD(qo, DM_DIV(DM_SUB(qv, qo), SG::i2d(nn)));
-                    Row<M>* rw = rows + node;
-                    rw->n[slot] = nn;
-                    rw->q[slot] = qn;
+                    const double qn = DM_ADD(qo, div_by_count(DM_SUB(qv, qo), SG::i2d(nn)));
+                    store_child(&rows[node].c[slot], qn, nn, (stamp << 8) | 0xffu);
                     if (link != 0xffu) {  // the same (node, child) higher up on this path backs up on top of this update
                         uint4* up = s_path + link * BD;
                         up->y = (uint32_t)nn;
@@ -322,11 +360,10 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
             }
         }
 #ifdef MCTSB200_PHASE_TIMING
-        if ((threadIdx.x & 31) == 0 && (blockIdx.x % 37) == 0 && threadIdx.x < 64 && n_sims)
-            printf("PT block %d warp %d: iters %u | descent %lld cyc/iter %.2f levels/iter -> %.0f cyc/level | rollout %lld cyc/iter %.2f steps/iter -> %.0f cyc/step | backup %lld cyc/iter -> %.0f cyc/level\n",
-                   (int)blockIdx.x, (int)(threadIdx.x >> 5), n_sims, cyc[0] / n_sims, (double)trips[0] / n_sims, (double)cyc[0] / (double)max(trips[0], 1LL),
-                   cyc[1] / n_sims, (double)trips[1] / n_sims, (double)cyc[1] / (double)max(trips[1], 1LL), cyc[2] / n_sims,
-                   (double)cyc[2] / (double)max(trips[2], 1LL));
+        if ((threadIdx.x & 31) == 0 && n_sims)  // PT block warp smid | levels/iter steps/iter | cycles/iter: descent rollout backup | per level, step, level
+            printf("PT %d %d %d | %.2f %.2f | %lld %lld %lld | %.0f %.0f %.0f\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)__smid(),
+                   (double)trips[0] / n_sims, (double)trips[1] / n_sims, cyc[0] / n_sims, cyc[1] / n_sims, cyc[2] / n_sims,
+                   (double)cyc[0] / (double)max(trips[0], 1LL), (double)cyc[1] / (double)max(trips[1], 1LL), (double)cyc[2] / (double)max(trips[2], 1LL));
 #endif
 
         h.n_state = n_state;
@@ -354,18 +391,30 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 #endif
 }
 
-// total_n(snode) = sum of its children's n (src/vanilla.jl:296-305 sets it to the sum of init_N, :272-273 add one to
-// both per backup). Written once after the search, one thread per row.
+// After the last search launch: rewrite every row in place from the kernel's FastRow layout into Row<M>
+// (q[A], n[A], total_n = sum of the children's n -- src/vanilla.jl:296-305 and :272-273 keep them equal --,
+// all-children label word, key = 1-based insertion sequence number), which is what decide_kernel, the root
+// queries and the tree export read. One thread per row.
 template <class M>
-__global__ void total_n_kernel(Row<M>* rows, long long n_rows) {
+__global__ void finalize_rows_kernel(Row<M>* rows, const uint16_t* seq, long long n_rows) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_rows) return;
-    Row<M>* rw = rows + i;
-    if (rw->packed == 0) return;
+    const FastRow fr = *reinterpret_cast<const FastRow*>(rows + i);
+    Row<M> out;
     int tot = 0;
+    uint32_t pk = 0;
 #pragma unroll
-    for (int k = 0; k < M::kActions; ++k) tot += rw->n[k];
-    rw->total_n = tot;
+    for (int k = 0; k < M::kActions; ++k) {
+        out.q[k] = fr.c[k].q;
+        out.n[k] = fr.c[k].n;
+        tot += fr.c[k].n;
+        pk = Row<M>::pack_add(pk, k, k);
+    }
+    const bool present = fr.c[0].tag != 0;
+    out.total_n = present ? tot : 0;
+    out.packed = present ? pk : 0u;
+    out.key = (typename M::Key)seq[i];
+    rows[i] = out;
 }
 
 template <class M>
