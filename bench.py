@@ -106,7 +106,8 @@ class ClockSampler(threading.Thread):
 
     def stop(self):
         self._stop_ev.set()
-        self.join(timeout=2)
+        if self.is_alive():
+            self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
@@ -247,7 +248,8 @@ def main():
             fn()
         barrier()
         sampler = ClockSampler(local_rank)
-        sampler.start()
+        if not os.environ.get("BENCH_NO_SAMPLER"):
+            sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         stats = [fn() for _ in range(steps)]

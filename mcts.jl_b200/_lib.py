@@ -44,7 +44,8 @@ def build_library(verbose: bool = False) -> str:
 
 
 def load_library(path: Optional[str] = None) -> C.CDLL:
-    path = os.path.abspath(path or DEFAULT_LIB)
+    # MCTSB200_LIB: tuning experiments only (an alternative build of the same CUDA library, e.g. other -D switches)
+    path = os.path.abspath(path or os.environ.get("MCTSB200_LIB") or DEFAULT_LIB)
     if path in _lib_cache:
         return _lib_cache[path]
     if not os.path.exists(path):

@@ -71,6 +71,7 @@ struct Storage {
     Geometry geo{};
     size_t row_bytes = 0, aux_bytes = 0, map_entry_bytes = 0;
     DevBuf hdr, rows, aux, trans, map, path;
+    DevBuf rows_fast;  // working table of uct_fast.cuh (interleaved); `rows` receives the Row<M> table after the search
 };
 
 }  // namespace
@@ -271,12 +272,15 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     const size_t total = b_hdr + b_rows + b_aux + b_trans + b_map + b_path;
 
     Storage& st = ctx->st;
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const size_t have = st.hdr.cap + st.rows.cap + st.aux.cap + st.trans.cap + st.map.cap + st.path.cap;
-    if (total > free_b + have)
-        return fail(MCTSB200_ERR_CAPACITY, "node tables need %.2f GB but only %.2f GB of HBM are free; plan fewer roots per call", total / 1e9,
-                    (free_b + have) / 1e9);
+    const bool grows = b_hdr > st.hdr.cap || b_rows > st.rows.cap || b_aux > st.aux.cap || b_trans > st.trans.cap || b_map > st.map.cap || b_path > st.path.cap;
+    if (grows) {  // (cudaMemGetInfo is slow: only ask when something has to be allocated)
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        if (total > free_b + have)
+            return fail(MCTSB200_ERR_CAPACITY, "node tables need %.2f GB but only %.2f GB of HBM are free; plan fewer roots per call", total / 1e9,
+                        (free_b + have) / 1e9);
+    }
     st.valid = false;
     CUDA_TRY(st.hdr.ensure(b_hdr));
     CUDA_TRY(st.rows.ensure(b_rows));
@@ -294,7 +298,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     st.map_entry_bytes = map_entry;
     CUDA_TRY(cudaMemsetAsync(st.hdr.p, 0, b_hdr, ctx->stream));
     if (b_map) CUDA_TRY(cudaMemsetAsync(st.map.p, 0, b_map, ctx->stream));
-    if (direct) CUDA_TRY(cudaMemsetAsync(st.rows.p, 0, b_rows, ctx->stream));  // Row::packed == 0 <=> state not in the tree
+    // (the fast kernel's own table is allocated and zero-filled in run_search, once the slot count is known)
     return MCTSB200_OK;
 }
 
@@ -404,8 +408,8 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
 }
 
 // debugging / tuning switches (environment): MCTSB200_PATH_SMEM=0 keeps the tile kernel's path stacks in HBM,
-// MCTSB200_FAST=0 disables the shared-memory lane-per-tree UCT kernel, MCTSB200_LANE_ORDER=1 groups trees with
-// equal root states into the same warps (off by default: measured slower)
+// MCTSB200_FAST=0 disables the shared-memory lane-per-tree UCT kernel, MCTSB200_LANE_ORDER=0/1 switches the grouping
+// of trees with equal root states into the same warps (default: on for the lane-per-tree kernel, off for the tile kernel)
 bool env_enabled(const char* name, bool dflt = true) {
     const char* v = std::getenv(name);
     if (!v || !v[0]) return dflt;
@@ -530,7 +534,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.n_slots = n_trees;
     int fast_block = 0;  // block size the lane order was dealt for
     if constexpr (M::kDense) {
-        if (root_stride == 1 && n_trees > 32 && n_trees < (1LL << 30) && env_enabled("MCTSB200_LANE_ORDER", false)) {
+        if (root_stride == 1 && n_trees > 32 && n_trees < (1LL << 30) && env_enabled("MCTSB200_LANE_ORDER", fast >= 0)) {
             const int n_bins = MdpAccess<M>::dense_count(ctx);
             const int tpw = 32 / G;  // tiles per warp
             // upper bound of the padded slot count (the exact one is only known on the device): every non-empty
@@ -561,6 +565,20 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             args.n_slots = n_warps * tpw;
             launches += 3;
         }
+    }
+    if (fast >= 0) {
+        // the fast kernel's working table: 64 B per (slot, state), slots padded to whole warps, zero = "not in the tree"
+        const long long slots32 = (args.n_slots + 31) / 32 * 32;
+        const size_t bytes = (size_t)slots32 * (size_t)st.geo.NS * 64;
+        if (bytes > st.rows_fast.cap) {
+            size_t free_b = 0, total_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            if (bytes > free_b + st.rows_fast.cap)
+                return fail(MCTSB200_ERR_CAPACITY, "node tables need %.2f GB more HBM than is free; plan fewer roots per call", (bytes - st.rows_fast.cap) / 1e9);
+        }
+        CUDA_TRY(st.rows_fast.ensure(bytes));
+        CUDA_TRY(cudaMemsetAsync(st.rows_fast.p, 0, bytes, ctx->stream));
+        args.rows_fast = st.rows_fast.p;
     }
     // one search launch over iterations [args.iter_begin, args.iter_end)
     auto launch = [&]() -> int32_t {
@@ -612,9 +630,11 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     }
     if constexpr (M::kFast) if (fast >= 0) {
-        const long long n_rows = n_trees * st.geo.NS;
+        const long long slots32 = (args.n_slots + 31) / 32 * 32;
+        const long long n_rows = slots32 * st.geo.NS;
         auto kernel = finalize_rows_kernel<M>;
-        MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (Row<M>*)st.rows.p, (const uint16_t*)st.map.p, n_rows);
+        MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (const FastRow*)st.rows_fast.p, args.order,
+                        (const uint16_t*)st.map.p, (Row<M>*)st.rows.p, st.geo.NS, args.n_slots);
         CUDA_TRY(cudaGetLastError());
         ++launches;
     }
@@ -953,7 +973,7 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     if (!c) return MCTSB200_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->counters,
+    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->counters,
                       &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
                       &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->gw_fast};
     for (DevBuf* b : bufs) b->release();

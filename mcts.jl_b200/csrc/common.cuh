@@ -199,6 +199,7 @@ struct KernelArgs {
     Geometry geo;
     TreeHeader* hdr;
     Row<M>* rows;
+    void* rows_fast;                    // uct_fast.cuh: FastRow table, [warp][state][lane]
     Aux<M>* aux;
     TransRec* trans;
     void* map;

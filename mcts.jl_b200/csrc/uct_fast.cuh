@@ -13,7 +13,9 @@
 //       no global memory;
 //     * a state node is 64 bytes = 4 children x {q f64, n i32, tag u32}, indexed directly by the state's dense
 //       index (no state -> node map) and read with two 256-bit loads; the successor's row is requested as soon as
-//       the successor is known;
+//       the successor is known. The rows of the 32 trees of a warp are interleaved, [warp][state][lane], so the
+//       warp's working set is one contiguous ~200 KB region (TLB reach) and lanes that stand on the same state
+//       read neighbouring rows;
 //     * a global store evicts its line from L1, so in a read-modify-write backup every load pays an L2 round trip
 //       (~350 cycles, scripts/microbench/lat.cu). The backup here loads nothing: the descent leaves a 16-byte
 //       record per level in shared memory ([level][lane], conflict-free) with the visited (node, child) and that
@@ -147,7 +149,8 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
     const long long slot_id = (long long)blockIdx.x * BD + threadIdx.x;
     const long long tree = slot_id >= args.n_slots ? -1 : args.order ? (long long)args.order[slot_id] : slot_id;
     if (tree >= 0) {
-        FastRow* const rows = reinterpret_cast<FastRow*>(args.rows) + tree * args.geo.NS;
+        // row of state c of this lane's tree: rows[c * 32]  ([warp][state][lane] interleaving)
+        FastRow* const rows = reinterpret_cast<FastRow*>(args.rows_fast) + (slot_id >> 5) * ((long long)args.geo.NS * 32) + (slot_id & 31);
         uint16_t* const seq = reinterpret_cast<uint16_t*>(args.map) + tree * args.geo.MAP;  // insertion sequence number per state
         TreeHeader* const hd = args.hdr + tree;
         TreeHeader h = *hd;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 
         // insert_node! (src/vanilla.jl:292-307): all A children at once
         auto insert = [&](int cell) {
-            FastRow* rw = rows + cell;
+            FastRow* rw = rows + cell * 32;
 #pragma unroll
             for (int k = 0; k < A; ++k) store_child(&rw->c[k], cfg.init_Q, cfg.init_N, 0xffu);
             seq[cell] = (uint16_t)(++n_state);
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 
         if (args.iter_begin == 0 && h.iterations == 0 && status == MCTSB200_OK) {  // root lookup / insertion (src/vanilla.jl:219-224)
             root = M::dense_index(args.mdp, M::load(args.mdp, args.roots[tree * args.root_stride]));
-            if (rows[root].c[0].tag == 0) insert(root);
+            if (rows[root * 32].c[0].tag == 0) insert(root);
         }
 
 #ifdef MCTSB200_PHASE_TIMING
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                 bool leaf = false;
                 uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
                 FastChild k[A];
-                load_row(rows + root, k);
+                load_row(rows + root * 32, k);
                 for (;;) {
                     if (cell == TERM) break;  // isterminal: value 0.0, no statistics update at this node
                     if (d == 0) {
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     }
                     ++n_levels;
                     if ((top & 3) == 0) philox_block(seed, tree_index, (uint32_t)it, 0u, (uint32_t)(top >> 2), b0, b1, b2, b3);
-                    const uint32_t w = (top & 2) ? ((top & 1) ? b3 : b2) : ((top & 1) ? b1 : b0);
+                    const uint32_t w = (top & 2) ? ((top & 1) ? b3 : b2) : ((top & 1) ? b1 : b0);  // word `top` of stream 0
 
                     // ---- best_sanode_UCB (src/vanilla.jl:354-386) ----
                     int slot;
@@ -270,20 +273,21 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 
                     // sp, r = @gen(:sp,:r)(mdp, s, a, rng); the reward is re-read from the table during backup
                     const int sp = M::fast_gen(ft, cell, slot, w);
+                    // what the backup needs from this level
+                    const int ns = slot == 0 ? k[0].n : slot == 1 ? k[1].n : slot == 2 ? k[2].n : k[3].n;
+                    const double qs = slot == 0 ? k[0].q : slot == 1 ? k[1].q : slot == 2 ? k[2].q : k[3].q;
+                    const uint32_t tg = slot == 0 ? k[0].tag : slot == 1 ? k[1].tag : slot == 2 ? k[2].tag : k[3].tag;
                     {
                         // record the level; tag the child so that a later level of this path on the same (node, child) finds this one
-                        const int ns = slot == 0 ? k[0].n : slot == 1 ? k[1].n : slot == 2 ? k[2].n : k[3].n;
-                        const double qs = slot == 0 ? k[0].q : slot == 1 ? k[1].q : slot == 2 ? k[2].q : k[3].q;
-                        const uint32_t tg = slot == 0 ? k[0].tag : slot == 1 ? k[1].tag : slot == 2 ? k[2].tag : k[3].tag;
                         const uint32_t link = (tg >> 8) == stamp ? (tg & 0xffu) : 0xffu;
                         s_path[top * BD] = uint4{(uint32_t)cell | ((uint32_t)slot << 16) | (link << 24), (uint32_t)ns, (uint32_t)__double2loint(qs),
                                                  (uint32_t)__double2hiint(qs)};
-                        rows[cell].c[slot].tag = (stamp << 8) | (uint32_t)top;
+                        rows[cell * 32].c[slot].tag = (stamp << 8) | (uint32_t)top;  // (before the successor's row is read: it may be this row)
                     }
                     ++top;
                     --d;
                     cell = sp;
-                    load_row(rows + cell, k);
+                    load_row(rows + sp * 32, k);
                     if (k[0].tag == 0) {  // new node: estimate_value(sp, depth-1), also when sp is terminal
                         insert(cell);
                         leaf = true;
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     const int nn = (int)e.y + 1;
                     const double qo = __hiloint2double((int)e.w, (int)e.z);
                     const double qn = DM_ADD(qo, div_by_count(DM_SUB(qv, qo), SG::i2d(nn)));
-                    store_child(&rows[node].c[slot], qn, nn, (stamp << 8) | 0xffu);
+                    store_child(&rows[node * 32].c[slot], qn, nn, (stamp << 8) | 0xffu);
                     if (link != 0xffu) {  // the same (node, child) higher up on this path backs up on top of this update
                         uint4* up = s_path + link * BD;
                         up->y = (uint32_t)nn;
@@ -391,15 +395,20 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 #endif
 }
 
-// After the last search launch: rewrite every row in place from the kernel's FastRow layout into Row<M>
-// (q[A], n[A], total_n = sum of the children's n -- src/vanilla.jl:296-305 and :272-273 keep them equal --,
-// all-children label word, key = 1-based insertion sequence number), which is what decide_kernel, the root
-// queries and the tree export read. One thread per row.
+// After the last search launch: copy every row from the kernel's interleaved FastRow table into the Row<M> table
+// [tree][state] (q[A], n[A], total_n = sum of the children's n -- src/vanilla.jl:296-305 and :272-273 keep them
+// equal --, all-children label word, key = 1-based insertion sequence number), which is what decide_kernel, the root
+// queries and the tree export read. One thread per (slot, state); consecutive threads read consecutive lanes.
 template <class M>
-__global__ void finalize_rows_kernel(Row<M>* rows, const uint16_t* seq, long long n_rows) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rows) return;
-    const FastRow fr = *reinterpret_cast<const FastRow*>(rows + i);
+__global__ void finalize_rows_kernel(const FastRow* rows_fast, const int* order, const uint16_t* seq, Row<M>* rows, int NS, long long n_slots) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // ((warp * NS) + state) * 32 + lane
+    const long long warp = i / ((long long)NS * 32);
+    const int state = (int)((i / 32) % NS), lane = (int)(i & 31);
+    const long long slot = warp * 32 + lane;
+    if (slot >= n_slots) return;
+    const long long tree = order ? (long long)order[slot] : slot;
+    if (tree < 0) return;
+    const FastRow fr = rows_fast[i];
     Row<M> out;
     int tot = 0;
     uint32_t pk = 0;
@@ -413,8 +422,8 @@ __global__ void finalize_rows_kernel(Row<M>* rows, const uint16_t* seq, long lon
     const bool present = fr.c[0].tag != 0;
     out.total_n = present ? tot : 0;
     out.packed = present ? pk : 0u;
-    out.key = (typename M::Key)seq[i];
-    rows[i] = out;
+    out.key = (typename M::Key)seq[tree * NS + state];
+    rows[tree * NS + state] = out;
 }
 
 template <class M>

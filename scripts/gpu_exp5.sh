@@ -1,0 +1,10 @@
+set -x
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.log
+: > gpurun_out/exp5.log
+B="timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+run() { echo "## $*" >> gpurun_out/exp5.log; env "$@" 2>&1 | tail -1 | python scripts/summarize_bench.py >> gpurun_out/exp5.log; }
+run X=1 $B
+run X=1 $B --workload config2-uct-gridworld-stochastic
+run X=1 $B --workload config3-dpw-gridworld
+run X=1 timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --workload config4-dpw-mountaincar
+cat gpurun_out/exp5.log

@@ -27,6 +27,10 @@ for l in dis:
         continue
     if not on:
         continue
+    ms = re.match(r"^(\$__internal_\d+_\$)?(__cuda_\w+):", l)
+    if ms:
+        cur = ("subroutine " + ms.group(2), 0)
+        continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
         if "inlined at" not in l:
