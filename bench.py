@@ -68,7 +68,7 @@ def make_workload(name, n_roots=None, lanes=0, n_iterations=None, same_root=None
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU every 200 ms during the timed region (NVML)."""
+    """Samples SM clock / throttle reasons of one GPU every 20 ms during the timed region (NVML)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -102,7 +102,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_ev.wait(0.2)
+            self._stop_ev.wait(0.02)
 
     def stop(self):
         self._stop_ev.set()
@@ -124,7 +124,8 @@ def ncu_traffic(workload):
     """dram bytes per launch of the search kernel from the committed ncu capture, if one exists."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload)
+            v = json.load(f).get(workload)
+            return int(v) if isinstance(v, (int, float)) else None
     except Exception:
         return None
 
@@ -151,7 +152,8 @@ def cpu_sample(workload, seconds_target=15.0, threads=None):
     dt = time.perf_counter() - t0
     return {"value": st.n_simulations / dt, "unit": "simulations/s", "cores": threads, "kind": "port",
             "sample": f"{n} of the workload's roots x {cfg.n_iterations} iterations (oracle, {threads} threads, {dt:.1f} s)",
-            "rollout_steps_per_s": st.n_rollout_steps / dt, "seconds": dt, "n_simulations": int(st.n_simulations)}
+            "rollout_steps_per_s": st.n_rollout_steps / dt, "seconds": dt, "n_simulations": int(st.n_simulations),
+            "n_iterations": int(cfg.n_iterations), "depth": int(cfg.depth)}
 
 
 def run_reference(args, rank, world):
@@ -171,7 +173,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "MCTS simulations/sec", "value": value, "unit": "simulations/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(vals)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "reference CPU path = C++ oracle port of MCTS.jl (Julia not installed); each step is a bounded root sample"},
+        "config": {"workload": args.workload, "n_iterations": int(last["n_iterations"]), "depth": int(last["depth"]),
+                   "note": "reference CPU path = C++ oracle port of MCTS.jl (Julia not installed); each step is a bounded root sample"},
         "cpu_baseline": {"value": value, "unit": "simulations/s", "cores": threads, "kind": "port", "sample": last["sample"]},
         "e2e": {"value": value, "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -292,7 +295,7 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
-                     "kernel": "search_kernel (one launch per step)"},
+                     "kernel": ("uct_fast_kernel" if int(st_dev[-1].kernel_variant) == 1 else "search_kernel") + " (one launch per step)"},
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
