@@ -19,7 +19,7 @@
 #include <vector>
 
 #include "search.cuh"
-#include "uct_fast.cuh"
+#include "dpw_fast.cuh"
 
 using namespace mctsb200;
 
@@ -71,7 +71,8 @@ struct Storage {
     Geometry geo{};
     size_t row_bytes = 0, aux_bytes = 0, map_entry_bytes = 0;
     DevBuf hdr, rows, aux, trans, map, path;
-    DevBuf rows_fast;  // working table of uct_fast.cuh (interleaved); `rows` receives the Row<M> table after the search
+    DevBuf rows_fast;   // working table of uct_fast.cuh / dpw_fast.cuh (interleaved); `rows` receives the Row<M> table after the search
+    DevBuf trans_fast;  // dpw_fast.cuh: per-slot transition multisets (interleaved)
 };
 
 }  // namespace
@@ -111,6 +112,12 @@ struct MdpAccess<GridWorldDev> {
     }
     static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_GW_SEEK; }
     static bool fast_ready(const mctsb200_ctx* c) { return c->gw_dev.fast_tt != nullptr; }
+    // Deterministic transitions + a deterministic rollout policy + vanilla UCT (DPW draws random actions): trees planned
+    // from equal root states are then identical whatever their Philox streams, so lanes that share a root run in lockstep.
+    static bool lockstep(const mctsb200_ctx* c, const mctsb200_solver_cfg* cfg) {
+        return c->gw_host.tprob == 1.0 && cfg->kind == MCTSB200_KIND_UCT && cfg->estimate_kind == MCTSB200_EST_ROLLOUT &&
+               cfg->rollout_policy != MCTSB200_POLICY_RANDOM;
+    }
     // a state-only deterministic rollout policy as a table over dense state indices (GridWorldDev::policy_action restated on the host)
     static bool tabulate_policy(const mctsb200_ctx* c, const mctsb200_solver_cfg* cfg, std::vector<unsigned char>& out) {
         if (cfg->rollout_policy != MCTSB200_POLICY_GW_SEEK) return false;
@@ -132,6 +139,7 @@ struct MdpAccess<MountainCarDev> {
         return (std::isfinite(s.x) && std::isfinite(s.v) && std::fabs(s.x) < 1e5) ? 0 : -1;
     }
     static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_MC_ENERGY; }
+    static bool lockstep(const mctsb200_ctx*, const mctsb200_solver_cfg*) { return false; }
 };
 
 // For every (boundary class, action): the positions where the reference's sampling expression
@@ -408,8 +416,8 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
 }
 
 // debugging / tuning switches (environment): MCTSB200_PATH_SMEM=0 keeps the tile kernel's path stacks in HBM,
-// MCTSB200_FAST=0 disables the shared-memory lane-per-tree UCT kernel, MCTSB200_LANE_ORDER=0/1 switches the grouping
-// of trees with equal root states into the same warps (default: on for the lane-per-tree kernel, off for the tile kernel)
+// MCTSB200_FAST=0 disables the shared-memory lane-per-tree kernels, MCTSB200_LANE_ORDER=0/1 switches the grouping of trees
+// with equal root states into the same warps (default: on exactly when equal roots give identical trees, see lockstep())
 bool env_enabled(const char* name, bool dflt = true) {
     const char* v = std::getenv(name);
     if (!v || !v[0]) return dflt;
@@ -464,14 +472,16 @@ constexpr size_t kFastSmemLimit = 220 * 1024;
 // dense-state MDP whose tables fit in shared memory. Returns the policy variant or -1.
 template <class M, int KIND>
 int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg) {
-    if constexpr (!M::kFast || KIND != MCTSB200_KIND_UCT) {
+    if constexpr (!M::kFast) {
         return -1;
     } else {
         if (!env_enabled("MCTSB200_FAST") || !MdpAccess<M>::fast_ready(ctx)) return -1;
         if (cfg->estimate_kind != MCTSB200_EST_ROLLOUT || cfg->rollouts_per_leaf != 1 || cfg->lanes_per_tree > 1) return -1;
         if (cfg->init_q_table || cfg->init_n_table) return -1;
         if (cfg->exploration_constant == 0.0) return -1;  // argmax-Q selection: the tile kernel has that path
-        if (cfg->depth > 254 || cfg->n_iterations >= (1LL << 24) - 1) return -1;  // (iteration, level) tags of the children
+        // (iteration, level) tags of the children: 24 bits of iteration for UCT, 16 for DPW
+        if (cfg->depth > 254 || cfg->n_iterations >= (KIND == MCTSB200_KIND_UCT ? (1LL << 24) - 1 : (1LL << 16) - 1)) return -1;
+        if (KIND == MCTSB200_KIND_DPW && !(cfg->check_repeat_state && cfg->check_repeat_action)) return -1;  // unmerged nodes: tile kernel
         // the kernel indexes the UCB tables without a range check: every visit count must be inside them
         const long long bound = 4LL * std::max<long long>(cfg->init_N, 0) + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1;
         if (bound + 1 > (1LL << 20)) return -1;
@@ -534,7 +544,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.n_slots = n_trees;
     int fast_block = 0;  // block size the lane order was dealt for
     if constexpr (M::kDense) {
-        if (root_stride == 1 && n_trees > 32 && n_trees < (1LL << 30) && env_enabled("MCTSB200_LANE_ORDER", fast >= 0)) {
+        if (root_stride == 1 && n_trees > 32 && n_trees < (1LL << 30) && env_enabled("MCTSB200_LANE_ORDER", fast >= 0 && MdpAccess<M>::lockstep(ctx, cfg))) {
             const int n_bins = MdpAccess<M>::dense_count(ctx);
             const int tpw = 32 / G;  // tiles per warp
             // upper bound of the padded slot count (the exact one is only known on the device): every non-empty
@@ -579,15 +589,22 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         CUDA_TRY(st.rows_fast.ensure(bytes));
         CUDA_TRY(cudaMemsetAsync(st.rows_fast.p, 0, bytes, ctx->stream));
         args.rows_fast = st.rows_fast.p;
+        if (KIND == MCTSB200_KIND_DPW) {
+            CUDA_TRY(st.trans_fast.ensure(2 * bytes));
+            CUDA_TRY(cudaMemsetAsync(st.trans_fast.p, 0, 2 * bytes, ctx->stream));
+            args.trans_fast = st.trans_fast.p;
+        }
     }
     // one search launch over iterations [args.iter_begin, args.iter_end)
     auto launch = [&]() -> int32_t {
-        if constexpr (M::kFast && KIND == MCTSB200_KIND_UCT) {
+        if constexpr (M::kFast) {
             if (fast >= 0) {
                 const long long per_sm = (args.n_slots + ctx->sm_count - 1) / ctx->sm_count;
                 const int block = fast_block ? fast_block : fast_block_threads<M>(ctx, per_sm, args.geo.depth);
                 const int grid = (int)((args.n_slots + block - 1) / block);
-                return launch_uct_fast<M>(args, fast, grid, block, fast_smem_bytes<M>(args.mdp, args.geo.depth, block), ctx->stream);
+                const size_t smem = fast_smem_bytes<M>(args.mdp, args.geo.depth, block);
+                if (KIND == MCTSB200_KIND_UCT) return launch_uct_fast<M>(args, fast, grid, block, smem, ctx->stream);
+                return launch_dpw_fast<M>(args, fast, grid, block, smem, ctx->stream);
             }
         }
         launch_search<M, KIND>(args, G, ctx->stream);
@@ -632,9 +649,16 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     if constexpr (M::kFast) if (fast >= 0) {
         const long long slots32 = (args.n_slots + 31) / 32 * 32;
         const long long n_rows = slots32 * st.geo.NS;
-        auto kernel = finalize_rows_kernel<M>;
-        MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (const FastRow*)st.rows_fast.p, args.order,
-                        (const uint16_t*)st.map.p, (Row<M>*)st.rows.p, st.geo.NS, args.n_slots);
+        if (KIND == MCTSB200_KIND_UCT) {
+            auto kernel = finalize_rows_kernel<M>;
+            MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (const FastRow*)st.rows_fast.p, args.order,
+                            (const uint16_t*)st.map.p, (Row<M>*)st.rows.p, st.geo.NS, args.n_slots);
+        } else {
+            auto kernel = dpw_finalize_kernel<M>;
+            MCTSB200_LAUNCH(kernel, (unsigned)((args.n_slots + 127) / 128), 128, 0, ctx->stream, (const FastRow*)st.rows_fast.p,
+                            (const DpwTransRow*)st.trans_fast.p, args.order, (const uint16_t*)st.map.p, args.mdp, (TreeHeader*)st.hdr.p,
+                            (Row<M>*)st.rows.p, (Aux<M>*)st.aux.p, (TransRec*)st.trans.p, st.geo.NS, st.geo.NT, args.n_slots);
+        }
         CUDA_TRY(cudaGetLastError());
         ++launches;
     }
@@ -787,17 +811,20 @@ int32_t fetch_tree(mctsb200_ctx* ctx, long long i, HostTree<M>& t) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemcpy(&t.h, (const TreeHeader*)st.hdr.p + i, sizeof(TreeHeader), cudaMemcpyDeviceToHost));
     t.rows.resize((size_t)t.h.n_state);
+    std::vector<int> cell_of;  // direct layout: dense state index of node id (insertion order)
     if (st.direct) {
         // rows are stored by dense state index; bring them into insertion order and restore the key
         if constexpr (M::kDense) {
             std::vector<Row<M>> all((size_t)st.geo.NS);
             CUDA_TRY(cudaMemcpy(all.data(), (const Row<M>*)st.rows.p + i * st.geo.NS, sizeof(Row<M>) * all.size(), cudaMemcpyDeviceToHost));
+            cell_of.assign(t.rows.size(), -1);
             for (size_t cell = 0; cell < all.size(); ++cell) {
-                if (all[cell].packed == 0) continue;
                 const size_t seq = (size_t)all[cell].key;
-                if (seq == 0 || seq > t.rows.size()) return fail(MCTSB200_ERR_STATE, "corrupt direct-indexed node table");
+                if (seq == 0) continue;  // the state is not in the tree
+                if (seq > t.rows.size()) return fail(MCTSB200_ERR_STATE, "corrupt direct-indexed node table");
                 t.rows[seq - 1] = all[cell];
                 t.rows[seq - 1].key = (typename M::Key)cell;
+                cell_of[seq - 1] = (int)cell;
             }
         }
     } else if (t.h.n_state)
@@ -805,7 +832,13 @@ int32_t fetch_tree(mctsb200_ctx* ctx, long long i, HostTree<M>& t) {
     if (st.kind == MCTSB200_KIND_DPW) {
         t.aux.resize((size_t)t.h.n_state);
         t.trans.resize((size_t)t.h.n_trans);
-        if (t.h.n_state) CUDA_TRY(cudaMemcpy(t.aux.data(), (const Aux<M>*)st.aux.p + i * st.geo.NS, sizeof(Aux<M>) * (size_t)t.h.n_state, cudaMemcpyDeviceToHost));
+        if (st.direct) {
+            std::vector<Aux<M>> all((size_t)st.geo.NS);
+            CUDA_TRY(cudaMemcpy(all.data(), (const Aux<M>*)st.aux.p + i * st.geo.NS, sizeof(Aux<M>) * all.size(), cudaMemcpyDeviceToHost));
+            for (size_t nid = 0; nid < t.aux.size(); ++nid)
+                if (cell_of[nid] >= 0) t.aux[nid] = all[(size_t)cell_of[nid]];
+        } else if (t.h.n_state)
+            CUDA_TRY(cudaMemcpy(t.aux.data(), (const Aux<M>*)st.aux.p + i * st.geo.NS, sizeof(Aux<M>) * (size_t)t.h.n_state, cudaMemcpyDeviceToHost));
         if (t.h.n_trans) CUDA_TRY(cudaMemcpy(t.trans.data(), (const TransRec*)st.trans.p + i * st.geo.NT, sizeof(TransRec) * (size_t)t.h.n_trans, cudaMemcpyDeviceToHost));
     }
     return MCTSB200_OK;
@@ -973,7 +1006,7 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     if (!c) return MCTSB200_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->counters,
+    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->counters,
                       &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
                       &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->gw_fast};
     for (DevBuf* b : bufs) b->release();

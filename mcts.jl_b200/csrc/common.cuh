@@ -199,7 +199,8 @@ struct KernelArgs {
     Geometry geo;
     TreeHeader* hdr;
     Row<M>* rows;
-    void* rows_fast;                    // uct_fast.cuh: FastRow table, [warp][state][lane]
+    void* rows_fast;                    // uct_fast.cuh / dpw_fast.cuh: FastRow table, [warp][state][lane]
+    void* trans_fast;                   // dpw_fast.cuh: DpwTransRow table, [warp][state][lane]
     Aux<M>* aux;
     TransRec* trans;
     void* map;

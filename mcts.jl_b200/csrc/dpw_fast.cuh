@@ -1,0 +1,497 @@
+// dpw_fast.cuh -- the lean double-progressive-widening kernel for small dense-state MDPs (SimpleGridWorld up to 127
+// cells), the DPW counterpart of uct_fast.cuh: one lane per tree, model tables in shared memory, direct-indexed
+// interleaved rows, load-free backup. Same algorithm, arithmetic and results as search_kernel<M, DPW, 1>
+// (search.cuh); it applies when states and actions are merged (check_repeat_state, check_repeat_action: the
+// reference's defaults), one rollout per leaf, c > 0.
+//
+// Reference lines restated: simulate src/dpw.jl:80-154 (action widening :94-114, state widening :119-141),
+// best_sanode_UCB :179-199, insert_state_node!/insert_action_node! src/dpw_types.jl:162-186,
+// RandomActionGenerator src/action_gen.jl:11-13, estimate_value src/domain_knowledge.jl:65-73.
+//
+// Node table (per tree, indexed by the state's dense index, [warp][state][lane] interleaved):
+//   row  (64 B)   4 child slots in insertion order x {q f64, n i32, tag u32};
+//                 tag = stamp16 << 16 | level << 8 | meta, meta = present | action label << 1 | seen << 3, where `seen` is
+//                 the 4-bit set of model outcomes (M::fast_gen's outcome index) this action node has produced, so
+//                 n_a_children = popcount(seen); bit 7 of slot 0's meta = "this state node exists" (a DPW state node
+//                 starts without children); (stamp16, level) = iteration and path level of the last descent that took
+//                 this child (0xff = none)
+//   trow (128 B)  per slot: pushes (length of the reference's transitions[sanode]), the multiplicity of each outcome,
+//                 the outcomes in first-occurrence order (2 bits each) and the action node's insertion sequence number
+//                 (sampling the multiset is distribution-identical to rand(rng, transitions[sanode])).
+//                 While an action node keeps widening -- always, for GridWorld with the reference's bench and default
+//                 parameters -- the descent never reads this table: it only issues fire-and-forget reductions on it.
+// total_n(snode) is the sum of its children's n (insert_action_node! adds init_N to both, every backup adds one to
+// both) and is never stored. After the last launch dpw_finalize_kernel writes the Row / Aux / TransRec tables that
+// the decision, query and export code reads.
+#pragma once
+#include "uct_fast.cuh"
+
+namespace mctsb200 {
+
+struct __align__(32) DpwSlotTrans {
+    uint32_t tpush;   // pushes
+    uint32_t cnt[4];  // multiplicity per outcome index
+    uint32_t order;   // outcome indices in first-occurrence order, 2 bits each
+    uint32_t aseq;    // 1-based insertion sequence number of the action node
+    uint32_t pad;
+};
+struct __align__(32) DpwTransRow {
+    DpwSlotTrans t[4];
+};
+static_assert(sizeof(DpwSlotTrans) == 32 && sizeof(DpwTransRow) == 128, "one slot = one sector");
+
+// the reference's exact DPW scores over the first nchild slots, out of line (rare)
+template <class M>
+__device__ __noinline__ int dpw_exact_scores_cold(const DevCfg* cfg, typename Search<M, 1>::Kids k, int nchild, int N) {
+    return Search<M, 1>::exact_scores(Tile<1>(), *cfg, k, nchild, N, true);
+}
+
+constexpr uint32_t kDpwPresent = 1u, kDpwNode = 0x80u;
+__device__ __forceinline__ int dpw_label(uint32_t tag) { return (int)((tag >> 1) & 3u); }
+__device__ __forceinline__ uint32_t dpw_seen(uint32_t tag) { return (tag >> 3) & 15u; }
+__device__ __forceinline__ int dpw_nac(uint32_t tag) { return __popc(dpw_seen(tag)); }
+
+template <class M, int POLICY>
+__global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __grid_constant__ KernelArgs<M> args) {
+    constexpr int A = M::kActions;
+    static_assert(A == 4, "a row holds exactly four child slots");
+    using SG = Search<M, 1>;
+#ifdef MCTSB200_HOST_EMU
+    static unsigned char fast_smem[256 * 1024];
+#else
+    extern __shared__ __align__(16) unsigned char fast_smem[];
+#endif
+    __shared__ unsigned long long s_cnt[CNT_COUNT];
+    const int BD = (int)blockDim.x;
+    const DevCfg& cfg = args.cfg;
+
+    // ---- stage the tables (as uct_fast_kernel) ----------------------------------------------------------
+    typename M::FastTables ft;
+    unsigned char* sm = M::fast_stage(args.mdp, fast_smem, ft);
+    double* s_rsqrt = reinterpret_cast<double*>(sm);
+    double* s_sqrtlog = s_rsqrt + kFastTab;
+    uint8_t* s_pol = reinterpret_cast<uint8_t*>(s_sqrtlog + kFastTab);
+    const int n_states = M::fast_states(args.mdp);
+    // per level: x = node | slot << 8 | (previous level of the same (node, slot) on this path, 0xff = none) << 16 | meta << 24,
+    // y = n[slot], (z, w) = q[slot] as read by the descent
+    uint4* s_path = reinterpret_cast<uint4*>(s_pol + (n_states + 15) / 16 * 16) + threadIdx.x;  // [level][lane]
+#ifdef MCTSB200_HOST_EMU
+    const int st0 = 0, st1 = 1;
+#else
+    const int st0 = (int)threadIdx.x, st1 = BD;
+    if (threadIdx.x < CNT_COUNT) s_cnt[threadIdx.x] = 0ull;
+#endif
+    for (int i = st0; i < kFastTab; i += st1) {
+        s_rsqrt[i] = i < cfg.rsqrt_tab_n ? cfg.rsqrt_tab[i] : 0.0;
+        s_sqrtlog[i] = i < cfg.log_tab_n ? cfg.sqrtlog_tab[i] : 0.0;
+    }
+    if (POLICY == FAST_POLICY_TABLE)
+        for (int i = st0; i < n_states; i += st1) s_pol[i] = cfg.policy_table[i];
+    __syncthreads();
+
+    const long long slot_id = (long long)blockIdx.x * BD + threadIdx.x;
+    const long long tree = slot_id >= args.n_slots ? -1 : args.order ? (long long)args.order[slot_id] : slot_id;
+    if (tree >= 0) {
+        const long long wbase = (slot_id >> 5) * ((long long)args.geo.NS * 32) + (slot_id & 31);
+        FastRow* const rows = reinterpret_cast<FastRow*>(args.rows_fast) + wbase;          // row of state c: rows[c * 32]
+        DpwTransRow* const trows = reinterpret_cast<DpwTransRow*>(args.trans_fast) + wbase;  // trow of state c: trows[c * 32]
+        uint16_t* const seq = reinterpret_cast<uint16_t*>(args.map) + tree * args.geo.MAP;
+        TreeHeader* const hd = args.hdr + tree;
+        TreeHeader h = *hd;
+        int n_state = h.n_state, n_action = h.n_action, root = h.root, status = h.status;
+        const uint64_t tree_index = (uint64_t)(args.tree_index_base + tree);
+        const uint64_t seed = cfg.seed;
+        const int TERM = ft.term;
+        const double gamma = M::discount(args.mdp), eps = cfg.rollout_eps, c_ucb = cfg.c;
+        const bool apw = cfg.enable_action_pw != 0, spw = cfg.enable_state_pw != 0;
+        // min n[sanode] for which an action node with 1..4 distinct successors may widen (src/dpw.jl:121); kept in registers
+        const int nmin_s1 = 1 < cfg.nmin_state_n ? __ldg(cfg.nmin_state + 1) : 0x7fffffff;
+        const int nmin_s2 = 2 < cfg.nmin_state_n ? __ldg(cfg.nmin_state + 2) : 0x7fffffff;
+        const int nmin_s3 = 3 < cfg.nmin_state_n ? __ldg(cfg.nmin_state + 3) : 0x7fffffff;
+        const int nmin_s4 = 4 < cfg.nmin_state_n ? __ldg(cfg.nmin_state + 4) : 0x7fffffff;
+        unsigned n_levels = 0, n_seen = 0, n_sins = 0, n_ains = 0, n_rollouts = 0, n_sims = 0, n_exact = 0, n_samples = 0;
+        unsigned long long n_steps = 0;
+
+        // insert_state_node! (src/dpw_types.jl:162-171): no children yet
+        auto insert_state = [&](int cell) {
+            store_child(&rows[cell * 32].c[0], 0.0, 0, kDpwNode);
+            seq[cell] = (uint16_t)(++n_state);
+            ++n_sins;
+        };
+
+        if (args.iter_begin == 0 && h.iterations == 0 && status == MCTSB200_OK) {  // src/dpw.jl:22-42
+            const typename M::State s0 = M::load(args.mdp, args.roots[tree * args.root_stride]);
+            if (M::is_terminal(args.mdp, s0)) {
+                status = MCTSB200_ERR_TERMINAL_ROOT;
+            } else {
+                root = M::dense_index(args.mdp, s0);
+                if (rows[root * 32].c[0].tag == 0) insert_state(root);
+            }
+        }
+
+        int it = args.iter_begin;
+        if (status == MCTSB200_OK) {
+            for (; it < args.iter_end; ++it) {
+                const uint32_t stamp = ((uint32_t)it + 1u) & 0xffffu;
+                // ---- descent: simulate(dpw, snode, d), one level per trip ------------------------------------
+                int cell = root, d = cfg.depth, top = 0;
+                bool leaf = false;
+                uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, wi = 0;  // stream 0: current block and the index of the next word
+                auto next_word = [&]() -> uint32_t {
+                    if ((wi & 3u) == 0u) philox_block(seed, tree_index, (uint32_t)it, 0u, wi >> 2, b0, b1, b2, b3);
+                    const uint32_t w = (wi & 2u) ? ((wi & 1u) ? b3 : b2) : ((wi & 1u) ? b1 : b0);
+                    ++wi;
+                    return w;
+                };
+                FastChild k[A];
+                load_row(rows + root * 32, k);
+                for (;;) {
+                    if (cell == TERM) break;  // isterminal: 0.0
+                    if (d == 0) {
+                        leaf = true;  // estimate_value(s, 0)
+                        break;
+                    }
+                    int nchild = (int)((k[0].tag & 1u) + (k[1].tag & 1u) + (k[2].tag & 1u) + (k[3].tag & 1u));  // slots fill in order
+                    int N = (k[0].n + k[1].n) + (k[2].n + k[3].n);  // total_n(snode); absent slots hold n = 0
+
+                    // ---- action progressive widening (src/dpw.jl:94-114) ----
+                    auto add_child = [&](int act) {
+                        const int j = nchild;
+                        const uint32_t tag = ((j == 0 ? k[0].tag : 0u) & kDpwNode) | kDpwPresent | ((uint32_t)act << 1);
+                        const double iq = cfg.init_Q;
+                        const int in = cfg.init_N;
+#pragma unroll
+                        for (int t = 0; t < A; ++t)
+                            if (t == j) {
+                                k[t].q = iq;
+                                k[t].n = in;
+                                k[t].tag = tag;
+                            }
+                        store_child(&rows[cell * 32].c[j], iq, in, tag);
+                        trows[cell * 32].t[j].aseq = (uint32_t)(++n_action);  // id of the action node (insertion order)
+                        N += in;  // tree.total_n[snode] += n0
+                        ++nchild;
+                        ++n_ains;
+                    };
+                    if (apw) {
+                        // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action[len]
+                        if (N >= cfg.nmin_action[nchild]) {
+                            const int act = (int)__umulhi(next_word(), (uint32_t)A);  // next_action(::RandomActionGenerator)
+                            bool present = false;
+#pragma unroll
+                            for (int t = 0; t < A; ++t) present |= t < nchild && dpw_label(k[t].tag) == act;
+                            if (!present) add_child(act);  // check_repeat_action
+                        }
+                    } else if (nchild == 0) {
+                        for (int act = 0; act < A; ++act) add_child(act);
+                    }
+                    ++n_levels;
+                    n_seen += (unsigned)nchild;
+
+                    // ---- best_sanode_UCB (src/dpw.jl:179-199) over the nchild present slots ----
+                    int slot;
+                    {
+                        int first_zero = SG::kNone;
+#pragma unroll
+                        for (int t = A - 1; t >= 0; --t)
+                            if (t < nchild && k[t].n == 0) first_zero = t;
+                        if (N <= 1) {
+                            // log(total_n) <= 0: unvisited children score q, and a visited one scores q + c*sqrt(0/n) = q
+                            slot = SG::kNone;
+                            double best = -CUDART_INF;
+#pragma unroll
+                            for (int t = 0; t < A; ++t)
+                                if (t < nchild && k[t].q > best) {
+                                    best = k[t].q;
+                                    slot = t;
+                                }
+                            if (slot == SG::kNone) slot = 0;
+                        } else if (first_zero != SG::kNone) {
+                            // n == 0 with log(total_n) > 0 scores +Inf and a later Inf is not > Inf: the first unvisited slot wins
+                            // unless an earlier slot is not finite -- left to the exact expression
+                            if (first_zero == 0) {
+                                slot = 0;
+                            } else {
+                                typename SG::Kids kk;
+#pragma unroll
+                                for (int t = 0; t < A; ++t) {
+                                    kk.q[t] = k[t].q;
+                                    kk.n[t] = t < nchild ? k[t].n : 1;
+                                }
+                                slot = dpw_exact_scores_cold<M>(&cfg, kk, nchild, N);
+                            }
+                        } else {
+                            double S[A], T[A], cs;
+                            if (N < kFastTab) {
+                                cs = DM_MUL(c_ucb, s_sqrtlog[N]);
+#pragma unroll
+                                for (int t = 0; t < A; ++t) T[t] = t < nchild ? DM_MUL(cs, s_rsqrt[k[t].n]) : 0.0;
+                            } else {
+                                cs = DM_MUL(c_ucb, __ldg(cfg.sqrtlog_tab + N));
+#pragma unroll
+                                for (int t = 0; t < A; ++t) T[t] = t < nchild ? DM_MUL(cs, __ldg(cfg.rsqrt_tab + k[t].n)) : 0.0;
+                            }
+                            double mag = 0.0;
+#pragma unroll
+                            for (int t = 0; t < A; ++t) {
+                                S[t] = t < nchild ? DM_ADD(k[t].q, T[t]) : -CUDART_INF;
+                                if (t < nchild) mag = DM_ADD(mag, DM_ADD(fabs(k[t].q), T[t]));
+                            }
+                            const double margin = DM_MUL(5.6843418860808015e-14, mag);
+                            const bool m01 = S[1] > S[0], m23 = S[3] > S[2];
+                            const double w01 = m01 ? S[1] : S[0], l01 = m01 ? S[0] : S[1];
+                            const double w23 = m23 ? S[3] : S[2], l23 = m23 ? S[2] : S[3];
+                            const bool mf = w23 > w01;
+                            const double best = mf ? w23 : w01;
+                            const double second = fmax(mf ? w01 : w23, mf ? l23 : l01);
+                            const int best_i = mf ? (m23 ? 3 : 2) : (m01 ? 1 : 0);
+                            if (best_i < nchild && DM_SUB(best, second) > margin) {  // (one child: second = -Inf)
+                                slot = best_i;
+                            } else {
+                                const int nb = best_i == 0 ? k[0].n : best_i == 1 ? k[1].n : best_i == 2 ? k[2].n : k[3].n;
+                                const double qb = best_i == 0 ? k[0].q : best_i == 1 ? k[1].q : best_i == 2 ? k[2].q : k[3].q;
+                                bool need_exact = !(best == best) || best_i >= nchild;
+                                int tie_i = best_i;
+#pragma unroll
+                                for (int t = A - 1; t >= 0; --t) {
+                                    if (t < nchild && t != best_i && !(DM_SUB(best, S[t]) > margin)) {
+                                        if (k[t].n == nb && k[t].q == qb) tie_i = min(tie_i, t);
+                                        else need_exact = true;
+                                    }
+                                }
+                                if (need_exact) {
+                                    ++n_exact;
+                                    typename SG::Kids kk;
+#pragma unroll
+                                    for (int t = 0; t < A; ++t) {
+                                        kk.q[t] = k[t].q;
+                                        kk.n[t] = t < nchild ? k[t].n : 1;
+                                    }
+                                    slot = dpw_exact_scores_cold<M>(&cfg, kk, nchild, N);
+                                } else {
+                                    slot = tie_i;
+                                }
+                            }
+                        }
+                    }
+                    const int ns = slot == 0 ? k[0].n : slot == 1 ? k[1].n : slot == 2 ? k[2].n : k[3].n;
+                    const double qs = slot == 0 ? k[0].q : slot == 1 ? k[1].q : slot == 2 ? k[2].q : k[3].q;
+                    const uint32_t tg = slot == 0 ? k[0].tag : slot == 1 ? k[1].tag : slot == 2 ? k[2].tag : k[3].tag;
+                    const int act = dpw_label(tg);
+                    uint32_t seen = dpw_seen(tg);
+                    const int nac = __popc(seen);
+
+                    // ---- state progressive widening (src/dpw.jl:119-141) ----
+                    DpwSlotTrans* const tp = &trows[cell * 32].t[slot];
+                    // requested now, needed only after the successor's row has been requested (or for re-sampling)
+                    uint4 t0 = *reinterpret_cast<const uint4*>(tp);           // tpush, cnt[0..2]
+                    uint2 t1 = *reinterpret_cast<const uint2*>(&tp->cnt[3]);  // cnt[3], order
+                    // (n_a_children <= k_state * n^alpha_state  <=>  n >= nmin_state[n_a_children])  ||  n_a_children == 0
+                    const int need = nac == 1 ? nmin_s1 : nac == 2 ? nmin_s2 : nac == 3 ? nmin_s3 : nmin_s4;
+                    const bool widen = nac == 0 || (spw && ns >= need);
+                    int sp, j = 0;
+                    bool new_pair = false;
+                    if (widen) {
+                        sp = M::fast_gen(ft, cell, act, next_word(), j);
+                        new_pair = !((seen >> j) & 1u);  // a new (sanode, spnode) pair: n_a_children += 1
+                        seen |= 1u << j;
+                    } else {
+                        // rand(rng, transitions[sanode]): position of the push-ordered vector = cumulative multiplicity in
+                        // first-occurrence order
+                        const int pos = (int)__umulhi(next_word(), t0.x);
+                        int cum = 0, jj = 0;
+                        bool done = false;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (!done && i < nac) {
+                                jj = (int)((t1.y >> (2 * i)) & 3u);
+                                cum += (int)(jj == 0 ? t0.y : jj == 1 ? t0.z : jj == 2 ? t0.w : t1.x);
+                                done = pos < cum;
+                            }
+                        }
+                        sp = M::fast_outcome(ft, cell, act, jj);
+                        ++n_samples;
+                    }
+                    const uint32_t meta = (tg & 0x87u) | (seen << 3);
+                    {
+                        const uint32_t link = (tg >> 16) == stamp ? ((tg >> 8) & 0xffu) : 0xffu;
+                        s_path[top * BD] = uint4{(uint32_t)cell | ((uint32_t)slot << 8) | (link << 16) | (meta << 24), (uint32_t)ns,
+                                                 (uint32_t)__double2loint(qs), (uint32_t)__double2hiint(qs)};
+                        rows[cell * 32].c[slot].tag = (stamp << 16) | ((uint32_t)top << 8) | meta;
+                    }
+                    ++top;
+                    --d;
+                    load_row(rows + sp * 32, k);
+                    if (widen) {
+                        // push!(transitions[sanode], (spnode, r)) in multiset form, in the shadow of the successor's row
+                        t0.x += 1;
+                        if (j == 0) t0.y += 1;
+                        if (j == 1) t0.z += 1;
+                        if (j == 2) t0.w += 1;
+                        *reinterpret_cast<uint4*>(tp) = t0;
+                        if (j == 3 || new_pair) {
+                            if (j == 3) t1.x += 1;
+                            if (new_pair) t1.y |= (uint32_t)j << (2 * nac);
+                            *reinterpret_cast<uint2*>(&tp->cnt[3]) = t1;
+                        }
+                    }
+                    cell = sp;
+                    if (k[0].tag == 0) {  // new state node: q = r + gamma * estimate_value(sp, d-1)
+                        insert_state(cell);
+                        leaf = true;
+                        break;
+                    }
+                }
+
+                // ---- leaf evaluation: one rollout (POMDPTools RolloutSimulator loop) --------------------------------
+                double v = 0.0;
+                if (leaf) {
+                    ++n_rollouts;
+                    const int max_steps = cfg.rollout_max_depth == -1 ? d : cfg.rollout_max_depth;
+                    constexpr int kWordsPerStep = POLICY == FAST_POLICY_RANDOM ? 2 : 1;
+                    constexpr int kStepsPerBlock = 4 / kWordsPerStep;
+                    double disc = 1.0, r_total = 0.0;
+                    int step = 1, cc = cell;
+                    uint32_t blk = 0;
+                    unsigned steps_here = 0;
+                    while (disc > eps && cc != TERM && step <= max_steps) {
+                        uint32_t w[4];
+                        philox_block(seed, tree_index, (uint32_t)it, 1u, blk++, w[0], w[1], w[2], w[3]);
+#pragma unroll
+                        for (int u = 0; u < kStepsPerBlock; ++u) {
+                            if (u > 0 && !(disc > eps && cc != TERM && step <= max_steps)) break;
+                            int ract;
+                            uint32_t wg;
+                            if (POLICY == FAST_POLICY_RANDOM) {
+                                ract = (int)__umulhi(w[2 * u], (uint32_t)A);
+                                wg = w[2 * u + 1];
+                            } else {
+                                ract = POLICY == FAST_POLICY_CONSTANT ? cfg.pparam[0] : (int)s_pol[cc];
+                                wg = w[u];
+                            }
+                            if (M::fast_has_reward(ft, cc)) r_total = DM_ADD(r_total, DM_MUL(disc, M::fast_reward(ft, cc)));
+                            cc = M::fast_gen(ft, cc, ract, wg);
+                            disc = DM_MUL(disc, gamma);
+                            ++step;
+                            ++steps_here;
+                        }
+                    }
+                    n_steps += steps_here;
+                    v = r_total;
+                }
+
+                // ---- backup (src/dpw.jl:149-151), deepest level first; no loads from the node table ----------------
+                for (int lvl = top - 1; lvl >= 0; --lvl) {
+                    const uint4 e = s_path[lvl * BD];
+                    const int node = (int)(e.x & 0xffu), slot = (int)((e.x >> 8) & 0xffu);
+                    const uint32_t link = (e.x >> 16) & 0xffu, meta = e.x >> 24;
+                    double qv = DM_MUL(gamma, v);
+                    if (M::fast_has_reward(ft, node)) qv = DM_ADD(M::fast_reward(ft, node), qv);
+                    const int nn = (int)e.y + 1;
+                    const double qo = __hiloint2double((int)e.w, (int)e.z);
+                    const double qn = DM_ADD(qo, div_by_count(DM_SUB(qv, qo), SG::i2d(nn)));
+                    store_child(&rows[node * 32].c[slot], qn, nn, (stamp << 16) | 0xff00u | meta);
+                    if (link != 0xffu) {  // the same (node, slot) higher up on this path backs up on top of this update
+                        uint4* up = s_path + link * BD;
+                        up->x = (up->x & 0x00ffffffu) | (meta << 24);
+                        up->y = (uint32_t)nn;
+                        up->z = (uint32_t)__double2loint(qn);
+                        up->w = (uint32_t)__double2hiint(qn);
+                    }
+                    v = qv;
+                }
+                ++n_sims;
+            }
+        }
+
+        h.n_state = n_state;
+        h.n_action = n_action;
+        h.root = root;
+        h.status = status;
+        h.iterations = status == MCTSB200_OK ? args.iter_end : it;
+        *hd = h;
+#ifdef MCTSB200_HOST_EMU
+        unsigned long long* dst = args.counters;
+#else
+        unsigned long long* dst = s_cnt;
+#endif
+        atomicAdd(dst + CNT_SIMULATIONS, (unsigned long long)n_sims);
+        atomicAdd(dst + CNT_LEVELS, (unsigned long long)n_levels);
+        atomicAdd(dst + CNT_CHILDREN_SEEN, (unsigned long long)n_seen);
+        atomicAdd(dst + CNT_STATE_INSERTS, (unsigned long long)n_sins);
+        atomicAdd(dst + CNT_ACTION_INSERTS, (unsigned long long)n_ains);
+        atomicAdd(dst + CNT_ROLLOUTS, (unsigned long long)n_rollouts);
+        atomicAdd(dst + CNT_ROLLOUT_STEPS, n_steps);
+        atomicAdd(dst + CNT_TRANS_SAMPLES, (unsigned long long)n_samples);
+        atomicAdd(dst + CNT_SELECT_EXACT, (unsigned long long)n_exact);
+    }
+#ifndef MCTSB200_HOST_EMU
+    __syncthreads();
+    if (threadIdx.x < CNT_COUNT && s_cnt[threadIdx.x]) atomicAdd(args.counters + threadIdx.x, s_cnt[threadIdx.x]);
+#endif
+}
+
+// After the last search launch: one thread per tree writes the Row / Aux / TransRec tables (indexed by dense state;
+// Row::key = insertion sequence number) and the transition count of the header from the kernel's interleaved tables.
+template <class M>
+__global__ void dpw_finalize_kernel(const FastRow* rows_fast, const DpwTransRow* trans_fast, const int* order, const uint16_t* seq,
+                                    const typename M::Params mdp, TreeHeader* hdr, Row<M>* rows, Aux<M>* aux, TransRec* trans, int NS, int NT,
+                                    long long n_slots) {
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const long long tree = order ? (long long)order[slot] : slot;
+    if (tree < 0) return;
+    const long long wbase = (slot >> 5) * ((long long)NS * 32) + (slot & 31);
+    const uint16_t* sq = seq + tree * NS;
+    Row<M>* orow = rows + tree * NS;
+    Aux<M>* oaux = aux + tree * NS;
+    TransRec* otr = trans + tree * NT;
+    int n_trans = 0;
+    for (int c = 0; c < NS; ++c) {
+        const FastRow fr = rows_fast[wbase + (long long)c * 32];
+        Row<M> out;
+        Aux<M> ax;
+        int tot = 0;
+        uint32_t pk = 0;
+#pragma unroll
+        for (int j = 0; j < M::kActions; ++j) {
+            const bool present = (fr.c[j].tag & kDpwPresent) != 0;
+            out.q[j] = present ? fr.c[j].q : 0.0;
+            out.n[j] = present ? fr.c[j].n : 0;
+            ax.nac[j] = 0;
+            ax.thead[j] = -1;
+            ax.tpush[j] = 0;
+            ax.seq[j] = 0;
+            if (!present) continue;
+            tot += fr.c[j].n;
+            pk = Row<M>::pack_add(pk, j, dpw_label(fr.c[j].tag));
+            const DpwSlotTrans tb = trans_fast[wbase + (long long)c * 32].t[j];
+            const int nac = dpw_nac(fr.c[j].tag);
+            ax.nac[j] = nac;
+            ax.tpush[j] = (int)tb.tpush;
+            ax.seq[j] = (int)tb.aseq;
+            for (int i = 0; i < nac && n_trans < NT; ++i) {  // records oldest first; the list head is the newest
+                const int oj = (int)((tb.order >> (2 * i)) & 3u);
+                TransRec t;
+                t.r = mdp.cells[c].reward;
+                t.sp = (int)sq[M::fast_outcome_global(mdp, c, dpw_label(fr.c[j].tag), oj)] - 1;
+                t.next = ax.thead[j];
+                t.count = (int)tb.cnt[oj];
+                t.pad[0] = t.pad[1] = t.pad[2] = 0;
+                otr[n_trans] = t;
+                ax.thead[j] = n_trans++;
+            }
+        }
+        out.total_n = tot;
+        out.packed = pk;
+        out.key = (typename M::Key)sq[c];
+        orow[c] = out;
+        oaux[c] = ax;
+    }
+    hdr[tree].n_trans = n_trans;
+}
+
+template <class M>
+int32_t launch_dpw_fast(const KernelArgs<M>& args, int policy, int grid, int block, size_t smem, cudaStream_t stream);
+
+}  // namespace mctsb200

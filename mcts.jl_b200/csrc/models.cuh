@@ -116,6 +116,20 @@ struct GridWorldDev {
         const int j = (int)(w > e.x) + (int)(w > e.y) + (int)(w > e.z);
         return cell + (int)(signed char)(e.w >> (8 * j));
     }
+    // Same, also returning the outcome index j < 4. Distinct outcome indices of one (state, action) are distinct
+    // successors (the plateaus of the sampling table are [stay, up, down, left, right] in that order, each at most once),
+    // so an action node's set of seen successors is a 4-bit mask (dpw_fast.cuh).
+    __device__ __forceinline__ static int fast_gen(const FastTables& ft, int cell, int a, uint32_t w, int& j) {
+        const uint4 e = *reinterpret_cast<const uint4*>(ft.tt + (cell * 4 + a));
+        j = (int)(w > e.x) + (int)(w > e.y) + (int)(w > e.z);
+        return cell + (int)(signed char)(e.w >> (8 * j));
+    }
+    __device__ __forceinline__ static int fast_outcome(const FastTables& ft, int cell, int a, int j) {
+        return cell + (int)(signed char)(ft.tt[cell * 4 + a].d >> (8 * j));
+    }
+    __host__ __device__ __forceinline__ static int fast_outcome_global(const Params& p, int cell, int a, int j) {
+        return cell + (int)(signed char)(p.fast_tt[cell * 4 + a].d >> (8 * j));
+    }
 
     __device__ __forceinline__ static State load(const Params& p, const AbiState& a) {
         return State{(a.x < 0 || a.y < 0) ? p.ncells : (int)(a.x - 1) + (int)(a.y - 1) * p.nx};

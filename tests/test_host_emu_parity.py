@@ -85,7 +85,22 @@ def test_emu_uct_options(emu_ctx, oracle, opts):
 
 def test_emu_dpw_gridworld(emu_ctx, oracle):
     s = m.DPWSolver(n_iterations=300, depth=20, exploration_constant=10.0, k_state=4.0, alpha_state=1 / 8, k_action=4.0, alpha_action=1 / 8, rng=3)
-    run_both(emu_ctx, oracle, s, GW, gridworld_roots(50), compare_trees=range(0, 50, 4))
+    _, _, _, st = run_both(emu_ctx, oracle, s, GW, gridworld_roots(50), compare_trees=range(0, 50, 4))
+    assert st.kernel_variant == 1  # the shared-memory lane-per-tree DPW kernel
+    # deterministic model: every action node has one successor, self-loops at the walls repeat (node, slot) pairs on a path
+    s = m.DPWSolver(n_iterations=300, depth=20, exploration_constant=5.0, rng=3, estimate_value=m.RolloutEstimator(m.SeekTarget((9, 3))))
+    run_both(emu_ctx, oracle, s, GW_DET, gridworld_roots(50), compare_trees=range(0, 50, 4))
+    # widening that actually stops: few successors allowed, so transitions are re-sampled from the stored multiset
+    s = m.DPWSolver(n_iterations=400, depth=12, exploration_constant=3.0, k_state=1.0, alpha_state=0.2, k_action=1.5, alpha_action=0.3, rng=5)
+    _, _, _, st = run_both(emu_ctx, oracle, s, GW, gridworld_roots(30), compare_trees=range(0, 30, 3))
+    assert st.kernel_variant == 1 and st.n_transition_samples > 0
+
+
+def test_emu_generic_dpw_kernel_still_matches(emu_ctx, oracle, monkeypatch):
+    monkeypatch.setenv("MCTSB200_FAST", "0")
+    s = m.DPWSolver(n_iterations=200, depth=15, exploration_constant=10.0, k_state=4.0, alpha_state=1 / 8, k_action=4.0, alpha_action=1 / 8, rng=3)
+    _, _, _, st = run_both(emu_ctx, oracle, s, GW, gridworld_roots(30), compare_trees=range(0, 30, 4))
+    assert st.kernel_variant == 0
 
 
 @pytest.mark.parametrize("opts", [
