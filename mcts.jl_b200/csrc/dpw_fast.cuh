@@ -207,19 +207,12 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                                 }
                             if (slot == SG::kNone) slot = 0;
                         } else if (first_zero != SG::kNone) {
-                            // n == 0 with log(total_n) > 0 scores +Inf and a later Inf is not > Inf: the first unvisited slot wins
-                            // unless an earlier slot is not finite -- left to the exact expression
-                            if (first_zero == 0) {
-                                slot = 0;
-                            } else {
-                                typename SG::Kids kk;
+                            // n == 0 with log(total_n) > 0 scores +Inf, and a later Inf is not > Inf: the first unvisited slot
+                            // wins unless an earlier (visited, hence finite exploration term) slot already scores +Inf
+                            slot = first_zero;
 #pragma unroll
-                                for (int t = 0; t < A; ++t) {
-                                    kk.q[t] = k[t].q;
-                                    kk.n[t] = t < nchild ? k[t].n : 1;
-                                }
-                                slot = dpw_exact_scores_cold<M>(&cfg, kk, nchild, N);
-                            }
+                            for (int t = A - 2; t >= 0; --t)
+                                if (t < first_zero && k[t].q == CUDART_INF) slot = t;
                         } else {
                             double S[A], T[A], cs;
                             if (N < kFastTab) {

@@ -104,3 +104,54 @@ def test_auto_lanes_and_terminal_roots(gpu_ctx, oracle):
     assert stats.lanes_per_tree in (1, 2, 4, 8, 16, 32)
     a, q, st, stats = run_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=50, depth=10, rng=2), GW, roots)
     assert st[-1] == m.abi.ERR_TERMINAL_ROOT and (st[:-1] == 0).all()
+
+
+def test_full_size_config2_properties_and_sampled_oracle(gpu_ctx, oracle):
+    """BASELINE config 2 at full size (65,536 roots x 1,000 iterations, deterministic variant): size-independent
+    properties of the whole batch plus bit-exact trees for a sample of roots against the oracle."""
+    roots = gridworld_roots(65536)
+    solver = m.MCTSSolver(n_iterations=1000, depth=20, exploration_constant=5.0, rng=0,
+                          estimate_value=m.RolloutEstimator(m.ConstantPolicy("up"), max_depth=50))
+    cfg, keep = m.build_cfg(solver, GW_DET)
+    gpu_ctx.configure(GW_DET.mdp_id, GW_DET.params())
+    enc = GW_DET.encode_states(roots)
+    a, q, st, stats = gpu_ctx.plan(cfg, GW_DET.mdp_id, enc, want_status=True)
+    assert stats.kernel_variant == 1 and stats.n_simulations == 65536 * 1000 and (st == 0).all()
+    # deterministic model + deterministic rollout policy: the 655 trees that share a root cell are identical
+    cell = np.arange(65536) % 100
+    for c in range(100):
+        idx = np.nonzero(cell == c)[0]
+        assert (a[idx] == a[idx[0]]).all() and (q[idx].view(np.int64) == q[idx[0]].view(np.int64)).all()
+    # every simulation backs up through the root at least once unless the root is terminal-adjacent: visit counts add up
+    for i in (0, 1234, 65535):
+        rs = gpu_ctx.root_stats(i)
+        assert int(rs["n"].sum()) == rs["total_n"] >= 1000
+    # sampled trees against the oracle, bit for bit (same global root indices)
+    sample = [0, 1, 37, 99, 100, 4242, 65535]
+    oracle.configure(GW_DET.mdp_id, GW_DET.params())
+    for i in sample:
+        a2, q2, _, _ = oracle.plan(cfg, GW_DET.mdp_id, enc[i:i + 1], i)
+        assert a2[0] == a[i] and q2.view(np.int64)[0] == q.view(np.int64)[i]
+        t1 = gpu_ctx.tree_export(i, GW_DET.state_dtype, GW_DET.state_width)
+        t2 = oracle.tree_export(0, GW_DET.state_dtype, GW_DET.state_width)
+        from helpers import assert_trees_equal
+        assert_trees_equal(t1, t2, f"tree {i}")
+    del keep
+
+
+def test_full_size_config3_dpw_sampled_oracle(gpu_ctx, oracle):
+    """BASELINE config 3 at full size (16,384 roots, bench/non-terminal_gw_dpw.jl solver): counters and sampled trees."""
+    roots = gridworld_roots(16384)
+    solver = m.DPWSolver(n_iterations=1000, depth=20, exploration_constant=10.0, k_state=4.0, alpha_state=1 / 8, k_action=4.0, alpha_action=1 / 8, rng=0)
+    cfg, keep = m.build_cfg(solver, GW)
+    gpu_ctx.configure(GW.mdp_id, GW.params())
+    enc = GW.encode_states(roots)
+    a, q, st, stats = gpu_ctx.plan(cfg, GW.mdp_id, enc, want_status=True)
+    assert stats.kernel_variant == 1 and stats.n_simulations == 16384 * 1000 and (st == 0).all()
+    oracle.configure(GW.mdp_id, GW.params())
+    from helpers import assert_trees_equal
+    for i in (0, 55, 9999, 16383):
+        a2, q2, _, _ = oracle.plan(cfg, GW.mdp_id, enc[i:i + 1], i)
+        assert a2[0] == a[i] and q2.view(np.int64)[0] == q.view(np.int64)[i]
+        assert_trees_equal(gpu_ctx.tree_export(i, GW.state_dtype, GW.state_width), oracle.tree_export(0, GW.state_dtype, GW.state_width), f"tree {i}")
+    del keep
