@@ -21,8 +21,9 @@ if world > 1:
 ctx = m.Context(local)
 gw = m.SimpleGridWorld()
 total_sims = int(float(os.environ.get("TOTAL_SIMS", "1e7")))
-trees_per_gpu = 148 * 8  # T = 1 184 trees per GPU
-n_trees = trees_per_gpu * world
+# a FIXED ensemble (8 GPUs x 1 184 trees, ~1 056 iterations each), sharded by global tree index: the merged
+# sums do not depend on the number of GPUs
+n_trees = int(os.environ.get("TREES", str(8 * 148 * 8)))
 n_iter = max(1, total_sims // n_trees)
 solver = m.MCTSSolver(n_iterations=n_iter, depth=20, exploration_constant=5.0, rng=5)
 for rep in range(3):
