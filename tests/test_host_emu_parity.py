@@ -137,3 +137,52 @@ def test_emu_terminal_dpw_root_reports_status(emu_ctx, oracle):
     roots = gridworld_roots(10) + [(-1, -1)]
     a, q, st, stats = run_both(emu_ctx, oracle, m.DPWSolver(n_iterations=50, depth=10, rng=2), GW, roots)
     assert st[-1] == m.abi.ERR_TERMINAL_ROOT and (st[:-1] == 0).all()
+
+
+# ---- edge cases of the lane-per-tree kernels (their own code paths: tables, tags, forwarding, ordering) ----------------
+@pytest.mark.parametrize("kind", ["uct", "dpw"])
+@pytest.mark.parametrize("case", [
+    dict(mdp=dict(size=(11, 11), rewards={(6, 6): 2.0, (1, 11): -1.0}), roots=[(1, 1), (11, 11), (6, 5), (6, 6), (3, 9)]),  # 121 cells: largest fast grid
+    dict(mdp=dict(size=(1, 7), rewards={(1, 7): 1.0}), roots=[(1, 1), (1, 4), (1, 7)]),                                       # corridor: most moves fold into "stay"
+    dict(mdp=dict(size=(3, 2), rewards={(3, 2): -0.0, (1, 1): 4.0}, tprob=0.4), roots=[(2, 1), (3, 2), (1, 2)]),            # a reward of -0.0
+    dict(mdp=dict(tprob=0.0), roots=[(1, 1), (5, 5), (10, 10)]),                                                               # the intended move never happens
+    dict(mdp=dict(tprob=1.0, discount=1.0), roots=[(1, 1), (9, 2), (4, 4)]),
+    dict(mdp=dict(rewards={(5, 5): 1.0}, terminate_from=[(2, 2)]), roots=[(5, 5), (2, 2), (5, 4)]),                           # reward cell that does not terminate
+])
+def test_emu_fast_kernels_edge_models(emu_ctx, oracle, kind, case):
+    mdp = m.SimpleGridWorld(**case["mdp"])
+    S = m.MCTSSolver if kind == "uct" else m.DPWSolver
+    for kw in (dict(), dict(init_N=2, init_Q=0.5), dict(estimate_value=m.RolloutEstimator(m.RandomSolver(), max_depth=-1, eps=0.3)),
+               dict(estimate_value=m.RolloutEstimator(m.ConstantPolicy("left"), max_depth=7))):
+        s = S(n_iterations=120, depth=9, exploration_constant=2.5, rng=13, **kw)
+        _, _, _, st = run_both(emu_ctx, oracle, s, mdp, case["roots"] * 3)
+        assert st.kernel_variant == 1
+
+
+@pytest.mark.parametrize("n_roots", [1, 31, 33, 97])
+def test_emu_fast_kernels_ragged_batches_and_lane_order(emu_ctx, oracle, monkeypatch, n_roots):
+    roots = gridworld_roots(n_roots)
+    for order in ("0", "1"):
+        monkeypatch.setenv("MCTSB200_LANE_ORDER", order)
+        for s in (m.MCTSSolver(n_iterations=60, depth=10, exploration_constant=5.0, rng=2),
+                  m.MCTSSolver(n_iterations=60, depth=10, exploration_constant=5.0, estimate_value=m.RolloutEstimator(m.ConstantPolicy("up"))),
+                  m.DPWSolver(n_iterations=60, depth=10, exploration_constant=5.0, rng=2)):
+            mdp = GW_DET if isinstance(s.estimate_value.solver, m.ConstantPolicy) else GW
+            _, _, _, st = run_both(emu_ctx, oracle, s, mdp, roots, base=7)
+            assert st.kernel_variant == 1
+
+
+def test_emu_grid_above_127_cells_uses_tile_kernel(emu_ctx, oracle):
+    mdp = m.SimpleGridWorld(size=(12, 12), rewards={(6, 6): 1.0})
+    _, _, _, st = run_both(emu_ctx, oracle, m.MCTSSolver(n_iterations=100, depth=10, exploration_constant=3.0, rng=1), mdp, [(1, 1), (12, 12)])
+    assert st.kernel_variant == 0
+    _, _, _, st = run_both(emu_ctx, oracle, m.DPWSolver(n_iterations=100, depth=10, rng=1), mdp, [(1, 1), (12, 12)])
+    assert st.kernel_variant == 0
+
+
+def test_emu_max_time_chunks_give_the_same_trees(emu_ctx, oracle):
+    """max_time runs the search in several launches; with a generous budget all iterations run and nothing may differ."""
+    for s in (m.MCTSSolver(n_iterations=90, depth=10, exploration_constant=5.0, rng=4, max_time=1e6),
+              m.DPWSolver(n_iterations=90, depth=10, rng=4, max_time=1e6)):
+        _, _, _, st = run_both(emu_ctx, oracle, s, GW, gridworld_roots(20))
+        assert st.iterations_done == 90 and st.n_kernel_launches > 2
