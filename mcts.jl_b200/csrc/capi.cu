@@ -319,6 +319,11 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     d.init_Q = cfg->init_Q;
     d.estimate_const = cfg->estimate_const;
     d.rollout_eps = cfg->rollout_eps;
+    {
+        const double g = MdpAccess<M>::params(ctx).discount;  // (M::discount is a device function)
+        const int steps = std::max(cfg->rollout_max_depth, cfg->depth) + 1;
+        d.disc_always_positive = (cfg->rollout_eps == 0.0 && g > 0.0 && g <= 1.0 && std::pow(g, (double)steps) > 1e-300) ? 1 : 0;
+    }
     d.seed = cfg->seed;
     d.depth = cfg->depth;
     d.K = cfg->rollouts_per_leaf;

@@ -95,6 +95,11 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
         const long long wbase = (slot_id >> 5) * ((long long)args.geo.NS * 32) + (slot_id & 31);
         FastRow* const rows = reinterpret_cast<FastRow*>(args.rows_fast) + wbase;          // row of state c: rows[c * 32]
         DpwTransRow* const trows = reinterpret_cast<DpwTransRow*>(args.trans_fast) + wbase;  // trow of state c: trows[c * 32]
+        // (one 32 x 32-bit multiply-add per row address instead of 64-bit index arithmetic)
+        auto row_at = [&](int c) -> FastRow* { return reinterpret_cast<FastRow*>(reinterpret_cast<char*>(rows) + (uint32_t)c * (32u * (uint32_t)sizeof(FastRow))); };
+        auto trow_at = [&](int c) -> DpwTransRow* {
+            return reinterpret_cast<DpwTransRow*>(reinterpret_cast<char*>(trows) + (uint32_t)c * (32u * (uint32_t)sizeof(DpwTransRow)));
+        };
         uint16_t* const seq = reinterpret_cast<uint16_t*>(args.map) + tree * args.geo.MAP;
         TreeHeader* const hd = args.hdr + tree;
         TreeHeader h = *hd;
@@ -114,7 +119,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
 
         // insert_state_node! (src/dpw_types.jl:162-171): no children yet
         auto insert_state = [&](int cell) {
-            store_child(&rows[cell * 32].c[0], 0.0, 0, kDpwNode);
+            store_child(&row_at(cell)->c[0], 0.0, 0, kDpwNode);
             seq[cell] = (uint16_t)(++n_state);
             ++n_sins;
         };
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                 status = MCTSB200_ERR_TERMINAL_ROOT;
             } else {
                 root = M::dense_index(args.mdp, s0);
-                if (rows[root * 32].c[0].tag == 0) insert_state(root);
+                if (row_at(root)->c[0].tag == 0) insert_state(root);
             }
         }
 
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                     return w;
                 };
                 FastChild k[A];
-                load_row(rows + root * 32, k);
+                load_row(row_at(root), k);
                 for (;;) {
                     if (cell == TERM) break;  // isterminal: 0.0
                     if (d == 0) {
@@ -167,8 +172,8 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                                 k[t].n = in;
                                 k[t].tag = tag;
                             }
-                        store_child(&rows[cell * 32].c[j], iq, in, tag);
-                        trows[cell * 32].t[j].aseq = (uint32_t)(++n_action);  // id of the action node (insertion order)
+                        store_child(&row_at(cell)->c[j], iq, in, tag);
+                        trow_at(cell)->t[j].aseq = (uint32_t)(++n_action);  // id of the action node (insertion order)
                         N += in;  // tree.total_n[snode] += n0
                         ++nchild;
                         ++n_ains;
@@ -236,9 +241,9 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                             const double w23 = m23 ? S[3] : S[2], l23 = m23 ? S[2] : S[3];
                             const bool mf = w23 > w01;
                             const double best = mf ? w23 : w01;
-                            const double second = fmax(mf ? w01 : w23, mf ? l23 : l01);
+                            const double o1 = mf ? w01 : w23, o2 = mf ? l23 : l01;  // the other pair's winner, the loser beside the best
                             const int best_i = mf ? (m23 ? 3 : 2) : (m01 ? 1 : 0);
-                            if (best_i < nchild && DM_SUB(best, second) > margin) {  // (one child: second = -Inf)
+                            if (best_i < nchild && DM_SUB(best, o1) > margin && DM_SUB(best, o2) > margin) {  // (absent slots: -Inf)
                                 slot = best_i;
                             } else {
                                 const int nb = best_i == 0 ? k[0].n : best_i == 1 ? k[1].n : best_i == 2 ? k[2].n : k[3].n;
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                     const int nac = __popc(seen);
 
                     // ---- state progressive widening (src/dpw.jl:119-141) ----
-                    DpwSlotTrans* const tp = &trows[cell * 32].t[slot];
+                    DpwSlotTrans* const tp = &trow_at(cell)->t[slot];
                     // requested now, needed only after the successor's row has been requested (or for re-sampling)
                     uint4 t0 = *reinterpret_cast<const uint4*>(tp);           // tpush, cnt[0..2]
                     uint2 t1 = *reinterpret_cast<const uint2*>(&tp->cnt[3]);  // cnt[3], order
@@ -310,11 +315,11 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                         const uint32_t link = (tg >> 16) == stamp ? ((tg >> 8) & 0xffu) : 0xffu;
                         s_path[top * BD] = uint4{(uint32_t)cell | ((uint32_t)slot << 8) | (link << 16) | (meta << 24), (uint32_t)ns,
                                                  (uint32_t)__double2loint(qs), (uint32_t)__double2hiint(qs)};
-                        rows[cell * 32].c[slot].tag = (stamp << 16) | ((uint32_t)top << 8) | meta;
+                        row_at(cell)->c[slot].tag = (stamp << 16) | ((uint32_t)top << 8) | meta;
                     }
                     ++top;
                     --d;
-                    load_row(rows + sp * 32, k);
+                    load_row(row_at(sp), k);
                     if (widen) {
                         // push!(transitions[sanode], (spnode, r)) in multiset form, in the shadow of the successor's row
                         t0.x += 1;
@@ -346,17 +351,18 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                     double disc = 1.0, r_total = 0.0;
                     int step = 1, cc = cell;
                     uint32_t blk = 0;
-                    unsigned steps_here = 0;
-                    while (disc > eps && cc != TERM && step <= max_steps) {
+                    // `disc > eps` of the reference's loop guard is provably always true for eps = 0 and these depths
+                    const bool dchk = !cfg.disc_always_positive;
+                    while ((!dchk || disc > eps) && cc != TERM && step <= max_steps) {
                         uint32_t w[4];
                         philox_block(seed, tree_index, (uint32_t)it, 1u, blk++, w[0], w[1], w[2], w[3]);
 #pragma unroll
                         for (int u = 0; u < kStepsPerBlock; ++u) {
-                            if (u > 0 && !(disc > eps && cc != TERM && step <= max_steps)) break;
+                            if (u > 0 && !((!dchk || disc > eps) && cc != TERM && step <= max_steps)) break;
                             int ract;
                             uint32_t wg;
                             if (POLICY == FAST_POLICY_RANDOM) {
-                                ract = (int)__umulhi(w[2 * u], (uint32_t)A);
+                                ract = (int)__umulhi(w[2 * u], (uint32_t)A);  // rand(rng, actions(mdp, s))
                                 wg = w[2 * u + 1];
                             } else {
                                 ract = POLICY == FAST_POLICY_CONSTANT ? cfg.pparam[0] : (int)s_pol[cc];
@@ -366,10 +372,9 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                             cc = M::fast_gen(ft, cc, ract, wg);
                             disc = DM_MUL(disc, gamma);
                             ++step;
-                            ++steps_here;
                         }
                     }
-                    n_steps += steps_here;
+                    n_steps += (unsigned)(step - 1);
                     v = r_total;
                 }
 
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                     const int nn = (int)e.y + 1;
                     const double qo = __hiloint2double((int)e.w, (int)e.z);
                     const double qn = DM_ADD(qo, div_by_count(DM_SUB(qv, qo), SG::i2d(nn)));
-                    store_child(&rows[node * 32].c[slot], qn, nn, (stamp << 16) | 0xff00u | meta);
+                    store_child(&row_at(node)->c[slot], qn, nn, (stamp << 16) | 0xff00u | meta);
                     if (link != 0xffu) {  // the same (node, slot) higher up on this path backs up on top of this update
                         uint4* up = s_path + link * BD;
                         up->x = (up->x & 0x00ffffffu) | (meta << 24);

@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
     if (tree >= 0) {
         // row of state c of this lane's tree: rows[c * 32]  ([warp][state][lane] interleaving)
         FastRow* const rows = reinterpret_cast<FastRow*>(args.rows_fast) + (slot_id >> 5) * ((long long)args.geo.NS * 32) + (slot_id & 31);
+        // (one 32 x 32-bit multiply-add per row address instead of 64-bit index arithmetic)
+        auto row_at = [&](int c) -> FastRow* { return reinterpret_cast<FastRow*>(reinterpret_cast<char*>(rows) + (uint32_t)c * (32u * (uint32_t)sizeof(FastRow))); };
         uint16_t* const seq = reinterpret_cast<uint16_t*>(args.map) + tree * args.geo.MAP;  // insertion sequence number per state
         TreeHeader* const hd = args.hdr + tree;
         TreeHeader h = *hd;
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 
         // insert_node! (src/vanilla.jl:292-307): all A children at once
         auto insert = [&](int cell) {
-            FastRow* rw = rows + cell * 32;
+            FastRow* rw = row_at(cell);
 #pragma unroll
             for (int k = 0; k < A; ++k) store_child(&rw->c[k], cfg.init_Q, cfg.init_N, 0xffu);
             seq[cell] = (uint16_t)(++n_state);
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 
         if (args.iter_begin == 0 && h.iterations == 0 && status == MCTSB200_OK) {  // root lookup / insertion (src/vanilla.jl:219-224)
             root = M::dense_index(args.mdp, M::load(args.mdp, args.roots[tree * args.root_stride]));
-            if (rows[root * 32].c[0].tag == 0) insert(root);
+            if (row_at(root)->c[0].tag == 0) insert(root);
         }
 
 #ifdef MCTSB200_PHASE_TIMING
@@ -183,7 +185,10 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 #define PT_CLOCK(var) const long long var = clock64()
 #define PT_ADD(i, v) cyc[i] += (v)
 #define PT_TRIP(i, v) trips[i] += (v)
+        long long lv[5] = {0, 0, 0, 0, 0};  // inside a descent level: wait for the row, select, gen, record + issue, rest
+#define PT_LV(i, v) lv[i] += (v)
 #else
+#define PT_LV(i, v)
 #define PT_CLOCK(var)
 #define PT_ADD(i, v)
 #define PT_TRIP(i, v)
@@ -198,8 +203,9 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                 bool leaf = false;
                 uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
                 FastChild k[A];
-                load_row(rows + root * 32, k);
+                load_row(row_at(root), k);
                 for (;;) {
+                    PT_CLOCK(l0);
                     if (cell == TERM) break;  // isterminal: value 0.0, no statistics update at this node
                     if (d == 0) {
                         leaf = true;  // estimate_value(s, 0)
@@ -238,9 +244,9 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                         const double w23 = m23 ? S[3] : S[2], l23 = m23 ? S[2] : S[3];
                         const bool mf = w23 > w01;
                         const double best = mf ? w23 : w01;
-                        const double second = fmax(mf ? w01 : w23, mf ? l23 : l01);
+                        const double o1 = mf ? w01 : w23, o2 = mf ? l23 : l01;  // the other pair's winner, the loser beside the best
                         const int best_i = mf ? (m23 ? 3 : 2) : (m01 ? 1 : 0);
-                        if (DM_SUB(best, second) > margin) {
+                        if (DM_SUB(best, o1) > margin && DM_SUB(best, o2) > margin) {
                             slot = best_i;
                         } else {
                             // near-tie: children inside the margin with bit-identical (n, q) have bit-identical reference
@@ -271,8 +277,13 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                         }
                     }
 
+                    PT_CLOCK(l1);
                     // sp, r = @gen(:sp,:r)(mdp, s, a, rng); the reward is re-read from the table during backup
                     const int sp = M::fast_gen(ft, cell, slot, w);
+#ifdef MCTSB200_PHASE_TIMING
+                    if (sp < 0) break;  // (never: makes the clock below wait for the successor)
+#endif
+                    PT_CLOCK(l2);
                     // what the backup needs from this level
                     const int ns = slot == 0 ? k[0].n : slot == 1 ? k[1].n : slot == 2 ? k[2].n : k[3].n;
                     const double qs = slot == 0 ? k[0].q : slot == 1 ? k[1].q : slot == 2 ? k[2].q : k[3].q;
@@ -282,12 +293,21 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                         const uint32_t link = (tg >> 8) == stamp ? (tg & 0xffu) : 0xffu;
                         s_path[top * BD] = uint4{(uint32_t)cell | ((uint32_t)slot << 16) | (link << 24), (uint32_t)ns, (uint32_t)__double2loint(qs),
                                                  (uint32_t)__double2hiint(qs)};
-                        rows[cell * 32].c[slot].tag = (stamp << 8) | (uint32_t)top;  // (before the successor's row is read: it may be this row)
+                        row_at(cell)->c[slot].tag = (stamp << 8) | (uint32_t)top;  // (before the successor's row is read: it may be this row)
                     }
                     ++top;
                     --d;
                     cell = sp;
-                    load_row(rows + sp * 32, k);
+                    load_row(row_at(sp), k);
+                    PT_CLOCK(l3);
+                    PT_LV(1, l1 - l0);
+                    PT_LV(2, l2 - l1);
+                    PT_LV(3, l3 - l2);
+#ifdef MCTSB200_PHASE_TIMING
+                    const bool fresh = k[0].tag == 0;
+                    PT_CLOCK(l4);
+                    PT_LV(0, l4 - l3);
+#endif
                     if (k[0].tag == 0) {  // new node: estimate_value(sp, depth-1), also when sp is terminal
                         insert(cell);
                         leaf = true;
@@ -307,13 +327,14 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     double disc = 1.0, r_total = 0.0;
                     int step = 1, cc = cell;
                     uint32_t blk = 0;
-                    unsigned steps_here = 0;
-                    while (disc > eps && cc != TERM && step <= max_steps) {
+                    // `disc > eps` of the reference's loop guard is provably always true for eps = 0 and these depths
+                    const bool dchk = !cfg.disc_always_positive;
+                    while ((!dchk || disc > eps) && cc != TERM && step <= max_steps) {
                         uint32_t w[4];
                         philox_block(seed, tree_index, (uint32_t)it, 1u, blk++, w[0], w[1], w[2], w[3]);
 #pragma unroll
                         for (int u = 0; u < kStepsPerBlock; ++u) {
-                            if (u > 0 && !(disc > eps && cc != TERM && step <= max_steps)) break;
+                            if (u > 0 && !((!dchk || disc > eps) && cc != TERM && step <= max_steps)) break;
                             int act;
                             uint32_t wg;
                             if (POLICY == FAST_POLICY_RANDOM) {
@@ -327,11 +348,9 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                             cc = M::fast_gen(ft, cc, act, wg);
                             disc = DM_MUL(disc, gamma);
                             ++step;
-                            ++steps_here;
                         }
                     }
-                    n_steps += steps_here;
-                    PT_TRIP(1, steps_here);
+                    n_steps += (unsigned)(step - 1);
                     v = r_total;
                 }
                 PT_CLOCK(t2);
@@ -346,7 +365,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     const int nn = (int)e.y + 1;
                     const double qo = __hiloint2double((int)e.w, (int)e.z);
                     const double qn = DM_ADD(qo, div_by_count(DM_SUB(qv, qo), SG::i2d(nn)));
-                    store_child(&rows[node * 32].c[slot], qn, nn, (stamp << 8) | 0xffu);
+                    store_child(&row_at(node)->c[slot], qn, nn, (stamp << 8) | 0xffu);
                     if (link != 0xffu) {  // the same (node, child) higher up on this path backs up on top of this update
                         uint4* up = s_path + link * BD;
                         up->y = (uint32_t)nn;
@@ -365,9 +384,11 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
         }
 #ifdef MCTSB200_PHASE_TIMING
         if ((threadIdx.x & 31) == 0 && n_sims)  // PT block warp smid | levels/iter steps/iter | cycles/iter: descent rollout backup | per level, step, level
-            printf("PT %d %d %d | %.2f %.2f | %lld %lld %lld | %.0f %.0f %.0f\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)__smid(),
-                   (double)trips[0] / n_sims, (double)trips[1] / n_sims, cyc[0] / n_sims, cyc[1] / n_sims, cyc[2] / n_sims,
-                   (double)cyc[0] / (double)max(trips[0], 1LL), (double)cyc[1] / (double)max(trips[1], 1LL), (double)cyc[2] / (double)max(trips[2], 1LL));
+            printf("PT %d %d %d | %.2f %.2f | %lld %lld %lld | %.0f %.0f %.0f | level: rowwait %.0f select %.0f gen %.0f record+issue %.0f\n", (int)blockIdx.x,
+                   (int)(threadIdx.x >> 5), (int)__smid(), (double)trips[0] / n_sims, (double)trips[1] / n_sims, cyc[0] / n_sims, cyc[1] / n_sims,
+                   cyc[2] / n_sims, (double)cyc[0] / (double)max(trips[0], 1LL), (double)cyc[1] / (double)max(trips[1], 1LL),
+                   (double)cyc[2] / (double)max(trips[2], 1LL), (double)lv[0] / (double)max(trips[0], 1LL), (double)lv[1] / (double)max(trips[0], 1LL),
+                   (double)lv[2] / (double)max(trips[0], 1LL), (double)lv[3] / (double)max(trips[0], 1LL));
 #endif
 
         h.n_state = n_state;
