@@ -101,7 +101,10 @@ typedef struct {
     /* DPW only */
     double k_action, alpha_action, k_state, alpha_state;
     int32_t enable_action_pw, enable_state_pw, check_repeat_state, check_repeat_action;
-    int32_t keep_tree;            /* DPW keep_tree / vanilla reuse_tree                            */
+    int32_t keep_tree;            /* DPW keep_tree / vanilla reuse_tree: the next plan call with the same ctx, solver kind,
+                                     MDP and number of roots continues tree i for root i (src/vanilla.jl:213-217,
+                                     src/dpw.jl:31-37) until mctsb200_clear_trees. Needs a dense-state MDP with merged
+                                     states (bounded node table), else MCTSB200_ERR_UNSUPPORTED                      */
     int32_t lanes_per_tree;       /* 0 = auto; else 1,2,4,8,16,32 lanes cooperate on one tree      */
     /* node initialisers and leaf estimator */
     double init_Q;

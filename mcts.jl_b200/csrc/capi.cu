@@ -66,6 +66,8 @@ struct DevBuf {
 struct Storage {
     bool valid = false;
     bool direct = false;  // rows indexed by the state's dense index (uct_fast.cuh); Row::key holds the insertion sequence number
+    bool keep = false;    // the trees were built with reuse_tree / keep_tree and may be continued by the next plan call
+    long long visits = 0; // upper bound of the visits any node of the kept trees has received so far
     int kind = 0, mdp_id = 0;
     long long n_trees = 0;
     Geometry geo{};
@@ -235,8 +237,10 @@ int32_t validate_cfg(const mctsb200_solver_cfg* cfg, int n_actions, bool dense, 
     return MCTSB200_OK;
 }
 
+// Sizes and (re)allocates the node tables of a plan call. With reuse_tree / keep_tree (src/vanilla.jl:213-217,
+// src/dpw.jl:31-37) and compatible tables from the previous call, the tables are kept as they are (*reused = true).
 template <class M>
-int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_trees, bool direct) {
+int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_trees, bool direct, bool* reused) {
     constexpr int A = M::kActions;
     const bool dpw = cfg->kind == MCTSB200_KIND_DPW;
     const long long n_iter = cfg->n_iterations;
@@ -244,6 +248,12 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     const bool merge_states = !dpw || cfg->check_repeat_state;
     long long NS = n_iter + 1;
     if (M::kDense && merge_states) NS = std::min<long long>(NS, dense);
+    if (cfg->keep_tree) {
+        // a kept tree grows call after call: only a dense state space with merged states bounds it
+        if (!(M::kDense && merge_states))
+            return fail(MCTSB200_ERR_UNSUPPORTED, "reuse_tree / keep_tree needs an MDP with a dense state index and merged states (bounded node table)");
+        NS = dense;
+    }
     if (direct) NS = dense;
     const bool maintain_lookup = !dpw || cfg->keep_tree || cfg->check_repeat_state;
     if (M::kDense && maintain_lookup && NS > 65535) return fail(MCTSB200_ERR_CAPACITY, "dense state map limited to 65535 nodes per tree");
@@ -251,7 +261,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     if (dpw) {
         const long long by_iter = std::max<long long>(1, n_iter * std::max(cfg->depth, 1));
         const long long by_pairs = NS * A * std::min<long long>(M::kMaxBranch, NS);
-        NT = cfg->check_repeat_state ? std::min(by_iter, by_pairs) : std::max<long long>(1, n_iter);
+        NT = cfg->check_repeat_state ? (cfg->keep_tree ? by_pairs : std::min(by_iter, by_pairs)) : std::max<long long>(1, n_iter);
     }
     long long MAP = 0;
     size_t map_entry = 0;
@@ -280,6 +290,15 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     const size_t total = b_hdr + b_rows + b_aux + b_trans + b_map + b_path;
 
     Storage& st = ctx->st;
+    *reused = false;
+    if (cfg->keep_tree && st.valid && st.keep && st.kind == cfg->kind && st.mdp_id == M::kMdpId && st.n_trees == n_trees) {
+        if (st.direct != direct || st.geo.NS != g.NS || st.geo.NT != g.NT || st.geo.MAP != g.MAP)
+            return fail(MCTSB200_ERR_STATE, "the kept trees cannot be continued with this configuration (different kernel layout); call clear_tree first");
+        CUDA_TRY(st.path.ensure(b_path));
+        st.geo.depth = g.depth;
+        *reused = true;
+        return MCTSB200_OK;
+    }
     const size_t have = st.hdr.cap + st.rows.cap + st.aux.cap + st.trans.cap + st.map.cap + st.path.cap;
     const bool grows = b_hdr > st.hdr.cap || b_rows > st.rows.cap || b_aux > st.aux.cap || b_trans > st.trans.cap || b_map > st.map.cap || b_path > st.path.cap;
     if (grows) {  // (cudaMemGetInfo is slow: only ask when something has to be allocated)
@@ -298,6 +317,8 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     CUDA_TRY(st.path.ensure(b_path));
     st.kind = cfg->kind;
     st.direct = direct;
+    st.keep = cfg->keep_tree != 0;
+    st.visits = 0;
     st.mdp_id = M::kMdpId;
     st.n_trees = n_trees;
     st.geo = g;
@@ -311,7 +332,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
 }
 
 template <class M>
-int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg& d) {
+int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg& d, long long prior_visits) {
     constexpr int A = M::kActions;
     std::memset(&d, 0, sizeof d);
     d.n_iterations = cfg->n_iterations;
@@ -374,9 +395,9 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     }
 
     // visit-count bound: every backup adds one visit; at most depth backups per simulation
-    const long long bound = std::min<long long>(2000000000LL, max_init_n * A + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1);
-    if (max_init_n * A + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1 > 2000000000LL)
-        return fail(MCTSB200_ERR_CAPACITY, "visit counts may exceed 32 bits");
+    const long long bound_raw = max_init_n * A + prior_visits + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1;
+    const long long bound = std::min<long long>(2000000000LL, bound_raw);
+    if (bound_raw > 2000000000LL) return fail(MCTSB200_ERR_CAPACITY, "visit counts may exceed 32 bits (clear_tree to start over)");
 
     // log table: det_log(N), N < log_tab_n (grown lazily, shared by all configurations)
     const int want = (int)std::min<long long>(bound + 1, 1 << 20);
@@ -476,7 +497,7 @@ constexpr size_t kFastSmemLimit = 220 * 1024;
 // The shared-memory lane-per-tree kernel (uct_fast.cuh) applies to vanilla UCT with one rollout per leaf on a
 // dense-state MDP whose tables fit in shared memory. Returns the policy variant or -1.
 template <class M, int KIND>
-int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg) {
+int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long prior_visits) {
     if constexpr (!M::kFast) {
         return -1;
     } else {
@@ -488,7 +509,7 @@ int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg) {
         if (cfg->depth > 254 || cfg->n_iterations >= (KIND == MCTSB200_KIND_UCT ? (1LL << 24) - 1 : (1LL << 16) - 1)) return -1;
         if (KIND == MCTSB200_KIND_DPW && !(cfg->check_repeat_state && cfg->check_repeat_action)) return -1;  // unmerged nodes: tile kernel
         // the kernel indexes the UCB tables without a range check: every visit count must be inside them
-        const long long bound = 4LL * std::max<long long>(cfg->init_N, 0) + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1;
+        const long long bound = 4LL * std::max<long long>(cfg->init_N, 0) + prior_visits + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1;
         if (bound + 1 > (1LL << 20)) return -1;
         if (fast_smem_bytes<M>(MdpAccess<M>::params(ctx), std::max(cfg->depth, 1), 64) > kFastSmemLimit) return -1;
         switch (cfg->rollout_policy) {
@@ -515,13 +536,22 @@ template <class M, int KIND>
 int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const typename M::AbiState* d_roots, long long n_trees,
                    long long root_stride, long long tree_index_base, int* d_action, double* d_bestq, int* d_status,
                    mctsb200_plan_stats* stats) {
-    DevCfg dcfg;
-    int32_t rc = build_dev_cfg<M>(ctx, cfg, dcfg);
-    if (rc) return rc;
-    const int fast = fast_variant<M, KIND>(ctx, cfg);
-    rc = setup_storage<M>(ctx, cfg, n_trees, fast >= 0);
-    if (rc) return rc;
     Storage& st = ctx->st;
+    // visits already in the trees if this call continues kept ones (reuse_tree / keep_tree)
+    const bool may_reuse = cfg->keep_tree && st.valid && st.keep && st.kind == cfg->kind && st.mdp_id == M::kMdpId && st.n_trees == n_trees;
+    const long long prior_visits = may_reuse ? st.visits : 0;
+    DevCfg dcfg;
+    int32_t rc = build_dev_cfg<M>(ctx, cfg, dcfg, prior_visits);
+    if (rc) return rc;
+    const int fast = fast_variant<M, KIND>(ctx, cfg, prior_visits);
+    bool reused = false;
+    rc = setup_storage<M>(ctx, cfg, n_trees, fast >= 0, &reused);
+    if (rc) return rc;
+    if (reused) {  // same trees, new search: iteration counters and per-root status start over
+        MCTSB200_LAUNCH(begin_call_kernel, (unsigned)((n_trees + 255) / 256), 256, 0, ctx->stream, (TreeHeader*)st.hdr.p, n_trees);
+        CUDA_TRY(cudaGetLastError());
+    }
+    st.valid = false;
     CUDA_TRY(ctx->counters.ensure(sizeof(unsigned long long) * CNT_COUNT));
     CUDA_TRY(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned long long) * CNT_COUNT, ctx->stream));
 
@@ -549,7 +579,9 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.n_slots = n_trees;
     int fast_block = 0;  // block size the lane order was dealt for
     if constexpr (M::kDense) {
-        if (root_stride == 1 && n_trees > 32 && n_trees < (1LL << 30) && env_enabled("MCTSB200_LANE_ORDER", fast >= 0 && MdpAccess<M>::lockstep(ctx, cfg))) {
+        // (kept trees live in their lane's slot of the interleaved table: the slot <-> tree map must not change between calls)
+        if (root_stride == 1 && n_trees > 32 && n_trees < (1LL << 30) && !cfg->keep_tree &&
+            env_enabled("MCTSB200_LANE_ORDER", fast >= 0 && MdpAccess<M>::lockstep(ctx, cfg))) {
             const int n_bins = MdpAccess<M>::dense_count(ctx);
             const int tpw = 32 / G;  // tiles per warp
             // upper bound of the padded slot count (the exact one is only known on the device): every non-empty
@@ -591,12 +623,16 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             if (bytes > free_b + st.rows_fast.cap)
                 return fail(MCTSB200_ERR_CAPACITY, "node tables need %.2f GB more HBM than is free; plan fewer roots per call", (bytes - st.rows_fast.cap) / 1e9);
         }
-        CUDA_TRY(st.rows_fast.ensure(bytes));
-        CUDA_TRY(cudaMemsetAsync(st.rows_fast.p, 0, bytes, ctx->stream));
+        if (!reused) {
+            CUDA_TRY(st.rows_fast.ensure(bytes));
+            CUDA_TRY(cudaMemsetAsync(st.rows_fast.p, 0, bytes, ctx->stream));
+        }
         args.rows_fast = st.rows_fast.p;
         if (KIND == MCTSB200_KIND_DPW) {
-            CUDA_TRY(st.trans_fast.ensure(2 * bytes));
-            CUDA_TRY(cudaMemsetAsync(st.trans_fast.p, 0, 2 * bytes, ctx->stream));
+            if (!reused) {
+                CUDA_TRY(st.trans_fast.ensure(2 * bytes));
+                CUDA_TRY(cudaMemsetAsync(st.trans_fast.p, 0, 2 * bytes, ctx->stream));
+            }
             args.trans_fast = st.trans_fast.p;
         }
     }
@@ -680,6 +716,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaEventElapsedTime(&kernel_ms, ctx->ev0, ctx->ev1));
     st.valid = true;
+    st.visits = prior_visits + (long long)done * std::max(cfg->depth, 1);
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         stats->n_trees = n_trees;

@@ -797,6 +797,14 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
 #endif
 }
 
+// A plan call that continues kept trees (reuse_tree / keep_tree): the trees stay, the search starts over.
+static __global__ void begin_call_kernel(TreeHeader* hdr, long long n_trees) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    hdr[t].iterations = 0;
+    hdr[t].status = MCTSB200_OK;
+}
+
 // Root decision: best_sanode_Q (src/vanilla.jl:339-349) / best_sanode (src/dpw.jl:163-173).
 template <class M>
 __global__ void decide_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS, long long n_trees, int* action_out,

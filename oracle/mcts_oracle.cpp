@@ -43,6 +43,7 @@
 //     sampled by cumulative count in first-occurrence order) -- distribution-identical;
 //     the device uses the multiset form.
 #include <algorithm>
+#include <any>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -140,6 +141,7 @@ struct GWPosHash {
 
 // SimpleGridWorld: actions (:up,:down,:left,:right); dir up(0,1) down(0,-1) left(-1,0) right(1,0).
 struct GridWorld {
+    static constexpr int kMdpId = MCTSB200_MDP_GRIDWORLD;
     using State = GWPos;
     static constexpr int kActions = 4;
     int nx = 10, ny = 10;
@@ -214,6 +216,7 @@ struct MCStateHash {
 
 // MountainCar: actions [-1., 0., 1.]; gen is deterministic.
 struct MountainCar {
+    static constexpr int kMdpId = MCTSB200_MDP_MOUNTAINCAR;
     using State = MCState;
     static constexpr int kActions = 3;
     double gamma, cost, jackpot;
@@ -378,6 +381,22 @@ struct VanillaPlanner {
     VanillaPlanner(const M& m, const mctsb200_solver_cfg& c, uint64_t tree_index)
         : mdp(m), cfg(c), hooks{m, c, tree_index, 0, &cnt} {}
 
+    // planner.tree across calls (reuse_tree, src/vanilla.jl:213-217): the tree outlives the planner object of one call
+    struct Saved {
+        std::unordered_map<S, int64_t, H> state_map;
+        std::vector<std::vector<int64_t>> child_ids;
+        std::vector<int64_t> total_n;
+        std::vector<S> s_labels;
+        std::vector<int64_t> n;
+        std::vector<double> q;
+        std::vector<int32_t> a_labels;
+    };
+    Saved save() { return Saved{std::move(state_map), std::move(child_ids), std::move(total_n), std::move(s_labels), std::move(n), std::move(q), std::move(a_labels)}; }
+    void load(Saved&& t) {
+        state_map = std::move(t.state_map); child_ids = std::move(t.child_ids); total_n = std::move(t.total_n); s_labels = std::move(t.s_labels);
+        n = std::move(t.n); q = std::move(t.q); a_labels = std::move(t.a_labels);
+    }
+
     int64_t insert_node(const S& s) {
         s_labels.push_back(s);
         state_map[s] = (int64_t)s_labels.size();
@@ -527,6 +546,30 @@ struct DPWPlanner {
 
     DPWPlanner(const M& m, const mctsb200_solver_cfg& c, uint64_t tree_index, bool literal)
         : mdp(m), cfg(c), literal_transitions(literal), hooks{m, c, tree_index, 0, &cnt} {}
+
+    // p.tree across calls (keep_tree, src/dpw.jl:31-37)
+    struct Saved {
+        std::vector<int64_t> total_n;
+        std::vector<std::vector<int64_t>> children;
+        std::vector<S> s_labels;
+        std::unordered_map<S, int64_t, H> s_lookup;
+        std::vector<int64_t> n;
+        std::vector<double> q;
+        std::vector<std::vector<std::pair<int64_t, double>>> transitions;
+        std::vector<int32_t> a_labels;
+        std::map<std::pair<int64_t, int32_t>, int64_t> a_lookup;
+        std::vector<int64_t> n_a_children;
+        std::set<std::pair<int64_t, int64_t>> unique_transitions;
+    };
+    Saved save() {
+        return Saved{std::move(total_n), std::move(children), std::move(s_labels), std::move(s_lookup), std::move(n), std::move(q),
+                     std::move(transitions), std::move(a_labels), std::move(a_lookup), std::move(n_a_children), std::move(unique_transitions)};
+    }
+    void load(Saved&& t) {
+        total_n = std::move(t.total_n); children = std::move(t.children); s_labels = std::move(t.s_labels); s_lookup = std::move(t.s_lookup);
+        n = std::move(t.n); q = std::move(t.q); transitions = std::move(t.transitions); a_labels = std::move(t.a_labels);
+        a_lookup = std::move(t.a_lookup); n_a_children = std::move(t.n_a_children); unique_transitions = std::move(t.unique_transitions);
+    }
 
     int64_t insert_state_node(const S& s, bool maintain_s_lookup) {
         total_n.push_back(0);
@@ -763,14 +806,19 @@ struct RootResult {
 
 static std::vector<std::unique_ptr<ExportedTree>> g_trees;
 static std::vector<RootResult> g_roots;
+// trees kept for the next call (reuse_tree / keep_tree): one per root index, valid for one (solver kind, MDP) pair
+static std::vector<std::any> g_saved;
+static int g_saved_kind = -1, g_saved_mdp = -1;
 static std::mutex g_mu;
 
 template <class M, class H>
 static void plan_one(const M& mdp, const mctsb200_solver_cfg& cfg, const typename M::State& root, uint64_t tree_index,
                      bool literal, bool keep, RootResult& res, Counters& cnt, std::unique_ptr<ExportedTree>& tree_out,
-                     int64_t& iterations_done) {
+                     int64_t& iterations_done, std::any* saved) {
     if (cfg.kind == MCTSB200_KIND_UCT) {
         VanillaPlanner<M, H> p(mdp, cfg, tree_index);
+        using SavedT = typename VanillaPlanner<M, H>::Saved;
+        if (cfg.keep_tree && saved && saved->has_value()) p.load(std::move(std::any_cast<SavedT&>(*saved)));
         int64_t rootid = 0;
         iterations_done = p.build_tree(root, rootid);
         const int64_t best = p.best_sanode_Q(rootid);
@@ -789,8 +837,11 @@ static void plan_one(const M& mdp, const mctsb200_solver_cfg& cfg, const typenam
             tree_out.reset(new ExportedTree());
             p.export_tree(*tree_out);
         }
+        if (cfg.keep_tree && saved) *saved = p.save();
     } else {
         DPWPlanner<M, H> p(mdp, cfg, tree_index, literal);
+        using SavedT = typename DPWPlanner<M, H>::Saved;
+        if (cfg.keep_tree && saved && saved->has_value()) p.load(std::move(std::any_cast<SavedT&>(*saved)));
         int64_t rootid = 0;
         res.status = p.search(root, rootid, iterations_done);
         if (res.status == MCTSB200_OK) {
@@ -812,6 +863,7 @@ static void plan_one(const M& mdp, const mctsb200_solver_cfg& cfg, const typenam
             tree_out.reset(new ExportedTree());
             p.export_tree(*tree_out);
         }
+        if (cfg.keep_tree && saved) *saved = p.save();
     }
 }
 
@@ -827,6 +879,13 @@ static int32_t plan_batch(const M& mdp, const mctsb200_solver_cfg& cfg, const ty
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<RootResult> results((size_t)n_roots);
     std::vector<std::unique_ptr<ExportedTree>> trees((size_t)n_roots);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        const bool compatible = cfg.keep_tree && (int64_t)g_saved.size() == n_roots && g_saved_kind == cfg.kind && g_saved_mdp == M::kMdpId;
+        if (!compatible) g_saved.assign(cfg.keep_tree ? (size_t)n_roots : 0, std::any());
+        g_saved_kind = cfg.kind;
+        g_saved_mdp = M::kMdpId;
+    }
     std::vector<Counters> per_thread((size_t)std::max(1, n_threads));
     std::atomic<int64_t> next{0};
     std::atomic<int64_t> min_done{std::numeric_limits<int64_t>::max()};
@@ -837,7 +896,7 @@ static int32_t plan_batch(const M& mdp, const mctsb200_solver_cfg& cfg, const ty
             Counters c;
             int64_t done = 0;
             plan_one<M, H>(mdp, cfg, roots[same_root ? 0 : i], (uint64_t)(base + i), literal, keep, results[(size_t)i], c,
-                           trees[(size_t)i], done);
+                           trees[(size_t)i], done, cfg.keep_tree ? &g_saved[(size_t)i] : nullptr);
             per_thread[(size_t)tid].add(c);
             int64_t cur = min_done.load();
             while (done < cur && !min_done.compare_exchange_weak(cur, done)) {
@@ -891,6 +950,14 @@ static void copy_out(T* dst, const std::vector<T>& src) {
 }
 
 extern "C" {
+
+// clear_tree!(planner) (src/vanilla.jl:148, src/dpw.jl:6-8): forget the trees kept for reuse
+int32_t oracle_clear_trees(void) {
+    std::lock_guard<std::mutex> lk(oracle::g_mu);
+    oracle::g_saved.clear();
+    oracle::g_saved_kind = oracle::g_saved_mdp = -1;
+    return MCTSB200_OK;
+}
 
 int32_t oracle_plan(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* params, const void* roots, int64_t n_roots,
                     int64_t root_index_base, int32_t n_threads, int32_t keep_trees, int32_t literal_transitions,

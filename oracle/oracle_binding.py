@@ -81,7 +81,12 @@ class Oracle:
         self._params = {}
 
     def configure(self, mdp_id: int, params) -> None:
+        if mdp_id in self._params and bytes(self._params[mdp_id]) != bytes(params):
+            self.clear_trees()  # like mctsb200_mdp_configure: a new model invalidates the trees kept for reuse
         self._params[mdp_id] = params
+
+    def clear_trees(self) -> None:
+        self.lib.oracle_clear_trees()
 
     def plan(self, cfg, mdp_id: int, roots: np.ndarray, root_index_base: int = 0, n_threads: int = 1, keep_trees: bool = True,
              literal_transitions: bool = False, same_root: bool = False, n_trees: int | None = None):

@@ -155,3 +155,21 @@ def test_full_size_config3_dpw_sampled_oracle(gpu_ctx, oracle):
         assert a2[0] == a[i] and q2.view(np.int64)[0] == q.view(np.int64)[i]
         assert_trees_equal(gpu_ctx.tree_export(i, GW.state_dtype, GW.state_width), oracle.tree_export(0, GW.state_dtype, GW.state_width), f"tree {i}")
     del keep
+
+
+@pytest.mark.parametrize("kind,lanes", [("uct", None), ("dpw", None), ("uct", 4), ("dpw", 8)])
+def test_kept_trees_continue_across_calls(gpu_ctx, oracle, kind, lanes):
+    """reuse_tree (src/vanilla.jl:213-217) / keep_tree (src/dpw.jl:31-37): an episode-like sequence of plan calls grows the
+    same trees; lanes=None runs the lane-per-tree kernels, otherwise the tile kernel."""
+    gpu_ctx.clear_trees()
+    oracle.clear_trees()
+    if kind == "uct":
+        mk = lambda seed: m.MCTSSolver(n_iterations=120, depth=12, exploration_constant=5.0, rng=seed, reuse_tree=True)
+    else:
+        mk = lambda seed: m.DPWSolver(n_iterations=120, depth=12, exploration_constant=5.0, rng=seed, keep_tree=True)
+    roots = gridworld_roots(96)
+    for call, shift in enumerate((0, 1, 11, 0)):
+        rs = [(1 + (x - 1 + shift) % 10, 1 + (y - 1 + shift // 10) % 10) for x, y in roots]
+        run_both(gpu_ctx, oracle, mk(200 + call), GW, rs, lanes=lanes, compare_trees=range(0, 96, 5))
+    gpu_ctx.clear_trees()
+    oracle.clear_trees()

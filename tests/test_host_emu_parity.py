@@ -186,3 +186,42 @@ def test_emu_max_time_chunks_give_the_same_trees(emu_ctx, oracle):
               m.DPWSolver(n_iterations=90, depth=10, rng=4, max_time=1e6)):
         _, _, _, st = run_both(emu_ctx, oracle, s, GW, gridworld_roots(20))
         assert st.iterations_done == 90 and st.n_kernel_launches > 2
+
+
+# ---- trees kept across calls: reuse_tree (src/vanilla.jl:213-217) / keep_tree (src/dpw.jl:31-37) -----------------------
+@pytest.mark.parametrize("fast", ["1", "0"])
+@pytest.mark.parametrize("kind", ["uct", "dpw"])
+def test_emu_kept_trees_continue_across_calls(emu_ctx, oracle, monkeypatch, kind, fast):
+    monkeypatch.setenv("MCTSB200_FAST", fast)
+    emu_ctx.clear_trees()
+    oracle.clear_trees()
+    if kind == "uct":
+        mk = lambda seed: m.MCTSSolver(n_iterations=70, depth=10, exploration_constant=5.0, rng=seed, reuse_tree=True)
+    else:
+        mk = lambda seed: m.DPWSolver(n_iterations=70, depth=10, exploration_constant=5.0, rng=seed, keep_tree=True)
+    roots = gridworld_roots(40)
+    sizes = []
+    for call, shift in enumerate((0, 1, 11, 0)):  # an episode-like sequence of root states per tree; the last returns to the start
+        rs = [(1 + (x - 1 + shift) % 10, 1 + (y - 1 + shift // 10) % 10) for x, y in roots]
+        _, _, _, st = run_both(emu_ctx, oracle, mk(100 + call), GW, rs, compare_trees=range(0, 40, 3))
+        assert st.kernel_variant == int(fast)
+        sizes.append(emu_ctx.tree_export(0)["total_n"].shape[0])
+    assert sizes == sorted(sizes) and sizes[-1] > sizes[0]  # the tree of root 0 only ever grows
+    # clear_tree! starts over
+    emu_ctx.clear_trees()
+    oracle.clear_trees()
+    run_both(emu_ctx, oracle, mk(100), GW, roots, compare_trees=range(0, 40, 7))
+    assert emu_ctx.tree_export(0)["total_n"].shape[0] == sizes[0]
+
+
+def test_emu_kept_trees_need_a_bounded_table(emu_ctx):
+    mc = m.MountainCar()
+    cfg, keep = m.build_cfg(m.DPWSolver(n_iterations=20, depth=5, keep_tree=True), mc)
+    emu_ctx.configure(mc.mdp_id, mc.params())
+    with pytest.raises(m.MCTSB200Error) as ei:
+        emu_ctx.plan(cfg, mc.mdp_id, mc.encode_states(mountaincar_roots(2)))
+    assert ei.value.status == m.abi.ERR_UNSUPPORTED
+    cfg, keep = m.build_cfg(m.DPWSolver(n_iterations=20, depth=5, keep_tree=True, check_repeat_state=False), GW)
+    emu_ctx.configure(GW.mdp_id, GW.params())
+    with pytest.raises(m.MCTSB200Error):
+        emu_ctx.plan(cfg, GW.mdp_id, GW.encode_states(gridworld_roots(2)))
