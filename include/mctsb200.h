@@ -197,6 +197,20 @@ int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg
 int32_t mctsb200_root_parallel_decide(const double* sum_n, const double* sum_nq, int32_t n_actions,
                                       double init_q, int32_t* action_idx_out, double* best_q_out, double* q_out);
 
+/* ---- episode driver -------------------------------------------------------------------------------- */
+/* Replaces simulate(RolloutSimulator(max_steps = max_steps), mdp, planner, s0) -- the loop that
+ * bench/non-terminal_gw.jl:18,31, bench/non-terminal_gw_dpw.jl and test/performance.jl:33-40 time -- for n_episodes
+ * start states in lockstep, without leaving the device between environment steps: at step t every running episode
+ * plans from its current state (one mctsb200_plan over the whole batch with the Philox key cfg->seed + t; with
+ * keep_tree the trees follow their episodes), then the environment moves with gen(mdp, s, a, rng), rng = Philox stream
+ * (env_seed, episode_index_base + i, t, 0). An episode ends in a terminal state or after max_steps steps.
+ * Outputs (host, n_episodes each; may be NULL): the discounted return sum_t gamma^t r_t, the number of steps taken and
+ * the last state. stats_out: work counters summed over all plan calls. */
+int32_t mctsb200_run_episodes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* initial_states,
+                              int64_t n_episodes, size_t state_bytes, int32_t max_steps, uint64_t env_seed,
+                              int64_t episode_index_base, double* return_out, int32_t* steps_out, void* final_states_out,
+                              mctsb200_plan_stats* stats_out);
+
 /* ---- tree queries (info[:tree], value(), ranked_actions) ------------------------------------------ */
 /* Children of the root of tree root_i, in child order. Buffers hold >= n_actions entries. */
 int32_t mctsb200_root_stats(mctsb200_ctx* ctx, int64_t root_i, int32_t* n_children, int32_t* action_idx,

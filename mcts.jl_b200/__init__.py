@@ -15,10 +15,12 @@ from . import _abi as abi
 from ._lib import Context, MCTSB200Error, build_library, load_library
 from .models import GWPos, MountainCar, SimpleGridWorld
 from .solvers import (ConstantPolicy, DPWPlanner, DPWSolver, EnergyPolicy, ExceptionRethrow, MCTSPlanner, MCTSSolver,
-                      RandomPolicy, RandomSolver, RolloutEstimator, SeekTarget, build_cfg, clear_tree, ranked_actions, solve)
+                      RandomPolicy, RandomSolver, RolloutEstimator, RolloutSimulator, SeekTarget, build_cfg, clear_tree, ranked_actions,
+                      simulate, simulate_batch, solve)
 
 __all__ = [
     "abi", "Context", "MCTSB200Error", "build_library", "load_library", "GWPos", "MountainCar", "SimpleGridWorld",
     "ConstantPolicy", "DPWPlanner", "DPWSolver", "EnergyPolicy", "ExceptionRethrow", "MCTSPlanner", "MCTSSolver",
-    "RandomPolicy", "RandomSolver", "RolloutEstimator", "SeekTarget", "build_cfg", "clear_tree", "ranked_actions", "solve",
+    "RandomPolicy", "RandomSolver", "RolloutEstimator", "RolloutSimulator", "SeekTarget", "build_cfg", "clear_tree", "ranked_actions",
+    "simulate", "simulate_batch", "solve",
 ]

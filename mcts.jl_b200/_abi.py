@@ -165,6 +165,7 @@ EXPORTED_SYMBOLS = (
     "mctsb200_plan",
     "mctsb200_plan_device",
     "mctsb200_plan_root_parallel",
+    "mctsb200_run_episodes",
     "mctsb200_root_parallel_decide",
     "mctsb200_root_stats",
     "mctsb200_tree_sizes_query",
@@ -192,6 +193,7 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.mctsb200_plan.argtypes = [vp, P(SolverCfg), i32, vp, i64, sz, i64, vp, vp, vp, P(PlanStats)]
     lib.mctsb200_plan_device.argtypes = [vp, P(SolverCfg), i32, vp, i64, sz, i64, vp, vp, vp, P(PlanStats)]
     lib.mctsb200_plan_root_parallel.argtypes = [vp, P(SolverCfg), i32, vp, sz, i64, i64, vp, vp, vp, P(PlanStats)]
+    lib.mctsb200_run_episodes.argtypes = [vp, P(SolverCfg), i32, vp, i64, sz, i32, u64, i64, vp, vp, vp, P(PlanStats)]
     lib.mctsb200_root_parallel_decide.argtypes = [vp, vp, i32, dbl, P(i32), P(dbl), vp]
     lib.mctsb200_root_stats.argtypes = [vp, i64, P(i32), vp, vp, vp, P(i64)]
     lib.mctsb200_tree_sizes_query.argtypes = [vp, i64, P(TreeSizes)]

@@ -146,6 +146,21 @@ class Context:
                                                   C.c_void_p(d_status or None), C.byref(stats)))
         return stats
 
+    def run_episodes(self, cfg: abi.SolverCfg, mdp_id: int, states: np.ndarray, max_steps: int, env_seed: int = 0,
+                     episode_index_base: int = 0):
+        """simulate(RolloutSimulator(max_steps=max_steps), mdp, planner, s0) for every row of states, on the device.
+        Returns (discounted returns, steps taken, final states, stats summed over the plan calls)."""
+        states = np.ascontiguousarray(states)
+        n = states.shape[0]
+        state_bytes = states.dtype.itemsize * int(np.prod(states.shape[1:], dtype=np.int64)) if n else 0
+        returns = np.empty(n, dtype=np.float64)
+        steps = np.empty(n, dtype=np.int32)
+        final = np.empty_like(states)
+        stats = abi.PlanStats()
+        self._check(self.lib.mctsb200_run_episodes(self._h, C.byref(cfg), mdp_id, _ptr(states), n, state_bytes, int(max_steps), int(env_seed),
+                                                   int(episode_index_base), _ptr(returns), _ptr(steps), _ptr(final), C.byref(stats)))
+        return returns, steps, final, stats
+
     def plan_root_parallel(self, cfg: abi.SolverCfg, mdp_id: int, root: np.ndarray, n_trees: int, tree_index_base: int = 0,
                            d_sums: int = 0):
         root = np.ascontiguousarray(root)

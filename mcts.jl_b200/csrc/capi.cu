@@ -95,6 +95,7 @@ struct mctsb200_ctx {
     Storage st;
     DevBuf counters, log_tab, sqrtlog_tab, rsqrt_tab, nmin_state, init_q, init_n, value_tab, io_roots, io_action, io_bestq, io_status, sums;
     DevBuf order, order_bins, policy_tab;
+    DevBuf ep_states, ep_disc, ep_ret, ep_steps, ep_active, ep_count;
     int log_tab_n = 0;
 };
 
@@ -838,6 +839,83 @@ int32_t root_parallel_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg
     return MCTSB200_OK;
 }
 
+// ---- episode driver ------------------------------------------------------------------------------
+template <class M>
+int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const void* initial_states, long long n, size_t state_bytes,
+                          int max_steps, unsigned long long env_seed, long long base, double* return_out, int32_t* steps_out,
+                          void* final_states_out, mctsb200_plan_stats* stats) {
+    using Abi = typename M::AbiState;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
+    int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok);
+    if (rc) return rc;
+    if (state_bytes != sizeof(Abi) || !initial_states || n <= 0 || max_steps < 0 || base < 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad run_episodes arguments");
+    const Abi* h = (const Abi*)initial_states;
+    for (long long i = 0; i < n; ++i)
+        if (MdpAccess<M>::check_root(ctx, h[i])) return fail(MCTSB200_ERR_INVALID_ARG, "start state %lld is not a valid state of this MDP", i);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx->ep_states.ensure(sizeof(Abi) * (size_t)n));
+    CUDA_TRY(ctx->ep_disc.ensure(sizeof(double) * (size_t)n));
+    CUDA_TRY(ctx->ep_ret.ensure(sizeof(double) * (size_t)n));
+    CUDA_TRY(ctx->ep_steps.ensure(sizeof(int) * (size_t)n));
+    CUDA_TRY(ctx->ep_active.ensure(sizeof(int) * (size_t)n));
+    CUDA_TRY(ctx->ep_count.ensure(sizeof(int) * ((size_t)max_steps + 1)));
+    CUDA_TRY(ctx->io_action.ensure(sizeof(int) * (size_t)n));
+    CUDA_TRY(ctx->io_status.ensure(sizeof(int) * (size_t)n));
+    Abi* d_s = (Abi*)ctx->ep_states.p;
+    int* d_cnt = (int*)ctx->ep_count.p;  // d_cnt[t] = episodes still running before step t
+    CUDA_TRY(cudaMemcpyAsync(d_s, initial_states, sizeof(Abi) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int) * ((size_t)max_steps + 1), ctx->stream));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    const typename M::Params mdp = MdpAccess<M>::params(ctx);
+    {
+        auto k = episode_init_kernel<M>;
+        MCTSB200_LAUNCH(k, grid, 256, 0, ctx->stream, mdp, (const Abi*)d_s, n, (double*)ctx->ep_disc.p, (double*)ctx->ep_ret.p, (int*)ctx->ep_steps.p,
+                        (int*)ctx->ep_active.p, d_cnt);
+        CUDA_TRY(cudaGetLastError());
+    }
+    mctsb200_plan_stats tot;
+    std::memset(&tot, 0, sizeof tot);
+    int launches = 1;
+    for (int t = 0; t < max_steps; ++t) {
+        int running = 0;
+        CUDA_TRY(cudaMemcpyAsync(&running, d_cnt + t, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (running == 0) break;
+        mctsb200_solver_cfg c = *cfg;
+        c.seed = cfg->seed + (uint64_t)t;
+        mctsb200_plan_stats st;
+        if (cfg->kind == MCTSB200_KIND_UCT)
+            rc = run_search<M, MCTSB200_KIND_UCT>(ctx, &c, d_s, n, 1, base, (int*)ctx->io_action.p, nullptr, (int*)ctx->io_status.p, &st);
+        else
+            rc = run_search<M, MCTSB200_KIND_DPW>(ctx, &c, d_s, n, 1, base, (int*)ctx->io_action.p, nullptr, (int*)ctx->io_status.p, &st);
+        if (rc) return rc;
+        tot.n_simulations += st.n_simulations; tot.n_tree_levels += st.n_tree_levels; tot.n_dpw_children_seen += st.n_dpw_children_seen;
+        tot.n_state_inserts += st.n_state_inserts; tot.n_action_inserts += st.n_action_inserts; tot.n_rollouts += st.n_rollouts;
+        tot.n_rollout_steps += st.n_rollout_steps; tot.n_transition_samples += st.n_transition_samples; tot.n_select_exact += st.n_select_exact;
+        tot.algorithmic_bytes += st.algorithmic_bytes; tot.kernel_ms += st.kernel_ms;
+        tot.lanes_per_tree = st.lanes_per_tree; tot.kernel_variant = st.kernel_variant; tot.iterations_done = st.iterations_done;
+        launches += st.n_kernel_launches + 1;
+        auto k = episode_step_kernel<M>;
+        MCTSB200_LAUNCH(k, grid, 256, 0, ctx->stream, mdp, d_s, (const int*)ctx->io_action.p, n, env_seed, base, t, (double*)ctx->ep_disc.p,
+                        (double*)ctx->ep_ret.p, (int*)ctx->ep_steps.p, (int*)ctx->ep_active.p, d_cnt + t + 1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (return_out) CUDA_TRY(cudaMemcpyAsync(return_out, ctx->ep_ret.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (steps_out) CUDA_TRY(cudaMemcpyAsync(steps_out, ctx->ep_steps.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (final_states_out) CUDA_TRY(cudaMemcpyAsync(final_states_out, d_s, sizeof(Abi) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        tot.n_trees = n;
+        tot.n_kernel_launches = launches;
+        tot.h2d_bytes = (int64_t)(sizeof(Abi) * (size_t)n);
+        tot.d2h_bytes = (int64_t)((return_out ? 8 : 0) + (steps_out ? 4 : 0) + (final_states_out ? sizeof(Abi) : 0)) * n;
+        tot.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        *stats = tot;
+    }
+    return MCTSB200_OK;
+}
+
 // ---- tree export --------------------------------------------------------------------------------
 template <class M>
 struct HostTree {
@@ -1050,7 +1128,8 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->counters,
                       &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
-                      &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->gw_fast};
+                      &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->gw_fast,
+                      &c->ep_states, &c->ep_disc, &c->ep_ret, &c->ep_steps, &c->ep_active, &c->ep_count};
     for (DevBuf* b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1213,6 +1292,19 @@ int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg
         return root_parallel_dispatch<GridWorldDev>(ctx, cfg, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out);
     if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
         return root_parallel_dispatch<MountainCarDev>(ctx, cfg, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out);
+    return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+}
+
+int32_t mctsb200_run_episodes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* initial_states, int64_t n_episodes,
+                              size_t state_bytes, int32_t max_steps, uint64_t env_seed, int64_t episode_index_base, double* return_out,
+                              int32_t* steps_out, void* final_states_out, mctsb200_plan_stats* stats_out) {
+    if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD)
+        return episodes_dispatch<GridWorldDev>(ctx, cfg, initial_states, n_episodes, state_bytes, max_steps, env_seed, episode_index_base, return_out,
+                                               steps_out, final_states_out, stats_out);
+    if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
+        return episodes_dispatch<MountainCarDev>(ctx, cfg, initial_states, n_episodes, state_bytes, max_steps, env_seed, episode_index_base,
+                                                 return_out, steps_out, final_states_out, stats_out);
     return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
 }
 

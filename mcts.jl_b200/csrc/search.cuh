@@ -805,6 +805,39 @@ static __global__ void begin_call_kernel(TreeHeader* hdr, long long n_trees) {
     hdr[t].status = MCTSB200_OK;
 }
 
+// Episode driver (mctsb200_run_episodes): the environment side of simulate(::RolloutSimulator, mdp, planner, s0).
+template <class M>
+__global__ void episode_init_kernel(const typename M::Params mdp, const typename M::AbiState* s, long long n, double* disc, double* ret, int* steps,
+                                    int* active, int* n_active) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool run = !M::is_terminal(mdp, M::load(mdp, s[i]));
+    disc[i] = 1.0;
+    ret[i] = 0.0;
+    steps[i] = 0;
+    active[i] = run ? 1 : 0;
+    if (run) atomicAdd(n_active, 1);
+}
+// one environment step of every running episode: sp, r = gen(mdp, s, a, rng); r_total += disc*r; disc *= discount
+template <class M>
+__global__ void episode_step_kernel(const typename M::Params mdp, typename M::AbiState* s, const int* action, long long n, unsigned long long env_seed,
+                                    long long base, int t, double* disc, double* ret, int* steps, int* active, int* n_active) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !active[i]) return;
+    Stream rng;
+    rng.init(env_seed, (uint64_t)(base + i), (uint32_t)t, 0u);
+    const typename M::State cur = M::load(mdp, s[i]);
+    typename M::State sp;
+    double r;
+    M::gen(mdp, cur, action[i], rng, sp, r);
+    ret[i] = DM_ADD(ret[i], DM_MUL(disc[i], r));
+    disc[i] = DM_MUL(disc[i], M::discount(mdp));
+    s[i] = M::store(mdp, sp);
+    steps[i] += 1;
+    if (M::is_terminal(mdp, sp)) active[i] = 0;
+    else atomicAdd(n_active, 1);
+}
+
 // Root decision: best_sanode_Q (src/vanilla.jl:339-349) / best_sanode (src/dpw.jl:163-173).
 template <class M>
 __global__ void decide_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS, long long n_trees, int* action_out,

@@ -335,6 +335,21 @@ class _Planner:
     def _label(self, idx: int):
         return self.mdp.actions[int(idx)]
 
+    def run_episodes(self, states: Sequence, max_steps: int, env_seed: int = 0, episode_index_base: int = 0):
+        """One closed-loop episode per start state, planning at every step (mctsb200_run_episodes).
+        Returns (discounted returns float64[n], steps int32[n], final states, stats)."""
+        cfg, keep = build_cfg(self.solver, self.mdp)
+        cfg.seed = (cfg.seed + self._calls) & 0xFFFFFFFFFFFFFFFF
+        self.ctx.configure(self.mdp.mdp_id, self.mdp.params())
+        s0 = self.mdp.encode_states(states)
+        returns, steps, final, stats = self.ctx.run_episodes(cfg, self.mdp.mdp_id, s0, max_steps, env_seed, episode_index_base)
+        del keep
+        self._calls += int(steps.max()) if len(steps) else 0
+        self._roots = None
+        self.tree = None
+        self.last_stats = stats
+        return returns, steps, [self.mdp.decode_state(r) for r in final], stats
+
     def clear_tree(self):
         """clear_tree!(planner)"""
         self.tree = None
@@ -449,6 +464,32 @@ def solve(solver, mdp, ctx: Optional[Context] = None, device: int = 0):
         build_cfg(solver, mdp)
         return MCTSPlanner(solver, mdp, ctx, device)
     raise TypeError(f"solve: unknown solver type {type(solver).__name__}")
+
+
+class RolloutSimulator:
+    """POMDPTools.RolloutSimulator(rng, max_steps): the simulator bench/non-terminal_gw.jl:18 and test/performance.jl:33 drive
+    the planners with. eps is not supported (the device loop stops on max_steps or a terminal state only)."""
+
+    def __init__(self, rng=None, max_steps: Optional[int] = None, eps=None):
+        if eps is not None:
+            raise _unsupported("RolloutSimulator(eps=...)")
+        self.rng, self.max_steps = rng, max_steps
+
+
+def simulate(sim: RolloutSimulator, mdp, planner: _Planner, initialstate):
+    """simulate(sim, mdp, planner, s0) -> discounted return of one episode."""
+    if sim.max_steps is None:
+        raise _unsupported("RolloutSimulator without max_steps")
+    assert mdp is planner.mdp
+    return float(planner.run_episodes([initialstate], sim.max_steps, _seed_of(sim.rng))[0][0])
+
+
+def simulate_batch(sim: RolloutSimulator, mdp, planner: _Planner, initialstates: Sequence) -> np.ndarray:
+    """Batch extension: one independent episode per start state, all on the device in lockstep."""
+    if sim.max_steps is None:
+        raise _unsupported("RolloutSimulator without max_steps")
+    assert mdp is planner.mdp
+    return planner.run_episodes(initialstates, sim.max_steps, _seed_of(sim.rng))[0]
 
 
 def clear_tree(planner: _Planner) -> None:

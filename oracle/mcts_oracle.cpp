@@ -949,6 +949,61 @@ static void copy_out(T* dst, const std::vector<T>& src) {
     if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(T));
 }
 
+namespace oracle {
+// Episode driver: simulate(RolloutSimulator(max_steps = max_steps), mdp, planner, s0) for n_episodes start states in
+// lockstep -- the loop bench/non-terminal_gw.jl:18,31 and bench/non-terminal_gw_dpw.jl time. Per environment step t every
+// episode that is still running plans from its current state (plan call t uses the Philox key seed + t; finished episodes
+// stay in the batch so that tree i always belongs to episode i) and then the environment moves with the stream
+// (env_seed, episode index, t, stream 0). Returns the discounted return and the number of steps of every episode.
+template <class M, class H>
+static int32_t run_episodes_impl(const M& mdp, const mctsb200_solver_cfg& cfg0, typename M::State* s, int64_t n, int32_t max_steps,
+                                 uint64_t env_seed, int64_t base, int n_threads, double* ret_out, int32_t* steps_out,
+                                 mctsb200_plan_stats* stats) {
+    std::vector<double> disc((size_t)n, 1.0), ret((size_t)n, 0.0);
+    std::vector<int32_t> steps((size_t)n, 0), act((size_t)n), status((size_t)n);
+    std::vector<char> active((size_t)n, 1);
+    mctsb200_plan_stats tot;
+    std::memset(&tot, 0, sizeof tot);
+    for (int64_t i = 0; i < n; ++i) active[(size_t)i] = !mdp.isterminal(s[i]);
+    for (int32_t t = 0; t < max_steps; ++t) {
+        bool any = false;
+        for (int64_t i = 0; i < n; ++i) any |= active[(size_t)i] != 0;
+        if (!any) break;
+        mctsb200_solver_cfg cfg = cfg0;
+        cfg.seed = cfg0.seed + (uint64_t)t;
+        mctsb200_plan_stats st;
+        const int32_t rc = plan_batch<M, H>(mdp, cfg, s, n, base, n_threads, false, false, false, act.data(), nullptr, status.data(), &st);
+        if (rc != MCTSB200_OK) return rc;
+        tot.n_simulations += st.n_simulations; tot.n_tree_levels += st.n_tree_levels; tot.n_dpw_children_seen += st.n_dpw_children_seen;
+        tot.n_state_inserts += st.n_state_inserts; tot.n_action_inserts += st.n_action_inserts; tot.n_rollouts += st.n_rollouts;
+        tot.n_rollout_steps += st.n_rollout_steps; tot.n_transition_samples += st.n_transition_samples;
+        tot.algorithmic_bytes += st.algorithmic_bytes;
+        for (int64_t i = 0; i < n; ++i) {
+            if (!active[(size_t)i]) continue;
+            Stream rng(env_seed, (uint64_t)(base + i), (uint32_t)t, 0);
+            typename M::State sp;
+            double r;
+            mdp.gen(s[i], act[(size_t)i], rng, sp, r);
+            ret[(size_t)i] = ret[(size_t)i] + disc[(size_t)i] * r;
+            disc[(size_t)i] = disc[(size_t)i] * mdp.discount();
+            s[i] = sp;
+            steps[(size_t)i] += 1;
+            if (mdp.isterminal(sp)) active[(size_t)i] = 0;
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        if (ret_out) ret_out[i] = ret[(size_t)i];
+        if (steps_out) steps_out[i] = steps[(size_t)i];
+    }
+    if (stats) {
+        tot.n_trees = n;
+        *stats = tot;
+    }
+    return MCTSB200_OK;
+}
+
+}  // namespace oracle
+
 extern "C" {
 
 // clear_tree!(planner) (src/vanilla.jl:148, src/dpw.jl:6-8): forget the trees kept for reuse
@@ -1044,6 +1099,23 @@ int32_t oracle_plan_root_parallel(const mctsb200_solver_cfg* cfg, int32_t mdp_id
         }
     }
     return MCTSB200_OK;
+}
+
+int32_t oracle_run_episodes(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* params, void* states_inout, int64_t n_episodes,
+                            int32_t max_steps, uint64_t env_seed, int64_t episode_index_base, int32_t n_threads, double* return_out,
+                            int32_t* steps_out, mctsb200_plan_stats* stats) {
+    using namespace oracle;
+    if (!cfg || cfg->struct_size != (int32_t)sizeof(mctsb200_solver_cfg) || !params || !states_inout || n_episodes <= 0) return MCTSB200_ERR_INVALID_ARG;
+    if (mdp_id == MCTSB200_MDP_GRIDWORLD) {
+        GridWorld m(*(const mctsb200_gridworld_params*)params);
+        return run_episodes_impl<GridWorld, GWPosHash>(m, *cfg, (GWPos*)states_inout, n_episodes, max_steps, env_seed, episode_index_base, n_threads,
+                                                       return_out, steps_out, stats);
+    } else if (mdp_id == MCTSB200_MDP_MOUNTAINCAR) {
+        MountainCar m(*(const mctsb200_mountaincar_params*)params);
+        return run_episodes_impl<MountainCar, MCStateHash>(m, *cfg, (MCState*)states_inout, n_episodes, max_steps, env_seed, episode_index_base,
+                                                           n_threads, return_out, steps_out, stats);
+    }
+    return MCTSB200_ERR_INVALID_ARG;
 }
 
 // ---- small probes used by the unit tests ----

@@ -55,6 +55,8 @@ def load(libm: bool = False) -> C.CDLL:
     lib.oracle_tree_export.restype = i32
     lib.oracle_plan_root_parallel.argtypes = [P(abi.SolverCfg), i32, vp, vp, i64, i64, i32, vp, vp, P(abi.PlanStats)]
     lib.oracle_plan_root_parallel.restype = i32
+    lib.oracle_run_episodes.argtypes = [P(abi.SolverCfg), i32, vp, vp, i64, i32, u64, i64, i32, vp, vp, P(abi.PlanStats)]
+    lib.oracle_run_episodes.restype = i32
     lib.oracle_philox.argtypes = [u64, u64, u32, u32, i32, vp]
     lib.oracle_philox_raw.argtypes = [vp, vp, vp]
     for f in ("oracle_log", "oracle_cos", "oracle_libm_log", "oracle_libm_cos"):
@@ -102,6 +104,20 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle_plan failed with {rc}")
         return actions, best_q, status, stats
+
+    def run_episodes(self, cfg, mdp_id: int, states: np.ndarray, max_steps: int, env_seed: int = 0, episode_index_base: int = 0,
+                     n_threads: int = 1):
+        """simulate(RolloutSimulator(max_steps), mdp, planner, s0) for every row of states; same shapes as Context.run_episodes."""
+        final = np.array(states, copy=True, order="C")
+        n = final.shape[0]
+        returns = np.empty(n, dtype=np.float64)
+        steps = np.empty(n, dtype=np.int32)
+        stats = abi.PlanStats()
+        rc = self.lib.oracle_run_episodes(C.byref(cfg), mdp_id, C.byref(self._params[mdp_id]), _ptr(final), n, int(max_steps), int(env_seed),
+                                          int(episode_index_base), int(n_threads), _ptr(returns), _ptr(steps), C.byref(stats))
+        if rc != 0:
+            raise RuntimeError(f"oracle_run_episodes failed with {rc}")
+        return returns, steps, final, stats
 
     def plan_root_parallel(self, cfg, mdp_id: int, root: np.ndarray, n_trees: int, tree_index_base: int = 0, n_threads: int = 1):
         root = np.ascontiguousarray(root)

@@ -62,3 +62,23 @@ def run_both(ctx, orc, solver, mdp, roots, base: int = 0, compare_trees="all", l
         assert rs1["total_n"] == rs2["total_n"]
     del keep
     return a1, q1, s1, st1
+
+
+def run_episodes_both(ctx, orc, solver, mdp, starts, max_steps: int, env_seed: int = 0, base: int = 0):
+    """The closed-loop episode driver (plan at every step, then gen) on the library and on the oracle, bit-for-bit."""
+    cfg, keep = m.build_cfg(solver, mdp)
+    ctx.configure(mdp.mdp_id, mdp.params())
+    orc.configure(mdp.mdp_id, mdp.params())
+    ctx.clear_trees()
+    orc.clear_trees()
+    s0 = mdp.encode_states(starts)
+    r1, n1, f1, st1 = ctx.run_episodes(cfg, mdp.mdp_id, s0, max_steps, env_seed, base)
+    r2, n2, f2, st2 = orc.run_episodes(cfg, mdp.mdp_id, s0, max_steps, env_seed, base, n_threads=4)
+    assert np.array_equal(n1, n2), f"episode lengths differ at {np.nonzero(n1 != n2)[0][:10]}"
+    assert np.array_equal(bits(r1), bits(r2)), f"returns differ at {np.nonzero(bits(r1) != bits(r2))[0][:10]}"
+    assert np.array_equal(f1.view(np.uint8), f2.view(np.uint8)), "final states differ"
+    d1, d2 = st1.as_dict(), st2.as_dict()
+    for k in COUNTER_KEYS:
+        assert d1[k] == d2[k], f"counter {k}: {d1[k]} != {d2[k]}"
+    del keep
+    return r1, n1, f1, st1

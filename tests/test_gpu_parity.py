@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import mcts_jl_b200 as m
-from helpers import gridworld_roots, mountaincar_roots, run_both
+from helpers import run_episodes_both, gridworld_roots, mountaincar_roots, run_both
 
 pytestmark = pytest.mark.gpu
 
@@ -173,3 +173,33 @@ def test_kept_trees_continue_across_calls(gpu_ctx, oracle, kind, lanes):
         run_both(gpu_ctx, oracle, mk(200 + call), GW, rs, lanes=lanes, compare_trees=range(0, 96, 5))
     gpu_ctx.clear_trees()
     oracle.clear_trees()
+
+
+# ---- episode driver: simulate(RolloutSimulator(max_steps), mdp, planner, s0) (bench/non-terminal_gw.jl:18,31) ----------
+@pytest.mark.parametrize("kind", ["uct", "uct-reuse", "dpw", "dpw-keep"])
+def test_episodes_gridworld(gpu_ctx, oracle, kind):
+    est = m.RolloutEstimator(m.RandomSolver(), max_depth=10)
+    if kind.startswith("uct"):
+        s = m.MCTSSolver(n_iterations=150, depth=12, exploration_constant=5.0, rng=3, estimate_value=est, reuse_tree=kind.endswith("reuse"))
+    else:
+        s = m.DPWSolver(n_iterations=150, depth=12, exploration_constant=5.0, rng=3, estimate_value=est, keep_tree=kind.endswith("keep"))
+    starts = [p for p in gridworld_roots(400) if not GW.isterminal(p)][:300]
+    ret, steps, final, st = run_episodes_both(gpu_ctx, oracle, s, GW, starts, max_steps=15, env_seed=99, base=7)
+    assert steps.max() == 15 and steps.min() < 15
+    gpu_ctx.clear_trees()
+    oracle.clear_trees()
+
+
+def test_episodes_nonterminal_gridworld_benchmark_shape(gpu_ctx, oracle):
+    """bench/non-terminal_gw.jl:11-18 scaled down: no terminal cells, n_iterations per step, every episode runs max_steps."""
+    gw = m.SimpleGridWorld(terminate_from=())
+    s = m.MCTSSolver(n_iterations=200, depth=20, exploration_constant=5.0, rng=1)
+    ret, steps, final, st = run_episodes_both(gpu_ctx, oracle, s, gw, gridworld_roots(256), max_steps=20, env_seed=5)
+    assert (steps == 20).all() and st.n_simulations == 200 * 256 * 20
+
+
+def test_episodes_mountaincar(gpu_ctx, oracle):
+    s = m.DPWSolver(n_iterations=100, depth=10, exploration_constant=2.0, rng=11, estimate_value=m.RolloutEstimator(m.EnergyPolicy(), max_depth=30))
+    starts = mountaincar_roots(40) + [(0.6, 0.0)]
+    ret, steps, final, st = run_episodes_both(gpu_ctx, oracle, s, MC, starts, max_steps=8, env_seed=2)
+    assert steps[-1] == 0 and ret[-1] == 0.0

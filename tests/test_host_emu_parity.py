@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 import mcts_jl_b200 as m
-from helpers import gridworld_roots, mountaincar_roots, run_both
+from helpers import gridworld_roots, mountaincar_roots, run_both, run_episodes_both
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GW = m.SimpleGridWorld()
@@ -225,3 +225,46 @@ def test_emu_kept_trees_need_a_bounded_table(emu_ctx):
     emu_ctx.configure(GW.mdp_id, GW.params())
     with pytest.raises(m.MCTSB200Error):
         emu_ctx.plan(cfg, GW.mdp_id, GW.encode_states(gridworld_roots(2)))
+
+
+# ---- episode driver: simulate(RolloutSimulator(max_steps), mdp, planner, s0) (bench/non-terminal_gw.jl:18,31) ----------
+@pytest.mark.parametrize("kind", ["uct", "uct-reuse", "dpw", "dpw-keep"])
+def test_emu_episodes_gridworld(emu_ctx, oracle, kind):
+    est = m.RolloutEstimator(m.RandomSolver(), max_depth=10)
+    if kind.startswith("uct"):
+        s = m.MCTSSolver(n_iterations=60, depth=10, exploration_constant=5.0, rng=3, estimate_value=est, reuse_tree=kind.endswith("reuse"))
+    else:
+        s = m.DPWSolver(n_iterations=60, depth=10, exploration_constant=5.0, rng=3, estimate_value=est, keep_tree=kind.endswith("keep"))
+    starts = [p for p in gridworld_roots(100) if not GW.isterminal(p)][:48]
+    ret, steps, final, st = run_episodes_both(emu_ctx, oracle, s, GW, starts, max_steps=12, env_seed=99, base=7)
+    assert steps.max() == 12 and steps.min() < 12  # some episodes reach a reward cell early, some run to the step limit
+    assert (ret != 0).any()
+    assert st.n_simulations <= 60 * 48 * 12
+
+
+def test_emu_episodes_nonterminal_gridworld(emu_ctx, oracle):
+    """bench/non-terminal_gw.jl: no terminal states, every episode runs max_steps steps."""
+    gw = m.SimpleGridWorld(terminate_from=())
+    s = m.MCTSSolver(n_iterations=40, depth=8, exploration_constant=5.0, rng=1)
+    ret, steps, final, st = run_episodes_both(emu_ctx, oracle, s, gw, gridworld_roots(33), max_steps=9, env_seed=5)
+    assert (steps == 9).all()
+    assert st.n_simulations == 40 * 33 * 9
+
+
+def test_emu_episodes_mountaincar_and_terminal_starts(emu_ctx, oracle):
+    s = m.DPWSolver(n_iterations=30, depth=8, exploration_constant=2.0, rng=11, estimate_value=m.RolloutEstimator(m.EnergyPolicy(), max_depth=20))
+    starts = mountaincar_roots(6) + [(0.6, 0.0)]  # the last start state is already terminal: zero steps, zero return
+    ret, steps, final, st = run_episodes_both(emu_ctx, oracle, s, MC, starts, max_steps=5, env_seed=2)
+    assert steps[-1] == 0 and ret[-1] == 0.0 and tuple(final[-1]) == (0.6, 0.0)
+    ret0, steps0, _, _ = run_episodes_both(emu_ctx, oracle, s, MC, starts, max_steps=0)
+    assert (steps0 == 0).all() and (ret0 == 0).all()
+
+
+def test_emu_simulate_mirror(emu_ctx):
+    planner = m.solve(m.MCTSSolver(n_iterations=30, depth=8, rng=4), GW, ctx=emu_ctx)
+    sim = m.RolloutSimulator(rng=8, max_steps=6)
+    one = m.simulate(sim, GW, planner, (2, 2))
+    many = m.simulate_batch(sim, GW, m.solve(m.MCTSSolver(n_iterations=30, depth=8, rng=4), GW, ctx=emu_ctx), [(2, 2), (5, 5)])
+    assert isinstance(one, float) and many.shape == (2,) and one == many[0]
+    with pytest.raises(m.MCTSB200Error):
+        m.simulate(m.RolloutSimulator(), GW, planner, (2, 2))
