@@ -332,6 +332,8 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     return MCTSB200_OK;
 }
 
+constexpr long long kUcbTabMax = 1LL << 22;  // entries of the log / sqrt-log / 1/sqrt tables (visit counts beyond: computed)
+
 template <class M>
 int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg& d, long long prior_visits) {
     constexpr int A = M::kActions;
@@ -401,8 +403,9 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     if (bound_raw > 2000000000LL) return fail(MCTSB200_ERR_CAPACITY, "visit counts may exceed 32 bits (clear_tree to start over)");
 
     // log table: det_log(N), N < log_tab_n (grown lazily, shared by all configurations)
-    const int want = (int)std::min<long long>(bound + 1, 1 << 20);
+    int want = (int)std::min<long long>(bound + 1, kUcbTabMax);
     if (want > ctx->log_tab_n) {
+        want = (int)std::min<long long>(std::max<long long>(want, 2LL * ctx->log_tab_n), kUcbTabMax);  // kept trees: grow in doublings
         std::vector<double> tab((size_t)want), stab((size_t)want), rtab((size_t)want);
         for (int i = 0; i < want; ++i) {
             tab[(size_t)i] = det_log((double)i);
@@ -511,7 +514,7 @@ int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long pr
         if (KIND == MCTSB200_KIND_DPW && !(cfg->check_repeat_state && cfg->check_repeat_action)) return -1;  // unmerged nodes: tile kernel
         // the kernel indexes the UCB tables without a range check: every visit count must be inside them
         const long long bound = 4LL * std::max<long long>(cfg->init_N, 0) + prior_visits + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1;
-        if (bound + 1 > (1LL << 20)) return -1;
+        if (bound + 1 > kUcbTabMax) return -1;
         if (fast_smem_bytes<M>(MdpAccess<M>::params(ctx), std::max(cfg->depth, 1), 64) > kFastSmemLimit) return -1;
         switch (cfg->rollout_policy) {
             case MCTSB200_POLICY_RANDOM: return FAST_POLICY_RANDOM;
@@ -694,12 +697,13 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         if (KIND == MCTSB200_KIND_UCT) {
             auto kernel = finalize_rows_kernel<M>;
             MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (const FastRow*)st.rows_fast.p, args.order,
-                            (const uint16_t*)st.map.p, (Row<M>*)st.rows.p, st.geo.NS, args.n_slots);
+                            (const uint16_t*)st.map.p, (Row<M>*)st.rows.p, st.geo.NS, args.n_slots, args.counters + CNT_MAX_VISITS);
         } else {
             auto kernel = dpw_finalize_kernel<M>;
             MCTSB200_LAUNCH(kernel, (unsigned)((args.n_slots + 127) / 128), 128, 0, ctx->stream, (const FastRow*)st.rows_fast.p,
                             (const DpwTransRow*)st.trans_fast.p, args.order, (const uint16_t*)st.map.p, args.mdp, (TreeHeader*)st.hdr.p,
-                            (Row<M>*)st.rows.p, (Aux<M>*)st.aux.p, (TransRec*)st.trans.p, st.geo.NS, st.geo.NT, args.n_slots);
+                            (Row<M>*)st.rows.p, (Aux<M>*)st.aux.p, (TransRec*)st.trans.p, st.geo.NS, st.geo.NT, args.n_slots,
+                            args.counters + CNT_MAX_VISITS);
         }
         CUDA_TRY(cudaGetLastError());
         ++launches;
@@ -717,7 +721,8 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaEventElapsedTime(&kernel_ms, ctx->ev0, ctx->ev1));
     st.valid = true;
-    st.visits = prior_visits + (long long)done * std::max(cfg->depth, 1);
+    // bound of the visit counts now in the trees: exact after a fast-kernel call, else one visit per backup
+    st.visits = fast >= 0 ? (long long)h_cnt[CNT_MAX_VISITS] : prior_visits + (long long)done * std::max(cfg->depth, 1);
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         stats->n_trees = n_trees;

@@ -159,7 +159,9 @@ struct Geometry {
 
 enum CounterId {
     CNT_SIMULATIONS = 0, CNT_LEVELS, CNT_CHILDREN_SEEN, CNT_STATE_INSERTS, CNT_ACTION_INSERTS, CNT_ROLLOUTS, CNT_ROLLOUT_STEPS,
-    CNT_TRANS_SAMPLES, CNT_SELECT_EXACT, CNT_COUNT
+    CNT_TRANS_SAMPLES, CNT_SELECT_EXACT,
+    CNT_MAX_VISITS,  // not a sum: the largest node visit count, written by the fast kernels' finalize pass
+    CNT_COUNT
 };
 
 // device view of the solver configuration

@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
 template <class M>
 __global__ void dpw_finalize_kernel(const FastRow* rows_fast, const DpwTransRow* trans_fast, const int* order, const uint16_t* seq,
                                     const typename M::Params mdp, TreeHeader* hdr, Row<M>* rows, Aux<M>* aux, TransRec* trans, int NS, int NT,
-                                    long long n_slots) {
+                                    long long n_slots, unsigned long long* max_visits) {
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const long long tree = order ? (long long)order[slot] : slot;
@@ -444,7 +444,7 @@ __global__ void dpw_finalize_kernel(const FastRow* rows_fast, const DpwTransRow*
     Row<M>* orow = rows + tree * NS;
     Aux<M>* oaux = aux + tree * NS;
     TransRec* otr = trans + tree * NT;
-    int n_trans = 0;
+    int n_trans = 0, most = 0;
     for (int c = 0; c < NS; ++c) {
         const FastRow fr = rows_fast[wbase + (long long)c * 32];
         Row<M> out;
@@ -481,12 +481,14 @@ __global__ void dpw_finalize_kernel(const FastRow* rows_fast, const DpwTransRow*
             }
         }
         out.total_n = tot;
+        most = tot > most ? tot : most;
         out.packed = pk;
         out.key = (typename M::Key)sq[c];
         orow[c] = out;
         oaux[c] = ax;
     }
     hdr[tree].n_trans = n_trans;
+    if ((unsigned long long)most > *(volatile unsigned long long*)max_visits) atomicMax(max_visits, (unsigned long long)most);
 }
 
 template <class M>

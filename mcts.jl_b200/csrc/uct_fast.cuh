@@ -421,7 +421,8 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 // equal --, all-children label word, key = 1-based insertion sequence number), which is what decide_kernel, the root
 // queries and the tree export read. One thread per (slot, state); consecutive threads read consecutive lanes.
 template <class M>
-__global__ void finalize_rows_kernel(const FastRow* rows_fast, const int* order, const uint16_t* seq, Row<M>* rows, int NS, long long n_slots) {
+__global__ void finalize_rows_kernel(const FastRow* rows_fast, const int* order, const uint16_t* seq, Row<M>* rows, int NS, long long n_slots,
+                                     unsigned long long* max_visits) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // ((warp * NS) + state) * 32 + lane
     const long long warp = i / ((long long)NS * 32);
     const int state = (int)((i / 32) % NS), lane = (int)(i & 31);
@@ -445,6 +446,8 @@ __global__ void finalize_rows_kernel(const FastRow* rows_fast, const int* order,
     out.packed = present ? pk : 0u;
     out.key = (typename M::Key)seq[tree * NS + state];
     rows[tree * NS + state] = out;
+    // the largest visit count bounds the next call's UCB-table indices when the trees are kept
+    if (present && (unsigned long long)tot > *(volatile unsigned long long*)max_visits) atomicMax(max_visits, (unsigned long long)tot);
 }
 
 template <class M>

@@ -49,6 +49,7 @@ static inline int __any_sync(unsigned, int p) { return p; }
 static inline long long __double_as_longlong(double x) { long long u; std::memcpy(&u, &x, 8); return u; }
 static inline double __longlong_as_double(long long u) { double x; std::memcpy(&x, &u, 8); return x; }
 template <class T, class U> static inline T atomicAdd(T* p, U v) { T old = *p; *p += (T)v; return old; }
+template <class T, class U> static inline T atomicMax(T* p, U v) { T old = *p; if ((T)v > old) *p = (T)v; return old; }
 template <class T, class U> static inline T atomicOr(T* p, U v) { T old = *p; *p |= (T)v; return old; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 struct uint2 { unsigned x, y; };
