@@ -193,6 +193,23 @@ end
 action(p::B200Planner, s) = first(action_info(p, s))
 MCTS.clear_tree!(p::B200Planner) = check(ccall((:mctsb200_clear_trees, LIB), Int32, (Ptr{Cvoid},), p.ctx.h))
 
+# ---- simulate(RolloutSimulator(max_steps = T), mdp, planner, s0) for a batch of start states, on the device ----------
+"Closed-loop episodes (bench/non-terminal_gw.jl:18,31): returns (discounted returns, steps taken, final states)."
+function simulate_batch(sim::RolloutSimulator, p::B200Planner, starts::AbstractVector; env_seed::Integer = 0, episode_index_base::Integer = 0)
+    sim.max_steps === nothing && error("RolloutSimulator needs max_steps for the device episode loop")
+    cfg = Ref(cfg_from(p.solver, p.mdp))
+    n = length(starts)
+    s0 = collect(starts); sT = similar(s0)
+    ret = Vector{Float64}(undef, n); steps = Vector{Int32}(undef, n)
+    GC.@preserve s0 sT ret steps begin
+        check(ccall((:mctsb200_run_episodes, LIB), Int32,
+                    (Ptr{Cvoid}, Ref{SolverCfg}, Int32, Ptr{Cvoid}, Int64, Csize_t, Int32, UInt64, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Cvoid}, Ref{PlanStats}),
+                    p.ctx.h, cfg, p.mdp_id, pointer(s0), n, state_bytes(p), sim.max_steps, env_seed, episode_index_base, ret, steps, pointer(sT), p.stats))
+    end
+    return ret, steps, sT
+end
+POMDPs.simulate(sim::RolloutSimulator, mdp::MDP, p::B200Planner, s0) = first(simulate_batch(sim, p, [s0]))[1]
+
 # ---- info[:tree]: the MCTSTree / DPWTree vectors, exported on demand (two-call pattern) -------------------
 struct DeviceTree; planner::B200Planner; root_i::Int; end
 struct TreeSizes; n_state_nodes::Int64; n_action_nodes::Int64; n_transitions::Int64; state_bytes::Int64; end
