@@ -68,6 +68,7 @@ struct Storage {
     bool direct = false;  // rows indexed by the state's dense index (uct_fast.cuh); Row::key holds the insertion sequence number
     bool keep = false;    // the trees were built with reuse_tree / keep_tree and may be continued by the next plan call
     long long visits = 0; // upper bound of the visits any node of the kept trees has received so far
+    double q_bound = 0;   // bound of |Q| in the kept trees (DevCfg::q_bound of the calls that built them)
     int kind = 0, mdp_id = 0;
     long long n_trees = 0;
     Geometry geo{};
@@ -95,6 +96,8 @@ struct mctsb200_ctx {
     Storage st;
     DevBuf counters, log_tab, sqrtlog_tab, rsqrt_tab, nmin_state, init_q, init_n, value_tab, io_roots, io_action, io_bestq, io_status, sums;
     DevBuf order, order_bins, policy_tab;
+    double gw_reward_max = 0.0;
+    bool gw_fast_det = false;
     DevBuf ep_states, ep_disc, ep_ret, ep_steps, ep_active, ep_count;
     int log_tab_n = 0;
 };
@@ -115,6 +118,8 @@ struct MdpAccess<GridWorldDev> {
     }
     static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_GW_SEEK; }
     static bool fast_ready(const mctsb200_ctx* c) { return c->gw_dev.fast_tt != nullptr; }
+    static double reward_bound(const mctsb200_ctx* c) { return c->gw_reward_max; }  // max |reward(s, a)|
+    static bool fast_deterministic(const mctsb200_ctx* c) { return c->gw_fast_det; }   // every FastEntry has one outcome
     // Deterministic transitions + a deterministic rollout policy + vanilla UCT (DPW draws random actions): trees planned
     // from equal root states are then identical whatever their Philox streams, so lanes that share a root run in lockstep.
     static bool lockstep(const mctsb200_ctx* c, const mctsb200_solver_cfg* cfg) {
@@ -143,6 +148,7 @@ struct MdpAccess<MountainCarDev> {
     }
     static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_MC_ENERGY; }
     static bool lockstep(const mctsb200_ctx*, const mctsb200_solver_cfg*) { return false; }
+    static double reward_bound(const mctsb200_ctx*) { return NAN; }
 };
 
 // For every (boundary class, action): the positions where the reference's sampling expression
@@ -347,6 +353,12 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
         const double g = MdpAccess<M>::params(ctx).discount;  // (M::discount is a device function)
         const int steps = std::max(cfg->rollout_max_depth, cfg->depth) + 1;
         d.disc_always_positive = (cfg->rollout_eps == 0.0 && g > 0.0 && g <= 1.0 && std::pow(g, (double)steps) > 1e-300) ? 1 : 0;
+        // |Q| <= max(|init_Q|, max|r| * sum_{t < H} g^t): every Q is init_Q or a running mean of discounted returns over at most
+        // H = depth + rollout steps rewards (a little slack for the rounding of the running mean)
+        const double H = (double)std::max(cfg->depth, 1) + (double)std::max(cfg->rollout_max_depth == -1 ? cfg->depth : cfg->rollout_max_depth, 0);
+        const double geo = (g >= 0.0 && g < 1.0) ? std::min(H, 1.0 / (1.0 - g)) : (g == 1.0 ? H : NAN);
+        d.q_bound = std::fmax(std::fabs(cfg->init_Q), MdpAccess<M>::reward_bound(ctx) * geo) * 1.0009765625;
+        if (!std::isfinite(cfg->init_Q) || !std::isfinite(MdpAccess<M>::reward_bound(ctx) * geo)) d.q_bound = NAN;
     }
     d.seed = cfg->seed;
     d.depth = cfg->depth;
@@ -548,6 +560,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     int32_t rc = build_dev_cfg<M>(ctx, cfg, dcfg, prior_visits);
     if (rc) return rc;
     const int fast = fast_variant<M, KIND>(ctx, cfg, prior_visits);
+    if (may_reuse) dcfg.q_bound = (std::isnan(st.q_bound) || std::isnan(dcfg.q_bound)) ? NAN : std::max(dcfg.q_bound, st.q_bound);
     bool reused = false;
     rc = setup_storage<M>(ctx, cfg, n_trees, fast >= 0, &reused);
     if (rc) return rc;
@@ -648,7 +661,13 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
                 const int block = fast_block ? fast_block : fast_block_threads<M>(ctx, per_sm, args.geo.depth);
                 const int grid = (int)((args.n_slots + block - 1) / block);
                 const size_t smem = fast_smem_bytes<M>(args.mdp, args.geo.depth, block);
-                if (KIND == MCTSB200_KIND_UCT) return launch_uct_fast<M>(args, fast, grid, block, smem, ctx->stream);
+                if (KIND == MCTSB200_KIND_UCT) {
+                    // successors-ahead descent: only where the extra lookups land in idle issue slots
+                    const bool ahead = env_enabled("MCTSB200_AHEAD", MdpAccess<M>::lockstep(ctx, cfg) || args.n_slots <= 128LL * ctx->sm_count);
+                    // single-outcome transitions: no random words for them at all
+                    const bool det = ahead && MdpAccess<M>::fast_deterministic(ctx) && env_enabled("MCTSB200_DET", true);
+                    return launch_uct_fast<M>(args, fast, det ? FAST_MODE_DET : ahead ? FAST_MODE_AHEAD : FAST_MODE_PLAIN, grid, block, smem, ctx->stream);
+                }
                 return launch_dpw_fast<M>(args, fast, grid, block, smem, ctx->stream);
             }
         }
@@ -722,6 +741,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     CUDA_TRY(cudaEventElapsedTime(&kernel_ms, ctx->ev0, ctx->ev1));
     st.valid = true;
     // bound of the visit counts now in the trees: exact after a fast-kernel call, else one visit per backup
+    st.q_bound = dcfg.q_bound;
     st.visits = fast >= 0 ? (long long)h_cnt[CNT_MAX_VISITS] : prior_visits + (long long)done * std::max(cfg->depth, 1);
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
@@ -1218,7 +1238,7 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
                     e.d = (uint32_t)((cells - c) & 0xff);  // plateau 0 -> terminal state
                     if (info[(size_t)c].term_from) continue;  // Deterministic(terminal state)
                     const GridWorldDev::Thresholds& T = thr[info[(size_t)c].row + a];
-                    if (T.t[3] != 0xffffffffu) ok = false;
+                    if (T.t[3] != 0xffffffffu || T.t[0] > T.t[1] || T.t[1] > T.t[2]) ok = false;  // (fast_gen relies on ascending thresholds)
                     e.d = 0;
                     for (int i = 0; i < 3; ++i) e.t[i] = T.t[i];
                     for (int i = 0; i < 4; ++i) e.d |= (uint32_t)(dlt[(T.codes >> (4 * i)) & 15u] & 0xff) << (8 * i);
@@ -1227,6 +1247,9 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
             // a reward of -0.0 could make a running sum -0.0, for which adding +0.0 is not the identity: always add then
             if (neg_zero)
                 for (int i = 0; i < 4; ++i) ctx->gw_dev.fast_rbits[i] = 0xffffffffu;
+            ctx->gw_fast_det = true;
+            for (const auto& e : fast)
+                if (e.t[0] != 0xffffffffu) ctx->gw_fast_det = false;
             if (ok) {
                 CUDA_TRY(ctx->gw_fast.ensure(fast.size() * sizeof(GridWorldDev::FastEntry)));
                 CUDA_TRY(cudaMemcpy(ctx->gw_fast.p, fast.data(), fast.size() * sizeof(GridWorldDev::FastEntry), cudaMemcpyHostToDevice));
@@ -1238,6 +1261,8 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
         CUDA_TRY(cudaMemcpy(ctx->gw_reward.p, info.data(), info.size() * sizeof(GridWorldDev::CellInfo), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(ctx->gw_term.p, thr.data(), thr.size() * sizeof(GridWorldDev::Thresholds), cudaMemcpyHostToDevice));
         ctx->gw_host = p;
+        ctx->gw_reward_max = 0.0;
+        for (const auto& ci : info) ctx->gw_reward_max = std::isfinite(ci.reward) ? std::max(ctx->gw_reward_max, std::fabs(ci.reward)) : INFINITY;
         ctx->gw_dev.nx = p.nx;
         ctx->gw_dev.ny = p.ny;
         ctx->gw_dev.ncells = cells;

@@ -192,6 +192,7 @@ struct DevCfg {
     int pparam[4];
     int rollout_max_depth;
     int enable_action_pw, enable_state_pw, check_repeat_state, maintain_lookup;
+    double q_bound;              // fast kernels: bound of |Q| over everything this search (and the kept trees) can hold; NaN = none
     int disc_always_positive;    // eps == 0 and discount^steps cannot underflow: the rollout guard `disc > eps` is always true
 };
 

@@ -1,12 +1,12 @@
-// Instantiates the shared-memory lane-per-tree kernels (uct_fast.cuh, dpw_fast.cuh) for SimpleGridWorld, one variant
-// per rollout-policy kind.
-#include "dpw_fast.cuh"
+// Instantiates the shared-memory lane-per-tree UCT kernel (uct_fast.cuh) for SimpleGridWorld: one variant per
+// rollout-policy kind and descent mode.
+#include "uct_fast.cuh"
 
 namespace mctsb200 {
 
-template <class M, int POLICY>
+template <class M, int POLICY, int MODE>
 static int32_t launch_fast_one(const KernelArgs<M>& args, int grid, int block, size_t smem, cudaStream_t stream) {
-    auto kernel = uct_fast_kernel<M, POLICY>;
+    auto kernel = uct_fast_kernel<M, POLICY, MODE>;
 #ifndef MCTSB200_HOST_EMU
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MCTSB200_ERR_CUDA;
 #endif
@@ -14,31 +14,22 @@ static int32_t launch_fast_one(const KernelArgs<M>& args, int grid, int block, s
     return MCTSB200_OK;
 }
 
-template <>
-int32_t launch_uct_fast<GridWorldDev>(const KernelArgs<GridWorldDev>& args, int policy, int grid, int block, size_t smem, cudaStream_t stream) {
+template <class M, int MODE>
+static int32_t launch_fast_policy(const KernelArgs<M>& args, int policy, int grid, int block, size_t smem, cudaStream_t stream) {
     switch (policy) {
-        case FAST_POLICY_RANDOM: return launch_fast_one<GridWorldDev, FAST_POLICY_RANDOM>(args, grid, block, smem, stream);
-        case FAST_POLICY_CONSTANT: return launch_fast_one<GridWorldDev, FAST_POLICY_CONSTANT>(args, grid, block, smem, stream);
-        default: return launch_fast_one<GridWorldDev, FAST_POLICY_TABLE>(args, grid, block, smem, stream);
+        case FAST_POLICY_RANDOM: return launch_fast_one<M, FAST_POLICY_RANDOM, MODE>(args, grid, block, smem, stream);
+        case FAST_POLICY_CONSTANT: return launch_fast_one<M, FAST_POLICY_CONSTANT, MODE>(args, grid, block, smem, stream);
+        default: return launch_fast_one<M, FAST_POLICY_TABLE, MODE>(args, grid, block, smem, stream);
     }
 }
 
-template <class M, int POLICY>
-static int32_t launch_dpw_fast_one(const KernelArgs<M>& args, int grid, int block, size_t smem, cudaStream_t stream) {
-    auto kernel = dpw_fast_kernel<M, POLICY>;
-#ifndef MCTSB200_HOST_EMU
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MCTSB200_ERR_CUDA;
-#endif
-    MCTSB200_LAUNCH(kernel, (unsigned)grid, (unsigned)block, smem, stream, args);
-    return MCTSB200_OK;
-}
-
 template <>
-int32_t launch_dpw_fast<GridWorldDev>(const KernelArgs<GridWorldDev>& args, int policy, int grid, int block, size_t smem, cudaStream_t stream) {
-    switch (policy) {
-        case FAST_POLICY_RANDOM: return launch_dpw_fast_one<GridWorldDev, FAST_POLICY_RANDOM>(args, grid, block, smem, stream);
-        case FAST_POLICY_CONSTANT: return launch_dpw_fast_one<GridWorldDev, FAST_POLICY_CONSTANT>(args, grid, block, smem, stream);
-        default: return launch_dpw_fast_one<GridWorldDev, FAST_POLICY_TABLE>(args, grid, block, smem, stream);
+int32_t launch_uct_fast<GridWorldDev>(const KernelArgs<GridWorldDev>& args, int policy, int mode, int grid, int block, size_t smem,
+                                      cudaStream_t stream) {
+    switch (mode) {
+        case FAST_MODE_DET: return launch_fast_policy<GridWorldDev, FAST_MODE_DET>(args, policy, grid, block, smem, stream);
+        case FAST_MODE_AHEAD: return launch_fast_policy<GridWorldDev, FAST_MODE_AHEAD>(args, policy, grid, block, smem, stream);
+        default: return launch_fast_policy<GridWorldDev, FAST_MODE_PLAIN>(args, policy, grid, block, smem, stream);
     }
 }
 

@@ -111,18 +111,41 @@ struct GridWorldDev {
         return (((cell & 64) ? hi : lo) >> (cell & 31)) & 1u;
     }
     __device__ __forceinline__ static double fast_reward(const FastTables& ft, int cell) { return ft.reward[cell]; }
+    // PRMT with sign-replicating selector nibbles (the __byte_perm intrinsic only honours three bits per nibble)
+    __device__ __forceinline__ static int prmt_sext(uint32_t d, uint32_t sel) {
+#ifdef MCTSB200_HOST_EMU
+        return (int)__byte_perm(d, 0u, sel);  // (the emulator's shim implements the full PRMT selector)
+#else
+        uint32_t r;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(d), "r"(0u), "r"(sel));
+        return (int)r;
+#endif
+    }
+    // (the thresholds ascend, so the last one exceeded names the outcome; the byte-permute selector j | 0x8880 + 0x1110 j picks
+    // delta byte j sign-extended)
     __device__ __forceinline__ static int fast_gen(const FastTables& ft, int cell, int a, uint32_t w) {
         const uint4 e = *reinterpret_cast<const uint4*>(ft.tt + (cell * 4 + a));
-        const int j = (int)(w > e.x) + (int)(w > e.y) + (int)(w > e.z);
-        return cell + (int)(signed char)(e.w >> (8 * j));
+        uint32_t sel = 0x8880u;
+        if (w > e.x) sel = 0x9991u;
+        if (w > e.y) sel = 0xaaa2u;
+        if (w > e.z) sel = 0xbbb3u;
+        return cell + prmt_sext(e.w, sel);
+    }
+    // every (state, action) has the single outcome of plateau 0 (Params::fast_det, checked by the host)
+    __device__ __forceinline__ static int fast_gen_det(const FastTables& ft, int cell, int a) {
+        return cell + (int)(signed char)(ft.tt[cell * 4 + a].d & 0xffu);
     }
     // Same, also returning the outcome index j < 4. Distinct outcome indices of one (state, action) are distinct
     // successors (the plateaus of the sampling table are [stay, up, down, left, right] in that order, each at most once),
     // so an action node's set of seen successors is a 4-bit mask (dpw_fast.cuh).
     __device__ __forceinline__ static int fast_gen(const FastTables& ft, int cell, int a, uint32_t w, int& j) {
         const uint4 e = *reinterpret_cast<const uint4*>(ft.tt + (cell * 4 + a));
-        j = (int)(w > e.x) + (int)(w > e.y) + (int)(w > e.z);
-        return cell + (int)(signed char)(e.w >> (8 * j));
+        uint32_t sel = 0x8880u;
+        if (w > e.x) sel = 0x9991u;
+        if (w > e.y) sel = 0xaaa2u;
+        if (w > e.z) sel = 0xbbb3u;
+        j = (int)(sel & 3u);
+        return cell + prmt_sext(e.w, sel);
     }
     __device__ __forceinline__ static int fast_outcome(const FastTables& ft, int cell, int a, int j) {
         return cell + (int)(signed char)(ft.tt[cell * 4 + a].d >> (8 * j));

@@ -35,6 +35,8 @@
 #ifdef MCTSB200_PHASE_TIMING
 #include <cstdio>
 #endif
+#include <type_traits>
+
 #include "search.cuh"
 
 namespace mctsb200 {
@@ -50,6 +52,7 @@ __device__ __forceinline__ unsigned __smid() {
 constexpr int kFastMaxThreads = 512;
 constexpr int kFastTab = 2048;  // entries of sqrt(log N) and 1/sqrt(n) staged in shared memory
 enum { FAST_POLICY_RANDOM = 0, FAST_POLICY_CONSTANT = 1, FAST_POLICY_TABLE = 2 };
+enum { FAST_MODE_PLAIN = 0, FAST_MODE_AHEAD = 1, FAST_MODE_DET = 2 };
 
 // words b0..b3 of block `blk` of stream (seed, tree, iteration, stream_id) -- the contract of include/mctsb200.h
 __device__ __forceinline__ void philox_block(uint64_t seed, uint64_t tree, uint32_t it, uint32_t stream_id, uint32_t blk, uint32_t& b0, uint32_t& b1,
@@ -108,10 +111,17 @@ static inline size_t fast_smem_bytes(const typename M::Params& p, int depth, int
            sizeof(uint4) * (size_t)depth * (size_t)block_threads;
 }
 
-template <class M, int POLICY>
+// MODE selects the descent / transition code:
+//   FAST_MODE_PLAIN   the chosen action's successor is sampled after the selection
+//   FAST_MODE_AHEAD   the successors of all A actions are looked up while the node's row is still in flight (pays when the
+//                     warps have idle issue slots: lanes in lockstep, or few warps per SM)
+//   FAST_MODE_DET     AHEAD for an MDP whose every transition has a single outcome (host-checked): no random word is drawn
+//                     for transitions at all -- the sampled successor does not depend on it
+template <class M, int POLICY, int MODE>
 __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __grid_constant__ KernelArgs<M> args) {
     constexpr int A = M::kActions;
     static_assert(A == 4, "a row holds exactly four children");
+    constexpr bool AHEAD = MODE != FAST_MODE_PLAIN, DET = MODE == FAST_MODE_DET;
     using SG = Search<M, 1>;
 #ifdef MCTSB200_HOST_EMU
     static unsigned char fast_smem[256 * 1024];
@@ -140,7 +150,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
 #endif
     for (int i = st0; i < kFastTab; i += st1) {
         s_rsqrt[i] = i < cfg.rsqrt_tab_n ? cfg.rsqrt_tab[i] : 0.0;
-        s_sqrtlog[i] = i < cfg.log_tab_n ? cfg.sqrtlog_tab[i] : 0.0;
+        s_sqrtlog[i] = i < cfg.log_tab_n ? DM_MUL(cfg.c, cfg.sqrtlog_tab[i]) : 0.0;  // c * sqrt(log N), the product the scores start from
     }
     if (POLICY == FAST_POLICY_TABLE)
         for (int i = st0; i < n_states; i += st1) s_pol[i] = cfg.policy_table[i];
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
         const uint64_t tree_index = (uint64_t)(args.tree_index_base + tree);
         const uint64_t seed = cfg.seed;
         const int TERM = ft.term;
-        const double gamma = M::discount(args.mdp), eps = cfg.rollout_eps, c_ucb = cfg.c;
+        const double gamma = M::discount(args.mdp), eps = cfg.rollout_eps, c_ucb = cfg.c, q_bound = cfg.q_bound;
         unsigned n_levels = 0, n_inserts = 0, n_rollouts = 0, n_sims = 0, n_exact = 0;
         unsigned long long n_steps = 0;
 
@@ -206,14 +216,38 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                 load_row(row_at(root), k);
                 for (;;) {
                     PT_CLOCK(l0);
+                    // While this node's row is still on its way from L2: everything that does not need it -- the random word of
+                    // this level and the successor each action would lead to (sp, r = @gen(:sp,:r)(mdp, s, a, rng) for all a).
+                    uint32_t w = 0;
+                    if (!DET) {
+                        if ((top & 3) == 0) philox_block(seed, tree_index, (uint32_t)it, 0u, (uint32_t)(top >> 2), b0, b1, b2, b3);
+                        w = (top & 2) ? ((top & 1) ? b3 : b2) : ((top & 1) ? b1 : b0);  // word `top` of stream 0
+                    }
+                    int spc[A];
+                    if (AHEAD) {
+#pragma unroll
+                        for (int j = 0; j < A; ++j) spc[j] = DET ? M::fast_gen_det(ft, cell, j) : M::fast_gen(ft, cell, j, w);
+                    }
+#ifdef MCTSB200_PHASE_TIMING
+                    if (AHEAD && spc[0] + spc[1] + spc[2] + spc[3] < 0) break;  // (never: makes the clock below wait for the successors)
+                    PT_CLOCK(lA);
+                    if (k[0].tag == 0xdeadbeefu) break;  // (never: makes the clock below wait for the row)
+                    PT_CLOCK(lB);
+                    PT_LV(2, lA - l0);
+                    PT_LV(0, lB - lA);
+#endif
+                    // first use of the row
+                    if (k[0].tag == 0) {  // new node: estimate_value(sp, depth-1), also when sp is terminal
+                        insert(cell);
+                        leaf = true;
+                        break;
+                    }
                     if (cell == TERM) break;  // isterminal: value 0.0, no statistics update at this node
                     if (d == 0) {
                         leaf = true;  // estimate_value(s, 0)
                         break;
                     }
                     ++n_levels;
-                    if ((top & 3) == 0) philox_block(seed, tree_index, (uint32_t)it, 0u, (uint32_t)(top >> 2), b0, b1, b2, b3);
-                    const uint32_t w = (top & 2) ? ((top & 1) ? b3 : b2) : ((top & 1) ? b1 : b0);  // word `top` of stream 0
 
                     // ---- best_sanode_UCB (src/vanilla.jl:354-386) ----
                     int slot;
@@ -225,7 +259,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                         const int N = (k[0].n + k[1].n) + (k[2].n + k[3].n);  // total_n(snode): always the sum over its children
                         double S[A], T[A], cs;
                         if (N < kFastTab) {  // then every n_j is below kFastTab too: all five factors come from shared memory
-                            cs = DM_MUL(c_ucb, s_sqrtlog[N]);
+                            cs = s_sqrtlog[N];
 #pragma unroll
                             for (int j = 0; j < A; ++j) T[j] = DM_MUL(cs, s_rsqrt[k[j].n]);
                         } else {
@@ -235,9 +269,9 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                         }
 #pragma unroll
                         for (int j = 0; j < A; ++j) S[j] = DM_ADD(k[j].q, T[j]);
-                        const double mag = DM_ADD(DM_ADD(DM_ADD(fabs(k[0].q), T[0]), DM_ADD(fabs(k[1].q), T[1])),
-                                                  DM_ADD(DM_ADD(fabs(k[2].q), T[2]), DM_ADD(fabs(k[3].q), T[3])));
-                        const double margin = DM_MUL(5.6843418860808015e-14, mag);  // 2^-44 * sum(|q| + term); NaN if any input is
+                        // 2^-44 * sum(|q_j| + |term_j|) <= 2^-42 * (max|q| + |c sqrt(log N)|): q_bound is the host's bound of every Q
+                        // value this search can produce (NaN when there is none, which sends every selection to the exact path)
+                        const double margin = DM_MUL(2.2737367544323206e-13, DM_ADD(q_bound, fabs(cs)));
                         // two-round tournament; equal scores keep the lower index, like the reference's strict '>' scan
                         const bool m01 = S[1] > S[0], m23 = S[3] > S[2];
                         const double w01 = m01 ? S[1] : S[0], l01 = m01 ? S[0] : S[1];
@@ -277,13 +311,12 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                         }
                     }
 
-                    PT_CLOCK(l1);
-                    // sp, r = @gen(:sp,:r)(mdp, s, a, rng); the reward is re-read from the table during backup
-                    const int sp = M::fast_gen(ft, cell, slot, w);
+                    // the successor of the chosen action; the reward is re-read from the table during backup
+                    const int sp = AHEAD ? (slot == 0 ? spc[0] : slot == 1 ? spc[1] : slot == 2 ? spc[2] : spc[3]) : M::fast_gen(ft, cell, slot, w);
 #ifdef MCTSB200_PHASE_TIMING
-                    if (sp < 0) break;  // (never: makes the clock below wait for the successor)
+                    if (sp < 0) break;  // (never: makes the clock below wait for the selection)
 #endif
-                    PT_CLOCK(l2);
+                    PT_CLOCK(l1);
                     // what the backup needs from this level
                     const int ns = slot == 0 ? k[0].n : slot == 1 ? k[1].n : slot == 2 ? k[2].n : k[3].n;
                     const double qs = slot == 0 ? k[0].q : slot == 1 ? k[1].q : slot == 2 ? k[2].q : k[3].q;
@@ -300,19 +333,10 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     cell = sp;
                     load_row(row_at(sp), k);
                     PT_CLOCK(l3);
-                    PT_LV(1, l1 - l0);
-                    PT_LV(2, l2 - l1);
-                    PT_LV(3, l3 - l2);
 #ifdef MCTSB200_PHASE_TIMING
-                    const bool fresh = k[0].tag == 0;
-                    PT_CLOCK(l4);
-                    PT_LV(0, l4 - l3);
+                    PT_LV(1, l1 - lB);
+                    PT_LV(3, l3 - l1);
 #endif
-                    if (k[0].tag == 0) {  // new node: estimate_value(sp, depth-1), also when sp is terminal
-                        insert(cell);
-                        leaf = true;
-                        break;
-                    }
                 }
                 PT_CLOCK(t1);
                 PT_TRIP(0, top);
@@ -327,29 +351,34 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     double disc = 1.0, r_total = 0.0;
                     int step = 1, cc = cell;
                     uint32_t blk = 0;
-                    // `disc > eps` of the reference's loop guard is provably always true for eps = 0 and these depths
-                    const bool dchk = !cfg.disc_always_positive;
-                    while ((!dchk || disc > eps) && cc != TERM && step <= max_steps) {
-                        uint32_t w[4];
-                        philox_block(seed, tree_index, (uint32_t)it, 1u, blk++, w[0], w[1], w[2], w[3]);
+                    // `disc > eps` of the reference's loop guard is provably always true for eps = 0 and these depths: that
+                    // version of the loop carries no FP64 compare
+                    auto run = [&](auto DCHK) {
+                        constexpr bool dchk = decltype(DCHK)::value;
+                        while ((!dchk || disc > eps) && cc != TERM && step <= max_steps) {
+                            uint32_t w[4] = {0u, 0u, 0u, 0u};
+                            if (!(DET && POLICY != FAST_POLICY_RANDOM)) philox_block(seed, tree_index, (uint32_t)it, 1u, blk++, w[0], w[1], w[2], w[3]);
 #pragma unroll
-                        for (int u = 0; u < kStepsPerBlock; ++u) {
-                            if (u > 0 && !((!dchk || disc > eps) && cc != TERM && step <= max_steps)) break;
-                            int act;
-                            uint32_t wg;
-                            if (POLICY == FAST_POLICY_RANDOM) {
-                                act = (int)__umulhi(w[2 * u], (uint32_t)A);  // rand(rng, actions(mdp, s))
-                                wg = w[2 * u + 1];
-                            } else {
-                                act = POLICY == FAST_POLICY_CONSTANT ? cfg.pparam[0] : (int)s_pol[cc];
-                                wg = w[u];
+                            for (int u = 0; u < kStepsPerBlock; ++u) {
+                                if (u > 0 && !((!dchk || disc > eps) && cc != TERM && step <= max_steps)) break;
+                                int act;
+                                uint32_t wg;
+                                if (POLICY == FAST_POLICY_RANDOM) {
+                                    act = (int)__umulhi(w[2 * u], (uint32_t)A);  // rand(rng, actions(mdp, s))
+                                    wg = w[2 * u + 1];
+                                } else {
+                                    act = POLICY == FAST_POLICY_CONSTANT ? cfg.pparam[0] : (int)s_pol[cc];
+                                    wg = w[u];
+                                }
+                                if (M::fast_has_reward(ft, cc)) r_total = DM_ADD(r_total, DM_MUL(disc, M::fast_reward(ft, cc)));
+                                cc = DET ? M::fast_gen_det(ft, cc, act) : M::fast_gen(ft, cc, act, wg);
+                                disc = DM_MUL(disc, gamma);
+                                ++step;
                             }
-                            if (M::fast_has_reward(ft, cc)) r_total = DM_ADD(r_total, DM_MUL(disc, M::fast_reward(ft, cc)));
-                            cc = M::fast_gen(ft, cc, act, wg);
-                            disc = DM_MUL(disc, gamma);
-                            ++step;
                         }
-                    }
+                    };
+                    if (cfg.disc_always_positive) run(std::false_type{});
+                    else run(std::true_type{});
                     n_steps += (unsigned)(step - 1);
                     v = r_total;
                 }
@@ -384,7 +413,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
         }
 #ifdef MCTSB200_PHASE_TIMING
         if ((threadIdx.x & 31) == 0 && n_sims)  // PT block warp smid | levels/iter steps/iter | cycles/iter: descent rollout backup | per level, step, level
-            printf("PT %d %d %d | %.2f %.2f | %lld %lld %lld | %.0f %.0f %.0f | level: rowwait %.0f select %.0f gen %.0f record+issue %.0f\n", (int)blockIdx.x,
+            printf("PT %d %d %d | %.2f %.2f | %lld %lld %lld | %.0f %.0f %.0f | level: rowwait %.0f select %.0f pre-gen %.0f record+issue %.0f\n", (int)blockIdx.x,
                    (int)(threadIdx.x >> 5), (int)__smid(), (double)trips[0] / n_sims, (double)trips[1] / n_sims, cyc[0] / n_sims, cyc[1] / n_sims,
                    cyc[2] / n_sims, (double)cyc[0] / (double)max(trips[0], 1LL), (double)cyc[1] / (double)max(trips[1], 1LL),
                    (double)cyc[2] / (double)max(trips[2], 1LL), (double)lv[0] / (double)max(trips[0], 1LL), (double)lv[1] / (double)max(trips[0], 1LL),
@@ -451,6 +480,6 @@ __global__ void finalize_rows_kernel(const FastRow* rows_fast, const int* order,
 }
 
 template <class M>
-int32_t launch_uct_fast(const KernelArgs<M>& args, int policy, int grid, int block, size_t smem, cudaStream_t stream);
+int32_t launch_uct_fast(const KernelArgs<M>& args, int policy, int mode, int grid, int block, size_t smem, cudaStream_t stream);
 
 }  // namespace mctsb200

@@ -8,6 +8,9 @@ for l in open(sys.argv[1]):
             import re
             print("ms_per_step", re.search(r'"ms_per_step": ([0-9.]+)', l).group(1))
         continue
+    if "level:" in l:
+        print(l.strip()[l.index("level:"):]) if len(rows) < 2 else None
+        l = l[:l.index("level:")]
     p = l.replace("|", " ").split()
     rows.append([float(x) for x in p[1:]])
 a = np.array(rows)  # block warp smid lv st cd cr cb pd pr pb

@@ -52,6 +52,17 @@ template <class T, class U> static inline T atomicAdd(T* p, U v) { T old = *p; *
 template <class T, class U> static inline T atomicMax(T* p, U v) { T old = *p; if ((T)v > old) *p = (T)v; return old; }
 template <class T, class U> static inline T atomicOr(T* p, U v) { T old = *p; *p |= (T)v; return old; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {  // PRMT, default mode
+    const uint64_t src = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t n = (s >> (4 * i)) & 0xfu;
+        uint32_t b = (uint32_t)(src >> (8 * (n & 7u))) & 0xffu;
+        if (n & 8u) b = (b & 0x80u) ? 0xffu : 0x00u;
+        r |= b << (8 * i);
+    }
+    return r;
+}
 struct uint2 { unsigned x, y; };
 
 namespace mctsb200_emu {

@@ -203,3 +203,14 @@ def test_episodes_mountaincar(gpu_ctx, oracle):
     starts = mountaincar_roots(40) + [(0.6, 0.0)]
     ret, steps, final, st = run_episodes_both(gpu_ctx, oracle, s, MC, starts, max_steps=8, env_seed=2)
     assert steps[-1] == 0 and ret[-1] == 0.0
+
+
+@pytest.mark.parametrize("ahead,det", [("0", "1"), ("1", "0"), ("1", "1")])
+def test_uct_both_descent_orders(gpu_ctx, oracle, monkeypatch, ahead, det):
+    monkeypatch.setenv("MCTSB200_AHEAD", ahead)
+    monkeypatch.setenv("MCTSB200_DET", det)
+    s = m.MCTSSolver(n_iterations=300, depth=20, exploration_constant=5.0, rng=3)
+    run_both(gpu_ctx, oracle, s, GW, gridworld_roots(200), compare_trees=range(0, 200, 17))
+    for pol in (m.ConstantPolicy("up"), m.SeekTarget((9, 3)), m.RandomSolver()):
+        s = m.MCTSSolver(n_iterations=300, depth=20, exploration_constant=5.0, estimate_value=m.RolloutEstimator(pol))
+        run_both(gpu_ctx, oracle, s, GW_DET, gridworld_roots(200), compare_trees=range(0, 200, 17))

@@ -57,6 +57,19 @@ def test_emu_uct_stochastic(emu_ctx, oracle):
     assert st.kernel_variant == 1  # the shared-memory lane-per-tree kernel
 
 
+@pytest.mark.parametrize("ahead,det", [("0", "1"), ("1", "0"), ("1", "1")])
+def test_emu_uct_both_descent_orders(emu_ctx, oracle, monkeypatch, ahead, det):
+    """successors looked up ahead of the selection (lockstep / small batches) or after it, with and without the
+    no-random-word transitions of a deterministic MDP: same trees"""
+    monkeypatch.setenv("MCTSB200_AHEAD", ahead)
+    monkeypatch.setenv("MCTSB200_DET", det)
+    s = m.MCTSSolver(n_iterations=150, depth=15, exploration_constant=5.0, rng=3)
+    run_both(emu_ctx, oracle, s, GW, gridworld_roots(40), compare_trees=range(0, 40, 7))
+    for pol in (m.SeekTarget((9, 3)), m.ConstantPolicy("left"), m.RandomSolver()):
+        s = m.MCTSSolver(n_iterations=150, depth=15, exploration_constant=5.0, estimate_value=m.RolloutEstimator(pol))
+        run_both(emu_ctx, oracle, s, GW_DET, gridworld_roots(40), compare_trees=range(0, 40, 7))
+
+
 def test_emu_generic_uct_kernel_still_matches(emu_ctx, oracle, monkeypatch):
     """MCTSB200_FAST=0 forces the tile kernel on the configurations the lean kernel normally takes."""
     monkeypatch.setenv("MCTSB200_FAST", "0")
