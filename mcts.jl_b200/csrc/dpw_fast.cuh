@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
 #endif
     for (int i = st0; i < kFastTab; i += st1) {
         s_rsqrt[i] = i < cfg.rsqrt_tab_n ? cfg.rsqrt_tab[i] : 0.0;
-        s_sqrtlog[i] = i < cfg.log_tab_n ? cfg.sqrtlog_tab[i] : 0.0;
+        s_sqrtlog[i] = i < cfg.log_tab_n ? DM_MUL(cfg.c, cfg.sqrtlog_tab[i]) : 0.0;  // c * sqrt(log N)
     }
     if (POLICY == FAST_POLICY_TABLE)
         for (int i = st0; i < n_states; i += st1) s_pol[i] = cfg.policy_table[i];
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                         } else {
                             double S[A], T[A], cs;
                             if (N < kFastTab) {
-                                cs = DM_MUL(c_ucb, s_sqrtlog[N]);
+                                cs = s_sqrtlog[N];
 #pragma unroll
                                 for (int t = 0; t < A; ++t) T[t] = t < nchild ? DM_MUL(cs, s_rsqrt[k[t].n]) : 0.0;
                             } else {
@@ -229,13 +229,10 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
 #pragma unroll
                                 for (int t = 0; t < A; ++t) T[t] = t < nchild ? DM_MUL(cs, __ldg(cfg.rsqrt_tab + k[t].n)) : 0.0;
                             }
-                            double mag = 0.0;
 #pragma unroll
-                            for (int t = 0; t < A; ++t) {
-                                S[t] = t < nchild ? DM_ADD(k[t].q, T[t]) : -CUDART_INF;
-                                if (t < nchild) mag = DM_ADD(mag, DM_ADD(fabs(k[t].q), T[t]));
-                            }
-                            const double margin = DM_MUL(5.6843418860808015e-14, mag);
+                            for (int t = 0; t < A; ++t) S[t] = t < nchild ? DM_ADD(k[t].q, T[t]) : -CUDART_INF;
+                            // 2^-44 * sum(|q| + |term|) <= 2^-42 * (max|q| + |c sqrt(log N)|), see uct_fast.cuh; NaN without a bound
+                            const double margin = DM_MUL(2.2737367544323206e-13, DM_ADD(cfg.q_bound, fabs(cs)));
                             const bool m01 = S[1] > S[0], m23 = S[3] > S[2];
                             const double w01 = m01 ? S[1] : S[0], l01 = m01 ? S[0] : S[1];
                             const double w23 = m23 ? S[3] : S[2], l23 = m23 ? S[2] : S[3];
@@ -351,29 +348,34 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                     double disc = 1.0, r_total = 0.0;
                     int step = 1, cc = cell;
                     uint32_t blk = 0;
-                    // `disc > eps` of the reference's loop guard is provably always true for eps = 0 and these depths
-                    const bool dchk = !cfg.disc_always_positive;
-                    while ((!dchk || disc > eps) && cc != TERM && step <= max_steps) {
-                        uint32_t w[4];
-                        philox_block(seed, tree_index, (uint32_t)it, 1u, blk++, w[0], w[1], w[2], w[3]);
+                    // `disc > eps` of the reference's loop guard is provably always true for eps = 0 and these depths: that
+                    // version of the loop carries no FP64 compare
+                    auto run = [&](auto DCHK) {
+                        constexpr bool dchk = decltype(DCHK)::value;
+                        while ((!dchk || disc > eps) && cc != TERM && step <= max_steps) {
+                            uint32_t w[4];
+                            philox_block(seed, tree_index, (uint32_t)it, 1u, blk++, w[0], w[1], w[2], w[3]);
 #pragma unroll
-                        for (int u = 0; u < kStepsPerBlock; ++u) {
-                            if (u > 0 && !((!dchk || disc > eps) && cc != TERM && step <= max_steps)) break;
-                            int ract;
-                            uint32_t wg;
-                            if (POLICY == FAST_POLICY_RANDOM) {
-                                ract = (int)__umulhi(w[2 * u], (uint32_t)A);  // rand(rng, actions(mdp, s))
-                                wg = w[2 * u + 1];
-                            } else {
-                                ract = POLICY == FAST_POLICY_CONSTANT ? cfg.pparam[0] : (int)s_pol[cc];
-                                wg = w[u];
+                            for (int u = 0; u < kStepsPerBlock; ++u) {
+                                if (u > 0 && !((!dchk || disc > eps) && cc != TERM && step <= max_steps)) break;
+                                int ract;
+                                uint32_t wg;
+                                if (POLICY == FAST_POLICY_RANDOM) {
+                                    ract = (int)__umulhi(w[2 * u], (uint32_t)A);  // rand(rng, actions(mdp, s))
+                                    wg = w[2 * u + 1];
+                                } else {
+                                    ract = POLICY == FAST_POLICY_CONSTANT ? cfg.pparam[0] : (int)s_pol[cc];
+                                    wg = w[u];
+                                }
+                                if (M::fast_has_reward(ft, cc)) r_total = DM_ADD(r_total, DM_MUL(disc, M::fast_reward(ft, cc)));
+                                cc = M::fast_gen(ft, cc, ract, wg);
+                                disc = DM_MUL(disc, gamma);
+                                ++step;
                             }
-                            if (M::fast_has_reward(ft, cc)) r_total = DM_ADD(r_total, DM_MUL(disc, M::fast_reward(ft, cc)));
-                            cc = M::fast_gen(ft, cc, ract, wg);
-                            disc = DM_MUL(disc, gamma);
-                            ++step;
                         }
-                    }
+                    };
+                    if (cfg.disc_always_positive) run(std::false_type{});
+                    else run(std::true_type{});
                     n_steps += (unsigned)(step - 1);
                     v = r_total;
                 }

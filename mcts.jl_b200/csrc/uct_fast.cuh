@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     PT_LV(2, lA - l0);
                     PT_LV(0, lB - lA);
 #endif
-                    // first use of the row
-                    if (k[0].tag == 0) {  // new node: estimate_value(sp, depth-1), also when sp is terminal
+                    // first use of the row (AHEAD; otherwise the row was checked as soon as it was requested, below)
+                    if (AHEAD && k[0].tag == 0) {  // new node: estimate_value(sp, depth-1), also when sp is terminal
                         insert(cell);
                         leaf = true;
                         break;
@@ -332,6 +332,11 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     --d;
                     cell = sp;
                     load_row(row_at(sp), k);
+                    if (!AHEAD && k[0].tag == 0) {  // (divergent lanes: leaving the loop here saves the trip to the top)
+                        insert(cell);
+                        leaf = true;
+                        break;
+                    }
                     PT_CLOCK(l3);
 #ifdef MCTSB200_PHASE_TIMING
                     PT_LV(1, l1 - lB);
