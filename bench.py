@@ -37,6 +37,9 @@ WORKLOADS = {
     # name: (mdp kwargs, solver kind, solver kwargs, n_roots)
     "config2-uct-gridworld-deterministic": dict(mdp="gw", mdp_kw=dict(tprob=1.0), kind="uct", policy="up",
                                                 solver_kw=dict(n_iterations=1000, depth=20, exploration_constant=5.0), n_roots=65536),
+    # the default SimpleGridWorld (tprob = 0.7) with the deterministic rollout policy: the other reading of BASELINE config 2
+    "config2-uct-gridworld-default": dict(mdp="gw", mdp_kw=dict(tprob=0.7), kind="uct", policy="up",
+                                          solver_kw=dict(n_iterations=1000, depth=20, exploration_constant=5.0), n_roots=65536),
     "config2-uct-gridworld-stochastic": dict(mdp="gw", mdp_kw=dict(tprob=0.7), kind="uct", policy="random",
                                              solver_kw=dict(n_iterations=1000, depth=20, exploration_constant=5.0), n_roots=65536),
     "config3-dpw-gridworld": dict(mdp="gw", mdp_kw=dict(tprob=0.7), kind="dpw", policy="random",

@@ -64,7 +64,8 @@ struct GridWorldDev {
     struct FastTables {
         const FastEntry* tt;   // shared memory, [ncells + 1][4]
         const double* reward;  // shared memory, [ncells + 1]
-        uint32_t rbits[4];     // bit c: reward(c) is not +0.0 (adding +0.0 is exact identity, so those cells skip the arithmetic)
+        const uint8_t* rflag;  // shared memory, [ncells + 1]: reward(c) is not +0.0 (adding +0.0 is the exact identity, so those
+                               // cells skip the arithmetic)
         int term;              // dense index of the terminal state
     };
 
@@ -83,7 +84,7 @@ struct GridWorldDev {
     static constexpr bool kFast = true;
     __host__ __device__ __forceinline__ static int fast_states(const Params& p) { return p.ncells + 1; }
     __host__ __device__ __forceinline__ static size_t fast_table_bytes(const Params& p) {
-        return ((sizeof(FastEntry) * 4 + sizeof(double)) * (size_t)(p.ncells + 1) + 15) / 16 * 16;
+        return ((sizeof(FastEntry) * 4 + sizeof(double) + 1) * (size_t)(p.ncells + 1) + 15) / 16 * 16;
     }
     // copies the tables into shared memory (all threads of the block; the caller synchronises); returns the
     // first free 16-byte aligned address
@@ -97,19 +98,19 @@ struct GridWorldDev {
 #else
         const int i0 = (int)threadIdx.x, di = (int)blockDim.x;
 #endif
+        uint8_t* flg = reinterpret_cast<uint8_t*>(rew + n);
         for (int i = i0; i < n * 4; i += di) dst[i] = src[i];
-        for (int i = i0; i < n; i += di) rew[i] = p.cells[i].reward;
+        for (int i = i0; i < n; i += di) {
+            rew[i] = p.cells[i].reward;
+            flg[i] = (uint8_t)((p.fast_rbits[i >> 5] >> (i & 31)) & 1u);
+        }
         ft.tt = reinterpret_cast<const FastEntry*>(smem);
         ft.reward = rew;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ft.rbits[i] = p.fast_rbits[i];
+        ft.rflag = flg;
         ft.term = p.ncells;
         return smem + fast_table_bytes(p);
     }
-    __device__ __forceinline__ static bool fast_has_reward(const FastTables& ft, int cell) {
-        const uint32_t lo = (cell & 32) ? ft.rbits[1] : ft.rbits[0], hi = (cell & 32) ? ft.rbits[3] : ft.rbits[2];
-        return (((cell & 64) ? hi : lo) >> (cell & 31)) & 1u;
-    }
+    __device__ __forceinline__ static bool fast_has_reward(const FastTables& ft, int cell) { return ft.rflag[cell] != 0; }
     __device__ __forceinline__ static double fast_reward(const FastTables& ft, int cell) { return ft.reward[cell]; }
     // PRMT with sign-replicating selector nibbles (the __byte_perm intrinsic only honours three bits per nibble)
     __device__ __forceinline__ static int prmt_sext(uint32_t d, uint32_t sel) {
