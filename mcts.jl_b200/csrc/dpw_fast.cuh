@@ -245,15 +245,13 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                             } else {
                                 const int nb = best_i == 0 ? k[0].n : best_i == 1 ? k[1].n : best_i == 2 ? k[2].n : k[3].n;
                                 const double qb = best_i == 0 ? k[0].q : best_i == 1 ? k[1].q : best_i == 2 ? k[2].q : k[3].q;
-                                bool need_exact = !(best == best) || best_i >= nchild;
-                                int tie_i = best_i;
+                                // (see uct_fast.cuh: identical (n, q) inside the margin = identical scores, and the tournament kept the
+                                // lowest index; absent slots score -Inf and are outside any finite margin)
+                                bool ok = (best == best) & (best_i < nchild);
 #pragma unroll
-                                for (int t = A - 1; t >= 0; --t) {
-                                    if (t < nchild && t != best_i && !(DM_SUB(best, S[t]) > margin)) {
-                                        if (k[t].n == nb && k[t].q == qb) tie_i = min(tie_i, t);
-                                        else need_exact = true;
-                                    }
-                                }
+                                for (int t = 0; t < A; ++t) ok &= (DM_SUB(best, S[t]) > margin) | ((k[t].n == nb) & (k[t].q == qb));
+                                const bool need_exact = !ok;
+                                const int tie_i = best_i;
                                 if (need_exact) {
                                     ++n_exact;
                                     typename SG::Kids kk;

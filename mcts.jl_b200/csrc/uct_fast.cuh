@@ -283,20 +283,17 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                         if (DM_SUB(best, o1) > margin && DM_SUB(best, o2) > margin) {
                             slot = best_i;
                         } else {
-                            // near-tie: children inside the margin with bit-identical (n, q) have bit-identical reference
-                            // scores (tie -> lowest index); anything else is decided by the reference's exact expression
+                            // near-tie: a child inside the margin with (n, q) bit-identical to the winner's has a bit-identical
+                            // score -- in the reference too -- and the tournament above already kept the lowest index among equal
+                            // scores; anything else inside the margin is decided by the reference's exact expression
                             const int nb = best_i == 0 ? k[0].n : best_i == 1 ? k[1].n : best_i == 2 ? k[2].n : k[3].n;
                             const double qb = best_i == 0 ? k[0].q : best_i == 1 ? k[1].q : best_i == 2 ? k[2].q : k[3].q;
-                            bool need_exact = !(best == best);
-                            int tie_i = best_i;
+                            bool ok = best == best;
 #pragma unroll
-                            for (int j = A - 1; j >= 0; --j) {
-                                if (j != best_i && !(DM_SUB(best, S[j]) > margin)) {
-                                    if (k[j].n == nb && k[j].q == qb) tie_i = min(tie_i, j);
-                                    else need_exact = true;
-                                }
-                            }
-                            if (need_exact) {
+                            for (int j = 0; j < A; ++j) ok &= (DM_SUB(best, S[j]) > margin) | ((k[j].n == nb) & (k[j].q == qb));
+                            if (ok) {
+                                slot = best_i;
+                            } else {
                                 ++n_exact;
                                 typename SG::Kids kk;
 #pragma unroll
@@ -305,8 +302,6 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                                     kk.n[j] = k[j].n;
                                 }
                                 slot = exact_scores_cold<M>(&cfg, kk, N);
-                            } else {
-                                slot = tie_i;
                             }
                         }
                     }
