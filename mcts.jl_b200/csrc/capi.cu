@@ -630,6 +630,29 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             launches += 3;
         }
     }
+    if (fast >= 0 && !args.order && !cfg->keep_tree && root_stride == 1 && n_trees < (1LL << 30)) {
+        // lanes that do not run in lockstep: spread the trees over more warps while one wave of blocks still holds them all
+        int spread = 1;
+        const char* ev = std::getenv("MCTSB200_SPREAD");
+        if (ev && ev[0]) {
+            spread = std::atoi(ev);
+        } else if (!MdpAccess<M>::lockstep(ctx, cfg)) {
+            // (measured on B200: pays up to about 8 warps per SM, config 3 +2.5 %, 4096 DPW roots +24 %; beyond that the wider
+            // footprint in L1/L2 eats the gain)
+            for (int s2 = 2; s2 <= 8; s2 *= 2)
+                if ((n_trees * s2 + 31) / 32 <= (long long)ctx->sm_count * 8) spread = s2;
+        }
+        if (spread == 2 || spread == 4 || spread == 8) {
+            const int active = 32 / spread;
+            const long long n_warps = (n_trees + active - 1) / active;
+            args.n_slots = n_warps * 32;
+            CUDA_TRY(ctx->order.ensure(sizeof(int) * (size_t)args.n_slots));
+            MCTSB200_LAUNCH(order_spread_kernel, (unsigned)((args.n_slots + 255) / 256), 256, 0, ctx->stream, (int*)ctx->order.p, args.n_slots, active, n_trees);
+            CUDA_TRY(cudaGetLastError());
+            args.order = (const int*)ctx->order.p;
+            launches += 1;
+        }
+    }
     if (fast >= 0) {
         // the fast kernel's working table: 64 B per (slot, state), slots padded to whole warps, zero = "not in the tree"
         const long long slots32 = (args.n_slots + 31) / 32 * 32;

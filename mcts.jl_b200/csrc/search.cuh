@@ -903,6 +903,18 @@ __global__ void order_hist_kernel(const typename M::Params mdp, const typename M
     if (t < n_trees) atomicAdd(bins + M::dense_index(mdp, M::load(mdp, roots[t])), 1);
 }
 // bins[0..n): group sizes -> first slot of each group, every group rounded up to a multiple of `tpw` slots (one block)
+// slot -> tree map that leaves lanes idle: only the first `active` lanes of every warp hold a tree. Trees whose lanes
+// diverge (stochastic transitions / policies) then wait for the slowest of `active` neighbours instead of 32, and a
+// batch too small to fill the SMs gets more warps to hide latency with.
+static __global__ void order_spread_kernel(int* order, long long n_slots, int active, long long n_trees) {
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const long long warp = slot >> 5;
+    const int lane = (int)(slot & 31);
+    const long long tree = warp * active + lane;
+    order[slot] = (lane < active && tree < n_trees) ? (int)tree : -1;
+}
+
 static __global__ void order_scan_kernel(int* bins, int n, int tpw) {
 #ifdef MCTSB200_HOST_EMU
     if (threadIdx.x == 0) {
