@@ -300,7 +300,8 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
-                     "kernel": ("uct_fast_kernel" if int(st_dev[-1].kernel_variant) == 1 else "search_kernel") + " (one launch per step)"},
+                     "kernel": ((("uct_fast_kernel" if WORKLOADS[args.workload]["kind"] == "uct" else "dpw_fast_kernel")
+                                 if int(st_dev[-1].kernel_variant) == 1 else "search_kernel") + " (one launch per step)")},
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -175,8 +175,10 @@ def test_emu_fast_kernels_edge_models(emu_ctx, oracle, kind, case):
 @pytest.mark.parametrize("n_roots", [1, 31, 33, 97])
 def test_emu_fast_kernels_ragged_batches_and_lane_order(emu_ctx, oracle, monkeypatch, n_roots):
     roots = gridworld_roots(n_roots)
-    for order in ("0", "1"):
+    # lane order on / off; trees spread over idle-lane warps (1 = every lane holds a tree, default: chosen by batch size)
+    for order, spread in (("0", "1"), ("1", "1"), ("0", "4"), ("0", "")):
         monkeypatch.setenv("MCTSB200_LANE_ORDER", order)
+        monkeypatch.setenv("MCTSB200_SPREAD", spread)
         for s in (m.MCTSSolver(n_iterations=60, depth=10, exploration_constant=5.0, rng=2),
                   m.MCTSSolver(n_iterations=60, depth=10, exploration_constant=5.0, estimate_value=m.RolloutEstimator(m.ConstantPolicy("up"))),
                   m.DPWSolver(n_iterations=60, depth=10, exploration_constant=5.0, rng=2)):
