@@ -76,6 +76,10 @@ struct Storage {
     DevBuf hdr, rows, aux, trans, map, path;
     DevBuf rows_fast;   // working table of uct_fast.cuh / dpw_fast.cuh (interleaved); `rows` receives the Row<M> table after the search
     DevBuf trans_fast;  // dpw_fast.cuh: per-slot transition multisets (interleaved)
+    // the fast kernels' tables are converted to Row / Aux / TransRec only when a tree query needs them
+    int32_t (*finalize_fn)(mctsb200_ctx*) = nullptr;
+    long long fin_slots = 0;
+    bool fin_order = false;
 };
 
 }  // namespace
@@ -547,6 +551,32 @@ int fast_block_threads(mctsb200_ctx* ctx, long long slots_per_sm, int depth) {
     return block;
 }
 
+// Converts the fast kernels' interleaved tables of the last plan call into the Row / Aux / TransRec tables.
+template <class M, int KIND>
+int32_t finalize_pending(mctsb200_ctx* ctx) {
+    Storage& st = ctx->st;
+    st.finalize_fn = nullptr;
+    if constexpr (M::kFast) {
+        const long long n_slots = st.fin_slots;
+        const int* order = st.fin_order ? (const int*)ctx->order.p : nullptr;
+        unsigned long long* max_visits = (unsigned long long*)ctx->counters.p + CNT_MAX_VISITS;
+        if (KIND == MCTSB200_KIND_UCT) {
+            const long long n_rows = (n_slots + 31) / 32 * 32 * st.geo.NS;
+            auto kernel = finalize_rows_kernel<M>;
+            MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (const FastRow*)st.rows_fast.p, order, (const uint16_t*)st.map.p,
+                            (Row<M>*)st.rows.p, st.geo.NS, n_slots, max_visits);
+        } else {
+            auto kernel = dpw_finalize_kernel<M>;
+            MCTSB200_LAUNCH(kernel, (unsigned)((n_slots + 127) / 128), 128, 0, ctx->stream, (const FastRow*)st.rows_fast.p,
+                            (const DpwTransRow*)st.trans_fast.p, order, (const uint16_t*)st.map.p, MdpAccess<M>::params(ctx), (TreeHeader*)st.hdr.p,
+                            (Row<M>*)st.rows.p, (Aux<M>*)st.aux.p, (TransRec*)st.trans.p, st.geo.NS, st.geo.NT, n_slots, max_visits);
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // (the tree queries read with plain cudaMemcpy)
+    }
+    return MCTSB200_OK;
+}
+
 // Runs the search for trees whose roots are already on the device. d_* outputs may be null.
 template <class M, int KIND>
 int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const typename M::AbiState* d_roots, long long n_trees,
@@ -733,24 +763,26 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         }
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     }
+    // kept trees need the largest visit count (a by-product of the conversion) for the next call's table bound
+    const bool lazy = fast >= 0 && !cfg->keep_tree && env_enabled("MCTSB200_LAZY_EXPORT");
+    st.finalize_fn = nullptr;
     if constexpr (M::kFast) if (fast >= 0) {
-        const long long slots32 = (args.n_slots + 31) / 32 * 32;
-        const long long n_rows = slots32 * st.geo.NS;
-        if (KIND == MCTSB200_KIND_UCT) {
-            auto kernel = finalize_rows_kernel<M>;
-            MCTSB200_LAUNCH(kernel, (unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream, (const FastRow*)st.rows_fast.p, args.order,
-                            (const uint16_t*)st.map.p, (Row<M>*)st.rows.p, st.geo.NS, args.n_slots, args.counters + CNT_MAX_VISITS);
+        st.fin_slots = args.n_slots;
+        st.fin_order = args.order != nullptr;
+        if (lazy) {
+            auto kernel = decide_fast_kernel<M, KIND>;
+            MCTSB200_LAUNCH(kernel, (unsigned)((args.n_slots + 127) / 128), 128, 0, ctx->stream, (const TreeHeader*)st.hdr.p, (const FastRow*)st.rows_fast.p,
+                            args.order, st.geo.NS, args.n_slots, d_action, d_bestq, d_status);
+            CUDA_TRY(cudaGetLastError());
+            ++launches;
+            st.finalize_fn = &finalize_pending<M, KIND>;
         } else {
-            auto kernel = dpw_finalize_kernel<M>;
-            MCTSB200_LAUNCH(kernel, (unsigned)((args.n_slots + 127) / 128), 128, 0, ctx->stream, (const FastRow*)st.rows_fast.p,
-                            (const DpwTransRow*)st.trans_fast.p, args.order, (const uint16_t*)st.map.p, args.mdp, (TreeHeader*)st.hdr.p,
-                            (Row<M>*)st.rows.p, (Aux<M>*)st.aux.p, (TransRec*)st.trans.p, st.geo.NS, st.geo.NT, args.n_slots,
-                            args.counters + CNT_MAX_VISITS);
+            rc = finalize_pending<M, KIND>(ctx);
+            if (rc) return rc;
+            ++launches;
         }
-        CUDA_TRY(cudaGetLastError());
-        ++launches;
     }
-    {
+    if (!lazy) {
         const unsigned grid = (unsigned)((n_trees + 127) / 128);
         auto kernel = decide_kernel<M>;
         MCTSB200_LAUNCH(kernel, grid, 128, 0, ctx->stream, (const TreeHeader*)st.hdr.p, (const Row<M>*)st.rows.p, st.geo.NS, n_trees, d_action, d_bestq,
@@ -868,6 +900,7 @@ int32_t root_parallel_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg
         CUDA_TRY(ctx->sums.ensure(sizeof(double) * 2 * M::kActions));
         d_sums = (double*)ctx->sums.p;
     }
+    if (ctx->st.finalize_fn && (rc = ctx->st.finalize_fn(ctx))) return rc;
     auto kernel = root_sums_kernel<M>;
     MCTSB200_LAUNCH(kernel, 1, 32, 0, ctx->stream, (const TreeHeader*)ctx->st.hdr.p, (const Row<M>*)ctx->st.rows.p, ctx->st.geo.NS, n_trees, d_sums);
     CUDA_TRY(cudaGetLastError());
@@ -1127,6 +1160,7 @@ int32_t check_tree_query(mctsb200_ctx* ctx, long long i) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
     if (!ctx->st.valid) return fail(MCTSB200_ERR_STATE, "no tree: call mctsb200_plan first");
     if (i < 0 || i >= ctx->st.n_trees) return fail(MCTSB200_ERR_INVALID_ARG, "root index %lld out of range [0,%lld)", i, ctx->st.n_trees);
+    if (ctx->st.finalize_fn) return ctx->st.finalize_fn(ctx);  // first tree query after a plan call: write the export tables
     return MCTSB200_OK;
 }
 

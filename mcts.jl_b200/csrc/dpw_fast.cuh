@@ -491,6 +491,43 @@ __global__ void dpw_finalize_kernel(const FastRow* rows_fast, const DpwTransRow*
     if ((unsigned long long)most > *(volatile unsigned long long*)max_visits) atomicMax(max_visits, (unsigned long long)most);
 }
 
+// Root decision (decide_kernel of search.cuh) straight from the fast kernels' interleaved table, one thread per slot:
+// best_sanode_Q (src/vanilla.jl:339-349) / best_sanode (src/dpw.jl:163-173). The Row / Aux / TransRec tables that the
+// tree queries read are then only written when somebody asks for a tree (finalize_rows_kernel / dpw_finalize_kernel).
+template <class M, int KIND>
+__global__ void decide_fast_kernel(const TreeHeader* hdr, const FastRow* rows_fast, const int* order, int NS, long long n_slots, int* action_out,
+                                   double* best_q_out, int* status_out) {
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const long long tree = order ? (long long)order[slot] : slot;
+    if (tree < 0) return;
+    const TreeHeader h = hdr[tree];
+    int act = 0;
+    double bq = 0.0;
+    if (h.status != MCTSB200_ERR_TERMINAL_ROOT && h.n_state > 0) {
+        const FastRow fr = rows_fast[(slot >> 5) * ((long long)NS * 32) + (long long)h.root * 32 + (slot & 31)];
+        double best = -CUDART_INF;
+        int pick = -1;
+#pragma unroll
+        for (int j = 0; j < M::kActions; ++j) {
+            const bool present = KIND == MCTSB200_KIND_UCT ? fr.c[0].tag != 0 : (fr.c[j].tag & kDpwPresent) != 0;
+            if (!present) continue;
+            if (pick < 0) pick = j;  // vanilla default: the first child; DPW without children: none
+            if (fr.c[j].q > best) {
+                best = fr.c[j].q;
+                pick = j;
+            }
+        }
+        if (pick >= 0) {
+            act = KIND == MCTSB200_KIND_UCT ? pick : dpw_label(fr.c[pick].tag);
+            bq = fr.c[pick].q;
+        }
+    }
+    if (action_out) action_out[tree] = act;
+    if (best_q_out) best_q_out[tree] = bq;
+    if (status_out) status_out[tree] = h.status;
+}
+
 template <class M>
 int32_t launch_dpw_fast(const KernelArgs<M>& args, int policy, int grid, int block, size_t smem, cudaStream_t stream);
 
