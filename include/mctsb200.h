@@ -197,6 +197,19 @@ int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg
 int32_t mctsb200_root_parallel_decide(const double* sum_n, const double* sum_nq, int32_t n_actions,
                                       double init_q, int32_t* action_idx_out, double* best_q_out, double* q_out);
 
+/* ---- host hooks between launches -------------------------------------------------------------------- */
+/* Coarse stand-ins for MCTSSolver.callback (src/vanilla.jl:26,231: called after every iteration) and solver.timer
+ * (src/vanilla.jl:25,226-232; src/dpw.jl:44-52). Host functions cannot run inside a kernel, but they can run between
+ * launches: with a progress function set, every plan call of this ctx runs in chunks of `every` iterations
+ * (every = 1 reproduces the reference's per-iteration callback exactly, at one launch per iteration) and calls
+ * progress(user, iterations_done, n_iterations) after each chunk; a non-zero return ends the search. The tree
+ * queries below are valid inside the callback. timer(user) -> seconds replaces the monotonic clock that max_time is
+ * measured with. NULL clears either hook. */
+typedef int32_t (*mctsb200_progress_fn)(void* user, int64_t iterations_done, int64_t n_iterations);
+typedef double (*mctsb200_timer_fn)(void* user);
+int32_t mctsb200_set_progress_callback(mctsb200_ctx* ctx, mctsb200_progress_fn fn, void* user, int64_t every);
+int32_t mctsb200_set_timer(mctsb200_ctx* ctx, mctsb200_timer_fn fn, void* user);
+
 /* ---- episode driver -------------------------------------------------------------------------------- */
 /* Replaces simulate(RolloutSimulator(max_steps = max_steps), mdp, planner, s0) -- the loop that
  * bench/non-terminal_gw.jl:18,31, bench/non-terminal_gw_dpw.jl and test/performance.jl:33-40 time -- for n_episodes

@@ -166,6 +166,8 @@ EXPORTED_SYMBOLS = (
     "mctsb200_plan_device",
     "mctsb200_plan_root_parallel",
     "mctsb200_run_episodes",
+    "mctsb200_set_progress_callback",
+    "mctsb200_set_timer",
     "mctsb200_root_parallel_decide",
     "mctsb200_root_stats",
     "mctsb200_tree_sizes_query",
@@ -175,6 +177,10 @@ EXPORTED_SYMBOLS = (
     "mctsb200_device_cos",
     "mctsb200_device_philox",
 )
+
+
+PROGRESS_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int64, C.c_int64)  # mctsb200_progress_fn
+TIMER_FN = C.CFUNCTYPE(C.c_double, C.c_void_p)                         # mctsb200_timer_fn
 
 
 def declare(lib: C.CDLL) -> C.CDLL:
@@ -194,6 +200,8 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.mctsb200_plan_device.argtypes = [vp, P(SolverCfg), i32, vp, i64, sz, i64, vp, vp, vp, P(PlanStats)]
     lib.mctsb200_plan_root_parallel.argtypes = [vp, P(SolverCfg), i32, vp, sz, i64, i64, vp, vp, vp, P(PlanStats)]
     lib.mctsb200_run_episodes.argtypes = [vp, P(SolverCfg), i32, vp, i64, sz, i32, u64, i64, vp, vp, vp, P(PlanStats)]
+    lib.mctsb200_set_progress_callback.argtypes = [vp, PROGRESS_FN, vp, i64]
+    lib.mctsb200_set_timer.argtypes = [vp, TIMER_FN, vp]
     lib.mctsb200_root_parallel_decide.argtypes = [vp, vp, i32, dbl, P(i32), P(dbl), vp]
     lib.mctsb200_root_stats.argtypes = [vp, i64, P(i32), vp, vp, vp, P(i64)]
     lib.mctsb200_tree_sizes_query.argtypes = [vp, i64, P(TreeSizes)]

@@ -161,6 +161,25 @@ class Context:
                                                    int(episode_index_base), _ptr(returns), _ptr(steps), _ptr(final), C.byref(stats)))
         return returns, steps, final, stats
 
+    # -- host hooks between launches --
+    def set_progress_callback(self, fn=None, every: int = 1) -> None:
+        """fn(iterations_done, n_iterations) -> truthy to stop; called after every `every` iterations of each plan call. None clears."""
+        if fn is None:
+            self._progress = abi.PROGRESS_FN()  # NULL
+            self._check(self.lib.mctsb200_set_progress_callback(self._h, self._progress, None, 0))
+            return
+
+        def thunk(_user, done, total):
+            return 1 if fn(int(done), int(total)) else 0
+
+        self._progress = abi.PROGRESS_FN(thunk)  # (kept alive as long as it is installed)
+        self._check(self.lib.mctsb200_set_progress_callback(self._h, self._progress, None, int(every)))
+
+    def set_timer(self, fn=None) -> None:
+        """fn() -> seconds: the clock max_time is measured with (solver.timer). None restores the monotonic clock."""
+        self._timer = abi.TIMER_FN((lambda _user: float(fn())) if fn is not None else 0)
+        self._check(self.lib.mctsb200_set_timer(self._h, self._timer, None))
+
     def plan_root_parallel(self, cfg: abi.SolverCfg, mdp_id: int, root: np.ndarray, n_trees: int, tree_index_base: int = 0,
                            d_sums: int = 0):
         root = np.ascontiguousarray(root)

@@ -102,6 +102,12 @@ struct mctsb200_ctx {
     DevBuf order, order_bins, policy_tab;
     double gw_reward_max = 0.0;
     bool gw_fast_det = false;
+    // host hooks run between launches (mctsb200_set_progress_callback / mctsb200_set_timer)
+    mctsb200_progress_fn progress_fn = nullptr;
+    void* progress_user = nullptr;
+    long long progress_every = 0;
+    mctsb200_timer_fn timer_fn = nullptr;
+    void* timer_user = nullptr;
     DevBuf ep_states, ep_disc, ep_ret, ep_steps, ep_active, ep_count;
     int log_tab_n = 0;
 };
@@ -209,6 +215,18 @@ int next_pow2(long long v) {
     long long p = 1;
     while (p < v) p <<= 1;
     return (int)p;
+}
+
+// A max_time search may ask for "unbounded" iterations -- the reference's own tests pass typemax(Int)
+// (test/runtests.jl:91-118). Iteration stamps and visit counters are 32-bit here, so such a call runs at most
+// min(2^24 - 2, 2e9 / depth) iterations: hours of search for one tree.
+const mctsb200_solver_cfg* effective_cfg(const mctsb200_solver_cfg* cfg, mctsb200_solver_cfg& tmp) {
+    if (!cfg || cfg->struct_size != (int32_t)sizeof(mctsb200_solver_cfg) || !std::isfinite(cfg->max_time)) return cfg;
+    const long long cap = std::min<long long>((1LL << 24) - 2, 2000000000LL / std::max(std::min(cfg->depth, 100000), 1));
+    if (cfg->n_iterations <= cap) return cfg;
+    tmp = *cfg;
+    tmp.n_iterations = cap;
+    return &tmp;
 }
 
 int32_t validate_cfg(const mctsb200_solver_cfg* cfg, int n_actions, bool dense, bool (*policy_ok)(int)) {
@@ -419,7 +437,8 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     if (bound_raw > 2000000000LL) return fail(MCTSB200_ERR_CAPACITY, "visit counts may exceed 32 bits (clear_tree to start over)");
 
     // log table: det_log(N), N < log_tab_n (grown lazily, shared by all configurations)
-    int want = (int)std::min<long long>(bound + 1, kUcbTabMax);
+    // (a max_time search has no useful bound: a smaller table, visit counts beyond it take the exact path)
+    int want = (int)std::min<long long>(bound + 1, std::isfinite(cfg->max_time) ? (1LL << 20) : kUcbTabMax);
     if (want > ctx->log_tab_n) {
         want = (int)std::min<long long>(std::max<long long>(want, 2LL * ctx->log_tab_n), kUcbTabMax);  // kept trees: grow in doublings
         std::vector<double> tab((size_t)want), stab((size_t)want), rtab((size_t)want);
@@ -440,7 +459,9 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     d.sqrtlog_tab = (const double*)ctx->sqrtlog_tab.p;
     d.rsqrt_tab = (const double*)ctx->rsqrt_tab.p;
     d.log_tab_n = ctx->log_tab_n;
-    d.rsqrt_tab_n = ctx->log_tab_n;
+    if (const char* ev = std::getenv("MCTSB200_UCB_TABLE_ENTRIES"))  // test hook: a short table exercises the beyond-the-table path
+        if (std::atoi(ev) >= 2048) d.log_tab_n = std::min(d.log_tab_n, std::atoi(ev));
+    d.rsqrt_tab_n = d.log_tab_n;
 
     if (cfg->kind == MCTSB200_KIND_DPW) {
         for (int len = 0; len < 16; ++len) d.nmin_action[len] = len <= A ? nmin_for(cfg->k_action, cfg->alpha_action, len, bound) : 0x7fffffff;
@@ -528,9 +549,7 @@ int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long pr
         // (iteration, level) tags of the children: 24 bits of iteration for UCT, 16 for DPW
         if (cfg->depth > 254 || cfg->n_iterations >= (KIND == MCTSB200_KIND_UCT ? (1LL << 24) - 1 : (1LL << 16) - 1)) return -1;
         if (KIND == MCTSB200_KIND_DPW && !(cfg->check_repeat_state && cfg->check_repeat_action)) return -1;  // unmerged nodes: tile kernel
-        // the kernel indexes the UCB tables without a range check: every visit count must be inside them
-        const long long bound = 4LL * std::max<long long>(cfg->init_N, 0) + prior_visits + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1;
-        if (bound + 1 > kUcbTabMax) return -1;
+        (void)prior_visits;  // (visit counts beyond the UCB tables take the exact path inside the kernels)
         if (fast_smem_bytes<M>(MdpAccess<M>::params(ctx), std::max(cfg->depth, 1), 64) > kFastSmemLimit) return -1;
         switch (cfg->rollout_policy) {
             case MCTSB200_POLICY_RANDOM: return FAST_POLICY_RANDOM;
@@ -728,8 +747,14 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         return MCTSB200_OK;
     };
     float kernel_ms = 0.f;
-    const auto t_start = std::chrono::steady_clock::now();
-    if (!std::isfinite(cfg->max_time)) {
+    // seconds on the clock max_time is measured with: the caller's timer (solver.timer) or the monotonic clock
+    auto now_s = [&]() -> double {
+        if (ctx->timer_fn) return ctx->timer_fn(ctx->timer_user);
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const bool timed = std::isfinite(cfg->max_time);
+    const bool hooked = ctx->progress_fn != nullptr && ctx->progress_every >= 1;
+    if (!timed && !hooked) {
         args.iter_begin = 0;
         args.iter_end = n_iter;
         CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -739,23 +764,41 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         launches += 1;
         done = n_iter;
     } else {
-        // max_time (src/vanilla.jl:232, src/dpw.jl:52): the timer is read after each chunk of iterations;
-        // at least one iteration always runs. Chunks grow until one takes ~1/16 of the budget.
-        int chunk = 1;
+        // max_time (src/vanilla.jl:232, src/dpw.jl:52): the timer is read after each chunk of iterations; at least one
+        // iteration always runs. Chunks grow until one takes ~1/16 of the budget. A progress callback
+        // (src/vanilla.jl:231) fixes the chunk at `every` iterations.
+        const double start_s = now_s();
+        int chunk = hooked ? (int)std::min<long long>(ctx->progress_every, 1 << 20) : 1;
         CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
         while (done < n_iter || (n_iter == 0 && launches == 0)) {
             args.iter_begin = done;
             args.iter_end = std::min(n_iter, done + chunk);
-            const auto c0 = std::chrono::steady_clock::now();
+            const double c0 = now_s();
             if (launch()) return fail(MCTSB200_ERR_CUDA, "launching the search kernel failed");
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             ++launches;
             done = args.iter_end;
-            const auto now = std::chrono::steady_clock::now();
-            const double elapsed = std::chrono::duration<double>(now - t_start).count();
-            if (elapsed >= cfg->max_time || n_iter == 0) break;
-            const double chunk_s = std::chrono::duration<double>(now - c0).count();
+            if (hooked) {
+                // the tree queries work inside the callback (the fast kernels' tables are converted on demand)
+                st.valid = true;
+                if constexpr (M::kFast) {
+                    st.fin_slots = args.n_slots;
+                    st.fin_order = args.order != nullptr;
+                    st.finalize_fn = fast >= 0 ? &finalize_pending<M, KIND> : nullptr;
+                }
+                const int32_t stop = ctx->progress_fn(ctx->progress_user, done, n_iter);
+                st.valid = false;
+                st.finalize_fn = nullptr;
+                if (stop) break;
+            }
+            if (n_iter == 0) break;
+            if (!timed) continue;
+            const double now = now_s();
+            const double elapsed = now - start_s;
+            if (elapsed >= cfg->max_time) break;
+            if (hooked) continue;
+            const double chunk_s = now - c0;
             if (chunk_s < cfg->max_time / 16.0) chunk = std::min(chunk * 2, 1 << 20);
             const double per_iter = chunk_s / (double)(args.iter_end - args.iter_begin);
             const double left = cfg->max_time - elapsed;
@@ -818,6 +861,8 @@ int32_t plan_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const v
     using Abi = typename M::AbiState;
     const auto t0 = std::chrono::steady_clock::now();
     if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
+    mctsb200_solver_cfg cfg_capped;
+    cfg = effective_cfg(cfg, cfg_capped);
     int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok);
     if (rc) return rc;
     if (state_bytes != sizeof(Abi)) return fail(MCTSB200_ERR_INVALID_ARG, "state_bytes %zu != %zu", state_bytes, sizeof(Abi));
@@ -883,6 +928,8 @@ int32_t root_parallel_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg
     using Abi = typename M::AbiState;
     const auto t0 = std::chrono::steady_clock::now();
     if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
+    mctsb200_solver_cfg cfg_capped;
+    cfg = effective_cfg(cfg, cfg_capped);
     int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok);
     if (rc) return rc;
     if (state_bytes != sizeof(Abi) || !root_state || n_trees <= 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad root_parallel arguments");
@@ -928,6 +975,8 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
     using Abi = typename M::AbiState;
     const auto t0 = std::chrono::steady_clock::now();
     if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
+    mctsb200_solver_cfg cfg_capped;
+    cfg = effective_cfg(cfg, cfg_capped);
     int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok);
     if (rc) return rc;
     if (state_bytes != sizeof(Abi) || !initial_states || n <= 0 || max_steps < 0 || base < 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad run_episodes arguments");
@@ -1380,6 +1429,22 @@ int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg
     if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
         return root_parallel_dispatch<MountainCarDev>(ctx, cfg, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out);
     return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+}
+
+int32_t mctsb200_set_progress_callback(mctsb200_ctx* ctx, mctsb200_progress_fn fn, void* user, int64_t every) {
+    if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (fn && every < 1) return fail(MCTSB200_ERR_INVALID_ARG, "a progress callback needs every >= 1 iterations");
+    ctx->progress_fn = fn;
+    ctx->progress_user = fn ? user : nullptr;
+    ctx->progress_every = fn ? every : 0;
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_set_timer(mctsb200_ctx* ctx, mctsb200_timer_fn fn, void* user) {
+    if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    ctx->timer_fn = fn;
+    ctx->timer_user = fn ? user : nullptr;
+    return MCTSB200_OK;
 }
 
 int32_t mctsb200_run_episodes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* initial_states, int64_t n_episodes,

@@ -224,10 +224,14 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                                 cs = s_sqrtlog[N];
 #pragma unroll
                                 for (int t = 0; t < A; ++t) T[t] = t < nchild ? DM_MUL(cs, s_rsqrt[k[t].n]) : 0.0;
-                            } else {
+                            } else if (N < cfg.log_tab_n) {
                                 cs = DM_MUL(c_ucb, __ldg(cfg.sqrtlog_tab + N));
 #pragma unroll
                                 for (int t = 0; t < A; ++t) T[t] = t < nchild ? DM_MUL(cs, __ldg(cfg.rsqrt_tab + k[t].n)) : 0.0;
+                            } else {
+                                cs = __longlong_as_double(0x7ff8000000000000LL);  // beyond the tables: NaN -> the exact path decides
+#pragma unroll
+                                for (int t = 0; t < A; ++t) T[t] = cs;
                             }
 #pragma unroll
                             for (int t = 0; t < A; ++t) S[t] = t < nchild ? DM_ADD(k[t].q, T[t]) : -CUDART_INF;

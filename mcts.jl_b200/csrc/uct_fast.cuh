@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
         const uint64_t seed = cfg.seed;
         const int TERM = ft.term;
         const double gamma = M::discount(args.mdp), eps = cfg.rollout_eps, c_ucb = cfg.c, q_bound = cfg.q_bound;
+        const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
         unsigned n_levels = 0, n_inserts = 0, n_rollouts = 0, n_sims = 0, n_exact = 0;
         unsigned long long n_steps = 0;
 
@@ -262,10 +263,16 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                             cs = s_sqrtlog[N];
 #pragma unroll
                             for (int j = 0; j < A; ++j) T[j] = DM_MUL(cs, s_rsqrt[k[j].n]);
-                        } else {
+                        } else if (N < cfg.log_tab_n) {
                             cs = DM_MUL(c_ucb, __ldg(cfg.sqrtlog_tab + N));
 #pragma unroll
                             for (int j = 0; j < A; ++j) T[j] = DM_MUL(cs, __ldg(cfg.rsqrt_tab + k[j].n));
+                        } else {
+                            // beyond the tables (a max_time search that ran long): NaN scores fail every test below and send the
+                            // selection to the reference's exact expression
+                            cs = kNaN;
+#pragma unroll
+                            for (int j = 0; j < A; ++j) T[j] = kNaN;
                         }
 #pragma unroll
                         for (int j = 0; j < A; ++j) S[j] = DM_ADD(k[j].q, T[j]);

@@ -193,6 +193,28 @@ end
 action(p::B200Planner, s) = first(action_info(p, s))
 MCTS.clear_tree!(p::B200Planner) = check(ccall((:mctsb200_clear_trees, LIB), Int32, (Ptr{Cvoid},), p.ctx.h))
 
+# ---- MCTSSolver.callback / solver.timer: host functions run between launches ------------------------------------
+# callback(planner, i) after every iteration (src/vanilla.jl:231) = a progress hook with every = 1; a coarser `every`
+# trades fidelity for fewer launches. The planner is passed through the user pointer.
+function _progress_thunk(user::Ptr{Cvoid}, done::Int64, total::Int64)::Int32
+    p = unsafe_pointer_to_objref(user)::B200Planner
+    p.solver.callback(p, Int(done))
+    return Int32(0)
+end
+_timer_thunk(user::Ptr{Cvoid})::Float64 = (unsafe_pointer_to_objref(user)::B200Planner).solver.timer()
+function install_hooks!(p::B200Planner; every::Integer = 1)   # p must be a mutable struct kept alive (GC.@preserve) during plan
+    if p.solver isa MCTSSolver
+        check(ccall((:mctsb200_set_progress_callback, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), p.ctx.h,
+                    @cfunction(_progress_thunk, Int32, (Ptr{Cvoid}, Int64, Int64)), pointer_from_objref(p), every))
+    end
+    check(ccall((:mctsb200_set_timer, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), p.ctx.h,
+                @cfunction(_timer_thunk, Float64, (Ptr{Cvoid},)), pointer_from_objref(p)))
+end
+function clear_hooks!(p::B200Planner)
+    check(ccall((:mctsb200_set_progress_callback, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), p.ctx.h, C_NULL, C_NULL, 0))
+    check(ccall((:mctsb200_set_timer, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), p.ctx.h, C_NULL, C_NULL))
+end
+
 # ---- simulate(RolloutSimulator(max_steps = T), mdp, planner, s0) for a batch of start states, on the device ----------
 "Closed-loop episodes (bench/non-terminal_gw.jl:18,31): returns (discounted returns, steps taken, final states)."
 function simulate_batch(sim::RolloutSimulator, p::B200Planner, starts::AbstractVector; env_seed::Integer = 0, episode_index_base::Integer = 0)

@@ -99,6 +99,7 @@ class MCTSSolver:
     timer: Optional[Callable] = None
     callback: Optional[Callable] = None
     # device extensions (not in the reference)
+    callback_every: int = 1  # iterations between two calls of `callback` (1 = the reference's per-iteration callback)
     rollouts_per_leaf: int = 1
     lanes_per_tree: int = 0
 
@@ -176,11 +177,8 @@ def build_cfg(solver, mdp) -> tuple[abi.SolverCfg, list]:
     cfg.lanes_per_tree = int(solver.lanes_per_tree)
     cfg.seed = _seed_of(solver.rng)
 
-    # host callbacks have no device form
-    if solver.timer is not None:
-        raise _unsupported("a custom `timer`")
-    if not is_dpw and solver.callback is not None:
-        raise _unsupported("a per-iteration `callback`")
+    # `timer` and vanilla's `callback` run on the host between launches (Context.set_timer / set_progress_callback, installed
+    # by _Planner._plan); the other host callbacks have no device form
     if is_dpw:
         if solver.reset_callback is not None:
             raise _unsupported("`reset_callback`")
@@ -325,10 +323,26 @@ class _Planner:
         cfg.seed = (cfg.seed + self._calls) & 0xFFFFFFFFFFFFFFFF  # successive calls see fresh randomness
         self.ctx.configure(self.mdp.mdp_id, self.mdp.params())
         roots = self.mdp.encode_states(states)
-        actions, best_q, status, stats = self.ctx.plan(cfg, self.mdp.mdp_id, roots, root_index_base, want_status)
+        self._roots = [self.mdp.decode_state(r) for r in roots]
+        cb = getattr(self.solver, "callback", None)
+        if cb is not None:  # callback(planner, iteration) (src/vanilla.jl:231); planner.tree is live inside it
+            def progress(done, _total):
+                self.tree = TreeView(self, 0)
+                cb(self, done)
+                return False
+
+            self.ctx.set_progress_callback(progress, max(1, int(self.solver.callback_every)))
+        if self.solver.timer is not None:
+            self.ctx.set_timer(self.solver.timer)
+        try:
+            actions, best_q, status, stats = self.ctx.plan(cfg, self.mdp.mdp_id, roots, root_index_base, want_status)
+        finally:
+            if cb is not None:
+                self.ctx.set_progress_callback(None)
+            if self.solver.timer is not None:
+                self.ctx.set_timer(None)
         del keep
         self._calls += 1
-        self._roots = [self.mdp.decode_state(r) for r in roots]
         self.last_stats = stats
         return actions, best_q, status, stats
 

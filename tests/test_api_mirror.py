@@ -56,7 +56,7 @@ def test_option_matrix_like_options_jl(ctx):
         for bad in (dict(init_Q="bad"), dict(init_N="bad"), dict(estimate_value="bad")):
             with pytest.raises(TypeError):
                 m.solve(S(**base, **bad), GW, ctx=ctx)
-    for kw in (dict(callback=lambda p, n: None), dict(timer=lambda: 0.0), dict(enable_tree_vis=True)):
+    for kw in (dict(enable_tree_vis=True),):  # (callback and timer run on the host between launches: tested below)
         with pytest.raises(m.MCTSB200Error) as ei:
             m.solve(m.MCTSSolver(**kw), GW, ctx=ctx)
         assert ei.value.status == m.abi.ERR_UNSUPPORTED
@@ -136,3 +136,57 @@ def test_max_time_runs_at_least_one_iteration(ctx):
     p.action((1, 1))
     assert 1 <= p.last_stats.iterations_done < 10**6
     assert int(p.last_stats.n_simulations) == p.last_stats.iterations_done
+
+
+def test_timing_like_runtests(ctx):
+    """test/runtests.jl:90-119: n_iterations = typemax(Int) with max_time: the search stops on the clock."""
+    import time
+    for S in (m.MCTSSolver, m.DPWSolver):
+        p = m.solve(S(n_iterations=2**63 - 1, depth=10, max_time=0.3, exploration_constant=5.0), GW, ctx=ctx)
+        p.action((1, 1))  # (first call: tables, module load)
+        t0 = time.perf_counter()
+        a = p.action((1, 1))
+        dt = time.perf_counter() - t0
+        assert a in GW.actions and abs(dt - 0.3) < 0.25
+        assert 0 < p.last_stats.iterations_done < 2**24
+
+
+def test_callbacks_like_runtests(ctx):
+    """test/runtests.jl:165-180: callback(planner, iteration) runs once per iteration and can look at planner.tree."""
+    calls, sizes = [], []
+
+    def callback(planner, iteration_index):
+        calls.append(iteration_index)
+        sizes.append(len(planner.tree.total_n))
+
+    policy = m.solve(m.MCTSSolver(n_iterations=10, callback=callback), GW, ctx=ctx)
+    a = policy.action((1, 1))
+    assert a in GW.actions and calls == list(range(1, 11))
+    assert sizes == sorted(sizes) and sizes[-1] > 1  # the tree grows under the callback's eyes
+    # coarser: every 4 iterations -> after 4, 8 and (the rest) 10
+    calls.clear()
+    m.solve(m.MCTSSolver(n_iterations=10, callback=callback, callback_every=4), GW, ctx=ctx).action((1, 1))
+    assert calls == [4, 8, 10]
+    # the hook is gone afterwards, and the chunked search built the same tree as an unchunked one
+    calls.clear()
+    p1 = m.solve(m.MCTSSolver(n_iterations=50, rng=9), GW, ctx=ctx)
+    a1, i1 = p1.action_info((2, 2))
+    assert calls == []
+    p2 = m.solve(m.MCTSSolver(n_iterations=50, rng=9, callback=lambda p, i: None, callback_every=7), GW, ctx=ctx)
+    a2, i2 = p2.action_info((2, 2))
+    assert a1 == a2 and i1["best_Q"] == i2["best_Q"]
+
+
+def test_custom_timer_decides_when_max_time_is_up(ctx):
+    """solver.timer (src/vanilla.jl:25,226-232; src/dpw.jl:44-52): a fake clock that advances 1 s per reading stops the
+    search after the first chunk -- at least one iteration always runs."""
+    for S in (m.MCTSSolver, m.DPWSolver):
+        ticks = [0.0]
+
+        def fake():
+            ticks[0] += 1.0
+            return ticks[0]
+
+        p = m.solve(S(n_iterations=100000, depth=5, max_time=1.5, timer=fake), GW, ctx=ctx)
+        a = p.action((1, 1))
+        assert a in GW.actions and 1 <= p.last_stats.iterations_done < 100000

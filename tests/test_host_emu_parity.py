@@ -283,3 +283,14 @@ def test_emu_simulate_mirror(emu_ctx):
     assert isinstance(one, float) and many.shape == (2,) and one == many[0]
     with pytest.raises(m.MCTSB200Error):
         m.simulate(m.RolloutSimulator(), GW, planner, (2, 2))
+
+
+def test_emu_visit_counts_beyond_the_ucb_tables(emu_ctx, oracle, monkeypatch):
+    """a long max_time search outgrows the sqrt(log N) / 1/sqrt(n) tables: those selections take the exact expression"""
+    monkeypatch.setenv("MCTSB200_UCB_TABLE_ENTRIES", "2048")
+    for s in (m.MCTSSolver(n_iterations=4000, depth=6, exploration_constant=5.0, rng=5),
+              m.DPWSolver(n_iterations=4000, depth=6, exploration_constant=5.0, rng=5)):
+        for fast in ("1", "0"):
+            monkeypatch.setenv("MCTSB200_FAST", fast)
+            _, _, _, st = run_both(emu_ctx, oracle, s, GW, [(2, 2), (9, 9)])
+            assert st.kernel_variant == int(fast) and st.n_select_exact > 1000
