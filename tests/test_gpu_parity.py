@@ -214,3 +214,14 @@ def test_uct_both_descent_orders(gpu_ctx, oracle, monkeypatch, ahead, det):
     for pol in (m.ConstantPolicy("up"), m.SeekTarget((9, 3)), m.RandomSolver()):
         s = m.MCTSSolver(n_iterations=300, depth=20, exploration_constant=5.0, estimate_value=m.RolloutEstimator(pol))
         run_both(gpu_ctx, oracle, s, GW_DET, gridworld_roots(200), compare_trees=range(0, 200, 17))
+
+
+def test_visit_counts_beyond_the_ucb_tables(gpu_ctx, oracle, monkeypatch):
+    """selections whose visit counts lie beyond the sqrt(log N) / 1/sqrt(n) tables take the reference's exact expression"""
+    monkeypatch.setenv("MCTSB200_UCB_TABLE_ENTRIES", "2048")
+    for s in (m.MCTSSolver(n_iterations=5000, depth=8, exploration_constant=5.0, rng=5),
+              m.DPWSolver(n_iterations=5000, depth=8, exploration_constant=5.0, rng=5)):
+        for fast in ("1", "0"):
+            monkeypatch.setenv("MCTSB200_FAST", fast)
+            _, _, _, st = run_both(gpu_ctx, oracle, s, GW, gridworld_roots(64), compare_trees=range(0, 64, 9))
+            assert st.kernel_variant == int(fast) and st.n_select_exact > 1000
