@@ -504,6 +504,13 @@ int pick_lanes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_tr
     return 1;  // the host emulator runs one lane at a time
 #endif
     if (cfg->lanes_per_tree) return cfg->lanes_per_tree;
+    // One rollout per leaf and room for a warp per tree: a single lane runs the tree and the other 31 stay idle
+    // (run_search spreads the trees, see order_spread_kernel) -- the same one-tree-per-warp isolation as a 32-lane tile
+    // without its shuffles and redundant lanes (MountainCar DPW, 1 024 roots: 13.5 vs 10.5 Msim/s).
+    if (cfg->rollouts_per_leaf == 1) {
+        const size_t smem1 = use_path_smem(std::max(cfg->depth, 1), 1) ? path_smem_bytes(std::max(cfg->depth, 1), 1) : 0;
+        if (n_trees * 32 <= (long long)search_occupancy<M, KIND>(1, smem1) * kBlockThreads * ctx->sm_count) return 1;
+    }
     // Widest tile that still lets every tree be resident at once (one wave). Lanes beyond |A| and K do no useful work,
     // but a wider tile also means fewer TREES per warp, and trees sharing a warp wait for each other in every phase
     // (measured on MountainCar DPW, 1 024 roots: 6.3 / 8.4 / 10.3 / 12.8 Msim/s for 4 / 8 / 16 / 32 lanes per tree).
@@ -679,19 +686,23 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             launches += 3;
         }
     }
-    if (fast >= 0 && !args.order && !cfg->keep_tree && root_stride == 1 && n_trees < (1LL << 30)) {
+    if ((fast >= 0 || G == 1) && !args.order && !cfg->keep_tree && root_stride == 1 && n_trees < (1LL << 30)) {
         // lanes that do not run in lockstep: spread the trees over more warps while one wave of blocks still holds them all
         int spread = 1;
         const char* ev = std::getenv("MCTSB200_SPREAD");
         if (ev && ev[0]) {
             spread = std::atoi(ev);
+        } else if (fast < 0) {
+            // tile kernel with one lane per tree: a warp per tree when one wave holds them all (pick_lanes chose G = 1 for that)
+            const size_t smem1 = args.path_smem ? path_smem_bytes(st.geo.depth, 1) : 0;
+            if (cfg->rollouts_per_leaf == 1 && n_trees * 32 <= (long long)search_occupancy<M, KIND>(1, smem1) * kBlockThreads * ctx->sm_count) spread = 32;
         } else if (!MdpAccess<M>::lockstep(ctx, cfg)) {
             // (measured on B200: pays up to about 8 warps per SM, config 3 +2.5 %, 4096 DPW roots +24 %; beyond that the wider
             // footprint in L1/L2 eats the gain)
             for (int s2 = 2; s2 <= 8; s2 *= 2)
                 if ((n_trees * s2 + 31) / 32 <= (long long)ctx->sm_count * 8) spread = s2;
         }
-        if (spread == 2 || spread == 4 || spread == 8) {
+        if (spread == 2 || spread == 4 || spread == 8 || spread == 16 || spread == 32) {
             const int active = 32 / spread;
             const long long n_warps = (n_trees + active - 1) / active;
             args.n_slots = n_warps * 32;
