@@ -639,7 +639,19 @@ struct Search {
                 const int need = nac < a.cfg.nmin_state_n ? __ldg(a.cfg.nmin_state + nac) : 0x7fffffff;
                 widen = rw->n[slot] >= need;
             }
-            if (widen) {
+            if (M::kMaxBranch == 1 && widen && nac == 1 && a.cfg.check_repeat_state) {
+                // A model whose (s, a) has exactly one successor, with merged states: gen would return the state this action
+                // node already leads to and the lookup would find its node -- push!(transitions[sanode], ...) on the one
+                // record, without the transition arithmetic and the hash probe (MountainCar: gen draws no random number).
+                const int rec = ax->thead[slot];
+                spnode = trans[rec].sp;
+                r = trans[rec].r;
+                sp = M::state_of(a.mdp, rows[spnode].key);
+                if (lead()) {
+                    trans[rec].count += 1;
+                    ax->tpush[slot] += 1;
+                }
+            } else if (widen) {
                 M::gen(a.mdp, s, act, rng, sp, r);
                 spnode = a.cfg.check_repeat_state ? map_lookup(sp) : -1;
                 if (spnode < 0) {
