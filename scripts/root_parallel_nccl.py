@@ -21,9 +21,13 @@ if world > 1:
 ctx = m.Context(local)
 gw = m.SimpleGridWorld()
 total_sims = int(float(os.environ.get("TOTAL_SIMS", "1e7")))
-# a FIXED ensemble (8 GPUs x 1 184 trees, ~1 056 iterations each), sharded by global tree index: the merged
-# sums do not depend on the number of GPUs
-n_trees = int(os.environ.get("TREES", str(8 * 148 * 8)))
+# ENSEMBLE=fixed (default): a FIXED ensemble (8 GPUs x 1 184 trees, ~1 056 iterations each), sharded by global
+#   tree index: the merged sums -- and the decision -- do not depend on the number of GPUs. One tree's 1 056 iterations are a
+#   serial chain, so the time per decision does not shrink with more GPUs either.
+# ENSEMBLE=scaled: 9 472 trees PER GPU and 10^7 / trees iterations each: the same number of simulations per decision, the
+#   serial chain of every tree N times shorter (a different, statistically equivalent ensemble for every N).
+mode = os.environ.get("ENSEMBLE", "fixed")
+n_trees = int(os.environ.get("TREES", str(8 * 148 * 8))) * (world if mode == "scaled" else 1)
 n_iter = max(1, total_sims // n_trees)
 solver = m.MCTSSolver(n_iterations=n_iter, depth=20, exploration_constant=5.0, rng=5)
 for rep in range(3):
@@ -35,7 +39,7 @@ for rep in range(3):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
 if rank == 0:
-    print(json.dumps({"config": "config5-root-parallel", "n_gpus": world, "trees": n_trees, "iterations_per_tree": n_iter,
+    print(json.dumps({"config": "config5-root-parallel", "ensemble": mode, "n_gpus": world, "trees": n_trees, "iterations_per_tree": n_iter,
                       "simulations": int(n_trees * n_iter), "seconds_per_decision": dt, "simulations_per_s": n_trees * n_iter / dt,
                       "action": gw.actions[a], "best_q": best, "q": [float(x) for x in q], "sum_n": [float(x) for x in sum_n],
                       "kernel_ms_rank0": float(stats.kernel_ms)}))
