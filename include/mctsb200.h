@@ -86,6 +86,11 @@ enum {
     MCTSB200_POLICY_MC_ENERGY = 3  /* MountainCar: push in the direction of motion (v<0 ? -1 : +1)  */
 };
 
+/* run-time registered MDP plugins (mctsb200_mdp_register below) */
+#define MCTSB200_MDP_PLUGIN_BASE 100
+#define MCTSB200_POLICY_PLUGIN 100 /* rollout_policy ids >= this are passed to the plugin's policy_action            */
+#define MCTSB200_PLUGIN_PARAM_BYTES 256
+
 /* Flat mirror of MCTSSolver (src/vanilla.jl:28-62) and DPWSolver (src/dpw_types.jl:45-100).
  * Fields that hold host closures in the reference (callback, timer, reset_callback, show_progress,
  * Function/object-valued init_Q/init_N/estimate_value/next_action) have no representation here: the
@@ -152,6 +157,7 @@ typedef struct {
 
 typedef struct mctsb200_ctx mctsb200_ctx;
 
+#ifndef __CUDACC_RTC__ /* (this header is also part of the run-time compiled plugin programs: types only there) */
 /* ---- lifecycle --------------------------------------------------------------------------------- */
 int32_t mctsb200_abi_version(void);
 const char* mctsb200_last_error(void);
@@ -164,6 +170,21 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* ctx);
 int32_t mctsb200_mdp_lookup(const char* name, int32_t* mdp_id); /* "SimpleGridWorld", "MountainCar" */
 int32_t mctsb200_mdp_info(int32_t mdp_id, int32_t* n_actions, int64_t* state_bytes);
 int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* pod_params, size_t bytes);
+
+/* Run-time registration of an MDP plugin (SURVEY.md 8b "MDP plugin (device side)", 8f rank 3): the device-side
+ * counterpart of defining POMDPs.gen / isterminal / actions / discount for a new model in Julia (call sites
+ * src/vanilla.jl:247,258,297, src/dpw.jl:22,87,107,122) and of a custom rollout policy (src/domain_knowledge.jl:56-57).
+ * `cuda_source` is CUDA C++ text defining `struct <plugin_struct>` with the members documented in
+ * mcts.jl_b200/csrc/custom.cuh (Params beginning with `double discount`, is_terminal, gen, policy_action); states are
+ * `state_doubles` float64 values (2 or 4: pad unused ones with 0.0), actions are indices 0..n_actions-1 (2, 3 or 4),
+ * `max_branch` bounds the distinct successors of one (s, a): 1 = deterministic transitions, 0 = unbounded (continuous
+ * noise). The tile kernel is compiled around the plugin with NVRTC for sm_100a; compiler errors are returned through
+ * mctsb200_last_error(). Needs no GPU (the cubin is loaded at the first plan call). The id is process-wide; every ctx
+ * configures its own parameters with mctsb200_mdp_configure(ctx, id, &Params, sizeof(Params)). Registering the same
+ * name again with a different definition replaces it (same id). mctsb200_mdp_lookup / mctsb200_mdp_info know the id.
+ * Plugin MDPs run on the tile kernel: hashed states, so no dense tables (init_q_table, value_table) and no keep_tree. */
+int32_t mctsb200_mdp_register(const char* name, const char* cuda_source, const char* plugin_struct, int32_t state_doubles,
+                              int32_t n_actions, int32_t max_branch, int32_t* mdp_id_out);
 
 /* ---- planning: replaces build_tree (src/vanilla.jl:209-237) / the DPW loop (src/dpw.jl:29-67) ---- */
 /* Plans for n_roots independent root states (one tree each). roots: n_roots*state_bytes host bytes.
@@ -267,6 +288,7 @@ int32_t mctsb200_device_cos(mctsb200_ctx* ctx, const double* x, int64_t n, doubl
 /* First 4*n_blocks Philox4x32-10 words of stream (seed, tree, iteration, stream_id), from the device. */
 int32_t mctsb200_device_philox(mctsb200_ctx* ctx, uint64_t seed, uint64_t tree, uint32_t iteration,
                                uint32_t stream_id, int32_t n_blocks, uint32_t* out);
+#endif /* __CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -6,20 +6,21 @@ Layout:
   csrc/        hand-written sm_100a CUDA kernels + the C ABI (libmctsb200.so; header: include/mctsb200.h)
   _abi.py      ctypes mirror of the header
   _lib.py      loader + Context wrapper (raises if the CUDA library / a B200 is missing: no CPU fallback)
-  models.py    SimpleGridWorld / MountainCar parameter structs (device plugins live in csrc/models.cuh)
+  models.py    SimpleGridWorld / MountainCar parameter structs (device plugins live in csrc/models.cuh), PluginMDP
+  plugins/     MDP plugins registered at run time (CUDA text compiled with NVRTC around the tile kernel)
   solvers.py   MCTSSolver / DPWSolver / solve / action / action_info / value / ranked_actions mirror
   distributed.py  root sharding across ranks and the root-parallel allreduce
   julia/       the Julia glue a maintainer would add to MCTS.jl (unexecuted here: no Julia in the image)
 """
 from . import _abi as abi
-from ._lib import Context, MCTSB200Error, build_library, load_library
-from .models import GWPos, MountainCar, SimpleGridWorld
-from .solvers import (ConstantPolicy, DPWPlanner, DPWSolver, EnergyPolicy, ExceptionRethrow, MCTSPlanner, MCTSSolver,
+from ._lib import Context, MCTSB200Error, build_library, load_library, register_mdp
+from .models import GWPos, MountainCar, MountainCarPlugin, NoisyMountainCar, PluginMDP, SimpleGridWorld
+from .solvers import (ConstantPolicy, DPWPlanner, DPWSolver, EnergyPolicy, ExceptionRethrow, MCTSPlanner, MCTSSolver, PluginPolicy,
                       RandomPolicy, RandomSolver, RolloutEstimator, RolloutSimulator, SeekTarget, build_cfg, clear_tree, ranked_actions,
                       simulate, simulate_batch, solve)
 
 __all__ = [
-    "abi", "Context", "MCTSB200Error", "build_library", "load_library", "GWPos", "MountainCar", "SimpleGridWorld",
+    "abi", "Context", "MCTSB200Error", "build_library", "load_library", "GWPos", "MountainCar", "SimpleGridWorld", "register_mdp", "PluginMDP", "MountainCarPlugin", "NoisyMountainCar", "PluginPolicy",
     "ConstantPolicy", "DPWPlanner", "DPWSolver", "EnergyPolicy", "ExceptionRethrow", "MCTSPlanner", "MCTSSolver",
     "RandomPolicy", "RandomSolver", "RolloutEstimator", "RolloutSimulator", "SeekTarget", "build_cfg", "clear_tree", "ranked_actions",
     "simulate", "simulate_batch", "solve",

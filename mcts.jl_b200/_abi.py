@@ -29,6 +29,8 @@ STATUS_NAMES = {
 
 MDP_GRIDWORLD = 0
 MDP_MOUNTAINCAR = 1
+MDP_PLUGIN_BASE = 100      # ids of MDP plugins registered at run time (mctsb200_mdp_register)
+PLUGIN_PARAM_BYTES = 256
 
 KIND_UCT = 0
 KIND_DPW = 1
@@ -41,6 +43,7 @@ POLICY_RANDOM = 0
 POLICY_CONSTANT = 1
 POLICY_GW_SEEK = 2
 POLICY_MC_ENERGY = 3
+POLICY_PLUGIN = 100        # ids >= this go to the plugin's policy_action
 
 GW_MAX_SPECIAL = 32
 
@@ -162,6 +165,7 @@ EXPORTED_SYMBOLS = (
     "mctsb200_mdp_lookup",
     "mctsb200_mdp_info",
     "mctsb200_mdp_configure",
+    "mctsb200_mdp_register",
     "mctsb200_plan",
     "mctsb200_plan_device",
     "mctsb200_plan_root_parallel",
@@ -196,6 +200,7 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.mctsb200_mdp_lookup.argtypes = [C.c_char_p, P(i32)]
     lib.mctsb200_mdp_info.argtypes = [i32, P(i32), P(i64)]
     lib.mctsb200_mdp_configure.argtypes = [vp, i32, vp, sz]
+    lib.mctsb200_mdp_register.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, i32, P(i32)]
     lib.mctsb200_plan.argtypes = [vp, P(SolverCfg), i32, vp, i64, sz, i64, vp, vp, vp, P(PlanStats)]
     lib.mctsb200_plan_device.argtypes = [vp, P(SolverCfg), i32, vp, i64, sz, i64, vp, vp, vp, P(PlanStats)]
     lib.mctsb200_plan_root_parallel.argtypes = [vp, P(SolverCfg), i32, vp, sz, i64, i64, vp, vp, vp, P(PlanStats)]

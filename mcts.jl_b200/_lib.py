@@ -62,6 +62,19 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     return lib
 
 
+def register_mdp(name: str, cuda_source: str, plugin_struct: str, state_doubles: int, n_actions: int, max_branch: int = 1,
+                 lib_path: Optional[str] = None) -> int:
+    """mctsb200_mdp_register: compile the tile kernel around a device-side MDP plugin (NVRTC, sm_100a) and return its
+    process-wide mdp_id. Compiler errors raise MCTSB200Error with the NVRTC log. Needs no GPU."""
+    lib = load_library(lib_path)
+    out = C.c_int32(-1)
+    rc = lib.mctsb200_mdp_register(name.encode(), cuda_source.encode(), plugin_struct.encode(), int(state_doubles), int(n_actions),
+                                   int(max_branch), C.byref(out))
+    if rc != abi.OK:
+        raise MCTSB200Error(rc, lib.mctsb200_last_error().decode("utf-8", "replace"))
+    return out.value
+
+
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

@@ -20,6 +20,12 @@
 
 #include "search.cuh"
 #include "dpw_fast.cuh"
+#include "custom.cuh"
+#ifndef MCTSB200_HOST_EMU
+#include <map>
+
+#include "plugin_rt.h"
+#endif
 
 using namespace mctsb200;
 
@@ -110,6 +116,13 @@ struct mctsb200_ctx {
     void* timer_user = nullptr;
     DevBuf ep_states, ep_disc, ep_ret, ep_steps, ep_active, ep_count;
     int log_tab_n = 0;
+#ifndef MCTSB200_HOST_EMU
+    // run-time registered MDP plugins (plugin_rt.cu): parameters configured for this ctx, by plugin index
+    struct alignas(16) PluginParams { unsigned char bytes[kCustomParamBytes]; };
+    std::map<int, PluginParams> plugin_params;
+    int cur_plugin = -1;       // plugin index of the call in progress
+    int cur_max_branch = 1;    // its max_branch (0 = unbounded)
+#endif
 };
 
 namespace {
@@ -119,6 +132,8 @@ struct MdpAccess;
 template <>
 struct MdpAccess<GridWorldDev> {
     static bool ready(const mctsb200_ctx* c) { return c->gw_ok; }
+    static int mdp_id(const mctsb200_ctx*) { return MCTSB200_MDP_GRIDWORLD; }
+    static long long max_branch(const mctsb200_ctx*) { return GridWorldDev::kMaxBranch; }
     static const GridWorldDev::Params& params(const mctsb200_ctx* c) { return c->gw_dev; }
     static int dense_count(const mctsb200_ctx* c) { return c->gw_dev.nx * c->gw_dev.ny + 1; }
     static int32_t check_root(const mctsb200_ctx* c, const GridWorldDev::AbiState& s) {
@@ -151,6 +166,8 @@ struct MdpAccess<GridWorldDev> {
 template <>
 struct MdpAccess<MountainCarDev> {
     static bool ready(const mctsb200_ctx* c) { return c->mc_ok; }
+    static int mdp_id(const mctsb200_ctx*) { return MCTSB200_MDP_MOUNTAINCAR; }
+    static long long max_branch(const mctsb200_ctx*) { return MountainCarDev::kMaxBranch; }
     static const MountainCarDev::Params& params(const mctsb200_ctx* c) { return c->mc_dev; }
     static int dense_count(const mctsb200_ctx*) { return 0; }
     static int32_t check_root(const mctsb200_ctx*, const MountainCarDev::AbiState& s) {
@@ -160,6 +177,28 @@ struct MdpAccess<MountainCarDev> {
     static bool lockstep(const mctsb200_ctx*, const mctsb200_solver_cfg*) { return false; }
     static double reward_bound(const mctsb200_ctx*) { return NAN; }
 };
+#ifndef MCTSB200_HOST_EMU
+// a plugin registered at run time (custom.cuh): hashed float64 states like MountainCar, parameters are the plugin's POD
+template <int SD, int A>
+struct MdpAccess<CustomDev<SD, A>> {
+    using M = CustomDev<SD, A>;
+    static bool ready(const mctsb200_ctx* c) { return c->plugin_params.count(c->cur_plugin) != 0; }
+    static int mdp_id(const mctsb200_ctx* c) { return MCTSB200_MDP_PLUGIN_BASE + c->cur_plugin; }
+    static long long max_branch(const mctsb200_ctx* c) { return c->cur_max_branch >= 1 ? c->cur_max_branch : (1LL << 30); }
+    static const typename M::Params& params(const mctsb200_ctx* c) {
+        return *reinterpret_cast<const typename M::Params*>(c->plugin_params.find(c->cur_plugin)->second.bytes);
+    }
+    static int dense_count(const mctsb200_ctx*) { return 0; }
+    static int32_t check_root(const mctsb200_ctx*, const typename M::AbiState& s) {
+        for (int i = 0; i < SD; ++i)
+            if (!std::isfinite(s.v[i])) return -1;
+        return 0;
+    }
+    static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p >= MCTSB200_POLICY_PLUGIN; }
+    static bool lockstep(const mctsb200_ctx*, const mctsb200_solver_cfg*) { return false; }
+    static double reward_bound(const mctsb200_ctx*) { return NAN; }
+};
+#endif
 
 // For every (boundary class, action): the positions where the reference's sampling expression
 // (GridWorldDev::sample_destination, evaluated here on the host with the same individually rounded operations)
@@ -289,7 +328,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     long long NT = 0;
     if (dpw) {
         const long long by_iter = std::max<long long>(1, n_iter * std::max(cfg->depth, 1));
-        const long long by_pairs = NS * A * std::min<long long>(M::kMaxBranch, NS);
+        const long long by_pairs = NS * A * std::min<long long>(MdpAccess<M>::max_branch(ctx), NS);
         NT = cfg->check_repeat_state ? (cfg->keep_tree ? by_pairs : std::min(by_iter, by_pairs)) : std::max<long long>(1, n_iter);
     }
     long long MAP = 0;
@@ -320,7 +359,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
 
     Storage& st = ctx->st;
     *reused = false;
-    if (cfg->keep_tree && st.valid && st.keep && st.kind == cfg->kind && st.mdp_id == M::kMdpId && st.n_trees == n_trees) {
+    if (cfg->keep_tree && st.valid && st.keep && st.kind == cfg->kind && st.mdp_id == MdpAccess<M>::mdp_id(ctx) && st.n_trees == n_trees) {
         if (st.direct != direct || st.geo.NS != g.NS || st.geo.NT != g.NT || st.geo.MAP != g.MAP)
             return fail(MCTSB200_ERR_STATE, "the kept trees cannot be continued with this configuration (different kernel layout); call clear_tree first");
         CUDA_TRY(st.path.ensure(b_path));
@@ -348,7 +387,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     st.direct = direct;
     st.keep = cfg->keep_tree != 0;
     st.visits = 0;
-    st.mdp_id = M::kMdpId;
+    st.mdp_id = MdpAccess<M>::mdp_id(ctx);
     st.n_trees = n_trees;
     st.geo = g;
     st.row_bytes = sizeof(Row<M>);
@@ -466,13 +505,16 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     if (cfg->kind == MCTSB200_KIND_DPW) {
         for (int len = 0; len < 16; ++len) d.nmin_action[len] = len <= A ? nmin_for(cfg->k_action, cfg->alpha_action, len, bound) : 0x7fffffff;
         std::vector<int> ns;
-        const long long max_len = cfg->check_repeat_state ? (long long)M::kMaxBranch : std::min<long long>(cfg->n_iterations + 1, (1 << 20) - 2);
+        // n_a_children never exceeds the model's branching (merged states) nor the pushes of the search
+        const long long need_len = cfg->check_repeat_state ? std::min<long long>(MdpAccess<M>::max_branch(ctx), cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1)
+                                                           : cfg->n_iterations + 1;
+        const long long max_len = std::min<long long>(need_len, (1 << 20) - 2);
         for (long long len = 0; len <= max_len; ++len) {
             const int v = nmin_for(cfg->k_state, cfg->alpha_state, (int)len, bound);
             ns.push_back(v);
             if (v == 0x7fffffff) break;
         }
-        if (!cfg->check_repeat_state && ns.back() != 0x7fffffff && (long long)ns.size() - 1 < cfg->n_iterations + 1)
+        if (ns.back() != 0x7fffffff && (long long)ns.size() - 1 < need_len)
             return fail(MCTSB200_ERR_UNSUPPORTED, "state-widening table would exceed 2^20 entries");
         CUDA_TRY(ctx->nmin_state.ensure(ns.size() * sizeof(int)));
         CUDA_TRY(cudaMemcpy(ctx->nmin_state.p, ns.data(), ns.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -498,6 +540,58 @@ bool use_path_smem(int depth, int G) {
     return env_enabled("MCTSB200_PATH_SMEM") && path_smem_bytes(depth, G) <= kPathSmemLimit;
 }
 
+// Tile-kernel occupancy and launch: the ahead-of-time instantiations (inst_*.cu) or, for a plugin registered at run time,
+// the kernels NVRTC compiled around it (plugin_rt.cu).
+#ifndef MCTSB200_HOST_EMU
+const void* plugin_kernel_or_fail(mctsb200_ctx* ctx, int kind, int kernel_id) {
+    std::string err;
+    const void* k = mctsb200_rt::plugin_kernel(ctx->cur_plugin, kind, kernel_id, err);
+    if (!k) fail(MCTSB200_ERR_CUDA, "%s", err.c_str());
+    return k;
+}
+int tile_kernel_id(int G) { return G == 1 ? 0 : G == 2 ? 1 : G == 4 ? 2 : G == 8 ? 3 : G == 16 ? 4 : 5; }
+#endif
+
+template <class M, int KIND>
+int tile_occupancy(mctsb200_ctx* ctx, int G, size_t smem) {
+#ifndef MCTSB200_HOST_EMU
+    if constexpr (M::kCustom) {
+        const void* k = plugin_kernel_or_fail(ctx, KIND, tile_kernel_id(G));
+        if (!k) return 0;
+        int blocks = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k, kBlockThreads, smem) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        return blocks;
+    } else
+#endif
+    {
+        (void)ctx;
+        return search_occupancy<M, KIND>(G, smem);
+    }
+}
+
+template <class M, int KIND>
+int32_t tile_launch(mctsb200_ctx* ctx, const KernelArgs<M>& args, int G) {
+#ifndef MCTSB200_HOST_EMU
+    if constexpr (M::kCustom) {
+        const void* k = plugin_kernel_or_fail(ctx, KIND, tile_kernel_id(G));
+        if (!k) return MCTSB200_ERR_CUDA;
+        const long long threads = args.n_slots * G;
+        const unsigned grid = (unsigned)((threads + kBlockThreads - 1) / kBlockThreads);
+        const size_t smem = args.path_smem ? path_smem_bytes(args.geo.depth, G) : 0;
+        void* params[] = {(void*)&args};
+        CUDA_TRY(cudaLaunchKernel(k, dim3(grid), dim3(kBlockThreads), params, smem, ctx->stream));
+        return MCTSB200_OK;
+    } else
+#endif
+    {
+        launch_search<M, KIND>(args, G, ctx->stream);
+        return MCTSB200_OK;
+    }
+}
+
 template <class M, int KIND>
 int pick_lanes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_trees) {
 #ifdef MCTSB200_HOST_EMU
@@ -509,7 +603,7 @@ int pick_lanes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_tr
     // without its shuffles and redundant lanes (MountainCar DPW, 1 024 roots: 13.5 vs 10.5 Msim/s).
     if (cfg->rollouts_per_leaf == 1) {
         const size_t smem1 = use_path_smem(std::max(cfg->depth, 1), 1) ? path_smem_bytes(std::max(cfg->depth, 1), 1) : 0;
-        if (n_trees * 32 <= (long long)search_occupancy<M, KIND>(1, smem1) * kBlockThreads * ctx->sm_count) return 1;
+        if (n_trees * 32 <= (long long)tile_occupancy<M, KIND>(ctx, 1, smem1) * kBlockThreads * ctx->sm_count) return 1;
     }
     // Widest tile that still lets every tree be resident at once (one wave). Lanes beyond |A| and K do no useful work,
     // but a wider tile also means fewer TREES per warp, and trees sharing a warp wait for each other in every phase
@@ -518,7 +612,7 @@ int pick_lanes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long n_tr
     const int depth = std::max(cfg->depth, 1);
     for (int G = 2; G <= 32; G *= 2) {
         const size_t smem = use_path_smem(depth, G) ? path_smem_bytes(depth, G) : 0;
-        const long long resident = (long long)search_occupancy<M, KIND>(G, smem) * kBlockThreads * ctx->sm_count;
+        const long long resident = (long long)tile_occupancy<M, KIND>(ctx, G, smem) * kBlockThreads * ctx->sm_count;
         if (n_trees * G <= resident) best = G;
     }
     return best;
@@ -610,7 +704,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
                    mctsb200_plan_stats* stats) {
     Storage& st = ctx->st;
     // visits already in the trees if this call continues kept ones (reuse_tree / keep_tree)
-    const bool may_reuse = cfg->keep_tree && st.valid && st.keep && st.kind == cfg->kind && st.mdp_id == M::kMdpId && st.n_trees == n_trees;
+    const bool may_reuse = cfg->keep_tree && st.valid && st.keep && st.kind == cfg->kind && st.mdp_id == MdpAccess<M>::mdp_id(ctx) && st.n_trees == n_trees;
     const long long prior_visits = may_reuse ? st.visits : 0;
     DevCfg dcfg;
     int32_t rc = build_dev_cfg<M>(ctx, cfg, dcfg, prior_visits);
@@ -695,7 +789,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         } else if (fast < 0) {
             // tile kernel with one lane per tree: a warp per tree when one wave holds them all (pick_lanes chose G = 1 for that)
             const size_t smem1 = args.path_smem ? path_smem_bytes(st.geo.depth, 1) : 0;
-            if (cfg->rollouts_per_leaf == 1 && n_trees * 32 <= (long long)search_occupancy<M, KIND>(1, smem1) * kBlockThreads * ctx->sm_count) spread = 32;
+            if (cfg->rollouts_per_leaf == 1 && n_trees * 32 <= (long long)tile_occupancy<M, KIND>(ctx, 1, smem1) * kBlockThreads * ctx->sm_count) spread = 32;
         } else if (!MdpAccess<M>::lockstep(ctx, cfg)) {
             // (measured on B200: pays up to about 8 warps per SM, config 3 +2.5 %, 4096 DPW roots +24 %; beyond that the wider
             // footprint in L1/L2 eats the gain)
@@ -754,8 +848,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
                 return launch_dpw_fast<M>(args, fast, grid, block, smem, ctx->stream);
             }
         }
-        launch_search<M, KIND>(args, G, ctx->stream);
-        return MCTSB200_OK;
+        return tile_launch<M, KIND>(ctx, args, G);
     };
     float kernel_ms = 0.f;
     // seconds on the clock max_time is measured with: the caller's timer (solver.timer) or the monotonic clock
@@ -769,7 +862,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         args.iter_begin = 0;
         args.iter_end = n_iter;
         CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
-        if (launch()) return fail(MCTSB200_ERR_CUDA, "launching the search kernel failed");
+        if (launch()) return M::kCustom ? MCTSB200_ERR_CUDA : fail(MCTSB200_ERR_CUDA, "launching the search kernel failed");
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
         launches += 1;
@@ -785,7 +878,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             args.iter_begin = done;
             args.iter_end = std::min(n_iter, done + chunk);
             const double c0 = now_s();
-            if (launch()) return fail(MCTSB200_ERR_CUDA, "launching the search kernel failed");
+            if (launch()) return M::kCustom ? MCTSB200_ERR_CUDA : fail(MCTSB200_ERR_CUDA, "launching the search kernel failed");
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             ++launches;
@@ -1009,6 +1102,18 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
     CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int) * ((size_t)max_steps + 1), ctx->stream));
     const unsigned grid = (unsigned)((n + 255) / 256);
     const typename M::Params mdp = MdpAccess<M>::params(ctx);
+#ifndef MCTSB200_HOST_EMU
+    if constexpr (M::kCustom) {
+        const void* k = plugin_kernel_or_fail(ctx, cfg->kind, mctsb200_rt::K_EPISODE_INIT);
+        if (!k) return MCTSB200_ERR_CUDA;
+        const Abi* a_s = d_s;
+        long long a_n = n;
+        double *a_disc = (double*)ctx->ep_disc.p, *a_ret = (double*)ctx->ep_ret.p;
+        int *a_steps = (int*)ctx->ep_steps.p, *a_active = (int*)ctx->ep_active.p, *a_cnt = d_cnt;
+        void* params[] = {(void*)&mdp, &a_s, &a_n, &a_disc, &a_ret, &a_steps, &a_active, &a_cnt};
+        CUDA_TRY(cudaLaunchKernel(k, dim3(grid), dim3(256), params, 0, ctx->stream));
+    } else
+#endif
     {
         auto k = episode_init_kernel<M>;
         MCTSB200_LAUNCH(k, grid, 256, 0, ctx->stream, mdp, (const Abi*)d_s, n, (double*)ctx->ep_disc.p, (double*)ctx->ep_ret.p, (int*)ctx->ep_steps.p,
@@ -1037,10 +1142,27 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
         tot.algorithmic_bytes += st.algorithmic_bytes; tot.kernel_ms += st.kernel_ms;
         tot.lanes_per_tree = st.lanes_per_tree; tot.kernel_variant = st.kernel_variant; tot.iterations_done = st.iterations_done;
         launches += st.n_kernel_launches + 1;
-        auto k = episode_step_kernel<M>;
-        MCTSB200_LAUNCH(k, grid, 256, 0, ctx->stream, mdp, d_s, (const int*)ctx->io_action.p, n, env_seed, base, t, (double*)ctx->ep_disc.p,
-                        (double*)ctx->ep_ret.p, (int*)ctx->ep_steps.p, (int*)ctx->ep_active.p, d_cnt + t + 1);
-        CUDA_TRY(cudaGetLastError());
+#ifndef MCTSB200_HOST_EMU
+        if constexpr (M::kCustom) {
+            const void* k = plugin_kernel_or_fail(ctx, cfg->kind, mctsb200_rt::K_EPISODE_STEP);
+            if (!k) return MCTSB200_ERR_CUDA;
+            Abi* a_s = d_s;
+            const int* a_act = (const int*)ctx->io_action.p;
+            long long a_n = n, a_base = base;
+            unsigned long long a_seed = env_seed;
+            int a_t = t;
+            double *a_disc = (double*)ctx->ep_disc.p, *a_ret = (double*)ctx->ep_ret.p;
+            int *a_steps = (int*)ctx->ep_steps.p, *a_active = (int*)ctx->ep_active.p, *a_cnt = d_cnt + t + 1;
+            void* params[] = {(void*)&mdp, &a_s, &a_act, &a_n, &a_seed, &a_base, &a_t, &a_disc, &a_ret, &a_steps, &a_active, &a_cnt};
+            CUDA_TRY(cudaLaunchKernel(k, dim3(grid), dim3(256), params, 0, ctx->stream));
+        } else
+#endif
+        {
+            auto k = episode_step_kernel<M>;
+            MCTSB200_LAUNCH(k, grid, 256, 0, ctx->stream, mdp, d_s, (const int*)ctx->io_action.p, n, env_seed, base, t, (double*)ctx->ep_disc.p,
+                            (double*)ctx->ep_ret.p, (int*)ctx->ep_steps.p, (int*)ctx->ep_active.p, d_cnt + t + 1);
+            CUDA_TRY(cudaGetLastError());
+        }
     }
     if (return_out) CUDA_TRY(cudaMemcpyAsync(return_out, ctx->ep_ret.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     if (steps_out) CUDA_TRY(cudaMemcpyAsync(steps_out, ctx->ep_steps.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1229,6 +1351,43 @@ int32_t check_tree_query(mctsb200_ctx* ctx, long long i) {
 // =====================================================================================================
 // extern "C" surface
 // =====================================================================================================
+// Runs `return CALL(M);` with M = the trait struct of mdp_id. A plugin id (mctsb200_mdp_register) selects that plugin for the
+// call in progress; the host code exists for the shapes listed here (state doubles x actions).
+#ifndef MCTSB200_HOST_EMU
+using Custom22 = CustomDev<2, 2>;
+using Custom23 = CustomDev<2, 3>;
+using Custom24 = CustomDev<2, 4>;
+using Custom42 = CustomDev<4, 2>;
+using Custom43 = CustomDev<4, 3>;
+using Custom44 = CustomDev<4, 4>;
+bool plugin_shape_ok(int sd, int a) { return (sd == 2 || sd == 4) && a >= 2 && a <= 4; }
+#define MCTSB200_FOR_PLUGIN(ctx, mdp_id, CALL)                                                              \
+    if ((mdp_id) >= MCTSB200_MDP_PLUGIN_BASE) {                                                             \
+        const mctsb200_rt::PluginInfo* pi__ = mctsb200_rt::plugin_info((mdp_id) - MCTSB200_MDP_PLUGIN_BASE); \
+        if (pi__) {                                                                                         \
+            (ctx)->cur_plugin = (mdp_id) - MCTSB200_MDP_PLUGIN_BASE;                                        \
+            (ctx)->cur_max_branch = pi__->max_branch;                                                       \
+            switch (pi__->state_doubles * 10 + pi__->n_actions) {                                           \
+                case 22: return CALL(Custom22);                                                             \
+                case 23: return CALL(Custom23);                                                             \
+                case 24: return CALL(Custom24);                                                             \
+                case 42: return CALL(Custom42);                                                             \
+                case 43: return CALL(Custom43);                                                             \
+                case 44: return CALL(Custom44);                                                             \
+            }                                                                                               \
+        }                                                                                                   \
+    }
+#else
+#define MCTSB200_FOR_PLUGIN(ctx, mdp_id, CALL)
+#endif
+#define MCTSB200_FOR_MDP(ctx, mdp_id, CALL)                                     \
+    do {                                                                        \
+        if ((mdp_id) == MCTSB200_MDP_GRIDWORLD) return CALL(GridWorldDev);      \
+        if ((mdp_id) == MCTSB200_MDP_MOUNTAINCAR) return CALL(MountainCarDev);  \
+        MCTSB200_FOR_PLUGIN(ctx, mdp_id, CALL)                                  \
+        return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", (int)(mdp_id)); \
+    } while (0)
+
 extern "C" {
 
 int32_t mctsb200_abi_version(void) { return MCTSB200_ABI_VERSION; }
@@ -1284,8 +1443,47 @@ int32_t mctsb200_mdp_lookup(const char* name, int32_t* mdp_id) {
     if (!name || !mdp_id) return fail(MCTSB200_ERR_INVALID_ARG, "NULL argument");
     if (!std::strcmp(name, "SimpleGridWorld")) *mdp_id = MCTSB200_MDP_GRIDWORLD;
     else if (!std::strcmp(name, "MountainCar")) *mdp_id = MCTSB200_MDP_MOUNTAINCAR;
-    else return fail(MCTSB200_ERR_UNSUPPORTED, "no device plugin registered for MDP '%s' (built in: SimpleGridWorld, MountainCar)", name);
+    else {
+#ifndef MCTSB200_HOST_EMU
+        const int idx = mctsb200_rt::lookup_plugin(name);
+        if (idx >= 0) {
+            *mdp_id = MCTSB200_MDP_PLUGIN_BASE + idx;
+            return MCTSB200_OK;
+        }
+#endif
+        return fail(MCTSB200_ERR_UNSUPPORTED,
+                    "no device plugin registered for MDP '%s' (built in: SimpleGridWorld, MountainCar; others: mctsb200_mdp_register)", name);
+    }
     return MCTSB200_OK;
+}
+
+int32_t mctsb200_mdp_register(const char* name, const char* cuda_source, const char* plugin_struct, int32_t state_doubles, int32_t n_actions,
+                              int32_t max_branch, int32_t* mdp_id_out) {
+#ifdef MCTSB200_HOST_EMU
+    return fail(MCTSB200_ERR_UNSUPPORTED, "plugins are compiled for the device only");
+#else
+    if (!name || !name[0] || !cuda_source || !plugin_struct || !plugin_struct[0] || !mdp_id_out) return fail(MCTSB200_ERR_INVALID_ARG, "NULL or empty argument");
+    if (!std::strcmp(name, "SimpleGridWorld") || !std::strcmp(name, "MountainCar")) return fail(MCTSB200_ERR_INVALID_ARG, "'%s' is a built-in MDP", name);
+    if (!plugin_shape_ok(state_doubles, n_actions))
+        return fail(MCTSB200_ERR_UNSUPPORTED, "plugin shape (%d state doubles, %d actions) is not available: state_doubles 2 or 4, n_actions 2..4", state_doubles,
+                    n_actions);
+    if (max_branch < 0) return fail(MCTSB200_ERR_INVALID_ARG, "max_branch must be >= 0 (0 = unbounded)");
+    mctsb200_rt::PluginInfo info;
+    info.name = name;
+    info.source = cuda_source;
+    info.struct_name = plugin_struct;
+    info.state_doubles = state_doubles;
+    info.n_actions = n_actions;
+    info.max_branch = max_branch;
+    std::string err;
+    const int idx = mctsb200_rt::register_plugin(info, err);
+    if (idx < 0) {
+        g_err = err;  // (compiler logs are longer than fail()'s buffer)
+        return MCTSB200_ERR_INVALID_ARG;
+    }
+    *mdp_id_out = MCTSB200_MDP_PLUGIN_BASE + idx;
+    return MCTSB200_OK;
+#endif
 }
 
 int32_t mctsb200_mdp_info(int32_t mdp_id, int32_t* n_actions, int64_t* state_bytes) {
@@ -1296,6 +1494,13 @@ int32_t mctsb200_mdp_info(int32_t mdp_id, int32_t* n_actions, int64_t* state_byt
         if (n_actions) *n_actions = MountainCarDev::kActions;
         if (state_bytes) *state_bytes = sizeof(MountainCarDev::AbiState);
     } else {
+#ifndef MCTSB200_HOST_EMU
+        if (const mctsb200_rt::PluginInfo* pi = mctsb200_rt::plugin_info(mdp_id - MCTSB200_MDP_PLUGIN_BASE)) {
+            if (n_actions) *n_actions = pi->n_actions;
+            if (state_bytes) *state_bytes = (int64_t)sizeof(double) * pi->state_doubles;
+            return MCTSB200_OK;
+        }
+#endif
         return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
     }
     return MCTSB200_OK;
@@ -1407,39 +1612,49 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
         ctx->st.valid = false;
         return MCTSB200_OK;
     }
+#ifndef MCTSB200_HOST_EMU
+    if (mctsb200_rt::plugin_info(mdp_id - MCTSB200_MDP_PLUGIN_BASE)) {
+        // the plugin's own Params POD, `double discount` first (custom.cuh)
+        if (!pod || bytes < sizeof(double) || bytes > (size_t)kCustomParamBytes)
+            return fail(MCTSB200_ERR_INVALID_ARG, "plugin params: %zu bytes, expected 8..%d (Params begins with `double discount`)", bytes, kCustomParamBytes);
+        double discount;
+        std::memcpy(&discount, pod, sizeof discount);
+        if (!(discount >= 0.0 && discount <= 1.0)) return fail(MCTSB200_ERR_INVALID_ARG, "discount must be in [0,1]");
+        mctsb200_ctx::PluginParams pp;
+        std::memset(pp.bytes, 0, sizeof pp.bytes);
+        std::memcpy(pp.bytes, pod, bytes);
+        ctx->plugin_params[mdp_id - MCTSB200_MDP_PLUGIN_BASE] = pp;
+        ctx->st.valid = false;
+        return MCTSB200_OK;
+    }
+#endif
     return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
 }
 
 int32_t mctsb200_plan(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* roots, int64_t n_roots, size_t state_bytes,
                       int64_t root_index_base, int32_t* action_idx_out, double* best_q_out, int32_t* status_out, mctsb200_plan_stats* stats_out) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
-    if (mdp_id == MCTSB200_MDP_GRIDWORLD)
-        return plan_dispatch<GridWorldDev>(ctx, cfg, roots, false, n_roots, state_bytes, root_index_base, action_idx_out, best_q_out, status_out, false, stats_out);
-    if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
-        return plan_dispatch<MountainCarDev>(ctx, cfg, roots, false, n_roots, state_bytes, root_index_base, action_idx_out, best_q_out, status_out, false, stats_out);
-    return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+#define MCTSB200_CALL(M) plan_dispatch<M>(ctx, cfg, roots, false, n_roots, state_bytes, root_index_base, action_idx_out, best_q_out, status_out, false, stats_out)
+    MCTSB200_FOR_MDP(ctx, mdp_id, MCTSB200_CALL);
+#undef MCTSB200_CALL
 }
 
 int32_t mctsb200_plan_device(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* d_roots, int64_t n_roots,
                              size_t state_bytes, int64_t root_index_base, int32_t* d_action_idx_out, double* d_best_q_out, int32_t* d_status_out,
                              mctsb200_plan_stats* stats_out) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
-    if (mdp_id == MCTSB200_MDP_GRIDWORLD)
-        return plan_dispatch<GridWorldDev>(ctx, cfg, d_roots, true, n_roots, state_bytes, root_index_base, d_action_idx_out, d_best_q_out, d_status_out, true, stats_out);
-    if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
-        return plan_dispatch<MountainCarDev>(ctx, cfg, d_roots, true, n_roots, state_bytes, root_index_base, d_action_idx_out, d_best_q_out, d_status_out, true, stats_out);
-    return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+#define MCTSB200_CALL(M) plan_dispatch<M>(ctx, cfg, d_roots, true, n_roots, state_bytes, root_index_base, d_action_idx_out, d_best_q_out, d_status_out, true, stats_out)
+    MCTSB200_FOR_MDP(ctx, mdp_id, MCTSB200_CALL);
+#undef MCTSB200_CALL
 }
 
 int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* root_state, size_t state_bytes,
                                     int64_t n_trees, int64_t tree_index_base, double* sum_n_out, double* sum_nq_out, double* d_sums_out,
                                     mctsb200_plan_stats* stats_out) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
-    if (mdp_id == MCTSB200_MDP_GRIDWORLD)
-        return root_parallel_dispatch<GridWorldDev>(ctx, cfg, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out);
-    if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
-        return root_parallel_dispatch<MountainCarDev>(ctx, cfg, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out);
-    return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+#define MCTSB200_CALL(M) root_parallel_dispatch<M>(ctx, cfg, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out)
+    MCTSB200_FOR_MDP(ctx, mdp_id, MCTSB200_CALL);
+#undef MCTSB200_CALL
 }
 
 int32_t mctsb200_set_progress_callback(mctsb200_ctx* ctx, mctsb200_progress_fn fn, void* user, int64_t every) {
@@ -1462,13 +1677,10 @@ int32_t mctsb200_run_episodes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg,
                               size_t state_bytes, int32_t max_steps, uint64_t env_seed, int64_t episode_index_base, double* return_out,
                               int32_t* steps_out, void* final_states_out, mctsb200_plan_stats* stats_out) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
-    if (mdp_id == MCTSB200_MDP_GRIDWORLD)
-        return episodes_dispatch<GridWorldDev>(ctx, cfg, initial_states, n_episodes, state_bytes, max_steps, env_seed, episode_index_base, return_out,
-                                               steps_out, final_states_out, stats_out);
-    if (mdp_id == MCTSB200_MDP_MOUNTAINCAR)
-        return episodes_dispatch<MountainCarDev>(ctx, cfg, initial_states, n_episodes, state_bytes, max_steps, env_seed, episode_index_base,
-                                                 return_out, steps_out, final_states_out, stats_out);
-    return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", mdp_id);
+#define MCTSB200_CALL(M) \
+    episodes_dispatch<M>(ctx, cfg, initial_states, n_episodes, state_bytes, max_steps, env_seed, episode_index_base, return_out, steps_out, final_states_out, stats_out)
+    MCTSB200_FOR_MDP(ctx, mdp_id, MCTSB200_CALL);
+#undef MCTSB200_CALL
 }
 
 int32_t mctsb200_root_parallel_decide(const double* sum_n, const double* sum_nq, int32_t n_actions, double init_q, int32_t* action_idx_out,
@@ -1492,24 +1704,27 @@ int32_t mctsb200_root_parallel_decide(const double* sum_n, const double* sum_nq,
 int32_t mctsb200_root_stats(mctsb200_ctx* ctx, int64_t root_i, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q, int64_t* total_n) {
     int32_t rc = check_tree_query(ctx, root_i);
     if (rc) return rc;
-    if (ctx->st.mdp_id == MCTSB200_MDP_GRIDWORLD) return root_stats_impl<GridWorldDev>(ctx, root_i, n_children, action_idx, n, q, total_n);
-    return root_stats_impl<MountainCarDev>(ctx, root_i, n_children, action_idx, n, q, total_n);
+#define MCTSB200_CALL(M) root_stats_impl<M>(ctx, root_i, n_children, action_idx, n, q, total_n)
+    MCTSB200_FOR_MDP(ctx, ctx->st.mdp_id, MCTSB200_CALL);
+#undef MCTSB200_CALL
 }
 
 int32_t mctsb200_tree_sizes_query(mctsb200_ctx* ctx, int64_t root_i, mctsb200_tree_sizes* sizes) {
     int32_t rc = check_tree_query(ctx, root_i);
     if (rc) return rc;
     if (!sizes) return fail(MCTSB200_ERR_INVALID_ARG, "sizes is NULL");
-    if (ctx->st.mdp_id == MCTSB200_MDP_GRIDWORLD) return tree_sizes_impl<GridWorldDev>(ctx, root_i, sizes);
-    return tree_sizes_impl<MountainCarDev>(ctx, root_i, sizes);
+#define MCTSB200_CALL(M) tree_sizes_impl<M>(ctx, root_i, sizes)
+    MCTSB200_FOR_MDP(ctx, ctx->st.mdp_id, MCTSB200_CALL);
+#undef MCTSB200_CALL
 }
 
 int32_t mctsb200_tree_export(mctsb200_ctx* ctx, int64_t root_i, const mctsb200_tree_buffers* buffers) {
     int32_t rc = check_tree_query(ctx, root_i);
     if (rc) return rc;
     if (!buffers) return fail(MCTSB200_ERR_INVALID_ARG, "buffers is NULL");
-    if (ctx->st.mdp_id == MCTSB200_MDP_GRIDWORLD) return tree_export_impl<GridWorldDev>(ctx, root_i, buffers);
-    return tree_export_impl<MountainCarDev>(ctx, root_i, buffers);
+#define MCTSB200_CALL(M) tree_export_impl<M>(ctx, root_i, buffers)
+    MCTSB200_FOR_MDP(ctx, ctx->st.mdp_id, MCTSB200_CALL);
+#undef MCTSB200_CALL
 }
 
 int32_t mctsb200_clear_trees(mctsb200_ctx* ctx) {

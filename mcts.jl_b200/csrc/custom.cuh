@@ -1,0 +1,101 @@
+// custom.cuh -- the trait struct behind an MDP plugin registered at run time (mctsb200_mdp_register, include/mctsb200.h).
+//
+// SURVEY.md 8(b) "MDP plugin (device side)" / 8(f) rank 3. A user plugin is CUDA source text that defines one struct:
+//
+//     struct MyMdp {
+//         struct Params { double discount; /* ... any POD, <= 256 bytes in all, `discount` first ... */ };
+//         // s / sp: the state, kStateDoubles float64 values (statetype(mdp) as the host passes it)
+//         __device__ static bool is_terminal(const Params& p, const double* s);                       // isterminal(mdp, s)
+//         __device__ static void gen(const Params& p, const double* s, int a, mctsb200::Stream& rng,
+//                                    double* sp, double& r);                                         // @gen(:sp,:r)(mdp, s, a, rng)
+//         // rollout policies beyond MCTSB200_POLICY_RANDOM / _CONSTANT (ids >= MCTSB200_POLICY_PLUGIN):
+//         __device__ static int policy_action(const Params& p, int policy, const int* pp, const double* s, mctsb200::Stream& rng);
+//     };
+//
+// `a` is the 0-based index into actions(mdp); random numbers come from `rng.next()` (32-bit words of the tree's Philox
+// stream), `rng.uniform_int(n)`, `rng.uniform01()`. The source sees everything search.cuh sees (DM_ADD / DM_MUL /
+// det_cos / det_log for reproducible arithmetic). The library compiles search_kernel<CustomDev<SD, A>, KIND, G> around
+// it with NVRTC for sm_100a -- the same tile kernel the built-in MountainCar runs -- and launches the result; nothing of
+// a plugin ever runs on the host (north star: no CPU fallback).
+//
+// The host half of the library is compiled ahead of time for a fixed set of shapes (SD state doubles x A actions, see
+// MCTSB200_CUSTOM_SHAPES in capi.cu); the layout of KernelArgs<CustomDev<SD, A>> does not depend on the plugin.
+#pragma once
+#include "common.cuh"
+
+#ifndef MCTSB200_CUSTOM_MAX_BRANCH
+#define MCTSB200_CUSTOM_MAX_BRANCH 1  // (only the run-time compiled kernels read it; the host sizes tables from the registry)
+#endif
+
+namespace mctsb200 {
+
+constexpr int kCustomParamBytes = 256;
+
+// the plugin struct of a shape; specialised by the generated NVRTC program, never by the ahead-of-time build
+template <int SD, int A>
+struct CustomPluginOf;
+
+template <int SD, int A>
+struct CustomDev {
+    static constexpr int kActions = A;
+    static constexpr bool kDense = false;
+    static constexpr int kMaxBranch = MCTSB200_CUSTOM_MAX_BRANCH;
+    static constexpr bool kFast = false;
+    static constexpr bool kCustom = true;
+    static constexpr int kStateDoubles = SD;
+
+    struct AbiState { double v[SD]; };
+    typedef AbiState State;
+    typedef AbiState Key;
+    struct __align__(16) Params {
+        double discount;  // the first member of every plugin's Params
+        unsigned char rest[kCustomParamBytes - sizeof(double)];
+    };
+
+    __host__ __device__ __forceinline__ static State load(const Params&, const AbiState& a) { return a; }
+    __host__ __device__ __forceinline__ static AbiState store(const Params&, const State& s) { return s; }
+    __host__ __device__ __forceinline__ static State state_of(const Params&, const Key& k) { return k; }
+    __host__ __device__ __forceinline__ static Key key_of(const Params&, const State& s) { return s; }
+
+#if defined(__CUDACC_RTC__)
+    using P = typename CustomPluginOf<SD, A>::type;
+    using PParams = typename P::Params;
+    static_assert(sizeof(PParams) <= sizeof(Params), "a plugin's Params must fit in 256 bytes");
+    __device__ __forceinline__ static const PParams& pp_of(const Params& p) { return *reinterpret_cast<const PParams*>(&p); }
+
+    __device__ __forceinline__ static bool is_terminal(const Params& p, const State& s) { return P::is_terminal(pp_of(p), s.v); }
+    __device__ __forceinline__ static double discount(const Params& p) { return p.discount; }
+    __device__ __forceinline__ static int dense_index(const Params&, const State&) { return -1; }
+    // isequal on Float64 tuples == bitwise equality (as for the built-in MountainCar)
+    __device__ __forceinline__ static bool key_equal(const Key& a, const Key& b) {
+        bool eq = true;
+#pragma unroll
+        for (int i = 0; i < SD; ++i) eq = eq && __double_as_longlong(a.v[i]) == __double_as_longlong(b.v[i]);
+        return eq;
+    }
+    __device__ __forceinline__ static uint32_t hash(const State& s) {
+        uint64_t h = 0x7F4A7C159E3779B9ull;
+#pragma unroll
+        for (int i = 0; i < SD; ++i) {
+            h ^= (uint64_t)__double_as_longlong(s.v[i]) * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+            h ^= h >> 29;
+        }
+        h ^= h >> 33;
+        h *= 0xff51afd7ed558ccdull;
+        h ^= h >> 33;
+        return (uint32_t)h;
+    }
+    __device__ __forceinline__ static void gen(const Params& p, const State& s, int a, Stream& rng, State& sp, double& r) {
+        State out;
+        P::gen(pp_of(p), s.v, a, rng, out.v, r);
+        sp = out;
+    }
+    __device__ __forceinline__ static int policy_action(const Params& p, int policy, const int* pp, const State& s, Stream& rng) {
+        if (policy == MCTSB200_POLICY_RANDOM) return rng.uniform_int(kActions);
+        if (policy == MCTSB200_POLICY_CONSTANT) return pp[0];
+        return P::policy_action(pp_of(p), policy, pp, s.v, rng);
+    }
+#endif
+};
+
+}  // namespace mctsb200

@@ -28,6 +28,7 @@ struct GridWorldDev {
     static constexpr bool kDense = true;
     static constexpr int kMaxBranch = 5;
     static constexpr int kMdpId = MCTSB200_MDP_GRIDWORLD;
+    static constexpr bool kCustom = false;  // (custom.cuh: plugins registered at run time)
 
     struct AbiState { long long x, y; };
     // On the device a state is its dense cell index: (x-1) + (y-1)*nx, and nx*ny for the terminal state (-1,-1).
@@ -231,6 +232,7 @@ struct MountainCarDev {
     static constexpr bool kDense = false;
     static constexpr int kMaxBranch = 1;
     static constexpr int kMdpId = MCTSB200_MDP_MOUNTAINCAR;
+    static constexpr bool kCustom = false;
     static constexpr bool kFast = false;
 
     struct AbiState { double x, v; };

@@ -974,12 +974,14 @@ __global__ void order_scatter_kernel(const typename M::Params mdp, const typenam
 }
 
 // dynamic shared memory of one block of the G variant: the path stacks, if they fit
-static inline size_t path_smem_bytes(int depth, int G) { return sizeof(PathEntry) * (size_t)depth * (size_t)(kBlockThreads / G); }
+__host__ __device__ static inline size_t path_smem_bytes(int depth, int G) { return sizeof(PathEntry) * (size_t)depth * (size_t)(kBlockThreads / G); }
 constexpr size_t kPathSmemLimit = 48 * 1024;
 
+#ifndef __CUDACC_RTC__  // (host-side launchers: not part of a run-time compiled plugin program, plugin_rt.cu)
 template <class M, int KIND>
 void launch_search(const KernelArgs<M>& args, int G, cudaStream_t stream);
 template <class M, int KIND>
 int search_occupancy(int G, size_t smem_bytes);  // resident blocks per SM of the G variant
+#endif
 
 }  // namespace mctsb200

@@ -6,8 +6,10 @@ only carry parameters: all model arithmetic runs on the device.
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from dataclasses import dataclass, field
-from typing import Dict, Iterable, Optional, Sequence, Set, Tuple
+from typing import Any, Dict, Iterable, Optional, Sequence, Set, Tuple
 
 import numpy as np
 
@@ -117,3 +119,85 @@ class MountainCar:
 
     def params(self) -> abi.MountainCarParams:
         return abi.MountainCarParams(float(self.discount), float(self.cost), float(self.jackpot))
+
+
+PLUGIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "plugins")
+
+
+@dataclass
+class PluginMDP:
+    """An MDP whose device plugin is registered at run time (include/mctsb200.h: mctsb200_mdp_register) -- the stand-in for
+    defining POMDPs.gen / isterminal / actions / discount for a new model in Julia. `source` is CUDA text defining
+    `struct <struct_name>` (interface: csrc/custom.cuh); `params` is a ctypes.Structure mirroring its `Params` POD
+    (`double discount` first). States are tuples of `state_width` float64 values (2 or 4)."""
+
+    name: str
+    source: str
+    struct_name: str
+    actions: Tuple[Any, ...]
+    params_struct: C.Structure
+    state_width: int = 2
+    max_branch: int = 1        # distinct successors of one (s, a): 1 = deterministic, 0 = unbounded
+    terminal: Any = None       # optional host-side isterminal(s) (DPW's terminal-root error path in the Python mirror)
+    lib_path: Optional[str] = None
+    oracle_mdp_id: Optional[int] = None  # tests only: the id under which oracle/mcts_oracle.cpp restates this model
+
+    state_dtype = np.float64
+    dense = False
+    _mdp_id: Optional[int] = field(default=None, init=False, repr=False)
+
+    @classmethod
+    def from_file(cls, path: str, **kw) -> "PluginMDP":
+        with open(path if os.path.isabs(path) else os.path.join(PLUGIN_DIR, path), encoding="utf-8") as f:
+            return cls(source=f.read(), **kw)
+
+    @property
+    def mdp_id(self) -> int:
+        if self._mdp_id is None:
+            from ._lib import register_mdp
+
+            self._mdp_id = register_mdp(self.name, self.source, self.struct_name, self.state_width, len(self.actions), self.max_branch,
+                                        self.lib_path)
+        return self._mdp_id
+
+    @property
+    def discount(self) -> float:
+        return float(self.params_struct.discount)
+
+    def isterminal(self, s) -> bool:
+        return bool(self.terminal(s)) if self.terminal is not None else False
+
+    def action_index(self, a) -> int:
+        return self.actions.index(a)
+
+    def encode_states(self, states: Sequence) -> np.ndarray:
+        return np.ascontiguousarray(np.asarray(states, dtype=np.float64).reshape(-1, self.state_width))
+
+    def decode_state(self, row) -> Tuple[float, ...]:
+        return tuple(float(x) for x in row)
+
+    def params(self) -> C.Structure:
+        return self.params_struct
+
+
+class NoisyMountainCarParams(C.Structure):
+    """Params of plugins/noisy_mountaincar.cuh."""
+
+    _fields_ = [("discount", C.c_double), ("cost", C.c_double), ("jackpot", C.c_double), ("noise", C.c_double)]
+
+
+def MountainCarPlugin(discount: float = 0.99, cost: float = -1.0, jackpot: float = 100.0, name: str = "MountainCarPlugin") -> PluginMDP:
+    """The built-in MountainCar written as a run-time plugin (plugins/mountaincar.cuh): same arithmetic, so searches are
+    bit-identical to `MountainCar()` -- the parity anchor of the registration path."""
+    return PluginMDP.from_file("mountaincar.cuh", name=name, struct_name="MountainCarPlugin", actions=(-1.0, 0.0, 1.0),
+                               params_struct=abi.MountainCarParams(float(discount), float(cost), float(jackpot)), state_width=2, max_branch=1,
+                               terminal=lambda s: s[0] >= 0.5, oracle_mdp_id=abi.MDP_MOUNTAINCAR)
+
+
+def NoisyMountainCar(discount: float = 0.99, cost: float = -1.0, jackpot: float = 100.0, noise: float = 0.002,
+                     name: str = "NoisyMountainCar") -> PluginMDP:
+    """MountainCar with uniform velocity noise (plugins/noisy_mountaincar.cuh): a continuous-state MDP with stochastic
+    transitions -- every gen call can produce a new state, the case double progressive widening exists for."""
+    return PluginMDP.from_file("noisy_mountaincar.cuh", name=name, struct_name="NoisyMountainCar", actions=(-1.0, 0.0, 1.0),
+                               params_struct=NoisyMountainCarParams(float(discount), float(cost), float(jackpot), float(noise)), state_width=2,
+                               max_branch=0, terminal=lambda s: s[0] >= 0.5, oracle_mdp_id=1000)

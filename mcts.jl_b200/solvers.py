@@ -57,6 +57,14 @@ class EnergyPolicy:
 
 
 @dataclass
+class PluginPolicy:
+    """A rollout policy implemented by a run-time MDP plugin's `policy_action` (id >= abi.POLICY_PLUGIN, up to 4 int params)."""
+
+    policy_id: int = 100
+    params: tuple = ()
+
+
+@dataclass
 class RolloutEstimator:
     """src/domain_knowledge.jl:27-37."""
 
@@ -248,6 +256,12 @@ def build_cfg(solver, mdp) -> tuple[abi.SolverCfg, list]:
             cfg.rollout_policy_param[0], cfg.rollout_policy_param[1] = int(pol.target[0]), int(pol.target[1])
         elif isinstance(pol, EnergyPolicy):
             cfg.rollout_policy = abi.POLICY_MC_ENERGY
+        elif isinstance(pol, PluginPolicy):
+            if pol.policy_id < abi.POLICY_PLUGIN or len(pol.params) > 4:
+                raise ValueError("PluginPolicy: policy_id >= 100 and at most 4 integer parameters")
+            cfg.rollout_policy = int(pol.policy_id)
+            for i, v in enumerate(pol.params):
+                cfg.rollout_policy_param[i] = int(v)
         elif callable(pol):
             raise _unsupported("a Function-valued rollout policy (use ConstantPolicy / SeekTarget / EnergyPolicy)")
         else:

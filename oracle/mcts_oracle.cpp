@@ -241,6 +241,40 @@ struct MountainCar {
     }
 };
 
+// MountainCar with uniform velocity noise: the model of mcts.jl_b200/plugins/noisy_mountaincar.cuh, a plugin registered at run
+// time through mctsb200_mdp_register (no counterpart in the reference; it checks that the tile kernel compiled around a plugin
+// follows src/dpw.jl:80-154 for a continuous-state MDP with stochastic transitions). One random word per gen call.
+struct NoisyMountainCarParams {
+    double discount, cost, jackpot, noise;
+};
+constexpr int kOracleMdpNoisyMountainCar = 1000;  // oracle-side id (the library's plugin ids are assigned at registration)
+struct NoisyMountainCar {
+    static constexpr int kMdpId = kOracleMdpNoisyMountainCar;
+    using State = MCState;
+    static constexpr int kActions = 3;
+    double gamma, cost, jackpot, noise;
+    explicit NoisyMountainCar(const NoisyMountainCarParams& p) : gamma(p.discount), cost(p.cost), jackpot(p.jackpot), noise(p.noise) {}
+    double discount() const { return gamma; }
+    int n_actions(const State&) const { return kActions; }
+    bool isterminal(const State& s) const { return s.x >= 0.5; }
+    int64_t state_index(const State&) const { return -1; }
+    int64_t n_states() const { return 0; }
+    void gen(const State& s, int ai, Stream& rng, State& sp, double& r) const {
+        const double a = (double)(ai - 1);
+        const double u = rng.uniform01();
+        double v_ = (s.v + a * 0.001) + o_cos(3.0 * s.x) * -0.0025;
+        v_ = v_ + (u - 0.5) * noise;
+        v_ = std::max(std::min(0.07, v_), -0.07);
+        double x_ = s.x + v_;
+        if (x_ < -1.2) {
+            x_ = -1.2;
+            v_ = 0.0;
+        }
+        sp = MCState{x_, v_};
+        r = isterminal(sp) ? jackpot : cost;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Work counters (same definitions as mctsb200_plan_stats)
 // ---------------------------------------------------------------------------------------------
@@ -281,6 +315,7 @@ struct Hooks {
                 else return 1;               // :down
             }
             case MCTSB200_POLICY_MC_ENERGY:
+            case MCTSB200_POLICY_PLUGIN:  // (policy 100 of the shipped plugins: the same heuristic)
                 return state_v(s) < 0.0 ? 0 : 2;
         }
         return 0;
@@ -1029,6 +1064,11 @@ int32_t oracle_plan(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* 
         return plan_batch<MountainCar, MCStateHash>(m, *cfg, (const MCState*)roots, n_roots, root_index_base, n_threads,
                                                     keep_trees != 0, literal_transitions != 0, same_root != 0, action_out, bestq_out,
                                                     status_out, stats);
+    } else if (mdp_id == kOracleMdpNoisyMountainCar) {
+        NoisyMountainCar m(*(const NoisyMountainCarParams*)params);
+        return plan_batch<NoisyMountainCar, MCStateHash>(m, *cfg, (const MCState*)roots, n_roots, root_index_base, n_threads,
+                                                         keep_trees != 0, literal_transitions != 0, same_root != 0, action_out, bestq_out,
+                                                         status_out, stats);
     }
     return MCTSB200_ERR_INVALID_ARG;
 }
@@ -1114,6 +1154,10 @@ int32_t oracle_run_episodes(const mctsb200_solver_cfg* cfg, int32_t mdp_id, cons
         MountainCar m(*(const mctsb200_mountaincar_params*)params);
         return run_episodes_impl<MountainCar, MCStateHash>(m, *cfg, (MCState*)states_inout, n_episodes, max_steps, env_seed, episode_index_base,
                                                            n_threads, return_out, steps_out, stats);
+    } else if (mdp_id == kOracleMdpNoisyMountainCar) {
+        NoisyMountainCar m(*(const NoisyMountainCarParams*)params);
+        return run_episodes_impl<NoisyMountainCar, MCStateHash>(m, *cfg, (MCState*)states_inout, n_episodes, max_steps, env_seed,
+                                                                episode_index_base, n_threads, return_out, steps_out, stats);
     }
     return MCTSB200_ERR_INVALID_ARG;
 }

@@ -8,6 +8,13 @@ COUNTER_KEYS = ["n_simulations", "n_tree_levels", "n_dpw_children_seen", "n_stat
                 "n_rollout_steps", "n_transition_samples", "algorithmic_bytes"]
 
 
+def oracle_id(mdp) -> int:
+    """The oracle's id of a model (a run-time plugin's library id is assigned at registration; the oracle restates the shipped
+    plugins under fixed ids)."""
+    oid = getattr(mdp, "oracle_mdp_id", None)
+    return mdp.mdp_id if oid is None else oid
+
+
 def bits(a: np.ndarray) -> np.ndarray:
     return a.view(np.int64) if a.dtype == np.float64 else a
 
@@ -41,10 +48,10 @@ def run_both(ctx, orc, solver, mdp, roots, base: int = 0, compare_trees="all", l
     if lanes is not None:
         cfg.lanes_per_tree = lanes
     ctx.configure(mdp.mdp_id, mdp.params())
-    orc.configure(mdp.mdp_id, mdp.params())
+    orc.configure(oracle_id(mdp), mdp.params())
     r = mdp.encode_states(roots)
     a1, q1, s1, st1 = ctx.plan(cfg, mdp.mdp_id, r, base, want_status=True)
-    a2, q2, s2, st2 = orc.plan(cfg, mdp.mdp_id, r, base, literal_transitions=literal, n_threads=4)
+    a2, q2, s2, st2 = orc.plan(cfg, oracle_id(mdp), r, base, literal_transitions=literal, n_threads=4)
     assert np.array_equal(s1, s2), "per-root status differs"
     assert np.array_equal(a1, a2), f"actions differ at {np.nonzero(a1 != a2)[0][:10]}"
     assert np.array_equal(bits(q1), bits(q2)), "best_Q differs"
@@ -68,12 +75,12 @@ def run_episodes_both(ctx, orc, solver, mdp, starts, max_steps: int, env_seed: i
     """The closed-loop episode driver (plan at every step, then gen) on the library and on the oracle, bit-for-bit."""
     cfg, keep = m.build_cfg(solver, mdp)
     ctx.configure(mdp.mdp_id, mdp.params())
-    orc.configure(mdp.mdp_id, mdp.params())
+    orc.configure(oracle_id(mdp), mdp.params())
     ctx.clear_trees()
     orc.clear_trees()
     s0 = mdp.encode_states(starts)
     r1, n1, f1, st1 = ctx.run_episodes(cfg, mdp.mdp_id, s0, max_steps, env_seed, base)
-    r2, n2, f2, st2 = orc.run_episodes(cfg, mdp.mdp_id, s0, max_steps, env_seed, base, n_threads=4)
+    r2, n2, f2, st2 = orc.run_episodes(cfg, oracle_id(mdp), s0, max_steps, env_seed, base, n_threads=4)
     assert np.array_equal(n1, n2), f"episode lengths differ at {np.nonzero(n1 != n2)[0][:10]}"
     assert np.array_equal(bits(r1), bits(r2)), f"returns differ at {np.nonzero(bits(r1) != bits(r2))[0][:10]}"
     assert np.array_equal(f1.view(np.uint8), f2.view(np.uint8)), "final states differ"

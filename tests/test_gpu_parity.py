@@ -225,3 +225,81 @@ def test_visit_counts_beyond_the_ucb_tables(gpu_ctx, oracle, monkeypatch):
             monkeypatch.setenv("MCTSB200_FAST", fast)
             _, _, _, st = run_both(gpu_ctx, oracle, s, GW, gridworld_roots(64), compare_trees=range(0, 64, 9))
             assert st.kernel_variant == int(fast) and st.n_select_exact > 1000
+
+
+# ---- MDP plugins registered at run time (mctsb200_mdp_register: NVRTC-compiled tile kernel) -----------------------------------
+def _same_results(r1, r2):
+    a1, q1, s1, st1 = r1
+    a2, q2, s2, st2 = r2
+    assert np.array_equal(a1, a2) and np.array_equal(q1.view(np.int64), q2.view(np.int64)) and np.array_equal(s1, s2)
+    from helpers import COUNTER_KEYS
+
+    for k in COUNTER_KEYS:
+        assert getattr(st1, k) == getattr(st2, k), k
+
+
+@pytest.mark.parametrize("lanes", [None, 1, 4, 32])
+def test_plugin_mountaincar_matches_builtin_and_oracle(gpu_ctx, oracle, lanes):
+    """The built-in MountainCar re-registered as a run-time plugin (plugins/mountaincar.cuh): bit-identical to the oracle -- and so
+    to the ahead-of-time kernels -- for DPW, vanilla UCT and a policy implemented by the plugin, for several tile widths."""
+    mcp = m.MountainCarPlugin()
+    roots = mountaincar_roots(24)
+    for mdp, pol in ((MC, m.EnergyPolicy()), (mcp, m.PluginPolicy(100))):
+        r_dpw = run_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=400, depth=50, rng=8), mdp, roots, lanes=lanes)
+        r_uct = run_both(gpu_ctx, oracle, m.MCTSSolver(n_iterations=300, depth=30, exploration_constant=10.0, rng=9), mdp, roots, lanes=lanes)
+        r_pol = run_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=300, depth=50, rng=8, estimate_value=m.RolloutEstimator(pol, max_depth=100)),
+                         mdp, roots, lanes=lanes)
+        if mdp is MC:
+            built_in = (r_dpw, r_uct, r_pol)
+        else:
+            for x, y in zip(built_in, (r_dpw, r_uct, r_pol)):
+                _same_results(x, y)
+            assert r_dpw[3].kernel_variant == 0
+
+
+@pytest.mark.parametrize("lanes", [None, 1, 8])
+def test_plugin_noisy_mountaincar_bit_exact(gpu_ctx, oracle, lanes):
+    """A continuous-state MDP with stochastic transitions as a plugin (plugins/noisy_mountaincar.cuh, max_branch = 0): state widening
+    really widens (every gen call is a new state). DPW defaults, DPW with unmerged states, vanilla UCT, leaf-parallel rollouts."""
+    mdp = m.NoisyMountainCar()
+    roots = mountaincar_roots(20, seed=3)
+    a, q, s, st = run_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=500, depth=30, rng=4), mdp, roots, lanes=lanes)
+    assert st.n_transition_samples > 0  # re-sampling of existing transitions happened (src/dpw.jl:140)
+    run_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=300, depth=20, k_state=2.0, alpha_state=0.3, check_repeat_state=False, rng=5), mdp, roots, lanes=lanes)
+    run_both(gpu_ctx, oracle, m.MCTSSolver(n_iterations=300, depth=20, exploration_constant=5.0, rng=6), mdp, roots, lanes=lanes)
+    if lanes in (None, 8):
+        run_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=200, depth=20, rng=7, rollouts_per_leaf=8), mdp, roots, lanes=lanes)
+
+
+def test_plugin_episodes_and_root_parallel(gpu_ctx, oracle):
+    mdp = m.NoisyMountainCar(noise=0.004)
+    s = m.DPWSolver(n_iterations=100, depth=10, exploration_constant=2.0, rng=11, estimate_value=m.RolloutEstimator(m.PluginPolicy(100), max_depth=30))
+    starts = mountaincar_roots(40) + [(0.6, 0.0)]
+    ret, steps, final, st = run_episodes_both(gpu_ctx, oracle, s, mdp, starts, max_steps=8, env_seed=2)
+    assert steps[-1] == 0 and ret[-1] == 0.0
+    # root-parallel ensemble (config 5's call shape) on a plugin MDP
+    from helpers import oracle_id
+
+    cfg, _ = m.build_cfg(m.MCTSSolver(n_iterations=200, depth=20, exploration_constant=5.0, rng=3), mdp)
+    gpu_ctx.configure(mdp.mdp_id, mdp.params())
+    oracle.configure(oracle_id(mdp), mdp.params())
+    root = mdp.encode_states([(-0.5, 0.0)])
+    n1, nq1, _ = gpu_ctx.plan_root_parallel(cfg, mdp.mdp_id, root, 64)
+    n2, nq2, _ = oracle.plan_root_parallel(cfg, oracle_id(mdp), root, 64, n_threads=4)
+    assert np.array_equal(n1, n2) and np.allclose(nq1, nq2, rtol=1e-12)
+
+
+def test_plugin_needs_configure_and_refuses_dense_options(gpu_ctx):
+    src = m.MountainCarPlugin().source
+    mdp = m.PluginMDP(name="Unconfigured", source=src, struct_name="MountainCarPlugin", actions=(-1.0, 0.0, 1.0),
+                      params_struct=m.abi.MountainCarParams(0.99, -1.0, 100.0))
+    cfg, _ = m.build_cfg(m.MCTSSolver(n_iterations=10, depth=5), mdp)
+    with pytest.raises(m.MCTSB200Error) as e:
+        gpu_ctx.plan(cfg, mdp.mdp_id, mdp.encode_states([(-0.5, 0.0)]))
+    assert e.value.status == m.abi.ERR_STATE
+    gpu_ctx.configure(mdp.mdp_id, mdp.params())
+    gpu_ctx.plan(cfg, mdp.mdp_id, mdp.encode_states([(-0.5, 0.0)]))
+    cfg.keep_tree = 1
+    with pytest.raises(m.MCTSB200Error) as e:
+        gpu_ctx.plan(cfg, mdp.mdp_id, mdp.encode_states([(-0.5, 0.0)]))
+    assert e.value.status == m.abi.ERR_UNSUPPORTED

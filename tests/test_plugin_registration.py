@@ -1,0 +1,76 @@
+"""Run-time MDP plugin registration (mctsb200_mdp_register), the CPU half: NVRTC compiles the tile kernel
+around the plugin for sm_100a without a GPU, so the interface, the compiler-error path and the id bookkeeping are checked here;
+the searches themselves are in tests/test_gpu_parity.py (-m gpu)."""
+import ctypes as C
+
+import pytest
+
+import mcts_jl_b200 as m
+from mcts_jl_b200 import abi
+
+
+def _lib():
+    return m.load_library()
+
+
+def test_shipped_plugins_compile_and_get_stable_ids():
+    mc = m.MountainCarPlugin()
+    a = mc.mdp_id
+    assert a >= abi.MDP_PLUGIN_BASE
+    # the same definition again: same id, no recompilation needed
+    assert m.register_mdp(mc.name, mc.source, mc.struct_name, 2, 3, 1) == a
+    noisy = m.NoisyMountainCar()
+    b = noisy.mdp_id
+    assert b >= abi.MDP_PLUGIN_BASE and b != a
+    lib = _lib()
+    out = C.c_int32(-1)
+    assert lib.mctsb200_mdp_lookup(mc.name.encode(), C.byref(out)) == abi.OK and out.value == a
+    na, sb = C.c_int32(), C.c_int64()
+    assert lib.mctsb200_mdp_info(b, C.byref(na), C.byref(sb)) == abi.OK
+    assert (na.value, sb.value) == (3, 16)
+    assert lib.mctsb200_mdp_info(abi.MDP_PLUGIN_BASE + 9999, C.byref(na), C.byref(sb)) == abi.ERR_INVALID_ARG
+
+
+def test_compiler_errors_are_reported():
+    with pytest.raises(m.MCTSB200Error) as e:
+        m.register_mdp("Broken", "struct Broken { struct Params { double discount; }; };", "Broken", 2, 3, 1)
+    assert e.value.status == abi.ERR_INVALID_ARG
+    assert "does not compile" in e.value.message and "is_terminal" in e.value.message
+    with pytest.raises(m.MCTSB200Error) as e:
+        m.register_mdp("Syntax", "struct Syntax { this is not C++ };", "Syntax", 2, 3, 1)
+    assert "Syntax.plugin" in e.value.message  # the log points into the user's text
+    out = C.c_int32(-1)
+    assert _lib().mctsb200_mdp_lookup(b"Broken", C.byref(out)) == abi.ERR_UNSUPPORTED  # a failed registration leaves nothing behind
+
+
+def test_argument_checks():
+    src = m.MountainCarPlugin().source
+    for sd, na in [(3, 3), (2, 5), (2, 1), (8, 2)]:
+        with pytest.raises(m.MCTSB200Error) as e:
+            m.register_mdp("Shape", src, "MountainCarPlugin", sd, na, 1)
+        assert e.value.status == abi.ERR_UNSUPPORTED
+    with pytest.raises(m.MCTSB200Error) as e:
+        m.register_mdp("MountainCar", src, "MountainCarPlugin", 2, 3, 1)  # built-in names stay built in
+    assert e.value.status == abi.ERR_INVALID_ARG
+    with pytest.raises(m.MCTSB200Error):
+        m.register_mdp("Neg", src, "MountainCarPlugin", 2, 3, -1)
+    # Params larger than the 256 bytes the ABI carries: rejected at compile time by the adapter's static_assert
+    big = src.replace("double cost, jackpot;", "double cost, jackpot; double pad[40];")
+    with pytest.raises(m.MCTSB200Error) as e:
+        m.register_mdp("BigParams", big, "MountainCarPlugin", 2, 3, 1)
+    assert "256 bytes" in e.value.message
+
+
+def test_redefinition_keeps_the_id():
+    src = m.MountainCarPlugin().source
+    a = m.register_mdp("Redefine", src, "MountainCarPlugin", 2, 3, 1)
+    b = m.register_mdp("Redefine", src.replace("0.001", "0.002"), "MountainCarPlugin", 2, 3, 1)
+    assert a == b
+
+
+def test_plugin_policy_cfg():
+    mdp = m.MountainCarPlugin()
+    cfg, _ = m.build_cfg(m.DPWSolver(estimate_value=m.RolloutEstimator(m.PluginPolicy(100, (1, 2)))), mdp)
+    assert cfg.rollout_policy == abi.POLICY_PLUGIN and list(cfg.rollout_policy_param)[:2] == [1, 2]
+    with pytest.raises(ValueError):
+        m.build_cfg(m.DPWSolver(estimate_value=m.RolloutEstimator(m.PluginPolicy(5))), mdp)
