@@ -82,6 +82,17 @@ end
 device_mdp(m::MountainCar) = (MDP_MOUNTAINCAR, Ref(MountainCarParams(m.discount, m.cost, m.jackpot)), sizeof(MountainCarParams))
 device_mdp(m) = error("no device plugin registered for $(typeof(m)); libmctsb200 has no CPU fallback")
 
+# Run-time registration of a device plugin for a new MDP type (include/mctsb200.h: mctsb200_mdp_register). `source` is CUDA text
+# defining `struct <plugin_struct>` (csrc/custom.cuh); afterwards add a `device_mdp(::YourMDP)` method returning
+# (id, Ref(params_pod), sizeof(params_pod)) with a POD that mirrors the plugin's `Params` (`discount` first).
+function register_mdp(name::AbstractString, source::AbstractString, plugin_struct::AbstractString;
+                      state_doubles::Integer, n_actions::Integer, max_branch::Integer = 1)
+    id = Ref{Int32}(-1)
+    check(ccall((:mctsb200_mdp_register, LIB), Int32, (Cstring, Cstring, Cstring, Int32, Int32, Int32, Ref{Int32}),
+                name, source, plugin_struct, state_doubles, n_actions, max_branch, id))
+    return id[]
+end
+
 # ---- context --------------------------------------------------------------------------------------------
 mutable struct Ctx
     h::Ptr{Cvoid}
