@@ -72,9 +72,11 @@ struct Stream {
         c0 += 1;
         have = 4;
     }
+    // (the unread words are kept at the front: b0 is always the next one)
     __host__ __device__ __forceinline__ uint32_t next() {
         if (have == 0) refill();
-        const uint32_t w = have == 4 ? b0 : have == 3 ? b1 : have == 2 ? b2 : b3;
+        const uint32_t w = b0;
+        b0 = b1; b1 = b2; b2 = b3;
         --have;
         return w;
     }
@@ -147,6 +149,10 @@ struct __align__(32) Aux {
     int thead[M::kActions];  // newest transition record, -1 = none
     int tpush[M::kActions];  // length of the reference's transitions[sanode] (pushes)
     int seq[M::kActions];    // 1-based insertion sequence of the action node (reference id)
+    // the action node's newest transition record, mirrored (models with a single successor per (s, a) follow it without
+    // touching the record table: search.cuh, dpw_iteration)
+    int sp1[M::kActions];
+    double r1[M::kActions];
 };
 
 // geometry of the tables of one plan call

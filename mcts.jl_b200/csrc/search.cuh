@@ -108,6 +108,15 @@ struct Tile {
 // send CUDA's IEEE division to its ~150-instruction slow path; 0 / n is the numerator itself, sign included.
 __device__ __forceinline__ double div_by_count(double x, double n) { return x == 0.0 ? x : DM_DIV(x, n); }
 
+// multiplicity of a transition record += 1, fire-and-forget (RED: the warp does not wait for the old value)
+__device__ __forceinline__ void bump_count(int* count) {
+#ifdef MCTSB200_HOST_EMU
+    *count += 1;
+#else
+    atomicAdd(count, 1);
+#endif
+}
+
 template <class M, int G>
 struct Search {
     using State = typename M::State;
@@ -585,20 +594,47 @@ struct Search {
         n_action += 1;
     }
 
+    // element `slot` of a small array held in registers (a dynamic index would move the array to local memory)
+    template <class T2>
+    __device__ __forceinline__ static T2 pick(const T2 (&v)[A], int slot) {
+        T2 out = v[0];
+#pragma unroll
+        for (int k = 1; k < A; ++k)
+            if (slot == k) out = v[k];
+        return out;
+    }
+
     // one iteration of src/dpw.jl:48-56: simulate(dpw, snode, depth) as descent + backup
     __device__ __forceinline__ void dpw_iteration(int root, uint32_t it) {
         Stream rng;
         rng.init(a.cfg.seed, tree_index, it, 0u);
         int node = root, d = a.cfg.depth, top = 0;
-        State s = M::state_of(a.mdp, rows[node].key);
+        State s;
         int leaf = 0;  // 0: terminal (value 0.0), 1: estimate_value(s, d), 2: table overflow (see uct_iteration)
+        PT_CLOCK(t0);
         for (;;) {
+            PT_ADD(3, 1);
+            // Everything this level needs from the node is requested at once: the row (children statistics and the state label)
+            // and the per-child transition bookkeeping, so the level pays ONE trip to L2 / HBM instead of a chain
+            // row -> aux -> transition record -> successor's label.
+            Row<M>* rw = rows + node;
+            Aux<M>* ax = aux + node;
+            int x_nac[A], x_thead[A], x_tpush[A], x_sp1[A];
+            double x_r1[A];
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                x_nac[k] = ax->nac[k];
+                x_thead[k] = ax->thead[k];
+                x_tpush[k] = ax->tpush[k];
+                x_sp1[k] = ax->sp1[k];
+                x_r1[k] = ax->r1[k];
+            }
+            s = M::state_of(a.mdp, rw->key);
             if (M::is_terminal(a.mdp, s)) break;
             if (d == 0) {
                 leaf = 1;
                 break;
             }
-            Row<M>* rw = rows + node;
             int nchild = rw->nchild();
             // ---- action progressive widening (src/dpw.jl:94-114) ----
             if (a.cfg.enable_action_pw) {
@@ -607,15 +643,29 @@ struct Search {
                     const int act = rng.uniform_int(A);  // next_action(::RandomActionGenerator)
                     bool present = false;
                     const uint32_t pk = rw->packed;
-                    for (int j = 0; j < nchild; ++j) present |= ((int)((pk >> (4 * j)) & 15u) == act);
+#pragma unroll
+                    for (int j = 0; j < A; ++j) present |= (j < nchild) & ((int)((pk >> (4 * j)) & 15u) == act);
                     if (!present) {  // check_repeat_action (always on; see capi.cu)
                         dpw_insert_action(node, nchild, s, act);
+#pragma unroll
+                        for (int k = 0; k < A; ++k)
+                            if (k == nchild) {
+                                x_nac[k] = 0;
+                                x_thead[k] = -1;
+                                x_tpush[k] = 0;
+                            }
                         ++nchild;
                         tile.sync();
                     }
                 }
             } else if (nchild == 0) {
                 for (int act = 0; act < A; ++act) dpw_insert_action(node, act, s, act);
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    x_nac[k] = 0;
+                    x_thead[k] = -1;
+                    x_tpush[k] = 0;
+                }
                 nchild = A;
                 tile.sync();
             }
@@ -625,14 +675,13 @@ struct Search {
             }
             const int slot = select_child(rw, nchild, true);
             const int act = rw->alabel(slot);
-            Aux<M>* ax = aux + node;
 
             // ---- state progressive widening (src/dpw.jl:119-141) ----
             bool new_node = false;
             int spnode;
             double r;
             State sp;
-            const int nac = ax->nac[slot];
+            const int nac = pick(x_nac, slot);
             bool widen = nac == 0;
             if (!widen && a.cfg.enable_state_pw) {
                 // n_a_children <= k_state * n^alpha_state  <=>  n >= nmin_state[n_a_children]
@@ -643,13 +692,11 @@ struct Search {
                 // A model whose (s, a) has exactly one successor, with merged states: gen would return the state this action
                 // node already leads to and the lookup would find its node -- push!(transitions[sanode], ...) on the one
                 // record, without the transition arithmetic and the hash probe (MountainCar: gen draws no random number).
-                const int rec = ax->thead[slot];
-                spnode = trans[rec].sp;
-                r = trans[rec].r;
-                sp = M::state_of(a.mdp, rows[spnode].key);
+                spnode = pick(x_sp1, slot);
+                r = pick(x_r1, slot);
                 if (lead()) {
-                    trans[rec].count += 1;
-                    ax->tpush[slot] += 1;
+                    bump_count(&trans[pick(x_thead, slot)].count);
+                    ax->tpush[slot] = pick(x_tpush, slot) + 1;
                 }
             } else if (widen) {
                 M::gen(a.mdp, s, act, rng, sp, r);
@@ -665,7 +712,7 @@ struct Search {
                 // push!(transitions[sanode], (spnode, r)) in multiset form; unique_transitions bookkeeping
                 int rec = -1;
                 if (!new_node) {
-                    for (rec = ax->thead[slot]; rec >= 0; rec = trans[rec].next)
+                    for (rec = pick(x_thead, slot); rec >= 0; rec = trans[rec].next)
                         if (trans[rec].sp == spnode) break;
                 }
                 if (rec < 0 && n_trans >= a.geo.NT) {
@@ -675,52 +722,64 @@ struct Search {
                 }
                 if (lead()) {
                     if (rec >= 0) {
-                        trans[rec].count += 1;
+                        bump_count(&trans[rec].count);
                     } else {
                         TransRec t;
                         t.r = r;
                         t.sp = spnode;
-                        t.next = ax->thead[slot];
+                        t.next = pick(x_thead, slot);
                         t.count = 1;
                         t.pad[0] = t.pad[1] = t.pad[2] = 0;
                         trans[n_trans] = t;
                         ax->thead[slot] = n_trans;
                         ax->nac[slot] = nac + 1;
+                        ax->sp1[slot] = spnode;
+                        ax->r1[slot] = r;
                     }
-                    ax->tpush[slot] += 1;
+                    ax->tpush[slot] = pick(x_tpush, slot) + 1;
                 }
                 if (rec < 0) n_trans += 1;
             } else {
                 // rand(rng, transitions[sanode]): index j of the push-ordered multiset; records are chained
                 // newest-first, so walk with the mirrored index
-                const int pushes = ax->tpush[slot];
+                const int pushes = pick(x_tpush, slot);
                 const int j = rng.uniform_int(pushes);
-                int jm = pushes - 1 - j, cum = 0, rec = ax->thead[slot];
-                for (;;) {
-                    const int cnt_r = trans[rec].count;
-                    if (jm < cum + cnt_r || trans[rec].next < 0) break;
-                    cum += cnt_r;
-                    rec = trans[rec].next;
+                if (M::kMaxBranch == 1 && a.cfg.check_repeat_state) {  // a single record: every draw picks it
+                    spnode = pick(x_sp1, slot);
+                    r = pick(x_r1, slot);
+                } else {
+                    int jm = pushes - 1 - j, cum = 0, rec = pick(x_thead, slot);
+                    for (;;) {
+                        const int cnt_r = trans[rec].count;
+                        if (jm < cum + cnt_r || trans[rec].next < 0) break;
+                        cum += cnt_r;
+                        rec = trans[rec].next;
+                    }
+                    spnode = trans[rec].sp;
+                    r = trans[rec].r;
                 }
-                spnode = trans[rec].sp;
-                r = trans[rec].r;
-                sp = M::state_of(a.mdp, rows[spnode].key);
                 if (lead()) cnt[CNT_TRANS_SAMPLES] += 1;
             }
             if (lead()) path[top * path_stride] = PathEntry{node, slot, r};
             ++top;
             tile.sync();
             node = spnode;
-            s = sp;
             --d;
             if (new_node) {
+                s = sp;
                 leaf = 1;  // estimate_value(sp, d-1)
                 break;
             }
         }
         if (leaf == 2) return;
+        PT_CLOCK(t1);
         const double v = leaf == 1 ? estimate(s, d, it) : 0.0;
+        PT_CLOCK(t2);
         backup(top, v);
+        PT_CLOCK(t3);
+        PT_ADD(0, t1 - t0);
+        PT_ADD(1, t2 - t1);
+        PT_ADD(2, t3 - t2);
         if (lead()) cnt[CNT_SIMULATIONS] += 1;
     }
 };
@@ -778,7 +837,11 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
         }
 
 #ifdef MCTSB200_PHASE_TIMING
+#ifdef MCTSB200_PT_ALL
+        if ((threadIdx.x & 31) == 0)
+#else
         if ((threadIdx.x & 31) == 0 && (blockIdx.x % 97) == 0 && threadIdx.x < 64)
+#endif
             printf("PT block %d warp %d: iters %d descent %lld leaf %lld backup %lld (cycles/iter) trips/iter %.2f\n", (int)blockIdx.x, (int)(threadIdx.x >> 5),
                    args.iter_end - args.iter_begin, S.cyc[0] / (args.iter_end - args.iter_begin), S.cyc[1] / (args.iter_end - args.iter_begin),
                    S.cyc[2] / (args.iter_end - args.iter_begin), (double)S.cyc[3] / (args.iter_end - args.iter_begin));

@@ -13,9 +13,9 @@ struct MountainCarPlugin {
     // sp, r = @gen(:sp, :r)(mdp, s, a, rng):  v' = clamp(v + a*0.001 + cos(3x)*-0.0025, -0.07, 0.07); x' = x + v'; inelastic wall at -1.2.
     // DM_ADD / DM_MUL / det_cos: individually rounded operations, identical on every device and in the CPU oracle.
     __device__ static void gen(const Params& p, const double* s, int ai, mctsb200::Stream&, double* sp, double& r) {
-        const double a = (double)(ai - 1);
-        double v_ = DM_ADD(DM_ADD(s[1], DM_MUL(a, 0.001)), DM_MUL(det_cos(DM_MUL(3.0, s[0])), -0.0025));
-        v_ = fmax(fmin(0.07, v_), -0.07);
+        const double push = ai == 0 ? -0.001 : (ai == 1 ? 0.0 : 0.001);  // a * 0.001 for a in (-1., 0., 1.): exact
+        double v_ = DM_ADD(DM_ADD(s[1], push), DM_MUL(det_cos(DM_MUL(3.0, s[0])), -0.0025));
+        v_ = v_ > 0.07 ? 0.07 : (v_ < -0.07 ? -0.07 : v_);  // clamp (two compares: FP64 min/max are multi-instruction sequences)
         double x_ = DM_ADD(s[0], v_);
         if (x_ < -1.2) {
             x_ = -1.2;

@@ -9,11 +9,11 @@ struct NoisyMountainCar {
     };
     __device__ static bool is_terminal(const Params&, const double* s) { return s[0] >= 0.5; }
     __device__ static void gen(const Params& p, const double* s, int ai, mctsb200::Stream& rng, double* sp, double& r) {
-        const double a = (double)(ai - 1);
+        const double push = ai == 0 ? -0.001 : (ai == 1 ? 0.0 : 0.001);  // a * 0.001 for a in (-1., 0., 1.): exact
         const double u = rng.uniform01();
-        double v_ = DM_ADD(DM_ADD(s[1], DM_MUL(a, 0.001)), DM_MUL(det_cos(DM_MUL(3.0, s[0])), -0.0025));
+        double v_ = DM_ADD(DM_ADD(s[1], push), DM_MUL(det_cos(DM_MUL(3.0, s[0])), -0.0025));
         v_ = DM_ADD(v_, DM_MUL(DM_SUB(u, 0.5), p.noise));
-        v_ = fmax(fmin(0.07, v_), -0.07);
+        v_ = v_ > 0.07 ? 0.07 : (v_ < -0.07 ? -0.07 : v_);  // clamp (two compares: FP64 min/max are multi-instruction sequences)
         double x_ = DM_ADD(s[0], v_);
         if (x_ < -1.2) {
             x_ = -1.2;

@@ -1,6 +1,6 @@
 # debug experiment: rebuild with phase timing, run short benches (args separated by ';'), rebuild clean
 set -x
-touch mcts.jl_b200/csrc/*.cuh; make -C mcts.jl_b200/csrc -j16 EXTRA=-DMCTSB200_PHASE_TIMING > /dev/null 2>&1
+touch mcts.jl_b200/csrc/*.cuh; make -C mcts.jl_b200/csrc -j16 EXTRA="-DMCTSB200_PHASE_TIMING $PT_EXTRA" > /dev/null 2>&1
 i=0
 IFS=';' read -ra RUNS <<< "$*"
 for r in "${RUNS[@]}"; do
