@@ -183,7 +183,8 @@ class PluginMDP:
 class NoisyMountainCarParams(C.Structure):
     """Params of plugins/noisy_mountaincar.cuh."""
 
-    _fields_ = [("discount", C.c_double), ("cost", C.c_double), ("jackpot", C.c_double), ("noise", C.c_double)]
+    _fields_ = [("discount", C.c_double), ("cost", C.c_double), ("jackpot", C.c_double), ("noise", C.c_double),
+                ("push", C.c_double * 4), ("n_actions", C.c_int32), ("pad", C.c_int32)]
 
 
 def MountainCarPlugin(discount: float = 0.99, cost: float = -1.0, jackpot: float = 100.0, name: str = "MountainCarPlugin") -> PluginMDP:
@@ -195,9 +196,24 @@ def MountainCarPlugin(discount: float = 0.99, cost: float = -1.0, jackpot: float
 
 
 def NoisyMountainCar(discount: float = 0.99, cost: float = -1.0, jackpot: float = 100.0, noise: float = 0.002,
-                     name: str = "NoisyMountainCar") -> PluginMDP:
+                     actions: Tuple[float, ...] = (-1.0, 0.0, 1.0), name: Optional[str] = None, state_width: int = 2) -> PluginMDP:
     """MountainCar with uniform velocity noise (plugins/noisy_mountaincar.cuh): a continuous-state MDP with stochastic
-    transitions -- every gen call can produce a new state, the case double progressive widening exists for."""
-    return PluginMDP.from_file("noisy_mountaincar.cuh", name=name, struct_name="NoisyMountainCar", actions=(-1.0, 0.0, 1.0),
-                               params_struct=NoisyMountainCarParams(float(discount), float(cost), float(jackpot), float(noise)), state_width=2,
-                               max_branch=0, terminal=lambda s: s[0] >= 0.5, oracle_mdp_id=1000)
+    transitions -- every gen call can produce a new state, the case double progressive widening exists for. `actions` are
+    2 to 4 accelerations (velocity increment a * 0.001); `state_width=4` registers the same model with two padding
+    coordinates (carried along unchanged), which exercises the 4-double host shapes."""
+    if not 2 <= len(actions) <= 4:
+        raise ValueError("2 to 4 actions")
+    p = NoisyMountainCarParams(float(discount), float(cost), float(jackpot), float(noise))
+    for i, a in enumerate(actions):
+        p.push[i] = float(a) * 0.001
+    p.n_actions = len(actions)
+    with open(os.path.join(PLUGIN_DIR, "noisy_mountaincar.cuh"), encoding="utf-8") as f:
+        src = f.read()
+    if state_width == 4:  # the padding coordinates are part of the state (and of its hash key); the dynamics ignore them
+        src = src.replace("        sp[0] = x_;\n", "        sp[0] = x_;\n        sp[2] = s[2];\n        sp[3] = s[3];\n")
+        assert "sp[3] = s[3]" in src
+    elif state_width != 2:
+        raise ValueError("state_width 2 or 4")
+    return PluginMDP(name=name or f"NoisyMountainCar{state_width}x{len(actions)}", source=src, struct_name="NoisyMountainCar",
+                     actions=tuple(float(a) for a in actions), params_struct=p, state_width=state_width, max_branch=0,
+                     terminal=lambda s: s[0] >= 0.5, oracle_mdp_id=1000 if state_width == 2 else None)

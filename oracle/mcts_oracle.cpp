@@ -155,6 +155,7 @@ struct GridWorld {
     }
     double discount() const { return gamma; }
     int n_actions(const State&) const { return kActions; }
+    int max_actions() const { return kActions; }
     bool isterminal(const State& s) const { return s.x < 0 || s.y < 0; }  // any(x->x<0, s)
     bool inbounds(const State& s) const { return 1 <= s.x && s.x <= nx && 1 <= s.y && s.y <= ny; }
     double reward(const State& s) const {  // reward(mdp, s, a) = get(mdp.rewards, s, 0.0)
@@ -223,6 +224,7 @@ struct MountainCar {
     explicit MountainCar(const mctsb200_mountaincar_params& p) : gamma(p.discount), cost(p.cost), jackpot(p.jackpot) {}
     double discount() const { return gamma; }
     int n_actions(const State&) const { return kActions; }
+    int max_actions() const { return kActions; }
     bool isterminal(const State& s) const { return s.x >= 0.5; }
     int64_t state_index(const State&) const { return -1; }
     int64_t n_states() const { return 0; }
@@ -246,23 +248,29 @@ struct MountainCar {
 // follows src/dpw.jl:80-154 for a continuous-state MDP with stochastic transitions). One random word per gen call.
 struct NoisyMountainCarParams {
     double discount, cost, jackpot, noise;
+    double push[4];     // velocity increment of action i (POMDPModels' MountainCar: a * 0.001 for a in (-1., 0., 1.))
+    int32_t n_actions;  // 2..4: the plugin is registered once per action-set size (the shape is a registration argument)
+    int32_t pad;
 };
 constexpr int kOracleMdpNoisyMountainCar = 1000;  // oracle-side id (the library's plugin ids are assigned at registration)
 struct NoisyMountainCar {
     static constexpr int kMdpId = kOracleMdpNoisyMountainCar;
     using State = MCState;
     static constexpr int kActions = 3;
-    double gamma, cost, jackpot, noise;
-    explicit NoisyMountainCar(const NoisyMountainCarParams& p) : gamma(p.discount), cost(p.cost), jackpot(p.jackpot), noise(p.noise) {}
+    double gamma, cost, jackpot, noise, push[4];
+    int n_act;
+    explicit NoisyMountainCar(const NoisyMountainCarParams& p) : gamma(p.discount), cost(p.cost), jackpot(p.jackpot), noise(p.noise), n_act(p.n_actions) {
+        for (int i = 0; i < 4; ++i) push[i] = p.push[i];
+    }
     double discount() const { return gamma; }
-    int n_actions(const State&) const { return kActions; }
+    int n_actions(const State&) const { return n_act; }
+    int max_actions() const { return n_act; }
     bool isterminal(const State& s) const { return s.x >= 0.5; }
     int64_t state_index(const State&) const { return -1; }
     int64_t n_states() const { return 0; }
     void gen(const State& s, int ai, Stream& rng, State& sp, double& r) const {
-        const double a = (double)(ai - 1);
         const double u = rng.uniform01();
-        double v_ = (s.v + a * 0.001) + o_cos(3.0 * s.x) * -0.0025;
+        double v_ = (s.v + push[ai]) + o_cos(3.0 * s.x) * -0.0025;
         v_ = v_ + (u - 0.5) * noise;
         v_ = std::max(std::min(0.07, v_), -0.07);
         double x_ = s.x + v_;
@@ -963,7 +971,7 @@ static int32_t plan_batch(const M& mdp, const mctsb200_solver_cfg& cfg, const ty
         stats->n_rollouts = tot.n_rollouts;
         stats->n_rollout_steps = tot.n_rollout_steps;
         stats->n_transition_samples = tot.n_transition_samples;
-        stats->algorithmic_bytes = algorithmic_bytes(cfg, tot, M::kActions);
+        stats->algorithmic_bytes = algorithmic_bytes(cfg, tot, mdp.max_actions());
         stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         stats->lanes_per_tree = 1;
         stats->iterations_done = n_roots ? (int32_t)std::min<int64_t>(min_done.load(), INT32_MAX) : 0;

@@ -303,3 +303,36 @@ def test_plugin_needs_configure_and_refuses_dense_options(gpu_ctx):
     with pytest.raises(m.MCTSB200Error) as e:
         gpu_ctx.plan(cfg, mdp.mdp_id, mdp.encode_states([(-0.5, 0.0)]))
     assert e.value.status == m.abi.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("actions", [(-1.0, 1.0), (-1.0, 0.0, 1.0), (-1.0, -0.5, 0.5, 1.0)])
+def test_plugin_every_host_shape(gpu_ctx, oracle, actions):
+    """The host half of the library exists for 2- and 4-double states x 2..4 actions (capi.cu: MCTSB200_FOR_PLUGIN). The noisy
+    MountainCar with 2, 3 and 4 accelerations against the oracle bit-for-bit (2-double states), and the same model carrying two
+    padding coordinates (4-double states): the state map hashes other keys, the search must not notice."""
+    m2 = m.NoisyMountainCar(actions=actions, state_width=2)
+    m4 = m.NoisyMountainCar(actions=actions, state_width=4)
+    roots2 = mountaincar_roots(16, seed=len(actions))
+    roots4 = [(x, v, 7.0, -3.0) for x, v in roots2]
+    for solver in (m.DPWSolver(n_iterations=300, depth=25, rng=21), m.MCTSSolver(n_iterations=200, depth=15, exploration_constant=3.0, rng=22)):
+        r2 = run_both(gpu_ctx, oracle, solver, m2, roots2)
+        t2 = [gpu_ctx.tree_export(i, m2.state_dtype, 2) for i in range(len(roots2))]
+        cfg, _ = m.build_cfg(solver, m4)
+        gpu_ctx.configure(m4.mdp_id, m4.params())
+        r4 = gpu_ctx.plan(cfg, m4.mdp_id, m4.encode_states(roots4), 0, want_status=True)
+        _same_results(r2, r4)
+        for i in range(len(roots4)):
+            t4 = gpu_ctx.tree_export(i, m4.state_dtype, 4)
+            for k in t2[i]:
+                if k == "s_labels":
+                    lab = t4[k].reshape(-1, 4)
+                    assert np.array_equal(lab[:, :2].view(np.int64), t2[i][k].reshape(-1, 2).view(np.int64))
+                    assert (lab[:, 2] == 7.0).all() and (lab[:, 3] == -3.0).all()
+                else:
+                    assert np.array_equal(t4[k], t2[i][k]), k
+    # closed-loop episodes (the run-time compiled episode kernels) on the 4-double shape against the 2-double one
+    s = m.DPWSolver(n_iterations=60, depth=10, rng=23)
+    ret2, steps2, final2, _ = m.solve(s, m2, ctx=gpu_ctx).run_episodes(roots2, 5, 9)
+    ret4, steps4, final4, _ = m.solve(s, m4, ctx=gpu_ctx).run_episodes(roots4, 5, 9)
+    assert np.array_equal(ret2.view(np.int64), ret4.view(np.int64)) and np.array_equal(steps2, steps4)
+    assert [f[:2] for f in final4] == list(final2) and all(f[2:] == (7.0, -3.0) for f in final4)

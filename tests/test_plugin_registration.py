@@ -22,6 +22,9 @@ def test_shipped_plugins_compile_and_get_stable_ids():
     noisy = m.NoisyMountainCar()
     b = noisy.mdp_id
     assert b >= abi.MDP_PLUGIN_BASE and b != a
+    # every host shape (2 / 4 state doubles x 2..4 actions) compiles
+    ids = {m.NoisyMountainCar(actions=acts, state_width=sw).mdp_id for sw in (2, 4) for acts in ((-1.0, 1.0), (-1.0, 0.0, 1.0), (-1.0, -0.5, 0.5, 1.0))}
+    assert len(ids) == 6 and b in ids
     lib = _lib()
     out = C.c_int32(-1)
     assert lib.mctsb200_mdp_lookup(mc.name.encode(), C.byref(out)) == abi.OK and out.value == a
