@@ -47,6 +47,12 @@ WORKLOADS = {
                                                  k_action=4.0, alpha_action=1 / 8), n_roots=16384),
     "config4-dpw-mountaincar": dict(mdp="mc", mdp_kw=dict(), kind="dpw", policy="random", solver_kw=dict(n_iterations=10000, depth=50),
                                     n_roots=1024),
+    # config 4 with MountainCar registered at run time as a plugin (mctsb200_mdp_register: the NVRTC-compiled tile kernel), and
+    # its noisy variant (continuous-state stochastic transitions: state widening really widens)
+    "config4-dpw-mountaincar-plugin": dict(mdp="mc-plugin", mdp_kw=dict(), kind="dpw", policy="random",
+                                           solver_kw=dict(n_iterations=10000, depth=50), n_roots=1024),
+    "config4-dpw-noisy-mountaincar-plugin": dict(mdp="noisy-plugin", mdp_kw=dict(), kind="dpw", policy="random",
+                                                 solver_kw=dict(n_iterations=10000, depth=50), n_roots=1024),
 }
 
 
@@ -56,7 +62,7 @@ def make_workload(name, n_roots=None, lanes=0, n_iterations=None, same_root=None
 
     w = WORKLOADS[name]
     n = n_roots or w["n_roots"]
-    mdp = m.SimpleGridWorld(**w["mdp_kw"]) if w["mdp"] == "gw" else m.MountainCar(**w["mdp_kw"])
+    mdp = {"gw": m.SimpleGridWorld, "mc": m.MountainCar, "mc-plugin": m.MountainCarPlugin, "noisy-plugin": m.NoisyMountainCar}[w["mdp"]](**w["mdp_kw"])
     pol = {"up": m.ConstantPolicy("up"), "random": m.RandomSolver()}[w["policy"]]
     kw = dict(w["solver_kw"])
     if n_iterations:
@@ -142,16 +148,17 @@ def cpu_sample(workload, seconds_target=15.0, threads=None):
     threads = threads or max(1, os.cpu_count() or 1)
     mdp, solver, roots = make_workload(workload)
     cfg, keep = m.build_cfg(solver, mdp)
-    orc.configure(mdp.mdp_id, mdp.params())
+    oid = mdp.mdp_id if getattr(mdp, "oracle_mdp_id", None) is None else mdp.oracle_mdp_id  # (plugins: the oracle's own id)
+    orc.configure(oid, mdp.params())
     # calibrate on a small sample, then size the real one for ~seconds_target
     t0 = time.perf_counter()
-    _, _, _, st = orc.plan(cfg, mdp.mdp_id, roots[: 2 * threads], n_threads=threads, keep_trees=False)
+    _, _, _, st = orc.plan(cfg, oid, roots[: 2 * threads], n_threads=threads, keep_trees=False)
     dt = max(time.perf_counter() - t0, 1e-6)
     per_root = dt / (2 * threads)
     n = int(min(len(roots), max(threads, seconds_target / per_root)))
     n = max(threads, n // threads * threads)
     t0 = time.perf_counter()
-    _, _, _, st = orc.plan(cfg, mdp.mdp_id, roots[:n], n_threads=threads, keep_trees=False)
+    _, _, _, st = orc.plan(cfg, oid, roots[:n], n_threads=threads, keep_trees=False)
     dt = time.perf_counter() - t0
     return {"value": st.n_simulations / dt, "unit": "simulations/s", "cores": threads, "kind": "port",
             "sample": f"{n} of the workload's roots x {cfg.n_iterations} iterations (oracle, {threads} threads, {dt:.1f} s)",
