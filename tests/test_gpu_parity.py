@@ -336,3 +336,24 @@ def test_plugin_every_host_shape(gpu_ctx, oracle, actions):
     ret4, steps4, final4, _ = m.solve(s, m4, ctx=gpu_ctx).run_episodes(roots4, 5, 9)
     assert np.array_equal(ret2.view(np.int64), ret4.view(np.int64)) and np.array_equal(steps2, steps4)
     assert [f[:2] for f in final4] == list(final2) and all(f[2:] == (7.0, -3.0) for f in final4)
+
+
+def test_config1_root_q_within_3_sigma_over_1000_seeds(gpu_ctx, oracle):
+    """BASELINE config 1 (README case: one root, n_iterations=50, depth=20, c=5, random rollouts on the default stochastic
+    GridWorld) over 1 000 seeds. Same seeds: the device and the oracle agree bit-for-bit (stronger than the north star asks for a
+    stochastic model). Independent seeds -- how a run compares with the reference's own MersenneTwister-driven search: the mean
+    root Q of every action lies within 3 sigma of the other ensemble's (tolerance = 3 * sqrt(var_a/n + var_b/n))."""
+    n = 1000
+    roots = [(1, 2)] * n
+    solver_a = m.MCTSSolver(n_iterations=50, depth=20, exploration_constant=5.0, rng=0)
+    run_both(gpu_ctx, oracle, solver_a, GW, roots, compare_trees=range(0, n, 97))
+    qa = np.array([gpu_ctx.root_stats(i)["q"] for i in range(n)])
+    solver_b = m.MCTSSolver(n_iterations=50, depth=20, exploration_constant=5.0, rng=12345)
+    cfg, _ = m.build_cfg(solver_b, GW)
+    oracle.configure(GW.mdp_id, GW.params())
+    oracle.plan(cfg, GW.mdp_id, GW.encode_states(roots), n_threads=4)
+    qb = np.array([oracle.root_stats(i)["q"] for i in range(n)])
+    assert qa.shape == qb.shape == (n, 4)
+    tol = 3.0 * np.sqrt(qa.var(axis=0, ddof=1) / n + qb.var(axis=0, ddof=1) / n)
+    assert (np.abs(qa.mean(axis=0) - qb.mean(axis=0)) <= tol).all(), (qa.mean(axis=0), qb.mean(axis=0), tol)
+    assert (tol > 0).all() and not np.array_equal(qa, qb)
