@@ -80,6 +80,7 @@ struct Storage {
     Geometry geo{};
     size_t row_bytes = 0, aux_bytes = 0, map_entry_bytes = 0;
     DevBuf hdr, rows, aux, trans, map, path;
+    DevBuf plog;        // push-log arena of models with unbounded branching (search.cuh: kPushLog)
     DevBuf rows_fast;   // working table of uct_fast.cuh / dpw_fast.cuh (interleaved); `rows` receives the Row<M> table after the search
     DevBuf trans_fast;  // dpw_fast.cuh: per-slot transition multisets (interleaved)
     // the fast kernels' tables are converted to Row / Aux / TransRec only when a tree query needs them
@@ -343,11 +344,20 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
         MAP = next_pow2(2 * NS);
         map_entry = sizeof(HashSlot);
     }
+    // Unbounded branching (a plugin registered with max_branch = 0): every action node keeps the reference's transitions vector,
+    // one entry per push, in chunks that double. A node with p pushes has allocated < 4p + 8 entries in all.
+    long long NP = 0;
+    if (dpw && MdpAccess<M>::max_branch(ctx) >= (1LL << 30)) {
+        const long long pushes = std::max<long long>(1, n_iter * std::max(cfg->depth, 1));  // at most one push per tree level
+        NP = 4 * pushes + 8 * std::min<long long>(NS * A, pushes);
+        if (NP > 0x7fffffffLL) return fail(MCTSB200_ERR_CAPACITY, "push log would exceed 2^31 entries per tree");
+    }
     Geometry g;
     g.NS = (int)NS;
     g.NT = (int)std::max<long long>(NT, 1);
     g.MAP = (int)MAP;
     g.depth = std::max(cfg->depth, 1);
+    g.NP = (int)NP;
 
     const size_t b_hdr = sizeof(TreeHeader) * (size_t)n_trees;
     const size_t b_rows = sizeof(Row<M>) * (size_t)NS * (size_t)n_trees;
@@ -355,20 +365,22 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     const size_t b_trans = dpw ? sizeof(TransRec) * (size_t)g.NT * (size_t)n_trees : 0;
     const size_t b_map = map_entry * (size_t)MAP * (size_t)n_trees;
     const size_t b_path = direct ? 0 : sizeof(PathEntry) * (size_t)g.depth * (size_t)n_trees;
-    const size_t total = b_hdr + b_rows + b_aux + b_trans + b_map + b_path;
+    const size_t b_plog = sizeof(int) * (size_t)NP * (size_t)n_trees;
+    const size_t total = b_hdr + b_rows + b_aux + b_trans + b_map + b_path + b_plog;
 
     Storage& st = ctx->st;
     *reused = false;
     if (cfg->keep_tree && st.valid && st.keep && st.kind == cfg->kind && st.mdp_id == MdpAccess<M>::mdp_id(ctx) && st.n_trees == n_trees) {
-        if (st.direct != direct || st.geo.NS != g.NS || st.geo.NT != g.NT || st.geo.MAP != g.MAP)
+        if (st.direct != direct || st.geo.NS != g.NS || st.geo.NT != g.NT || st.geo.MAP != g.MAP || st.geo.NP != g.NP)
             return fail(MCTSB200_ERR_STATE, "the kept trees cannot be continued with this configuration (different kernel layout); call clear_tree first");
         CUDA_TRY(st.path.ensure(b_path));
         st.geo.depth = g.depth;
         *reused = true;
         return MCTSB200_OK;
     }
-    const size_t have = st.hdr.cap + st.rows.cap + st.aux.cap + st.trans.cap + st.map.cap + st.path.cap;
-    const bool grows = b_hdr > st.hdr.cap || b_rows > st.rows.cap || b_aux > st.aux.cap || b_trans > st.trans.cap || b_map > st.map.cap || b_path > st.path.cap;
+    const size_t have = st.hdr.cap + st.rows.cap + st.aux.cap + st.trans.cap + st.map.cap + st.path.cap + st.plog.cap;
+    const bool grows = b_hdr > st.hdr.cap || b_rows > st.rows.cap || b_aux > st.aux.cap || b_trans > st.trans.cap || b_map > st.map.cap ||
+                       b_path > st.path.cap || b_plog > st.plog.cap;
     if (grows) {  // (cudaMemGetInfo is slow: only ask when something has to be allocated)
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -383,6 +395,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     CUDA_TRY(st.trans.ensure(b_trans));
     CUDA_TRY(st.map.ensure(b_map));
     CUDA_TRY(st.path.ensure(b_path));
+    CUDA_TRY(st.plog.ensure(b_plog));
     st.kind = cfg->kind;
     st.direct = direct;
     st.keep = cfg->keep_tree != 0;
@@ -731,6 +744,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.rows = (Row<M>*)st.rows.p;
     args.aux = KIND == MCTSB200_KIND_DPW ? (Aux<M>*)st.aux.p : nullptr;
     args.trans = KIND == MCTSB200_KIND_DPW ? (TransRec*)st.trans.p : nullptr;
+    args.plog = (KIND == MCTSB200_KIND_DPW && st.geo.NP > 0) ? (int*)st.plog.p : nullptr;
     args.map = st.map.p;
     args.path = (PathEntry*)st.path.p;
     args.roots = d_roots;
@@ -1427,7 +1441,7 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     if (!c) return MCTSB200_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->counters,
+    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->st.plog, &c->counters,
                       &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
                       &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->gw_fast,
                       &c->ep_states, &c->ep_disc, &c->ep_ret, &c->ep_steps, &c->ep_active, &c->ep_count};

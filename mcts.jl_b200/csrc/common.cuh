@@ -100,7 +100,8 @@ struct TreeHeader {
     int root;        // 0-based root node id
     int status;      // MCTSB200_OK / ERR_TERMINAL_ROOT / ERR_CAPACITY
     int iterations;  // iterations completed
-    int pad[2];
+    int n_plog;      // push-log arena entries in use (unbounded-branching models)
+    int pad;
 };
 
 struct __align__(16) PathEntry {
@@ -153,6 +154,11 @@ struct __align__(32) Aux {
     // touching the record table: search.cuh, dpw_iteration)
     int sp1[M::kActions];
     double r1[M::kActions];
+    // models with unbounded branching (run-time plugins registered with max_branch = 0): the action node's push log -- the
+    // reference's transitions[sanode] vector itself, one record id per push, so rand(rng, transitions[sanode]) is one indexed
+    // load instead of a walk over up to k*n^alpha records. [pbase, pbase + pcap) in the tree's plog arena, grown by doubling.
+    int pbase[M::kActions];
+    int pcap[M::kActions];
 };
 
 // geometry of the tables of one plan call
@@ -161,6 +167,7 @@ struct Geometry {
     int NT;         // transition-record capacity per tree
     int MAP;        // map entries per tree (dense: n_dense u16; hash: power-of-two HashSlots)
     int depth;      // path entries per tree
+    int NP;         // push-log arena entries per tree (0 unless the model has unbounded branching)
 };
 
 enum CounterId {
@@ -213,6 +220,7 @@ struct KernelArgs {
     void* trans_fast;                   // dpw_fast.cuh: DpwTransRow table, [warp][state][lane]
     Aux<M>* aux;
     TransRec* trans;
+    int* plog;                          // push-log arena, [n_trees][NP] (null unless the model has unbounded branching)
     void* map;
     PathEntry* path;
     const typename M::AbiState* roots;  // device

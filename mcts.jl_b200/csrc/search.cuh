@@ -134,7 +134,8 @@ struct Search {
     HashSlot* hmap;
     uint64_t tree_index;
     // header mirror (registers, tile-uniform)
-    int n_state, n_action, n_trans, status;
+    int n_state, n_action, n_trans, n_plog, status;
+    int* plog;  // this tree's push-log arena
     // per-lane work counters (per-tree counts fit 32 bits: n_iterations*depth <= 2e9 is validated on the host;
     // rollout steps can exceed that and are kept in 64 bits)
     unsigned cnt[CNT_COUNT];
@@ -153,6 +154,8 @@ struct Search {
         rows = args.rows + tree * args.geo.NS;
         aux = args.aux ? args.aux + tree * args.geo.NS : nullptr;
         trans = args.trans ? args.trans + tree * args.geo.NT : nullptr;
+        plog = args.plog ? args.plog + tree * args.geo.NP : nullptr;
+        n_plog = 0;
         path = args.path + tree * args.geo.depth;
         path_stride = 1;
         dmap = M::kDense ? (uint16_t*)args.map + tree * args.geo.MAP : nullptr;
@@ -588,6 +591,8 @@ struct Search {
             ax->nac[slot] = 0;
             ax->thead[slot] = -1;
             ax->tpush[slot] = 0;
+            ax->pbase[slot] = 0;
+            ax->pcap[slot] = 0;
             ax->seq[slot] = n_action + 1;
             cnt[CNT_ACTION_INSERTS] += 1;
         }
@@ -604,6 +609,10 @@ struct Search {
         return out;
     }
 
+    // unbounded branching (a run-time plugin registered with max_branch = 0): transitions[sanode] is kept as the reference keeps
+    // it, a vector with one entry per push (Aux::pbase / pcap, the plog arena); otherwise as distinct records with multiplicities
+    static constexpr bool kPushLog = M::kMaxBranch == 0;
+
     // one iteration of src/dpw.jl:48-56: simulate(dpw, snode, depth) as descent + backup
     __device__ __forceinline__ void dpw_iteration(int root, uint32_t it) {
         Stream rng;
@@ -619,7 +628,7 @@ struct Search {
             // row -> aux -> transition record -> successor's label.
             Row<M>* rw = rows + node;
             Aux<M>* ax = aux + node;
-            int x_nac[A], x_thead[A], x_tpush[A], x_sp1[A];
+            int x_nac[A], x_thead[A], x_tpush[A], x_sp1[A], x_pbase[A], x_pcap[A];
             double x_r1[A];
 #pragma unroll
             for (int k = 0; k < A; ++k) {
@@ -628,6 +637,8 @@ struct Search {
                 x_tpush[k] = ax->tpush[k];
                 x_sp1[k] = ax->sp1[k];
                 x_r1[k] = ax->r1[k];
+                x_pbase[k] = kPushLog ? ax->pbase[k] : 0;
+                x_pcap[k] = kPushLog ? ax->pcap[k] : 0;
             }
             s = M::state_of(a.mdp, rw->key);
             if (M::is_terminal(a.mdp, s)) break;
@@ -653,6 +664,7 @@ struct Search {
                                 x_nac[k] = 0;
                                 x_thead[k] = -1;
                                 x_tpush[k] = 0;
+                                x_pcap[k] = 0;
                             }
                         ++nchild;
                         tile.sync();
@@ -665,6 +677,7 @@ struct Search {
                     x_nac[k] = 0;
                     x_thead[k] = -1;
                     x_tpush[k] = 0;
+                    x_pcap[k] = 0;
                 }
                 nchild = A;
                 tile.sync();
@@ -720,6 +733,28 @@ struct Search {
                     leaf = 2;
                     break;
                 }
+                if constexpr (kPushLog) {
+                    // push!(transitions[sanode], ...) literally: append the record id to the action node's log
+                    const int pushes = pick(x_tpush, slot), cap = pick(x_pcap, slot);
+                    int base = pick(x_pbase, slot);
+                    if (pushes == cap) {  // full (or not allocated yet): move to a chunk twice as large at the end of the arena
+                        const int ncap = cap ? 2 * cap : 4;
+                        if (n_plog + ncap > a.geo.NP) {
+                            status = MCTSB200_ERR_CAPACITY;
+                            leaf = 2;
+                            break;
+                        }
+                        const int nbase = n_plog;
+                        for (int i = tile.lane; i < pushes; i += G) plog[nbase + i] = plog[base + i];
+                        if (lead()) {
+                            ax->pbase[slot] = nbase;
+                            ax->pcap[slot] = ncap;
+                        }
+                        n_plog += ncap;
+                        base = nbase;
+                    }
+                    if (lead()) plog[base + pushes] = rec >= 0 ? rec : n_trans;
+                }
                 if (lead()) {
                     if (rec >= 0) {
                         bump_count(&trans[rec].count);
@@ -747,6 +782,10 @@ struct Search {
                 if (M::kMaxBranch == 1 && a.cfg.check_repeat_state) {  // a single record: every draw picks it
                     spnode = pick(x_sp1, slot);
                     r = pick(x_r1, slot);
+                } else if (kPushLog) {  // transitions[sanode][j]
+                    const int rec = plog[pick(x_pbase, slot) + j];
+                    spnode = trans[rec].sp;
+                    r = trans[rec].r;
                 } else {
                     int jm = pushes - 1 - j, cum = 0, rec = pick(x_thead, slot);
                     for (;;) {
@@ -811,6 +850,7 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
         S.n_state = h.n_state;
         S.n_action = h.n_action;
         S.n_trans = h.n_trans;
+        S.n_plog = h.n_plog;
         S.status = h.status;
         int root = h.root;
 
@@ -850,6 +890,7 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
             h.n_state = S.n_state;
             h.n_action = S.n_action;
             h.n_trans = S.n_trans;
+            h.n_plog = S.n_plog;
             h.status = S.status;
             h.root = root;
             h.iterations = S.status == MCTSB200_OK ? args.iter_end : it;

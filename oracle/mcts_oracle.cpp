@@ -142,6 +142,7 @@ struct GWPosHash {
 // SimpleGridWorld: actions (:up,:down,:left,:right); dir up(0,1) down(0,-1) left(-1,0) right(1,0).
 struct GridWorld {
     static constexpr int kMdpId = MCTSB200_MDP_GRIDWORLD;
+    static constexpr bool kLiteralTransitions = false;  // (the device keeps transitions[sanode] as records with multiplicities)
     using State = GWPos;
     static constexpr int kActions = 4;
     int nx = 10, ny = 10;
@@ -218,6 +219,7 @@ struct MCStateHash {
 // MountainCar: actions [-1., 0., 1.]; gen is deterministic.
 struct MountainCar {
     static constexpr int kMdpId = MCTSB200_MDP_MOUNTAINCAR;
+    static constexpr bool kLiteralTransitions = false;
     using State = MCState;
     static constexpr int kActions = 3;
     double gamma, cost, jackpot;
@@ -255,6 +257,7 @@ struct NoisyMountainCarParams {
 constexpr int kOracleMdpNoisyMountainCar = 1000;  // oracle-side id (the library's plugin ids are assigned at registration)
 struct NoisyMountainCar {
     static constexpr int kMdpId = kOracleMdpNoisyMountainCar;
+    static constexpr bool kLiteralTransitions = true;  // unbounded branching: the device keeps the push-ordered vector itself
     using State = MCState;
     static constexpr int kActions = 3;
     double gamma, cost, jackpot, noise, push[4];
@@ -882,7 +885,7 @@ static void plan_one(const M& mdp, const mctsb200_solver_cfg& cfg, const typenam
         }
         if (cfg.keep_tree && saved) *saved = p.save();
     } else {
-        DPWPlanner<M, H> p(mdp, cfg, tree_index, literal);
+        DPWPlanner<M, H> p(mdp, cfg, tree_index, literal || M::kLiteralTransitions);
         using SavedT = typename DPWPlanner<M, H>::Saved;
         if (cfg.keep_tree && saved && saved->has_value()) p.load(std::move(std::any_cast<SavedT&>(*saved)));
         int64_t rootid = 0;
