@@ -157,6 +157,32 @@ def test_full_size_config3_dpw_sampled_oracle(gpu_ctx, oracle):
     del keep
 
 
+def test_full_size_config4_mountaincar_sampled_oracle(gpu_ctx, oracle):
+    """BASELINE config 4 at the size one GPU plans (1,024 of the 8,192 MountainCar roots, DPWSolver(n_iterations=10_000, depth=50),
+    random rollouts): size-independent properties of every tree and whole sampled trees against the oracle, bit-for-bit. Roots
+    are indexed as rank 3 of the 8-GPU run would index them (global root index = Philox stream)."""
+    n, base = 1024, 3 * 1024
+    roots = mountaincar_roots(8192)[base:base + n]
+    solver = m.DPWSolver(n_iterations=10000, depth=50, rng=0)
+    cfg, keep = m.build_cfg(solver, MC)
+    gpu_ctx.configure(MC.mdp_id, MC.params())
+    enc = MC.encode_states(roots)
+    a, q, st, stats = gpu_ctx.plan(cfg, MC.mdp_id, enc, base, want_status=True)
+    assert stats.kernel_variant == 0 and stats.n_simulations == n * 10000 and (st == 0).all()
+    assert stats.n_rollouts >= stats.n_state_inserts - n  # a rollout per new state node (every node but the roots), and per depth-0 leaf
+    for i in range(0, n, 37):
+        rs = gpu_ctx.root_stats(i)
+        assert rs["total_n"] == 10000 == int(rs["n"].sum()) and len(rs["n"]) == 3  # every iteration backs up through the root
+        assert q[i] == rs["q"].max() and a[i] == int(rs["action_idx"][int(np.argmax(rs["q"]))])
+    oracle.configure(MC.mdp_id, MC.params())
+    from helpers import assert_trees_equal
+    for i in (0, 511, 1023):
+        a2, q2, _, _ = oracle.plan(cfg, MC.mdp_id, enc[i:i + 1], base + i)
+        assert a2[0] == a[i] and q2.view(np.int64)[0] == q.view(np.int64)[i]
+        assert_trees_equal(gpu_ctx.tree_export(i, MC.state_dtype, MC.state_width), oracle.tree_export(0, MC.state_dtype, MC.state_width), f"tree {i}")
+    del keep
+
+
 @pytest.mark.parametrize("kind,lanes", [("uct", None), ("dpw", None), ("uct", 4), ("dpw", 8)])
 def test_kept_trees_continue_across_calls(gpu_ctx, oracle, kind, lanes):
     """reuse_tree (src/vanilla.jl:213-217) / keep_tree (src/dpw.jl:31-37): an episode-like sequence of plan calls grows the
