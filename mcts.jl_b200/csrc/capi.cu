@@ -593,7 +593,7 @@ int32_t tile_launch(mctsb200_ctx* ctx, const KernelArgs<M>& args, int G) {
         if (!k) return MCTSB200_ERR_CUDA;
         const long long threads = args.n_slots * G;
         const unsigned grid = (unsigned)((threads + kBlockThreads - 1) / kBlockThreads);
-        const size_t smem = args.path_smem ? path_smem_bytes(args.geo.depth, G) : 0;
+        const size_t smem = args.path_smem ? path_smem_bytes(args.geo.depth, G, args.path_tiles) : 0;
         void* params[] = {(void*)&args};
         CUDA_TRY(cudaLaunchKernel(k, dim3(grid), dim3(kBlockThreads), params, smem, ctx->stream));
         return MCTSB200_OK;
@@ -819,6 +819,15 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             CUDA_TRY(cudaGetLastError());
             args.order = (const int*)ctx->order.p;
             launches += 1;
+            if (fast < 0) {
+                // only the first `active` tiles of a warp hold a tree: their path stacks are all the block needs in shared memory
+                // (depth 50 with one tree per warp: 3 KB instead of 100 KB, which did not fit and left the stacks in HBM)
+                args.path_tiles = active;
+                args.path_smem = (env_enabled("MCTSB200_PATH_SMEM") && path_smem_bytes(st.geo.depth, G, active) <= kPathSmemLimit) ? 1 : 0;
+#ifdef MCTSB200_HOST_EMU
+                args.path_smem = 0;
+#endif
+            }
         }
     }
     if (fast >= 0) {

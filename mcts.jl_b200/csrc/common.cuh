@@ -231,6 +231,7 @@ struct KernelArgs {
     const int* order;                   // device, may be null: tile slot -> tree or -1 (see order_*_kernel in search.cuh)
     long long n_slots;                  // tile slots of the launch (= n_trees without an order)
     int path_smem;                      // 1: the path stacks of a block live in dynamic shared memory, [level][tile]
+    int path_tiles;                     // tiles per warp that own a path stack (0 = all 32/G; fewer when the trees are spread one per warp)
     int iter_begin, iter_end;
 };
 

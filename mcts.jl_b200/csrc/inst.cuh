@@ -9,7 +9,7 @@ static void launch_one(const KernelArgs<M>& args, cudaStream_t stream) {
     const long long threads = args.n_slots * G;
     const unsigned grid = (unsigned)((threads + kBlockThreads - 1) / kBlockThreads);
     auto kernel = search_kernel<M, KIND, G>;
-    const size_t smem = args.path_smem ? path_smem_bytes(args.geo.depth, G) : 0;
+    const size_t smem = args.path_smem ? path_smem_bytes(args.geo.depth, G, args.path_tiles) : 0;
     MCTSB200_LAUNCH(kernel, grid, kBlockThreads, smem, stream, args);
 }
 

@@ -841,8 +841,10 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
 #ifndef MCTSB200_HOST_EMU
         if (args.path_smem) {  // [level][tile]: tiles at the same level touch consecutive 16 B entries
             extern __shared__ __align__(16) unsigned char dyn_smem[];
-            S.path = reinterpret_cast<PathEntry*>(dyn_smem) + threadIdx.x / G;
-            S.path_stride = kBlockThreads / G;
+            // (spread batches keep their trees in the first path_tiles tiles of each warp: only those get a stack)
+            const int tpw = args.path_tiles ? args.path_tiles : 32 / G;
+            S.path = reinterpret_cast<PathEntry*>(dyn_smem) + (threadIdx.x >> 5) * tpw + (threadIdx.x & 31) / G;
+            S.path_stride = (kBlockThreads / 32) * tpw;
         }
 #endif
         TreeHeader* hd = args.hdr + tree;
@@ -1078,7 +1080,9 @@ __global__ void order_scatter_kernel(const typename M::Params mdp, const typenam
 }
 
 // dynamic shared memory of one block of the G variant: the path stacks, if they fit
-__host__ __device__ static inline size_t path_smem_bytes(int depth, int G) { return sizeof(PathEntry) * (size_t)depth * (size_t)(kBlockThreads / G); }
+__host__ __device__ static inline size_t path_smem_bytes(int depth, int G, int path_tiles = 0) {
+    return sizeof(PathEntry) * (size_t)depth * (size_t)(kBlockThreads / 32) * (size_t)(path_tiles ? path_tiles : 32 / G);
+}
 constexpr size_t kPathSmemLimit = 48 * 1024;
 
 #ifndef __CUDACC_RTC__  // (host-side launchers: not part of a run-time compiled plugin program, plugin_rt.cu)
