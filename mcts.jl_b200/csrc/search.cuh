@@ -284,11 +284,13 @@ struct Search {
             const PathEntry e = path[lvl * path_stride];
             const double qv = DM_ADD(e.r, DM_MUL(gamma, v));
             if (lead()) {
+                // all three reads before the first write: a load that follows a store to the same line waits for L2
                 Row<M>* rw = rows + e.node;
                 const int nn = rw->n[e.slot] + 1;
-                rw->n[e.slot] = nn;
-                rw->total_n += 1;
+                const int tn = rw->total_n + 1;
                 const double qo = rw->q[e.slot];
+                rw->n[e.slot] = nn;
+                rw->total_n = tn;
                 rw->q[e.slot] = DM_ADD(qo, div_by_count(DM_SUB(qv, qo), i2d(nn)));
             }
             v = qv;
