@@ -160,7 +160,14 @@ def cpu_sample(workload, seconds_target=15.0, threads=None):
     t0 = time.perf_counter()
     _, _, _, st = orc.plan(cfg, oid, roots[:n], n_threads=threads, keep_trees=False)
     dt = time.perf_counter() - t0
-    return {"value": st.n_simulations / dt, "unit": "simulations/s", "cores": threads, "kind": "port",
+    # the reference solver itself is single-threaded (one planner, one tree): the same port on ONE thread, a ~5 s sample
+    n1 = int(max(1, min(len(roots), 5.0 / max(per_root * threads, 1e-9))))
+    t1 = time.perf_counter()
+    _, _, _, st1 = orc.plan(cfg, oid, roots[:n1], n_threads=1, keep_trees=False)
+    dt1 = time.perf_counter() - t1
+    single = {"value": st1.n_simulations / dt1, "unit": "simulations/s", "cores": 1,
+              "sample": f"{n1} of the workload's roots x {cfg.n_iterations} iterations (oracle, 1 thread, {dt1:.1f} s)"}
+    return {"value": st.n_simulations / dt, "unit": "simulations/s", "cores": threads, "kind": "port", "single_thread": single,
             "sample": f"{n} of the workload's roots x {cfg.n_iterations} iterations (oracle, {threads} threads, {dt:.1f} s)",
             "rollout_steps_per_s": st.n_rollout_steps / dt, "seconds": dt, "n_simulations": int(st.n_simulations),
             "n_iterations": int(cfg.n_iterations), "depth": int(cfg.depth)}
