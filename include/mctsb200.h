@@ -185,6 +185,10 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
  * Plugin MDPs run on the tile kernel: hashed states, so no dense tables (init_q_table, value_table) and no keep_tree. */
 int32_t mctsb200_mdp_register(const char* name, const char* cuda_source, const char* plugin_struct, int32_t state_doubles,
                               int32_t n_actions, int32_t max_branch, int32_t* mdp_id_out);
+/* Compiled plugin programs are cached on disk, keyed by a hash of the generated program, the library's kernel sources, the compiler
+ * options and the CUDA version ($MCTSB200_CACHE_DIR, default ~/.cache/mctsb200; MCTSB200_CACHE=0 disables): a later process
+ * registers a known plugin without running the compiler. Counts for this process: programs read from the cache / compiled. */
+int32_t mctsb200_plugin_cache_stats(int64_t* hits_out, int64_t* misses_out);
 
 /* ---- planning: replaces build_tree (src/vanilla.jl:209-237) / the DPW loop (src/dpw.jl:29-67) ---- */
 /* Plans for n_roots independent root states (one tree each). roots: n_roots*state_bytes host bytes.

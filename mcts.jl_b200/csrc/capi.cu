@@ -1509,6 +1509,16 @@ int32_t mctsb200_mdp_register(const char* name, const char* cuda_source, const c
 #endif
 }
 
+int32_t mctsb200_plugin_cache_stats(int64_t* hits_out, int64_t* misses_out) {
+    long long h = 0, m = 0;
+#ifndef MCTSB200_HOST_EMU
+    mctsb200_rt::plugin_cache_stats(&h, &m);
+#endif
+    if (hits_out) *hits_out = h;
+    if (misses_out) *misses_out = m;
+    return MCTSB200_OK;
+}
+
 int32_t mctsb200_mdp_info(int32_t mdp_id, int32_t* n_actions, int64_t* state_bytes) {
     if (mdp_id == MCTSB200_MDP_GRIDWORLD) {
         if (n_actions) *n_actions = GridWorldDev::kActions;

@@ -24,5 +24,7 @@ const PluginInfo* plugin_info(int index);       // null if unknown
 const void* plugin_kernel(int index, int kind, int kernel_id, std::string& err);
 // The generated program text of (plugin, kind): what NVRTC is given besides the embedded library headers.
 std::string plugin_program_text(const PluginInfo& info, int kind);
+// Programs of this process served from the on-disk cache ($MCTSB200_CACHE_DIR) / compiled with NVRTC.
+void plugin_cache_stats(long long* hits, long long* misses);
 
 }  // namespace mctsb200_rt

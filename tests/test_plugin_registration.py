@@ -77,3 +77,33 @@ def test_plugin_policy_cfg():
     assert cfg.rollout_policy == abi.POLICY_PLUGIN and list(cfg.rollout_policy_param)[:2] == [1, 2]
     with pytest.raises(ValueError):
         m.build_cfg(m.DPWSolver(estimate_value=m.RolloutEstimator(m.PluginPolicy(5))), mdp)
+
+
+def test_compiled_programs_are_cached_on_disk(tmp_path):
+    """A second process registers a known plugin from the on-disk cache ($MCTSB200_CACHE_DIR) without running the compiler; a
+    changed definition misses."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import ctypes as C, sys, mcts_jl_b200 as m\n"
+            "mdp = m.MountainCarPlugin(name='CacheProbe')\n"
+            "if len(sys.argv) > 1: mdp.source = mdp.source.replace('0.001', '0.0015')\n"
+            "mdp.mdp_id\n"
+            "h, mi = C.c_int64(), C.c_int64()\n"
+            "m.load_library().mctsb200_plugin_cache_stats(C.byref(h), C.byref(mi))\n"
+            "print('STATS', h.value, mi.value)\n")
+    env = dict(os.environ, MCTSB200_CACHE_DIR=str(tmp_path / "cache"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(*args):
+        out = subprocess.run([sys.executable, "-c", code, *args], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        return [int(x) for x in out.stdout.split("STATS")[1].split()]
+
+    assert run() == [0, 1]          # compiled, stored
+    assert len(list((tmp_path / "cache").glob("plugin_*.bin"))) == 1
+    assert run() == [1, 0]          # served from the cache
+    assert run("changed") == [0, 1]  # another definition: another key
+    env["MCTSB200_CACHE"] = "0"
+    assert run() == [0, 1]          # cache off
