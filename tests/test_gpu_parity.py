@@ -383,3 +383,25 @@ def test_config1_root_q_within_3_sigma_over_1000_seeds(gpu_ctx, oracle):
     tol = 3.0 * np.sqrt(qa.var(axis=0, ddof=1) / n + qb.var(axis=0, ddof=1) / n)
     assert (np.abs(qa.mean(axis=0) - qb.mean(axis=0)) <= tol).all(), (qa.mean(axis=0), qb.mean(axis=0), tol)
     assert (tol > 0).all() and not np.array_equal(qa, qb)
+
+
+def test_plugin_max_time_callback_and_value_queries(gpu_ctx, oracle):
+    """The host hooks between launches (max_time chunks, per-iteration callback; src/vanilla.jl:229-235, src/dpw.jl:44-56) and the
+    tree queries on a plugin MDP: the chunked launches go through the run-time compiled kernels, and a search cut into chunks
+    builds the same tree as an unchunked one."""
+    mdp = m.NoisyMountainCar()
+    root = (-0.5, 0.0)
+    p = m.solve(m.DPWSolver(n_iterations=2**63 - 1, depth=20, max_time=0.2), mdp, ctx=gpu_ctx)
+    a = p.action(root)
+    assert a in mdp.actions and 0 < p.last_stats.iterations_done < 2**24
+    calls = []
+    pc = m.solve(m.MCTSSolver(n_iterations=40, depth=15, exploration_constant=3.0, rng=4, callback=lambda pl, i: calls.append((i, len(pl.tree.total_n))),
+                              callback_every=16), mdp, ctx=gpu_ctx)
+    a1, info1 = pc.action_info(root)
+    assert [c[0] for c in calls] == [16, 32, 40] and calls[0][1] <= calls[-1][1]
+    pu = m.solve(m.MCTSSolver(n_iterations=40, depth=15, exploration_constant=3.0, rng=4), mdp, ctx=gpu_ctx)
+    a2, info2 = pu.action_info(root)
+    assert a1 == a2 and info1["best_Q"] == info2["best_Q"]
+    assert pu.value(root) == info2["best_Q"] and pu.value(root, a2) == info2["best_Q"]
+    ranked = m.ranked_actions(pu, root)
+    assert ranked[0][0] == a2 and len(ranked) == 3
