@@ -12,6 +12,8 @@
 //         __device__ static int policy_action(const Params& p, int policy, const int* pp, const double* s, mctsb200::Stream& rng);
 //     };
 //
+// Params is an opaque POD to the library: it may carry pointers to tables the caller keeps in device memory (a tabular model, a
+// value table; tests/test_gpu_parity.py::test_plugin_params_may_carry_device_pointers).
 // `a` is the 0-based index into actions(mdp); random numbers come from `rng.next()` (32-bit words of the tree's Philox
 // stream), `rng.uniform_int(n)`, `rng.uniform01()`. The source sees everything search.cuh sees (DM_ADD / DM_MUL /
 // det_cos / det_log for reproducible arithmetic). The library compiles search_kernel<CustomDev<SD, A>, KIND, G> around

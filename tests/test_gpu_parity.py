@@ -405,3 +405,37 @@ def test_plugin_max_time_callback_and_value_queries(gpu_ctx, oracle):
     assert pu.value(root) == info2["best_Q"] and pu.value(root, a2) == info2["best_Q"]
     ranked = m.ranked_actions(pu, root)
     assert ranked[0][0] == a2 and len(ranked) == 3
+
+
+def test_plugin_params_may_carry_device_pointers(gpu_ctx):
+    """A plugin's Params are an opaque POD: they may hold pointers to tables the caller keeps in device memory (a tabular model,
+    a learned value table, ...). The noisy MountainCar with its action table behind a device pointer plans exactly like the one
+    that carries the table inside Params."""
+    import ctypes as C
+
+    import torch
+
+    ref = m.NoisyMountainCar()
+    src = ref.source.replace("double push[4];", "const double* push;").replace("p.push[ai]", "__ldg(p.push + ai)")
+    assert src != ref.source
+
+    class P(C.Structure):
+        _fields_ = [("discount", C.c_double), ("cost", C.c_double), ("jackpot", C.c_double), ("noise", C.c_double), ("push", C.c_void_p),
+                    ("n_actions", C.c_int32), ("pad", C.c_int32)]
+
+    table = torch.tensor([ref.params_struct.push[i] for i in range(3)], dtype=torch.float64, device="cuda")
+    rp = ref.params_struct
+    mdp = m.PluginMDP(name="NoisyMountainCarTable", source=src, struct_name="NoisyMountainCar", actions=ref.actions,
+                      params_struct=P(rp.discount, rp.cost, rp.jackpot, rp.noise, table.data_ptr(), 3, 0), state_width=2, max_branch=0)
+    roots = mountaincar_roots(24, seed=5)
+    out = []
+    for model in (ref, mdp):
+        res = []
+        for solver in (m.DPWSolver(n_iterations=300, depth=25, rng=31), m.MCTSSolver(n_iterations=200, depth=15, exploration_constant=3.0, rng=32)):
+            cfg, _ = m.build_cfg(solver, model)
+            gpu_ctx.configure(model.mdp_id, model.params())
+            res.append(gpu_ctx.plan(cfg, model.mdp_id, model.encode_states(roots), 0, want_status=True))
+        out.append(res)
+    for x, y in zip(*out):
+        _same_results(x, y)
+    del table
