@@ -21,7 +21,7 @@
 // a plugin ever runs on the host (north star: no CPU fallback).
 //
 // The host half of the library is compiled ahead of time for a fixed set of shapes (SD state doubles x A actions, see
-// MCTSB200_CUSTOM_SHAPES in capi.cu); the layout of KernelArgs<CustomDev<SD, A>> does not depend on the plugin.
+// MCTSB200_FOR_PLUGIN in capi.cu); the layout of KernelArgs<CustomDev<SD, A>> does not depend on the plugin.
 #pragma once
 #include "common.cuh"
 
