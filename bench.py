@@ -47,6 +47,9 @@ WORKLOADS = {
                                                  k_action=4.0, alpha_action=1 / 8), n_roots=16384),
     "config4-dpw-mountaincar": dict(mdp="mc", mdp_kw=dict(), kind="dpw", policy="random", solver_kw=dict(n_iterations=10000, depth=50),
                                     n_roots=1024),
+    # (not a BASELINE config) vanilla UCT on MountainCar: the tile kernel's successor cache for single-successor hashed models
+    "uct-mountaincar": dict(mdp="mc", mdp_kw=dict(), kind="uct", policy="random",
+                            solver_kw=dict(n_iterations=10000, depth=50, exploration_constant=10.0), n_roots=1024),
     # config 4 with MountainCar registered at run time as a plugin (mctsb200_mdp_register: the NVRTC-compiled tile kernel), and
     # its noisy variant (continuous-state stochastic transitions: state widening really widens)
     "config4-dpw-mountaincar-plugin": dict(mdp="mc-plugin", mdp_kw=dict(), kind="dpw", policy="random",

@@ -361,7 +361,9 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
 
     const size_t b_hdr = sizeof(TreeHeader) * (size_t)n_trees;
     const size_t b_rows = sizeof(Row<M>) * (size_t)NS * (size_t)n_trees;
-    const size_t b_aux = dpw ? sizeof(Aux<M>) * (size_t)NS * (size_t)n_trees : 0;
+    // (vanilla UCT on a hashed-state single-successor model keeps its successor cache in the same table: search.cuh, kSuccCache)
+    const bool uct_succ_cache = !dpw && !M::kDense && MdpAccess<M>::max_branch(ctx) == 1;
+    const size_t b_aux = (dpw || uct_succ_cache) ? sizeof(Aux<M>) * (size_t)NS * (size_t)n_trees : 0;
     const size_t b_trans = dpw ? sizeof(TransRec) * (size_t)g.NT * (size_t)n_trees : 0;
     const size_t b_map = map_entry * (size_t)MAP * (size_t)n_trees;
     const size_t b_path = direct ? 0 : sizeof(PathEntry) * (size_t)g.depth * (size_t)n_trees;
@@ -742,7 +744,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.geo = st.geo;
     args.hdr = (TreeHeader*)st.hdr.p;
     args.rows = (Row<M>*)st.rows.p;
-    args.aux = KIND == MCTSB200_KIND_DPW ? (Aux<M>*)st.aux.p : nullptr;
+    args.aux = (KIND == MCTSB200_KIND_DPW || (!M::kDense && MdpAccess<M>::max_branch(ctx) == 1 && env_enabled("MCTSB200_SUCC_CACHE"))) ? (Aux<M>*)st.aux.p : nullptr;
     args.trans = KIND == MCTSB200_KIND_DPW ? (TransRec*)st.trans.p : nullptr;
     args.plog = (KIND == MCTSB200_KIND_DPW && st.geo.NP > 0) ? (int*)st.plog.p : nullptr;
     args.map = st.map.p;

@@ -171,6 +171,16 @@ struct Search {
     // exact int -> double for 0 <= n < 2^31 on the FP64 pipe (I2F.F64 would go through the 16-lane XU pipe)
     __device__ __forceinline__ static double i2d(int n) { return DM_SUB(__hiloint2double(0x43300000, n), 4503599627370496.0); }
 
+    // element `slot` of a small per-child array held in registers (a dynamic index would move the array to local memory)
+    template <class T2>
+    __device__ __forceinline__ static T2 pick_a(const T2 (&v)[M::kActions], int slot) {
+        T2 out = v[0];
+#pragma unroll
+        for (int k = 1; k < M::kActions; ++k)
+            if (slot == k) out = v[k];
+        return out;
+    }
+
     // ---- numeric hooks (src/domain_knowledge.jl:10,82,91 + table stand-ins) ----
     __device__ __forceinline__ double init_Q(const State& s, int act) const {
         if (M::kDense && a.cfg.init_q_table) return __ldg(a.cfg.init_q_table + M::dense_index(a.mdp, s) * A + act);
@@ -329,11 +339,20 @@ struct Search {
             map_insert(s, id);
             cnt[CNT_STATE_INSERTS] += 1;
             cnt[CNT_ACTION_INSERTS] += A;
+            if (kSuccCache && aux) {
+#pragma unroll
+                for (int k = 0; k < A; ++k) aux[id].sp1[k] = -1;  // successors not looked up yet
+            }
         }
         n_state = id + 1;
         n_action += A;
         return id;
     }
+
+    // Vanilla UCT on a hashed-state model whose (s, a) has a single successor (MountainCar, plugins registered with
+    // max_branch = 1; their gen draws no random numbers): the node a child leads to is remembered in Aux::sp1 / r1 the first time it
+    // is looked up, and later visits follow it without the transition arithmetic and the hash probe.
+    static constexpr bool kSuccCache = M::kMaxBranch == 1 && !M::kDense;
 
     // ---- selection ---------------------------------------------------------------------------
     static constexpr int T = (A + G - 1) / G;  // children per lane
@@ -530,19 +549,43 @@ struct Search {
                 break;
             }
             if (lead()) cnt[CNT_LEVELS] += 1;
+            const bool cache = kSuccCache && aux != nullptr;
+            int c_sp[A];
+            double c_r[A];
+            if (cache) {  // (requested together with the row the selection reads)
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    c_sp[k] = aux[node].sp1[k];
+                    c_r[k] = aux[node].r1[k];
+                }
+            }
             const int slot = select_child(rows + node, A, false);
             State sp;
             double r;
-            M::gen(a.mdp, s, slot, rng, sp, r);
+            int next;
+            const int known = cache ? pick_a(c_sp, slot) : -1;
+            if (known >= 0) {
+                next = known;
+                r = pick_a(c_r, slot);
+                sp = M::state_of(a.mdp, rows[next].key);
+            } else {
+                M::gen(a.mdp, s, slot, rng, sp, r);
+                next = map_lookup(sp);
+            }
             if (lead()) path[top * path_stride] = PathEntry{node, slot, r};
             ++top;
             --d;
             s = sp;
-            node = map_lookup(sp);
-            if (node < 0) {
-                leaf = uct_insert(sp) < 0 ? 2 : 1;  // new node: estimate_value(sp, depth-1), also when sp is terminal
-                break;
+            if (next < 0) {
+                next = uct_insert(sp);  // new node: estimate_value(sp, depth-1), also when sp is terminal
+                leaf = next < 0 ? 2 : 1;
             }
+            if (cache && known < 0 && next >= 0 && lead()) {
+                aux[node].sp1[slot] = next;
+                aux[node].r1[slot] = r;
+            }
+            if (leaf) break;
+            node = next;
         }
         if (leaf == 2) return;  // capacity error: abandon this simulation
         tile.sync();
