@@ -177,8 +177,9 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
  * `cuda_source` is CUDA C++ text defining `struct <plugin_struct>` with the members documented in
  * mcts.jl_b200/csrc/custom.cuh (Params beginning with `double discount`, is_terminal, gen, policy_action); states are
  * `state_doubles` float64 values (2 or 4: pad unused ones with 0.0), actions are indices 0..n_actions-1 (2, 3 or 4),
- * `max_branch` bounds the distinct successors of one (s, a): 1 = deterministic transitions, 0 = unbounded (continuous
- * noise). The tile kernel is compiled around the plugin with NVRTC for sm_100a; compiler errors are returned through
+ * `max_branch` bounds the distinct successors of one (s, a): 0 = unbounded (always correct; what a host wrapper should
+ * default to), 1 = deterministic transitions -- an explicit promise: the kernels then reuse the first sampled successor of an
+ * action node instead of calling gen again, so a stochastic gen registered with 1 would get silently narrow trees. The tile kernel is compiled around the plugin with NVRTC for sm_100a; compiler errors are returned through
  * mctsb200_last_error(). Needs no GPU (the cubin is loaded at the first plan call). The id is process-wide; every ctx
  * configures its own parameters with mctsb200_mdp_configure(ctx, id, &Params, sizeof(Params)). Registering the same
  * name again with a different definition replaces it (same id). mctsb200_mdp_lookup / mctsb200_mdp_info know the id.

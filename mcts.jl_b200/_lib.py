@@ -62,7 +62,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     return lib
 
 
-def register_mdp(name: str, cuda_source: str, plugin_struct: str, state_doubles: int, n_actions: int, max_branch: int = 1,
+def register_mdp(name: str, cuda_source: str, plugin_struct: str, state_doubles: int, n_actions: int, max_branch: int = 0,
                  lib_path: Optional[str] = None) -> int:
     """mctsb200_mdp_register: compile the tile kernel around a device-side MDP plugin (NVRTC, sm_100a) and return its
     process-wide mdp_id. Compiler errors raise MCTSB200Error with the NVRTC log. Needs no GPU."""

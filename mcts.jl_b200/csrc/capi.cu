@@ -716,7 +716,7 @@ int32_t finalize_pending(mctsb200_ctx* ctx) {
 template <class M, int KIND>
 int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const typename M::AbiState* d_roots, long long n_trees,
                    long long root_stride, long long tree_index_base, int* d_action, double* d_bestq, int* d_status,
-                   mctsb200_plan_stats* stats) {
+                   mctsb200_plan_stats* stats, unsigned* status_flags = nullptr) {
     Storage& st = ctx->st;
     // visits already in the trees if this call continues kept ones (reuse_tree / keep_tree)
     const bool may_reuse = cfg->keep_tree && st.valid && st.keep && st.kind == cfg->kind && st.mdp_id == MdpAccess<M>::mdp_id(ctx) && st.n_trees == n_trees;
@@ -944,7 +944,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         if (lazy) {
             auto kernel = decide_fast_kernel<M, KIND>;
             MCTSB200_LAUNCH(kernel, (unsigned)((args.n_slots + 127) / 128), 128, 0, ctx->stream, (const TreeHeader*)st.hdr.p, (const FastRow*)st.rows_fast.p,
-                            args.order, st.geo.NS, args.n_slots, d_action, d_bestq, d_status);
+                            args.order, st.geo.NS, args.n_slots, d_action, d_bestq, d_status, (unsigned long long*)ctx->counters.p + CNT_STATUS_FLAGS);
             CUDA_TRY(cudaGetLastError());
             ++launches;
             st.finalize_fn = &finalize_pending<M, KIND>;
@@ -958,7 +958,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
         const unsigned grid = (unsigned)((n_trees + 127) / 128);
         auto kernel = decide_kernel<M>;
         MCTSB200_LAUNCH(kernel, grid, 128, 0, ctx->stream, (const TreeHeader*)st.hdr.p, (const Row<M>*)st.rows.p, st.geo.NS, n_trees, d_action, d_bestq,
-                        d_status);
+                        d_status, (unsigned long long*)ctx->counters.p + CNT_STATUS_FLAGS);
         CUDA_TRY(cudaGetLastError());
         ++launches;
     }
@@ -970,6 +970,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     // bound of the visit counts now in the trees: exact after a fast-kernel call, else one visit per backup
     st.q_bound = dcfg.q_bound;
     st.visits = fast >= 0 ? (long long)h_cnt[CNT_MAX_VISITS] : prior_visits + (long long)done * std::max(cfg->depth, 1);
+    if (status_flags) *status_flags = (unsigned)h_cnt[CNT_STATUS_FLAGS];
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         stats->n_trees = n_trees;
@@ -1023,21 +1024,17 @@ int32_t plan_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const v
         d_bestq = (double*)ctx->io_bestq.p;
         d_status = (int*)ctx->io_status.p;
     }
-    if (cfg->kind == MCTSB200_KIND_UCT) rc = run_search<M, MCTSB200_KIND_UCT>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats);
-    else rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats);
+    unsigned flags = 0;  // OR of the trees' status, reduced on the device: errors surface even without a status buffer
+    if (cfg->kind == MCTSB200_KIND_UCT) rc = run_search<M, MCTSB200_KIND_UCT>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats, &flags);
+    else rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats, &flags);
     if (rc) return rc;
-    int32_t worst = MCTSB200_OK;
+    int32_t worst = (flags & 2u) ? MCTSB200_ERR_CAPACITY : (flags & 1u) ? MCTSB200_ERR_TERMINAL_ROOT : MCTSB200_OK;
     if (!out_on_device) {
-        std::vector<int> h_status((size_t)n_roots);
         if (action_out) CUDA_TRY(cudaMemcpyAsync(action_out, d_action, sizeof(int) * (size_t)n_roots, cudaMemcpyDeviceToHost, ctx->stream));
         if (bestq_out) CUDA_TRY(cudaMemcpyAsync(bestq_out, d_bestq, sizeof(double) * (size_t)n_roots, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * (size_t)n_roots, cudaMemcpyDeviceToHost, ctx->stream));
+        if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out, d_status, sizeof(int) * (size_t)n_roots, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        d2h += (int64_t)((action_out ? sizeof(int) : 0) + (bestq_out ? sizeof(double) : 0) + sizeof(int)) * n_roots;
-        for (long long i = 0; i < n_roots; ++i) {
-            if (status_out) status_out[i] = h_status[(size_t)i];
-            if (h_status[(size_t)i] != MCTSB200_OK && worst == MCTSB200_OK) worst = h_status[(size_t)i];
-        }
+        d2h += (int64_t)((action_out ? sizeof(int) : 0) + (bestq_out ? sizeof(double) : 0) + (status_out ? sizeof(int) : 0)) * n_roots;
     }
     if (stats) {
         stats->h2d_bytes = h2d;
@@ -1066,11 +1063,14 @@ int32_t root_parallel_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(ctx->io_roots.ensure(sizeof(Abi)));
     CUDA_TRY(cudaMemcpyAsync(ctx->io_roots.p, root_state, sizeof(Abi), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned flags = 0;
     if (cfg->kind == MCTSB200_KIND_UCT)
-        rc = run_search<M, MCTSB200_KIND_UCT>(ctx, cfg, (const Abi*)ctx->io_roots.p, n_trees, 0, base, nullptr, nullptr, nullptr, stats);
+        rc = run_search<M, MCTSB200_KIND_UCT>(ctx, cfg, (const Abi*)ctx->io_roots.p, n_trees, 0, base, nullptr, nullptr, nullptr, stats, &flags);
     else
-        rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, (const Abi*)ctx->io_roots.p, n_trees, 0, base, nullptr, nullptr, nullptr, stats);
+        rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, (const Abi*)ctx->io_roots.p, n_trees, 0, base, nullptr, nullptr, nullptr, stats, &flags);
     if (rc) return rc;
+    if (flags & 2u) return fail(MCTSB200_ERR_CAPACITY, "a per-tree table overflowed");
+    if (flags & 1u) return fail(MCTSB200_ERR_TERMINAL_ROOT, "MCTS cannot handle terminal states: the root state is terminal (src/dpw.jl:22-27)");
     double* d_sums = d_sums_out;
     if (!d_sums) {
         CUDA_TRY(ctx->sums.ensure(sizeof(double) * 2 * M::kActions));
@@ -1156,11 +1156,14 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
         mctsb200_solver_cfg c = *cfg;
         c.seed = cfg->seed + (uint64_t)t;
         mctsb200_plan_stats st;
+        unsigned flags = 0;
         if (cfg->kind == MCTSB200_KIND_UCT)
-            rc = run_search<M, MCTSB200_KIND_UCT>(ctx, &c, d_s, n, 1, base, (int*)ctx->io_action.p, nullptr, (int*)ctx->io_status.p, &st);
+            rc = run_search<M, MCTSB200_KIND_UCT>(ctx, &c, d_s, n, 1, base, (int*)ctx->io_action.p, nullptr, (int*)ctx->io_status.p, &st, &flags);
         else
-            rc = run_search<M, MCTSB200_KIND_DPW>(ctx, &c, d_s, n, 1, base, (int*)ctx->io_action.p, nullptr, (int*)ctx->io_status.p, &st);
+            rc = run_search<M, MCTSB200_KIND_DPW>(ctx, &c, d_s, n, 1, base, (int*)ctx->io_action.p, nullptr, (int*)ctx->io_status.p, &st, &flags);
         if (rc) return rc;
+        // (a finished episode's root is terminal: expected here; an overflowed table is not)
+        if (flags & 2u) return fail(MCTSB200_ERR_CAPACITY, "a per-tree table overflowed at episode step %d", t);
         tot.n_simulations += st.n_simulations; tot.n_tree_levels += st.n_tree_levels; tot.n_dpw_children_seen += st.n_dpw_children_seen;
         tot.n_state_inserts += st.n_state_inserts; tot.n_action_inserts += st.n_action_inserts; tot.n_rollouts += st.n_rollouts;
         tot.n_rollout_steps += st.n_rollout_steps; tot.n_transition_samples += st.n_transition_samples; tot.n_select_exact += st.n_select_exact;

@@ -174,6 +174,7 @@ enum CounterId {
     CNT_SIMULATIONS = 0, CNT_LEVELS, CNT_CHILDREN_SEEN, CNT_STATE_INSERTS, CNT_ACTION_INSERTS, CNT_ROLLOUTS, CNT_ROLLOUT_STEPS,
     CNT_TRANS_SAMPLES, CNT_SELECT_EXACT,
     CNT_MAX_VISITS,  // not a sum: the largest node visit count, written by the fast kernels' finalize pass
+    CNT_STATUS_FLAGS,  // not a sum: OR over the trees' status (bit 0: a terminal DPW root, bit 1: a table overflowed), written by the decision kernels
     CNT_COUNT
 };
 

@@ -500,7 +500,7 @@ __global__ void dpw_finalize_kernel(const FastRow* rows_fast, const DpwTransRow*
 // tree queries read are then only written when somebody asks for a tree (finalize_rows_kernel / dpw_finalize_kernel).
 template <class M, int KIND>
 __global__ void decide_fast_kernel(const TreeHeader* hdr, const FastRow* rows_fast, const int* order, int NS, long long n_slots, int* action_out,
-                                   double* best_q_out, int* status_out) {
+                                   double* best_q_out, int* status_out, unsigned long long* status_flags) {
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= n_slots) return;
     const long long tree = order ? (long long)order[slot] : slot;
@@ -530,6 +530,7 @@ __global__ void decide_fast_kernel(const TreeHeader* hdr, const FastRow* rows_fa
     if (action_out) action_out[tree] = act;
     if (best_q_out) best_q_out[tree] = bq;
     if (status_out) status_out[tree] = h.status;
+    if (h.status != MCTSB200_OK) atomicOr(status_flags, h.status == MCTSB200_ERR_TERMINAL_ROOT ? 1ull : 2ull);
 }
 
 template <class M>

@@ -1004,7 +1004,7 @@ __global__ void episode_step_kernel(const typename M::Params mdp, typename M::Ab
 // Root decision: best_sanode_Q (src/vanilla.jl:339-349) / best_sanode (src/dpw.jl:163-173).
 template <class M>
 __global__ void decide_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS, long long n_trees, int* action_out,
-                              double* best_q_out, int* status_out) {
+                              double* best_q_out, int* status_out, unsigned long long* status_flags) {
     const long long tree = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tree >= n_trees) return;
     const TreeHeader h = hdr[tree];
@@ -1029,6 +1029,8 @@ __global__ void decide_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS,
     if (action_out) action_out[tree] = act;
     if (best_q_out) best_q_out[tree] = bq;
     if (status_out) status_out[tree] = h.status;
+    // the call's worst status reaches the host with the counters even when the caller passed no status buffer
+    if (h.status != MCTSB200_OK) atomicOr(status_flags, h.status == MCTSB200_ERR_TERMINAL_ROOT ? 1ull : 2ull);
 }
 
 // Root-parallel partial sums (BASELINE config 5): lane a sums action a over all trees in tree order, so

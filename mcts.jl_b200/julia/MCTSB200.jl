@@ -86,7 +86,7 @@ device_mdp(m) = error("no device plugin registered for $(typeof(m)); libmctsb200
 # defining `struct <plugin_struct>` (csrc/custom.cuh); afterwards add a `device_mdp(::YourMDP)` method returning
 # (id, Ref(params_pod), sizeof(params_pod)) with a POD that mirrors the plugin's `Params` (`discount` first).
 function register_mdp(name::AbstractString, source::AbstractString, plugin_struct::AbstractString;
-                      state_doubles::Integer, n_actions::Integer, max_branch::Integer = 1)
+                      state_doubles::Integer, n_actions::Integer, max_branch::Integer = 0)
     id = Ref{Int32}(-1)
     check(ccall((:mctsb200_mdp_register, LIB), Int32, (Cstring, Cstring, Cstring, Int32, Int32, Int32, Ref{Int32}),
                 name, source, plugin_struct, state_doubles, n_actions, max_branch, id))

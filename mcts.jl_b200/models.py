@@ -137,7 +137,8 @@ class PluginMDP:
     actions: Tuple[Any, ...]
     params_struct: C.Structure
     state_width: int = 2
-    max_branch: int = 1        # distinct successors of one (s, a): 1 = deterministic, 0 = unbounded
+    max_branch: int = 0        # distinct successors of one (s, a): 0 = unbounded (always correct, the default); 1 = deterministic
+                               # transitions, an explicit opt-in: the kernels then reuse the first sampled successor
     terminal: Any = None       # optional host-side isterminal(s) (DPW's terminal-root error path in the Python mirror)
     lib_path: Optional[str] = None
     oracle_mdp_id: Optional[int] = None  # tests only: the id under which oracle/mcts_oracle.cpp restates this model
