@@ -20,9 +20,12 @@
  *   - every entry point is extern "C", takes plain pointers and sizes, never throws, never aborts;
  *   - return value: 0 = MCTSB200_OK, negative = error; text via mctsb200_last_error() (thread local);
  *   - the caller owns every host buffer; the library owns all device memory inside a ctx;
- *   - a ctx is bound to ONE CUDA device (one process per GPU; multi-GPU = several processes, roots
- *     sharded by the host with `root_index_base`, see mcts.jl_b200/distributed.py) and is not re-entrant,
- *     exactly like a reference planner (src/vanilla.jl:129-135);
+ *   - a ctx made by mctsb200_ctx_create is bound to ONE CUDA device; a ctx made by mctsb200_ctx_create_multi owns one child
+ *     ctx per device of this process and fans every call out to them (one host thread and one stream per device, roots sharded
+ *     in contiguous blocks, Philox streams keyed by the global root index, so the result equals the one-device result bit
+ *     for bit). With one process per GPU (torchrun, MPI) each rank keeps its own ctx, shards with `root_index_base`, and
+ *     joins a communicator with mctsb200_comm_init for the one collective the path has (root-parallel search). A ctx is not
+ *     re-entrant, exactly like a reference planner (src/vanilla.jl:129-135);
  *   - there is NO CPU fallback: without a usable CUDA device every compute call fails.
  *   - actions are returned as 0-based indices into actions(mdp) iteration order
  *     (SimpleGridWorld: up, down, left, right; MountainCar: -1.0, 0.0, 1.0); node ids in exported
@@ -38,7 +41,7 @@
 extern "C" {
 #endif
 
-#define MCTSB200_ABI_VERSION 1
+#define MCTSB200_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------------------------- */
 enum {
@@ -166,6 +169,22 @@ const char* mctsb200_last_error(void);
 int32_t mctsb200_ctx_create(int32_t device_id, void* stream, mctsb200_ctx** out);
 int32_t mctsb200_ctx_destroy(mctsb200_ctx* ctx);
 
+/* ---- multi-GPU (the reference has no counterpart: it plans one state per call on one thread) ----------------- */
+/* One ctx over n_dev devices of this process. Every entry point below accepts it: mctsb200_mdp_configure configures all devices;
+ * mctsb200_plan / mctsb200_run_episodes shard the roots / episodes in contiguous blocks (global indices = root_index_base + i, so
+ * outputs and trees equal the one-device call bit for bit; no data-path collective); mctsb200_plan_root_parallel splits the
+ * ensemble's trees over the devices and merges the per-device partial sums with ONE ncclAllReduce (sum, int64, 5*|A|+1 words)
+ * per decision over NVLink -- the only inter-GPU traffic of the library; tree queries address tree i of the whole call.
+ * Not available on a multi-device ctx: mctsb200_plan_device and d_sums_out (device pointers belong to one device), the host
+ * hooks between launches. NCCL (libnccl.so.2) is loaded at the first multi-device create; one device needs none. */
+int32_t mctsb200_ctx_create_multi(const int32_t* device_ids, int32_t n_dev, mctsb200_ctx** out);
+int32_t mctsb200_ctx_device_count(mctsb200_ctx* ctx, int32_t* n_dev_out);
+/* One process per GPU: rank 0 makes an id (128 bytes = NCCL_UNIQUE_ID_BYTES), the host distributes it by whatever it has
+ * (torch.distributed broadcast, MPI_Bcast, a file), and every rank attaches its single-device ctx. Afterwards
+ * mctsb200_plan_root_parallel on that ctx is a collective call: it returns the sums merged over all ranks. */
+int32_t mctsb200_comm_unique_id(void* id_out, size_t bytes);
+int32_t mctsb200_comm_init(mctsb200_ctx* ctx, const void* unique_id, size_t bytes, int32_t n_ranks, int32_t rank);
+
 /* ---- MDP plugins ------------------------------------------------------------------------------- */
 int32_t mctsb200_mdp_lookup(const char* name, int32_t* mdp_id); /* "SimpleGridWorld", "MountainCar" */
 int32_t mctsb200_mdp_info(int32_t mdp_id, int32_t* n_actions, int64_t* state_bytes);
@@ -210,15 +229,24 @@ int32_t mctsb200_plan_device(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, 
                              mctsb200_plan_stats* stats_out);
 
 /* Root-parallel search of ONE root (BASELINE config 5): n_trees independent trees of the same root
- * (Philox tree index = tree_index_base + t), n_iterations each. Writes the per-ctx partial sums
- * sum_n[a] = sum_t N_t(a), sum_nq[a] = sum_t N_t(a)*Q_t(a) (host, n_actions each; summed in fixed
- * tree order). The host all-reduces them across GPUs (one NCCL allreduce) and calls
- * mctsb200_root_parallel_decide. d_sums_out: optional DEVICE buffer of 2*n_actions doubles that receives
- * [sum_n | sum_nq] for an in-place NCCL allreduce. */
+ * (Philox tree index = tree_index_base + t), n_iterations each. Writes sum_n[a] = sum_t N_t(a) and
+ * sum_nq[a] = sum_t N_t(a)*Q_t(a) (host, n_actions each), then the host calls mctsb200_root_parallel_decide.
+ * The sums are accumulated in INTEGER arithmetic: every once-rounded double product N*Q is taken as a multiple of 2^-64
+ * (rounded toward zero; |N*Q| < 2^40, else the sum is NaN) and added in 128-bit two's complement, and the total is rounded to
+ * double once. They therefore do not depend on the order of the trees, on the number of devices or on the reduction order of
+ * the collective: on a multi-device ctx, or on a ctx that joined a communicator (mctsb200_comm_init), the partial sums of
+ * all devices / ranks are merged by ONE ncclAllReduce inside this call and every rank receives the same merged sums, bit-equal to
+ * a single-device call with the same trees (n_trees may be 0 on a rank of a communicator). d_sums_out: optional DEVICE
+ * buffer of 2*n_actions doubles that receives [sum_n | sum_nq] as returned. */
 int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id,
                                     const void* root_state, size_t state_bytes, int64_t n_trees,
                                     int64_t tree_index_base, double* sum_n_out, double* sum_nq_out,
                                     double* d_sums_out, mctsb200_plan_stats* stats_out);
+/* For hosts that merge with their own transport (MPI, gloo): the integer words behind the sums of this ctx's last
+ * root-parallel call -- [n[A] | four 32-bit limbs per action in int64 | inexact flag], 5*|A|+1 words; add them across ranks as
+ * int64 (any order) and convert with mctsb200_root_sums_merge. Two-call pattern: words_out NULL returns the count. */
+int32_t mctsb200_root_sums_words(mctsb200_ctx* ctx, int64_t* words_out, int32_t capacity, int32_t* n_words_out);
+int32_t mctsb200_root_sums_merge(const int64_t* words, int32_t n_actions, double* sum_n_out, double* sum_nq_out);
 /* Q_a = sum_nq/sum_n (a with sum_n == 0 keeps init_Q); action = first argmax, as best_sanode_Q. */
 int32_t mctsb200_root_parallel_decide(const double* sum_n, const double* sum_nq, int32_t n_actions,
                                       double init_q, int32_t* action_idx_out, double* best_q_out, double* q_out);

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK = 0
 ERR_INVALID_ARG = -1
@@ -162,6 +162,12 @@ EXPORTED_SYMBOLS = (
     "mctsb200_last_error",
     "mctsb200_ctx_create",
     "mctsb200_ctx_destroy",
+    "mctsb200_ctx_create_multi",
+    "mctsb200_ctx_device_count",
+    "mctsb200_comm_unique_id",
+    "mctsb200_comm_init",
+    "mctsb200_root_sums_words",
+    "mctsb200_root_sums_merge",
     "mctsb200_mdp_lookup",
     "mctsb200_mdp_info",
     "mctsb200_mdp_configure",
@@ -198,6 +204,12 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.mctsb200_last_error.restype = C.c_char_p
     lib.mctsb200_ctx_create.argtypes = [i32, vp, P(vp)]
     lib.mctsb200_ctx_destroy.argtypes = [vp]
+    lib.mctsb200_ctx_create_multi.argtypes = [P(i32), i32, P(vp)]
+    lib.mctsb200_ctx_device_count.argtypes = [vp, P(i32)]
+    lib.mctsb200_comm_unique_id.argtypes = [vp, sz]
+    lib.mctsb200_comm_init.argtypes = [vp, vp, sz, i32, i32]
+    lib.mctsb200_root_sums_words.argtypes = [vp, vp, i32, P(i32)]
+    lib.mctsb200_root_sums_merge.argtypes = [vp, i32, vp, vp]
     lib.mctsb200_mdp_lookup.argtypes = [C.c_char_p, P(i32)]
     lib.mctsb200_mdp_info.argtypes = [i32, P(i32), P(i64)]
     lib.mctsb200_mdp_configure.argtypes = [vp, i32, vp, sz]

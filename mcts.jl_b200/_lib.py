@@ -80,14 +80,51 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 class Context:
-    """One mctsb200_ctx: bound to one CUDA device, not re-entrant (like a reference planner)."""
+    """One mctsb200_ctx, not re-entrant (like a reference planner). `device` is a CUDA ordinal, or a sequence of ordinals for a
+    multi-device ctx (mctsb200_ctx_create_multi): the same calls then shard roots / episodes / ensemble trees over the devices
+    inside the library and return what one device would, bit for bit."""
 
-    def __init__(self, device: int = 0, stream: int = 0, lib_path: Optional[str] = None):
+    def __init__(self, device=0, stream: int = 0, lib_path: Optional[str] = None):
         self.lib = load_library(lib_path)
         self._h = C.c_void_p()
-        self._check(self.lib.mctsb200_ctx_create(int(device), C.c_void_p(stream or None), C.byref(self._h)))
-        self.device = int(device)
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int32 * len(device))(*[int(d) for d in device])
+            self._check(self.lib.mctsb200_ctx_create_multi(ids, len(device), C.byref(self._h)))
+            self.devices = [int(d) for d in device]
+            self.device = self.devices[0]
+        else:
+            self._check(self.lib.mctsb200_ctx_create(int(device), C.c_void_p(stream or None), C.byref(self._h)))
+            self.device = int(device)
+            self.devices = [self.device]
         self._configured: dict[int, bytes] = {}
+        self.comm_ranks = 1
+
+    # -- one process per GPU: join a communicator (the id travels by the host's own means) --
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.mctsb200_comm_unique_id(buf, 128))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int) -> None:
+        """After this, plan_root_parallel on this ctx is a collective call (one ncclAllReduce inside the library)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.mctsb200_comm_init(self._h, buf, 128, int(n_ranks), int(rank)))
+        self.comm_ranks = int(n_ranks)
+
+    def root_sums_words(self) -> np.ndarray:
+        """Integer words behind the sums of the last root-parallel call (for hosts that merge with their own transport)."""
+        n = C.c_int32()
+        self._check(self.lib.mctsb200_root_sums_words(self._h, None, 0, C.byref(n)))
+        w = np.zeros(n.value, dtype=np.int64)
+        self._check(self.lib.mctsb200_root_sums_words(self._h, _ptr(w), n.value, C.byref(n)))
+        return w
+
+    def root_sums_merge(self, words: np.ndarray, n_actions: int):
+        words = np.ascontiguousarray(words, dtype=np.int64)
+        assert len(words) == 5 * n_actions + 1
+        sn, snq = np.zeros(n_actions), np.zeros(n_actions)
+        self._check(self.lib.mctsb200_root_sums_merge(_ptr(words), int(n_actions), _ptr(sn), _ptr(snq)))
+        return sn, snq
 
     # -- plumbing --
     def _check(self, status: int) -> None:

@@ -22,10 +22,14 @@
 #include "dpw_fast.cuh"
 #include "custom.cuh"
 #ifndef MCTSB200_HOST_EMU
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <map>
 
 #include "plugin_rt.h"
 #endif
+#include <thread>
 
 using namespace mctsb200;
 
@@ -117,6 +121,14 @@ struct mctsb200_ctx {
     void* timer_user = nullptr;
     DevBuf ep_states, ep_disc, ep_ret, ep_steps, ep_active, ep_count;
     int log_tab_n = 0;
+    // multi-GPU (mctsb200_ctx_create_multi / mctsb200_comm_init): a group ctx owns one child ctx per device and fans every call
+    // out to them, one host thread per device; a ctx that is a rank of a communicator merges its root-parallel partial sums
+    // with ONE ncclAllReduce on its own stream
+    std::vector<mctsb200_ctx*> kids;
+    std::vector<long long> kid_lo;  // shard bounds of the last plan / episode call: child k holds items [kid_lo[k], kid_lo[k+1])
+    void* comm = nullptr;           // ncclComm_t
+    int comm_ranks = 1, comm_rank = 0;
+    std::vector<long long> root_words;  // integer partial sums of the last root-parallel call (root_sums_kernel)
 #ifndef MCTSB200_HOST_EMU
     // run-time registered MDP plugins (plugin_rt.cu): parameters configured for this ctx, by plugin index
     struct alignas(16) PluginParams { unsigned char bytes[kCustomParamBytes]; };
@@ -127,6 +139,63 @@ struct mctsb200_ctx {
 };
 
 namespace {
+
+// ---- NCCL, loaded on first use (the library has no link-time dependency on it; a process that already holds a libnccl.so.2,
+// e.g. torch's, shares that copy) -----------------------------------------------------------------------------------------
+#ifndef MCTSB200_HOST_EMU
+struct Nccl {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        const char* names[] = {std::getenv("MCTSB200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n || !n[0]) continue;
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) {
+            error = "libnccl.so.2 not found (set MCTSB200_NCCL_LIB): multi-GPU root-parallel search needs NCCL";
+            return false;
+        }
+#define MCTSB200_SYM(f)                                                    \
+    f = reinterpret_cast<decltype(f)>(dlsym(handle, "nccl" #f));           \
+    if (!f) {                                                              \
+        error = "libnccl lacks nccl" #f;                                   \
+        handle = nullptr;                                                  \
+        return false;                                                      \
+    }
+        MCTSB200_SYM(GetUniqueId) MCTSB200_SYM(CommInitRank) MCTSB200_SYM(CommInitAll) MCTSB200_SYM(CommDestroy) MCTSB200_SYM(AllReduce)
+        MCTSB200_SYM(GetErrorString)
+#undef MCTSB200_SYM
+        return true;
+    }
+};
+Nccl g_nccl;
+#define NCCL_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        ncclResult_t r__ = (expr);                                                                             \
+        if (r__ != ncclSuccess) return fail(MCTSB200_ERR_CUDA, "%s: %s", #expr, g_nccl.GetErrorString(r__));  \
+    } while (0)
+#endif
+
+// the int64 words of root_sums_kernel (search.cuh) -> [sum_n | sum_nq] doubles: limbs recombined in 128-bit two's complement, one
+// rounding to double, exact scaling by 2^-64; NaN if a product could not be taken as a fixed-point value
+void root_sums_to_double(const long long* w, int A, double* sum_n, double* sum_nq) {
+    for (int a = 0; a < A; ++a) {
+        sum_n[a] = (double)w[a];
+        const long long* c = w + A + 4 * a;
+        const __int128 v = (__int128)c[0] + (__int128)((unsigned __int128)(__int128)c[1] << 32) + (__int128)((unsigned __int128)(__int128)c[2] << 64) +
+                           (__int128)((unsigned __int128)(__int128)c[3] << 96);
+        sum_nq[a] = w[5 * A] ? NAN : std::ldexp((double)v, -64);
+    }
+}
 
 template <class M>
 struct MdpAccess;
@@ -1058,37 +1127,56 @@ int32_t root_parallel_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg
     cfg = effective_cfg(cfg, cfg_capped);
     int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok);
     if (rc) return rc;
-    if (state_bytes != sizeof(Abi) || !root_state || n_trees <= 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad root_parallel arguments");
+    // (a rank of a communicator may hold no tree of a small ensemble: it still takes part in the allreduce)
+    const bool in_comm = ctx->comm != nullptr && ctx->comm_ranks > 1;
+    if (state_bytes != sizeof(Abi) || !root_state || n_trees < 0 || (n_trees == 0 && !in_comm)) return fail(MCTSB200_ERR_INVALID_ARG, "bad root_parallel arguments");
     if (MdpAccess<M>::check_root(ctx, *(const Abi*)root_state)) return fail(MCTSB200_ERR_INVALID_ARG, "root state is not a valid state of this MDP");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(ctx->io_roots.ensure(sizeof(Abi)));
     CUDA_TRY(cudaMemcpyAsync(ctx->io_roots.p, root_state, sizeof(Abi), cudaMemcpyHostToDevice, ctx->stream));
     unsigned flags = 0;
-    if (cfg->kind == MCTSB200_KIND_UCT)
+    if (n_trees == 0) {
+        if (stats) std::memset(stats, 0, sizeof *stats);
+    } else if (cfg->kind == MCTSB200_KIND_UCT)
         rc = run_search<M, MCTSB200_KIND_UCT>(ctx, cfg, (const Abi*)ctx->io_roots.p, n_trees, 0, base, nullptr, nullptr, nullptr, stats, &flags);
     else
         rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, (const Abi*)ctx->io_roots.p, n_trees, 0, base, nullptr, nullptr, nullptr, stats, &flags);
     if (rc) return rc;
     if (flags & 2u) return fail(MCTSB200_ERR_CAPACITY, "a per-tree table overflowed");
     if (flags & 1u) return fail(MCTSB200_ERR_TERMINAL_ROOT, "MCTS cannot handle terminal states: the root state is terminal (src/dpw.jl:22-27)");
-    double* d_sums = d_sums_out;
-    if (!d_sums) {
-        CUDA_TRY(ctx->sums.ensure(sizeof(double) * 2 * M::kActions));
-        d_sums = (double*)ctx->sums.p;
+    constexpr int W = kRootSumsWords(M::kActions);
+    CUDA_TRY(ctx->sums.ensure(sizeof(long long) * W));
+    unsigned long long* d_words = (unsigned long long*)ctx->sums.p;
+    CUDA_TRY(cudaMemsetAsync(d_words, 0, sizeof(long long) * W, ctx->stream));
+    int launches = 0;
+    if (n_trees > 0) {
+        if (ctx->st.finalize_fn && (rc = ctx->st.finalize_fn(ctx))) return rc;
+        auto kernel = root_sums_kernel<M>;
+        MCTSB200_LAUNCH(kernel, (unsigned)((n_trees + 255) / 256), 256, 0, ctx->stream, (const TreeHeader*)ctx->st.hdr.p, (const Row<M>*)ctx->st.rows.p,
+                        ctx->st.geo.NS, n_trees, d_words);
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
     }
-    if (ctx->st.finalize_fn && (rc = ctx->st.finalize_fn(ctx))) return rc;
-    auto kernel = root_sums_kernel<M>;
-    MCTSB200_LAUNCH(kernel, 1, 32, 0, ctx->stream, (const TreeHeader*)ctx->st.hdr.p, (const Row<M>*)ctx->st.rows.p, ctx->st.geo.NS, n_trees, d_sums);
-    CUDA_TRY(cudaGetLastError());
-    double h[2 * M::kActions];
-    CUDA_TRY(cudaMemcpyAsync(h, d_sums, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+#ifndef MCTSB200_HOST_EMU
+    if (ctx->comm && ctx->comm_ranks > 1) {
+        // the only inter-GPU traffic of a decision: one allreduce of 5*|A|+1 int64 words over NVLink, in place, on the search's stream
+        NCCL_TRY(g_nccl.AllReduce(d_words, d_words, W, ncclInt64, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+        ++launches;
+    }
+#endif
+    long long h[W];
+    CUDA_TRY(cudaMemcpyAsync(h, d_words, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->root_words.assign(h, h + W);  // (mctsb200_root_sums_words: hosts that merge with their own transport)
+    double sums[2 * M::kActions];
+    root_sums_to_double(h, M::kActions, sums, sums + M::kActions);
     for (int i = 0; i < M::kActions; ++i) {
-        if (sum_n_out) sum_n_out[i] = h[i];
-        if (sum_nq_out) sum_nq_out[i] = h[M::kActions + i];
+        if (sum_n_out) sum_n_out[i] = sums[i];
+        if (sum_nq_out) sum_nq_out[i] = sums[M::kActions + i];
     }
+    if (d_sums_out) CUDA_TRY(cudaMemcpy(d_sums_out, sums, sizeof sums, cudaMemcpyHostToDevice));
     if (stats) {
-        stats->n_kernel_launches += 1;
+        stats->n_kernel_launches += launches;
         stats->h2d_bytes = sizeof(Abi);
         stats->d2h_bytes = sizeof h;
         stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1374,6 +1462,152 @@ int32_t check_tree_query(mctsb200_ctx* ctx, long long i) {
     return MCTSB200_OK;
 }
 
+
+// ---- multi-GPU fan-out (mctsb200_ctx_create_multi) ------------------------------------------------------------------------
+// contiguous block of shard k of n items over w shards: sizes differ by at most one, earlier shards take the remainder
+void shard_bounds(long long n, int w, std::vector<long long>& lo) {
+    lo.assign((size_t)w + 1, 0);
+    const long long base = n / w, rem = n % w;
+    for (int k = 0; k < w; ++k) lo[(size_t)k + 1] = lo[(size_t)k] + base + (k < rem ? 1 : 0);
+}
+
+void add_stats(mctsb200_plan_stats& tot, const mctsb200_plan_stats& s) {
+    tot.n_trees += s.n_trees; tot.n_simulations += s.n_simulations; tot.n_tree_levels += s.n_tree_levels;
+    tot.n_dpw_children_seen += s.n_dpw_children_seen; tot.n_state_inserts += s.n_state_inserts; tot.n_action_inserts += s.n_action_inserts;
+    tot.n_rollouts += s.n_rollouts; tot.n_rollout_steps += s.n_rollout_steps; tot.n_transition_samples += s.n_transition_samples;
+    tot.n_select_exact += s.n_select_exact; tot.algorithmic_bytes += s.algorithmic_bytes;
+    tot.kernel_ms = std::max(tot.kernel_ms, s.kernel_ms);  // the devices run side by side
+    tot.h2d_bytes += s.h2d_bytes; tot.d2h_bytes += s.d2h_bytes; tot.n_kernel_launches += s.n_kernel_launches;
+    if (s.n_trees) {
+        tot.lanes_per_tree = s.lanes_per_tree;
+        tot.kernel_variant = s.kernel_variant;
+        tot.iterations_done = tot.iterations_done ? std::min(tot.iterations_done, s.iterations_done) : s.iterations_done;
+    }
+}
+
+// fn(k, child) on one host thread per child; the first failing child's status and message are returned
+template <class F>
+int32_t fan_out(mctsb200_ctx* g, F&& fn) {
+    const size_t n = g->kids.size();
+    std::vector<int32_t> rc(n, MCTSB200_OK);
+    std::vector<std::string> err(n);
+    auto body = [&](size_t k) {
+        rc[k] = fn((int)k, g->kids[k]);
+        if (rc[k]) err[k] = g_err;  // (thread local)
+    };
+#ifdef MCTSB200_HOST_EMU
+    for (size_t k = 0; k < n; ++k) body(k);  // (the emulator's "shared memory" is one static buffer: one kernel at a time)
+#else
+    std::vector<std::thread> th;
+    for (size_t k = 1; k < n; ++k) th.emplace_back(body, k);
+    body(0);
+    for (auto& t : th) t.join();
+#endif
+    for (size_t k = 0; k < n; ++k)
+        if (rc[k]) {
+            g_err = "device " + std::to_string(g->kids[k]->device) + ": " + err[k];
+            return rc[k];
+        }
+    return MCTSB200_OK;
+}
+
+// which child holds item i of the last sharded call
+int32_t group_locate(mctsb200_ctx* g, long long i, mctsb200_ctx** kid, long long* local) {
+    for (size_t k = 0; k + 1 < g->kid_lo.size(); ++k)
+        if (i >= g->kid_lo[k] && i < g->kid_lo[k + 1]) {
+            *kid = g->kids[k];
+            *local = i - g->kid_lo[k];
+            return MCTSB200_OK;
+        }
+    return g->kid_lo.empty() ? fail(MCTSB200_ERR_STATE, "no tree: call mctsb200_plan first") : fail(MCTSB200_ERR_INVALID_ARG, "root index %lld out of range", i);
+}
+
+int32_t group_plan(mctsb200_ctx* g, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* roots, int64_t n_roots, size_t state_bytes,
+                   int64_t base, int32_t* action_out, double* bestq_out, int32_t* status_out, mctsb200_plan_stats* stats_out) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (n_roots <= 0 || !roots) return fail(MCTSB200_ERR_INVALID_ARG, "need at least one root state");
+    shard_bounds(n_roots, (int)g->kids.size(), g->kid_lo);
+    std::vector<mctsb200_plan_stats> st(g->kids.size());
+    for (auto& x : st) std::memset(&x, 0, sizeof x);
+    const int32_t rc = fan_out(g, [&](int k, mctsb200_ctx* c) -> int32_t {
+        const long long lo = g->kid_lo[(size_t)k], hi = g->kid_lo[(size_t)k + 1];
+        if (hi == lo) return MCTSB200_OK;
+        // Philox streams are keyed by the GLOBAL root index: the sharded call returns what one device would
+        return mctsb200_plan(c, cfg, mdp_id, (const char*)roots + (size_t)lo * state_bytes, hi - lo, state_bytes, base + lo, action_out ? action_out + lo : nullptr,
+                             bestq_out ? bestq_out + lo : nullptr, status_out ? status_out + lo : nullptr, &st[(size_t)k]);
+    });
+    if (stats_out) {
+        std::memset(stats_out, 0, sizeof *stats_out);
+        for (const auto& x : st) add_stats(*stats_out, x);
+        stats_out->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return rc;
+}
+
+int32_t group_run_episodes(mctsb200_ctx* g, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* initial_states, int64_t n, size_t state_bytes,
+                           int32_t max_steps, uint64_t env_seed, int64_t base, double* return_out, int32_t* steps_out, void* final_out,
+                           mctsb200_plan_stats* stats_out) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (n <= 0 || !initial_states) return fail(MCTSB200_ERR_INVALID_ARG, "bad run_episodes arguments");
+    shard_bounds(n, (int)g->kids.size(), g->kid_lo);
+    std::vector<mctsb200_plan_stats> st(g->kids.size());
+    for (auto& x : st) std::memset(&x, 0, sizeof x);
+    const int32_t rc = fan_out(g, [&](int k, mctsb200_ctx* c) -> int32_t {
+        const long long lo = g->kid_lo[(size_t)k], hi = g->kid_lo[(size_t)k + 1];
+        if (hi == lo) return MCTSB200_OK;
+        return mctsb200_run_episodes(c, cfg, mdp_id, (const char*)initial_states + (size_t)lo * state_bytes, hi - lo, state_bytes, max_steps, env_seed, base + lo,
+                                     return_out ? return_out + lo : nullptr, steps_out ? steps_out + lo : nullptr,
+                                     final_out ? (char*)final_out + (size_t)lo * state_bytes : nullptr, &st[(size_t)k]);
+    });
+    if (stats_out) {
+        std::memset(stats_out, 0, sizeof *stats_out);
+        for (const auto& x : st) add_stats(*stats_out, x);
+        stats_out->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return rc;
+}
+
+int32_t group_root_parallel(mctsb200_ctx* g, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* root_state, size_t state_bytes, int64_t n_trees,
+                            int64_t base, double* sum_n_out, double* sum_nq_out, double* d_sums_out, mctsb200_plan_stats* stats_out) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (d_sums_out) return fail(MCTSB200_ERR_UNSUPPORTED, "d_sums_out belongs to one device: a multi-device ctx merges the sums itself");
+    if (n_trees <= 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad root_parallel arguments");
+    int32_t n_actions = 0;
+    if (int32_t e = mctsb200_mdp_info(mdp_id, &n_actions, nullptr)) return e;
+    shard_bounds(n_trees, (int)g->kids.size(), g->kid_lo);
+    const bool nccl = g->kids[0]->comm != nullptr;  // else (several ctxs on one device): the host adds the integer words
+    std::vector<mctsb200_plan_stats> st(g->kids.size());
+    for (auto& x : st) std::memset(&x, 0, sizeof x);
+    std::vector<std::vector<double>> sums(g->kids.size(), std::vector<double>(2 * (size_t)n_actions, 0.0));
+    const int32_t rc = fan_out(g, [&](int k, mctsb200_ctx* c) -> int32_t {
+        const long long lo = g->kid_lo[(size_t)k], hi = g->kid_lo[(size_t)k + 1];
+        c->root_words.clear();
+        if (hi == lo && !nccl) return MCTSB200_OK;
+        // with a communicator every child allreduces in place on its own stream (ONE ncclAllReduce per decision) and returns the
+        // merged sums
+        return mctsb200_plan_root_parallel(c, cfg, mdp_id, root_state, state_bytes, hi - lo, base + lo, sums[(size_t)k].data(),
+                                           sums[(size_t)k].data() + n_actions, nullptr, &st[(size_t)k]);
+    });
+    if (rc) return rc;
+    std::vector<double> merged = sums[0];
+    if (!nccl && g->kids.size() > 1) {
+        std::vector<long long> w((size_t)(5 * n_actions + 1), 0);
+        for (mctsb200_ctx* c : g->kids)
+            for (size_t i = 0; i < c->root_words.size() && i < w.size(); ++i) w[i] += c->root_words[i];
+        root_sums_to_double(w.data(), n_actions, merged.data(), merged.data() + n_actions);
+    }
+    for (int a = 0; a < n_actions; ++a) {
+        if (sum_n_out) sum_n_out[a] = merged[(size_t)a];
+        if (sum_nq_out) sum_nq_out[a] = merged[(size_t)(n_actions + a)];
+    }
+    if (stats_out) {
+        std::memset(stats_out, 0, sizeof *stats_out);
+        for (const auto& x : st) add_stats(*stats_out, x);
+        stats_out->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return MCTSB200_OK;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1453,7 +1687,19 @@ int32_t mctsb200_ctx_create(int32_t device_id, void* stream, mctsb200_ctx** out)
 
 int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     if (!c) return MCTSB200_OK;
+    if (!c->kids.empty()) {  // a multi-device ctx owns its children (and they own their communicator ranks)
+        for (mctsb200_ctx* k : c->kids) mctsb200_ctx_destroy(k);
+        delete c;
+        return MCTSB200_OK;
+    }
     cudaSetDevice(c->device);
+#ifndef MCTSB200_HOST_EMU
+    if (c->comm) {
+        cudaStreamSynchronize(c->stream);
+        g_nccl.CommDestroy((ncclComm_t)c->comm);
+        c->comm = nullptr;
+    }
+#endif
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->st.plog, &c->counters,
                       &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
@@ -1464,6 +1710,111 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_ctx_create_multi(const int32_t* device_ids, int32_t n_dev, mctsb200_ctx** out) {
+    if (!out) return fail(MCTSB200_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    if (!device_ids || n_dev < 1 || n_dev > 64) return fail(MCTSB200_ERR_INVALID_ARG, "need 1..64 device ids");
+    bool distinct = true;
+    for (int i = 0; i < n_dev; ++i)
+        for (int j = 0; j < i; ++j) distinct &= device_ids[i] != device_ids[j];
+    mctsb200_ctx* g = new mctsb200_ctx();
+    g->device = device_ids[0];
+    for (int i = 0; i < n_dev; ++i) {
+        mctsb200_ctx* k = nullptr;
+        const int32_t rc = mctsb200_ctx_create(device_ids[i], nullptr, &k);
+        if (rc) {
+            for (mctsb200_ctx* x : g->kids) mctsb200_ctx_destroy(x);
+            delete g;
+            return rc;
+        }
+        g->kids.push_back(k);
+    }
+#ifndef MCTSB200_HOST_EMU
+    if (n_dev > 1 && distinct) {
+        // one communicator over the devices of this process: root-parallel partial sums are merged with one ncclAllReduce over
+        // NVLink per decision (several ctxs on ONE device, a debugging setup, are merged by the host instead)
+        std::vector<ncclComm_t> comms((size_t)n_dev);
+        std::vector<int> devs(device_ids, device_ids + n_dev);
+        ncclResult_t r = ncclSuccess;
+        if (!g_nccl.load() || (r = g_nccl.CommInitAll(comms.data(), n_dev, devs.data())) != ncclSuccess) {
+            const std::string why = g_nccl.handle ? g_nccl.GetErrorString(r) : g_nccl.error;
+            for (mctsb200_ctx* x : g->kids) mctsb200_ctx_destroy(x);
+            delete g;
+            return fail(MCTSB200_ERR_CUDA, "ncclCommInitAll over %d devices failed: %s", n_dev, why.c_str());
+        }
+        for (int i = 0; i < n_dev; ++i) {
+            g->kids[(size_t)i]->comm = comms[(size_t)i];
+            g->kids[(size_t)i]->comm_ranks = n_dev;
+            g->kids[(size_t)i]->comm_rank = i;
+        }
+    }
+#endif
+    *out = g;
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_ctx_device_count(mctsb200_ctx* ctx, int32_t* n_dev_out) {
+    if (!ctx || !n_dev_out) return fail(MCTSB200_ERR_INVALID_ARG, "NULL argument");
+    *n_dev_out = ctx->kids.empty() ? 1 : (int32_t)ctx->kids.size();
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_comm_unique_id(void* id_out, size_t bytes) {
+#ifdef MCTSB200_HOST_EMU
+    (void)id_out; (void)bytes;
+    return fail(MCTSB200_ERR_UNSUPPORTED, "NCCL is a device-side transport");
+#else
+    if (!id_out || bytes < sizeof(ncclUniqueId)) return fail(MCTSB200_ERR_INVALID_ARG, "id buffer must hold %zu bytes", sizeof(ncclUniqueId));
+    if (!g_nccl.load()) return fail(MCTSB200_ERR_CUDA, "%s", g_nccl.error.c_str());
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    std::memset(id_out, 0, bytes);
+    std::memcpy(id_out, &id, sizeof id);
+    return MCTSB200_OK;
+#endif
+}
+
+int32_t mctsb200_comm_init(mctsb200_ctx* ctx, const void* unique_id, size_t bytes, int32_t n_ranks, int32_t rank) {
+#ifdef MCTSB200_HOST_EMU
+    (void)ctx; (void)unique_id; (void)bytes; (void)n_ranks; (void)rank;
+    return fail(MCTSB200_ERR_UNSUPPORTED, "NCCL is a device-side transport");
+#else
+    if (!ctx || !unique_id || bytes < sizeof(ncclUniqueId)) return fail(MCTSB200_ERR_INVALID_ARG, "bad comm_init arguments");
+    if (!ctx->kids.empty()) return fail(MCTSB200_ERR_UNSUPPORTED, "a multi-device ctx already owns its communicator");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(MCTSB200_ERR_INVALID_ARG, "rank %d of %d", rank, n_ranks);
+    if (ctx->comm) return fail(MCTSB200_ERR_STATE, "this ctx already is a rank of a communicator");
+    if (!g_nccl.load()) return fail(MCTSB200_ERR_CUDA, "%s", g_nccl.error.c_str());
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof id);
+    ncclComm_t comm = nullptr;
+    NCCL_TRY(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+    ctx->comm = comm;
+    ctx->comm_ranks = n_ranks;
+    ctx->comm_rank = rank;
+    return MCTSB200_OK;
+#endif
+}
+
+int32_t mctsb200_root_sums_words(mctsb200_ctx* ctx, int64_t* words_out, int32_t capacity, int32_t* n_words_out) {
+    if (!ctx || !n_words_out) return fail(MCTSB200_ERR_INVALID_ARG, "NULL argument");
+    if (!ctx->kids.empty()) return fail(MCTSB200_ERR_UNSUPPORTED, "a multi-device ctx merges the sums itself");
+    if (ctx->root_words.empty()) return fail(MCTSB200_ERR_STATE, "no root-parallel call yet");
+    *n_words_out = (int32_t)ctx->root_words.size();
+    if (words_out) {
+        if (capacity < *n_words_out) return fail(MCTSB200_ERR_INVALID_ARG, "need room for %d words", *n_words_out);
+        for (size_t i = 0; i < ctx->root_words.size(); ++i) words_out[i] = ctx->root_words[i];
+    }
+    return MCTSB200_OK;
+}
+
+int32_t mctsb200_root_sums_merge(const int64_t* words, int32_t n_actions, double* sum_n_out, double* sum_nq_out) {
+    if (!words || n_actions < 1 || n_actions > 64 || !sum_n_out || !sum_nq_out) return fail(MCTSB200_ERR_INVALID_ARG, "bad arguments");
+    std::vector<long long> w(words, words + 5 * n_actions + 1);
+    root_sums_to_double(w.data(), n_actions, sum_n_out, sum_nq_out);
     return MCTSB200_OK;
 }
 
@@ -1546,6 +1897,12 @@ int32_t mctsb200_mdp_info(int32_t mdp_id, int32_t* n_actions, int64_t* state_byt
 
 int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* pod, size_t bytes) {
     if (!ctx || !pod) return fail(MCTSB200_ERR_INVALID_ARG, "NULL argument");
+    if (!ctx->kids.empty()) {
+        for (mctsb200_ctx* k : ctx->kids)
+            if (int32_t rc = mctsb200_mdp_configure(k, mdp_id, pod, bytes)) return rc;
+        ctx->kid_lo.clear();
+        return MCTSB200_OK;
+    }
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (mdp_id == MCTSB200_MDP_GRIDWORLD) {
         if (bytes != sizeof(mctsb200_gridworld_params)) return fail(MCTSB200_ERR_INVALID_ARG, "gridworld params: %zu bytes, expected %zu", bytes, sizeof(mctsb200_gridworld_params));
@@ -1672,6 +2029,7 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
 int32_t mctsb200_plan(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* roots, int64_t n_roots, size_t state_bytes,
                       int64_t root_index_base, int32_t* action_idx_out, double* best_q_out, int32_t* status_out, mctsb200_plan_stats* stats_out) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (!ctx->kids.empty()) return group_plan(ctx, cfg, mdp_id, roots, n_roots, state_bytes, root_index_base, action_idx_out, best_q_out, status_out, stats_out);
 #define MCTSB200_CALL(M) plan_dispatch<M>(ctx, cfg, roots, false, n_roots, state_bytes, root_index_base, action_idx_out, best_q_out, status_out, false, stats_out)
     MCTSB200_FOR_MDP(ctx, mdp_id, MCTSB200_CALL);
 #undef MCTSB200_CALL
@@ -1681,6 +2039,7 @@ int32_t mctsb200_plan_device(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, 
                              size_t state_bytes, int64_t root_index_base, int32_t* d_action_idx_out, double* d_best_q_out, int32_t* d_status_out,
                              mctsb200_plan_stats* stats_out) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (!ctx->kids.empty()) return fail(MCTSB200_ERR_UNSUPPORTED, "device pointers belong to one device: use mctsb200_plan (host buffers) on a multi-device ctx");
 #define MCTSB200_CALL(M) plan_dispatch<M>(ctx, cfg, d_roots, true, n_roots, state_bytes, root_index_base, d_action_idx_out, d_best_q_out, d_status_out, true, stats_out)
     MCTSB200_FOR_MDP(ctx, mdp_id, MCTSB200_CALL);
 #undef MCTSB200_CALL
@@ -1690,6 +2049,7 @@ int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg
                                     int64_t n_trees, int64_t tree_index_base, double* sum_n_out, double* sum_nq_out, double* d_sums_out,
                                     mctsb200_plan_stats* stats_out) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (!ctx->kids.empty()) return group_root_parallel(ctx, cfg, mdp_id, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out);
 #define MCTSB200_CALL(M) root_parallel_dispatch<M>(ctx, cfg, root_state, state_bytes, n_trees, tree_index_base, sum_n_out, sum_nq_out, d_sums_out, stats_out)
     MCTSB200_FOR_MDP(ctx, mdp_id, MCTSB200_CALL);
 #undef MCTSB200_CALL
@@ -1697,6 +2057,8 @@ int32_t mctsb200_plan_root_parallel(mctsb200_ctx* ctx, const mctsb200_solver_cfg
 
 int32_t mctsb200_set_progress_callback(mctsb200_ctx* ctx, mctsb200_progress_fn fn, void* user, int64_t every) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (ctx->kids.size() > 1) return fail(MCTSB200_ERR_UNSUPPORTED, "host hooks between launches are per device: not available on a multi-device ctx");
+    if (ctx->kids.size() == 1) return mctsb200_set_progress_callback(ctx->kids[0], fn, user, every);
     if (fn && every < 1) return fail(MCTSB200_ERR_INVALID_ARG, "a progress callback needs every >= 1 iterations");
     ctx->progress_fn = fn;
     ctx->progress_user = fn ? user : nullptr;
@@ -1706,6 +2068,8 @@ int32_t mctsb200_set_progress_callback(mctsb200_ctx* ctx, mctsb200_progress_fn f
 
 int32_t mctsb200_set_timer(mctsb200_ctx* ctx, mctsb200_timer_fn fn, void* user) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (ctx->kids.size() > 1) return fail(MCTSB200_ERR_UNSUPPORTED, "host hooks between launches are per device: not available on a multi-device ctx");
+    if (ctx->kids.size() == 1) return mctsb200_set_timer(ctx->kids[0], fn, user);
     ctx->timer_fn = fn;
     ctx->timer_user = fn ? user : nullptr;
     return MCTSB200_OK;
@@ -1715,6 +2079,9 @@ int32_t mctsb200_run_episodes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg,
                               size_t state_bytes, int32_t max_steps, uint64_t env_seed, int64_t episode_index_base, double* return_out,
                               int32_t* steps_out, void* final_states_out, mctsb200_plan_stats* stats_out) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    if (!ctx->kids.empty())
+        return group_run_episodes(ctx, cfg, mdp_id, initial_states, n_episodes, state_bytes, max_steps, env_seed, episode_index_base, return_out, steps_out,
+                                  final_states_out, stats_out);
 #define MCTSB200_CALL(M) \
     episodes_dispatch<M>(ctx, cfg, initial_states, n_episodes, state_bytes, max_steps, env_seed, episode_index_base, return_out, steps_out, final_states_out, stats_out)
     MCTSB200_FOR_MDP(ctx, mdp_id, MCTSB200_CALL);
@@ -1740,6 +2107,12 @@ int32_t mctsb200_root_parallel_decide(const double* sum_n, const double* sum_nq,
 }
 
 int32_t mctsb200_root_stats(mctsb200_ctx* ctx, int64_t root_i, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q, int64_t* total_n) {
+    if (ctx && !ctx->kids.empty()) {
+        mctsb200_ctx* kid = nullptr;
+        long long local = 0;
+        if (int32_t e = group_locate(ctx, root_i, &kid, &local)) return e;
+        return mctsb200_root_stats(kid, local, n_children, action_idx, n, q, total_n);
+    }
     int32_t rc = check_tree_query(ctx, root_i);
     if (rc) return rc;
 #define MCTSB200_CALL(M) root_stats_impl<M>(ctx, root_i, n_children, action_idx, n, q, total_n)
@@ -1748,6 +2121,12 @@ int32_t mctsb200_root_stats(mctsb200_ctx* ctx, int64_t root_i, int32_t* n_childr
 }
 
 int32_t mctsb200_tree_sizes_query(mctsb200_ctx* ctx, int64_t root_i, mctsb200_tree_sizes* sizes) {
+    if (ctx && !ctx->kids.empty()) {
+        mctsb200_ctx* kid = nullptr;
+        long long local = 0;
+        if (int32_t e = group_locate(ctx, root_i, &kid, &local)) return e;
+        return mctsb200_tree_sizes_query(kid, local, sizes);
+    }
     int32_t rc = check_tree_query(ctx, root_i);
     if (rc) return rc;
     if (!sizes) return fail(MCTSB200_ERR_INVALID_ARG, "sizes is NULL");
@@ -1757,6 +2136,12 @@ int32_t mctsb200_tree_sizes_query(mctsb200_ctx* ctx, int64_t root_i, mctsb200_tr
 }
 
 int32_t mctsb200_tree_export(mctsb200_ctx* ctx, int64_t root_i, const mctsb200_tree_buffers* buffers) {
+    if (ctx && !ctx->kids.empty()) {
+        mctsb200_ctx* kid = nullptr;
+        long long local = 0;
+        if (int32_t e = group_locate(ctx, root_i, &kid, &local)) return e;
+        return mctsb200_tree_export(kid, local, buffers);
+    }
     int32_t rc = check_tree_query(ctx, root_i);
     if (rc) return rc;
     if (!buffers) return fail(MCTSB200_ERR_INVALID_ARG, "buffers is NULL");
@@ -1767,11 +2152,14 @@ int32_t mctsb200_tree_export(mctsb200_ctx* ctx, int64_t root_i, const mctsb200_t
 
 int32_t mctsb200_clear_trees(mctsb200_ctx* ctx) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
+    for (mctsb200_ctx* k : ctx->kids) k->st.valid = false;
+    ctx->kid_lo.clear();
     ctx->st.valid = false;
     return MCTSB200_OK;
 }
 
 int32_t mctsb200_device_log(mctsb200_ctx* ctx, const double* x, int64_t n, double* out) {
+    if (ctx && !ctx->kids.empty()) return mctsb200_device_log(ctx->kids[0], x, n, out);
     if (!ctx || !x || !out || n < 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad arguments");
     if (n == 0) return MCTSB200_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1788,6 +2176,7 @@ int32_t mctsb200_device_log(mctsb200_ctx* ctx, const double* x, int64_t n, doubl
 }
 
 int32_t mctsb200_device_cos(mctsb200_ctx* ctx, const double* x, int64_t n, double* out) {
+    if (ctx && !ctx->kids.empty()) return mctsb200_device_cos(ctx->kids[0], x, n, out);
     if (!ctx || !x || !out || n < 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad arguments");
     if (n == 0) return MCTSB200_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1804,6 +2193,7 @@ int32_t mctsb200_device_cos(mctsb200_ctx* ctx, const double* x, int64_t n, doubl
 }
 
 int32_t mctsb200_device_philox(mctsb200_ctx* ctx, uint64_t seed, uint64_t tree, uint32_t iteration, uint32_t stream_id, int32_t n_blocks, uint32_t* out) {
+    if (ctx && !ctx->kids.empty()) return mctsb200_device_philox(ctx->kids[0], seed, tree, iteration, stream_id, n_blocks, out);
     if (!ctx || !out || n_blocks < 1 || n_blocks > 4096) return fail(MCTSB200_ERR_INVALID_ARG, "bad arguments");
     CUDA_TRY(cudaSetDevice(ctx->device));
     DevBuf o;

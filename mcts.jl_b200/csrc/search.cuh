@@ -1033,27 +1033,77 @@ __global__ void decide_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS,
     if (h.status != MCTSB200_OK) atomicOr(status_flags, h.status == MCTSB200_ERR_TERMINAL_ROOT ? 1ull : 2ull);
 }
 
-// Root-parallel partial sums (BASELINE config 5): lane a sums action a over all trees in tree order, so
-// the result is bit-identical to a sequential host loop. out = [sum_n[0..A) | sum_nq[0..A)].
+// Root-parallel partial sums (BASELINE config 5): sum_t N_t(a) and sum_t N_t(a)*Q_t(a) over the roots of all trees, in INTEGER
+// arithmetic so that the result does not depend on the order of the trees, on how they are sharded over devices or on the
+// reduction order of the allreduce that merges the devices' partial sums: each (once-rounded) double product N*Q is taken as a
+// multiple of 2^-64 (rounded toward zero) in 128-bit two's complement and accumulated in four 32-bit limbs held in int64
+// counters; the host recombines the limbs and rounds once to double (capi.cu, root_sums_to_double).
+// out: [n[A] | limbs[A][4] | inexact flag]  (kRootSumsWords(A) int64 words)
+__host__ __device__ constexpr int kRootSumsWords(int A) { return 5 * A + 1; }
+// false if p is not finite or |p| >= 2^40 (then the sum is flagged inexact and the decision reports NaN)
+__host__ __device__ __forceinline__ bool fix64_limbs(double p, long long (&c)[4]) {
+    const uint64_t b = dm_bits(p);
+    const int ex = (int)((b >> 52) & 0x7ffu);
+    if (ex == 0x7ff) return false;
+    const uint64_t mant = (b & 0x000fffffffffffffULL) | (ex ? 0x0010000000000000ULL : 0ULL);
+    const int e = (ex ? ex : 1) - 1075 + 64;  // fixed = mant * 2^e
+    if (e > 51) return false;                 // |p| >= 2^40
+    uint64_t lo, hi;
+    if (e >= 0) {
+        lo = mant << e;
+        hi = e == 0 ? 0ULL : mant >> (64 - e);
+    } else {
+        lo = -e >= 64 ? 0ULL : mant >> (-e);
+        hi = 0ULL;
+    }
+    if (b >> 63) {  // two's complement negation
+        lo = ~lo + 1ULL;
+        hi = ~hi + (lo == 0ULL ? 1ULL : 0ULL);
+    }
+    c[0] = (long long)(lo & 0xffffffffULL);
+    c[1] = (long long)(lo >> 32);
+    c[2] = (long long)(hi & 0xffffffffULL);
+    c[3] = (long long)hi >> 32;  // signed top limb
+    return true;
+}
 template <class M>
-__global__ void root_sums_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS, long long n_trees, double* out) {
-    const int act = threadIdx.x;
-    if (act >= M::kActions) return;
-    double sn = 0.0, snq = 0.0;
-    for (long long t = 0; t < n_trees; ++t) {
+__global__ void root_sums_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS, long long n_trees, unsigned long long* out) {
+    constexpr int A = M::kActions, W = kRootSumsWords(A);
+    __shared__ unsigned long long acc[W];
+#ifdef MCTSB200_HOST_EMU
+    unsigned long long* dst = out;  // (the emulator runs one thread at a time)
+#else
+    unsigned long long* dst = acc;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) acc[i] = 0ULL;
+    __syncthreads();
+#endif
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_trees) {
         const TreeHeader h = hdr[t];
-        if (h.n_state == 0) continue;
-        const Row<M>* rw = rows + t * NS + h.root;
-        for (int j = 0; j < rw->nchild(); ++j) {
-            if (rw->alabel(j) == act) {
-                const double nn = (double)rw->n[j];
-                sn = DM_ADD(sn, nn);
-                snq = DM_ADD(snq, DM_MUL(nn, rw->q[j]));
+        if (h.n_state != 0) {
+            const Row<M>* rw = rows + t * NS + h.root;
+            for (int j = 0; j < rw->nchild(); ++j) {
+                const int act = rw->alabel(j);
+                const int nn = rw->n[j];
+                long long c[4];
+                atomicAdd(dst + act, (unsigned long long)(long long)nn);
+                if (fix64_limbs(DM_MUL((double)nn, rw->q[j]), c)) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) atomicAdd(dst + A + 4 * act + i, (unsigned long long)c[i]);
+                } else {
+                    atomicOr(dst + 5 * A, 1ULL);
+                }
             }
         }
     }
-    out[act] = sn;
-    out[M::kActions + act] = snq;
+#ifndef MCTSB200_HOST_EMU
+    __syncthreads();
+    for (int i = threadIdx.x; i < W; i += blockDim.x)
+        if (acc[i]) {
+            if (i == 5 * A) atomicOr(out + i, acc[i]);
+            else atomicAdd(out + i, acc[i]);
+        }
+#endif
 }
 
 // Lane ordering for dense-state MDPs: a counting sort of the trees by root state, so that trees planning from

@@ -6,9 +6,15 @@ planning, one allreduce per decision for root-parallel search.
     by GLOBAL root index (`root_index_base`), hence the sharded result equals the single-GPU result bit-for-bit.
     Results are gathered with all_gather (4 + 8 B per root) only if the caller wants the full vectors.
   * Root-parallel search of one root (config 5): every rank grows `n_trees` independent trees of the same root
-    with distinct Philox tree indices; per-rank partial sums [sum N_a | sum N_a*Q_a] (2*|A| doubles = 64 B for
-    GridWorld) are merged with ONE allreduce over NVLink (NCCL) -- or gloo in the CPU tests -- and the decision
-    is argmax_a sum(NQ)/sum(N), first max, as best_sanode_Q (src/vanilla.jl:339-349).
+    with distinct Philox tree indices; the per-rank partial sums are INTEGER words (include/mctsb200.h:
+    mctsb200_plan_root_parallel), merged with ONE allreduce per decision, and the decision is
+    argmax_a sum(NQ)/sum(N), first max, as best_sanode_Q (src/vanilla.jl:339-349). On GPUs the allreduce is the
+    library's own ncclAllReduce over NVLink (`attach_comm` below joins the ranks' ctxs to one communicator; the
+    data never leaves the device before it is merged). Without a communicator (gloo in the CPU tests, MPI hosts)
+    this module adds the int64 words with the process group and converts them with mctsb200_root_sums_merge --
+    integer addition, so either way the merged sums equal a single-device run with the same trees bit for bit.
+  * One process driving several GPUs needs none of this: `Context([0, 1, ...])` (mctsb200_ctx_create_multi)
+    shards inside the library.
 """
 from __future__ import annotations
 
@@ -32,6 +38,24 @@ def _dist():
     import torch.distributed as dist
 
     return dist
+
+
+def attach_comm(ctx: Context, rank: Optional[int] = None, world: Optional[int] = None) -> None:
+    """Joins this rank's ctx to an NCCL communicator over all ranks of the default process group: rank 0 makes the id
+    (mctsb200_comm_unique_id), torch.distributed only carries its 128 bytes."""
+    import torch
+
+    dist = _dist()
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    if world == 1 or ctx.comm_ranks > 1:
+        return
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        buf = torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(buf, src=0)
+    ctx.comm_init(bytes(buf.cpu().numpy().tobytes()), world, rank)
 
 
 def plan_sharded(ctx: Context, solver, mdp, states: Sequence, rank: Optional[int] = None, world: Optional[int] = None,
@@ -90,17 +114,19 @@ def plan_root_parallel(ctx: Context, solver, mdp, state, n_trees_total: int, ran
     root = mdp.encode_states([state])
     lo, hi = shard_bounds(n_trees_total, rank, world)
     na = len(mdp.actions)
-    if hi > lo:
+    in_comm = ctx.comm_ranks > 1  # the library allreduces itself (attach_comm): every rank calls, also with no tree
+    if hi > lo or in_comm:
         sum_n, sum_nq, stats = ctx.plan_root_parallel(cfg, mdp.mdp_id, root, hi - lo, tree_index_base=lo)
     else:
         sum_n, sum_nq, stats = np.zeros(na), np.zeros(na), abi.PlanStats()
     del keep
-    if world > 1:
+    if world > 1 and not in_comm:
+        # no communicator (gloo, CPU tests): the process group adds the integer words, the library converts them
+        words = ctx.root_sums_words() if hi > lo else np.zeros(5 * na + 1, dtype=np.int64)
         dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
-        buf = torch.from_numpy(np.concatenate([sum_n, sum_nq])).to(dev)
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM)  # the only inter-GPU traffic of a decision: 2*|A| doubles
-        merged = buf.cpu().numpy()
-        sum_n, sum_nq = merged[:na], merged[na:]
+        buf = torch.from_numpy(words).to(dev)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)  # the only inter-rank traffic of a decision: 5*|A|+1 int64 words
+        sum_n, sum_nq = ctx.root_sums_merge(buf.cpu().numpy(), na)
     init_q = float(cfg.init_Q)
     a, bq, q = ctx.root_parallel_decide(sum_n, sum_nq, init_q)
     return a, bq, q, sum_n, stats

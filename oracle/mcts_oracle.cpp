@@ -1131,7 +1131,22 @@ int32_t oracle_tree_export(int64_t root_i, const mctsb200_tree_buffers* b) {
     return MCTSB200_OK;
 }
 
-// Root-parallel ensemble of one root (BASELINE config 5): per-action sums over trees in tree order.
+// Root-parallel ensemble of one root (BASELINE config 5). The reference has no such mode; the contract restated
+// here is include/mctsb200.h's: sum_n[a] = sum_t N_t(a); sum_nq[a] = the sum over trees of the once-rounded double products
+// N_t(a)*Q_t(a), each taken as a multiple of 2^-64 rounded toward zero, added exactly (128-bit integers) and rounded to double
+// once -- so the sums do not depend on the order of the trees or on how a multi-GPU run shards them. Written independently of
+// the library's limb arithmetic: frexp + __int128.
+static bool fix64_of(double p, __int128& out) {
+    if (!std::isfinite(p) || std::fabs(p) >= 1099511627776.0) return false;  // |p| < 2^40
+    int e;
+    const double m = std::frexp(p, &e);                          // p = m * 2^e, 0.5 <= |m| < 1
+    const long long mant = (long long)std::ldexp(m, 53);         // exact 53-bit integer (signed)
+    const int shift = e - 53 + 64;                               // p * 2^64 = mant * 2^shift
+    const unsigned __int128 mag = (unsigned __int128)(mant < 0 ? -mant : mant);
+    const unsigned __int128 fixed = shift >= 0 ? mag << shift : (-shift >= 64 ? (unsigned __int128)0 : mag >> (-shift));
+    out = mant < 0 ? -(__int128)fixed : (__int128)fixed;
+    return true;
+}
 int32_t oracle_plan_root_parallel(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* params, const void* root_state,
                                   int64_t n_trees, int64_t tree_index_base, int32_t n_threads, double* sum_n_out,
                                   double* sum_nq_out, mctsb200_plan_stats* stats) {
@@ -1140,14 +1155,22 @@ int32_t oracle_plan_root_parallel(const mctsb200_solver_cfg* cfg, int32_t mdp_id
                              nullptr, stats);
     if (rc != MCTSB200_OK) return rc;
     const int nA = mdp_id == MCTSB200_MDP_GRIDWORLD ? 4 : 3;
-    for (int a = 0; a < nA; ++a) sum_n_out[a] = sum_nq_out[a] = 0.0;
+    long long sn[4] = {0, 0, 0, 0};
+    __int128 snq[4] = {0, 0, 0, 0};
+    bool inexact = false;
     std::lock_guard<std::mutex> lk(g_mu);
     for (const RootResult& r : g_roots) {
         for (int i = 0; i < r.n_children; ++i) {
             const int a = r.child_action[(size_t)i];
-            sum_n_out[a] += (double)r.child_n[(size_t)i];
-            sum_nq_out[a] += (double)r.child_n[(size_t)i] * r.child_q[(size_t)i];
+            sn[a] += (long long)r.child_n[(size_t)i];
+            __int128 f;
+            if (fix64_of((double)r.child_n[(size_t)i] * r.child_q[(size_t)i], f)) snq[a] += f;
+            else inexact = true;
         }
+    }
+    for (int a = 0; a < nA; ++a) {
+        sum_n_out[a] = (double)sn[a];
+        sum_nq_out[a] = inexact ? std::nan("") : std::ldexp((double)snq[a], -64);
     }
     return MCTSB200_OK;
 }

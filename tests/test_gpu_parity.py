@@ -439,3 +439,55 @@ def test_plugin_params_may_carry_device_pointers(gpu_ctx):
     for x, y in zip(*out):
         _same_results(x, y)
     del table
+
+
+def _visible_devices():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+def test_multi_device_ctx_equals_one_device(gpu_ctx, oracle, n_dev):
+    """mctsb200_ctx_create_multi: the same entry points on a ctx over n_dev devices -- roots sharded inside the
+    library, root-parallel partial sums merged by the library's own ncclAllReduce -- return what ONE device returns, bit for
+    bit: actions, Q, trees addressed by global index, and the merged ensemble sums (integer words, so no reduction order can
+    show). n_dev = 1 runs everywhere; more devices run where the box has them."""
+    if _visible_devices() < n_dev:
+        pytest.skip(f"needs {n_dev} GPUs")
+    from helpers import assert_trees_equal, bits
+
+    multi = m.Context(list(range(n_dev)))
+    try:
+        for mdp, solver, roots in (
+            (GW, m.MCTSSolver(n_iterations=200, depth=20, exploration_constant=5.0, rng=4), gridworld_roots(301)),
+            (GW, m.DPWSolver(n_iterations=200, depth=20, exploration_constant=10.0, k_state=4.0, alpha_state=1 / 8, k_action=4.0, alpha_action=1 / 8, rng=4),
+             gridworld_roots(301)),
+            (MC, m.DPWSolver(n_iterations=300, depth=30, rng=4), mountaincar_roots(67)),
+        ):
+            cfg, keep = m.build_cfg(solver, mdp)
+            r = mdp.encode_states(roots)
+            for c in (gpu_ctx, multi):
+                c.configure(mdp.mdp_id, mdp.params())
+            a1, q1, s1, st1 = gpu_ctx.plan(cfg, mdp.mdp_id, r, 1000, want_status=True)
+            a2, q2, s2, st2 = multi.plan(cfg, mdp.mdp_id, r, 1000, want_status=True)
+            assert np.array_equal(a1, a2) and np.array_equal(bits(q1), bits(q2)) and np.array_equal(s1, s2)
+            for k in ("n_simulations", "n_tree_levels", "n_rollout_steps", "n_state_inserts", "algorithmic_bytes", "n_trees"):
+                assert getattr(st1, k) == getattr(st2, k), k
+            for i in (0, len(roots) // 2, len(roots) - 1):
+                assert_trees_equal(gpu_ctx.tree_export(i, mdp.state_dtype, mdp.state_width), multi.tree_export(i, mdp.state_dtype, mdp.state_width), f"tree {i}")
+            # root-parallel ensemble of one root, against one device and against the oracle
+            root = mdp.encode_states(roots[:1])
+            n1, nq1, _ = gpu_ctx.plan_root_parallel(cfg, mdp.mdp_id, root, 93, tree_index_base=5)
+            n2, nq2, _ = multi.plan_root_parallel(cfg, mdp.mdp_id, root, 93, tree_index_base=5)
+            oracle.configure(mdp.mdp_id, mdp.params())
+            n3, nq3, _ = oracle.plan_root_parallel(cfg, mdp.mdp_id, root, 93, tree_index_base=5, n_threads=4)
+            assert np.array_equal(n1, n2) and np.array_equal(bits(nq1), bits(nq2))
+            assert np.array_equal(n1, n3) and np.array_equal(bits(nq1), bits(nq3))
+            # fewer trees than devices: the empty shards still take part in the allreduce
+            n4, nq4, _ = multi.plan_root_parallel(cfg, mdp.mdp_id, root, 1, tree_index_base=5)
+            n5, nq5, _ = gpu_ctx.plan_root_parallel(cfg, mdp.mdp_id, root, 1, tree_index_base=5)
+            assert np.array_equal(n4, n5) and np.array_equal(bits(nq4), bits(nq5))
+            del keep
+    finally:
+        multi.close()
