@@ -10,6 +10,7 @@ Layout:
   plugins/     MDP plugins registered at run time (CUDA text compiled with NVRTC around the tile kernel)
   solvers.py   MCTSSolver / DPWSolver / solve / action / action_info / value / ranked_actions mirror
   distributed.py  root sharding across ranks and the root-parallel allreduce
+  workloads.py    the BASELINE.json configurations as synthetic workloads (root formulas, models, solver settings)
   julia/       the Julia glue a maintainer would add to MCTS.jl (unexecuted here: no Julia in the image)
 """
 from . import _abi as abi

@@ -45,8 +45,9 @@ def build_library(verbose: bool = False) -> str:
 
 def load_library(path: Optional[str] = None) -> C.CDLL:
     # MCTSB200_LIB: tuning experiments only (an alternative build of the same CUDA library, e.g. other -D switches)
+    explicit = path is not None
     path = os.path.abspath(path or os.environ.get("MCTSB200_LIB") or DEFAULT_LIB)
-    if path in _lib_cache:
+    if path in _lib_cache and (explicit or not hasattr(_lib_cache[path], "mctsb200_host_emulation")):
         return _lib_cache[path]
     if not os.path.exists(path):
         raise MCTSB200Error(
@@ -55,6 +56,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
             f"`make -C {CSRC_DIR}`). There is no CPU fallback.",
         )
     lib = abi.declare(C.CDLL(path))
+    if not explicit and hasattr(lib, "mctsb200_host_emulation"):
+        # the tests' host-emulation build is a CPU program: only a test that passes its path explicitly may load it
+        raise MCTSB200Error(abi.ERR_CUDA, f"{path} is the tests' host-emulation build, not the CUDA library. There is no CPU fallback.")
     got = lib.mctsb200_abi_version()
     if got != abi.ABI_VERSION:
         raise MCTSB200Error(abi.ERR_INVALID_ARG, f"ABI version {got} != {abi.ABI_VERSION}")

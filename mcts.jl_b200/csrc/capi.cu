@@ -1653,6 +1653,11 @@ bool plugin_shape_ok(int sd, int a) { return (sd == 2 || sd == 4) && a >= 2 && a
 extern "C" {
 
 int32_t mctsb200_abi_version(void) { return MCTSB200_ABI_VERSION; }
+#ifdef MCTSB200_HOST_EMU
+// only the tests' host-emulation build exports this marker: the product loader refuses such a library unless a test hands it over
+// explicitly (mcts.jl_b200/_lib.py), so no environment variable can turn the product path into a CPU path
+int32_t mctsb200_host_emulation(void) { return 1; }
+#endif
 const char* mctsb200_last_error(void) { return g_err.c_str(); }
 
 int32_t mctsb200_ctx_create(int32_t device_id, void* stream, mctsb200_ctx** out) {

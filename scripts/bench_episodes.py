@@ -32,7 +32,7 @@ def main():
     args = ap.parse_args()
 
     import mcts_jl_b200 as m
-    from helpers import gridworld_roots
+    from mcts_jl_b200.workloads import gridworld_roots
 
     mdp = m.SimpleGridWorld()
     if args.kind == "uct":  # bench/non-terminal_gw.jl:13-15

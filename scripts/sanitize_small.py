@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import mcts_jl_b200 as m
-from helpers import gridworld_roots, mountaincar_roots
+from mcts_jl_b200.workloads import gridworld_roots, mountaincar_roots
 
 ctx = m.Context(0)
 gw, mc, noisy = m.SimpleGridWorld(), m.MountainCar(), m.NoisyMountainCar()

@@ -26,20 +26,7 @@ def assert_trees_equal(t1: dict, t2: dict, what: str = "") -> None:
         assert np.array_equal(bits(t1[k]), bits(t2[k])), f"{what}: field {k} differs"
 
 
-def gridworld_roots(n: int):
-    """BASELINE config 2/3 root formula: root i = GWPos(1 + i mod 10, 1 + (i div 10) mod 10)."""
-    return [(1 + i % 10, 1 + (i // 10) % 10) for i in range(n)]
-
-
-def mountaincar_roots(n: int, seed: int = 0):
-    """Config 4 roots: x = -1.2 + 1.7 u1 (rejecting x >= 0.5), v = -0.07 + 0.14 u2."""
-    rng = np.random.default_rng(seed)
-    out = []
-    while len(out) < n:
-        x, v = -1.2 + 1.7 * rng.random(), -0.07 + 0.14 * rng.random()
-        if x < 0.5:
-            out.append((x, v))
-    return out
+from mcts_jl_b200.workloads import gridworld_roots, mountaincar_roots  # noqa: E402,F401  (the BASELINE root formulas live in the package)
 
 
 def run_both(ctx, orc, solver, mdp, roots, base: int = 0, compare_trees="all", lanes=None, literal=False):

@@ -24,7 +24,14 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "MCTS simulations/sec" and d["unit"] == "simulations/s"
     assert d["higher_is_better"] is True and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0
-    assert d["config"]["workload"] == "config2-uct-gridworld-deterministic" and d["config"]["n_iterations"] == 1000
+    # the headline is BASELINE config 2 on the DEFAULT SimpleGridWorld with the deterministic rollout policy, and the reference arm
+    # names exactly the configuration the product arm names (same keys, same values, roots_per_gpu included)
+    assert d["config"]["workload"] == "config2-uct-gridworld-default" and d["config"]["n_iterations"] == 1000
+    assert d["config"]["mdp_params"] == {"tprob": 0.7} and d["config"]["rollout_policy"] == "up" and d["config"]["roots_per_gpu"] == 65536
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.config_of("config2-uct-gridworld-default", 65536, 1)
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "roots" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

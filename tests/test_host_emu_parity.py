@@ -294,3 +294,12 @@ def test_emu_visit_counts_beyond_the_ucb_tables(emu_ctx, oracle, monkeypatch):
             monkeypatch.setenv("MCTSB200_FAST", fast)
             _, _, _, st = run_both(emu_ctx, oracle, s, GW, [(2, 2), (9, 9)])
             assert st.kernel_variant == int(fast) and st.n_select_exact > 1000
+
+
+def test_environment_cannot_select_the_emulation_build(emu_lib_path, monkeypatch):
+    """MCTSB200_LIB is for alternative CUDA builds; pointing it at the tests' CPU emulation is refused (no CPU path one env var away)."""
+    monkeypatch.setenv("MCTSB200_LIB", emu_lib_path)
+    with pytest.raises(m.MCTSB200Error) as ei:
+        m.load_library()
+    assert ei.value.status == m.abi.ERR_CUDA and "emulation" in str(ei.value)
+    assert m.load_library(emu_lib_path) is not None  # a test that names it explicitly may
