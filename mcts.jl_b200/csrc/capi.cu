@@ -823,6 +823,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.n_trees = n_trees;
     args.tree_index_base = tree_index_base;
     args.root_stride = root_stride;
+    args.prefetch_l2 = env_enabled("MCTSB200_PREFETCH_L2", true) ? 1 : 0;
 
     const int G = fast >= 0 ? 1 : pick_lanes<M, KIND>(ctx, cfg, n_trees);
     const int n_iter = (int)cfg->n_iterations;

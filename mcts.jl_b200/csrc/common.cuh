@@ -233,6 +233,7 @@ struct KernelArgs {
     long long n_slots;                  // tile slots of the launch (= n_trees without an order)
     int path_smem;                      // 1: the path stacks of a block live in dynamic shared memory, [level][tile]
     int path_tiles;                     // tiles per warp that own a path stack (0 = all 32/G; fewer when the trees are spread one per warp)
+    int prefetch_l2;                    // fast kernels: ask L2 for the rows of a level's possible successors while the level's own row is in flight
     int iter_begin, iter_end;
 };
 

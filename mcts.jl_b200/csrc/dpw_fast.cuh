@@ -156,6 +156,14 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                         leaf = true;  // estimate_value(s, 0)
                         break;
                     }
+                    if (args.prefetch_l2) {  // the rows this level's successor can be: towards L2 a level ahead (see uct_fast.cuh)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int nb = M::fast_neighbour(args.mdp, cell, j);
+                            prefetch_l2(row_at(nb));
+                            prefetch_l2(trow_at(nb));
+                        }
+                    }
                     int nchild = (int)((k[0].tag & 1u) + (k[1].tag & 1u) + (k[2].tag & 1u) + (k[3].tag & 1u));  // slots fill in order
                     int N = (k[0].n + k[1].n) + (k[2].n + k[3].n);  // total_n(snode); absent slots hold n = 0
 

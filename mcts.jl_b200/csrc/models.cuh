@@ -111,6 +111,12 @@ struct GridWorldDev {
         ft.term = p.ncells;
         return smem + fast_table_bytes(p);
     }
+    // dense index of the j-th state (j < 4) a move from `cell` can lead to besides `cell` itself and the terminal state: its four
+    // grid neighbours, whatever the action and the sampled outcome (the fast kernels ask L2 for their rows a level ahead)
+    __device__ __forceinline__ static int fast_neighbour(const Params& p, int cell, int j) {
+        const int d = j == 0 ? p.nx : j == 1 ? -p.nx : j == 2 ? -1 : 1;
+        return min(max(cell + d, 0), p.ncells);
+    }
     __device__ __forceinline__ static bool fast_has_reward(const FastTables& ft, int cell) { return ft.rflag[cell] != 0; }
     __device__ __forceinline__ static double fast_reward(const FastTables& ft, int cell) { return ft.reward[cell]; }
     // PRMT with sign-replicating selector nibbles (the __byte_perm intrinsic only honours three bits per nibble)

@@ -107,6 +107,33 @@ struct Tile {
 // x / n for a visit count n >= 1. An exactly zero numerator (every backup level inside a zero-reward region) would
 // send CUDA's IEEE division to its ~150-instruction slow path; 0 / n is the numerator itself, sign included.
 __device__ __forceinline__ double div_by_count(double x, double n) { return x == 0.0 ? x : DM_DIV(x, n); }
+// the same without a branch (two of these interleave in the backup below): the division always runs, on 1.0 when x is zero
+__device__ __forceinline__ double div_by_count_nb(double x, double n) {
+    const double d = DM_DIV(x == 0.0 ? 1.0 : x, n);
+    return x == 0.0 ? x : d;
+}
+
+// A whole POD of the node tables into registers with 256-bit loads that are issued HERE: written as plain member reads, the
+// compiler sinks each load below the branches that precede its first use, and a tree level then pays one L2 round trip after
+// another (state label -> terminal test -> transition bookkeeping -> widening test -> children statistics: three dependent
+// trips per level in the SASS of the first version) instead of one.
+template <class T>
+__device__ __forceinline__ void load_now(const T* p, T& out) {
+    static_assert(sizeof(T) % 32 == 0 && alignof(T) >= 32, "node-table PODs are whole 32-byte sectors");
+#ifdef MCTSB200_HOST_EMU
+    out = *p;
+#else
+    constexpr int kChunks = (int)(sizeof(T) / 32);
+    unsigned long long w[4 * kChunks];
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i)
+        asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+                     : "=l"(w[4 * i]), "=l"(w[4 * i + 1]), "=l"(w[4 * i + 2]), "=l"(w[4 * i + 3])
+                     : "l"(reinterpret_cast<const char*>(p) + 32 * i)
+                     : "memory");
+    memcpy(&out, w, sizeof(T));
+#endif
+}
 
 // multiplicity of a transition record += 1, fire-and-forget (RED: the warp does not wait for the old value)
 __device__ __forceinline__ void bump_count(int* count) {
@@ -287,23 +314,56 @@ struct Search {
     }
 
     // ---- backup (src/vanilla.jl:272-274, src/dpw.jl:149-151), deepest level first ---------------
+    // Two passes. What chains the levels together is only q_lvl = r_lvl + gamma * q_(lvl+1): two FP64 operations per level, run
+    // first, leaving q_lvl in the path entry. The statistics updates (n += 1, total_n += 1, q += (q_lvl - q) / n: three loads,
+    // a division, three stores) then depend on one another only where the same state node occurs twice on the path, so they run
+    // two levels at a time with their loads and divisions interleaved, and one after the other where two neighbouring levels
+    // share their node (self-loops and cycles: the deeper level's update must land first, as in the reference's unwinding
+    // recursion).
+    __device__ __forceinline__ void update_stats(Row<M>* rw, int slot, double qv) {
+        // all three reads before the first write: a load that follows a store to the same line waits for L2
+        const int nn = rw->n[slot] + 1;
+        const int tn = rw->total_n + 1;
+        const double qo = rw->q[slot];
+        rw->n[slot] = nn;
+        rw->total_n = tn;
+        rw->q[slot] = DM_ADD(qo, div_by_count(DM_SUB(qv, qo), i2d(nn)));
+    }
     __device__ __forceinline__ void backup(int top, double v) {
         tile.sync();
-        const double gamma = M::discount(a.mdp);
-        for (int lvl = top - 1; lvl >= 0; --lvl) {
-            const PathEntry e = path[lvl * path_stride];
-            const double qv = DM_ADD(e.r, DM_MUL(gamma, v));
-            if (lead()) {
-                // all three reads before the first write: a load that follows a store to the same line waits for L2
-                Row<M>* rw = rows + e.node;
-                const int nn = rw->n[e.slot] + 1;
-                const int tn = rw->total_n + 1;
-                const double qo = rw->q[e.slot];
-                rw->n[e.slot] = nn;
-                rw->total_n = tn;
-                rw->q[e.slot] = DM_ADD(qo, div_by_count(DM_SUB(qv, qo), i2d(nn)));
+        if (lead()) {
+            const double gamma = M::discount(a.mdp);
+            for (int lvl = top - 1; lvl >= 0; --lvl) {
+                PathEntry* e = path + lvl * path_stride;
+                v = DM_ADD(e->r, DM_MUL(gamma, v));
+                e->r = v;
             }
-            v = qv;
+            int lvl = top - 1;
+            for (; lvl >= 1; lvl -= 2) {
+                const PathEntry e0 = path[lvl * path_stride], e1 = path[(lvl - 1) * path_stride];
+                Row<M>* r0 = rows + e0.node;
+                Row<M>* r1 = rows + e1.node;
+                if (e0.node != e1.node) {
+                    const int nn0 = r0->n[e0.slot] + 1, tn0 = r0->total_n + 1;
+                    const int nn1 = r1->n[e1.slot] + 1, tn1 = r1->total_n + 1;
+                    const double qo0 = r0->q[e0.slot], qo1 = r1->q[e1.slot];
+                    const double d0 = div_by_count_nb(DM_SUB(e0.r, qo0), i2d(nn0));
+                    const double d1 = div_by_count_nb(DM_SUB(e1.r, qo1), i2d(nn1));
+                    r0->n[e0.slot] = nn0;
+                    r0->total_n = tn0;
+                    r0->q[e0.slot] = DM_ADD(qo0, d0);
+                    r1->n[e1.slot] = nn1;
+                    r1->total_n = tn1;
+                    r1->q[e1.slot] = DM_ADD(qo1, d1);
+                } else {
+                    update_stats(r0, e0.slot, e0.r);
+                    update_stats(r1, e1.slot, e1.r);
+                }
+            }
+            if (lvl == 0) {
+                const PathEntry e0 = path[0];
+                update_stats(rows + e0.node, e0.slot, e0.r);
+            }
         }
         tile.sync();
     }
@@ -385,6 +445,17 @@ struct Search {
             }
         }
         total_n = rw->total_n;
+    }
+
+    // the same from a row that is already in registers (load_now)
+    __device__ __forceinline__ void kids_of(const Row<M>& rw, int nchild, Kids& k, int& total_n) const {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int j = tile.lane + t * G;
+            k.n[t] = j < nchild ? pick_a(rw.n, j) : 1;
+            k.q[t] = j < nchild ? pick_a(rw.q, j) : 0.0;
+        }
+        total_n = rw.total_n;
     }
 
     // argmax(q, children): strict '>' scan from -Inf, default first child
@@ -477,6 +548,15 @@ struct Search {
         Kids k;
         int N;
         load_kids(rw, nchild, k, N);
+        return select_among(k, N, nchild, dpw);
+    }
+    __device__ __forceinline__ int select_child(const Row<M>& rw, int nchild, bool dpw) {
+        Kids k;
+        int N;
+        kids_of(rw, nchild, k, N);
+        return select_among(k, N, nchild, dpw);
+    }
+    __device__ __forceinline__ int select_among(const Kids& k, int N, int nchild, bool dpw) {
         const double c = a.cfg.c;
         if (c == 0.0) return argmax_q(k, nchild);
         int first_zero = kNone, n_max = 0;
@@ -538,36 +618,33 @@ struct Search {
         Stream rng;
         rng.init(a.cfg.seed, tree_index, it, 0u);
         int node = root, d = a.cfg.depth, top = 0;
-        State s = M::state_of(a.mdp, rows[node].key);
+        State s;
         int leaf = 0;  // 0: terminal (value 0.0), 1: estimate_value(s, d), 2: table overflow
         PT_CLOCK(t0);
+        const bool cache = kSuccCache && aux != nullptr;
         for (;;) {
             PT_ADD(3, 1);
+            // the node's row (state label + children statistics) and, for single-successor hashed models, its successor cache:
+            // one batch of loads before the first branch (load_now)
+            Row<M> R;
+            Aux<M> X;
+            load_now(rows + node, R);
+            if (cache) load_now(aux + node, X);
+            s = M::state_of(a.mdp, R.key);
             if (M::is_terminal(a.mdp, s)) break;
             if (d == 0) {
                 leaf = 1;
                 break;
             }
             if (lead()) cnt[CNT_LEVELS] += 1;
-            const bool cache = kSuccCache && aux != nullptr;
-            int c_sp[A];
-            double c_r[A];
-            if (cache) {  // (requested together with the row the selection reads)
-#pragma unroll
-                for (int k = 0; k < A; ++k) {
-                    c_sp[k] = aux[node].sp1[k];
-                    c_r[k] = aux[node].r1[k];
-                }
-            }
-            const int slot = select_child(rows + node, A, false);
+            const int slot = select_child(R, A, false);
             State sp;
             double r;
             int next;
-            const int known = cache ? pick_a(c_sp, slot) : -1;
+            const int known = cache ? pick_a(X.sp1, slot) : -1;
             if (known >= 0) {
                 next = known;
-                r = pick_a(c_r, slot);
-                sp = M::state_of(a.mdp, rows[next].key);
+                r = pick_a(X.r1, slot);
             } else {
                 M::gen(a.mdp, s, slot, rng, sp, r);
                 next = map_lookup(sp);
@@ -575,8 +652,8 @@ struct Search {
             if (lead()) path[top * path_stride] = PathEntry{node, slot, r};
             ++top;
             --d;
-            s = sp;
             if (next < 0) {
+                s = sp;
                 next = uct_insert(sp);  // new node: estimate_value(sp, depth-1), also when sp is terminal
                 leaf = next < 0 ? 2 : 1;
             }
@@ -623,16 +700,31 @@ struct Search {
         return id;
     }
 
-    // insert_action_node! (src/dpw_types.jl:174-186) into the next free slot of the row
-    __device__ __forceinline__ void dpw_insert_action(int node, int slot, const State& s, int act) {
+    // insert_action_node! (src/dpw_types.jl:174-186) into the next free slot of the row. R / X are the level's register copies
+    // of the node's row and transition bookkeeping: every lane updates them, the leader writes the same values through.
+    __device__ __forceinline__ void dpw_insert_action(int node, int slot, const State& s, int act, Row<M>& R, Aux<M>& X) {
+        const int n0 = init_N(s, act);
+        const double q0 = init_Q(s, act);
+        R.packed = Row<M>::pack_add(R.packed, slot, act);
+        R.total_n += n0;  // tree.total_n[snode] += n0
+#pragma unroll
+        for (int k = 0; k < A; ++k)
+            if (k == slot) {
+                R.n[k] = n0;
+                R.q[k] = q0;
+                X.nac[k] = 0;
+                X.thead[k] = -1;
+                X.tpush[k] = 0;
+                X.pbase[k] = 0;
+                X.pcap[k] = 0;
+            }
         if (lead()) {
             Row<M>* rw = rows + node;
             Aux<M>* ax = aux + node;
-            const int n0 = init_N(s, act);
             rw->n[slot] = n0;
-            rw->q[slot] = init_Q(s, act);
-            rw->packed = Row<M>::pack_add(rw->packed, slot, act);
-            rw->total_n += n0;  // tree.total_n[snode] += n0
+            rw->q[slot] = q0;
+            rw->packed = R.packed;
+            rw->total_n = R.total_n;
             ax->nac[slot] = 0;
             ax->thead[slot] = -1;
             ax->tpush[slot] = 0;
@@ -668,62 +760,39 @@ struct Search {
         PT_CLOCK(t0);
         for (;;) {
             PT_ADD(3, 1);
-            // Everything this level needs from the node is requested at once: the row (children statistics and the state label)
-            // and the per-child transition bookkeeping, so the level pays ONE trip to L2 / HBM instead of a chain
-            // row -> aux -> transition record -> successor's label.
+            // Everything this level needs from the node is requested at once, before the first branch: the row (children statistics
+            // and the state label) and the per-child transition bookkeeping, so the level pays ONE trip to L2 / HBM instead of a
+            // chain label -> bookkeeping -> statistics (load_now: 256-bit loads the compiler cannot sink).
             Row<M>* rw = rows + node;
             Aux<M>* ax = aux + node;
-            int x_nac[A], x_thead[A], x_tpush[A], x_sp1[A], x_pbase[A], x_pcap[A];
-            double x_r1[A];
-#pragma unroll
-            for (int k = 0; k < A; ++k) {
-                x_nac[k] = ax->nac[k];
-                x_thead[k] = ax->thead[k];
-                x_tpush[k] = ax->tpush[k];
-                x_sp1[k] = ax->sp1[k];
-                x_r1[k] = ax->r1[k];
-                x_pbase[k] = kPushLog ? ax->pbase[k] : 0;
-                x_pcap[k] = kPushLog ? ax->pcap[k] : 0;
-            }
-            s = M::state_of(a.mdp, rw->key);
+            Row<M> R;
+            Aux<M> X;
+            load_now(rw, R);
+            load_now(ax, X);
+            s = M::state_of(a.mdp, R.key);
             if (M::is_terminal(a.mdp, s)) break;
             if (d == 0) {
                 leaf = 1;
                 break;
             }
-            int nchild = rw->nchild();
+            int nchild = R.nchild();
             // ---- action progressive widening (src/dpw.jl:94-114) ----
             if (a.cfg.enable_action_pw) {
                 // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action[len]
-                if (rw->total_n >= a.cfg.nmin_action[nchild]) {
+                if (R.total_n >= a.cfg.nmin_action[nchild]) {
                     const int act = rng.uniform_int(A);  // next_action(::RandomActionGenerator)
                     bool present = false;
-                    const uint32_t pk = rw->packed;
+                    const uint32_t pk = R.packed;
 #pragma unroll
                     for (int j = 0; j < A; ++j) present |= (j < nchild) & ((int)((pk >> (4 * j)) & 15u) == act);
                     if (!present) {  // check_repeat_action (always on; see capi.cu)
-                        dpw_insert_action(node, nchild, s, act);
-#pragma unroll
-                        for (int k = 0; k < A; ++k)
-                            if (k == nchild) {
-                                x_nac[k] = 0;
-                                x_thead[k] = -1;
-                                x_tpush[k] = 0;
-                                x_pcap[k] = 0;
-                            }
+                        dpw_insert_action(node, nchild, s, act, R, X);
                         ++nchild;
                         tile.sync();
                     }
                 }
             } else if (nchild == 0) {
-                for (int act = 0; act < A; ++act) dpw_insert_action(node, act, s, act);
-#pragma unroll
-                for (int k = 0; k < A; ++k) {
-                    x_nac[k] = 0;
-                    x_thead[k] = -1;
-                    x_tpush[k] = 0;
-                    x_pcap[k] = 0;
-                }
+                for (int act = 0; act < A; ++act) dpw_insert_action(node, act, s, act, R, X);
                 nchild = A;
                 tile.sync();
             }
@@ -731,30 +800,30 @@ struct Search {
                 cnt[CNT_LEVELS] += 1;
                 cnt[CNT_CHILDREN_SEEN] += (unsigned)nchild;
             }
-            const int slot = select_child(rw, nchild, true);
-            const int act = rw->alabel(slot);
+            const int slot = select_child(R, nchild, true);
+            const int act = R.alabel(slot);
 
             // ---- state progressive widening (src/dpw.jl:119-141) ----
             bool new_node = false;
             int spnode;
             double r;
             State sp;
-            const int nac = pick(x_nac, slot);
+            const int nac = pick(X.nac, slot);
             bool widen = nac == 0;
             if (!widen && a.cfg.enable_state_pw) {
                 // n_a_children <= k_state * n^alpha_state  <=>  n >= nmin_state[n_a_children]
                 const int need = nac < a.cfg.nmin_state_n ? __ldg(a.cfg.nmin_state + nac) : 0x7fffffff;
-                widen = rw->n[slot] >= need;
+                widen = pick(R.n, slot) >= need;
             }
             if (M::kMaxBranch == 1 && widen && nac == 1 && a.cfg.check_repeat_state) {
                 // A model whose (s, a) has exactly one successor, with merged states: gen would return the state this action
                 // node already leads to and the lookup would find its node -- push!(transitions[sanode], ...) on the one
                 // record, without the transition arithmetic and the hash probe (MountainCar: gen draws no random number).
-                spnode = pick(x_sp1, slot);
-                r = pick(x_r1, slot);
+                spnode = pick(X.sp1, slot);
+                r = pick(X.r1, slot);
                 if (lead()) {
-                    bump_count(&trans[pick(x_thead, slot)].count);
-                    ax->tpush[slot] = pick(x_tpush, slot) + 1;
+                    bump_count(&trans[pick(X.thead, slot)].count);
+                    ax->tpush[slot] = pick(X.tpush, slot) + 1;
                 }
             } else if (widen) {
                 M::gen(a.mdp, s, act, rng, sp, r);
@@ -770,7 +839,7 @@ struct Search {
                 // push!(transitions[sanode], (spnode, r)) in multiset form; unique_transitions bookkeeping
                 int rec = -1;
                 if (!new_node) {
-                    for (rec = pick(x_thead, slot); rec >= 0; rec = trans[rec].next)
+                    for (rec = pick(X.thead, slot); rec >= 0; rec = trans[rec].next)
                         if (trans[rec].sp == spnode) break;
                 }
                 if (rec < 0 && n_trans >= a.geo.NT) {
@@ -780,8 +849,8 @@ struct Search {
                 }
                 if constexpr (kPushLog) {
                     // push!(transitions[sanode], ...) literally: append the record id to the action node's log
-                    const int pushes = pick(x_tpush, slot), cap = pick(x_pcap, slot);
-                    int base = pick(x_pbase, slot);
+                    const int pushes = pick(X.tpush, slot), cap = pick(X.pcap, slot);
+                    int base = pick(X.pbase, slot);
                     if (pushes == cap) {  // full (or not allocated yet): move to a chunk twice as large at the end of the arena
                         const int ncap = cap ? 2 * cap : 4;
                         if (n_plog + ncap > a.geo.NP) {
@@ -807,7 +876,7 @@ struct Search {
                         TransRec t;
                         t.r = r;
                         t.sp = spnode;
-                        t.next = pick(x_thead, slot);
+                        t.next = pick(X.thead, slot);
                         t.count = 1;
                         t.pad[0] = t.pad[1] = t.pad[2] = 0;
                         trans[n_trans] = t;
@@ -816,23 +885,23 @@ struct Search {
                         ax->sp1[slot] = spnode;
                         ax->r1[slot] = r;
                     }
-                    ax->tpush[slot] = pick(x_tpush, slot) + 1;
+                    ax->tpush[slot] = pick(X.tpush, slot) + 1;
                 }
                 if (rec < 0) n_trans += 1;
             } else {
                 // rand(rng, transitions[sanode]): index j of the push-ordered multiset; records are chained
                 // newest-first, so walk with the mirrored index
-                const int pushes = pick(x_tpush, slot);
+                const int pushes = pick(X.tpush, slot);
                 const int j = rng.uniform_int(pushes);
                 if (M::kMaxBranch == 1 && a.cfg.check_repeat_state) {  // a single record: every draw picks it
-                    spnode = pick(x_sp1, slot);
-                    r = pick(x_r1, slot);
+                    spnode = pick(X.sp1, slot);
+                    r = pick(X.r1, slot);
                 } else if (kPushLog) {  // transitions[sanode][j]
-                    const int rec = plog[pick(x_pbase, slot) + j];
+                    const int rec = plog[pick(X.pbase, slot) + j];
                     spnode = trans[rec].sp;
                     r = trans[rec].r;
                 } else {
-                    int jm = pushes - 1 - j, cum = 0, rec = pick(x_thead, slot);
+                    int jm = pushes - 1 - j, cum = 0, rec = pick(X.thead, slot);
                     for (;;) {
                         const int cnt_r = trans[rec].count;
                         if (jm < cum + cnt_r || trans[rec].next < 0) break;

@@ -94,6 +94,14 @@ __device__ __forceinline__ void load_row(const FastRow* rw, FastChild (&k)[4]) {
     k[3].q = __longlong_as_double((long long)b2); k[3].n = (int)(uint32_t)b3; k[3].tag = (uint32_t)(b3 >> 32);
 #endif
 }
+// a line towards L2 without touching L1 or a register (HBM -> L2 ahead of the load that will need it)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef MCTSB200_HOST_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 __device__ __forceinline__ void store_child(FastChild* c, double q, int n, uint32_t tag) {
     *reinterpret_cast<int4*>(c) = int4{__double2loint(q), __double2hiint(q), n, (int)tag};
 }
@@ -219,6 +227,14 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     PT_CLOCK(l0);
                     // While this node's row is still on its way from L2: everything that does not need it -- the random word of
                     // this level and the successor each action would lead to (sp, r = @gen(:sp,:r)(mdp, s, a, rng) for all a).
+                    // The batch's node tables are several times the L2 (65 536 trees x 101 rows x 64 B = 424 MB) and a warp's lanes walk
+                    // different trees, so without help nearly every level of a warp waits for HBM on behalf of one lane or another.
+                    // Whatever the action and the sampled outcome, the successor is this cell, the terminal state or one of the four
+                    // grid neighbours: their rows are asked for now, a whole level before one of them is loaded.
+                    if (!AHEAD && args.prefetch_l2) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) prefetch_l2(row_at(M::fast_neighbour(args.mdp, cell, j)));
+                    }
                     uint32_t w = 0;
                     if (!DET) {
                         if ((top & 3) == 0) philox_block(seed, tree_index, (uint32_t)it, 0u, (uint32_t)(top >> 2), b0, b1, b2, b3);
