@@ -823,7 +823,9 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.n_trees = n_trees;
     args.tree_index_base = tree_index_base;
     args.root_stride = root_stride;
-    args.prefetch_l2 = env_enabled("MCTSB200_PREFETCH_L2", true) ? 1 : 0;
+    // (measured on B200, profiles/r2b_*: 4 % SLOWER on config 2, 1 % on config 3 -- the rows that miss L2 are not what the
+    // levels wait for; kept as a switch for the record)
+    args.prefetch_l2 = env_enabled("MCTSB200_PREFETCH_L2", false) ? 1 : 0;
 
     const int G = fast >= 0 ? 1 : pick_lanes<M, KIND>(ctx, cfg, n_trees);
     const int n_iter = (int)cfg->n_iterations;

@@ -25,6 +25,7 @@
 namespace mctsb200 {
 
 constexpr int kBlockThreads = 128;
+constexpr int kTileTab = 1024;  // entries of c*sqrt(log N) and 1/sqrt(n) a block of the tile kernel stages in shared memory
 
 template <int G>
 struct Tile {
@@ -126,11 +127,20 @@ __device__ __forceinline__ void load_now(const T* p, T& out) {
     constexpr int kChunks = (int)(sizeof(T) / 32);
     unsigned long long w[4 * kChunks];
 #pragma unroll
-    for (int i = 0; i < kChunks; ++i)
+    for (int i = 0; i < kChunks; ++i) {
+#ifdef __CUDACC_RTC__  // (the PTX version NVRTC emits for run-time plugins has no 256-bit vector loads: two 128-bit ones)
+        asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(w[4 * i]), "=l"(w[4 * i + 1]) : "l"(reinterpret_cast<const char*>(p) + 32 * i) : "memory");
+        asm volatile("ld.global.v2.u64 {%0,%1}, [%2];"
+                     : "=l"(w[4 * i + 2]), "=l"(w[4 * i + 3])
+                     : "l"(reinterpret_cast<const char*>(p) + 32 * i + 16)
+                     : "memory");
+#else
         asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];"
                      : "=l"(w[4 * i]), "=l"(w[4 * i + 1]), "=l"(w[4 * i + 2]), "=l"(w[4 * i + 3])
                      : "l"(reinterpret_cast<const char*>(p) + 32 * i)
                      : "memory");
+#endif
+    }
     memcpy(&out, w, sizeof(T));
 #endif
 }
@@ -168,6 +178,12 @@ struct Search {
     unsigned cnt[CNT_COUNT];
     unsigned long long rollout_steps;
     int path_stride;  // entries between consecutive levels of this tile's path
+    // the heads of the two UCB tables in shared memory (c folded into the first: the same single rounded multiply), and the
+    // first widening thresholds in registers: a level then waits for no table load after its row has arrived
+    const double* s_cs;
+    const double* s_rs;
+    int nmin_s[4];      // nmin_state[0..3]
+    int nmin_a[A + 1];  // nmin_action[0..A]
 #ifdef MCTSB200_PHASE_TIMING
     long long cyc[4] = {0, 0, 0, 0};  // descent, leaf evaluation, backup, trips
 #define PT_CLOCK(var) const long long var = clock64()
@@ -191,6 +207,11 @@ struct Search {
 #pragma unroll
         for (int i = 0; i < CNT_COUNT; ++i) cnt[i] = 0;
         rollout_steps = 0;
+        s_cs = s_rs = nullptr;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nmin_s[i] = (args.cfg.nmin_state && i < args.cfg.nmin_state_n) ? __ldg(args.cfg.nmin_state + i) : 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i <= A; ++i) nmin_a[i] = args.cfg.nmin_action[i];
     }
 
     __device__ __forceinline__ bool lead() const { return tile.lane == 0; }
@@ -205,6 +226,15 @@ struct Search {
 #pragma unroll
         for (int k = 1; k < M::kActions; ++k)
             if (slot == k) out = v[k];
+        return out;
+    }
+
+    template <int N2>
+    __device__ __forceinline__ static int pick_n(const int (&v)[N2], int i) {
+        int out = v[0];
+#pragma unroll
+        for (int k = 1; k < N2; ++k)
+            if (i == k) out = v[k];
         return out;
     }
 
@@ -577,14 +607,14 @@ struct Search {
         n_max = -tile.min_int(-n_max);
         if (N >= a.cfg.log_tab_n || n_max >= a.cfg.rsqrt_tab_n) return select_exact(k, nchild, N, dpw);
 
-        const double cs = DM_MUL(c, __ldg(a.cfg.sqrtlog_tab + N));
+        const double cs = (s_cs && N < kTileTab) ? s_cs[N] : DM_MUL(c, __ldg(a.cfg.sqrtlog_tab + N));
         double best = -CUDART_INF, second = -CUDART_INF, mag = 0.0;
         int best_i = kNone;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const int j = tile.lane + t * G;
             if (j < nchild) {
-                const double term = DM_MUL(cs, __ldg(a.cfg.rsqrt_tab + k.n[t]));
+                const double term = DM_MUL(cs, (s_rs && k.n[t] < kTileTab) ? s_rs[k.n[t]] : __ldg(a.cfg.rsqrt_tab + k.n[t]));
                 const double S = DM_ADD(k.q[t], term);
                 mag = DM_ADD(mag, DM_ADD(fabs(k.q[t]), term));
                 if (S > best) {
@@ -779,7 +809,7 @@ struct Search {
             // ---- action progressive widening (src/dpw.jl:94-114) ----
             if (a.cfg.enable_action_pw) {
                 // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action[len]
-                if (R.total_n >= a.cfg.nmin_action[nchild]) {
+                if (R.total_n >= pick_n(nmin_a, nchild)) {
                     const int act = rng.uniform_int(A);  // next_action(::RandomActionGenerator)
                     bool present = false;
                     const uint32_t pk = R.packed;
@@ -812,7 +842,7 @@ struct Search {
             bool widen = nac == 0;
             if (!widen && a.cfg.enable_state_pw) {
                 // n_a_children <= k_state * n^alpha_state  <=>  n >= nmin_state[n_a_children]
-                const int need = nac < a.cfg.nmin_state_n ? __ldg(a.cfg.nmin_state + nac) : 0x7fffffff;
+                const int need = nac < 4 ? pick_n(nmin_s, nac) : (nac < a.cfg.nmin_state_n ? __ldg(a.cfg.nmin_state + nac) : 0x7fffffff);
                 widen = pick(R.n, slot) >= need;
             }
             if (M::kMaxBranch == 1 && widen && nac == 1 && a.cfg.check_repeat_state) {
@@ -944,7 +974,12 @@ template <class M, int KIND, int G>
 __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_constant__ KernelArgs<M> args) {
     __shared__ unsigned long long s_cnt[CNT_COUNT];
 #ifndef MCTSB200_HOST_EMU
+    __shared__ double s_ucb[2][kTileTab];
     if (threadIdx.x < CNT_COUNT) s_cnt[threadIdx.x] = 0ull;
+    for (int i = threadIdx.x; i < kTileTab; i += kBlockThreads) {
+        s_ucb[0][i] = i < args.cfg.log_tab_n ? DM_MUL(args.cfg.c, args.cfg.sqrtlog_tab[i]) : 0.0;
+        s_ucb[1][i] = i < args.cfg.rsqrt_tab_n ? args.cfg.rsqrt_tab[i] : 0.0;
+    }
     __syncthreads();
 #endif
 
@@ -953,6 +988,8 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
     if (tree >= 0) {
         Search<M, G> S(args, tree);
 #ifndef MCTSB200_HOST_EMU
+        S.s_cs = s_ucb[0];
+        S.s_rs = s_ucb[1];
         if (args.path_smem) {  // [level][tile]: tiles at the same level touch consecutive 16 B entries
             extern __shared__ __align__(16) unsigned char dyn_smem[];
             // (spread batches keep their trees in the first path_tiles tiles of each warp: only those get a stack)
