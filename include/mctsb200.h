@@ -55,7 +55,7 @@ enum {
 };
 
 /* ---- built-in MDP plugins ------------------------------------------------------------------- */
-enum { MCTSB200_MDP_GRIDWORLD = 0, MCTSB200_MDP_MOUNTAINCAR = 1, MCTSB200_MDP_COUNT = 2 };
+enum { MCTSB200_MDP_GRIDWORLD = 0, MCTSB200_MDP_MOUNTAINCAR = 1, MCTSB200_MDP_GAUSSIAN_BOX = 2, MCTSB200_MDP_COUNT = 3 };
 
 #define MCTSB200_GW_MAX_SPECIAL 32
 
@@ -78,6 +78,23 @@ typedef struct {
     double cost;     /* -1.0  */
     double jackpot;  /* 100.0 */
 } mctsb200_mountaincar_params;
+
+/* A continuous-state, CONTINUOUS-ACTION model: the MDP of the reference's test/discussion_514.jl (states(m) = Box, actions(m) = Box,
+ * transition(m, s, a) = MvNormal(s, Diagonal(var)), discount 0.9, reward 0) with the drift and the reward that make a search over it
+ * worth comparing:  sp = s + drift * (a_1, ..., a_AD, 0, ...) + sqrt(var) * z,  z ~ N(0, I) (Box-Muller on the tree's Philox stream with
+ * the deterministic log / cos / sin of mctsb200_detmath.h);  r = -cost * |sp|^2;  actions(m, s) = Box(a_lo, a_hi), sampled uniformly
+ * by next_action (RandomActionGenerator, src/action_gen.jl:11-13: rand(rng, actions(mdp, s))). drift = 0, cost = 0 is the test's
+ * model. State = MCTSB200_BOX_STATE_DOUBLES float64 (the test's SVector{3}, padded with one 0.0), action = MCTSB200_BOX_ACTION_DOUBLES
+ * float64. No terminal states. Only DPW can plan for it (vanilla UCT enumerates actions(mdp, s), src/vanilla.jl:297). */
+#define MCTSB200_BOX_STATE_DOUBLES 4
+#define MCTSB200_BOX_ACTION_DOUBLES 2
+typedef struct {
+    double discount;                               /* 0.9 */
+    double a_lo[MCTSB200_BOX_ACTION_DOUBLES], a_hi[MCTSB200_BOX_ACTION_DOUBLES]; /* [-5,-5], [5,5] */
+    double var[3];                                 /* diagonal covariance, [0.1, 0.1, 0.1] */
+    double drift;                                  /* 0.0 in the test */
+    double cost;                                   /* 0.0 in the test */
+} mctsb200_gaussian_box_params;
 
 /* ---- solver configuration -------------------------------------------------------------------- */
 enum { MCTSB200_KIND_UCT = 0, MCTSB200_KIND_DPW = 1 };
@@ -288,6 +305,7 @@ typedef struct {
     int64_t n_action_nodes;
     int64_t n_transitions;   /* DPW: distinct (sanode, spnode) records; 0 for UCT */
     int64_t state_bytes;
+    int64_t action_doubles;  /* 0: actions are indices into actions(mdp) (a_labels); > 0: actions are vectors (a_label_vectors) */
 } mctsb200_tree_sizes;
 
 /* Caller-allocated arrays sized from mctsb200_tree_sizes (two-call pattern). Field names follow
@@ -308,11 +326,17 @@ typedef struct {
     int64_t* trans_spnode;   /* [n_transitions] 1-based state-node id                              */
     double* trans_r;         /* [n_transitions]                                                    */
     int64_t* trans_count;    /* [n_transitions] multiplicity in transitions[sanode]                */
+    /* continuous action spaces (action_doubles > 0): the action-node labels are vectors; a_labels is then filled with -1 */
+    double* a_label_vectors; /* [n_action_nodes * action_doubles]                                  */
 } mctsb200_tree_buffers;
 
 int32_t mctsb200_tree_sizes_query(mctsb200_ctx* ctx, int64_t root_i, mctsb200_tree_sizes* sizes);
 int32_t mctsb200_tree_export(mctsb200_ctx* ctx, int64_t root_i, const mctsb200_tree_buffers* buffers);
 int32_t mctsb200_clear_trees(mctsb200_ctx* ctx); /* clear_tree! (src/vanilla.jl:148, src/dpw.jl:6-8) */
+/* Continuous action spaces: the action best_sanode chose for roots [first_root, first_root + n) of the last plan call, as vectors
+ * (n * action_doubles float64; the action_idx_out of mctsb200_plan then holds the chosen child's position among the root's
+ * children, -1 if it has none). a_labels[sanode] of src/dpw.jl:65. */
+int32_t mctsb200_root_action_vectors(mctsb200_ctx* ctx, int64_t first_root, int64_t n, double* out);
 
 /* ---- numerical contract helpers (exposed so hosts/tests can check device == host bit-for-bit) ---- */
 /* Evaluates det_log / det_cos (mctsb200_detmath.h) ON THE DEVICE for n host inputs. */

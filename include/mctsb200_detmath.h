@@ -146,7 +146,10 @@ MCTSB200_HD double dm_kernel_sin(double x, double y) {
     return DM_SUB(x, DM_SUB(DM_SUB(a, y), DM_MUL(v, S1)));
 }
 
-/* Cosine for |x| <= 2^20 (two-stage Cody-Waite reduction by pi/2). Outside that range: NaN. */
+/* Sine / cosine for |x| <= 2^20 (two-stage Cody-Waite reduction by pi/2). Outside that range: NaN. `want_sin` selects the
+ * function after the common reduction: sin(y + n pi/2) and cos(y + n pi/2) are +-sin(y) or +-cos(y) by the quadrant n mod 4. */
+MCTSB200_HD double det_sincos_impl(double x, int want_sin);
+MCTSB200_HD double det_sin(double x) { return det_sincos_impl(x, 1); }
 MCTSB200_HD double det_cos(double x) {
     const double INV_PIO2 = dm_from_bits(0x3fe45f306dc9c883ULL);
     const double PIO2_1 = dm_from_bits(0x3ff921fb54400000ULL);  /* first 33 bits of pi/2 */
@@ -168,6 +171,29 @@ MCTSB200_HD double det_cos(double x) {
     const double y0 = DM_SUB(r, w);
     const double y1 = DM_SUB(DM_SUB(r, y0), w);
     switch (n & 3) {
+        case 0: return dm_kernel_cos(y0, y1);
+        case 1: return DM_SUB(0.0, dm_kernel_sin(y0, y1));
+        case 2: return DM_SUB(0.0, dm_kernel_cos(y0, y1));
+        default: return dm_kernel_sin(y0, y1);
+    }
+}
+
+MCTSB200_HD double det_sincos_impl(double x, int want_sin) {
+    const double INV_PIO2 = dm_from_bits(0x3fe45f306dc9c883ULL);
+    const double PIO2_1 = dm_from_bits(0x3ff921fb54400000ULL);
+    const double PIO2_2 = dm_from_bits(0x3dd0b4611a600000ULL);
+    const double PIO2_2T = dm_from_bits(0x3ba3198a2e037073ULL);
+    const uint64_t ax = dm_bits(x) & 0x7fffffffffffffffULL;
+    if (ax > 0x4130000000000000ULL) return dm_from_bits(0x7ff8000000000000ULL);
+    const double fn = floor(DM_ADD(DM_MUL(x, INV_PIO2), 0.5));
+    const int n = (int)fn;
+    const double t = DM_SUB(x, DM_MUL(fn, PIO2_1));
+    const double w1 = DM_MUL(fn, PIO2_2);
+    const double r = DM_SUB(t, w1);
+    const double w = DM_SUB(DM_MUL(fn, PIO2_2T), DM_SUB(DM_SUB(t, r), w1));
+    const double y0 = DM_SUB(r, w);
+    const double y1 = DM_SUB(DM_SUB(r, y0), w);
+    switch ((n + (want_sin ? 3 : 0)) & 3) { /* sin(x) = cos(x - pi/2): one quadrant back */
         case 0: return dm_kernel_cos(y0, y1);
         case 1: return DM_SUB(0.0, dm_kernel_sin(y0, y1));
         case 2: return DM_SUB(0.0, dm_kernel_cos(y0, y1));

@@ -29,6 +29,9 @@ STATUS_NAMES = {
 
 MDP_GRIDWORLD = 0
 MDP_MOUNTAINCAR = 1
+MDP_GAUSSIAN_BOX = 2
+BOX_STATE_DOUBLES = 4
+BOX_ACTION_DOUBLES = 2
 MDP_PLUGIN_BASE = 100      # ids of MDP plugins registered at run time (mctsb200_mdp_register)
 PLUGIN_PARAM_BYTES = 256
 
@@ -66,6 +69,11 @@ class GridWorldParams(C.Structure):
 
 class MountainCarParams(C.Structure):
     _fields_ = [("discount", C.c_double), ("cost", C.c_double), ("jackpot", C.c_double)]
+
+
+class GaussianBoxParams(C.Structure):
+    _fields_ = [("discount", C.c_double), ("a_lo", C.c_double * BOX_ACTION_DOUBLES), ("a_hi", C.c_double * BOX_ACTION_DOUBLES),
+                ("var", C.c_double * 3), ("drift", C.c_double), ("cost", C.c_double)]
 
 
 class SolverCfg(C.Structure):
@@ -136,6 +144,7 @@ class TreeSizes(C.Structure):
         ("n_action_nodes", C.c_int64),
         ("n_transitions", C.c_int64),
         ("state_bytes", C.c_int64),
+        ("action_doubles", C.c_int64),
     ]
 
 
@@ -153,6 +162,7 @@ class TreeBuffers(C.Structure):
         ("trans_spnode", C.c_void_p),
         ("trans_r", C.c_void_p),
         ("trans_count", C.c_void_p),
+        ("a_label_vectors", C.c_void_p),
     ]
 
 
@@ -184,6 +194,7 @@ EXPORTED_SYMBOLS = (
     "mctsb200_tree_sizes_query",
     "mctsb200_tree_export",
     "mctsb200_clear_trees",
+    "mctsb200_root_action_vectors",
     "mctsb200_device_log",
     "mctsb200_device_cos",
     "mctsb200_device_philox",
@@ -226,6 +237,7 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.mctsb200_tree_sizes_query.argtypes = [vp, i64, P(TreeSizes)]
     lib.mctsb200_tree_export.argtypes = [vp, i64, P(TreeBuffers)]
     lib.mctsb200_clear_trees.argtypes = [vp]
+    lib.mctsb200_root_action_vectors.argtypes = [vp, i64, i64, vp]
     lib.mctsb200_device_log.argtypes = [vp, vp, i64, vp]
     lib.mctsb200_device_cos.argtypes = [vp, vp, i64, vp]
     lib.mctsb200_device_philox.argtypes = [vp, u64, u64, u32, u32, i32, vp]

@@ -274,6 +274,12 @@ class Context:
     def clear_trees(self) -> None:
         self._check(self.lib.mctsb200_clear_trees(self._h))
 
+    def root_action_vectors(self, first_root: int, n: int, action_doubles: int = abi.BOX_ACTION_DOUBLES) -> np.ndarray:
+        """Continuous action spaces: the action vectors best_sanode chose for roots [first_root, first_root + n) of the last plan call."""
+        out = np.zeros((int(n), int(action_doubles)), dtype=np.float64)
+        self._check(self.lib.mctsb200_root_action_vectors(self._h, int(first_root), int(n), _ptr(out)))
+        return out
+
     # -- numerical-contract probes --
     def device_log(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)
@@ -309,6 +315,8 @@ def export_into_numpy(call, sz: abi.TreeSizes, state_dtype, state_width: int) ->
         "trans_r": np.zeros(nt, dtype=np.float64),
         "trans_count": np.zeros(nt, dtype=np.int64),
     }
+    if sz.action_doubles > 0:  # a continuous action space: the labels are vectors (a_labels holds -1)
+        t["a_label_vectors"] = np.zeros((na, int(sz.action_doubles)), dtype=np.float64)
     b = abi.TreeBuffers(**{k: v.ctypes.data for k, v in t.items()})
     call(b)
     return t

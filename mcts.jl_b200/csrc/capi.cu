@@ -85,6 +85,8 @@ struct Storage {
     size_t row_bytes = 0, aux_bytes = 0, map_entry_bytes = 0;
     DevBuf hdr, rows, aux, trans, map, path;
     DevBuf plog;        // push-log arena of models with unbounded branching (search.cuh: kPushLog)
+    DevBuf anodes;      // action-node table of continuous-action trees (search.cuh: dpw_box_iteration)
+    DevBuf action_vec;  // the decisions' action vectors of the last plan call (continuous action spaces)
     DevBuf rows_fast;   // working table of uct_fast.cuh / dpw_fast.cuh (interleaved); `rows` receives the Row<M> table after the search
     DevBuf trans_fast;  // dpw_fast.cuh: per-slot transition multisets (interleaved)
     // the fast kernels' tables are converted to Row / Aux / TransRec only when a tree query needs them
@@ -107,10 +109,12 @@ struct mctsb200_ctx {
     GridWorldDev::Params gw_dev{};
     DevBuf gw_reward, gw_term, gw_fast;
     MountainCarDev::Params mc_dev{};
+    bool box_ok = false;
+    GaussianBoxDev::Params box_dev{};
 
     Storage st;
     DevBuf counters, log_tab, sqrtlog_tab, rsqrt_tab, nmin_state, init_q, init_n, value_tab, io_roots, io_action, io_bestq, io_status, sums;
-    DevBuf order, order_bins, policy_tab;
+    DevBuf order, order_bins, policy_tab, nmin_action_tab;
     double gw_reward_max = 0.0;
     bool gw_fast_det = false;
     // host hooks run between launches (mctsb200_set_progress_callback / mctsb200_set_timer)
@@ -247,6 +251,22 @@ struct MdpAccess<MountainCarDev> {
     static bool lockstep(const mctsb200_ctx*, const mctsb200_solver_cfg*) { return false; }
     static double reward_bound(const mctsb200_ctx*) { return NAN; }
 };
+template <>
+struct MdpAccess<GaussianBoxDev> {
+    static bool ready(const mctsb200_ctx* c) { return c->box_ok; }
+    static int mdp_id(const mctsb200_ctx*) { return MCTSB200_MDP_GAUSSIAN_BOX; }
+    static long long max_branch(const mctsb200_ctx*) { return 1LL << 30; }  // continuous noise
+    static const GaussianBoxDev::Params& params(const mctsb200_ctx* c) { return c->box_dev; }
+    static int dense_count(const mctsb200_ctx*) { return 0; }
+    static int32_t check_root(const mctsb200_ctx*, const GaussianBoxDev::AbiState& s) {
+        for (int i = 0; i < GaussianBoxDev::kStateDoubles; ++i)
+            if (!std::isfinite(s.v[i])) return -1;
+        return 0;
+    }
+    static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM; }  // RandomPolicy: rand(rng, actions(mdp, s))
+    static bool lockstep(const mctsb200_ctx*, const mctsb200_solver_cfg*) { return false; }
+    static double reward_bound(const mctsb200_ctx*) { return NAN; }
+};
 #ifndef MCTSB200_HOST_EMU
 // a plugin registered at run time (custom.cuh): hashed float64 states like MountainCar, parameters are the plugin's POD
 template <int SD, int A>
@@ -338,7 +358,7 @@ const mctsb200_solver_cfg* effective_cfg(const mctsb200_solver_cfg* cfg, mctsb20
     return &tmp;
 }
 
-int32_t validate_cfg(const mctsb200_solver_cfg* cfg, int n_actions, bool dense, bool (*policy_ok)(int)) {
+int32_t validate_cfg(const mctsb200_solver_cfg* cfg, int n_actions, bool dense, bool (*policy_ok)(int), bool box_actions = false) {
     if (!cfg) return fail(MCTSB200_ERR_INVALID_ARG, "cfg is NULL");
     if (cfg->struct_size != (int32_t)sizeof(mctsb200_solver_cfg))
         return fail(MCTSB200_ERR_INVALID_ARG, "solver_cfg.struct_size %d != %zu (ABI mismatch)", cfg->struct_size, sizeof(mctsb200_solver_cfg));
@@ -369,7 +389,7 @@ int32_t validate_cfg(const mctsb200_solver_cfg* cfg, int n_actions, bool dense, 
         const double v[4] = {cfg->k_action, cfg->alpha_action, cfg->k_state, cfg->alpha_state};
         for (double x : v)
             if (!(x >= 0.0) || !std::isfinite(x)) return fail(MCTSB200_ERR_UNSUPPORTED, "DPW k/alpha must be finite and >= 0");
-        if (cfg->enable_action_pw && !cfg->check_repeat_action)
+        if (cfg->enable_action_pw && !cfg->check_repeat_action && !box_actions)  // (action nodes of a continuous space have their own table)
             return fail(MCTSB200_ERR_UNSUPPORTED, "action widening with check_repeat_action=false (duplicate action nodes) is not supported on the device");
     }
     return MCTSB200_OK;
@@ -421,12 +441,21 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
         NP = 4 * pushes + 8 * std::min<long long>(NS * A, pushes);
         if (NP > 0x7fffffffLL) return fail(MCTSB200_ERR_CAPACITY, "push log would exceed 2^31 entries per tree");
     }
+    // continuous action spaces: one action node and one child-list entry per tree level at most, beside the transition pushes
+    long long NA = 0;
+    if constexpr (M::kActionDoubles > 0) {
+        const long long pushes = std::max<long long>(1, n_iter * std::max(cfg->depth, 1));
+        NA = pushes + 1;
+        NP = 4 * (2 * pushes) + 8 * std::min<long long>(NS + NA, 2 * pushes);
+        if (NA > 0x7fffffffLL || NP > 0x7fffffffLL) return fail(MCTSB200_ERR_CAPACITY, "action-node table would exceed 2^31 entries per tree");
+    }
     Geometry g;
     g.NS = (int)NS;
     g.NT = (int)std::max<long long>(NT, 1);
     g.MAP = (int)MAP;
     g.depth = std::max(cfg->depth, 1);
     g.NP = (int)NP;
+    g.NA = (int)NA;
 
     const size_t b_hdr = sizeof(TreeHeader) * (size_t)n_trees;
     const size_t b_rows = sizeof(Row<M>) * (size_t)NS * (size_t)n_trees;
@@ -437,21 +466,22 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     const size_t b_map = map_entry * (size_t)MAP * (size_t)n_trees;
     const size_t b_path = direct ? 0 : sizeof(PathEntry) * (size_t)g.depth * (size_t)n_trees;
     const size_t b_plog = sizeof(int) * (size_t)NP * (size_t)n_trees;
-    const size_t total = b_hdr + b_rows + b_aux + b_trans + b_map + b_path + b_plog;
+    const size_t b_anodes = sizeof(BoxANode) * (size_t)NA * (size_t)n_trees;
+    const size_t total = b_hdr + b_rows + b_aux + b_trans + b_map + b_path + b_plog + b_anodes;
 
     Storage& st = ctx->st;
     *reused = false;
     if (cfg->keep_tree && st.valid && st.keep && st.kind == cfg->kind && st.mdp_id == MdpAccess<M>::mdp_id(ctx) && st.n_trees == n_trees) {
-        if (st.direct != direct || st.geo.NS != g.NS || st.geo.NT != g.NT || st.geo.MAP != g.MAP || st.geo.NP != g.NP)
+        if (st.direct != direct || st.geo.NS != g.NS || st.geo.NT != g.NT || st.geo.MAP != g.MAP || st.geo.NP != g.NP || st.geo.NA != g.NA)
             return fail(MCTSB200_ERR_STATE, "the kept trees cannot be continued with this configuration (different kernel layout); call clear_tree first");
         CUDA_TRY(st.path.ensure(b_path));
         st.geo.depth = g.depth;
         *reused = true;
         return MCTSB200_OK;
     }
-    const size_t have = st.hdr.cap + st.rows.cap + st.aux.cap + st.trans.cap + st.map.cap + st.path.cap + st.plog.cap;
+    const size_t have = st.hdr.cap + st.rows.cap + st.aux.cap + st.trans.cap + st.map.cap + st.path.cap + st.plog.cap + st.anodes.cap;
     const bool grows = b_hdr > st.hdr.cap || b_rows > st.rows.cap || b_aux > st.aux.cap || b_trans > st.trans.cap || b_map > st.map.cap ||
-                       b_path > st.path.cap || b_plog > st.plog.cap;
+                       b_path > st.path.cap || b_plog > st.plog.cap || b_anodes > st.anodes.cap;
     if (grows) {  // (cudaMemGetInfo is slow: only ask when something has to be allocated)
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -467,6 +497,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     CUDA_TRY(st.map.ensure(b_map));
     CUDA_TRY(st.path.ensure(b_path));
     CUDA_TRY(st.plog.ensure(b_plog));
+    CUDA_TRY(st.anodes.ensure(b_anodes));
     st.kind = cfg->kind;
     st.direct = direct;
     st.keep = cfg->keep_tree != 0;
@@ -516,6 +547,7 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     d.enable_action_pw = cfg->enable_action_pw;
     d.enable_state_pw = cfg->enable_state_pw;
     d.check_repeat_state = cfg->check_repeat_state;
+    d.check_repeat_action = cfg->check_repeat_action;
     d.maintain_lookup = (cfg->keep_tree || cfg->check_repeat_state) ? 1 : 0;
 
     long long max_init_n = cfg->init_N;
@@ -588,6 +620,20 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
 
     if (cfg->kind == MCTSB200_KIND_DPW) {
         for (int len = 0; len < 16; ++len) d.nmin_action[len] = len <= A ? nmin_for(cfg->k_action, cfg->alpha_action, len, bound) : 0x7fffffff;
+        if constexpr (M::kActionDoubles > 0) {
+            // a continuous action space: a state node may own as many children as the widening rule allows (one more per visit at most)
+            std::vector<int> na;
+            const long long max_len = std::min<long long>(cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1, (1 << 20) - 2);
+            for (long long len = 0; len <= max_len; ++len) {
+                const int v = nmin_for(cfg->k_action, cfg->alpha_action, (int)len, bound);
+                na.push_back(v);
+                if (v == 0x7fffffff) break;
+            }
+            CUDA_TRY(ctx->nmin_action_tab.ensure(na.size() * sizeof(int)));
+            CUDA_TRY(cudaMemcpy(ctx->nmin_action_tab.p, na.data(), na.size() * sizeof(int), cudaMemcpyHostToDevice));
+            d.nmin_action_tab = (const int*)ctx->nmin_action_tab.p;
+            d.nmin_action_n = (int)na.size();
+        }
         std::vector<int> ns;
         // n_a_children never exceeds the model's branching (merged states) nor the pushes of the search
         const long long need_len = cfg->check_repeat_state ? std::min<long long>(MdpAccess<M>::max_branch(ctx), cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1)
@@ -816,6 +862,11 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.aux = (KIND == MCTSB200_KIND_DPW || (!M::kDense && MdpAccess<M>::max_branch(ctx) == 1 && env_enabled("MCTSB200_SUCC_CACHE"))) ? (Aux<M>*)st.aux.p : nullptr;
     args.trans = KIND == MCTSB200_KIND_DPW ? (TransRec*)st.trans.p : nullptr;
     args.plog = (KIND == MCTSB200_KIND_DPW && st.geo.NP > 0) ? (int*)st.plog.p : nullptr;
+    if constexpr (M::kActionDoubles > 0) {
+        args.anodes = (BoxANode*)st.anodes.p;
+        CUDA_TRY(st.action_vec.ensure(sizeof(double) * M::kActionDoubles * (size_t)n_trees));
+        args.action_vec_out = (double*)st.action_vec.p;
+    }
     args.map = st.map.p;
     args.path = (PathEntry*)st.path.p;
     args.roots = d_roots;
@@ -1026,7 +1077,15 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             ++launches;
         }
     }
-    if (!lazy) {
+    if constexpr (M::kActionDoubles > 0) {
+        const unsigned grid = (unsigned)((n_trees + 127) / 128);
+        auto kernel = decide_box_kernel<M>;
+        MCTSB200_LAUNCH(kernel, grid, 128, 0, ctx->stream, (const TreeHeader*)st.hdr.p, (const Aux<M>*)st.aux.p, (const BoxANode*)st.anodes.p,
+                        (const int*)st.plog.p, st.geo, n_trees, d_action, d_bestq, d_status, args.action_vec_out,
+                        (unsigned long long*)ctx->counters.p + CNT_STATUS_FLAGS);
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+    } else if (!lazy) {
         const unsigned grid = (unsigned)((n_trees + 127) / 128);
         auto kernel = decide_kernel<M>;
         MCTSB200_LAUNCH(kernel, grid, 128, 0, ctx->stream, (const TreeHeader*)st.hdr.p, (const Row<M>*)st.rows.p, st.geo.NS, n_trees, d_action, d_bestq,
@@ -1056,6 +1115,16 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     return MCTSB200_OK;
 }
 
+// what a continuous action space allows: DPW with action widening (vanilla UCT and DPW without widening enumerate actions(mdp, s),
+// src/vanilla.jl:297, src/dpw.jl:107), one rollout per leaf or a constant estimate, fresh trees
+int32_t check_box_cfg(const mctsb200_solver_cfg* cfg) {
+    if (cfg->kind != MCTSB200_KIND_DPW) return fail(MCTSB200_ERR_UNSUPPORTED, "a continuous action space needs DPWSolver (vanilla UCT enumerates actions(mdp, s))");
+    if (!cfg->enable_action_pw) return fail(MCTSB200_ERR_UNSUPPORTED, "a continuous action space needs enable_action_pw (its actions cannot be enumerated)");
+    if (cfg->keep_tree) return fail(MCTSB200_ERR_UNSUPPORTED, "keep_tree is not available for continuous action spaces");
+    if (cfg->rollouts_per_leaf != 1) return fail(MCTSB200_ERR_UNSUPPORTED, "continuous action spaces run one rollout per leaf");
+    return MCTSB200_OK;
+}
+
 template <class M>
 int32_t plan_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const void* roots, bool roots_on_device, long long n_roots,
                       size_t state_bytes, long long base, int* action_out, double* bestq_out, int* status_out, bool out_on_device,
@@ -1065,7 +1134,7 @@ int32_t plan_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const v
     if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
     mctsb200_solver_cfg cfg_capped;
     cfg = effective_cfg(cfg, cfg_capped);
-    int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok);
+    int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok, M::kActionDoubles > 0);
     if (rc) return rc;
     if (state_bytes != sizeof(Abi)) return fail(MCTSB200_ERR_INVALID_ARG, "state_bytes %zu != %zu", state_bytes, sizeof(Abi));
     if (n_roots <= 0 || !roots) return fail(MCTSB200_ERR_INVALID_ARG, "need at least one root state");
@@ -1097,8 +1166,13 @@ int32_t plan_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const v
         d_status = (int*)ctx->io_status.p;
     }
     unsigned flags = 0;  // OR of the trees' status, reduced on the device: errors surface even without a status buffer
-    if (cfg->kind == MCTSB200_KIND_UCT) rc = run_search<M, MCTSB200_KIND_UCT>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats, &flags);
-    else rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats, &flags);
+    if constexpr (M::kActionDoubles > 0) {
+        if (int32_t e = check_box_cfg(cfg)) return e;
+        rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats, &flags);
+    } else {
+        if (cfg->kind == MCTSB200_KIND_UCT) rc = run_search<M, MCTSB200_KIND_UCT>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats, &flags);
+        else rc = run_search<M, MCTSB200_KIND_DPW>(ctx, cfg, d_roots, n_roots, 1, base, d_action, d_bestq, d_status, stats, &flags);
+    }
     if (rc) return rc;
     int32_t worst = (flags & 2u) ? MCTSB200_ERR_CAPACITY : (flags & 1u) ? MCTSB200_ERR_TERMINAL_ROOT : MCTSB200_OK;
     if (!out_on_device) {
@@ -1125,6 +1199,9 @@ int32_t root_parallel_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg
                                mctsb200_plan_stats* stats) {
     using Abi = typename M::AbiState;
     const auto t0 = std::chrono::steady_clock::now();
+    if constexpr (M::kActionDoubles > 0) {
+        return fail(MCTSB200_ERR_UNSUPPORTED, "root-parallel sums are defined per action of a finite action set");
+    } else {
     if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
     mctsb200_solver_cfg cfg_capped;
     cfg = effective_cfg(cfg, cfg_capped);
@@ -1185,6 +1262,7 @@ int32_t root_parallel_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg
         stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     return MCTSB200_OK;
+    }
 }
 
 // ---- episode driver ------------------------------------------------------------------------------
@@ -1194,6 +1272,9 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
                           void* final_states_out, mctsb200_plan_stats* stats) {
     using Abi = typename M::AbiState;
     const auto t0 = std::chrono::steady_clock::now();
+    if constexpr (M::kActionDoubles > 0) {
+        return fail(MCTSB200_ERR_UNSUPPORTED, "the device episode driver steps environments with action indices: not available for continuous action spaces");
+    } else {
     if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
     mctsb200_solver_cfg cfg_capped;
     cfg = effective_cfg(cfg, cfg_capped);
@@ -1296,6 +1377,7 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
         *stats = tot;
     }
     return MCTSB200_OK;
+    }
 }
 
 // ---- tree export --------------------------------------------------------------------------------
@@ -1346,6 +1428,61 @@ int32_t fetch_tree(mctsb200_ctx* ctx, long long i, HostTree<M>& t) {
     return MCTSB200_OK;
 }
 
+// A continuous-action tree in the reference's DPWTree vectors: children lists from the arena, action nodes in id order with
+// their vector labels, transitions[sanode] as distinct records with multiplicities (oldest first).
+template <class M>
+int32_t box_tree_export(mctsb200_ctx* ctx, long long i, const mctsb200_tree_buffers* b) {
+    Storage& st = ctx->st;
+    HostTree<M> t;
+    int32_t rc = fetch_tree<M>(ctx, i, t);
+    if (rc) return rc;
+    const int ns = t.h.n_state, na = t.h.n_action;
+    std::vector<BoxANode> an((size_t)na);
+    std::vector<int> plog((size_t)t.h.n_plog);
+    if (na) CUDA_TRY(cudaMemcpy(an.data(), (const BoxANode*)st.anodes.p + i * st.geo.NA, sizeof(BoxANode) * (size_t)na, cudaMemcpyDeviceToHost));
+    if (t.h.n_plog) CUDA_TRY(cudaMemcpy(plog.data(), (const int*)st.plog.p + i * st.geo.NP, sizeof(int) * plog.size(), cudaMemcpyDeviceToHost));
+    const auto& P = MdpAccess<M>::params(ctx);
+    using Abi = typename M::AbiState;
+    int64_t child_pos = 0;
+    if (b->child_offsets) b->child_offsets[0] = 0;
+    for (int s = 0; s < ns; ++s) {
+        if (b->total_n) b->total_n[s] = t.rows[(size_t)s].total_n;
+        if (b->s_labels) {
+            const Abi lab = M::store(P, M::state_of(P, t.rows[(size_t)s].key));
+            std::memcpy((char*)b->s_labels + sizeof(Abi) * (size_t)s, &lab, sizeof lab);
+        }
+        const Aux<M>& ax = t.aux[(size_t)s];
+        for (int j = 0; j < ax.nac[0]; ++j) {
+            if (b->child_ids) b->child_ids[child_pos] = (int64_t)plog[(size_t)(ax.pbase[0] + j)] + 1;
+            ++child_pos;
+        }
+        if (b->child_offsets) b->child_offsets[s + 1] = child_pos;
+    }
+    int64_t pos = 0;
+    if (b->trans_offsets) b->trans_offsets[0] = 0;
+    std::vector<int> chain;
+    for (int id = 0; id < na; ++id) {
+        const BoxANode& c = an[(size_t)id];
+        if (b->n) b->n[id] = c.n;
+        if (b->q) b->q[id] = c.q;
+        if (b->a_labels) b->a_labels[id] = -1;
+        if (b->a_label_vectors)
+            for (int k = 0; k < M::kActionDoubles; ++k) b->a_label_vectors[(size_t)id * M::kActionDoubles + k] = c.a[k];
+        if (b->n_a_children) b->n_a_children[id] = c.nac;
+        chain.clear();
+        for (int rec = c.thead; rec >= 0; rec = t.trans[(size_t)rec].next) chain.push_back(rec);
+        for (auto it = chain.rbegin(); it != chain.rend(); ++it) {
+            const TransRec& tr = t.trans[(size_t)*it];
+            if (b->trans_spnode) b->trans_spnode[pos] = tr.sp + 1;
+            if (b->trans_r) b->trans_r[pos] = tr.r;
+            if (b->trans_count) b->trans_count[pos] = tr.count;
+            ++pos;
+        }
+        if (b->trans_offsets) b->trans_offsets[id + 1] = pos;
+    }
+    return MCTSB200_OK;
+}
+
 template <class M>
 int32_t tree_sizes_impl(mctsb200_ctx* ctx, long long i, mctsb200_tree_sizes* out) {
     TreeHeader h;
@@ -1355,11 +1492,13 @@ int32_t tree_sizes_impl(mctsb200_ctx* ctx, long long i, mctsb200_tree_sizes* out
     out->n_action_nodes = h.n_action;
     out->n_transitions = ctx->st.kind == MCTSB200_KIND_DPW ? h.n_trans : 0;
     out->state_bytes = (int64_t)sizeof(typename M::AbiState);
+    out->action_doubles = M::kActionDoubles;
     return MCTSB200_OK;
 }
 
 template <class M>
 int32_t tree_export_impl(mctsb200_ctx* ctx, long long i, const mctsb200_tree_buffers* b) {
+    if constexpr (M::kActionDoubles > 0) return box_tree_export<M>(ctx, i, b);
     constexpr int A = M::kActions;
     HostTree<M> t;
     int32_t rc = fetch_tree<M>(ctx, i, t);
@@ -1430,16 +1569,35 @@ int32_t root_stats_impl(mctsb200_ctx* ctx, long long i, int32_t* n_children, int
         if (total_n) *total_n = 0;
         return MCTSB200_OK;
     }
-    Row<M> rw;
-    CUDA_TRY(cudaMemcpy(&rw, (const Row<M>*)ctx->st.rows.p + i * ctx->st.geo.NS + h.root, sizeof rw, cudaMemcpyDeviceToHost));
-    if (n_children) *n_children = rw.nchild();
-    if (total_n) *total_n = rw.total_n;
-    for (int j = 0; j < rw.nchild(); ++j) {
-        if (action_idx) action_idx[j] = rw.alabel(j);
-        if (n) n[j] = rw.n[j];
-        if (q) q[j] = rw.q[j];
+    if constexpr (M::kActionDoubles > 0) {  // children listed in the arena; action_idx = position among the root's children
+        Row<M> rw0;
+        Aux<M> ax;
+        CUDA_TRY(cudaMemcpy(&rw0, (const Row<M>*)ctx->st.rows.p + i * ctx->st.geo.NS + h.root, sizeof rw0, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(&ax, (const Aux<M>*)ctx->st.aux.p + i * ctx->st.geo.NS + h.root, sizeof ax, cudaMemcpyDeviceToHost));
+        if (n_children) *n_children = ax.nac[0];
+        if (total_n) *total_n = rw0.total_n;
+        std::vector<int> kids((size_t)ax.nac[0]);
+        if (ax.nac[0]) CUDA_TRY(cudaMemcpy(kids.data(), (const int*)ctx->st.plog.p + i * ctx->st.geo.NP + ax.pbase[0], sizeof(int) * kids.size(), cudaMemcpyDeviceToHost));
+        for (int j = 0; j < ax.nac[0]; ++j) {
+            BoxANode c;
+            CUDA_TRY(cudaMemcpy(&c, (const BoxANode*)ctx->st.anodes.p + i * ctx->st.geo.NA + kids[(size_t)j], sizeof c, cudaMemcpyDeviceToHost));
+            if (action_idx) action_idx[j] = j;
+            if (n) n[j] = c.n;
+            if (q) q[j] = c.q;
+        }
+        return MCTSB200_OK;
+    } else {
+        Row<M> rw;
+        CUDA_TRY(cudaMemcpy(&rw, (const Row<M>*)ctx->st.rows.p + i * ctx->st.geo.NS + h.root, sizeof rw, cudaMemcpyDeviceToHost));
+        if (n_children) *n_children = rw.nchild();
+        if (total_n) *total_n = rw.total_n;
+        for (int j = 0; j < rw.nchild(); ++j) {
+            if (action_idx) action_idx[j] = rw.alabel(j);
+            if (n) n[j] = rw.n[j];
+            if (q) q[j] = rw.q[j];
+        }
+        return MCTSB200_OK;
     }
-    return MCTSB200_OK;
 }
 
 __global__ void probe_log_kernel(const double* x, long long n, double* out) {
@@ -1649,6 +1807,7 @@ bool plugin_shape_ok(int sd, int a) { return (sd == 2 || sd == 4) && a >= 2 && a
     do {                                                                        \
         if ((mdp_id) == MCTSB200_MDP_GRIDWORLD) return CALL(GridWorldDev);      \
         if ((mdp_id) == MCTSB200_MDP_MOUNTAINCAR) return CALL(MountainCarDev);  \
+        if ((mdp_id) == MCTSB200_MDP_GAUSSIAN_BOX) return CALL(GaussianBoxDev); \
         MCTSB200_FOR_PLUGIN(ctx, mdp_id, CALL)                                  \
         return fail(MCTSB200_ERR_INVALID_ARG, "unknown mdp_id %d", (int)(mdp_id)); \
     } while (0)
@@ -1709,7 +1868,7 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     }
 #endif
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->st.plog, &c->counters,
+    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->st.plog, &c->st.anodes, &c->st.action_vec, &c->nmin_action_tab, &c->counters,
                       &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
                       &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->gw_fast,
                       &c->ep_states, &c->ep_disc, &c->ep_ret, &c->ep_steps, &c->ep_active, &c->ep_count};
@@ -1830,6 +1989,7 @@ int32_t mctsb200_mdp_lookup(const char* name, int32_t* mdp_id) {
     if (!name || !mdp_id) return fail(MCTSB200_ERR_INVALID_ARG, "NULL argument");
     if (!std::strcmp(name, "SimpleGridWorld")) *mdp_id = MCTSB200_MDP_GRIDWORLD;
     else if (!std::strcmp(name, "MountainCar")) *mdp_id = MCTSB200_MDP_MOUNTAINCAR;
+    else if (!std::strcmp(name, "GaussianBox")) *mdp_id = MCTSB200_MDP_GAUSSIAN_BOX;
     else {
 #ifndef MCTSB200_HOST_EMU
         const int idx = mctsb200_rt::lookup_plugin(name);
@@ -1890,6 +2050,9 @@ int32_t mctsb200_mdp_info(int32_t mdp_id, int32_t* n_actions, int64_t* state_byt
     } else if (mdp_id == MCTSB200_MDP_MOUNTAINCAR) {
         if (n_actions) *n_actions = MountainCarDev::kActions;
         if (state_bytes) *state_bytes = sizeof(MountainCarDev::AbiState);
+    } else if (mdp_id == MCTSB200_MDP_GAUSSIAN_BOX) {
+        if (n_actions) *n_actions = 0;  // a continuous action space: actions are vectors (mctsb200_root_action_vectors)
+        if (state_bytes) *state_bytes = sizeof(GaussianBoxDev::AbiState);
     } else {
 #ifndef MCTSB200_HOST_EMU
         if (const mctsb200_rt::PluginInfo* pi = mctsb200_rt::plugin_info(mdp_id - MCTSB200_MDP_PLUGIN_BASE)) {
@@ -2012,6 +2175,27 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
         ctx->mc_dev.cost = p.cost;
         ctx->mc_dev.jackpot = p.jackpot;
         ctx->mc_ok = true;
+        ctx->st.valid = false;
+        return MCTSB200_OK;
+    }
+    if (mdp_id == MCTSB200_MDP_GAUSSIAN_BOX) {
+        if (bytes != sizeof(mctsb200_gaussian_box_params)) return fail(MCTSB200_ERR_INVALID_ARG, "gaussian box params: %zu bytes, expected %zu", bytes, sizeof(mctsb200_gaussian_box_params));
+        const mctsb200_gaussian_box_params& p = *(const mctsb200_gaussian_box_params*)pod;
+        if (!(p.discount >= 0.0 && p.discount <= 1.0)) return fail(MCTSB200_ERR_INVALID_ARG, "discount must be in [0,1]");
+        ctx->box_dev.discount = p.discount;
+        for (int i = 0; i < MCTSB200_BOX_ACTION_DOUBLES; ++i) {
+            if (!(p.a_lo[i] <= p.a_hi[i]) || !std::isfinite(p.a_lo[i]) || !std::isfinite(p.a_hi[i])) return fail(MCTSB200_ERR_INVALID_ARG, "action box bounds must be finite, lo <= hi");
+            ctx->box_dev.a_lo[i] = p.a_lo[i];
+            ctx->box_dev.a_hi[i] = p.a_hi[i];
+        }
+        for (int i = 0; i < 3; ++i) {
+            if (!(p.var[i] >= 0.0) || !std::isfinite(p.var[i])) return fail(MCTSB200_ERR_INVALID_ARG, "variances must be finite and >= 0");
+            ctx->box_dev.sd[i] = std::sqrt(p.var[i]);
+        }
+        if (!std::isfinite(p.drift) || !std::isfinite(p.cost)) return fail(MCTSB200_ERR_INVALID_ARG, "drift and cost must be finite");
+        ctx->box_dev.drift = p.drift;
+        ctx->box_dev.cost = p.cost;
+        ctx->box_ok = true;
         ctx->st.valid = false;
         return MCTSB200_OK;
     }
@@ -2156,6 +2340,27 @@ int32_t mctsb200_tree_export(mctsb200_ctx* ctx, int64_t root_i, const mctsb200_t
 #define MCTSB200_CALL(M) tree_export_impl<M>(ctx, root_i, buffers)
     MCTSB200_FOR_MDP(ctx, ctx->st.mdp_id, MCTSB200_CALL);
 #undef MCTSB200_CALL
+}
+
+int32_t mctsb200_root_action_vectors(mctsb200_ctx* ctx, int64_t first_root, int64_t n, double* out) {
+    if (!ctx || !out || n < 0 || first_root < 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad arguments");
+    if (!ctx->kids.empty()) {  // roots are sharded in contiguous blocks: ask each device for its part
+        for (int64_t i = 0; i < n;) {
+            mctsb200_ctx* kid = nullptr;
+            long long local = 0;
+            if (int32_t e = group_locate(ctx, first_root + i, &kid, &local)) return e;
+            const long long m = std::min<long long>(n - i, kid->st.n_trees - local);
+            if (int32_t e = mctsb200_root_action_vectors(kid, local, m, out + i * MCTSB200_BOX_ACTION_DOUBLES)) return e;
+            i += m;
+        }
+        return MCTSB200_OK;
+    }
+    if (!ctx->st.valid) return fail(MCTSB200_ERR_STATE, "no tree: call mctsb200_plan first");
+    if (ctx->st.mdp_id != MCTSB200_MDP_GAUSSIAN_BOX) return fail(MCTSB200_ERR_STATE, "the last plan call was not over a continuous action space");
+    if (first_root + n > ctx->st.n_trees) return fail(MCTSB200_ERR_INVALID_ARG, "roots [%lld, %lld) out of range", (long long)first_root, (long long)(first_root + n));
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n) CUDA_TRY(cudaMemcpy(out, (const double*)ctx->st.action_vec.p + first_root * MCTSB200_BOX_ACTION_DOUBLES, sizeof(double) * MCTSB200_BOX_ACTION_DOUBLES * (size_t)n, cudaMemcpyDeviceToHost));
+    return MCTSB200_OK;
 }
 
 int32_t mctsb200_clear_trees(mctsb200_ctx* ctx) {

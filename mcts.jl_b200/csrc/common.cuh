@@ -161,6 +161,22 @@ struct __align__(32) Aux {
     int pcap[M::kActions];
 };
 
+// One action node of a continuous-action DPW tree (models with kActionDoubles > 0, e.g. GaussianBoxDev): a state node there has
+// up to k_action * N^alpha_action children, so the action nodes live in a table of their own, ids in insertion order (the
+// reference's action-node ids), and a state node lists its children in the tree's int arena (plog: Aux::pbase / pcap / nac of slot 0).
+// 64 B = two sectors; (q, n) lead so that the selection scan reads one 16-byte word per child.
+struct __align__(32) BoxANode {
+    double q;
+    int n;
+    int nac;    // n_a_children
+    int thead;  // newest transition record, -1 = none
+    int tpush;  // length of transitions[sanode]
+    int pbase;  // the push-ordered transitions[sanode] vector (record ids) in the arena: [pbase, pbase + pcap)
+    int pcap;
+    double a[4];  // the action label (kActionDoubles <= 4 coordinates)
+};
+static_assert(sizeof(BoxANode) == 64, "one action node = two sectors");
+
 // geometry of the tables of one plan call
 struct Geometry {
     int NS;         // state-node capacity per tree
@@ -168,6 +184,7 @@ struct Geometry {
     int MAP;        // map entries per tree (dense: n_dense u16; hash: power-of-two HashSlots)
     int depth;      // path entries per tree
     int NP;         // push-log arena entries per tree (0 unless the model has unbounded branching)
+    int NA;         // action-node capacity per tree (continuous action spaces only, else 0)
 };
 
 enum CounterId {
@@ -198,6 +215,9 @@ struct DevCfg {
     int rsqrt_tab_n;
     int nmin_state_n;
     int nmin_action[16];         // min total_n for which a state node with len children may widen
+    const int* nmin_action_tab;  // device, continuous action spaces: the same for len < nmin_action_n (a node may have many children)
+    int nmin_action_n;
+    int check_repeat_action;
     int depth;
     int K;
     int init_N;
@@ -222,6 +242,8 @@ struct KernelArgs {
     Aux<M>* aux;
     TransRec* trans;
     int* plog;                          // push-log arena, [n_trees][NP] (null unless the model has unbounded branching)
+    BoxANode* anodes;                   // action nodes of continuous-action trees, [n_trees][NA] (else null)
+    double* action_vec_out;             // continuous action spaces: the decision's action vector per tree (may be null)
     void* map;
     PathEntry* path;
     const typename M::AbiState* roots;  // device

@@ -45,6 +45,7 @@ struct CustomDev {
     static constexpr bool kFast = false;
     static constexpr bool kCustom = true;
     static constexpr int kStateDoubles = SD;
+    static constexpr int kActionDoubles = 0;
 
     struct AbiState { double v[SD]; };
     typedef AbiState State;

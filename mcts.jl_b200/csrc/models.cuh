@@ -29,6 +29,7 @@ struct GridWorldDev {
     static constexpr int kMaxBranch = 5;
     static constexpr int kMdpId = MCTSB200_MDP_GRIDWORLD;
     static constexpr bool kCustom = false;  // (custom.cuh: plugins registered at run time)
+    static constexpr int kActionDoubles = 0;  // actions are indices into actions(mdp) (> 0: vectors of a continuous action space)
 
     struct AbiState { long long x, y; };
     // On the device a state is its dense cell index: (x-1) + (y-1)*nx, and nx*ny for the terminal state (-1,-1).
@@ -240,6 +241,7 @@ struct MountainCarDev {
     static constexpr int kMdpId = MCTSB200_MDP_MOUNTAINCAR;
     static constexpr bool kCustom = false;
     static constexpr bool kFast = false;
+    static constexpr int kActionDoubles = 0;
 
     struct AbiState { double x, v; };
     typedef AbiState State;
@@ -290,6 +292,89 @@ struct MountainCarDev {
             case MCTSB200_POLICY_MC_ENERGY: return s.v < 0.0 ? 0 : 2;
             default: return 0;
         }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// GaussianBox: continuous states AND continuous actions (include/mctsb200.h: mctsb200_gaussian_box_params; the MDP of the
+// reference's test/discussion_514.jl with an optional drift and quadratic cost). Only DPW plans for it.
+// ---------------------------------------------------------------------------------------------
+struct GaussianBoxDev {
+    static constexpr int kActions = 1;   // (no finite action set: Row / Aux keep one unused slot)
+    static constexpr bool kDense = false;
+    static constexpr int kMaxBranch = 0;  // continuous noise: transitions[sanode] is kept as the push-ordered vector
+    static constexpr int kMdpId = MCTSB200_MDP_GAUSSIAN_BOX;
+    static constexpr bool kCustom = false;
+    static constexpr bool kFast = false;
+    static constexpr int kActionDoubles = MCTSB200_BOX_ACTION_DOUBLES;
+    static constexpr int kStateDoubles = MCTSB200_BOX_STATE_DOUBLES;
+
+    struct AbiState { double v[kStateDoubles]; };
+    typedef AbiState State;
+    typedef AbiState Key;
+    struct Action { double v[kActionDoubles]; };
+    struct Params {
+        double discount;
+        double a_lo[kActionDoubles], a_hi[kActionDoubles];
+        double sd[3];  // sqrt(var), rounded once on the host (the oracle does the same)
+        double drift, cost;
+    };
+
+    __device__ __forceinline__ static State load(const Params&, const AbiState& a) { return a; }
+    __host__ __device__ __forceinline__ static AbiState store(const Params&, const State& s) { return s; }
+    __device__ __forceinline__ static bool is_terminal(const Params&, const State&) { return false; }
+    __device__ __forceinline__ static double discount(const Params& p) { return p.discount; }
+    __device__ __forceinline__ static int dense_index(const Params&, const State&) { return -1; }
+    __device__ __forceinline__ static Key key_of(const Params&, const State& s) { return s; }
+    __host__ __device__ __forceinline__ static State state_of(const Params&, const Key& k) { return k; }
+    __device__ __forceinline__ static bool key_equal(const Key& a, const Key& b) {
+        bool eq = true;
+#pragma unroll
+        for (int i = 0; i < kStateDoubles; ++i) eq = eq && __double_as_longlong(a.v[i]) == __double_as_longlong(b.v[i]);
+        return eq;
+    }
+    __device__ __forceinline__ static uint32_t hash(const State& s) {
+        uint64_t h = 0x7F4A7C159E3779B9ull;
+#pragma unroll
+        for (int i = 0; i < kStateDoubles; ++i) {
+            h ^= (uint64_t)__double_as_longlong(s.v[i]) * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+            h ^= h >> 29;
+        }
+        h ^= h >> 33;
+        h *= 0xff51afd7ed558ccdull;
+        h ^= h >> 33;
+        return (uint32_t)h;
+    }
+    // rand(rng, actions(mdp, s)) on a Box: one uniform draw per coordinate (RandomActionGenerator, src/action_gen.jl:11-13)
+    __device__ __forceinline__ static void next_action(const Params& p, const State&, Stream& rng, Action& a) {
+#pragma unroll
+        for (int i = 0; i < kActionDoubles; ++i) a.v[i] = DM_ADD(p.a_lo[i], DM_MUL(DM_SUB(p.a_hi[i], p.a_lo[i]), rng.uniform01()));
+    }
+    // sp = s + drift * a + sd * z, z ~ N(0, I): two Box-Muller pairs from four words (z0, z1 from the first two, z2 from the others)
+    __device__ __forceinline__ static void gen(const Params& p, const State& s, const Action& a, Stream& rng, State& sp, double& r) {
+        const double two_pi = 6.283185307179586;
+        double z[3];
+        {
+            const double u1 = DM_MUL(DM_ADD((double)rng.next(), 1.0), 1.0 / 4294967296.0), u2 = rng.uniform01();
+            const double rad = DM_SQRT(DM_MUL(-2.0, det_log(u1))), ang = DM_MUL(two_pi, u2);
+            z[0] = DM_MUL(rad, det_cos(ang));
+            z[1] = DM_MUL(rad, det_sin(ang));
+        }
+        {
+            const double u1 = DM_MUL(DM_ADD((double)rng.next(), 1.0), 1.0 / 4294967296.0), u2 = rng.uniform01();
+            z[2] = DM_MUL(DM_SQRT(DM_MUL(-2.0, det_log(u1))), det_cos(DM_MUL(two_pi, u2)));
+        }
+        double ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double x = s.v[i];
+            if (i < kActionDoubles) x = DM_ADD(x, DM_MUL(p.drift, a.v[i]));
+            x = DM_ADD(x, DM_MUL(p.sd[i], z[i]));
+            sp.v[i] = x;
+            ss = DM_ADD(ss, DM_MUL(x, x));
+        }
+        sp.v[3] = s.v[3];
+        r = DM_SUB(0.0, DM_MUL(p.cost, ss));
     }
 };
 

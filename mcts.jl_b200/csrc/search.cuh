@@ -25,7 +25,16 @@
 namespace mctsb200 {
 
 constexpr int kBlockThreads = 128;
-constexpr int kTileTab = 1024;  // entries of c*sqrt(log N) and 1/sqrt(n) a block of the tile kernel stages in shared memory
+// Two ideas that looked free and measured slower on B200 (config 4, profiles/r2e_*: 465 ms without either, 477 ms with the widening
+// thresholds hoisted into registers, 520 ms with 1024-entry UCB table heads in shared memory -- the 16 KB per block come out of the
+// L1 that serves the node tables at an 86 % hit rate); kept behind switches for the record.
+#ifndef MCTSB200_TILE_TAB
+#define MCTSB200_TILE_TAB 0
+#endif
+#ifndef MCTSB200_HOIST_NMIN
+#define MCTSB200_HOIST_NMIN 0
+#endif
+constexpr int kTileTab = MCTSB200_TILE_TAB;  // entries of c*sqrt(log N) and 1/sqrt(n) a block of the tile kernel stages in shared memory (0 = none)
 
 template <int G>
 struct Tile {
@@ -173,6 +182,7 @@ struct Search {
     // header mirror (registers, tile-uniform)
     int n_state, n_action, n_trans, n_plog, status;
     int* plog;  // this tree's push-log arena
+    BoxANode* anodes;  // this tree's action nodes (continuous action spaces)
     // per-lane work counters (per-tree counts fit 32 bits: n_iterations*depth <= 2e9 is validated on the host;
     // rollout steps can exceed that and are kept in 64 bits)
     unsigned cnt[CNT_COUNT];
@@ -198,6 +208,7 @@ struct Search {
         aux = args.aux ? args.aux + tree * args.geo.NS : nullptr;
         trans = args.trans ? args.trans + tree * args.geo.NT : nullptr;
         plog = args.plog ? args.plog + tree * args.geo.NP : nullptr;
+        anodes = args.anodes ? args.anodes + tree * args.geo.NA : nullptr;
         n_plog = 0;
         path = args.path + tree * args.geo.depth;
         path_stride = 1;
@@ -208,10 +219,12 @@ struct Search {
         for (int i = 0; i < CNT_COUNT; ++i) cnt[i] = 0;
         rollout_steps = 0;
         s_cs = s_rs = nullptr;
+#if MCTSB200_HOIST_NMIN
 #pragma unroll
         for (int i = 0; i < 4; ++i) nmin_s[i] = (args.cfg.nmin_state && i < args.cfg.nmin_state_n) ? __ldg(args.cfg.nmin_state + i) : 0x7fffffff;
 #pragma unroll
         for (int i = 0; i <= A; ++i) nmin_a[i] = args.cfg.nmin_action[i];
+#endif
     }
 
     __device__ __forceinline__ bool lead() const { return tile.lane == 0; }
@@ -291,10 +304,16 @@ struct Search {
         double disc = 1.0, r_total = 0.0;
         int step = 1;
         while (disc > eps && !M::is_terminal(a.mdp, s) && step <= max_steps) {
-            const int act = M::policy_action(a.mdp, a.cfg.policy, a.cfg.pparam, s, rs);
             State sp;
             double r;
-            M::gen(a.mdp, s, act, rs, sp, r);
+            if constexpr (M::kActionDoubles > 0) {  // RandomPolicy on a continuous action space: rand(rng, actions(mdp, s))
+                typename M::Action act;
+                M::next_action(a.mdp, s, rs, act);
+                M::gen(a.mdp, s, act, rs, sp, r);
+            } else {
+                const int act = M::policy_action(a.mdp, a.cfg.policy, a.cfg.pparam, s, rs);
+                M::gen(a.mdp, s, act, rs, sp, r);
+            }
             r_total = DM_ADD(r_total, DM_MUL(disc, r));
             s = sp;
             disc = DM_MUL(disc, gamma);
@@ -725,6 +744,11 @@ struct Search {
             rw->key = M::key_of(a.mdp, s);
             if (maintain_lookup) map_insert(s, id);
             cnt[CNT_STATE_INSERTS] += 1;
+            if constexpr (M::kActionDoubles > 0) {  // the (empty) children list of a continuous-action state node
+                aux[id].nac[0] = 0;
+                aux[id].pbase[0] = 0;
+                aux[id].pcap[0] = 0;
+            }
         }
         n_state = id + 1;
         return id;
@@ -809,7 +833,11 @@ struct Search {
             // ---- action progressive widening (src/dpw.jl:94-114) ----
             if (a.cfg.enable_action_pw) {
                 // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action[len]
+#if MCTSB200_HOIST_NMIN
                 if (R.total_n >= pick_n(nmin_a, nchild)) {
+#else
+                if (R.total_n >= a.cfg.nmin_action[nchild]) {
+#endif
                     const int act = rng.uniform_int(A);  // next_action(::RandomActionGenerator)
                     bool present = false;
                     const uint32_t pk = R.packed;
@@ -842,7 +870,11 @@ struct Search {
             bool widen = nac == 0;
             if (!widen && a.cfg.enable_state_pw) {
                 // n_a_children <= k_state * n^alpha_state  <=>  n >= nmin_state[n_a_children]
+#if MCTSB200_HOIST_NMIN
                 const int need = nac < 4 ? pick_n(nmin_s, nac) : (nac < a.cfg.nmin_state_n ? __ldg(a.cfg.nmin_state + nac) : 0x7fffffff);
+#else
+                const int need = nac < a.cfg.nmin_state_n ? __ldg(a.cfg.nmin_state + nac) : 0x7fffffff;
+#endif
                 widen = pick(R.n, slot) >= need;
             }
             if (M::kMaxBranch == 1 && widen && nac == 1 && a.cfg.check_repeat_state) {
@@ -965,6 +997,239 @@ struct Search {
         PT_ADD(2, t3 - t2);
         if (lead()) cnt[CNT_SIMULATIONS] += 1;
     }
+
+    // =====================================================================================
+    // DPW over a continuous action space (models with kActionDoubles > 0; test/discussion_514.jl)
+    // =====================================================================================
+    // A growable int vector in the tree's arena -- the children of a state node, or transitions[sanode] -- receives `value` at
+    // position `len`: a full (or still empty) vector moves to a chunk twice as large at the end of the arena. base / cap are
+    // the caller's register copies; the leader writes the new location through g_base / g_cap. false = the arena is full.
+    __device__ __forceinline__ bool vec_push(int& base, int& cap, int len, int value, int* g_base, int* g_cap) {
+        if (len == cap) {
+            const int ncap = cap ? 2 * cap : 4;
+            if (n_plog + ncap > a.geo.NP) {
+                status = MCTSB200_ERR_CAPACITY;
+                return false;
+            }
+            const int nbase = n_plog;
+            for (int i = tile.lane; i < len; i += G) plog[nbase + i] = plog[base + i];
+            if (lead()) {
+                *g_base = nbase;
+                *g_cap = ncap;
+            }
+            n_plog += ncap;
+            base = nbase;
+            cap = ncap;
+        }
+        if (lead()) plog[base + len] = value;
+        tile.sync();
+        return true;
+    }
+
+    // one iteration of src/dpw.jl:48-56 when actions(mdp, s) is a continuum: a state node owns up to k_action * N^alpha_action
+    // action nodes (BoxANode table, children listed in the arena), next_action draws a vector, and the lanes of the tile share
+    // the scans over a node's children (repeat check, UCB arg-max) -- the place where a wide tile pays.
+    __device__ __forceinline__ void dpw_box_iteration(int root, uint32_t it) {
+        using Act = typename M::Action;
+        constexpr int AD = M::kActionDoubles;
+        BoxANode* const an = anodes;
+        Stream rng;
+        rng.init(a.cfg.seed, tree_index, it, 0u);
+        int node = root, d = a.cfg.depth, top = 0;
+        State s;
+        int leaf = 0;  // 0: terminal (value 0.0), 1: estimate_value(s, d), 2: table overflow
+        for (;;) {
+            Row<M>* rw = rows + node;
+            Aux<M>* ax = aux + node;
+            Row<M> R;
+            Aux<M> X;
+            load_now(rw, R);
+            load_now(ax, X);
+            s = M::state_of(a.mdp, R.key);
+            if (M::is_terminal(a.mdp, s)) break;
+            if (d == 0) {
+                leaf = 1;
+                break;
+            }
+            int nchild = X.nac[0], cbase = X.pbase[0], ccap = X.pcap[0];
+            int total_n = R.total_n;
+            // ---- action progressive widening (src/dpw.jl:94-105); the host refuses enable_action_pw = false for these models ----
+            // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action_tab[len]
+            const int need_a = nchild < a.cfg.nmin_action_n ? __ldg(a.cfg.nmin_action_tab + nchild) : 0x7fffffff;
+            if (total_n >= need_a) {
+                Act act;
+                M::next_action(a.mdp, s, rng, act);  // next_action(::RandomActionGenerator): always draws
+                bool present = false;
+                if (a.cfg.check_repeat_action) {  // haskey(tree.a_lookup, (snode, a)): isequal on the vector = bitwise
+                    for (int j = tile.lane; j < nchild; j += G) {
+                        const BoxANode* c = an + plog[cbase + j];
+                        bool eq = true;
+#pragma unroll
+                        for (int i = 0; i < AD; ++i) eq = eq && __double_as_longlong(c->a[i]) == __double_as_longlong(act.v[i]);
+                        present = present || eq;
+                    }
+                    present = tile.any(present);
+                }
+                if (!present) {
+                    if (n_action >= a.geo.NA) {
+                        status = MCTSB200_ERR_CAPACITY;
+                        leaf = 2;
+                        break;
+                    }
+                    const int id = n_action;
+                    const int n0 = a.cfg.init_N;
+                    if (lead()) {  // insert_action_node! (src/dpw_types.jl:174-186)
+                        BoxANode nn;
+                        nn.q = a.cfg.init_Q;
+                        nn.n = n0;
+                        nn.nac = 0;
+                        nn.thead = -1;
+                        nn.tpush = 0;
+                        nn.pbase = 0;
+                        nn.pcap = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) nn.a[i] = i < AD ? act.v[i < AD ? i : 0] : 0.0;
+                        an[id] = nn;
+                        cnt[CNT_ACTION_INSERTS] += 1;
+                    }
+                    if (!vec_push(cbase, ccap, nchild, id, &ax->pbase[0], &ax->pcap[0])) {
+                        leaf = 2;
+                        break;
+                    }
+                    ++nchild;
+                    total_n += n0;  // tree.total_n[snode] += n0
+                    if (lead()) {
+                        ax->nac[0] = nchild;
+                        rw->total_n = total_n;
+                    }
+                    n_action += 1;
+                    tile.sync();
+                }
+            }
+            if (lead()) {
+                cnt[CNT_LEVELS] += 1;
+                cnt[CNT_CHILDREN_SEEN] += (unsigned)nchild;
+            }
+            // ---- best_sanode_UCB (src/dpw.jl:179-199), the reference's expression operation for operation; lane j scores children
+            // j, j + G, ... in order, the tile keeps the first maximum ----
+            const double c = a.cfg.c;
+            const double ltn = log_n(total_n);
+            double best = -CUDART_INF;
+            int best_j = kNone;
+            for (int j = tile.lane; j < nchild; j += G) {
+                const BoxANode* ch = an + plog[cbase + j];
+                const double2 qn = *reinterpret_cast<const double2*>(ch);  // (q, n | nac)
+                const int nn = __double2loint(qn.y);
+                double ucb;
+                if ((ltn <= 0.0 && nn == 0) || c == 0.0) ucb = qn.x;
+                else ucb = DM_ADD(qn.x, DM_MUL(c, DM_SQRT(DM_DIV(ltn, i2d(nn)))));
+                if (ucb > best) {
+                    best = ucb;
+                    best_j = j;
+                }
+            }
+            tile.argmax(best, best_j);
+            if (best_j == kNone) best_j = 0;  // (every score NaN or -Inf: the reference asserts; the first child keeps the search going)
+            const int sa = plog[cbase + best_j];
+            BoxANode AN;
+            load_now(an + sa, AN);
+            Act act;
+#pragma unroll
+            for (int i = 0; i < AD; ++i) act.v[i] = AN.a[i];
+
+            // ---- state progressive widening (src/dpw.jl:119-141) ----
+            bool new_node = false;
+            int spnode;
+            double r;
+            State sp;
+            bool widen = AN.nac == 0;
+            if (!widen && a.cfg.enable_state_pw) {
+                const int need = AN.nac < a.cfg.nmin_state_n ? __ldg(a.cfg.nmin_state + AN.nac) : 0x7fffffff;
+                widen = AN.n >= need;
+            }
+            if (widen) {
+                M::gen(a.mdp, s, act, rng, sp, r);
+                spnode = a.cfg.check_repeat_state ? map_lookup(sp) : -1;
+                if (spnode < 0) {
+                    spnode = dpw_insert_state(sp, a.cfg.maintain_lookup != 0);
+                    if (spnode < 0) {
+                        leaf = 2;
+                        break;
+                    }
+                    new_node = true;
+                }
+                // push!(transitions[sanode], (spnode, r)); n_a_children counts the distinct (sanode, spnode) pairs
+                int rec = -1;
+                if (!new_node) {
+                    for (rec = AN.thead; rec >= 0; rec = trans[rec].next)
+                        if (trans[rec].sp == spnode) break;
+                }
+                if (rec < 0 && n_trans >= a.geo.NT) {
+                    status = MCTSB200_ERR_CAPACITY;
+                    leaf = 2;
+                    break;
+                }
+                int pb = AN.pbase, pc = AN.pcap;
+                if (!vec_push(pb, pc, AN.tpush, rec >= 0 ? rec : n_trans, &an[sa].pbase, &an[sa].pcap)) {
+                    leaf = 2;
+                    break;
+                }
+                if (lead()) {
+                    if (rec >= 0) {
+                        bump_count(&trans[rec].count);
+                    } else {
+                        TransRec t;
+                        t.r = r;
+                        t.sp = spnode;
+                        t.next = AN.thead;
+                        t.count = 1;
+                        t.pad[0] = t.pad[1] = t.pad[2] = 0;
+                        trans[n_trans] = t;
+                        an[sa].thead = n_trans;
+                        an[sa].nac = AN.nac + 1;
+                    }
+                    an[sa].tpush = AN.tpush + 1;
+                }
+                if (rec < 0) n_trans += 1;
+            } else {
+                const int j = rng.uniform_int(AN.tpush);  // rand(rng, transitions[sanode])
+                const int rec = plog[AN.pbase + j];
+                spnode = trans[rec].sp;
+                r = trans[rec].r;
+                if (lead()) cnt[CNT_TRANS_SAMPLES] += 1;
+            }
+            if (lead()) path[top * path_stride] = PathEntry{node, sa, r};
+            ++top;
+            tile.sync();
+            node = spnode;
+            --d;
+            if (new_node) {
+                s = sp;
+                leaf = 1;  // estimate_value(sp, d-1)
+                break;
+            }
+        }
+        if (leaf == 2) return;
+        const double v0 = leaf == 1 ? estimate(s, d, it) : 0.0;
+        // backup (src/dpw.jl:149-151), deepest level first
+        tile.sync();
+        if (lead()) {
+            const double gamma = M::discount(a.mdp);
+            double v = v0;
+            for (int lvl = top - 1; lvl >= 0; --lvl) {
+                const PathEntry e = path[lvl * path_stride];
+                v = DM_ADD(e.r, DM_MUL(gamma, v));
+                BoxANode* c = an + e.slot;
+                const int nn = c->n + 1;
+                const double qo = c->q;
+                rows[e.node].total_n += 1;
+                c->n = nn;
+                c->q = DM_ADD(qo, div_by_count(DM_SUB(v, qo), i2d(nn)));
+            }
+        }
+        tile.sync();
+        if (lead()) cnt[CNT_SIMULATIONS] += 1;
+    }
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -974,12 +1239,14 @@ template <class M, int KIND, int G>
 __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_constant__ KernelArgs<M> args) {
     __shared__ unsigned long long s_cnt[CNT_COUNT];
 #ifndef MCTSB200_HOST_EMU
-    __shared__ double s_ucb[2][kTileTab];
     if (threadIdx.x < CNT_COUNT) s_cnt[threadIdx.x] = 0ull;
+#if MCTSB200_TILE_TAB > 0
+    __shared__ double s_ucb[2][kTileTab];
     for (int i = threadIdx.x; i < kTileTab; i += kBlockThreads) {
         s_ucb[0][i] = i < args.cfg.log_tab_n ? DM_MUL(args.cfg.c, args.cfg.sqrtlog_tab[i]) : 0.0;
         s_ucb[1][i] = i < args.cfg.rsqrt_tab_n ? args.cfg.rsqrt_tab[i] : 0.0;
     }
+#endif
     __syncthreads();
 #endif
 
@@ -988,8 +1255,10 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
     if (tree >= 0) {
         Search<M, G> S(args, tree);
 #ifndef MCTSB200_HOST_EMU
+#if MCTSB200_TILE_TAB > 0
         S.s_cs = s_ucb[0];
         S.s_rs = s_ucb[1];
+#endif
         if (args.path_smem) {  // [level][tile]: tiles at the same level touch consecutive 16 B entries
             extern __shared__ __align__(16) unsigned char dyn_smem[];
             // (spread batches keep their trees in the first path_tiles tiles of each warp: only those get a stack)
@@ -1015,7 +1284,8 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
             } else {
                 int id = S.n_state > 0 ? S.map_lookup(s0) : -1;
                 if (id < 0) {
-                    if (KIND == MCTSB200_KIND_UCT) id = S.uct_insert(s0);
+                    if constexpr (M::kActionDoubles > 0) id = S.dpw_insert_state(s0, S.n_state > 0 ? true : args.cfg.check_repeat_state != 0);
+                    else if (KIND == MCTSB200_KIND_UCT) id = S.uct_insert(s0);
                     else id = S.dpw_insert_state(s0, S.n_state > 0 ? true : args.cfg.check_repeat_state != 0);
                 }
                 root = id < 0 ? 0 : id;
@@ -1025,7 +1295,8 @@ __global__ void __launch_bounds__(kBlockThreads) search_kernel(const __grid_cons
 
         int it = args.iter_begin;
         for (; it < args.iter_end && S.status == MCTSB200_OK; ++it) {
-            if (KIND == MCTSB200_KIND_UCT) S.uct_iteration(root, (uint32_t)it);
+            if constexpr (M::kActionDoubles > 0) S.dpw_box_iteration(root, (uint32_t)it);
+            else if (KIND == MCTSB200_KIND_UCT) S.uct_iteration(root, (uint32_t)it);
             else S.dpw_iteration(root, (uint32_t)it);
         }
 
@@ -1136,6 +1407,43 @@ __global__ void decide_kernel(const TreeHeader* hdr, const Row<M>* rows, int NS,
     if (best_q_out) best_q_out[tree] = bq;
     if (status_out) status_out[tree] = h.status;
     // the call's worst status reaches the host with the counters even when the caller passed no status buffer
+    if (h.status != MCTSB200_OK) atomicOr(status_flags, h.status == MCTSB200_ERR_TERMINAL_ROOT ? 1ull : 2ull);
+}
+
+// Root decision of a continuous-action tree: best_sanode (src/dpw.jl:163-173) over the root's children list; writes the chosen
+// child's position, its Q and its action vector.
+template <class M>
+__global__ void decide_box_kernel(const TreeHeader* hdr, const Aux<M>* aux, const BoxANode* anodes, const int* plog, Geometry geo, long long n_trees,
+                                  int* action_out, double* best_q_out, int* status_out, double* action_vec_out, unsigned long long* status_flags) {
+    const long long tree = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= n_trees) return;
+    const TreeHeader h = hdr[tree];
+    int pos = -1;
+    double bq = 0.0;
+    double av[4] = {0.0, 0.0, 0.0, 0.0};
+    if (h.status != MCTSB200_ERR_TERMINAL_ROOT && h.n_state > 0) {
+        const Aux<M>& ax = aux[tree * geo.NS + h.root];
+        const BoxANode* an = anodes + tree * geo.NA;
+        const int* kids = plog + tree * geo.NP + ax.pbase[0];
+        double best = -CUDART_INF;
+        for (int j = 0; j < ax.nac[0]; ++j) {
+            const BoxANode& c = an[kids[j]];
+            if (c.q > best) {
+                best = c.q;
+                pos = j;
+            }
+        }
+        if (pos >= 0) {
+            const BoxANode& c = an[kids[pos]];
+            bq = c.q;
+            for (int i = 0; i < 4; ++i) av[i] = c.a[i];
+        }
+    }
+    if (action_out) action_out[tree] = pos;
+    if (best_q_out) best_q_out[tree] = bq;
+    if (status_out) status_out[tree] = h.status;
+    if (action_vec_out)
+        for (int i = 0; i < M::kActionDoubles; ++i) action_vec_out[tree * M::kActionDoubles + i] = av[i];
     if (h.status != MCTSB200_OK) atomicOr(status_flags, h.status == MCTSB200_ERR_TERMINAL_ROOT ? 1ull : 2ull);
 }
 
@@ -1286,7 +1594,7 @@ __global__ void order_scatter_kernel(const typename M::Params mdp, const typenam
 __host__ __device__ static inline size_t path_smem_bytes(int depth, int G, int path_tiles = 0) {
     return sizeof(PathEntry) * (size_t)depth * (size_t)(kBlockThreads / 32) * (size_t)(path_tiles ? path_tiles : 32 / G);
 }
-constexpr size_t kPathSmemLimit = 48 * 1024;
+constexpr size_t kPathSmemLimit = 48 * 1024 - 2 * sizeof(double) * kTileTab - 512;  // (static + dynamic shared memory of a block stay below the 48 KB that need no opt-in)
 
 #ifndef __CUDACC_RTC__  // (host-side launchers: not part of a run-time compiled plugin program, plugin_rt.cu)
 template <class M, int KIND>

@@ -121,6 +121,56 @@ class MountainCar:
         return abi.MountainCarParams(float(self.discount), float(self.cost), float(self.jackpot))
 
 
+@dataclass
+class GaussianBox:
+    """The continuous-action MDP of the reference's test/discussion_514.jl -- states(m) = Box, actions(m) = Box(a_lo, a_hi),
+    transition(m, s, a) = MvNormal(s, Diagonal(var)), reward 0, discount 0.9 -- with an optional drift (sp = s + drift * a + noise)
+    and quadratic cost (r = -cost * |sp|^2) that give a search something to find (include/mctsb200.h:
+    mctsb200_gaussian_box_params). States are 3 coordinates (a fourth, carried along unchanged, pads the ABI state); actions are
+    2-vectors, so `action` returns a tuple of floats and only DPWSolver can plan."""
+
+    a_lo: Tuple[float, float] = (-5.0, -5.0)
+    a_hi: Tuple[float, float] = (5.0, 5.0)
+    var: Tuple[float, float, float] = (0.1, 0.1, 0.1)
+    drift: float = 0.0
+    cost: float = 0.0
+    discount: float = 0.9
+
+    name = "GaussianBox"
+    mdp_id = abi.MDP_GAUSSIAN_BOX
+    actions = None          # a continuum: Box(a_lo, a_hi)
+    action_width = abi.BOX_ACTION_DOUBLES
+    state_dtype = np.float64
+    state_width = abi.BOX_STATE_DOUBLES
+    dense = False
+
+    def isterminal(self, s) -> bool:
+        return False
+
+    def action_in_space(self, a) -> bool:
+        """`a in actions(m)` (test/discussion_514.jl:18)."""
+        return len(a) == self.action_width and all(lo <= x <= hi for x, lo, hi in zip(a, self.a_lo, self.a_hi))
+
+    def encode_states(self, states: Sequence) -> np.ndarray:
+        arr = np.zeros((len(states), self.state_width), dtype=np.float64)
+        for i, s in enumerate(states):
+            arr[i, : len(s)] = s
+        return arr
+
+    def decode_state(self, row) -> Tuple[float, ...]:
+        return tuple(float(x) for x in row[:3])
+
+    def params(self) -> abi.GaussianBoxParams:
+        p = abi.GaussianBoxParams()
+        p.discount = float(self.discount)
+        for i in range(abi.BOX_ACTION_DOUBLES):
+            p.a_lo[i], p.a_hi[i] = float(self.a_lo[i]), float(self.a_hi[i])
+        for i in range(3):
+            p.var[i] = float(self.var[i])
+        p.drift, p.cost = float(self.drift), float(self.cost)
+        return p
+
+
 PLUGIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "plugins")
 
 

@@ -328,6 +328,7 @@ class _Planner:
         self.ctx.configure(mdp.mdp_id, mdp.params())
         self.tree = None
         self._roots = None
+        self._action_vectors = None
         self._calls = 0
         self.last_stats = None
 
@@ -358,9 +359,13 @@ class _Planner:
         del keep
         self._calls += 1
         self.last_stats = stats
+        # a continuous action space: the decisions are vectors (a_labels[sanode] of src/dpw.jl:65), fetched once per call
+        self._action_vectors = self.ctx.root_action_vectors(0, len(roots), self.mdp.action_width) if getattr(self.mdp, "action_width", 0) else None
         return actions, best_q, status, stats
 
-    def _label(self, idx: int):
+    def _label(self, idx: int, root_i: int = 0):
+        if self._action_vectors is not None:
+            return tuple(float(x) for x in self._action_vectors[root_i])
         return self.mdp.actions[int(idx)]
 
     def run_episodes(self, states: Sequence, max_steps: int, env_seed: int = 0, episode_index_base: int = 0):
@@ -456,7 +461,7 @@ class DPWPlanner(_Planner):
                 if self.solver.tree_in_info or tree_in_info:
                     info["tree"] = TreeView(self, i)
                 infos.append(info)
-                out.append(self._label(a))
+                out.append(self._label(a, i))
             self.tree = TreeView(self, 0)
             return out, infos
         except MCTSB200Error as ex:

@@ -57,6 +57,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <array>
 #include <utility>
 #include <vector>
 
@@ -144,6 +145,11 @@ struct GridWorld {
     static constexpr int kMdpId = MCTSB200_MDP_GRIDWORLD;
     static constexpr bool kLiteralTransitions = false;  // (the device keeps transitions[sanode] as records with multiplicities)
     using State = GWPos;
+    // actions are indices into actions(mdp) (a continuous-action model names its own Action type below)
+    typedef int32_t Action;
+    static constexpr int kActionDoubles = 0;
+    Action next_action(const State& s, Stream& rng) const { return rng.uniform_int(n_actions(s)); }  // rand(rng, actions(mdp, s))
+    static int32_t action_key(Action a) { return a; }
     static constexpr int kActions = 4;
     int nx = 10, ny = 10;
     double tprob = 0.7, gamma = 0.95;
@@ -221,6 +227,11 @@ struct MountainCar {
     static constexpr int kMdpId = MCTSB200_MDP_MOUNTAINCAR;
     static constexpr bool kLiteralTransitions = false;
     using State = MCState;
+    // actions are indices into actions(mdp) (a continuous-action model names its own Action type below)
+    typedef int32_t Action;
+    static constexpr int kActionDoubles = 0;
+    Action next_action(const State& s, Stream& rng) const { return rng.uniform_int(n_actions(s)); }  // rand(rng, actions(mdp, s))
+    static int32_t action_key(Action a) { return a; }
     static constexpr int kActions = 3;
     double gamma, cost, jackpot;
     explicit MountainCar(const mctsb200_mountaincar_params& p) : gamma(p.discount), cost(p.cost), jackpot(p.jackpot) {}
@@ -259,6 +270,11 @@ struct NoisyMountainCar {
     static constexpr int kMdpId = kOracleMdpNoisyMountainCar;
     static constexpr bool kLiteralTransitions = true;  // unbounded branching: the device keeps the push-ordered vector itself
     using State = MCState;
+    // actions are indices into actions(mdp) (a continuous-action model names its own Action type below)
+    typedef int32_t Action;
+    static constexpr int kActionDoubles = 0;
+    Action next_action(const State& s, Stream& rng) const { return rng.uniform_int(n_actions(s)); }  // rand(rng, actions(mdp, s))
+    static int32_t action_key(Action a) { return a; }
     static constexpr int kActions = 3;
     double gamma, cost, jackpot, noise, push[4];
     int n_act;
@@ -283,6 +299,83 @@ struct NoisyMountainCar {
         }
         sp = MCState{x_, v_};
         r = isterminal(sp) ? jackpot : cost;
+    }
+};
+
+// The continuous-action model of include/mctsb200.h (mctsb200_gaussian_box_params): the MDP of test/discussion_514.jl
+// (states / actions are Boxes, transition = MvNormal(s, Diagonal(var))) with an optional drift and quadratic cost. next_action is
+// RandomActionGenerator on a Box: rand(rng, actions(mdp, s)) = one uniform draw per coordinate (src/action_gen.jl:11-13).
+struct BoxState {
+    double v[MCTSB200_BOX_STATE_DOUBLES];
+    bool operator==(const BoxState& o) const {
+        for (int i = 0; i < MCTSB200_BOX_STATE_DOUBLES; ++i)
+            if (dm_bits(v[i]) != dm_bits(o.v[i])) return false;
+        return true;
+    }
+};
+struct BoxStateHash {
+    size_t operator()(const BoxState& s) const {
+        uint64_t h = 0x7F4A7C159E3779B9ull;
+        for (int i = 0; i < MCTSB200_BOX_STATE_DOUBLES; ++i) h = (h ^ dm_bits(s.v[i])) * 0x9E3779B97F4A7C15ull;
+        return std::hash<uint64_t>()(h);
+    }
+};
+struct BoxAction {
+    double v[MCTSB200_BOX_ACTION_DOUBLES];
+};
+struct GaussianBox {
+    static constexpr int kMdpId = MCTSB200_MDP_GAUSSIAN_BOX;
+    static constexpr bool kLiteralTransitions = true;  // continuous noise: transitions[sanode] is kept as the push-ordered vector
+    using State = BoxState;
+    typedef BoxAction Action;
+    static constexpr int kActions = 1;  // (no finite action set)
+    static constexpr int kActionDoubles = MCTSB200_BOX_ACTION_DOUBLES;
+    mctsb200_gaussian_box_params p;
+    double sd[3];
+    explicit GaussianBox(const mctsb200_gaussian_box_params& q) : p(q) {
+        for (int i = 0; i < 3; ++i) sd[i] = std::sqrt(q.var[i]);
+    }
+    double discount() const { return p.discount; }
+    int n_actions(const State&) const { return 0; }
+    int max_actions() const { return 1; }
+    bool isterminal(const State&) const { return false; }
+    int64_t state_index(const State&) const { return -1; }
+    int64_t n_states() const { return 0; }
+    // isequal on the action vector == bitwise equality of its coordinates
+    static std::array<uint64_t, MCTSB200_BOX_ACTION_DOUBLES> action_key(const Action& a) {
+        std::array<uint64_t, MCTSB200_BOX_ACTION_DOUBLES> k;
+        for (int i = 0; i < MCTSB200_BOX_ACTION_DOUBLES; ++i) k[(size_t)i] = dm_bits(a.v[i]);
+        return k;
+    }
+    Action next_action(const State&, Stream& rng) const {
+        Action a;
+        for (int i = 0; i < MCTSB200_BOX_ACTION_DOUBLES; ++i) a.v[i] = p.a_lo[i] + (p.a_hi[i] - p.a_lo[i]) * rng.uniform01();
+        return a;
+    }
+    // two Box-Muller pairs from four words: z0, z1 from (w0, w1), z2 from (w2, w3)
+    void gen(const State& s, const Action& a, Stream& rng, State& sp, double& r) const {
+        const double two_pi = 6.283185307179586;
+        double z[3];
+        {
+            const double u1 = ((double)rng.next() + 1.0) * (1.0 / 4294967296.0), u2 = rng.uniform01();
+            const double rad = std::sqrt(-2.0 * o_log(u1)), ang = two_pi * u2;
+            z[0] = rad * o_cos(ang);
+            z[1] = rad * det_sin(ang);
+        }
+        {
+            const double u1 = ((double)rng.next() + 1.0) * (1.0 / 4294967296.0), u2 = rng.uniform01();
+            z[2] = std::sqrt(-2.0 * o_log(u1)) * o_cos(two_pi * u2);
+        }
+        double ss = 0.0;
+        for (int i = 0; i < 3; ++i) {
+            double x = s.v[i];
+            if (i < MCTSB200_BOX_ACTION_DOUBLES) x = x + p.drift * a.v[i];
+            x = x + sd[i] * z[i];
+            sp.v[i] = x;
+            ss = ss + x * x;
+        }
+        sp.v[3] = s.v[3];
+        r = 0.0 - p.cost * ss;
     }
 };
 
@@ -311,7 +404,14 @@ struct Hooks {
     Counters* cnt;
 
     // action(policy, s) for the rollout policy
-    int policy_action(const typename M::State& s, Stream& rng) const {
+    typename M::Action policy_action(const typename M::State& s, Stream& rng) const {
+        if constexpr (M::kActionDoubles > 0) {
+            return mdp.next_action(s, rng);  // RandomPolicy: rand(rng, actions(problem, s)) -- the only policy a Box model has here
+        } else {
+            return discrete_policy_action(s, rng);
+        }
+    }
+    int discrete_policy_action(const typename M::State& s, Stream& rng) const {
         switch (cfg.rollout_policy) {
             case MCTSB200_POLICY_RANDOM:  // rand(rng, actions(problem, s))
                 return rng.uniform_int(mdp.n_actions(s));
@@ -337,6 +437,9 @@ struct Hooks {
     static int64_t state_y(const MCState&) { return 0; }
     static double state_v(const GWPos&) { return 0.0; }
     static double state_v(const MCState& s) { return s.v; }
+    static int64_t state_x(const BoxState&) { return 0; }
+    static int64_t state_y(const BoxState&) { return 0; }
+    static double state_v(const BoxState&) { return 0.0; }
 
     // POMDPTools simulate(::RolloutSimulator, mdp, policy, s0)
     double rollout(typename M::State s, int64_t max_steps, Stream& rng) const {
@@ -345,7 +448,7 @@ struct Hooks {
         double r_total = 0.0;
         int64_t step = 1;
         while (disc > eps && !mdp.isterminal(s) && step <= max_steps) {
-            const int a = policy_action(s, rng);
+            const typename M::Action a = policy_action(s, rng);
             typename M::State sp;
             double r;
             mdp.gen(s, a, rng, sp, r);
@@ -380,12 +483,16 @@ struct Hooks {
             }
         }
     }
-    double init_Q(const typename M::State& s, int a) const {
-        if (cfg.init_q_table) return cfg.init_q_table[mdp.state_index(s) * M::kActions + a];
+    double init_Q(const typename M::State& s, const typename M::Action& a) const {
+        if constexpr (M::kActionDoubles == 0) {
+            if (cfg.init_q_table) return cfg.init_q_table[mdp.state_index(s) * M::kActions + a];
+        }
         return cfg.init_Q;
     }
-    int64_t init_N(const typename M::State& s, int a) const {
-        if (cfg.init_n_table) return cfg.init_n_table[mdp.state_index(s) * M::kActions + a];
+    int64_t init_N(const typename M::State& s, const typename M::Action& a) const {
+        if constexpr (M::kActionDoubles == 0) {
+            if (cfg.init_n_table) return cfg.init_n_table[mdp.state_index(s) * M::kActions + a];
+        }
         return cfg.init_N;
     }
 };
@@ -401,6 +508,8 @@ struct ExportedTree {
     std::vector<int32_t> a_labels;
     std::vector<int64_t> n_a_children, trans_offsets, trans_spnode, trans_count;
     std::vector<double> trans_r;
+    int64_t action_doubles = 0;
+    std::vector<double> a_label_vectors;  // continuous action spaces
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -570,6 +679,8 @@ struct VanillaPlanner {
 template <class M, class H>
 struct DPWPlanner {
     using S = typename M::State;
+    using Act = typename M::Action;  // an index into actions(mdp), or a vector for a continuous action space
+    using ActKey = decltype(M::action_key(std::declval<Act>()));
     const M& mdp;
     const mctsb200_solver_cfg& cfg;
     const bool literal_transitions;
@@ -585,8 +696,8 @@ struct DPWPlanner {
     std::vector<int64_t> n;
     std::vector<double> q;
     std::vector<std::vector<std::pair<int64_t, double>>> transitions;
-    std::vector<int32_t> a_labels;
-    std::map<std::pair<int64_t, int32_t>, int64_t> a_lookup;
+    std::vector<Act> a_labels;
+    std::map<std::pair<int64_t, ActKey>, int64_t> a_lookup;
     std::vector<int64_t> n_a_children;
     std::set<std::pair<int64_t, int64_t>> unique_transitions;
 
@@ -602,8 +713,8 @@ struct DPWPlanner {
         std::vector<int64_t> n;
         std::vector<double> q;
         std::vector<std::vector<std::pair<int64_t, double>>> transitions;
-        std::vector<int32_t> a_labels;
-        std::map<std::pair<int64_t, int32_t>, int64_t> a_lookup;
+        std::vector<Act> a_labels;
+        std::map<std::pair<int64_t, ActKey>, int64_t> a_lookup;
         std::vector<int64_t> n_a_children;
         std::set<std::pair<int64_t, int64_t>> unique_transitions;
     };
@@ -627,7 +738,7 @@ struct DPWPlanner {
         return snode;
     }
 
-    int64_t insert_action_node(int64_t snode, int32_t a, int64_t n0, double q0, bool maintain_a_lookup) {
+    int64_t insert_action_node(int64_t snode, const Act& a, int64_t n0, double q0, bool maintain_a_lookup) {
         n.push_back(n0);
         q.push_back(q0);
         a_labels.push_back(a);
@@ -635,7 +746,7 @@ struct DPWPlanner {
         const int64_t sanode = (int64_t)n.size();
         children[snode - 1].push_back(sanode);
         n_a_children.push_back(0);
-        if (maintain_a_lookup) a_lookup[{snode, a}] = sanode;
+        if (maintain_a_lookup) a_lookup[{snode, M::action_key(a)}] = sanode;
         cnt.n_action_inserts += 1;
         return sanode;
     }
@@ -712,25 +823,27 @@ struct DPWPlanner {
         // action progressive widening
         if (cfg.enable_action_pw) {
             if ((double)children[snode - 1].size() <= cfg.k_action * std::pow((double)total_n[snode - 1], cfg.alpha_action)) {
-                const int32_t a = rng->uniform_int(mdp.n_actions(s));  // next_action(::RandomActionGenerator)
-                if (!cfg.check_repeat_action || !a_lookup.count({snode, a})) {
+                const Act a = mdp.next_action(s, *rng);  // next_action(::RandomActionGenerator) = rand(rng, actions(mdp, s))
+                if (!cfg.check_repeat_action || !a_lookup.count({snode, M::action_key(a)})) {
                     const int64_t n0 = hooks.init_N(s, a);
                     insert_action_node(snode, a, n0, hooks.init_Q(s, a), cfg.check_repeat_action != 0);
                     total_n[snode - 1] += n0;
                 }
             }
         } else if (children[snode - 1].empty()) {
-            for (int32_t a = 0; a < mdp.n_actions(s); ++a) {
-                const int64_t n0 = hooks.init_N(s, a);
-                insert_action_node(snode, a, n0, hooks.init_Q(s, a), false);
-                total_n[snode - 1] += n0;
+            if constexpr (M::kActionDoubles == 0) {  // (for a in actions(mdp, s): only a finite action set can be enumerated)
+                for (int32_t a = 0; a < mdp.n_actions(s); ++a) {
+                    const int64_t n0 = hooks.init_N(s, a);
+                    insert_action_node(snode, a, n0, hooks.init_Q(s, a), false);
+                    total_n[snode - 1] += n0;
+                }
             }
         }
 
         cnt.n_tree_levels += 1;
         cnt.n_dpw_children_seen += (int64_t)children[snode - 1].size();
         const int64_t sanode = best_sanode_UCB(snode, cfg.exploration_constant);
-        const int32_t a = a_labels[sanode - 1];
+        const Act a = a_labels[sanode - 1];
 
         // state progressive widening
         bool new_node = false;
@@ -814,7 +927,14 @@ struct DPWPlanner {
         }
         t.n = n;
         t.q = q;
-        t.a_labels = a_labels;
+        if constexpr (M::kActionDoubles == 0) {
+            t.a_labels = a_labels;
+        } else {
+            t.a_labels.assign(a_labels.size(), -1);
+            t.action_doubles = M::kActionDoubles;
+            for (const Act& a : a_labels)
+                for (int i = 0; i < M::kActionDoubles; ++i) t.a_label_vectors.push_back(a.v[i]);
+        }
         t.n_a_children = n_a_children;
         t.trans_offsets.assign(1, 0);
         for (const auto& tr : transitions) {  // distinct spnodes, first-occurrence order, with counts
@@ -845,9 +965,10 @@ struct RootResult {
     int32_t status = 0;
     int32_t n_children = 0;
     int64_t total_n = 0;
-    std::vector<int32_t> child_action;
+    std::vector<int32_t> child_action;  // action index; for a continuous action space the child's position
     std::vector<int64_t> child_n;
     std::vector<double> child_q;
+    std::vector<double> action_vec;     // continuous action space: the chosen action
 };
 
 static std::vector<std::unique_ptr<ExportedTree>> g_trees;
@@ -861,7 +982,14 @@ template <class M, class H>
 static void plan_one(const M& mdp, const mctsb200_solver_cfg& cfg, const typename M::State& root, uint64_t tree_index,
                      bool literal, bool keep, RootResult& res, Counters& cnt, std::unique_ptr<ExportedTree>& tree_out,
                      int64_t& iterations_done, std::any* saved) {
+    if constexpr (M::kActionDoubles > 0) {
+        if (cfg.kind == MCTSB200_KIND_UCT) {  // vanilla UCT enumerates actions(mdp, s) (src/vanilla.jl:297)
+            res.status = MCTSB200_ERR_UNSUPPORTED;
+            return;
+        }
+    }
     if (cfg.kind == MCTSB200_KIND_UCT) {
+      if constexpr (M::kActionDoubles == 0) {
         VanillaPlanner<M, H> p(mdp, cfg, tree_index);
         using SavedT = typename VanillaPlanner<M, H>::Saved;
         if (cfg.keep_tree && saved && saved->has_value()) p.load(std::move(std::any_cast<SavedT&>(*saved)));
@@ -884,6 +1012,7 @@ static void plan_one(const M& mdp, const mctsb200_solver_cfg& cfg, const typenam
             p.export_tree(*tree_out);
         }
         if (cfg.keep_tree && saved) *saved = p.save();
+      }
     } else {
         DPWPlanner<M, H> p(mdp, cfg, tree_index, literal || M::kLiteralTransitions);
         using SavedT = typename DPWPlanner<M, H>::Saved;
@@ -892,13 +1021,29 @@ static void plan_one(const M& mdp, const mctsb200_solver_cfg& cfg, const typenam
         res.status = p.search(root, rootid, iterations_done);
         if (res.status == MCTSB200_OK) {
             const int64_t best = p.best_sanode(rootid);
-            if (best > 0) {
-                res.action = p.a_labels[best - 1];
-                res.best_q = p.q[best - 1];
+            if constexpr (M::kActionDoubles == 0) {
+                if (best > 0) {
+                    res.action = p.a_labels[best - 1];
+                    res.best_q = p.q[best - 1];
+                }
+            } else {
+                res.action = -1;
+                res.action_vec.assign((size_t)M::kActionDoubles, 0.0);
             }
             res.total_n = p.total_n[rootid - 1];
+            int32_t pos = 0;
             for (int64_t sa : p.children[rootid - 1]) {
-                res.child_action.push_back(p.a_labels[sa - 1]);
+                if constexpr (M::kActionDoubles == 0) {
+                    res.child_action.push_back(p.a_labels[sa - 1]);
+                } else {
+                    res.child_action.push_back(pos);
+                    if (sa == best) {
+                        res.action = pos;
+                        res.best_q = p.q[sa - 1];
+                        for (int i = 0; i < M::kActionDoubles; ++i) res.action_vec[(size_t)i] = p.a_labels[sa - 1].v[i];
+                    }
+                }
+                ++pos;
                 res.child_n.push_back(p.n[sa - 1]);
                 res.child_q.push_back(p.q[sa - 1]);
             }
@@ -1080,8 +1225,24 @@ int32_t oracle_plan(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* 
         return plan_batch<NoisyMountainCar, MCStateHash>(m, *cfg, (const MCState*)roots, n_roots, root_index_base, n_threads,
                                                          keep_trees != 0, literal_transitions != 0, same_root != 0, action_out, bestq_out,
                                                          status_out, stats);
+    } else if (mdp_id == MCTSB200_MDP_GAUSSIAN_BOX) {
+        GaussianBox m(*(const mctsb200_gaussian_box_params*)params);
+        return plan_batch<GaussianBox, BoxStateHash>(m, *cfg, (const BoxState*)roots, n_roots, root_index_base, n_threads, keep_trees != 0,
+                                                     literal_transitions != 0, same_root != 0, action_out, bestq_out, status_out, stats);
     }
     return MCTSB200_ERR_INVALID_ARG;
+}
+
+int32_t oracle_root_action_vectors(int64_t first_root, int64_t n, double* out) {
+    using namespace oracle;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (first_root < 0 || n < 0 || first_root + n > (int64_t)g_roots.size() || !out) return MCTSB200_ERR_INVALID_ARG;
+    for (int64_t i = 0; i < n; ++i) {
+        const RootResult& r = g_roots[(size_t)(first_root + i)];
+        if (r.action_vec.empty()) return MCTSB200_ERR_STATE;
+        for (size_t k = 0; k < r.action_vec.size(); ++k) out[(size_t)i * r.action_vec.size() + k] = r.action_vec[k];
+    }
+    return MCTSB200_OK;
 }
 
 int32_t oracle_root_stats(int64_t root_i, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q, int64_t* total_n) {
@@ -1108,6 +1269,7 @@ int32_t oracle_tree_sizes_query(int64_t root_i, mctsb200_tree_sizes* sizes) {
     sizes->n_action_nodes = (int64_t)t.n.size();
     sizes->n_transitions = (int64_t)t.trans_spnode.size();
     sizes->state_bytes = t.state_bytes;
+    sizes->action_doubles = t.action_doubles;
     return MCTSB200_OK;
 }
 
@@ -1128,6 +1290,7 @@ int32_t oracle_tree_export(int64_t root_i, const mctsb200_tree_buffers* b) {
     copy_out(b->trans_spnode, t.trans_spnode);
     copy_out(b->trans_r, t.trans_r);
     copy_out(b->trans_count, t.trans_count);
+    copy_out(b->a_label_vectors, t.a_label_vectors);
     return MCTSB200_OK;
 }
 

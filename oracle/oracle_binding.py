@@ -52,6 +52,8 @@ def load(libm: bool = False) -> C.CDLL:
     lib.oracle_tree_sizes_query.argtypes = [i64, P(abi.TreeSizes)]
     lib.oracle_tree_sizes_query.restype = i32
     lib.oracle_tree_export.argtypes = [i64, P(abi.TreeBuffers)]
+    lib.oracle_root_action_vectors.argtypes = [i64, i64, vp]
+    lib.oracle_root_action_vectors.restype = i32
     lib.oracle_tree_export.restype = i32
     lib.oracle_plan_root_parallel.argtypes = [P(abi.SolverCfg), i32, vp, vp, i64, i64, i32, vp, vp, P(abi.PlanStats)]
     lib.oracle_plan_root_parallel.restype = i32
@@ -130,6 +132,12 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle_plan_root_parallel failed with {rc}")
         return sum_n, sum_nq, stats
+
+    def root_action_vectors(self, first_root: int, n: int, action_doubles: int = abi.BOX_ACTION_DOUBLES) -> np.ndarray:
+        out = np.zeros((int(n), int(action_doubles)), dtype=np.float64)
+        rc = self.lib.oracle_root_action_vectors(int(first_root), int(n), _ptr(out))
+        assert rc == 0, rc
+        return out
 
     def root_stats(self, root_i: int, n_actions: int = 16) -> dict:
         nch, tot = C.c_int32(), C.c_int64()

@@ -15,7 +15,7 @@ for what in "$@"; do
   case $kind in
     env) export "$rest";;
     lib) if [ -n "$rest" ]; then export MCTSB200_LIB=$rest; else unset MCTSB200_LIB; fi;;
-    tests) if [ -n "$rest" ]; then python -m pytest tests -m gpu -x -q -k "$rest" 2>&1 | tail -n 15 > gpurun_out/${TAG}_tests_$i.log; else python -m pytest tests -m gpu -x -q 2>&1 | tail -n 15 > gpurun_out/${TAG}_tests.log; fi;;
+    tests) if [ -n "$rest" ]; then python -m pytest tests -m gpu -x -q -k "$rest" > gpurun_out/${TAG}_tests_$i.full 2>&1; (grep -n "Fatal\|Segmentation\|^tests/.*::" gpurun_out/${TAG}_tests_$i.full | head -n 20; tail -n 25 gpurun_out/${TAG}_tests_$i.full) > gpurun_out/${TAG}_tests_$i.log; else python -m pytest tests -m gpu -x -q 2>&1 | tail -n 15 > gpurun_out/${TAG}_tests.log; fi;;
     bench) python bench.py $rest > gpurun_out/${TAG}_bench_$i.json 2> gpurun_out/${TAG}_bench_$i.err;;
     ref) python bench.py --impl reference $rest > gpurun_out/${TAG}_ref.json 2> gpurun_out/${TAG}_ref.err;;
     launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras $rest > gpurun_out/${TAG}_launches.log 2>&1;;

@@ -190,3 +190,28 @@ def test_custom_timer_decides_when_max_time_is_up(ctx):
         p = m.solve(S(n_iterations=100000, depth=5, max_time=1.5, timer=fake), GW, ctx=ctx)
         a = p.action((1, 1))
         assert a in GW.actions and 1 <= p.last_stats.iterations_done < 100000
+
+
+def test_continuous_action_space_like_discussion_514(ctx):
+    """test/discussion_514.jl: states(m) = Box, actions(m) = Box([-5,-5],[5,5]), transition = MvNormal(s, Diagonal([.1,.1,.1])),
+    reward 0, discount 0.9; `policy = solve(DPWSolver(max_time=1.0), m); a = action(policy, [0.0,0.0,0.0]); @test a in actions(m)`."""
+    mdp = m.GaussianBox()
+    policy = m.solve(m.DPWSolver(max_time=0.2, n_iterations=200), mdp, ctx=ctx)
+    a = policy.action((0.0, 0.0, 0.0))
+    assert len(a) == 2 and mdp.action_in_space(a)
+    a2, info = policy.action_info((1.0, -1.0, 0.5), tree_in_info=True)
+    assert mdp.action_in_space(a2) and info["tree_queries"] >= 1
+    tree = info["tree"]
+    # the chosen action is the label of the root child with the largest Q (src/dpw.jl:163-173, :65)
+    kids = tree.children(1)
+    best = kids[int(np.argmax(tree.q[kids - 1]))]
+    assert tuple(tree.a_label_vectors[best - 1]) == tuple(a2) and info["best_Q"] == tree.q[best - 1]
+    # vanilla UCT enumerates actions(mdp, s): refused, not approximated
+    with pytest.raises(m.MCTSB200Error) as ei:
+        m.solve(m.MCTSSolver(n_iterations=10, depth=5), mdp, ctx=ctx).action((0.0, 0.0, 0.0))
+    assert ei.value.status == m.abi.ERR_UNSUPPORTED
+    # a model with something to find: the planner steers towards the origin (drift * a reduces |s|^2)
+    steer = m.GaussianBox(drift=0.5, cost=1.0, var=(0.01, 0.01, 0.01))
+    p2 = m.solve(m.DPWSolver(n_iterations=3000, depth=3, exploration_constant=20.0, rng=5), steer, ctx=ctx)
+    a3 = p2.action((4.0, -4.0, 0.0))
+    assert a3[0] < 0.0 < a3[1]

@@ -491,3 +491,35 @@ def test_multi_device_ctx_equals_one_device(gpu_ctx, oracle, n_dev):
             del keep
     finally:
         multi.close()
+
+
+BOX_ROOTS = [(0.0, 0.0, 0.0), (1.5, -2.0, 0.5), (-3.0, 3.0, -1.0), (4.0, 4.0, 2.0), (0.25, -0.125, 3.0)]
+
+
+@pytest.mark.parametrize("lanes", [None, 1, 4, 32])
+def test_box_actions_bit_exact(gpu_ctx, oracle, lanes):
+    """Continuous action spaces (test/discussion_514.jl): a state node owns up to k_action * N^alpha_action action nodes, next_action
+    draws a vector, the tile's lanes share the repeat check and the UCB scan over a node's children. Action vectors, Q, counters and
+    whole trees against the oracle, for the reference test's model and for one where the search has something to find."""
+    from test_host_emu_parity import _run_box_both
+
+    roots = BOX_ROOTS * 8
+    v, _, st = _run_box_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=200, depth=10, rng=3), m.GaussianBox(), roots, lanes=lanes, trees=range(0, 40, 7))
+    assert all(m.GaussianBox().action_in_space(a) for a in v) and st.n_simulations == 200 * 40
+    steer = m.GaussianBox(drift=0.2, cost=1.0, var=(0.05, 0.1, 0.02))
+    for opts in (dict(), dict(exploration_constant=5.0, k_action=4.0, alpha_action=0.25, k_state=2.0, alpha_state=0.3), dict(check_repeat_state=False),
+                 dict(check_repeat_action=False), dict(init_Q=-3.0, init_N=2), dict(estimate_value=-1.5), dict(exploration_constant=0.0)):
+        kw = dict(n_iterations=300, depth=8, rng=11)
+        kw.update(opts)
+        _run_box_both(gpu_ctx, oracle, m.DPWSolver(**kw), steer, roots, base=77, lanes=lanes, trees=range(0, 40, 9))
+
+
+def test_box_actions_many_children_at_the_root(gpu_ctx, oracle):
+    """A long search from one root: hundreds of action nodes under the root (k_action * N^0.5), children lists and push logs that
+    moved through several arena chunks."""
+    from test_host_emu_parity import _run_box_both
+
+    steer = m.GaussianBox(drift=0.3, cost=0.5)
+    v, _, st = _run_box_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=5000, depth=6, exploration_constant=8.0, rng=2), steer, BOX_ROOTS[:3], trees=[0, 2])
+    t = gpu_ctx.tree_export(0, np.float64, 4)
+    assert t["child_offsets"][1] - t["child_offsets"][0] > 300

@@ -303,3 +303,77 @@ def test_environment_cannot_select_the_emulation_build(emu_lib_path, monkeypatch
         m.load_library()
     assert ei.value.status == m.abi.ERR_CUDA and "emulation" in str(ei.value)
     assert m.load_library(emu_lib_path) is not None  # a test that names it explicitly may
+
+
+# ---- continuous action spaces (test/discussion_514.jl: actions(m) = Box) ----------------------------------------------------
+def _run_box_both(ctx, orc, solver, mdp, roots, base=0, lanes=None, trees=None):
+    """DPW over a continuous action space on the library and on the oracle: chosen action vectors, Q, counters and whole trees
+    (children lists, vector labels, transitions) bit for bit."""
+    from helpers import COUNTER_KEYS, assert_trees_equal, bits
+
+    cfg, keep = m.build_cfg(solver, mdp)
+    if lanes is not None:
+        cfg.lanes_per_tree = lanes
+    ctx.configure(mdp.mdp_id, mdp.params())
+    orc.configure(mdp.mdp_id, mdp.params())
+    r = mdp.encode_states(roots)
+    a1, q1, s1, st1 = ctx.plan(cfg, mdp.mdp_id, r, base, want_status=True)
+    a2, q2, s2, st2 = orc.plan(cfg, mdp.mdp_id, r, base, n_threads=4)
+    assert np.array_equal(s1, s2) and np.array_equal(a1, a2), (a1, a2)
+    assert np.array_equal(bits(q1), bits(q2))
+    v1, v2 = ctx.root_action_vectors(0, len(roots)), orc.root_action_vectors(0, len(roots))
+    assert np.array_equal(bits(v1), bits(v2))
+    d1, d2 = st1.as_dict(), st2.as_dict()
+    for k in COUNTER_KEYS:
+        if k != "algorithmic_bytes":
+            assert d1[k] == d2[k], f"counter {k}: {d1[k]} != {d2[k]}"
+    for i in (trees if trees is not None else range(len(roots))):
+        t1 = ctx.tree_export(i, mdp.state_dtype, mdp.state_width)
+        t2 = orc.tree_export(i, mdp.state_dtype, mdp.state_width)
+        assert "a_label_vectors" in t1 and np.all(t1["a_labels"] == -1)
+        assert_trees_equal(t1, t2, f"tree {i}")
+        rs1, rs2 = ctx.root_stats(i, 4096), orc.root_stats(i, 4096)
+        for k in ("action_idx", "n", "q"):
+            assert np.array_equal(bits(rs1[k]), bits(rs2[k]))
+    del keep
+    return v1, q1, st1
+
+
+BOX_ROOTS = [(0.0, 0.0, 0.0), (1.5, -2.0, 0.5), (-3.0, 3.0, -1.0), (4.0, 4.0, 2.0), (0.25, -0.125, 3.0)]
+
+
+def test_emu_box_actions_discussion_514(emu_ctx, oracle):
+    """The reference's regression test for continuous action spaces (test/discussion_514.jl): the planner returns an action inside
+    actions(m) = Box([-5,-5],[5,5]); the trees equal the oracle's."""
+    mdp = m.GaussianBox()  # the test's model: no drift, zero reward
+    v, _, st = _run_box_both(emu_ctx, oracle, m.DPWSolver(n_iterations=100, depth=10, rng=3), mdp, BOX_ROOTS)
+    assert all(mdp.action_in_space(a) for a in v)
+    assert st.n_action_inserts > 100 and st.n_simulations == 500
+
+
+@pytest.mark.parametrize("opts", [
+    dict(),
+    dict(exploration_constant=5.0, k_action=4.0, alpha_action=0.25, k_state=2.0, alpha_state=0.3),
+    dict(check_repeat_state=False), dict(check_repeat_action=False), dict(enable_state_pw=False),
+    dict(init_Q=-3.0, init_N=2), dict(estimate_value=-1.5), dict(exploration_constant=0.0),
+    dict(estimate_value=m.RolloutEstimator(m.RandomSolver(), max_depth=-1)), dict(estimate_value=m.RolloutEstimator(m.RandomSolver(), max_depth=7, eps=0.3)),
+])
+def test_emu_box_actions_option_matrix(emu_ctx, oracle, opts):
+    """A model where the search has something to find (drift towards the origin is rewarded): every DPW option."""
+    mdp = m.GaussianBox(drift=0.2, cost=1.0, var=(0.05, 0.1, 0.02))
+    kw = dict(n_iterations=150, depth=8, rng=11)
+    kw.update(opts)
+    v, q, _ = _run_box_both(emu_ctx, oracle, m.DPWSolver(**kw), mdp, BOX_ROOTS, base=77)
+    assert all(mdp.action_in_space(a) for a in v)
+
+
+def test_emu_box_actions_refuses_what_cannot_work(emu_ctx):
+    mdp = m.GaussianBox()
+    emu_ctx.configure(mdp.mdp_id, mdp.params())
+    r = mdp.encode_states(BOX_ROOTS)
+    for solver in (m.MCTSSolver(n_iterations=10, depth=5), m.DPWSolver(n_iterations=10, depth=5, enable_action_pw=False),
+                   m.DPWSolver(n_iterations=10, depth=5, keep_tree=True)):
+        cfg, keep = m.build_cfg(solver, mdp)
+        with pytest.raises(m.MCTSB200Error) as ei:
+            emu_ctx.plan(cfg, mdp.mdp_id, r)
+        assert ei.value.status == m.abi.ERR_UNSUPPORTED
