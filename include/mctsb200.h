@@ -128,8 +128,11 @@ typedef struct {
     int32_t enable_action_pw, enable_state_pw, check_repeat_state, check_repeat_action;
     int32_t keep_tree;            /* DPW keep_tree / vanilla reuse_tree: the next plan call with the same ctx, solver kind,
                                      MDP and number of roots continues tree i for root i (src/vanilla.jl:213-217,
-                                     src/dpw.jl:31-37) until mctsb200_clear_trees. Needs a dense-state MDP with merged
-                                     states (bounded node table), else MCTSB200_ERR_UNSUPPORTED                      */
+                                     src/dpw.jl:31-37) until mctsb200_clear_trees. A dense-state MDP with merged states has a
+                                     bounded node table; any other tree (hashed states: MountainCar, run-time plugins; unmerged
+                                     states) grows by up to n_iterations state nodes per call and gets room for
+                                     keep_tree_calls calls, after which a tree reports MCTSB200_ERR_CAPACITY (clear and start
+                                     over)                                                                              */
     int32_t lanes_per_tree;       /* 0 = auto; else 1,2,4,8,16,32 lanes cooperate on one tree      */
     /* node initialisers and leaf estimator */
     double init_Q;
@@ -139,7 +142,7 @@ typedef struct {
     double estimate_const;
     int32_t rollout_policy_param[4];
     int32_t rollout_max_depth;    /* RolloutEstimator.max_depth; -1 = remaining depth              */
-    int32_t reserved0;
+    int32_t keep_tree_calls;      /* plan calls a kept tree of an unbounded model has room for (0 = 8)             */
     double rollout_eps;
     uint64_t seed;                /* Philox key                                                    */
     /* Optional dense tables (host pointers, may be NULL; only for MDPs with a dense state index):

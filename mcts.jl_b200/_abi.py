@@ -102,7 +102,7 @@ class SolverCfg(C.Structure):
         ("estimate_const", C.c_double),
         ("rollout_policy_param", C.c_int32 * 4),
         ("rollout_max_depth", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("keep_tree_calls", C.c_int32),
         ("rollout_eps", C.c_double),
         ("seed", C.c_uint64),
         ("init_q_table", C.POINTER(C.c_double)),

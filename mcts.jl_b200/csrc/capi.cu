@@ -406,20 +406,29 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     const bool merge_states = !dpw || cfg->check_repeat_state;
     long long NS = n_iter + 1;
     if (M::kDense && merge_states) NS = std::min<long long>(NS, dense);
+    // A kept tree grows call after call (src/dpw.jl:31-37, src/vanilla.jl:213-217). A dense state space with merged states bounds
+    // it; any other tree gets room for `keep_tree_calls` calls (one new state node per iteration at most) and reports
+    // MCTSB200_ERR_CAPACITY when that is used up.
+    const bool bounded = M::kDense && merge_states;
+    long long calls = 1;
     if (cfg->keep_tree) {
-        // a kept tree grows call after call: only a dense state space with merged states bounds it
-        if (!(M::kDense && merge_states))
-            return fail(MCTSB200_ERR_UNSUPPORTED, "reuse_tree / keep_tree needs an MDP with a dense state index and merged states (bounded node table)");
-        NS = dense;
+        if (bounded) {
+            NS = dense;
+        } else {
+            if (cfg->keep_tree_calls < 0 || cfg->keep_tree_calls > 100000) return fail(MCTSB200_ERR_INVALID_ARG, "keep_tree_calls out of range");
+            calls = cfg->keep_tree_calls ? cfg->keep_tree_calls : 8;
+            NS = calls * n_iter + 1;
+            if (NS > 0x7fffffffLL / 4) return fail(MCTSB200_ERR_CAPACITY, "kept trees would exceed 2^29 state nodes per tree");
+        }
     }
     if (direct) NS = dense;
     const bool maintain_lookup = !dpw || cfg->keep_tree || cfg->check_repeat_state;
     if (M::kDense && maintain_lookup && NS > 65535) return fail(MCTSB200_ERR_CAPACITY, "dense state map limited to 65535 nodes per tree");
     long long NT = 0;
     if (dpw) {
-        const long long by_iter = std::max<long long>(1, n_iter * std::max(cfg->depth, 1));
+        const long long by_iter = std::max<long long>(1, calls * n_iter * std::max(cfg->depth, 1));
         const long long by_pairs = NS * A * std::min<long long>(MdpAccess<M>::max_branch(ctx), NS);
-        NT = cfg->check_repeat_state ? (cfg->keep_tree ? by_pairs : std::min(by_iter, by_pairs)) : std::max<long long>(1, n_iter);
+        NT = cfg->check_repeat_state ? ((cfg->keep_tree && bounded) ? by_pairs : std::min(by_iter, by_pairs)) : std::max<long long>(1, calls * n_iter);
     }
     long long MAP = 0;
     size_t map_entry = 0;
@@ -437,7 +446,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     // one entry per push, in chunks that double. A node with p pushes has allocated < 4p + 8 entries in all.
     long long NP = 0;
     if (dpw && MdpAccess<M>::max_branch(ctx) >= (1LL << 30)) {
-        const long long pushes = std::max<long long>(1, n_iter * std::max(cfg->depth, 1));  // at most one push per tree level
+        const long long pushes = std::max<long long>(1, calls * n_iter * std::max(cfg->depth, 1));  // at most one push per tree level
         NP = 4 * pushes + 8 * std::min<long long>(NS * A, pushes);
         if (NP > 0x7fffffffLL) return fail(MCTSB200_ERR_CAPACITY, "push log would exceed 2^31 entries per tree");
     }

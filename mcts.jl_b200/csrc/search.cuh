@@ -284,10 +284,12 @@ struct Search {
         if (M::kDense) {
             dmap[M::dense_index(a.mdp, s)] = (uint16_t)(node + 1);
         } else {
+            // s_lookup[s] = snode: a state inserted again (unmerged states with keep_tree, src/dpw.jl:127) maps to its newest node
             const uint32_t tag = hash_of(s) | 1u;
             const int msk = a.geo.MAP - 1;
+            const Key key = M::key_of(a.mdp, s);
             int i = (int)(tag >> 1) & msk;
-            while (hmap[i].tag != 0) i = (i + 1) & msk;
+            while (hmap[i].tag != 0 && !(hmap[i].tag == tag && hmap[i].node != node && M::key_equal(rows[hmap[i].node].key, key))) i = (i + 1) & msk;
             hmap[i] = HashSlot{tag, node};
         }
     }

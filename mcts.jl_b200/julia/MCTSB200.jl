@@ -43,7 +43,7 @@ struct SolverCfg                       # mctsb200_solver_cfg
     estimate_kind::Int32; rollout_policy::Int32
     estimate_const::Float64
     rollout_policy_param::NTuple{4,Int32}
-    rollout_max_depth::Int32; reserved0::Int32
+    rollout_max_depth::Int32; keep_tree_calls::Int32
     rollout_eps::Float64
     seed::UInt64
     init_q_table::Ptr{Float64}; init_n_table::Ptr{Int64}; value_table::Ptr{Float64}

@@ -110,6 +110,7 @@ class MCTSSolver:
     callback_every: int = 1  # iterations between two calls of `callback` (1 = the reference's per-iteration callback)
     rollouts_per_leaf: int = 1
     lanes_per_tree: int = 0
+    keep_tree_calls: int = 0  # reuse_tree on a model without a bounded state table: calls a tree has room for (0 = 8)
 
 
 @dataclass
@@ -141,6 +142,7 @@ class DPWSolver:
     timer: Optional[Callable] = None
     rollouts_per_leaf: int = 1
     lanes_per_tree: int = 0
+    keep_tree_calls: int = 0  # keep_tree on a model without a bounded state table: calls a tree has room for (0 = 8)
 
 
 def _unsupported(what: str) -> MCTSB200Error:
@@ -183,6 +185,7 @@ def build_cfg(solver, mdp) -> tuple[abi.SolverCfg, list]:
     cfg.max_time = float(solver.max_time)
     cfg.rollouts_per_leaf = int(solver.rollouts_per_leaf)
     cfg.lanes_per_tree = int(solver.lanes_per_tree)
+    cfg.keep_tree_calls = int(getattr(solver, "keep_tree_calls", 0))
     cfg.seed = _seed_of(solver.rng)
 
     # `timer` and vanilla's `callback` run on the host between launches (Context.set_timer / set_progress_callback, installed

@@ -229,17 +229,45 @@ def test_emu_kept_trees_continue_across_calls(emu_ctx, oracle, monkeypatch, kind
     assert emu_ctx.tree_export(0)["total_n"].shape[0] == sizes[0]
 
 
-def test_emu_kept_trees_need_a_bounded_table(emu_ctx):
+@pytest.mark.parametrize("kind", ["dpw", "dpw-unmerged", "uct"])
+def test_emu_kept_trees_of_hashed_models(emu_ctx, oracle, kind):
+    """keep_tree / reuse_tree on a model without a bounded state table (MountainCar: hashed continuous states; DPW's main use with
+    kept trees, src/dpw.jl:31-37): the trees get room for keep_tree_calls calls; a 4-call episode-like sequence -- every root moves
+    on to a state its own tree already holds, or to a new one -- equals the oracle's bit for bit."""
+    emu_ctx.clear_trees()
+    oracle.clear_trees()
     mc = m.MountainCar()
-    cfg, keep = m.build_cfg(m.DPWSolver(n_iterations=20, depth=5, keep_tree=True), mc)
+    if kind == "uct":
+        mk = lambda seed: m.MCTSSolver(n_iterations=60, depth=12, exploration_constant=8.0, rng=seed, reuse_tree=True)
+    else:
+        mk = lambda seed: m.DPWSolver(n_iterations=60, depth=12, exploration_constant=8.0, rng=seed, keep_tree=True, check_repeat_state=kind == "dpw")
+    roots = mountaincar_roots(12)
+    for call in range(4):
+        a, _, _, _ = run_both(emu_ctx, oracle, mk(300 + call), mc, roots, compare_trees=range(0, 12, 3))
+        nxt = []
+        for (x, v), ai in zip(roots, a):  # follow the chosen action: the successor is in the tree already (deterministic model)
+            sp, _, _ = oracle.gen(mc.mdp_id, (x, v), int(ai))
+            nxt.append((float(sp[0]), float(sp[1])) if sp[0] < 0.5 else (x, v))
+        roots = nxt
+    sizes = emu_ctx.tree_export(0, np.float64, 2)["total_n"].shape[0]
+    assert sizes > 61  # the tree kept growing across the calls
+    emu_ctx.clear_trees()
+    oracle.clear_trees()
+
+
+def test_emu_kept_trees_report_capacity_when_their_room_is_used_up(emu_ctx):
+    mc = m.MountainCar()
+    emu_ctx.clear_trees()
+    cfg, keep = m.build_cfg(m.DPWSolver(n_iterations=40, depth=10, keep_tree=True, keep_tree_calls=1), mc)
     emu_ctx.configure(mc.mdp_id, mc.params())
+    r = mc.encode_states(mountaincar_roots(3))
+    emu_ctx.plan(cfg, mc.mdp_id, r)
     with pytest.raises(m.MCTSB200Error) as ei:
-        emu_ctx.plan(cfg, mc.mdp_id, mc.encode_states(mountaincar_roots(2)))
-    assert ei.value.status == m.abi.ERR_UNSUPPORTED
-    cfg, keep = m.build_cfg(m.DPWSolver(n_iterations=20, depth=5, keep_tree=True, check_repeat_state=False), GW)
-    emu_ctx.configure(GW.mdp_id, GW.params())
-    with pytest.raises(m.MCTSB200Error):
-        emu_ctx.plan(cfg, GW.mdp_id, GW.encode_states(gridworld_roots(2)))
+        for _ in range(3):
+            emu_ctx.plan(cfg, mc.mdp_id, r)
+    assert ei.value.status == m.abi.ERR_CAPACITY
+    emu_ctx.clear_trees()
+    emu_ctx.plan(cfg, mc.mdp_id, r)  # clear_tree! and start over
 
 
 # ---- episode driver: simulate(RolloutSimulator(max_steps), mdp, planner, s0) (bench/non-terminal_gw.jl:18,31) ----------
