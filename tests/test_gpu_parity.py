@@ -231,6 +231,33 @@ def test_episodes_mountaincar(gpu_ctx, oracle):
     assert steps[-1] == 0 and ret[-1] == 0.0
 
 
+@pytest.mark.parametrize("model", ["mountaincar", "mountaincar-uct", "noisy-plugin", "noisy-plugin-unmerged"])
+def test_kept_trees_of_hashed_models_follow_their_episodes(gpu_ctx, oracle, model):
+    """keep_tree (src/dpw.jl:31-37) / reuse_tree on models without a bounded state table -- DPW's main use of kept trees: a continuous
+    model planned along an episode. The closed-loop driver plans from every episode's current state with the tree it has grown so
+    far (root lookup through the hash map, or a new node when the noise took the environment somewhere new); returns, steps,
+    final states and every counter equal the oracle's over the whole episode."""
+    est = m.RolloutEstimator(m.RandomSolver(), max_depth=20)
+    if model == "mountaincar-uct":
+        mdp, s = MC, m.MCTSSolver(n_iterations=80, depth=10, exploration_constant=8.0, rng=11, estimate_value=est, reuse_tree=True)
+    else:
+        mdp = MC if model == "mountaincar" else m.NoisyMountainCar(noise=0.004)
+        s = m.DPWSolver(n_iterations=80, depth=10, exploration_constant=8.0, rng=11, estimate_value=est, keep_tree=True,
+                        check_repeat_state=not model.endswith("unmerged"))
+    starts = mountaincar_roots(24)
+    ret, steps, final, st = run_episodes_both(gpu_ctx, oracle, s, mdp, starts, max_steps=6, env_seed=4)
+    assert steps.max() == 6 and st.n_simulations == 24 * 80 * 6
+    # the room a kept tree has is finite: with space for one call only the second plan of the episode overflows, loudly
+    gpu_ctx.clear_trees()
+    s.keep_tree_calls = 1
+    with pytest.raises(m.MCTSB200Error) as ei:
+        cfg, keep = m.build_cfg(s, mdp)
+        gpu_ctx.run_episodes(cfg, mdp.mdp_id, mdp.encode_states(starts), 6, 4)
+    assert ei.value.status == m.abi.ERR_CAPACITY
+    gpu_ctx.clear_trees()
+    oracle.clear_trees()
+
+
 @pytest.mark.parametrize("ahead,det", [("0", "1"), ("1", "0"), ("1", "1")])
 def test_uct_both_descent_orders(gpu_ctx, oracle, monkeypatch, ahead, det):
     monkeypatch.setenv("MCTSB200_AHEAD", ahead)
@@ -312,7 +339,7 @@ def test_plugin_episodes_and_root_parallel(gpu_ctx, oracle):
     root = mdp.encode_states([(-0.5, 0.0)])
     n1, nq1, _ = gpu_ctx.plan_root_parallel(cfg, mdp.mdp_id, root, 64)
     n2, nq2, _ = oracle.plan_root_parallel(cfg, oracle_id(mdp), root, 64, n_threads=4)
-    assert np.array_equal(n1, n2) and np.allclose(nq1, nq2, rtol=1e-12)
+    assert np.array_equal(n1, n2) and np.array_equal(nq1.view(np.int64), nq2.view(np.int64))  # integer partial sums: exact
 
 
 def test_plugin_needs_configure_and_refuses_dense_options(gpu_ctx):

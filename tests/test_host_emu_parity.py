@@ -303,6 +303,18 @@ def test_emu_episodes_mountaincar_and_terminal_starts(emu_ctx, oracle):
     assert (steps0 == 0).all() and (ret0 == 0).all()
 
 
+@pytest.mark.parametrize("kind", ["dpw-keep", "uct-reuse"])
+def test_emu_episodes_mountaincar_with_kept_trees(emu_ctx, oracle, kind):
+    """the closed-loop driver with trees that follow their episodes, on a hashed-state model (see test_emu_kept_trees_of_hashed_models)"""
+    est = m.RolloutEstimator(m.RandomSolver(), max_depth=15)
+    if kind == "dpw-keep":
+        s = m.DPWSolver(n_iterations=40, depth=8, exploration_constant=8.0, rng=11, estimate_value=est, keep_tree=True)
+    else:
+        s = m.MCTSSolver(n_iterations=40, depth=8, exploration_constant=8.0, rng=11, estimate_value=est, reuse_tree=True)
+    ret, steps, final, st = run_episodes_both(emu_ctx, oracle, s, MC, mountaincar_roots(6), max_steps=5, env_seed=2)
+    assert steps.max() == 5 and st.n_simulations == 6 * 40 * 5
+
+
 def test_emu_simulate_mirror(emu_ctx):
     planner = m.solve(m.MCTSSolver(n_iterations=30, depth=8, rng=4), GW, ctx=emu_ctx)
     sim = m.RolloutSimulator(rng=8, max_steps=6)
