@@ -190,7 +190,7 @@ def cpu_sample(workload, seconds_target=15.0, threads=None, single_seconds=5.0):
     return out
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     W = workloads()
@@ -216,10 +216,18 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # rank 0 prints exactly ONE line on stdout, the JSON line: whatever a library writes to fd 1 meanwhile (NCCL's version banner
+    # when the library's own communicator comes up, for one) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     W = workloads()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -240,7 +248,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch
@@ -440,7 +448,7 @@ def main():
         except Exception as ex:  # the baseline must never break the GPU line
             line.setdefault("cpu_baseline", {"error": str(ex)})
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -103,7 +103,9 @@ enum {
     MCTSB200_POLICY_RANDOM = 0,    /* RandomPolicy: rand(rng, actions(mdp, s))                      */
     MCTSB200_POLICY_CONSTANT = 1,  /* FunctionPolicy(s -> actions[param[0]])  (test/options.jl:29)  */
     MCTSB200_POLICY_GW_SEEK = 2,   /* notebook SeekTarget(GWPos(param[0], param[1]))                */
-    MCTSB200_POLICY_MC_ENERGY = 3  /* MountainCar: push in the direction of motion (v<0 ? -1 : +1)  */
+    MCTSB200_POLICY_MC_ENERGY = 3, /* MountainCar: push in the direction of motion (v<0 ? -1 : +1)  */
+    MCTSB200_POLICY_TABLE = 4      /* FunctionPolicy(f) for any state-only f on a dense-state MDP, tabulated by the host:
+                                      action index = policy_table[state_index] (src/domain_knowledge.jl:57)             */
 };
 
 /* run-time registered MDP plugins (mctsb200_mdp_register below) */
@@ -151,6 +153,7 @@ typedef struct {
     const double* init_q_table;
     const int64_t* init_n_table;
     const double* value_table;    /* used when estimate_kind == MCTSB200_EST_TABLE                 */
+    const int32_t* policy_table;  /* [n_states] action indices, used when rollout_policy == MCTSB200_POLICY_TABLE */
 } mctsb200_solver_cfg;
 
 /* Work counters of one plan call (sums over all trees of the call). "Simulation" = one iteration of

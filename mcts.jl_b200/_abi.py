@@ -46,6 +46,7 @@ POLICY_RANDOM = 0
 POLICY_CONSTANT = 1
 POLICY_GW_SEEK = 2
 POLICY_MC_ENERGY = 3
+POLICY_TABLE = 4
 POLICY_PLUGIN = 100        # ids >= this go to the plugin's policy_action
 
 GW_MAX_SPECIAL = 32
@@ -108,6 +109,7 @@ class SolverCfg(C.Structure):
         ("init_q_table", C.POINTER(C.c_double)),
         ("init_n_table", C.POINTER(C.c_int64)),
         ("value_table", C.POINTER(C.c_double)),
+        ("policy_table", C.POINTER(C.c_int32)),
     ]
 
 

@@ -215,7 +215,7 @@ struct MdpAccess<GridWorldDev> {
         const bool term = s.x == -1 && s.y == -1;
         return (inb || term) ? 0 : -1;
     }
-    static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_GW_SEEK; }
+    static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_GW_SEEK || p == MCTSB200_POLICY_TABLE; }
     static bool fast_ready(const mctsb200_ctx* c) { return c->gw_dev.fast_tt != nullptr; }
     static double reward_bound(const mctsb200_ctx* c) { return c->gw_reward_max; }  // max |reward(s, a)|
     static bool fast_deterministic(const mctsb200_ctx* c) { return c->gw_fast_det; }   // every FastEntry has one outcome
@@ -227,8 +227,13 @@ struct MdpAccess<GridWorldDev> {
     }
     // a state-only deterministic rollout policy as a table over dense state indices (GridWorldDev::policy_action restated on the host)
     static bool tabulate_policy(const mctsb200_ctx* c, const mctsb200_solver_cfg* cfg, std::vector<unsigned char>& out) {
-        if (cfg->rollout_policy != MCTSB200_POLICY_GW_SEEK) return false;
         const int nx = c->gw_dev.nx, n = c->gw_dev.ncells;
+        if (cfg->rollout_policy == MCTSB200_POLICY_TABLE) {  // FunctionPolicy(f), tabulated by the caller
+            out.assign((size_t)n + 1, 0);
+            for (int cell = 0; cell <= n; ++cell) out[(size_t)cell] = (unsigned char)cfg->policy_table[cell];
+            return true;
+        }
+        if (cfg->rollout_policy != MCTSB200_POLICY_GW_SEEK) return false;
         out.assign((size_t)n + 1, 0);
         for (int cell = 0; cell <= n; ++cell) {
             const int x = cell % nx + 1, y = cell / nx + 1, tx = cfg->rollout_policy_param[0], ty = cfg->rollout_policy_param[1];
@@ -382,6 +387,8 @@ int32_t validate_cfg(const mctsb200_solver_cfg* cfg, int n_actions, bool dense, 
         if (!policy_ok(cfg->rollout_policy)) return fail(MCTSB200_ERR_UNSUPPORTED, "rollout policy %d is not available for this MDP", cfg->rollout_policy);
         if (cfg->rollout_policy == MCTSB200_POLICY_CONSTANT && (cfg->rollout_policy_param[0] < 0 || cfg->rollout_policy_param[0] >= n_actions))
             return fail(MCTSB200_ERR_INVALID_ARG, "constant rollout action out of range");
+        if (cfg->rollout_policy == MCTSB200_POLICY_TABLE && (!dense || !cfg->policy_table))
+            return fail(MCTSB200_ERR_UNSUPPORTED, "a tabulated rollout policy needs a dense-state MDP and a policy_table");
         if (cfg->rollout_max_depth < -1) return fail(MCTSB200_ERR_INVALID_ARG, "rollout max_depth must be >= -1");
         if (std::isnan(cfg->rollout_eps)) return fail(MCTSB200_ERR_INVALID_ARG, "rollout eps is NaN");
     }
@@ -563,6 +570,9 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
     const int dense = MdpAccess<M>::dense_count(ctx);
     if constexpr (M::kFast) {
         std::vector<unsigned char> pol;
+        if (cfg->estimate_kind == MCTSB200_EST_ROLLOUT && cfg->rollout_policy == MCTSB200_POLICY_TABLE)
+            for (int i = 0; i < MdpAccess<M>::dense_count(ctx); ++i)
+                if (cfg->policy_table[i] < 0 || cfg->policy_table[i] >= A) return fail(MCTSB200_ERR_INVALID_ARG, "policy_table entry %d out of range", i);
         if (cfg->estimate_kind == MCTSB200_EST_ROLLOUT && MdpAccess<M>::tabulate_policy(ctx, cfg, pol)) {
             CUDA_TRY(ctx->policy_tab.ensure(pol.size()));
             CUDA_TRY(cudaMemcpy(ctx->policy_tab.p, pol.data(), pol.size(), cudaMemcpyHostToDevice));
@@ -795,6 +805,7 @@ int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long pr
             case MCTSB200_POLICY_RANDOM: return FAST_POLICY_RANDOM;
             case MCTSB200_POLICY_CONSTANT: return FAST_POLICY_CONSTANT;
             case MCTSB200_POLICY_GW_SEEK: return FAST_POLICY_TABLE;
+            case MCTSB200_POLICY_TABLE: return FAST_POLICY_TABLE;
             default: return -1;
         }
     }

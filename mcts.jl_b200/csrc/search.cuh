@@ -313,7 +313,9 @@ struct Search {
                 M::next_action(a.mdp, s, rs, act);
                 M::gen(a.mdp, s, act, rs, sp, r);
             } else {
-                const int act = M::policy_action(a.mdp, a.cfg.policy, a.cfg.pparam, s, rs);
+                int act;
+                if (M::kDense && a.cfg.policy == MCTSB200_POLICY_TABLE) act = (int)a.cfg.policy_table[M::dense_index(a.mdp, s)];  // FunctionPolicy(f), tabulated
+                else act = M::policy_action(a.mdp, a.cfg.policy, a.cfg.pparam, s, rs);
                 M::gen(a.mdp, s, act, rs, sp, r);
             }
             r_total = DM_ADD(r_total, DM_MUL(disc, r));

@@ -46,7 +46,7 @@ struct SolverCfg                       # mctsb200_solver_cfg
     rollout_max_depth::Int32; keep_tree_calls::Int32
     rollout_eps::Float64
     seed::UInt64
-    init_q_table::Ptr{Float64}; init_n_table::Ptr{Int64}; value_table::Ptr{Float64}
+    init_q_table::Ptr{Float64}; init_n_table::Ptr{Int64}; value_table::Ptr{Float64}; policy_table::Ptr{Int32}
 end
 
 mutable struct PlanStats               # mctsb200_plan_stats

@@ -46,6 +46,13 @@ class ConstantPolicy:
 
 
 @dataclass
+class FunctionPolicy:
+    """POMDPTools.FunctionPolicy(f): action(policy, s) = f(s). On the device it becomes a table over the dense state space."""
+
+    f: Callable
+
+
+@dataclass
 class SeekTarget:
     """notebooks/Domain_Knowledge_Example.ipynb cell 12-13: move towards `target` (x first, then y)."""
 
@@ -265,8 +272,16 @@ def build_cfg(solver, mdp) -> tuple[abi.SolverCfg, list]:
             cfg.rollout_policy = int(pol.policy_id)
             for i, v in enumerate(pol.params):
                 cfg.rollout_policy_param[i] = int(v)
-        elif callable(pol):
-            raise _unsupported("a Function-valued rollout policy (use ConstantPolicy / SeekTarget / EnergyPolicy)")
+        elif isinstance(pol, FunctionPolicy) or callable(pol):
+            # FunctionPolicy(f) (src/domain_knowledge.jl:57; `RolloutEstimator(x->:up)`, test/options.jl:29): a state-only host function
+            # cannot run inside the search, but on a dense-state MDP it is a table over the states
+            f = pol.f if isinstance(pol, FunctionPolicy) else pol
+            if not mdp.dense:
+                raise _unsupported("a Function-valued rollout policy on a non-dense MDP (register it as a device rollout-policy plugin)")
+            tab = np.ascontiguousarray([mdp.action_index(f(mdp.state_from_index(i))) for i in range(mdp.n_states())], dtype=np.int32)
+            keep.append(tab)
+            cfg.rollout_policy = abi.POLICY_TABLE
+            cfg.policy_table = tab.ctypes.data_as(C.POINTER(C.c_int32))
         else:
             raise TypeError(f"RolloutEstimator: unsupported policy {type(pol).__name__}")
     elif isinstance(ev, np.ndarray) or callable(ev):

@@ -425,6 +425,8 @@ struct Hooks {
                 else if (ty > sy) return 0;  // :up
                 else return 1;               // :down
             }
+            case MCTSB200_POLICY_TABLE:  // FunctionPolicy(f) for a state-only f, tabulated over the dense state space
+                return cfg.policy_table[mdp.state_index(s)];
             case MCTSB200_POLICY_MC_ENERGY:
             case MCTSB200_POLICY_PLUGIN:  // (policy 100 of the shipped plugins: the same heuristic)
                 return state_v(s) < 0.0 ? 0 : 2;

@@ -246,7 +246,7 @@ def test_kept_trees_of_hashed_models_follow_their_episodes(gpu_ctx, oracle, mode
                         check_repeat_state=not model.endswith("unmerged"))
     starts = mountaincar_roots(24)
     ret, steps, final, st = run_episodes_both(gpu_ctx, oracle, s, mdp, starts, max_steps=6, env_seed=4)
-    assert steps.max() == 6 and st.n_simulations == 24 * 80 * 6
+    assert steps.max() == 6 and 24 * 80 * 3 < st.n_simulations <= 24 * 80 * 6  # (an episode that reaches the goal stops planning)
     # the room a kept tree has is finite: with space for one call only the second plan of the episode overflows, loudly
     gpu_ctx.clear_trees()
     s.keep_tree_calls = 1

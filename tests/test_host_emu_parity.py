@@ -312,7 +312,7 @@ def test_emu_episodes_mountaincar_with_kept_trees(emu_ctx, oracle, kind):
     else:
         s = m.MCTSSolver(n_iterations=40, depth=8, exploration_constant=8.0, rng=11, estimate_value=est, reuse_tree=True)
     ret, steps, final, st = run_episodes_both(emu_ctx, oracle, s, MC, mountaincar_roots(6), max_steps=5, env_seed=2)
-    assert steps.max() == 5 and st.n_simulations == 6 * 40 * 5
+    assert steps.max() == 5 and 6 * 40 * 2 < st.n_simulations <= 6 * 40 * 5
 
 
 def test_emu_simulate_mirror(emu_ctx):
@@ -417,3 +417,24 @@ def test_emu_box_actions_refuses_what_cannot_work(emu_ctx):
         with pytest.raises(m.MCTSB200Error) as ei:
             emu_ctx.plan(cfg, mdp.mdp_id, r)
         assert ei.value.status == m.abi.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("fast", ["1", "0"])
+def test_emu_function_policy_is_a_table_on_the_device(emu_ctx, oracle, monkeypatch, fast):
+    """RolloutEstimator(FunctionPolicy(f)) / RolloutEstimator(x -> :up) (test/options.jl:29, src/domain_knowledge.jl:57): a state-only
+    host function is tabulated over the dense state space once (MCTSB200_POLICY_TABLE); lane-per-tree and tile kernels, UCT and DPW."""
+    monkeypatch.setenv("MCTSB200_FAST", fast)
+    f = lambda s: "up" if s[0] < 5 else ("left" if s[1] > 3 else "right")
+    for est in (m.RolloutEstimator(m.FunctionPolicy(f), max_depth=30), m.RolloutEstimator(lambda s: "up")):
+        run_both(emu_ctx, oracle, m.MCTSSolver(n_iterations=120, depth=12, exploration_constant=5.0, rng=5, estimate_value=est), GW, gridworld_roots(30),
+                 compare_trees=range(0, 30, 7))
+        run_both(emu_ctx, oracle, m.DPWSolver(n_iterations=120, depth=12, exploration_constant=5.0, rng=5, estimate_value=est), GW, gridworld_roots(30),
+                 compare_trees=range(0, 30, 7))
+    # x -> :up on the deterministic GridWorld is the bit-exact variant of BASELINE config 2, requested the reference's way
+    est = m.RolloutEstimator(lambda s: "up")
+    a1, q1, _, _ = run_both(emu_ctx, oracle, m.MCTSSolver(n_iterations=100, depth=20, exploration_constant=5.0, estimate_value=est), GW_DET, gridworld_roots(20))
+    a2, q2, _, _ = run_both(emu_ctx, oracle, m.MCTSSolver(n_iterations=100, depth=20, exploration_constant=5.0, estimate_value=m.RolloutEstimator(m.ConstantPolicy("up"))),
+                            GW_DET, gridworld_roots(20))
+    assert np.array_equal(a1, a2) and np.array_equal(q1.view(np.int64), q2.view(np.int64))
+    with pytest.raises(m.MCTSB200Error):  # a hashed-state model has no table to put it in
+        m.build_cfg(m.MCTSSolver(estimate_value=m.RolloutEstimator(lambda s: 1.0)), MC)
