@@ -154,6 +154,10 @@ typedef struct {
     const int64_t* init_n_table;
     const double* value_table;    /* used when estimate_kind == MCTSB200_EST_TABLE                 */
     const int32_t* policy_table;  /* [n_states] action indices, used when rollout_policy == MCTSB200_POLICY_TABLE */
+    int32_t enable_tree_vis;      /* MCTSSolver.enable_tree_vis: record (action node => next state node) visit counts, the
+                                     tree's _vis_stats (src/vanilla.jl:268-270, 328-334), for D3Tree(::MCTSTree); vanilla UCT on
+                                     models with bounded branching (max_branch >= 1) only                                */
+    int32_t reserved1;
 } mctsb200_solver_cfg;
 
 /* Work counters of one plan call (sums over all trees of the call). "Simulation" = one iteration of
@@ -339,6 +343,10 @@ typedef struct {
 int32_t mctsb200_tree_sizes_query(mctsb200_ctx* ctx, int64_t root_i, mctsb200_tree_sizes* sizes);
 int32_t mctsb200_tree_export(mctsb200_ctx* ctx, int64_t root_i, const mctsb200_tree_buffers* buffers);
 int32_t mctsb200_clear_trees(mctsb200_ctx* ctx); /* clear_tree! (src/vanilla.jl:148, src/dpw.jl:6-8) */
+/* tree._vis_stats of a vanilla tree planned with enable_tree_vis (src/vanilla.jl:328-334): for every (action node, next state node)
+ * edge the search walked, how often -- what D3Tree(::MCTSTree) (src/visualization.jl:52-122) draws below an action node. Entries
+ * sorted by (said, spid), ids 1-based. Two-call pattern: NULL arrays return the count in n_out. */
+int32_t mctsb200_tree_vis_stats(mctsb200_ctx* ctx, int64_t root_i, int64_t* said, int64_t* spid, int64_t* count, int64_t capacity, int64_t* n_out);
 /* Continuous action spaces: the action best_sanode chose for roots [first_root, first_root + n) of the last plan call, as vectors
  * (n * action_doubles float64; the action_idx_out of mctsb200_plan then holds the chosen child's position among the root's
  * children, -1 if it has none). a_labels[sanode] of src/dpw.jl:65. */

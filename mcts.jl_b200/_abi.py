@@ -110,6 +110,8 @@ class SolverCfg(C.Structure):
         ("init_n_table", C.POINTER(C.c_int64)),
         ("value_table", C.POINTER(C.c_double)),
         ("policy_table", C.POINTER(C.c_int32)),
+        ("enable_tree_vis", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 
@@ -197,6 +199,7 @@ EXPORTED_SYMBOLS = (
     "mctsb200_tree_export",
     "mctsb200_clear_trees",
     "mctsb200_root_action_vectors",
+    "mctsb200_tree_vis_stats",
     "mctsb200_device_log",
     "mctsb200_device_cos",
     "mctsb200_device_philox",
@@ -240,6 +243,7 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.mctsb200_tree_export.argtypes = [vp, i64, P(TreeBuffers)]
     lib.mctsb200_clear_trees.argtypes = [vp]
     lib.mctsb200_root_action_vectors.argtypes = [vp, i64, i64, vp]
+    lib.mctsb200_tree_vis_stats.argtypes = [vp, i64, vp, vp, vp, i64, P(i64)]
     lib.mctsb200_device_log.argtypes = [vp, vp, i64, vp]
     lib.mctsb200_device_cos.argtypes = [vp, vp, i64, vp]
     lib.mctsb200_device_philox.argtypes = [vp, u64, u64, u32, u32, i32, vp]

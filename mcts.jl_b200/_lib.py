@@ -274,6 +274,14 @@ class Context:
     def clear_trees(self) -> None:
         self._check(self.lib.mctsb200_clear_trees(self._h))
 
+    def tree_vis_stats(self, root_i: int) -> dict:
+        """tree._vis_stats of a vanilla tree planned with enable_tree_vis: {(said, spid): visits}, ids 1-based (src/vanilla.jl:328-334)."""
+        n = C.c_int64()
+        self._check(self.lib.mctsb200_tree_vis_stats(self._h, int(root_i), None, None, None, 0, C.byref(n)))
+        said, spid, cnt = (np.zeros(n.value, dtype=np.int64) for _ in range(3))
+        self._check(self.lib.mctsb200_tree_vis_stats(self._h, int(root_i), _ptr(said), _ptr(spid), _ptr(cnt), n.value, C.byref(n)))
+        return {(int(a), int(b)): int(c) for a, b, c in zip(said, spid, cnt)}
+
     def root_action_vectors(self, first_root: int, n: int, action_doubles: int = abi.BOX_ACTION_DOUBLES) -> np.ndarray:
         """Continuous action spaces: the action vectors best_sanode chose for roots [first_root, first_root + n) of the last plan call."""
         out = np.zeros((int(n), int(action_doubles)), dtype=np.float64)

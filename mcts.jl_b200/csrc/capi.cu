@@ -9,6 +9,7 @@
 #endif
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -86,6 +87,8 @@ struct Storage {
     DevBuf hdr, rows, aux, trans, map, path;
     DevBuf plog;        // push-log arena of models with unbounded branching (search.cuh: kPushLog)
     DevBuf anodes;      // action-node table of continuous-action trees (search.cuh: dpw_box_iteration)
+    DevBuf vis;         // _vis_stats edges of vanilla trees planned with enable_tree_vis
+    int vis_branch = 0;
     DevBuf action_vec;  // the decisions' action vectors of the last plan call (continuous action spaces)
     DevBuf rows_fast;   // working table of uct_fast.cuh / dpw_fast.cuh (interleaved); `rows` receives the Row<M> table after the search
     DevBuf trans_fast;  // dpw_fast.cuh: per-slot transition multisets (interleaved)
@@ -793,6 +796,7 @@ int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long pr
         return -1;
     } else {
         if (!env_enabled("MCTSB200_FAST") || !MdpAccess<M>::fast_ready(ctx)) return -1;
+        if (cfg->enable_tree_vis) return -1;  // (the tile kernel records _vis_stats)
         if (cfg->estimate_kind != MCTSB200_EST_ROLLOUT || cfg->rollouts_per_leaf != 1 || cfg->lanes_per_tree > 1) return -1;
         if (cfg->init_q_table || cfg->init_n_table) return -1;
         if (cfg->exploration_constant == 0.0) return -1;  // argmax-Q selection: the tile kernel has that path
@@ -864,6 +868,16 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     bool reused = false;
     rc = setup_storage<M>(ctx, cfg, n_trees, fast >= 0, &reused);
     if (rc) return rc;
+    st.vis_branch = 0;
+    if (KIND == MCTSB200_KIND_UCT && cfg->enable_tree_vis) {
+        const long long mb = MdpAccess<M>::max_branch(ctx);
+        if (mb < 1 || mb > 64) return fail(MCTSB200_ERR_UNSUPPORTED, "enable_tree_vis needs a model with bounded branching (max_branch 1..64)");
+        st.vis_branch = (int)mb;
+        const size_t bytes = sizeof(VisRec) * (size_t)st.geo.NS * M::kActions * (size_t)mb * (size_t)n_trees;
+        const bool fresh = !reused || bytes > st.vis.cap;
+        CUDA_TRY(st.vis.ensure(bytes));
+        if (fresh) CUDA_TRY(cudaMemsetAsync(st.vis.p, 0, bytes, ctx->stream));
+    }
     if (reused) {  // same trees, new search: iteration counters and per-root status start over
         MCTSB200_LAUNCH(begin_call_kernel, (unsigned)((n_trees + 255) / 256), 256, 0, ctx->stream, (TreeHeader*)st.hdr.p, n_trees);
         CUDA_TRY(cudaGetLastError());
@@ -894,6 +908,8 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.n_trees = n_trees;
     args.tree_index_base = tree_index_base;
     args.root_stride = root_stride;
+    args.vis = st.vis_branch ? (VisRec*)st.vis.p : nullptr;
+    args.vis_branch = st.vis_branch;
     // (measured on B200, profiles/r2b_*: 4 % SLOWER on config 2, 1 % on config 3 -- the rows that miss L2 are not what the
     // levels wait for; kept as a switch for the record)
     args.prefetch_l2 = env_enabled("MCTSB200_PREFETCH_L2", false) ? 1 : 0;
@@ -1504,6 +1520,36 @@ int32_t box_tree_export(mctsb200_ctx* ctx, long long i, const mctsb200_tree_buff
 }
 
 template <class M>
+int32_t vis_stats_impl(mctsb200_ctx* ctx, long long i, int64_t* said, int64_t* spid, int64_t* count, int64_t capacity, int64_t* n_out) {
+    Storage& st = ctx->st;
+    if (st.kind != MCTSB200_KIND_UCT || st.vis_branch == 0) return fail(MCTSB200_ERR_STATE, "the last plan call did not record _vis_stats (MCTSSolver.enable_tree_vis)");
+    HostTree<M> t;
+    int32_t rc = fetch_tree<M>(ctx, i, t);
+    if (rc) return rc;
+    const int A = M::kActions, B = st.vis_branch;
+    std::vector<VisRec> v((size_t)st.geo.NS * A * B);
+    CUDA_TRY(cudaMemcpy(v.data(), (const VisRec*)st.vis.p + (size_t)i * v.size(), sizeof(VisRec) * v.size(), cudaMemcpyDeviceToHost));
+    std::vector<std::array<int64_t, 3>> out;
+    for (int node = 0; node < t.h.n_state; ++node)
+        for (int slot = 0; slot < A; ++slot)
+            for (int b = 0; b < B; ++b) {
+                const VisRec& e = v[((size_t)node * A + slot) * B + b];
+                if (e.count > 0) out.push_back({(int64_t)node * A + slot + 1, (int64_t)e.sp + 1, (int64_t)e.count});
+            }
+    std::sort(out.begin(), out.end());
+    *n_out = (int64_t)out.size();
+    if (said && spid && count) {
+        if (capacity < *n_out) return fail(MCTSB200_ERR_INVALID_ARG, "need room for %lld entries", (long long)*n_out);
+        for (size_t k = 0; k < out.size(); ++k) {
+            said[k] = out[k][0];
+            spid[k] = out[k][1];
+            count[k] = out[k][2];
+        }
+    }
+    return MCTSB200_OK;
+}
+
+template <class M>
 int32_t tree_sizes_impl(mctsb200_ctx* ctx, long long i, mctsb200_tree_sizes* out) {
     TreeHeader h;
     CUDA_TRY(cudaSetDevice(ctx->device));
@@ -1888,7 +1934,7 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     }
 #endif
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->st.plog, &c->st.anodes, &c->st.action_vec, &c->nmin_action_tab, &c->counters,
+    DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->st.plog, &c->st.anodes, &c->st.action_vec, &c->st.vis, &c->nmin_action_tab, &c->counters,
                       &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
                       &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->gw_fast,
                       &c->ep_states, &c->ep_disc, &c->ep_ret, &c->ep_steps, &c->ep_active, &c->ep_count};
@@ -2358,6 +2404,21 @@ int32_t mctsb200_tree_export(mctsb200_ctx* ctx, int64_t root_i, const mctsb200_t
     if (rc) return rc;
     if (!buffers) return fail(MCTSB200_ERR_INVALID_ARG, "buffers is NULL");
 #define MCTSB200_CALL(M) tree_export_impl<M>(ctx, root_i, buffers)
+    MCTSB200_FOR_MDP(ctx, ctx->st.mdp_id, MCTSB200_CALL);
+#undef MCTSB200_CALL
+}
+
+int32_t mctsb200_tree_vis_stats(mctsb200_ctx* ctx, int64_t root_i, int64_t* said, int64_t* spid, int64_t* count, int64_t capacity, int64_t* n_out) {
+    if (!n_out) return fail(MCTSB200_ERR_INVALID_ARG, "n_out is NULL");
+    if (ctx && !ctx->kids.empty()) {
+        mctsb200_ctx* kid = nullptr;
+        long long local = 0;
+        if (int32_t e = group_locate(ctx, root_i, &kid, &local)) return e;
+        return mctsb200_tree_vis_stats(kid, local, said, spid, count, capacity, n_out);
+    }
+    int32_t rc = check_tree_query(ctx, root_i);
+    if (rc) return rc;
+#define MCTSB200_CALL(M) vis_stats_impl<M>(ctx, root_i, said, spid, count, capacity, n_out)
     MCTSB200_FOR_MDP(ctx, ctx->st.mdp_id, MCTSB200_CALL);
 #undef MCTSB200_CALL
 }

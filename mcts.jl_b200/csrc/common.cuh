@@ -118,6 +118,12 @@ struct __align__(32) TransRec {
     int pad[3];
 };
 
+// one (action node => next state node) edge of a vanilla tree's _vis_stats (enable_tree_vis): count == 0 = free
+struct __align__(8) VisRec {
+    int sp;
+    int count;
+};
+
 struct __align__(8) HashSlot {
     uint32_t tag;  // 0 = empty; else (hash | 1)
     int node;
@@ -244,6 +250,8 @@ struct KernelArgs {
     int* plog;                          // push-log arena, [n_trees][NP] (null unless the model has unbounded branching)
     BoxANode* anodes;                   // action nodes of continuous-action trees, [n_trees][NA] (else null)
     double* action_vec_out;             // continuous action spaces: the decision's action vector per tree (may be null)
+    VisRec* vis;                        // enable_tree_vis: [n_trees][NS * kActions * vis_branch] edge visit counts (else null)
+    int vis_branch;
     void* map;
     PathEntry* path;
     const typename M::AbiState* roots;  // device

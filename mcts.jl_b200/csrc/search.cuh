@@ -714,6 +714,19 @@ struct Search {
                 aux[node].sp1[slot] = next;
                 aux[node].r1[slot] = r;
             }
+            if (a.vis && next >= 0 && lead()) {  // record_visit!(tree, said, spid) (src/vanilla.jl:268-270, 328-334)
+                VisRec* v = a.vis + ((long long)(tree_index - (uint64_t)a.tree_index_base) * a.geo.NS + node) * (A * a.vis_branch) + slot * a.vis_branch;
+                for (int b = 0; b < a.vis_branch; ++b) {
+                    if (v[b].count == 0) {
+                        v[b] = VisRec{next, 1};
+                        break;
+                    }
+                    if (v[b].sp == next) {
+                        v[b].count += 1;
+                        break;
+                    }
+                }
+            }
             if (leaf) break;
             node = next;
         }

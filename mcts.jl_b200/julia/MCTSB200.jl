@@ -47,6 +47,7 @@ struct SolverCfg                       # mctsb200_solver_cfg
     rollout_eps::Float64
     seed::UInt64
     init_q_table::Ptr{Float64}; init_n_table::Ptr{Int64}; value_table::Ptr{Float64}; policy_table::Ptr{Int32}
+    enable_tree_vis::Int32; reserved1::Int32
 end
 
 mutable struct PlanStats               # mctsb200_plan_stats

@@ -213,8 +213,7 @@ def build_cfg(solver, mdp) -> tuple[abi.SolverCfg, list]:
         cfg.keep_tree = int(bool(solver.keep_tree))
     else:
         cfg.keep_tree = int(bool(solver.reuse_tree))
-        if solver.enable_tree_vis:
-            raise _unsupported("`enable_tree_vis` (_vis_stats recording)")
+        cfg.enable_tree_vis = int(bool(solver.enable_tree_vis))  # record_visit! (src/vanilla.jl:268-270): tree._vis_stats
 
     # init_Q / init_N: Number, ndarray table, or (dense MDPs) a pure function tabulated once
     def table_or_const(val, name, dtype, ctype):
@@ -305,7 +304,7 @@ class TreeView:
     exported from the device on first access. Node ids are 1-based like in Julia."""
 
     def __init__(self, planner, root_i: int):
-        self._planner, self._root_i, self._data = planner, root_i, None
+        self._planner, self._root_i, self._data, self._vis = planner, root_i, None, None
 
     def _load(self) -> dict:
         if self._data is None:
@@ -330,6 +329,14 @@ class TreeView:
         return out
 
     s_lookup = state_map
+
+    @property
+    def _vis_stats(self) -> dict:
+        """(said, spid) => visits of a vanilla tree planned with enable_tree_vis (src/vanilla.jl:75, 328-334): what
+        D3Tree(::MCTSTree) draws below an action node (src/visualization.jl:52-122)."""
+        if self._vis is None:
+            self._vis = self._planner.ctx.tree_vis_stats(self._root_i)
+        return self._vis
 
     def children(self, snode: int) -> np.ndarray:
         d = self._load()

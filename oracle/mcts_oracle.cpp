@@ -512,6 +512,7 @@ struct ExportedTree {
     std::vector<double> trans_r;
     int64_t action_doubles = 0;
     std::vector<double> a_label_vectors;  // continuous action spaces
+    std::vector<int64_t> vis_said, vis_spid, vis_count;  // _vis_stats of a vanilla tree built with enable_tree_vis
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -534,6 +535,7 @@ struct VanillaPlanner {
     std::vector<int64_t> n;
     std::vector<double> q;
     std::vector<int32_t> a_labels;
+    std::map<std::pair<int64_t, int64_t>, int64_t> vis_stats;  // _vis_stats: (said => spid) => visits, only with enable_tree_vis
 
     VanillaPlanner(const M& m, const mctsb200_solver_cfg& c, uint64_t tree_index)
         : mdp(m), cfg(c), hooks{m, c, tree_index, 0, &cnt} {}
@@ -547,11 +549,12 @@ struct VanillaPlanner {
         std::vector<int64_t> n;
         std::vector<double> q;
         std::vector<int32_t> a_labels;
+        std::map<std::pair<int64_t, int64_t>, int64_t> vis_stats;
     };
-    Saved save() { return Saved{std::move(state_map), std::move(child_ids), std::move(total_n), std::move(s_labels), std::move(n), std::move(q), std::move(a_labels)}; }
+    Saved save() { return Saved{std::move(state_map), std::move(child_ids), std::move(total_n), std::move(s_labels), std::move(n), std::move(q), std::move(a_labels), std::move(vis_stats)}; }
     void load(Saved&& t) {
         state_map = std::move(t.state_map); child_ids = std::move(t.child_ids); total_n = std::move(t.total_n); s_labels = std::move(t.s_labels);
-        n = std::move(t.n); q = std::move(t.q); a_labels = std::move(t.a_labels);
+        n = std::move(t.n); q = std::move(t.q); a_labels = std::move(t.a_labels); vis_stats = std::move(t.vis_stats);
     }
 
     int64_t insert_node(const S& s) {
@@ -625,12 +628,15 @@ struct VanillaPlanner {
         mdp.gen(s, a_labels[said - 1], *rng, sp, r);
         double qv;
         auto it = state_map.find(sp);
+        int64_t spid;
         if (it == state_map.end()) {
-            insert_node(sp);
+            spid = insert_node(sp);
             qv = r + mdp.discount() * hooks.estimate_value(sp, depth - 1);
         } else {
-            qv = r + mdp.discount() * simulate(it->second, depth - 1);
+            spid = it->second;
+            qv = r + mdp.discount() * simulate(spid, depth - 1);
         }
+        if (cfg.enable_tree_vis) vis_stats[{said, spid}] += 1;  // record_visit! (src/vanilla.jl:268-270, 328-334)
         total_n[node - 1] += 1;
         n[said - 1] += 1;
         q[said - 1] += (qv - q[said - 1]) / (double)n[said - 1];
@@ -672,6 +678,11 @@ struct VanillaPlanner {
         t.n = n;
         t.q = q;
         t.a_labels = a_labels;
+        for (const auto& kv : vis_stats) {
+            t.vis_said.push_back(kv.first.first);
+            t.vis_spid.push_back(kv.first.second);
+            t.vis_count.push_back(kv.second);
+        }
     }
 };
 
@@ -1233,6 +1244,21 @@ int32_t oracle_plan(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* 
                                                      literal_transitions != 0, same_root != 0, action_out, bestq_out, status_out, stats);
     }
     return MCTSB200_ERR_INVALID_ARG;
+}
+
+int32_t oracle_tree_vis_stats(int64_t root_i, int64_t* said, int64_t* spid, int64_t* count, int64_t capacity, int64_t* n_out) {
+    using namespace oracle;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (root_i < 0 || root_i >= (int64_t)g_trees.size() || !g_trees[(size_t)root_i] || !n_out) return MCTSB200_ERR_STATE;
+    const ExportedTree& t = *g_trees[(size_t)root_i];
+    *n_out = (int64_t)t.vis_said.size();
+    if (said && spid && count) {
+        if (capacity < *n_out) return MCTSB200_ERR_INVALID_ARG;
+        copy_out(said, t.vis_said);
+        copy_out(spid, t.vis_spid);
+        copy_out(count, t.vis_count);
+    }
+    return MCTSB200_OK;
 }
 
 int32_t oracle_root_action_vectors(int64_t first_root, int64_t n, double* out) {

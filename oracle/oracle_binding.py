@@ -52,6 +52,8 @@ def load(libm: bool = False) -> C.CDLL:
     lib.oracle_tree_sizes_query.argtypes = [i64, P(abi.TreeSizes)]
     lib.oracle_tree_sizes_query.restype = i32
     lib.oracle_tree_export.argtypes = [i64, P(abi.TreeBuffers)]
+    lib.oracle_tree_vis_stats.argtypes = [i64, vp, vp, vp, i64, P(i64)]
+    lib.oracle_tree_vis_stats.restype = i32
     lib.oracle_root_action_vectors.argtypes = [i64, i64, vp]
     lib.oracle_root_action_vectors.restype = i32
     lib.oracle_tree_export.restype = i32
@@ -132,6 +134,13 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle_plan_root_parallel failed with {rc}")
         return sum_n, sum_nq, stats
+
+    def tree_vis_stats(self, root_i: int) -> dict:
+        n = C.c_int64()
+        assert self.lib.oracle_tree_vis_stats(int(root_i), None, None, None, 0, C.byref(n)) == 0
+        said, spid, cnt = (np.zeros(n.value, dtype=np.int64) for _ in range(3))
+        assert self.lib.oracle_tree_vis_stats(int(root_i), _ptr(said), _ptr(spid), _ptr(cnt), n.value, C.byref(n)) == 0
+        return {(int(a), int(b)): int(c) for a, b, c in zip(said, spid, cnt)}
 
     def root_action_vectors(self, first_root: int, n: int, action_doubles: int = abi.BOX_ACTION_DOUBLES) -> np.ndarray:
         out = np.zeros((int(n), int(action_doubles)), dtype=np.float64)

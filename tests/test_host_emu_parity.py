@@ -438,3 +438,31 @@ def test_emu_function_policy_is_a_table_on_the_device(emu_ctx, oracle, monkeypat
     assert np.array_equal(a1, a2) and np.array_equal(q1.view(np.int64), q2.view(np.int64))
     with pytest.raises(m.MCTSB200Error):  # a hashed-state model has no table to put it in
         m.build_cfg(m.MCTSSolver(estimate_value=m.RolloutEstimator(lambda s: 1.0)), MC)
+
+
+@pytest.mark.parametrize("mdp_name", ["gridworld", "mountaincar"])
+def test_emu_vis_stats_like_record_visit(emu_ctx, oracle, mdp_name):
+    """MCTSSolver(enable_tree_vis=true): tree._vis_stats[said => spid] counts every (action node, next state node) edge the search
+    walked (record_visit!, src/vanilla.jl:268-270, 328-334) -- what D3Tree(::MCTSTree) renders. Against the oracle, entry for entry;
+    the counts of an action node's edges add up to its visits."""
+    mdp, roots = (GW, gridworld_roots(12)) if mdp_name == "gridworld" else (MC, mountaincar_roots(6))
+    s = m.MCTSSolver(n_iterations=150, depth=12, exploration_constant=5.0, rng=9, enable_tree_vis=True)
+    _, _, _, st = run_both(emu_ctx, oracle, s, mdp, roots, compare_trees=range(0, len(roots), 3))
+    assert st.kernel_variant == 0  # the tile kernel records the edges
+    for i in range(0, len(roots), 3):
+        v1, v2 = emu_ctx.tree_vis_stats(i), oracle.tree_vis_stats(i)
+        assert v1 == v2 and len(v1) > 10
+        t = emu_ctx.tree_export(i, mdp.state_dtype, mdp.state_width)
+        per_action = {}
+        for (said, _spid), c in v1.items():
+            per_action[said] = per_action.get(said, 0) + c
+        for said, c in per_action.items():
+            assert c == t["n"][said - 1]  # init_N = 0: every visit of the action node walked one of its edges
+    # through the mirror: info[:tree]._vis_stats; without enable_tree_vis there is nothing to ask for
+    planner = m.solve(s, mdp, ctx=emu_ctx)
+    _, info = planner.action_info(roots[0])
+    assert sum(info["tree"]._vis_stats.values()) >= 150
+    planner2 = m.solve(m.MCTSSolver(n_iterations=20, depth=5), mdp, ctx=emu_ctx)
+    _, info2 = planner2.action_info(roots[0])
+    with pytest.raises(m.MCTSB200Error):
+        info2["tree"]._vis_stats
