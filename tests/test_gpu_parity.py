@@ -550,3 +550,17 @@ def test_box_actions_many_children_at_the_root(gpu_ctx, oracle):
     v, _, st = _run_box_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=5000, depth=6, exploration_constant=8.0, rng=2), steer, BOX_ROOTS[:3], trees=[0, 2])
     t = gpu_ctx.tree_export(0, np.float64, 4)
     assert t["child_offsets"][1] - t["child_offsets"][0] > 300
+
+
+@pytest.mark.parametrize("fast", ["1", "0"])
+def test_function_policy_is_a_table_on_the_device(gpu_ctx, oracle, monkeypatch, fast):
+    from test_host_emu_parity import test_emu_function_policy_is_a_table_on_the_device as body
+
+    body(gpu_ctx, oracle, monkeypatch, fast)
+
+
+@pytest.mark.parametrize("mdp_name", ["gridworld", "mountaincar"])
+def test_vis_stats_like_record_visit(gpu_ctx, oracle, mdp_name):
+    from test_host_emu_parity import test_emu_vis_stats_like_record_visit as body
+
+    body(gpu_ctx, oracle, mdp_name)
