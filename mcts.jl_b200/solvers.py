@@ -450,6 +450,19 @@ class MCTSPlanner(_Planner):
     def action(self, state):
         return self.action_info(state)[0]
 
+    def action_root_parallel(self, state, n_trees: int, tree_index_base: int = 0):
+        """Root-parallel decision for ONE root (BASELINE config 5; MCTSB200.jl: action_root_parallel): `n_trees` independent trees of
+        `solver.n_iterations` iterations each, their root statistics merged in integer arithmetic -- on a multi-device ctx
+        (`solve(..., device=[0, 1, ...])`) split over the devices and merged by one ncclAllReduce inside the library, with the same
+        result whatever the number of devices. Returns (action, {best_Q, q, sum_n})."""
+        cfg, keep = build_cfg(self.solver, self.mdp)
+        self.ctx.configure(self.mdp.mdp_id, self.mdp.params())
+        sn, snq, stats = self.ctx.plan_root_parallel(cfg, self.mdp.mdp_id, self.mdp.encode_states([state]), int(n_trees), tree_index_base)
+        a, bq, q = self.ctx.root_parallel_decide(sn, snq, float(cfg.init_Q))
+        del keep
+        self.last_stats = stats
+        return self._label(a), {"best_Q": bq, "q": q, "sum_n": sn}
+
     def value(self, state, a=None):
         """value(planner, s[, a]) (src/vanilla.jl:169-197)."""
         if self.tree is None:

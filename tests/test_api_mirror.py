@@ -217,3 +217,21 @@ def test_continuous_action_space_like_discussion_514(ctx):
     p2 = m.solve(m.DPWSolver(n_iterations=3000, depth=3, exploration_constant=20.0, rng=5), steer, ctx=ctx)
     a3 = p2.action((4.0, -4.0, 0.0))
     assert a3[0] < 0.0 < a3[1]
+
+
+def test_several_devices_behind_the_same_planner(emu_lib_path):
+    """MCTSB200.jl: `solve(B200(solver, [0, 1]), mdp)` -- a planner over several devices of one process (mctsb200_ctx_create_multi):
+    batch calls shard inside the library and return what one device returns; `action_root_parallel` merges the devices' trees.
+    (Two ctxs on the emulator's one device here; real devices in tests/test_gpu_parity.py::test_multi_device_ctx_equals_one_device.)"""
+    solver = m.MCTSSolver(n_iterations=60, depth=10, exploration_constant=5.0, rng=2)
+    one = m.solve(solver, GW, ctx=m.Context(0, lib_path=emu_lib_path))
+    two = m.solve(solver, GW, ctx=m.Context([0, 0], lib_path=emu_lib_path))
+    states = [(1 + i % 10, 1 + i // 10) for i in range(23)]
+    a1, i1 = one.action_info_batch(states)
+    a2, i2 = two.action_info_batch(states)
+    assert a1 == a2 and [x["best_Q"] for x in i1] == [x["best_Q"] for x in i2]
+    assert np.array_equal(i1[17]["tree"].q.view(np.int64), i2[17]["tree"].q.view(np.int64))  # tree 17 lives on the second device
+    r1, d1 = one.action_root_parallel((1, 1), 13)
+    r2, d2 = two.action_root_parallel((1, 1), 13)
+    assert r1 == r2 and d1["best_Q"] == d2["best_Q"] and np.array_equal(d1["sum_n"], d2["sum_n"])
+    assert np.array_equal(d1["q"].view(np.int64), d2["q"].view(np.int64))
