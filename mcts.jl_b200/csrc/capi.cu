@@ -1685,6 +1685,7 @@ int32_t check_tree_query(mctsb200_ctx* ctx, long long i) {
     if (!ctx) return fail(MCTSB200_ERR_INVALID_ARG, "ctx is NULL");
     if (!ctx->st.valid) return fail(MCTSB200_ERR_STATE, "no tree: call mctsb200_plan first");
     if (i < 0 || i >= ctx->st.n_trees) return fail(MCTSB200_ERR_INVALID_ARG, "root index %lld out of range [0,%lld)", i, ctx->st.n_trees);
+    CUDA_TRY(cudaSetDevice(ctx->device));                       // (a child of a multi-device ctx: its stream belongs to its own device)
     if (ctx->st.finalize_fn) return ctx->st.finalize_fn(ctx);  // first tree query after a plan call: write the export tables
     return MCTSB200_OK;
 }

@@ -268,3 +268,21 @@ def NoisyMountainCar(discount: float = 0.99, cost: float = -1.0, jackpot: float 
     return PluginMDP(name=name or f"NoisyMountainCar{state_width}x{len(actions)}", source=src, struct_name="NoisyMountainCar",
                      actions=tuple(float(a) for a in actions), params_struct=p, state_width=state_width, max_branch=0,
                      terminal=lambda s: s[0] >= 0.5, oracle_mdp_id=1000 if state_width == 2 else None)
+
+
+class InvertedPendulumParams(C.Structure):
+    """Params of plugins/inverted_pendulum.cuh."""
+
+    _fields_ = [("discount", C.c_double), ("g", C.c_double), ("m", C.c_double), ("l", C.c_double), ("M", C.c_double), ("alpha", C.c_double),
+                ("dt", C.c_double), ("cost", C.c_double), ("force", C.c_double * 3), ("noise", C.c_double)]
+
+
+def InvertedPendulum(g: float = 9.81, m: float = 2.0, l: float = 8.0, M: float = 8.0, dt: float = 0.1, discount: float = 0.99,
+                     cost: float = -1.0, noise: float = 10.0, name: str = "InvertedPendulum") -> PluginMDP:
+    """POMDPModels.InvertedPendulum (notebooks/Test_Visualization.ipynb cell 4) as a run-time plugin (plugins/inverted_pendulum.cuh):
+    state (theta, omega), actions (-50., 0., 50.), uniform force noise -- continuous stochastic transitions, max_branch = 0."""
+    p = InvertedPendulumParams(float(discount), float(g), float(m), float(l), float(M), 1.0 / (float(m) + float(M)), float(dt), float(cost))
+    p.force[0], p.force[1], p.force[2] = -50.0, 0.0, 50.0
+    p.noise = float(noise)
+    return PluginMDP.from_file("inverted_pendulum.cuh", name=name, struct_name="InvertedPendulum", actions=(-50.0, 0.0, 50.0), params_struct=p,
+                               state_width=2, max_branch=0, terminal=lambda s: abs(s[0]) > 1.5707963267948966, oracle_mdp_id=1001)

@@ -302,6 +302,44 @@ struct NoisyMountainCar {
     }
 };
 
+// POMDPModels.jl's InvertedPendulum as shipped in mcts.jl_b200/plugins/inverted_pendulum.cuh (the model of
+// notebooks/Test_Visualization.ipynb cell 4), registered at run time like NoisyMountainCar. Euler step, uniform force noise.
+struct InvertedPendulumParams {
+    double discount, g, m, l, M, alpha, dt, cost;
+    double force[3];
+    double noise;
+};
+constexpr int kOracleMdpInvertedPendulum = 1001;
+struct InvertedPendulum {
+    static constexpr int kMdpId = kOracleMdpInvertedPendulum;
+    static constexpr bool kLiteralTransitions = true;
+    using State = MCState;  // (theta, omega)
+    typedef int32_t Action;
+    static constexpr int kActionDoubles = 0;
+    Action next_action(const State& s, Stream& rng) const { return rng.uniform_int(n_actions(s)); }
+    static int32_t action_key(Action a) { return a; }
+    static constexpr int kActions = 3;
+    InvertedPendulumParams p;
+    explicit InvertedPendulum(const InvertedPendulumParams& q) : p(q) {}
+    double discount() const { return p.discount; }
+    int n_actions(const State&) const { return kActions; }
+    int max_actions() const { return kActions; }
+    bool isterminal(const State& s) const { return std::fabs(s.x) > 1.5707963267948966; }
+    int64_t state_index(const State&) const { return -1; }
+    int64_t n_states() const { return 0; }
+    void gen(const State& s, int ai, Stream& rng, State& sp, double& r) const {
+        const double th = s.x, w = s.v;
+        const double u = p.force[ai] + (rng.uniform01() - 0.5) * p.noise;
+        const double sn = det_sin(th), cs = o_cos(th), s2 = det_sin(2.0 * th);
+        const double aml = (p.alpha * p.m) * p.l;
+        const double num = (p.g * sn - ((aml * (w * w)) * s2) * 0.5) - (p.alpha * cs) * u;
+        const double den = (4.0 / 3.0) * p.l - (p.alpha * p.l) * (cs * cs);
+        const double acc = num / den;
+        sp = MCState{th + w * p.dt, w + acc * p.dt};
+        r = isterminal(sp) ? p.cost : 0.0;
+    }
+};
+
 // The continuous-action model of include/mctsb200.h (mctsb200_gaussian_box_params): the MDP of test/discussion_514.jl
 // (states / actions are Boxes, transition = MvNormal(s, Diagonal(var))) with an optional drift and quadratic cost. next_action is
 // RandomActionGenerator on a Box: rand(rng, actions(mdp, s)) = one uniform draw per coordinate (src/action_gen.jl:11-13).
@@ -427,8 +465,10 @@ struct Hooks {
             }
             case MCTSB200_POLICY_TABLE:  // FunctionPolicy(f) for a state-only f, tabulated over the dense state space
                 return cfg.policy_table[mdp.state_index(s)];
+            case MCTSB200_POLICY_PLUGIN:  // policy 100 of the shipped plugins
+                if constexpr (M::kMdpId == kOracleMdpInvertedPendulum) return (s.x + 0.3 * s.v) > 0.0 ? 2 : 0;  // push against the fall
+                return state_v(s) < 0.0 ? 0 : 2;                                                                    // (MountainCar family: as MC_ENERGY)
             case MCTSB200_POLICY_MC_ENERGY:
-            case MCTSB200_POLICY_PLUGIN:  // (policy 100 of the shipped plugins: the same heuristic)
                 return state_v(s) < 0.0 ? 0 : 2;
         }
         return 0;
@@ -1238,6 +1278,10 @@ int32_t oracle_plan(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* 
         return plan_batch<NoisyMountainCar, MCStateHash>(m, *cfg, (const MCState*)roots, n_roots, root_index_base, n_threads,
                                                          keep_trees != 0, literal_transitions != 0, same_root != 0, action_out, bestq_out,
                                                          status_out, stats);
+    } else if (mdp_id == kOracleMdpInvertedPendulum) {
+        InvertedPendulum m(*(const InvertedPendulumParams*)params);
+        return plan_batch<InvertedPendulum, MCStateHash>(m, *cfg, (const MCState*)roots, n_roots, root_index_base, n_threads, keep_trees != 0,
+                                                         literal_transitions != 0, same_root != 0, action_out, bestq_out, status_out, stats);
     } else if (mdp_id == MCTSB200_MDP_GAUSSIAN_BOX) {
         GaussianBox m(*(const mctsb200_gaussian_box_params*)params);
         return plan_batch<GaussianBox, BoxStateHash>(m, *cfg, (const BoxState*)roots, n_roots, root_index_base, n_threads, keep_trees != 0,

@@ -564,3 +564,16 @@ def test_vis_stats_like_record_visit(gpu_ctx, oracle, mdp_name):
     from test_host_emu_parity import test_emu_vis_stats_like_record_visit as body
 
     body(gpu_ctx, oracle, mdp_name)
+
+
+@pytest.mark.parametrize("lanes", [None, 4])
+def test_plugin_inverted_pendulum_bit_exact(gpu_ctx, oracle, lanes):
+    """POMDPModels.InvertedPendulum as a shipped run-time plugin (plugins/inverted_pendulum.cuh; det_sin + force noise), with the
+    solver of notebooks/Test_Visualization.ipynb cell 4: DPWSolver(depth=10, exploration_constant=10., alpha_state=1/8)."""
+    ip = m.InvertedPendulum()
+    rng = np.random.default_rng(4)
+    roots = [((u - 0.5) * 0.1, (v - 0.5) * 0.1) for u, v in rng.random((24, 2))]  # initialstate: uniform in [-0.05, 0.05]^2
+    s = m.DPWSolver(n_iterations=400, depth=10, exploration_constant=10.0, alpha_state=1 / 8, rng=4)
+    run_both(gpu_ctx, oracle, s, ip, roots, lanes=lanes, compare_trees=range(0, 24, 5), literal=True)
+    s2 = m.MCTSSolver(n_iterations=300, depth=10, exploration_constant=10.0, rng=4, estimate_value=m.RolloutEstimator(m.PluginPolicy(100), max_depth=30))
+    run_both(gpu_ctx, oracle, s2, ip, roots, lanes=lanes, compare_trees=range(0, 24, 5))

@@ -25,6 +25,9 @@ def test_shipped_plugins_compile_and_get_stable_ids():
     # every host shape (2 / 4 state doubles x 2..4 actions) compiles
     ids = {m.NoisyMountainCar(actions=acts, state_width=sw).mdp_id for sw in (2, 4) for acts in ((-1.0, 1.0), (-1.0, 0.0, 1.0), (-1.0, -0.5, 0.5, 1.0))}
     assert len(ids) == 6 and b in ids
+    # the InvertedPendulum of notebooks/Test_Visualization.ipynb cell 4 (det_sin, force noise) compiles too
+    ip = m.InvertedPendulum()
+    assert ip.mdp_id >= abi.MDP_PLUGIN_BASE and ip.mdp_id not in ids and ip.mdp_id != a
     lib = _lib()
     out = C.c_int32(-1)
     assert lib.mctsb200_mdp_lookup(mc.name.encode(), C.byref(out)) == abi.OK and out.value == a
