@@ -80,6 +80,7 @@ struct Storage {
     bool keep = false;    // the trees were built with reuse_tree / keep_tree and may be continued by the next plan call
     long long visits = 0; // upper bound of the visits any node of the kept trees has received so far
     double q_bound = 0;   // bound of |Q| in the kept trees (DevCfg::q_bound of the calls that built them)
+    double q_bound_tile = 0;
     int kind = 0, mdp_id = 0;
     long long n_trees = 0;
     Geometry geo{};
@@ -257,7 +258,7 @@ struct MdpAccess<MountainCarDev> {
     }
     static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p == MCTSB200_POLICY_MC_ENERGY; }
     static bool lockstep(const mctsb200_ctx*, const mctsb200_solver_cfg*) { return false; }
-    static double reward_bound(const mctsb200_ctx*) { return NAN; }
+    static double reward_bound(const mctsb200_ctx* c) { return std::fmax(std::fabs(c->mc_dev.cost), std::fabs(c->mc_dev.jackpot)); }  // max |reward(s, a, sp)|
 };
 template <>
 struct MdpAccess<GaussianBoxDev> {
@@ -554,6 +555,7 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
         const double geo = (g >= 0.0 && g < 1.0) ? std::min(H, 1.0 / (1.0 - g)) : (g == 1.0 ? H : NAN);
         d.q_bound = std::fmax(std::fabs(cfg->init_Q), MdpAccess<M>::reward_bound(ctx) * geo) * 1.0009765625;
         if (!std::isfinite(cfg->init_Q) || !std::isfinite(MdpAccess<M>::reward_bound(ctx) * geo)) d.q_bound = NAN;
+        d.q_bound_tile = (cfg->estimate_kind == MCTSB200_EST_ROLLOUT && !cfg->init_q_table) ? d.q_bound : NAN;
     }
     d.seed = cfg->seed;
     d.depth = cfg->depth;
@@ -864,7 +866,10 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     int32_t rc = build_dev_cfg<M>(ctx, cfg, dcfg, prior_visits);
     if (rc) return rc;
     const int fast = fast_variant<M, KIND>(ctx, cfg, prior_visits);
-    if (may_reuse) dcfg.q_bound = (std::isnan(st.q_bound) || std::isnan(dcfg.q_bound)) ? NAN : std::max(dcfg.q_bound, st.q_bound);
+    if (may_reuse) {
+        dcfg.q_bound = (std::isnan(st.q_bound) || std::isnan(dcfg.q_bound)) ? NAN : std::max(dcfg.q_bound, st.q_bound);
+        dcfg.q_bound_tile = (std::isnan(st.q_bound_tile) || std::isnan(dcfg.q_bound_tile)) ? NAN : std::max(dcfg.q_bound_tile, st.q_bound_tile);
+    }
     bool reused = false;
     rc = setup_storage<M>(ctx, cfg, n_trees, fast >= 0, &reused);
     if (rc) return rc;
@@ -1136,6 +1141,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     st.valid = true;
     // bound of the visit counts now in the trees: exact after a fast-kernel call, else one visit per backup
     st.q_bound = dcfg.q_bound;
+    st.q_bound_tile = dcfg.q_bound_tile;
     st.visits = fast >= 0 ? (long long)h_cnt[CNT_MAX_VISITS] : prior_visits + (long long)done * std::max(cfg->depth, 1);
     if (status_flags) *status_flags = (unsigned)h_cnt[CNT_STATUS_FLAGS];
     if (stats) {

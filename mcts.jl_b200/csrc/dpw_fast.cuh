@@ -141,13 +141,19 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                 // ---- descent: simulate(dpw, snode, d), one level per trip ------------------------------------
                 int cell = root, d = cfg.depth, top = 0;
                 bool leaf = false;
-                uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, wi = 0;  // stream 0: current block and the index of the next word
+                // stream 0: the block in b0..b3 and the index of the next word; a block is computed when one of its words is READ (a
+                // node that owns all four actions consumes its next_action draw unread: skip_word)
+                uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, wi = 0, wblk = 0xffffffffu;
                 auto next_word = [&]() -> uint32_t {
-                    if ((wi & 3u) == 0u) philox_block(seed, tree_index, (uint32_t)it, 0u, wi >> 2, b0, b1, b2, b3);
+                    if ((wi >> 2) != wblk) {
+                        wblk = wi >> 2;
+                        philox_block(seed, tree_index, (uint32_t)it, 0u, wblk, b0, b1, b2, b3);
+                    }
                     const uint32_t w = (wi & 2u) ? ((wi & 1u) ? b3 : b2) : ((wi & 1u) ? b1 : b0);
                     ++wi;
                     return w;
                 };
+                auto skip_word = [&]() { ++wi; };
                 FastChild k[A];
                 load_row(row_at(root), k);
                 for (;;) {
@@ -189,11 +195,15 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                     if (apw) {
                         // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action[len]
                         if (N >= cfg.nmin_action[nchild]) {
-                            const int act = (int)__umulhi(next_word(), (uint32_t)A);  // next_action(::RandomActionGenerator)
-                            bool present = false;
+                            if (nchild == A) {
+                                skip_word();  // next_action(::RandomActionGenerator) draws, but every action is a child already
+                            } else {
+                                const int act = (int)__umulhi(next_word(), (uint32_t)A);
+                                bool present = false;
 #pragma unroll
-                            for (int t = 0; t < A; ++t) present |= t < nchild && dpw_label(k[t].tag) == act;
-                            if (!present) add_child(act);  // check_repeat_action
+                                for (int t = 0; t < A; ++t) present |= t < nchild && dpw_label(k[t].tag) == act;
+                                if (!present) add_child(act);  // check_repeat_action
+                            }
                         }
                     } else if (nchild == 0) {
                         for (int act = 0; act < A; ++act) add_child(act);

@@ -612,14 +612,11 @@ struct Search {
     __device__ __forceinline__ int select_among(const Kids& k, int N, int nchild, bool dpw) {
         const double c = a.cfg.c;
         if (c == 0.0) return argmax_q(k, nchild);
-        int first_zero = kNone, n_max = 0;
+        int first_zero = kNone;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const int j = tile.lane + t * G;
-            if (j < nchild) {
-                if (k.n[t] == 0) first_zero = min(first_zero, j);
-                n_max = max(n_max, k.n[t]);
-            }
+            if (j < nchild && k.n[t] == 0) first_zero = min(first_zero, j);
         }
         first_zero = tile.min_int(first_zero);
         if (first_zero != kNone) {
@@ -627,19 +624,22 @@ struct Search {
             return select_exact(k, nchild, N, true);
         }
         if (dpw && N <= 1) return argmax_q(k, nchild);  // log(N) <= 0 with every n > 0: the exploration term is exactly 0
-        n_max = -tile.min_int(-n_max);
-        if (N >= a.cfg.log_tab_n || n_max >= a.cfg.rsqrt_tab_n) return select_exact(k, nchild, N, dpw);
+        // (total_n is the sum of its children's n -- both start from init_N and grow together -- so N bounds every index below)
+        if (N >= a.cfg.log_tab_n) return select_exact(k, nchild, N, dpw);
 
         const double cs = (s_cs && N < kTileTab) ? s_cs[N] : DM_MUL(c, __ldg(a.cfg.sqrtlog_tab + N));
         double best = -CUDART_INF, second = -CUDART_INF, mag = 0.0;
         int best_i = kNone;
+        // the margin: 2^-44 * sum(|q_j| + term_j) <= 2^-42 * (Q bound + c sqrt(log N)) for up to four children (1/sqrt(n) <= 1), known
+        // before the children's terms are; without a bound of |Q| it is summed from the children
+        const bool have_bound = A <= 4 && a.cfg.q_bound_tile == a.cfg.q_bound_tile;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const int j = tile.lane + t * G;
             if (j < nchild) {
                 const double term = DM_MUL(cs, (s_rs && k.n[t] < kTileTab) ? s_rs[k.n[t]] : __ldg(a.cfg.rsqrt_tab + k.n[t]));
                 const double S = DM_ADD(k.q[t], term);
-                mag = DM_ADD(mag, DM_ADD(fabs(k.q[t]), term));
+                if (!have_bound) mag = DM_ADD(mag, DM_ADD(fabs(k.q[t]), term));
                 if (S > best) {
                     second = best;
                     best = S;
@@ -654,9 +654,10 @@ struct Search {
             tile.argmax(best, best_i);
             const bool mine = best_i != kNone && (best_i % G) == tile.lane;  // the winner is one of this lane's children
             second = tile.max_double(mine ? second : lane_best);
-            mag = tile.sum_double(mag);
+            if (!have_bound) mag = tile.sum_double(mag);
         }
-        const double margin = DM_MUL(5.6843418860808015e-14, mag);  // 2^-44 * sum(|q| + term); NaN if any input is
+        const double margin = have_bound ? DM_MUL(2.2737367544323206e-13, DM_ADD(a.cfg.q_bound_tile, fabs(cs)))
+                                         : DM_MUL(5.6843418860808015e-14, mag);  // (NaN if any input is: the near-tie path decides)
         if (best_i != kNone && DM_SUB(best, second) > margin) return best_i;
         const int r = select_near_tie(tile, &a.cfg, k, nchild, N, dpw, cs, margin);
         if ((r & 256) && lead()) cnt[CNT_SELECT_EXACT] += 1;
@@ -855,15 +856,21 @@ struct Search {
 #else
                 if (R.total_n >= a.cfg.nmin_action[nchild]) {
 #endif
-                    const int act = rng.uniform_int(A);  // next_action(::RandomActionGenerator)
-                    bool present = false;
-                    const uint32_t pk = R.packed;
+                    // next_action(::RandomActionGenerator) always draws; a node that owns every action cannot gain one (check_repeat_action
+                    // is always on here, see capi.cu), so the word is consumed unread
+                    if (nchild == A) {
+                        rng.skip();
+                    } else {
+                        const int act = rng.uniform_int(A);
+                        bool present = false;
+                        const uint32_t pk = R.packed;
 #pragma unroll
-                    for (int j = 0; j < A; ++j) present |= (j < nchild) & ((int)((pk >> (4 * j)) & 15u) == act);
-                    if (!present) {  // check_repeat_action (always on; see capi.cu)
-                        dpw_insert_action(node, nchild, s, act, R, X);
-                        ++nchild;
-                        tile.sync();
+                        for (int j = 0; j < A; ++j) present |= (j < nchild) & ((int)((pk >> (4 * j)) & 15u) == act);
+                        if (!present) {
+                            dpw_insert_action(node, nchild, s, act, R, X);
+                            ++nchild;
+                            tile.sync();
+                        }
                     }
                 }
             } else if (nchild == 0) {
