@@ -229,7 +229,8 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
  * mctsb200_last_error(). Needs no GPU (the cubin is loaded at the first plan call). The id is process-wide; every ctx
  * configures its own parameters with mctsb200_mdp_configure(ctx, id, &Params, sizeof(Params)). Registering the same
  * name again with a different definition replaces it (same id). mctsb200_mdp_lookup / mctsb200_mdp_info know the id.
- * Plugin MDPs run on the tile kernel: hashed states, so no dense tables (init_q_table, value_table) and no keep_tree. */
+ * Plugin MDPs run on the tile kernel: hashed states, so no dense tables (init_q_table, value_table, policy_table); kept trees get
+ * room for keep_tree_calls calls. */
 int32_t mctsb200_mdp_register(const char* name, const char* cuda_source, const char* plugin_struct, int32_t state_doubles,
                               int32_t n_actions, int32_t max_branch, int32_t* mdp_id_out);
 /* Compiled plugin programs are cached on disk, keyed by a hash of the generated program, the library's kernel sources, the compiler

@@ -39,8 +39,8 @@ struct Stream {
     uint32_t k0, k1;
     uint32_t c0, c1, c2, c3;
     uint32_t b0, b1, b2, b3;
-    uint32_t pos;  // words consumed so far
-    uint32_t blk;  // the block whose words are in b0..b3 (0xffffffff = none yet)
+    int have;  // unread words of the current block, kept at the front: b0 is the next one
+    int pend;  // words consumed unread since the last block ran out (skip): their blocks are never computed
 
     __host__ __device__ __forceinline__ void init(uint64_t seed, uint64_t tree, uint32_t iteration, uint32_t stream_id) {
         k0 = (uint32_t)seed;
@@ -49,8 +49,8 @@ struct Stream {
         c1 = iteration;
         c2 = (uint32_t)tree;
         c3 = (uint32_t)(((tree >> 32) & 0xffffu) << 16) | (stream_id & 0xffffu);
-        pos = 0;
-        blk = 0xffffffffu;
+        have = 0;
+        pend = 0;
     }
     __host__ __device__ __forceinline__ void refill() {
         uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, ka = k0, kb = k1;
@@ -72,22 +72,39 @@ struct Stream {
         }
         b0 = x0; b1 = x1; b2 = x2; b3 = x3;
         c0 += 1;
+        have = 4;
     }
-    // word `pos` of the stream: block pos / 4 is computed when the first of its words is READ
     __host__ __device__ __forceinline__ uint32_t next() {
-        const uint32_t want = pos >> 2, j = pos & 3u;
-        if (want != blk) {
-            c0 = want;
-            refill();
-            blk = want;
+        if (have == 0) {
+            if (pend) {  // words skipped at a block boundary: jump over their whole blocks, drop the rest from the front of this one
+                c0 += (uint32_t)pend >> 2;
+                const int drop = pend & 3;
+                pend = 0;
+                refill();
+                if (drop >= 1) { b0 = b1; b1 = b2; b2 = b3; }
+                if (drop >= 2) { b0 = b1; b1 = b2; }
+                if (drop >= 3) { b0 = b1; }
+                have -= drop;
+            } else {
+                refill();
+            }
         }
-        ++pos;
-        return j == 0 ? b0 : j == 1 ? b1 : j == 2 ? b2 : b3;
+        const uint32_t w = b0;
+        b0 = b1; b1 = b2; b2 = b3;
+        --have;
+        return w;
     }
     // Consumes one word without looking at it. A counter-based stream makes that free: no block is computed for words nobody
     // reads. (A DPW level whose state node already owns every action still draws next_action, src/dpw.jl:96, but the draw cannot
     // change anything: the level walks on without the ten Philox rounds and later levels find the stream where the reference's is.)
-    __host__ __device__ __forceinline__ void skip() { ++pos; }
+    __host__ __device__ __forceinline__ void skip() {
+        if (have > 0) {
+            b0 = b1; b1 = b2; b2 = b3;
+            --have;
+        } else {
+            ++pend;
+        }
+    }
     __host__ __device__ __forceinline__ int uniform_int(int n) {
 #if defined(__CUDA_ARCH__)
         return (int)__umulhi(next(), (uint32_t)n);

@@ -632,7 +632,10 @@ struct Search {
         int best_i = kNone;
         // the margin: 2^-44 * sum(|q_j| + term_j) <= 2^-42 * (Q bound + c sqrt(log N)) for up to four children (1/sqrt(n) <= 1), known
         // before the children's terms are; without a bound of |Q| it is summed from the children
-        const bool have_bound = A <= 4 && a.cfg.q_bound_tile == a.cfg.q_bound_tile;
+#ifndef MCTSB200_TILE_QBOUND
+#define MCTSB200_TILE_QBOUND 1
+#endif
+        const bool have_bound = MCTSB200_TILE_QBOUND && A <= 4 && a.cfg.q_bound_tile == a.cfg.q_bound_tile;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const int j = tile.lane + t * G;

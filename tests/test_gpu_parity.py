@@ -352,7 +352,16 @@ def test_plugin_needs_configure_and_refuses_dense_options(gpu_ctx):
     assert e.value.status == m.abi.ERR_STATE
     gpu_ctx.configure(mdp.mdp_id, mdp.params())
     gpu_ctx.plan(cfg, mdp.mdp_id, mdp.encode_states([(-0.5, 0.0)]))
+    # kept trees work for hashed-state plugins (bounded room, see test_kept_trees_of_hashed_models_follow_their_episodes); what
+    # needs a dense state index does not
     cfg.keep_tree = 1
+    gpu_ctx.plan(cfg, mdp.mdp_id, mdp.encode_states([(-0.5, 0.0)]))
+    gpu_ctx.clear_trees()
+    cfg.keep_tree = 0
+    tab = np.zeros(3, dtype=np.float64)
+    import ctypes as C
+
+    cfg.init_q_table = tab.ctypes.data_as(C.POINTER(C.c_double))
     with pytest.raises(m.MCTSB200Error) as e:
         gpu_ctx.plan(cfg, mdp.mdp_id, mdp.encode_states([(-0.5, 0.0)]))
     assert e.value.status == m.abi.ERR_UNSUPPORTED
