@@ -917,7 +917,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.vis_branch = st.vis_branch;
     // (measured on B200, profiles/r2b_*: 4 % SLOWER on config 2, 1 % on config 3 -- the rows that miss L2 are not what the
     // levels wait for; kept as a switch for the record)
-    args.prefetch_l2 = env_enabled("MCTSB200_PREFETCH_L2", false) ? 1 : 0;
+    args.prefetch_l2 = env_enabled("MCTSB200_PREFETCH_L2", false) ? std::max(1, std::atoi(std::getenv("MCTSB200_PREFETCH_L2"))) : 0;
 
     const int G = fast >= 0 ? 1 : pick_lanes<M, KIND>(ctx, cfg, n_trees);
     const int n_iter = (int)cfg->n_iterations;

@@ -633,7 +633,7 @@ struct Search {
         // the margin: 2^-44 * sum(|q_j| + term_j) <= 2^-42 * (Q bound + c sqrt(log N)) for up to four children (1/sqrt(n) <= 1), known
         // before the children's terms are; without a bound of |Q| it is summed from the children
 #ifndef MCTSB200_TILE_QBOUND
-#define MCTSB200_TILE_QBOUND 1
+#define MCTSB200_TILE_QBOUND 0  // (measured on B200, profiles/r2k_*: the bound-based margin is 2 % SLOWER on config 4 than summing it)
 #endif
         const bool have_bound = MCTSB200_TILE_QBOUND && A <= 4 && a.cfg.q_bound_tile == a.cfg.q_bound_tile;
 #pragma unroll

@@ -86,8 +86,13 @@ __device__ __forceinline__ void load_row(const FastRow* rw, FastChild (&k)[4]) {
     for (int j = 0; j < 4; ++j) k[j] = rw->c[j];
 #else
     unsigned long long a0, a1, a2, a3, b0, b1, b2, b3;
+#ifdef MCTSB200_ROW_CG  // (experiment: rows bypass L1)
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(rw) : "memory");
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b0), "=l"(b1), "=l"(b2), "=l"(b3) : "l"(&rw->c[2]) : "memory");
+#else
     asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3) : "l"(rw) : "memory");
     asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(b0), "=l"(b1), "=l"(b2), "=l"(b3) : "l"(&rw->c[2]) : "memory");
+#endif
     k[0].q = __longlong_as_double((long long)a0); k[0].n = (int)(uint32_t)a1; k[0].tag = (uint32_t)(a1 >> 32);
     k[1].q = __longlong_as_double((long long)a2); k[1].n = (int)(uint32_t)a3; k[1].tag = (uint32_t)(a3 >> 32);
     k[2].q = __longlong_as_double((long long)b0); k[2].n = (int)(uint32_t)b1; k[2].tag = (uint32_t)(b1 >> 32);
@@ -233,7 +238,11 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) uct_fast_kernel(const __gr
                     // grid neighbours: their rows are asked for now, a whole level before one of them is loaded.
                     if (!AHEAD && args.prefetch_l2) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) prefetch_l2(row_at(M::fast_neighbour(args.mdp, cell, j)));
+                        for (int j = 0; j < 4; ++j) {
+                            const FastRow* nb = row_at(M::fast_neighbour(args.mdp, cell, j));
+                            prefetch_l2(nb);
+                            if (args.prefetch_l2 > 1) prefetch_l2(&nb->c[2]);  // (the row's second 32-byte sector)
+                        }
                     }
                     uint32_t w = 0;
                     if (!DET) {
