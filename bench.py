@@ -56,7 +56,7 @@ def config_of(name, n_roots, world):
     return {
         "workload": name, "roots_per_gpu": int(n_roots), "n_iterations": int(kw["n_iterations"]), "depth": int(kw["depth"]),
         "exploration_constant": float(kw.get("exploration_constant", 1.0)), "rollout_max_depth": 50, "rollout_policy": w["policy"],
-        "mdp": {"gw": "SimpleGridWorld", "mc": "MountainCar", "mc-plugin": "MountainCar (run-time plugin)", "noisy-plugin": "NoisyMountainCar (run-time plugin)"}[w["mdp"]],
+        "mdp": {"gw": "SimpleGridWorld", "mc": "MountainCar", "mc-plugin": "MountainCar (run-time plugin)", "noisy-plugin": "NoisyMountainCar (run-time plugin)", "box": "GaussianBox (continuous actions)"}[w["mdp"]],
         "mdp_params": {k: v for k, v in w["mdp_kw"].items()}, "solver": "MCTSSolver" if w["kind"] == "uct" else "DPWSolver",
         "sharding": f"roots x{world} (rank r plans global roots [r*{n_roots}, (r+1)*{n_roots}))",
         "l2": "node tables of all trees are larger than L2 and rebuilt from zero every step (no flush needed)",

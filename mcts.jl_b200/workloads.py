@@ -37,6 +37,10 @@ WORKLOADS = {
                                            solver_kw=dict(n_iterations=10000, depth=50), n_roots=1024),
     "config4-dpw-noisy-mountaincar-plugin": dict(mdp="noisy-plugin", mdp_kw=dict(), kind="dpw", policy="random",
                                                  solver_kw=dict(n_iterations=10000, depth=50), n_roots=1024),
+    # (not a BASELINE config) DPW over a continuous action space (test/discussion_514.jl's model with drift and cost): hundreds of action
+    # nodes under a state node, the case where a tile of lanes per tree pays (children scans)
+    "box-dpw-continuous-actions": dict(mdp="box", mdp_kw=dict(drift=0.3, cost=0.5), kind="dpw", policy="random",
+                                       solver_kw=dict(n_iterations=4000, depth=6, exploration_constant=8.0), n_roots=4096),
     # config 5's trees: one GridWorld root, default model, random rollouts (the README solver)
     "config5-root-parallel-uct-gridworld": dict(mdp="gw", mdp_kw=dict(tprob=0.7), kind="uct", policy="random",
                                                 solver_kw=dict(n_iterations=1056, depth=20, exploration_constant=5.0), n_roots=9472),
@@ -66,12 +70,12 @@ def mountaincar_roots(n: int, seed: int = 0):
 
 def make_workload(name, n_roots=None, lanes=0, n_iterations=None, same_root=None):
     """-> (mdp, solver, roots as the C-contiguous array the ABI takes)."""
-    from . import (ConstantPolicy, DPWSolver, MCTSSolver, MountainCar, MountainCarPlugin, NoisyMountainCar, RandomSolver, RolloutEstimator,
-                   SimpleGridWorld)
+    from . import (ConstantPolicy, DPWSolver, GaussianBox, MCTSSolver, MountainCar, MountainCarPlugin, NoisyMountainCar, RandomSolver,
+                   RolloutEstimator, SimpleGridWorld)
 
     w = WORKLOADS[name]
     n = n_roots or w["n_roots"]
-    mdp = {"gw": SimpleGridWorld, "mc": MountainCar, "mc-plugin": MountainCarPlugin, "noisy-plugin": NoisyMountainCar}[w["mdp"]](**w["mdp_kw"])
+    mdp = {"gw": SimpleGridWorld, "mc": MountainCar, "mc-plugin": MountainCarPlugin, "noisy-plugin": NoisyMountainCar, "box": GaussianBox}[w["mdp"]](**w["mdp_kw"])
     pol = {"up": ConstantPolicy("up"), "random": RandomSolver()}[w["policy"]]
     kw = dict(w["solver_kw"])
     if n_iterations:
@@ -79,7 +83,11 @@ def make_workload(name, n_roots=None, lanes=0, n_iterations=None, same_root=None
     kw["estimate_value"] = RolloutEstimator(pol, max_depth=50)
     kw["lanes_per_tree"] = lanes
     solver = (MCTSSolver if w["kind"] == "uct" else DPWSolver)(rng=0, **kw)
-    roots = gridworld_roots(n) if w["mdp"] == "gw" else mountaincar_roots(n)
+    if w["mdp"] == "box":
+        rng = np.random.default_rng(0)
+        roots = [tuple(float(x) for x in r) for r in rng.uniform(-4.0, 4.0, (n, 3))]
+    else:
+        roots = gridworld_roots(n) if w["mdp"] == "gw" else mountaincar_roots(n)
     if same_root:  # every tree plans from the same root state
         roots = [tuple(int(v) for v in same_root.split(","))] * n if isinstance(same_root, str) else [tuple(same_root)] * n
     return mdp, solver, mdp.encode_states(roots)
