@@ -233,6 +233,15 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
  * room for keep_tree_calls calls. */
 int32_t mctsb200_mdp_register(const char* name, const char* cuda_source, const char* plugin_struct, int32_t state_doubles,
                               int32_t n_actions, int32_t max_branch, int32_t* mdp_id_out);
+/* The same for a CONTINUOUS action space (actions(mdp) = a Box of `action_doubles` float64 coordinates, 1 or 2; the reference's
+ * test/discussion_514.jl with a model of the caller's own): the struct defines is_terminal, next_action (the action DPW's action
+ * widening proposes: next_action(gen, mdp, s, snode), src/dpw.jl:98 -- for the default RandomActionGenerator a draw from the Box,
+ * src/action_gen.jl:11-13), gen(params, s, a, rng, sp, r) with `a` the action vector, and policy_action for rollout policies
+ * >= MCTSB200_POLICY_PLUGIN (mcts.jl_b200/csrc/custom.cuh). Successors are unbounded (max_branch = 0). Such a model plans like
+ * MCTSB200_MDP_GAUSSIAN_BOX: DPW with action widening only, actions come back through mctsb200_root_action_vectors and
+ * tree_buffers.a_label_vectors, mctsb200_mdp_info reports n_actions = 0. The DPW program is compiled at registration. */
+int32_t mctsb200_mdp_register_continuous(const char* name, const char* cuda_source, const char* plugin_struct, int32_t state_doubles,
+                                         int32_t action_doubles, int32_t* mdp_id_out);
 /* Compiled plugin programs are cached on disk, keyed by a hash of the generated program, the library's kernel sources, the compiler
  * options and the CUDA version ($MCTSB200_CACHE_DIR, default ~/.cache/mctsb200; MCTSB200_CACHE=0 disables): a later process
  * registers a known plugin without running the compiler. Counts for this process: programs read from the cache / compiled. */
@@ -349,7 +358,8 @@ int32_t mctsb200_clear_trees(mctsb200_ctx* ctx); /* clear_tree! (src/vanilla.jl:
  * sorted by (said, spid), ids 1-based. Two-call pattern: NULL arrays return the count in n_out. */
 int32_t mctsb200_tree_vis_stats(mctsb200_ctx* ctx, int64_t root_i, int64_t* said, int64_t* spid, int64_t* count, int64_t capacity, int64_t* n_out);
 /* Continuous action spaces: the action best_sanode chose for roots [first_root, first_root + n) of the last plan call, as vectors
- * (n * action_doubles float64; the action_idx_out of mctsb200_plan then holds the chosen child's position among the root's
+ * (n * action_doubles float64 -- MCTSB200_BOX_ACTION_DOUBLES for the built-in model, what a plugin was registered with, also
+ * reported by mctsb200_tree_sizes.action_doubles; the action_idx_out of mctsb200_plan then holds the chosen child's position among the root's
  * children, -1 if it has none). a_labels[sanode] of src/dpw.jl:65. */
 int32_t mctsb200_root_action_vectors(mctsb200_ctx* ctx, int64_t first_root, int64_t n, double* out);
 

@@ -15,13 +15,13 @@ Layout:
 """
 from . import _abi as abi
 from ._lib import Context, MCTSB200Error, build_library, load_library, register_mdp
-from .models import GaussianBox, GWPos, InvertedPendulum, MountainCar, MountainCarPlugin, NoisyMountainCar, PluginMDP, SimpleGridWorld
+from .models import ContinuousPendulum, GaussianBox, GWPos, InvertedPendulum, MountainCar, MountainCarPlugin, NoisyMountainCar, PluginMDP, SimpleGridWorld
 from .solvers import (ConstantPolicy, DPWPlanner, DPWSolver, EnergyPolicy, ExceptionRethrow, FunctionPolicy, MCTSPlanner, MCTSSolver, PluginPolicy,
                       RandomPolicy, RandomSolver, RolloutEstimator, RolloutSimulator, SeekTarget, build_cfg, clear_tree, ranked_actions,
                       simulate, simulate_batch, solve)
 
 __all__ = [
-    "abi", "Context", "MCTSB200Error", "build_library", "load_library", "GaussianBox", "GWPos", "InvertedPendulum", "MountainCar", "SimpleGridWorld", "register_mdp", "PluginMDP", "MountainCarPlugin", "NoisyMountainCar", "PluginPolicy",
+    "abi", "Context", "MCTSB200Error", "build_library", "load_library", "ContinuousPendulum", "GaussianBox", "GWPos", "InvertedPendulum", "MountainCar", "SimpleGridWorld", "register_mdp", "PluginMDP", "MountainCarPlugin", "NoisyMountainCar", "PluginPolicy",
     "ConstantPolicy", "FunctionPolicy", "DPWPlanner", "DPWSolver", "EnergyPolicy", "ExceptionRethrow", "MCTSPlanner", "MCTSSolver",
     "RandomPolicy", "RandomSolver", "RolloutEstimator", "RolloutSimulator", "SeekTarget", "build_cfg", "clear_tree", "ranked_actions",
     "simulate", "simulate_batch", "solve",

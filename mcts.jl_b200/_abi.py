@@ -186,6 +186,7 @@ EXPORTED_SYMBOLS = (
     "mctsb200_mdp_info",
     "mctsb200_mdp_configure",
     "mctsb200_mdp_register",
+    "mctsb200_mdp_register_continuous",
     "mctsb200_plugin_cache_stats",
     "mctsb200_plan",
     "mctsb200_plan_device",
@@ -230,6 +231,7 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.mctsb200_mdp_info.argtypes = [i32, P(i32), P(i64)]
     lib.mctsb200_mdp_configure.argtypes = [vp, i32, vp, sz]
     lib.mctsb200_mdp_register.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, i32, P(i32)]
+    lib.mctsb200_mdp_register_continuous.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, P(i32)]
     lib.mctsb200_plugin_cache_stats.argtypes = [P(i64), P(i64)]
     lib.mctsb200_plan.argtypes = [vp, P(SolverCfg), i32, vp, i64, sz, i64, vp, vp, vp, P(PlanStats)]
     lib.mctsb200_plan_device.argtypes = [vp, P(SolverCfg), i32, vp, i64, sz, i64, vp, vp, vp, P(PlanStats)]

@@ -79,6 +79,19 @@ def register_mdp(name: str, cuda_source: str, plugin_struct: str, state_doubles:
     return out.value
 
 
+def register_mdp_continuous(name: str, cuda_source: str, plugin_struct: str, state_doubles: int, action_doubles: int,
+                            lib_path: Optional[str] = None) -> int:
+    """mctsb200_mdp_register_continuous: the same for a plugin whose actions are vectors of `action_doubles` float64 values
+    (actions(mdp) = a Box); its DPW program is compiled here."""
+    lib = load_library(lib_path)
+    out = C.c_int32(-1)
+    rc = lib.mctsb200_mdp_register_continuous(name.encode(), cuda_source.encode(), plugin_struct.encode(), int(state_doubles), int(action_doubles),
+                                              C.byref(out))
+    if rc != abi.OK:
+        raise MCTSB200Error(rc, lib.mctsb200_last_error().decode("utf-8", "replace"))
+    return out.value
+
+
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

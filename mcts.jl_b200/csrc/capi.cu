@@ -91,6 +91,7 @@ struct Storage {
     DevBuf vis;         // _vis_stats edges of vanilla trees planned with enable_tree_vis
     int vis_branch = 0;
     DevBuf action_vec;  // the decisions' action vectors of the last plan call (continuous action spaces)
+    int action_doubles = 0;  // ... and their width (0: the last plan call had a finite action set)
     DevBuf rows_fast;   // working table of uct_fast.cuh / dpw_fast.cuh (interleaved); `rows` receives the Row<M> table after the search
     DevBuf trans_fast;  // dpw_fast.cuh: per-slot transition multisets (interleaved)
     // the fast kernels' tables are converted to Row / Aux / TransRec only when a tree query needs them
@@ -294,6 +295,26 @@ struct MdpAccess<CustomDev<SD, A>> {
         return 0;
     }
     static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p == MCTSB200_POLICY_CONSTANT || p >= MCTSB200_POLICY_PLUGIN; }
+    static bool lockstep(const mctsb200_ctx*, const mctsb200_solver_cfg*) { return false; }
+    static double reward_bound(const mctsb200_ctx*) { return NAN; }
+};
+// ... with a continuous action space (mctsb200_mdp_register_continuous)
+template <int SD, int AD>
+struct MdpAccess<CustomBoxDev<SD, AD>> {
+    using M = CustomBoxDev<SD, AD>;
+    static bool ready(const mctsb200_ctx* c) { return c->plugin_params.count(c->cur_plugin) != 0; }
+    static int mdp_id(const mctsb200_ctx* c) { return MCTSB200_MDP_PLUGIN_BASE + c->cur_plugin; }
+    static long long max_branch(const mctsb200_ctx*) { return 1LL << 30; }
+    static const typename M::Params& params(const mctsb200_ctx* c) {
+        return *reinterpret_cast<const typename M::Params*>(c->plugin_params.find(c->cur_plugin)->second.bytes);
+    }
+    static int dense_count(const mctsb200_ctx*) { return 0; }
+    static int32_t check_root(const mctsb200_ctx*, const typename M::AbiState& s) {
+        for (int i = 0; i < SD; ++i)
+            if (!std::isfinite(s.v[i])) return -1;
+        return 0;
+    }
+    static bool policy_ok(int p) { return p == MCTSB200_POLICY_RANDOM || p >= MCTSB200_POLICY_PLUGIN; }
     static bool lockstep(const mctsb200_ctx*, const mctsb200_solver_cfg*) { return false; }
     static double reward_bound(const mctsb200_ctx*) { return NAN; }
 };
@@ -901,6 +922,7 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
     args.aux = (KIND == MCTSB200_KIND_DPW || (!M::kDense && MdpAccess<M>::max_branch(ctx) == 1 && env_enabled("MCTSB200_SUCC_CACHE"))) ? (Aux<M>*)st.aux.p : nullptr;
     args.trans = KIND == MCTSB200_KIND_DPW ? (TransRec*)st.trans.p : nullptr;
     args.plog = (KIND == MCTSB200_KIND_DPW && st.geo.NP > 0) ? (int*)st.plog.p : nullptr;
+    st.action_doubles = M::kActionDoubles;
     if constexpr (M::kActionDoubles > 0) {
         args.anodes = (BoxANode*)st.anodes.p;
         CUDA_TRY(st.action_vec.ensure(sizeof(double) * M::kActionDoubles * (size_t)n_trees));
@@ -1856,14 +1878,23 @@ using Custom24 = CustomDev<2, 4>;
 using Custom42 = CustomDev<4, 2>;
 using Custom43 = CustomDev<4, 3>;
 using Custom44 = CustomDev<4, 4>;
+using CustomBox21 = CustomBoxDev<2, 1>;
+using CustomBox22 = CustomBoxDev<2, 2>;
+using CustomBox41 = CustomBoxDev<4, 1>;
+using CustomBox42 = CustomBoxDev<4, 2>;
 bool plugin_shape_ok(int sd, int a) { return (sd == 2 || sd == 4) && a >= 2 && a <= 4; }
+bool plugin_box_shape_ok(int sd, int ad) { return (sd == 2 || sd == 4) && (ad == 1 || ad == 2); }
 #define MCTSB200_FOR_PLUGIN(ctx, mdp_id, CALL)                                                              \
     if ((mdp_id) >= MCTSB200_MDP_PLUGIN_BASE) {                                                             \
         const mctsb200_rt::PluginInfo* pi__ = mctsb200_rt::plugin_info((mdp_id) - MCTSB200_MDP_PLUGIN_BASE); \
         if (pi__) {                                                                                         \
             (ctx)->cur_plugin = (mdp_id) - MCTSB200_MDP_PLUGIN_BASE;                                        \
             (ctx)->cur_max_branch = pi__->max_branch;                                                       \
-            switch (pi__->state_doubles * 10 + pi__->n_actions) {                                           \
+            switch (pi__->action_doubles * 100 + pi__->state_doubles * 10 + pi__->n_actions) {              \
+                case 120: return CALL(CustomBox21);                                                         \
+                case 220: return CALL(CustomBox22);                                                         \
+                case 140: return CALL(CustomBox41);                                                         \
+                case 240: return CALL(CustomBox42);                                                         \
                 case 22: return CALL(Custom22);                                                             \
                 case 23: return CALL(Custom23);                                                             \
                 case 24: return CALL(Custom24);                                                             \
@@ -2099,6 +2130,36 @@ int32_t mctsb200_mdp_register(const char* name, const char* cuda_source, const c
     const int idx = mctsb200_rt::register_plugin(info, err);
     if (idx < 0) {
         g_err = err;  // (compiler logs are longer than fail()'s buffer)
+        return MCTSB200_ERR_INVALID_ARG;
+    }
+    *mdp_id_out = MCTSB200_MDP_PLUGIN_BASE + idx;
+    return MCTSB200_OK;
+#endif
+}
+
+int32_t mctsb200_mdp_register_continuous(const char* name, const char* cuda_source, const char* plugin_struct, int32_t state_doubles,
+                                         int32_t action_doubles, int32_t* mdp_id_out) {
+#ifdef MCTSB200_HOST_EMU
+    return fail(MCTSB200_ERR_UNSUPPORTED, "plugins are compiled for the device only");
+#else
+    if (!name || !name[0] || !cuda_source || !plugin_struct || !plugin_struct[0] || !mdp_id_out) return fail(MCTSB200_ERR_INVALID_ARG, "NULL or empty argument");
+    if (!std::strcmp(name, "SimpleGridWorld") || !std::strcmp(name, "MountainCar") || !std::strcmp(name, "GaussianBox"))
+        return fail(MCTSB200_ERR_INVALID_ARG, "'%s' is a built-in MDP", name);
+    if (!plugin_box_shape_ok(state_doubles, action_doubles))
+        return fail(MCTSB200_ERR_UNSUPPORTED, "plugin shape (%d state doubles, %d action doubles) is not available: state_doubles 2 or 4, action_doubles 1 or 2",
+                    state_doubles, action_doubles);
+    mctsb200_rt::PluginInfo info;
+    info.name = name;
+    info.source = cuda_source;
+    info.struct_name = plugin_struct;
+    info.state_doubles = state_doubles;
+    info.n_actions = 0;
+    info.max_branch = 0;
+    info.action_doubles = action_doubles;
+    std::string err;
+    const int idx = mctsb200_rt::register_plugin(info, err);
+    if (idx < 0) {
+        g_err = err;
         return MCTSB200_ERR_INVALID_ARG;
     }
     *mdp_id_out = MCTSB200_MDP_PLUGIN_BASE + idx;
@@ -2438,16 +2499,17 @@ int32_t mctsb200_root_action_vectors(mctsb200_ctx* ctx, int64_t first_root, int6
             long long local = 0;
             if (int32_t e = group_locate(ctx, first_root + i, &kid, &local)) return e;
             const long long m = std::min<long long>(n - i, kid->st.n_trees - local);
-            if (int32_t e = mctsb200_root_action_vectors(kid, local, m, out + i * MCTSB200_BOX_ACTION_DOUBLES)) return e;
+            if (int32_t e = mctsb200_root_action_vectors(kid, local, m, out + i * kid->st.action_doubles)) return e;
             i += m;
         }
         return MCTSB200_OK;
     }
     if (!ctx->st.valid) return fail(MCTSB200_ERR_STATE, "no tree: call mctsb200_plan first");
-    if (ctx->st.mdp_id != MCTSB200_MDP_GAUSSIAN_BOX) return fail(MCTSB200_ERR_STATE, "the last plan call was not over a continuous action space");
+    const int ad = ctx->st.action_doubles;
+    if (ad <= 0) return fail(MCTSB200_ERR_STATE, "the last plan call was not over a continuous action space");
     if (first_root + n > ctx->st.n_trees) return fail(MCTSB200_ERR_INVALID_ARG, "roots [%lld, %lld) out of range", (long long)first_root, (long long)(first_root + n));
     CUDA_TRY(cudaSetDevice(ctx->device));
-    if (n) CUDA_TRY(cudaMemcpy(out, (const double*)ctx->st.action_vec.p + first_root * MCTSB200_BOX_ACTION_DOUBLES, sizeof(double) * MCTSB200_BOX_ACTION_DOUBLES * (size_t)n, cudaMemcpyDeviceToHost));
+    if (n) CUDA_TRY(cudaMemcpy(out, (const double*)ctx->st.action_vec.p + first_root * ad, sizeof(double) * ad * (size_t)n, cudaMemcpyDeviceToHost));
     return MCTSB200_OK;
 }
 

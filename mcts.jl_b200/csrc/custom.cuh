@@ -20,6 +20,17 @@
 // it with NVRTC for sm_100a -- the same tile kernel the built-in MountainCar runs -- and launches the result; nothing of
 // a plugin ever runs on the host (north star: no CPU fallback).
 //
+// Continuous action spaces (mctsb200_mdp_register_continuous; actions(mdp) = a Box, test/discussion_514.jl): the struct defines
+//
+//         __device__ static bool is_terminal(const Params& p, const double* s);
+//         // next_action(gen, mdp, s, snode) (src/dpw.jl:98): the action DPW's action widening proposes, kActionDoubles float64 values
+//         __device__ static void next_action(const Params& p, const double* s, mctsb200::Stream& rng, double* a);
+//         __device__ static void gen(const Params& p, const double* s, const double* a, mctsb200::Stream& rng, double* sp, double& r);
+//         // rollout policies with ids >= MCTSB200_POLICY_PLUGIN (MCTSB200_POLICY_RANDOM is next_action itself):
+//         __device__ static void policy_action(const Params& p, int policy, const int* pp, const double* s, mctsb200::Stream& rng, double* a);
+//
+// and the library compiles search_kernel<CustomBoxDev<SD, AD>, DPW, G> around it (csrc/search.cuh: dpw_box_iteration).
+//
 // The host half of the library is compiled ahead of time for a fixed set of shapes (SD state doubles x A actions, see
 // MCTSB200_FOR_PLUGIN in capi.cu); the layout of KernelArgs<CustomDev<SD, A>> does not depend on the plugin.
 #pragma once
@@ -32,6 +43,36 @@
 namespace mctsb200 {
 
 constexpr int kCustomParamBytes = 256;
+
+// a plugin's parameters as the library sees them
+struct __align__(16) CustomParams {
+    double discount;  // the first member of every plugin's Params
+    unsigned char rest[kCustomParamBytes - sizeof(double)];
+};
+
+#if defined(__CUDACC_RTC__)
+// isequal on Float64 tuples == bitwise equality (as for the built-in MountainCar)
+template <int SD>
+__device__ __forceinline__ bool custom_key_equal(const double* a, const double* b) {
+    bool eq = true;
+#pragma unroll
+    for (int i = 0; i < SD; ++i) eq = eq && __double_as_longlong(a[i]) == __double_as_longlong(b[i]);
+    return eq;
+}
+template <int SD>
+__device__ __forceinline__ uint32_t custom_hash(const double* s) {
+    uint64_t h = 0x7F4A7C159E3779B9ull;
+#pragma unroll
+    for (int i = 0; i < SD; ++i) {
+        h ^= (uint64_t)__double_as_longlong(s[i]) * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h ^= h >> 29;
+    }
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+    return (uint32_t)h;
+}
+#endif
 
 // the plugin struct of a shape; specialised by the generated NVRTC program, never by the ahead-of-time build
 template <int SD, int A>
@@ -50,10 +91,7 @@ struct CustomDev {
     struct AbiState { double v[SD]; };
     typedef AbiState State;
     typedef AbiState Key;
-    struct __align__(16) Params {
-        double discount;  // the first member of every plugin's Params
-        unsigned char rest[kCustomParamBytes - sizeof(double)];
-    };
+    typedef CustomParams Params;
 
     __host__ __device__ __forceinline__ static State load(const Params&, const AbiState& a) { return a; }
     __host__ __device__ __forceinline__ static AbiState store(const Params&, const State& s) { return s; }
@@ -69,25 +107,8 @@ struct CustomDev {
     __device__ __forceinline__ static bool is_terminal(const Params& p, const State& s) { return P::is_terminal(pp_of(p), s.v); }
     __device__ __forceinline__ static double discount(const Params& p) { return p.discount; }
     __device__ __forceinline__ static int dense_index(const Params&, const State&) { return -1; }
-    // isequal on Float64 tuples == bitwise equality (as for the built-in MountainCar)
-    __device__ __forceinline__ static bool key_equal(const Key& a, const Key& b) {
-        bool eq = true;
-#pragma unroll
-        for (int i = 0; i < SD; ++i) eq = eq && __double_as_longlong(a.v[i]) == __double_as_longlong(b.v[i]);
-        return eq;
-    }
-    __device__ __forceinline__ static uint32_t hash(const State& s) {
-        uint64_t h = 0x7F4A7C159E3779B9ull;
-#pragma unroll
-        for (int i = 0; i < SD; ++i) {
-            h ^= (uint64_t)__double_as_longlong(s.v[i]) * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
-            h ^= h >> 29;
-        }
-        h ^= h >> 33;
-        h *= 0xff51afd7ed558ccdull;
-        h ^= h >> 33;
-        return (uint32_t)h;
-    }
+    __device__ __forceinline__ static bool key_equal(const Key& a, const Key& b) { return custom_key_equal<SD>(a.v, b.v); }
+    __device__ __forceinline__ static uint32_t hash(const State& s) { return custom_hash<SD>(s.v); }
     __device__ __forceinline__ static void gen(const Params& p, const State& s, int a, Stream& rng, State& sp, double& r) {
         State out;
         P::gen(pp_of(p), s.v, a, rng, out.v, r);
@@ -97,6 +118,63 @@ struct CustomDev {
         if (policy == MCTSB200_POLICY_RANDOM) return rng.uniform_int(kActions);
         if (policy == MCTSB200_POLICY_CONSTANT) return pp[0];
         return P::policy_action(pp_of(p), policy, pp, s.v, rng);
+    }
+#endif
+};
+
+// ---- continuous action spaces: the action is a vector of AD float64 values ---------------------------------------------------
+template <int SD, int AD>
+struct CustomBoxPluginOf;
+
+template <int SD, int AD>
+struct CustomBoxDev {
+    static constexpr int kActions = 1;    // (no finite action set: Row / Aux keep one unused slot, as GaussianBoxDev)
+    static constexpr bool kDense = false;
+    static constexpr int kMaxBranch = 0;  // transitions[sanode] is kept as the push-ordered vector
+    static constexpr bool kFast = false;
+    static constexpr bool kCustom = true;
+    static constexpr int kStateDoubles = SD;
+    static constexpr int kActionDoubles = AD;
+    static_assert(AD >= 1 && AD <= 4, "an action node's label holds up to four doubles (BoxANode)");
+
+    struct AbiState { double v[SD]; };
+    typedef AbiState State;
+    typedef AbiState Key;
+    struct Action { double v[AD]; };
+    typedef CustomParams Params;
+
+    __host__ __device__ __forceinline__ static State load(const Params&, const AbiState& a) { return a; }
+    __host__ __device__ __forceinline__ static AbiState store(const Params&, const State& s) { return s; }
+    __host__ __device__ __forceinline__ static State state_of(const Params&, const Key& k) { return k; }
+    __host__ __device__ __forceinline__ static Key key_of(const Params&, const State& s) { return s; }
+
+#if defined(__CUDACC_RTC__)
+    using P = typename CustomBoxPluginOf<SD, AD>::type;
+    using PParams = typename P::Params;
+    static_assert(sizeof(PParams) <= sizeof(Params), "a plugin's Params must fit in 256 bytes");
+    __device__ __forceinline__ static const PParams& pp_of(const Params& p) { return *reinterpret_cast<const PParams*>(&p); }
+
+    __device__ __forceinline__ static bool is_terminal(const Params& p, const State& s) { return P::is_terminal(pp_of(p), s.v); }
+    __device__ __forceinline__ static double discount(const Params& p) { return p.discount; }
+    __device__ __forceinline__ static int dense_index(const Params&, const State&) { return -1; }
+    __device__ __forceinline__ static bool key_equal(const Key& a, const Key& b) { return custom_key_equal<SD>(a.v, b.v); }
+    __device__ __forceinline__ static uint32_t hash(const State& s) { return custom_hash<SD>(s.v); }
+    __device__ __forceinline__ static void next_action(const Params& p, const State& s, Stream& rng, Action& a) {
+        Action out;
+        P::next_action(pp_of(p), s.v, rng, out.v);
+        a = out;
+    }
+    __device__ __forceinline__ static void gen(const Params& p, const State& s, const Action& a, Stream& rng, State& sp, double& r) {
+        State out;
+        P::gen(pp_of(p), s.v, a.v, rng, out.v, r);
+        sp = out;
+    }
+    // action(policy, s) of the rollout policy: RandomPolicy = rand(rng, actions(mdp, s)) = next_action's draw
+    __device__ __forceinline__ static void policy_action(const Params& p, int policy, const int* pp, const State& s, Stream& rng, Action& a) {
+        Action out;
+        if (policy == MCTSB200_POLICY_RANDOM) P::next_action(pp_of(p), s.v, rng, out.v);
+        else P::policy_action(pp_of(p), policy, pp, s.v, rng, out.v);
+        a = out;
     }
 #endif
 };

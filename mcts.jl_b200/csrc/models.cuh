@@ -350,6 +350,8 @@ struct GaussianBoxDev {
 #pragma unroll
         for (int i = 0; i < kActionDoubles; ++i) a.v[i] = DM_ADD(p.a_lo[i], DM_MUL(DM_SUB(p.a_hi[i], p.a_lo[i]), rng.uniform01()));
     }
+    // the rollout policy: only RandomPolicy (MdpAccess<GaussianBoxDev>::policy_ok)
+    __device__ __forceinline__ static void policy_action(const Params& p, int, const int*, const State& s, Stream& rng, Action& a) { next_action(p, s, rng, a); }
     // sp = s + drift * a + sd * z, z ~ N(0, I): two Box-Muller pairs from four words (z0, z1 from the first two, z2 from the others)
     __device__ __forceinline__ static void gen(const Params& p, const State& s, const Action& a, Stream& rng, State& sp, double& r) {
         const double two_pi = 6.283185307179586;

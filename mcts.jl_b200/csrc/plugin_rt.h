@@ -8,12 +8,13 @@ namespace mctsb200_rt {
 struct PluginInfo {
     std::string name, source, struct_name;
     int state_doubles = 0, n_actions = 0, max_branch = 0;
+    int action_doubles = 0;  // > 0: a continuous action space (CustomBoxDev<state_doubles, action_doubles>; only DPW plans for it)
 };
 
 // kernels of one (plugin, solver kind) program
 enum KernelId { K_SEARCH_G1 = 0, K_SEARCH_G2, K_SEARCH_G4, K_SEARCH_G8, K_SEARCH_G16, K_SEARCH_G32, K_EPISODE_INIT, K_EPISODE_STEP, K_COUNT };
 
-// Registers a plugin and compiles its vanilla-UCT program for sm_100a (this needs NVRTC but no GPU, so interface errors
+// Registers a plugin and compiles its vanilla-UCT program (continuous actions: its DPW program) for sm_100a (this needs NVRTC but no GPU, so interface errors
 // surface here with the compiler's log in `err`). Returns the plugin index (>= 0) or -1. A name registered before is
 // replaced if the definition differs (its index stays).
 int register_plugin(const PluginInfo& info, std::string& err);

@@ -310,7 +310,7 @@ struct Search {
             double r;
             if constexpr (M::kActionDoubles > 0) {  // RandomPolicy on a continuous action space: rand(rng, actions(mdp, s))
                 typename M::Action act;
-                M::next_action(a.mdp, s, rs, act);
+                M::policy_action(a.mdp, a.cfg.policy, a.cfg.pparam, s, rs, act);
                 M::gen(a.mdp, s, act, rs, sp, r);
             } else {
                 int act;

@@ -192,6 +192,11 @@ class PluginMDP:
     terminal: Any = None       # optional host-side isterminal(s) (DPW's terminal-root error path in the Python mirror)
     lib_path: Optional[str] = None
     oracle_mdp_id: Optional[int] = None  # tests only: the id under which oracle/mcts_oracle.cpp restates this model
+    # a continuous action space (mctsb200_mdp_register_continuous): actions(mdp) = Box(a_lo, a_hi) of action_width coordinates, `actions`
+    # is None, `action` returns a tuple of floats and only DPWSolver can plan
+    action_width: int = 0
+    a_lo: Tuple[float, ...] = ()
+    a_hi: Tuple[float, ...] = ()
 
     state_dtype = np.float64
     dense = False
@@ -205,11 +210,18 @@ class PluginMDP:
     @property
     def mdp_id(self) -> int:
         if self._mdp_id is None:
-            from ._lib import register_mdp
+            from ._lib import register_mdp, register_mdp_continuous
 
-            self._mdp_id = register_mdp(self.name, self.source, self.struct_name, self.state_width, len(self.actions), self.max_branch,
-                                        self.lib_path)
+            if self.action_width:
+                self._mdp_id = register_mdp_continuous(self.name, self.source, self.struct_name, self.state_width, self.action_width, self.lib_path)
+            else:
+                self._mdp_id = register_mdp(self.name, self.source, self.struct_name, self.state_width, len(self.actions), self.max_branch,
+                                            self.lib_path)
         return self._mdp_id
+
+    def action_in_space(self, a) -> bool:
+        """`a in actions(m)` for a continuous action space (test/discussion_514.jl:18)."""
+        return len(a) == self.action_width and all(lo <= x <= hi for x, lo, hi in zip(a, self.a_lo, self.a_hi))
 
     @property
     def discount(self) -> float:
@@ -229,6 +241,26 @@ class PluginMDP:
 
     def params(self) -> C.Structure:
         return self.params_struct
+
+
+class ContinuousPendulumParams(C.Structure):
+    """Params of plugins/continuous_pendulum.cuh."""
+
+    _fields_ = [("discount", C.c_double), ("g", C.c_double), ("m", C.c_double), ("l", C.c_double), ("M", C.c_double), ("alpha", C.c_double),
+                ("dt", C.c_double), ("cost", C.c_double), ("u_max", C.c_double), ("noise", C.c_double), ("effort", C.c_double), ("gain", C.c_double)]
+
+
+def ContinuousPendulum(u_max: float = 50.0, noise: float = 10.0, effort: float = 0.0, gain: float = 100.0, g: float = 9.81, m: float = 2.0,
+                       l: float = 8.0, M: float = 8.0, dt: float = 0.1, discount: float = 0.99, cost: float = -1.0,
+                       name: str = "ContinuousPendulum") -> "PluginMDP":
+    """An inverted pendulum with a continuous torque (plugins/continuous_pendulum.cuh): a run-time plugin whose action space is
+    Box([-u_max], [u_max]) -- the reference's test/discussion_514.jl case (actions(m) = Box) for a model the caller brings. State
+    (theta, omega); `action` returns a 1-tuple; rollout policy id 100 is a proportional controller."""
+    p = ContinuousPendulumParams(float(discount), float(g), float(m), float(l), float(M), 1.0 / (float(m) + float(M)), float(dt), float(cost),
+                                 float(u_max), float(noise), float(effort), float(gain))
+    return PluginMDP.from_file("continuous_pendulum.cuh", name=name, struct_name="ContinuousPendulum", actions=None, params_struct=p,
+                               state_width=2, max_branch=0, terminal=lambda s: abs(s[0]) > 1.5707963267948966, oracle_mdp_id=1002,
+                               action_width=1, a_lo=(-float(u_max),), a_hi=(float(u_max),))
 
 
 class NoisyMountainCarParams(C.Structure):

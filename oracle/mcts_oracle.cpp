@@ -340,6 +340,61 @@ struct InvertedPendulum {
     }
 };
 
+// mcts.jl_b200/plugins/continuous_pendulum.cuh: the pendulum above with a continuous torque -- a run-time plugin with a continuous
+// action space (actions(mdp) = Box([-u_max], [u_max]); next_action = RandomActionGenerator's rand(rng, actions(mdp, s))).
+struct ContinuousPendulumParams {
+    double discount, g, m, l, M, alpha, dt, cost;
+    double u_max, noise, effort, gain;
+};
+struct Vec1Action {
+    double v[1];
+};
+constexpr int kOracleMdpContinuousPendulum = 1002;
+struct ContinuousPendulum {
+    static constexpr int kMdpId = kOracleMdpContinuousPendulum;
+    static constexpr bool kLiteralTransitions = true;
+    using State = MCState;  // (theta, omega)
+    typedef Vec1Action Action;
+    static constexpr int kActions = 1;  // (no finite action set)
+    static constexpr int kActionDoubles = 1;
+    ContinuousPendulumParams p;
+    explicit ContinuousPendulum(const ContinuousPendulumParams& q) : p(q) {}
+    double discount() const { return p.discount; }
+    int n_actions(const State&) const { return 0; }
+    int max_actions() const { return 1; }
+    bool isterminal(const State& s) const { return std::fabs(s.x) > 1.5707963267948966; }
+    int64_t state_index(const State&) const { return -1; }
+    int64_t n_states() const { return 0; }
+    static std::array<uint64_t, 1> action_key(const Action& a) { return {dm_bits(a.v[0])}; }
+    Action next_action(const State&, Stream& rng) const {
+        Action a;
+        a.v[0] = (0.0 - p.u_max) + (2.0 * p.u_max) * rng.uniform01();
+        return a;
+    }
+    void gen(const State& s, const Action& a, Stream& rng, State& sp, double& r) const {
+        const double th = s.x, w = s.v;
+        const double u = a.v[0] + (rng.uniform01() - 0.5) * p.noise;
+        const double sn = det_sin(th), cs = o_cos(th), s2 = det_sin(2.0 * th);
+        const double aml = (p.alpha * p.m) * p.l;
+        const double num = (p.g * sn - ((aml * (w * w)) * s2) * 0.5) - (p.alpha * cs) * u;
+        const double den = (4.0 / 3.0) * p.l - (p.alpha * p.l) * (cs * cs);
+        const double acc = num / den;
+        sp = MCState{th + w * p.dt, w + acc * p.dt};
+        r = isterminal(sp) ? p.cost : 0.0 - p.effort * (a.v[0] * a.v[0]);
+    }
+    // rollout policy 100 of the plugin: proportional push against the fall; other ids: no torque
+    Action plugin_policy(int policy, const State& s) const {
+        Action a;
+        double u = 0.0;
+        if (policy == MCTSB200_POLICY_PLUGIN) {
+            u = p.gain * (s.x + 0.3 * s.v);
+            u = u > p.u_max ? p.u_max : (u < 0.0 - p.u_max ? 0.0 - p.u_max : u);
+        }
+        a.v[0] = u;
+        return a;
+    }
+};
+
 // The continuous-action model of include/mctsb200.h (mctsb200_gaussian_box_params): the MDP of test/discussion_514.jl
 // (states / actions are Boxes, transition = MvNormal(s, Diagonal(var))) with an optional drift and quadratic cost. next_action is
 // RandomActionGenerator on a Box: rand(rng, actions(mdp, s)) = one uniform draw per coordinate (src/action_gen.jl:11-13).
@@ -444,7 +499,10 @@ struct Hooks {
     // action(policy, s) for the rollout policy
     typename M::Action policy_action(const typename M::State& s, Stream& rng) const {
         if constexpr (M::kActionDoubles > 0) {
-            return mdp.next_action(s, rng);  // RandomPolicy: rand(rng, actions(problem, s)) -- the only policy a Box model has here
+            if constexpr (M::kMdpId == kOracleMdpContinuousPendulum) {
+                if (cfg.rollout_policy != MCTSB200_POLICY_RANDOM) return mdp.plugin_policy(cfg.rollout_policy, s);
+            }
+            return mdp.next_action(s, rng);  // RandomPolicy: rand(rng, actions(problem, s))
         } else {
             return discrete_policy_action(s, rng);
         }
@@ -1282,6 +1340,10 @@ int32_t oracle_plan(const mctsb200_solver_cfg* cfg, int32_t mdp_id, const void* 
         InvertedPendulum m(*(const InvertedPendulumParams*)params);
         return plan_batch<InvertedPendulum, MCStateHash>(m, *cfg, (const MCState*)roots, n_roots, root_index_base, n_threads, keep_trees != 0,
                                                          literal_transitions != 0, same_root != 0, action_out, bestq_out, status_out, stats);
+    } else if (mdp_id == kOracleMdpContinuousPendulum) {
+        ContinuousPendulum m(*(const ContinuousPendulumParams*)params);
+        return plan_batch<ContinuousPendulum, MCStateHash>(m, *cfg, (const MCState*)roots, n_roots, root_index_base, n_threads, keep_trees != 0,
+                                                           literal_transitions != 0, same_root != 0, action_out, bestq_out, status_out, stats);
     } else if (mdp_id == MCTSB200_MDP_GAUSSIAN_BOX) {
         GaussianBox m(*(const mctsb200_gaussian_box_params*)params);
         return plan_batch<GaussianBox, BoxStateHash>(m, *cfg, (const BoxState*)roots, n_roots, root_index_base, n_threads, keep_trees != 0,

@@ -561,6 +561,46 @@ def test_box_actions_many_children_at_the_root(gpu_ctx, oracle):
     assert t["child_offsets"][1] - t["child_offsets"][0] > 300
 
 
+@pytest.mark.parametrize("lanes", [None, 1, 4, 32])
+def test_plugin_continuous_actions_bit_exact(gpu_ctx, oracle, lanes):
+    """A run-time plugin with a continuous action space (mctsb200_mdp_register_continuous; plugins/continuous_pendulum.cuh: the inverted
+    pendulum with the torque as a Box([-50], [50]) action): the plugin's next_action / gen / policy_action run inside the NVRTC-compiled
+    dpw_box_iteration; action vectors, Q, counters and whole trees against the oracle's restatement."""
+    from test_host_emu_parity import _run_box_both
+
+    cp = m.ContinuousPendulum()
+    rng = np.random.default_rng(9)
+    roots = [((u - 0.5) * 0.1, (v - 0.5) * 0.1) for u, v in rng.random((24, 2))]
+    v, _, st = _run_box_both(gpu_ctx, oracle, m.DPWSolver(n_iterations=400, depth=10, exploration_constant=10.0, alpha_state=1 / 8, rng=4), cp, roots,
+                             lanes=lanes, trees=range(0, 24, 5))
+    assert all(cp.action_in_space(a) for a in v) and st.n_simulations == 400 * 24
+    # a torque cost (the best action is interior), a feedback controller as the rollout policy, unmerged actions and states
+    cp2 = m.ContinuousPendulum(effort=1e-4, noise=4.0, gain=150.0, name="ContinuousPendulumEffort")
+    for opts in (dict(estimate_value=m.RolloutEstimator(m.PluginPolicy(100), max_depth=30)), dict(check_repeat_action=False),
+                 dict(check_repeat_state=False, k_action=6.0, alpha_action=0.3), dict(estimate_value=0.0, init_Q=-0.5, init_N=1)):
+        kw = dict(n_iterations=300, depth=12, exploration_constant=2.0, rng=6)
+        kw.update(opts)
+        _run_box_both(gpu_ctx, oracle, m.DPWSolver(**kw), cp2, roots, base=500, lanes=lanes, trees=range(0, 24, 7))
+
+
+def test_plugin_continuous_actions_refusals(gpu_ctx):
+    """What a continuous action space cannot do, whoever brings the model: vanilla UCT, DPW without action widening, the episode driver."""
+    cp = m.ContinuousPendulum()
+    gpu_ctx.configure(cp.mdp_id, cp.params())
+    r = cp.encode_states([(0.01, 0.0)])
+    for solver in (m.MCTSSolver(n_iterations=10, depth=5), m.DPWSolver(n_iterations=10, depth=5, enable_action_pw=False)):
+        cfg, keep = m.build_cfg(solver, cp)
+        with pytest.raises(m.MCTSB200Error) as ei:
+            gpu_ctx.plan(cfg, cp.mdp_id, r)
+        assert ei.value.status == m.abi.ERR_UNSUPPORTED
+    cfg, keep = m.build_cfg(m.DPWSolver(n_iterations=10, depth=5), cp)
+    with pytest.raises(m.MCTSB200Error) as ei:
+        gpu_ctx.run_episodes(cfg, cp.mdp_id, r, 5, 0, 0)
+    assert ei.value.status == m.abi.ERR_UNSUPPORTED
+    gpu_ctx.plan(cfg, cp.mdp_id, r)  # ... and the ctx is still good
+    assert gpu_ctx.root_action_vectors(0, 1, 1).shape == (1, 1)
+
+
 @pytest.mark.parametrize("fast", ["1", "0"])
 def test_function_policy_is_a_table_on_the_device(gpu_ctx, oracle, monkeypatch, fast):
     from test_host_emu_parity import test_emu_function_policy_is_a_table_on_the_device as body

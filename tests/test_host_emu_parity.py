@@ -354,14 +354,15 @@ def _run_box_both(ctx, orc, solver, mdp, roots, base=0, lanes=None, trees=None):
     cfg, keep = m.build_cfg(solver, mdp)
     if lanes is not None:
         cfg.lanes_per_tree = lanes
+    oid = getattr(mdp, "oracle_mdp_id", None) or mdp.mdp_id  # (run-time plugins: the id under which the oracle restates the model)
     ctx.configure(mdp.mdp_id, mdp.params())
-    orc.configure(mdp.mdp_id, mdp.params())
+    orc.configure(oid, mdp.params())
     r = mdp.encode_states(roots)
     a1, q1, s1, st1 = ctx.plan(cfg, mdp.mdp_id, r, base, want_status=True)
-    a2, q2, s2, st2 = orc.plan(cfg, mdp.mdp_id, r, base, n_threads=4)
+    a2, q2, s2, st2 = orc.plan(cfg, oid, r, base, n_threads=4)
     assert np.array_equal(s1, s2) and np.array_equal(a1, a2), (a1, a2)
     assert np.array_equal(bits(q1), bits(q2))
-    v1, v2 = ctx.root_action_vectors(0, len(roots)), orc.root_action_vectors(0, len(roots))
+    v1, v2 = ctx.root_action_vectors(0, len(roots), mdp.action_width), orc.root_action_vectors(0, len(roots), mdp.action_width)
     assert np.array_equal(bits(v1), bits(v2))
     d1, d2 = st1.as_dict(), st2.as_dict()
     for k in COUNTER_KEYS:

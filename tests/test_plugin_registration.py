@@ -67,6 +67,41 @@ def test_argument_checks():
     assert "256 bytes" in e.value.message
 
 
+def test_continuous_action_plugins_compile():
+    """mctsb200_mdp_register_continuous: actions(mdp) = a Box (test/discussion_514.jl) for a model the caller brings. The DPW program
+    compiles at registration, for every host shape (2 / 4 state doubles x 1 / 2 action doubles); the interface is checked there."""
+    from mcts_jl_b200._lib import register_mdp_continuous
+
+    cp = m.ContinuousPendulum()
+    a = cp.mdp_id
+    assert a >= abi.MDP_PLUGIN_BASE and cp.actions is None and cp.action_width == 1
+    na, sb = C.c_int32(-1), C.c_int64()
+    assert _lib().mctsb200_mdp_info(a, C.byref(na), C.byref(sb)) == abi.OK
+    assert (na.value, sb.value) == (0, 16)  # no finite action set
+    assert register_mdp_continuous(cp.name, cp.source, cp.struct_name, 2, 1) == a  # the same definition again
+    # wider shapes: pad the state / the action (the dynamics ignore the padding)
+    wide = cp.source.replace("        sp[1] = DM_ADD(w, DM_MUL(acc, p.dt));\n", "        sp[1] = DM_ADD(w, DM_MUL(acc, p.dt));\n        sp[2] = s[2];\n        sp[3] = s[3];\n")
+    assert "sp[3] = s[3]" in wide
+    two = cp.source.replace("rng.uniform01()));\n    }", "rng.uniform01()));\n        a[1] = rng.uniform01();\n    }", 1)
+    assert "a[1] = rng.uniform01()" in two
+    two = two.replace("        a[0] = u;\n", "        a[0] = u;\n        a[1] = 0.0;\n")
+    ids = {register_mdp_continuous("CP41", wide, "ContinuousPendulum", 4, 1), register_mdp_continuous("CP22", two, "ContinuousPendulum", 2, 2),
+           register_mdp_continuous("CP42", wide.replace("rng.uniform01()));\n    }", "rng.uniform01()));\n        a[1] = rng.uniform01();\n    }", 1)
+                                   .replace("        a[0] = u;\n", "        a[0] = u;\n        a[1] = 0.0;\n"), "ContinuousPendulum", 4, 2)}
+    assert len(ids) == 3 and a not in ids
+    for sd, ad in [(2, 3), (3, 1), (2, 0), (8, 2)]:
+        with pytest.raises(m.MCTSB200Error) as e:
+            register_mdp_continuous("ShapeC", cp.source, "ContinuousPendulum", sd, ad)
+        assert e.value.status == abi.ERR_UNSUPPORTED
+    with pytest.raises(m.MCTSB200Error) as e:
+        register_mdp_continuous("GaussianBox", cp.source, "ContinuousPendulum", 2, 1)
+    assert e.value.status == abi.ERR_INVALID_ARG
+    # a discrete plugin's struct does not have the continuous interface: the compiler says which member is missing
+    with pytest.raises(m.MCTSB200Error) as e:
+        register_mdp_continuous("NotContinuous", m.MountainCarPlugin().source, "MountainCarPlugin", 2, 1)
+    assert "does not compile" in e.value.message and "next_action" in e.value.message
+
+
 def test_redefinition_keeps_the_id():
     src = m.MountainCarPlugin().source
     a = m.register_mdp("Redefine", src, "MountainCarPlugin", 2, 3, 1)
