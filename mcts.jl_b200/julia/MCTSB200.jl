@@ -92,6 +92,11 @@ n_dense_states(m::SimpleGridWorld) = m.size[1] * m.size[2] + 1
 dense_state(m::SimpleGridWorld, i) = i == m.size[1] * m.size[2] ? GWPos(-1, -1) : GWPos(i % m.size[1] + 1, i ÷ m.size[1] + 1)
 n_dense_states(m) = 0
 
+# A model whose actions(mdp) is a continuum (a Box: test/discussion_514.jl) says how many Float64 coordinates an action has; the library
+# then returns action VECTORS (mctsb200_root_action_vectors, tree_buffers.a_label_vectors) and `action` converts them to actiontype(mdp).
+action_doubles(m) = 0
+action_from_vector(m, v::AbstractVector{Float64}) = convert(actiontype(m), v)   # e.g. SVector{2,Float64}(v), Vector{Float64}
+
 # Run-time registration of a device plugin for a new MDP type (include/mctsb200.h: mctsb200_mdp_register). `source` is CUDA text
 # defining `struct <plugin_struct>` (csrc/custom.cuh); afterwards add a `device_mdp(::YourMDP)` method returning
 # (id, Ref(params_pod), sizeof(params_pod)) with a POD that mirrors the plugin's `Params` (`discount` first). max_branch = 0
@@ -101,6 +106,16 @@ function register_mdp(name::AbstractString, source::AbstractString, plugin_struc
     id = Ref{Int32}(-1)
     check(ccall((:mctsb200_mdp_register, LIB), Int32, (Cstring, Cstring, Cstring, Int32, Int32, Int32, Ref{Int32}),
                 name, source, plugin_struct, state_doubles, n_actions, max_branch, id))
+    return id[]
+end
+
+# The same for a model whose actions(mdp) is a Box (test/discussion_514.jl): the struct defines next_action / gen over action vectors
+# (csrc/custom.cuh), only DPWSolver plans for it and `action` returns the Vector{Float64} (see `action_vector` below).
+function register_mdp_continuous(name::AbstractString, source::AbstractString, plugin_struct::AbstractString;
+                                 state_doubles::Integer, action_doubles::Integer)
+    id = Ref{Int32}(-1)
+    check(ccall((:mctsb200_mdp_register_continuous, LIB), Int32, (Cstring, Cstring, Cstring, Int32, Int32, Ref{Int32}),
+                name, source, plugin_struct, state_doubles, action_doubles, id))
     return id[]
 end
 
@@ -206,6 +221,12 @@ function action_info_batch(p::B200Planner, states::AbstractVector; root_index_ba
         check(ccall((:mctsb200_plan, LIB), Int32,
                     (Ptr{Cvoid}, Ref{SolverCfg}, Int32, Ptr{Cvoid}, Int64, Csize_t, Int64, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ref{PlanStats}),
                     p.ctx.h, cfg, p.mdp_id, pointer(roots), n, state_bytes(p), root_index_base, act, bq, C_NULL, p.stats))
+    end
+    ad = action_doubles(p.mdp)
+    if ad > 0                                     # a continuous action space: a_labels[sanode] of src/dpw.jl:65 as vectors
+        vec = Matrix{Float64}(undef, ad, n)
+        check(ccall((:mctsb200_root_action_vectors, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), p.ctx.h, 0, n, vec))
+        return [action_from_vector(p.mdp, vec[:, i]) for i in 1:n], bq
     end
     as = collect(actions(p.mdp))                  # device returns 0-based indices into actions(mdp) iteration order
     return [as[i + 1] for i in act], bq
@@ -333,13 +354,15 @@ function export_vectors(p::B200Planner, root_i::Integer)
     check(ccall((:mctsb200_tree_sizes_query, LIB), Int32, (Ptr{Cvoid}, Int64, Ref{TreeSizes}), p.ctx.h, root_i, sz))
     ns, na, nt = sz[].n_state_nodes, sz[].n_action_nodes, sz[].n_transitions
     S = statetype(p.mdp)
+    ad = Int(sz[].action_doubles)                 # > 0: the labels are vectors (a_labels then holds -1)
     out = (total_n = zeros(Int64, ns), s_labels = Vector{S}(undef, ns), child_offsets = zeros(Int64, ns + 1), child_ids = zeros(Int64, na),
            n = zeros(Int64, na), q = zeros(Float64, na), a_labels = zeros(Int32, na), n_a_children = zeros(Int64, na),
-           trans_offsets = zeros(Int64, na + 1), trans_spnode = zeros(Int64, nt), trans_r = zeros(Float64, nt), trans_count = zeros(Int64, nt))
+           trans_offsets = zeros(Int64, na + 1), trans_spnode = zeros(Int64, nt), trans_r = zeros(Float64, nt), trans_count = zeros(Int64, nt),
+           a_label_vectors = zeros(Float64, max(ad, 1), na))
     GC.@preserve out begin
         b = TreeBuffers(pointer(out.total_n), pointer(out.s_labels), pointer(out.child_offsets), pointer(out.child_ids), pointer(out.n),
                         pointer(out.q), pointer(out.a_labels), pointer(out.n_a_children), pointer(out.trans_offsets), pointer(out.trans_spnode),
-                        pointer(out.trans_r), pointer(out.trans_count), C_NULL)
+                        pointer(out.trans_r), pointer(out.trans_count), ad > 0 ? pointer(out.a_label_vectors) : Ptr{Float64}(C_NULL))
         check(ccall((:mctsb200_tree_export, LIB), Int32, (Ptr{Cvoid}, Int64, Ref{TreeBuffers}), p.ctx.h, root_i, b))
     end
     return out
@@ -371,7 +394,13 @@ end
 function export_tree(p::B200Planner{<:DPWSolver}, root_i::Integer)
     v = export_vectors(p, root_i)
     S, A = statetype(p.mdp), actiontype(p.mdp)
-    as = collect(actions(p.mdp))
+    # the label of action node sa: an element of actions(mdp), or (continuous action spaces) the vector next_action drew
+    label = if action_doubles(p.mdp) > 0
+        sa -> action_from_vector(p.mdp, v.a_label_vectors[:, sa])
+    else
+        as = collect(actions(p.mdp))
+        sa -> as[v.a_labels[sa] + 1]
+    end
     t = MCTS.DPWTree{S,A}(length(v.total_n))
     for (i, s) in enumerate(v.s_labels)            # src/dpw_types.jl:123-159, field for field
         push!(t.total_n, v.total_n[i]); push!(t.s_labels, s)
@@ -379,11 +408,11 @@ function export_tree(p::B200Planner{<:DPWSolver}, root_i::Integer)
         push!(t.children, kids)
         t.s_lookup[s] = i                          # (the newest node of a repeated state, as `s_lookup[s] = snode` leaves it)
         for sa in kids
-            t.a_lookup[(i, as[v.a_labels[sa] + 1])] = sa
+            t.a_lookup[(i, label(sa))] = sa
         end
     end
     for sa in 1:length(v.n)
-        push!(t.n, v.n[sa]); push!(t.q, v.q[sa]); push!(t.a_labels, as[v.a_labels[sa] + 1]); push!(t.n_a_children, v.n_a_children[sa])
+        push!(t.n, v.n[sa]); push!(t.q, v.q[sa]); push!(t.a_labels, label(sa)); push!(t.n_a_children, v.n_a_children[sa])
         tr = Tuple{Int,Float64}[]
         for k in v.trans_offsets[sa]+1:v.trans_offsets[sa+1], _ in 1:v.trans_count[k]   # transitions[sanode] as a multiset: one entry per push
             push!(tr, (Int(v.trans_spnode[k]), v.trans_r[k]))
