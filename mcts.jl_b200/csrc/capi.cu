@@ -449,7 +449,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
         } else {
             if (cfg->keep_tree_calls < 0 || cfg->keep_tree_calls > 100000) return fail(MCTSB200_ERR_INVALID_ARG, "keep_tree_calls out of range");
             calls = cfg->keep_tree_calls ? cfg->keep_tree_calls : 8;
-            NS = calls * n_iter + 1;
+            NS = calls * (n_iter + 1);  // per call: one new state node per iteration at most, and a root the tree may not hold yet
             if (NS > 0x7fffffffLL / 4) return fail(MCTSB200_ERR_CAPACITY, "kept trees would exceed 2^29 state nodes per tree");
         }
     }
@@ -485,7 +485,7 @@ int32_t setup_storage(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long lo
     // continuous action spaces: one action node and one child-list entry per tree level at most, beside the transition pushes
     long long NA = 0;
     if constexpr (M::kActionDoubles > 0) {
-        const long long pushes = std::max<long long>(1, n_iter * std::max(cfg->depth, 1));
+        const long long pushes = std::max<long long>(1, calls * n_iter * std::max(cfg->depth, 1));
         NA = pushes + 1;
         NP = 4 * (2 * pushes) + 8 * std::min<long long>(NS + NA, 2 * pushes);
         if (NA > 0x7fffffffLL || NP > 0x7fffffffLL) return fail(MCTSB200_ERR_CAPACITY, "action-node table would exceed 2^31 entries per tree");
@@ -1184,7 +1184,6 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
 int32_t check_box_cfg(const mctsb200_solver_cfg* cfg) {
     if (cfg->kind != MCTSB200_KIND_DPW) return fail(MCTSB200_ERR_UNSUPPORTED, "a continuous action space needs DPWSolver (vanilla UCT enumerates actions(mdp, s))");
     if (!cfg->enable_action_pw) return fail(MCTSB200_ERR_UNSUPPORTED, "a continuous action space needs enable_action_pw (its actions cannot be enumerated)");
-    if (cfg->keep_tree) return fail(MCTSB200_ERR_UNSUPPORTED, "keep_tree is not available for continuous action spaces");
     if (cfg->rollouts_per_leaf != 1) return fail(MCTSB200_ERR_UNSUPPORTED, "continuous action spaces run one rollout per leaf");
     return MCTSB200_OK;
 }
@@ -1336,14 +1335,14 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
                           void* final_states_out, mctsb200_plan_stats* stats) {
     using Abi = typename M::AbiState;
     const auto t0 = std::chrono::steady_clock::now();
-    if constexpr (M::kActionDoubles > 0) {
-        return fail(MCTSB200_ERR_UNSUPPORTED, "the device episode driver steps environments with action indices: not available for continuous action spaces");
-    } else {
     if (!MdpAccess<M>::ready(ctx)) return fail(MCTSB200_ERR_STATE, "mdp_configure was not called for this MDP");
     mctsb200_solver_cfg cfg_capped;
     cfg = effective_cfg(cfg, cfg_capped);
-    int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok);
+    int32_t rc = validate_cfg(cfg, M::kActions, M::kDense, &MdpAccess<M>::policy_ok, M::kActionDoubles > 0);
     if (rc) return rc;
+    if constexpr (M::kActionDoubles > 0) {
+        if (int32_t e = check_box_cfg(cfg)) return e;
+    }
     if (state_bytes != sizeof(Abi) || !initial_states || n <= 0 || max_steps < 0 || base < 0) return fail(MCTSB200_ERR_INVALID_ARG, "bad run_episodes arguments");
     const Abi* h = (const Abi*)initial_states;
     for (long long i = 0; i < n; ++i)
@@ -1393,9 +1392,11 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
         c.seed = cfg->seed + (uint64_t)t;
         mctsb200_plan_stats st;
         unsigned flags = 0;
-        if (cfg->kind == MCTSB200_KIND_UCT)
-            rc = run_search<M, MCTSB200_KIND_UCT>(ctx, &c, d_s, n, 1, base, (int*)ctx->io_action.p, nullptr, (int*)ctx->io_status.p, &st, &flags);
-        else
+        if constexpr (M::kActionDoubles == 0) {
+            if (cfg->kind == MCTSB200_KIND_UCT)
+                rc = run_search<M, MCTSB200_KIND_UCT>(ctx, &c, d_s, n, 1, base, (int*)ctx->io_action.p, nullptr, (int*)ctx->io_status.p, &st, &flags);
+        }
+        if (cfg->kind == MCTSB200_KIND_DPW)
             rc = run_search<M, MCTSB200_KIND_DPW>(ctx, &c, d_s, n, 1, base, (int*)ctx->io_action.p, nullptr, (int*)ctx->io_status.p, &st, &flags);
         if (rc) return rc;
         // (a finished episode's root is terminal: expected here; an overflowed table is not)
@@ -1412,18 +1413,19 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
             if (!k) return MCTSB200_ERR_CUDA;
             Abi* a_s = d_s;
             const int* a_act = (const int*)ctx->io_action.p;
+            const double* a_vec = (const double*)ctx->st.action_vec.p;  // (continuous action spaces: the decisions of this step's search)
             long long a_n = n, a_base = base;
             unsigned long long a_seed = env_seed;
             int a_t = t;
             double *a_disc = (double*)ctx->ep_disc.p, *a_ret = (double*)ctx->ep_ret.p;
             int *a_steps = (int*)ctx->ep_steps.p, *a_active = (int*)ctx->ep_active.p, *a_cnt = d_cnt + t + 1;
-            void* params[] = {(void*)&mdp, &a_s, &a_act, &a_n, &a_seed, &a_base, &a_t, &a_disc, &a_ret, &a_steps, &a_active, &a_cnt};
+            void* params[] = {(void*)&mdp, &a_s, &a_act, &a_vec, &a_n, &a_seed, &a_base, &a_t, &a_disc, &a_ret, &a_steps, &a_active, &a_cnt};
             CUDA_TRY(cudaLaunchKernel(k, dim3(grid), dim3(256), params, 0, ctx->stream));
         } else
 #endif
         {
             auto k = episode_step_kernel<M>;
-            MCTSB200_LAUNCH(k, grid, 256, 0, ctx->stream, mdp, d_s, (const int*)ctx->io_action.p, n, env_seed, base, t, (double*)ctx->ep_disc.p,
+            MCTSB200_LAUNCH(k, grid, 256, 0, ctx->stream, mdp, d_s, (const int*)ctx->io_action.p, (const double*)ctx->st.action_vec.p, n, env_seed, base, t, (double*)ctx->ep_disc.p,
                             (double*)ctx->ep_ret.p, (int*)ctx->ep_steps.p, (int*)ctx->ep_active.p, d_cnt + t + 1);
             CUDA_TRY(cudaGetLastError());
         }
@@ -1441,7 +1443,6 @@ int32_t episodes_dispatch(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, con
         *stats = tot;
     }
     return MCTSB200_OK;
-    }
 }
 
 // ---- tree export --------------------------------------------------------------------------------

@@ -1387,8 +1387,9 @@ __global__ void episode_init_kernel(const typename M::Params mdp, const typename
 }
 // one environment step of every running episode: sp, r = gen(mdp, s, a, rng); r_total += disc*r; disc *= discount
 template <class M>
-__global__ void episode_step_kernel(const typename M::Params mdp, typename M::AbiState* s, const int* action, long long n, unsigned long long env_seed,
-                                    long long base, int t, double* disc, double* ret, int* steps, int* active, int* n_active) {
+__global__ void episode_step_kernel(const typename M::Params mdp, typename M::AbiState* s, const int* action, const double* action_vec, long long n,
+                                    unsigned long long env_seed, long long base, int t, double* disc, double* ret, int* steps, int* active,
+                                    int* n_active) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !active[i]) return;
     Stream rng;
@@ -1396,7 +1397,14 @@ __global__ void episode_step_kernel(const typename M::Params mdp, typename M::Ab
     const typename M::State cur = M::load(mdp, s[i]);
     typename M::State sp;
     double r;
-    M::gen(mdp, cur, action[i], rng, sp, r);
+    if constexpr (M::kActionDoubles > 0) {  // the planner's decision is a vector (decide_box_kernel wrote it)
+        typename M::Action av;
+#pragma unroll
+        for (int k = 0; k < M::kActionDoubles; ++k) av.v[k] = action_vec[i * M::kActionDoubles + k];
+        M::gen(mdp, cur, av, rng, sp, r);
+    } else {
+        M::gen(mdp, cur, action[i], rng, sp, r);
+    }
     ret[i] = DM_ADD(ret[i], DM_MUL(disc[i], r));
     disc[i] = DM_MUL(disc[i], M::discount(mdp));
     s[i] = M::store(mdp, sp);

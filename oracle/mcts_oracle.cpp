@@ -1285,7 +1285,17 @@ static int32_t run_episodes_impl(const M& mdp, const mctsb200_solver_cfg& cfg0, 
             Stream rng(env_seed, (uint64_t)(base + i), (uint32_t)t, 0);
             typename M::State sp;
             double r;
-            mdp.gen(s[i], act[(size_t)i], rng, sp, r);
+            if constexpr (M::kActionDoubles > 0) {  // the planner's decision is a vector: a_labels[best_sanode] (src/dpw.jl:65)
+                typename M::Action av;
+                {
+                    std::lock_guard<std::mutex> lk(g_mu);
+                    const RootResult& res = g_roots[(size_t)i];
+                    for (int k = 0; k < M::kActionDoubles; ++k) av.v[k] = res.action_vec.empty() ? 0.0 : res.action_vec[(size_t)k];
+                }
+                mdp.gen(s[i], av, rng, sp, r);
+            } else {
+                mdp.gen(s[i], act[(size_t)i], rng, sp, r);
+            }
             ret[(size_t)i] = ret[(size_t)i] + disc[(size_t)i] * r;
             disc[(size_t)i] = disc[(size_t)i] * mdp.discount();
             s[i] = sp;
@@ -1489,6 +1499,18 @@ int32_t oracle_run_episodes(const mctsb200_solver_cfg* cfg, int32_t mdp_id, cons
         NoisyMountainCar m(*(const NoisyMountainCarParams*)params);
         return run_episodes_impl<NoisyMountainCar, MCStateHash>(m, *cfg, (MCState*)states_inout, n_episodes, max_steps, env_seed,
                                                                 episode_index_base, n_threads, return_out, steps_out, stats);
+    } else if (mdp_id == kOracleMdpInvertedPendulum) {
+        InvertedPendulum m(*(const InvertedPendulumParams*)params);
+        return run_episodes_impl<InvertedPendulum, MCStateHash>(m, *cfg, (MCState*)states_inout, n_episodes, max_steps, env_seed,
+                                                                episode_index_base, n_threads, return_out, steps_out, stats);
+    } else if (mdp_id == kOracleMdpContinuousPendulum) {
+        ContinuousPendulum m(*(const ContinuousPendulumParams*)params);
+        return run_episodes_impl<ContinuousPendulum, MCStateHash>(m, *cfg, (MCState*)states_inout, n_episodes, max_steps, env_seed,
+                                                                  episode_index_base, n_threads, return_out, steps_out, stats);
+    } else if (mdp_id == MCTSB200_MDP_GAUSSIAN_BOX) {
+        GaussianBox m(*(const mctsb200_gaussian_box_params*)params);
+        return run_episodes_impl<GaussianBox, BoxStateHash>(m, *cfg, (BoxState*)states_inout, n_episodes, max_steps, env_seed,
+                                                            episode_index_base, n_threads, return_out, steps_out, stats);
     }
     return MCTSB200_ERR_INVALID_ARG;
 }

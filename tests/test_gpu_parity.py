@@ -583,8 +583,39 @@ def test_plugin_continuous_actions_bit_exact(gpu_ctx, oracle, lanes):
         _run_box_both(gpu_ctx, oracle, m.DPWSolver(**kw), cp2, roots, base=500, lanes=lanes, trees=range(0, 24, 7))
 
 
+@pytest.mark.parametrize("which,lanes", [("box", None), ("box", 1), ("box", 32), ("plugin", None), ("plugin", 4)])
+def test_continuous_actions_kept_trees(gpu_ctx, oracle, which, lanes):
+    """keep_tree (src/dpw.jl:31-37) over a continuous action space, built-in model and run-time plugin: four calls, every root moves on
+    to a successor its tree already holds, ERR_CAPACITY once the room for keep_tree_calls calls is used up."""
+    from test_host_emu_parity import BOX_ROOTS, _box_kept_trees
+
+    if which == "box":
+        _box_kept_trees(gpu_ctx, oracle, m.GaussianBox(drift=0.2, cost=1.0, var=(0.05, 0.1, 0.02)), BOX_ROOTS * 3, lanes=lanes)
+    else:
+        _box_kept_trees(gpu_ctx, oracle, m.ContinuousPendulum(), [(0.01 * i, -0.02 * i) for i in range(-4, 5)], lanes=lanes)
+
+
+@pytest.mark.parametrize("which", ["box", "box-keep", "plugin", "plugin-keep", "pendulum-3-torques"])
+def test_continuous_actions_episodes(gpu_ctx, oracle, which):
+    """mctsb200_run_episodes over a continuous action space: every step plans, the environment steps with the chosen action VECTOR.
+    Returns, episode lengths, final states and counters against the oracle (also for the three-torque InvertedPendulum plugin)."""
+    keep = which.endswith("keep")
+    if which.startswith("box"):
+        mdp = m.GaussianBox(drift=0.3, cost=0.5, var=(0.05, 0.1, 0.02))
+        from test_host_emu_parity import BOX_ROOTS
+        starts = BOX_ROOTS * 6
+        s = m.DPWSolver(n_iterations=120, depth=6, exploration_constant=3.0, rng=8, keep_tree=keep, keep_tree_calls=8)
+    else:
+        mdp = m.ContinuousPendulum(noise=20.0) if which.startswith("plugin") else m.InvertedPendulum(noise=20.0, name="InvertedPendulumNoisy")
+        starts = [(0.05 * i, -0.04 * i) for i in range(-12, 13)]
+        s = m.DPWSolver(n_iterations=150, depth=8, exploration_constant=5.0, alpha_state=1 / 8, rng=5, keep_tree=keep, keep_tree_calls=8,
+                        estimate_value=m.RolloutEstimator(m.PluginPolicy(100), max_depth=15))
+    ret, steps, final, st = run_episodes_both(gpu_ctx, oracle, s, mdp, starts, max_steps=7, env_seed=77, base=11)
+    assert steps.max() == 7
+
+
 def test_plugin_continuous_actions_refusals(gpu_ctx):
-    """What a continuous action space cannot do, whoever brings the model: vanilla UCT, DPW without action widening, the episode driver."""
+    """What a continuous action space cannot do, whoever brings the model: vanilla UCT, DPW without action widening, per-action sums."""
     cp = m.ContinuousPendulum()
     gpu_ctx.configure(cp.mdp_id, cp.params())
     r = cp.encode_states([(0.01, 0.0)])
@@ -594,8 +625,8 @@ def test_plugin_continuous_actions_refusals(gpu_ctx):
             gpu_ctx.plan(cfg, cp.mdp_id, r)
         assert ei.value.status == m.abi.ERR_UNSUPPORTED
     cfg, keep = m.build_cfg(m.DPWSolver(n_iterations=10, depth=5), cp)
-    with pytest.raises(m.MCTSB200Error) as ei:
-        gpu_ctx.run_episodes(cfg, cp.mdp_id, r, 5, 0, 0)
+    with pytest.raises(m.MCTSB200Error) as ei:  # the root-parallel sums are defined per action of a finite set
+        gpu_ctx.plan_root_parallel(cfg, cp.mdp_id, r[0], 8)
     assert ei.value.status == m.abi.ERR_UNSUPPORTED
     gpu_ctx.plan(cfg, cp.mdp_id, r)  # ... and the ctx is still good
     assert gpu_ctx.root_action_vectors(0, 1, 1).shape == (1, 1)

@@ -408,12 +408,48 @@ def test_emu_box_actions_option_matrix(emu_ctx, oracle, opts):
     assert all(mdp.action_in_space(a) for a in v)
 
 
+def _box_kept_trees(ctx, orc, mdp, roots, lanes=None):
+    """keep_tree over a continuous action space (src/dpw.jl:31-37): a 4-call sequence in which every root moves on to a successor its
+    own tree already holds (the second state node: the first successor the search generated), trees compared after every call."""
+    ctx.clear_trees()
+    orc.clear_trees()
+    sizes = []
+    for call in range(4):
+        s = m.DPWSolver(n_iterations=80, depth=8, exploration_constant=3.0, rng=40 + call, keep_tree=True, keep_tree_calls=4)
+        _run_box_both(ctx, orc, s, mdp, roots, base=10, lanes=lanes)
+        trees = [ctx.tree_export(i, mdp.state_dtype, mdp.state_width) for i in range(len(roots))]
+        sizes.append(trees[0]["total_n"].shape[0])
+        roots = [mdp.decode_state(t["s_labels"][1]) for t in trees]
+    assert sizes == sorted(sizes) and sizes[-1] > sizes[0] + 100  # the kept tree grows across the calls
+    cfg, keep = m.build_cfg(m.DPWSolver(n_iterations=80, depth=8, rng=1, keep_tree=True, keep_tree_calls=4), mdp)
+    with pytest.raises(m.MCTSB200Error) as ei:  # ... until its room is used up
+        for _ in range(8):
+            ctx.plan(cfg, mdp.mdp_id, mdp.encode_states(roots))
+    assert ei.value.status == m.abi.ERR_CAPACITY
+    ctx.clear_trees()
+    orc.clear_trees()
+
+
+def test_emu_box_actions_kept_trees(emu_ctx, oracle):
+    _box_kept_trees(emu_ctx, oracle, m.GaussianBox(drift=0.2, cost=1.0, var=(0.05, 0.1, 0.02)), BOX_ROOTS)
+
+
+@pytest.mark.parametrize("keep", [False, True])
+def test_emu_box_actions_episodes(emu_ctx, oracle, keep):
+    """Closed-loop episodes over a continuous action space: the step's decision is the action VECTOR of best_sanode, the environment
+    steps with it (gen(mdp, s, a, rng)); returns, final states and counters against the oracle."""
+    mdp = m.GaussianBox(drift=0.3, cost=0.5, var=(0.05, 0.1, 0.02))
+    s = m.DPWSolver(n_iterations=60, depth=6, exploration_constant=3.0, rng=8, keep_tree=keep, keep_tree_calls=6)
+    ret, steps, final, st = run_episodes_both(emu_ctx, oracle, s, mdp, BOX_ROOTS * 2, max_steps=5, env_seed=31, base=3)
+    assert (steps == 5).all() and (ret < 0).all()
+    assert st.n_simulations == 60 * 10 * 5
+
+
 def test_emu_box_actions_refuses_what_cannot_work(emu_ctx):
     mdp = m.GaussianBox()
     emu_ctx.configure(mdp.mdp_id, mdp.params())
     r = mdp.encode_states(BOX_ROOTS)
-    for solver in (m.MCTSSolver(n_iterations=10, depth=5), m.DPWSolver(n_iterations=10, depth=5, enable_action_pw=False),
-                   m.DPWSolver(n_iterations=10, depth=5, keep_tree=True)):
+    for solver in (m.MCTSSolver(n_iterations=10, depth=5), m.DPWSolver(n_iterations=10, depth=5, enable_action_pw=False)):
         cfg, keep = m.build_cfg(solver, mdp)
         with pytest.raises(m.MCTSB200Error) as ei:
             emu_ctx.plan(cfg, mdp.mdp_id, r)
