@@ -219,6 +219,31 @@ def test_continuous_action_space_like_discussion_514(ctx):
     assert a3[0] < 0.0 < a3[1]
 
 
+@pytest.mark.gpu
+def test_continuous_action_space_of_a_caller_supplied_model(gpu_ctx):
+    """The same through a run-time plugin (mctsb200_mdp_register_continuous): `action` returns the torque DPW chose, the exported tree
+    carries vector labels, kept trees continue, closed-loop episodes keep the pendulum up longer than no control."""
+    cp = m.ContinuousPendulum()
+    policy = m.solve(m.DPWSolver(n_iterations=2000, depth=10, exploration_constant=10.0, alpha_state=1 / 8, rng=3, keep_tree=True), cp, ctx=gpu_ctx)
+    (u,) = policy.action((0.03, 0.0))
+    assert cp.action_in_space((u,))
+    a2, info = policy.action_info((0.03, 0.0), tree_in_info=True)
+    tree = info["tree"]
+    kids = tree.children(1)
+    best = kids[int(np.argmax(tree.q[kids - 1]))]
+    assert tuple(tree.a_label_vectors[best - 1]) == tuple(a2) and len(kids) > 20
+    assert tree.total_n[0] >= 4000  # the second call continued the first call's tree
+    policy.clear_tree()
+    # falling over costs -1 and ends the episode: planned episodes from a tilted start last longer than uncontrolled ones
+    starts = [(0.15, 0.05)] * 16  # (the torque limit can hold the pendulum only below about 0.5 rad)
+    planned = m.solve(m.DPWSolver(n_iterations=400, depth=10, exploration_constant=1.0, alpha_state=1 / 8, rng=1,
+                                  estimate_value=m.RolloutEstimator(m.PluginPolicy(100), max_depth=20)), cp, ctx=gpu_ctx)
+    _, steps, _, _ = planned.run_episodes(starts, max_steps=60, env_seed=5)
+    idle = m.solve(m.DPWSolver(n_iterations=1, depth=1, rng=1, estimate_value=0.0), m.ContinuousPendulum(u_max=1e-9, name="IdlePendulum"), ctx=gpu_ctx)
+    _, steps0, _, _ = idle.run_episodes(starts, max_steps=60, env_seed=5)
+    assert steps.mean() > steps0.mean() + 3, (steps, steps0)  # (a 1 s search horizon sees the fall late: it delays it, no more)
+
+
 def test_several_devices_behind_the_same_planner(emu_lib_path):
     """MCTSB200.jl: `solve(B200(solver, [0, 1]), mdp)` -- a planner over several devices of one process (mctsb200_ctx_create_multi):
     batch calls shard inside the library and return what one device returns; `action_root_parallel` merges the devices' trees.
