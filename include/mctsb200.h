@@ -316,9 +316,15 @@ int32_t mctsb200_run_episodes(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg,
                               mctsb200_plan_stats* stats_out);
 
 /* ---- tree queries (info[:tree], value(), ranked_actions) ------------------------------------------ */
-/* Children of the root of tree root_i, in child order. Buffers hold >= n_actions entries. */
+/* Children of the root of tree root_i, in child order. Buffers hold >= n_actions entries (mctsb200_mdp_info). A continuous action
+ * space has no such bound: there this entry point only answers the count query (all three arrays NULL -> n_children, total_n) and
+ * refuses to write arrays (MCTSB200_ERR_UNSUPPORTED); use mctsb200_root_stats_n. */
 int32_t mctsb200_root_stats(mctsb200_ctx* ctx, int64_t root_i, int32_t* n_children, int32_t* action_idx,
                             int64_t* n, double* q, int64_t* total_n);
+/* The same with the arrays' capacity stated: at most `capacity` entries are written, n_children is the full count (two-call pattern:
+ * NULL arrays first). For every kind of tree. */
+int32_t mctsb200_root_stats_n(mctsb200_ctx* ctx, int64_t root_i, int64_t capacity, int32_t* n_children, int32_t* action_idx, int64_t* n,
+                              double* q, int64_t* total_n);
 
 typedef struct {
     int64_t n_state_nodes;

@@ -196,6 +196,7 @@ EXPORTED_SYMBOLS = (
     "mctsb200_set_timer",
     "mctsb200_root_parallel_decide",
     "mctsb200_root_stats",
+    "mctsb200_root_stats_n",
     "mctsb200_tree_sizes_query",
     "mctsb200_tree_export",
     "mctsb200_clear_trees",
@@ -241,6 +242,7 @@ def declare(lib: C.CDLL) -> C.CDLL:
     lib.mctsb200_set_timer.argtypes = [vp, TIMER_FN, vp]
     lib.mctsb200_root_parallel_decide.argtypes = [vp, vp, i32, dbl, P(i32), P(dbl), vp]
     lib.mctsb200_root_stats.argtypes = [vp, i64, P(i32), vp, vp, vp, P(i64)]
+    lib.mctsb200_root_stats_n.argtypes = [vp, i64, i64, P(i32), vp, vp, vp, P(i64)]
     lib.mctsb200_tree_sizes_query.argtypes = [vp, i64, P(TreeSizes)]
     lib.mctsb200_tree_export.argtypes = [vp, i64, P(TreeBuffers)]
     lib.mctsb200_clear_trees.argtypes = [vp]

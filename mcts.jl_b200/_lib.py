@@ -268,14 +268,18 @@ class Context:
         return a.value, bq.value, q
 
     # -- tree queries --
-    def root_stats(self, root_i: int, n_actions: int = 16) -> dict:
+    def root_stats(self, root_i: int, n_actions: Optional[int] = None) -> dict:
+        """Children of the root of tree root_i (mctsb200_root_stats_n, two calls: the count, then arrays of exactly that size -- a
+        continuous action space puts no bound on it). `n_actions` caps what is returned."""
         nch, tot = C.c_int32(), C.c_int64()
-        act = np.zeros(n_actions, dtype=np.int32)
-        n = np.zeros(n_actions, dtype=np.int64)
-        q = np.zeros(n_actions, dtype=np.float64)
-        self._check(self.lib.mctsb200_root_stats(self._h, int(root_i), C.byref(nch), _ptr(act), _ptr(n), _ptr(q), C.byref(tot)))
-        k = nch.value
-        return {"action_idx": act[:k].copy(), "n": n[:k].copy(), "q": q[:k].copy(), "total_n": tot.value}
+        self._check(self.lib.mctsb200_root_stats_n(self._h, int(root_i), 0, C.byref(nch), None, None, None, C.byref(tot)))
+        cap = nch.value if n_actions is None else min(int(n_actions), nch.value)
+        act = np.zeros(cap, dtype=np.int32)
+        n = np.zeros(cap, dtype=np.int64)
+        q = np.zeros(cap, dtype=np.float64)
+        if cap:
+            self._check(self.lib.mctsb200_root_stats_n(self._h, int(root_i), cap, C.byref(nch), _ptr(act), _ptr(n), _ptr(q), C.byref(tot)))
+        return {"action_idx": act, "n": n, "q": q, "total_n": tot.value}
 
     def tree_export(self, root_i: int, state_dtype=np.int64, state_width: int = 2) -> dict:
         """Two-call export into numpy arrays named after MCTSTree / DPWTree fields (ids are 1-based)."""

@@ -1655,7 +1655,10 @@ int32_t tree_export_impl(mctsb200_ctx* ctx, long long i, const mctsb200_tree_buf
 }
 
 template <class M>
-int32_t root_stats_impl(mctsb200_ctx* ctx, long long i, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q, int64_t* total_n) {
+// capacity: entries the caller's arrays hold (-1: the legacy entry point, "at least n_actions" -- which a continuous action space
+// cannot promise)
+int32_t root_stats_impl(mctsb200_ctx* ctx, long long i, long long capacity, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q,
+                        int64_t* total_n) {
     TreeHeader h;
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaMemcpy(&h, (const TreeHeader*)ctx->st.hdr.p + i, sizeof h, cudaMemcpyDeviceToHost));
@@ -1671,9 +1674,13 @@ int32_t root_stats_impl(mctsb200_ctx* ctx, long long i, int32_t* n_children, int
         CUDA_TRY(cudaMemcpy(&ax, (const Aux<M>*)ctx->st.aux.p + i * ctx->st.geo.NS + h.root, sizeof ax, cudaMemcpyDeviceToHost));
         if (n_children) *n_children = ax.nac[0];
         if (total_n) *total_n = rw0.total_n;
-        std::vector<int> kids((size_t)ax.nac[0]);
-        if (ax.nac[0]) CUDA_TRY(cudaMemcpy(kids.data(), (const int*)ctx->st.plog.p + i * ctx->st.geo.NP + ax.pbase[0], sizeof(int) * kids.size(), cudaMemcpyDeviceToHost));
-        for (int j = 0; j < ax.nac[0]; ++j) {
+        if (!action_idx && !n && !q) return MCTSB200_OK;  // the count query of the two-call pattern
+        if (capacity < 0)
+            return fail(MCTSB200_ERR_UNSUPPORTED, "a continuous action space puts no bound on a root's children (%d here): use mctsb200_root_stats_n", ax.nac[0]);
+        const int n_out = (int)std::min<long long>(capacity, ax.nac[0]);
+        std::vector<int> kids((size_t)n_out);
+        if (n_out) CUDA_TRY(cudaMemcpy(kids.data(), (const int*)ctx->st.plog.p + i * ctx->st.geo.NP + ax.pbase[0], sizeof(int) * kids.size(), cudaMemcpyDeviceToHost));
+        for (int j = 0; j < n_out; ++j) {
             BoxANode c;
             CUDA_TRY(cudaMemcpy(&c, (const BoxANode*)ctx->st.anodes.p + i * ctx->st.geo.NA + kids[(size_t)j], sizeof c, cudaMemcpyDeviceToHost));
             if (action_idx) action_idx[j] = j;
@@ -1686,7 +1693,8 @@ int32_t root_stats_impl(mctsb200_ctx* ctx, long long i, int32_t* n_children, int
         CUDA_TRY(cudaMemcpy(&rw, (const Row<M>*)ctx->st.rows.p + i * ctx->st.geo.NS + h.root, sizeof rw, cudaMemcpyDeviceToHost));
         if (n_children) *n_children = rw.nchild();
         if (total_n) *total_n = rw.total_n;
-        for (int j = 0; j < rw.nchild(); ++j) {
+        const int n_out = capacity < 0 ? rw.nchild() : (int)std::min<long long>(capacity, rw.nchild());
+        for (int j = 0; j < n_out; ++j) {
             if (action_idx) action_idx[j] = rw.alabel(j);
             if (n) n[j] = rw.n[j];
             if (q) q[j] = rw.q[j];
@@ -2433,18 +2441,27 @@ int32_t mctsb200_root_parallel_decide(const double* sum_n, const double* sum_nq,
     return MCTSB200_OK;
 }
 
-int32_t mctsb200_root_stats(mctsb200_ctx* ctx, int64_t root_i, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q, int64_t* total_n) {
+static int32_t root_stats_any(mctsb200_ctx* ctx, int64_t root_i, long long capacity, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q,
+                             int64_t* total_n) {
     if (ctx && !ctx->kids.empty()) {
         mctsb200_ctx* kid = nullptr;
         long long local = 0;
         if (int32_t e = group_locate(ctx, root_i, &kid, &local)) return e;
-        return mctsb200_root_stats(kid, local, n_children, action_idx, n, q, total_n);
+        return root_stats_any(kid, local, capacity, n_children, action_idx, n, q, total_n);
     }
     int32_t rc = check_tree_query(ctx, root_i);
     if (rc) return rc;
-#define MCTSB200_CALL(M) root_stats_impl<M>(ctx, root_i, n_children, action_idx, n, q, total_n)
+#define MCTSB200_CALL(M) root_stats_impl<M>(ctx, root_i, capacity, n_children, action_idx, n, q, total_n)
     MCTSB200_FOR_MDP(ctx, ctx->st.mdp_id, MCTSB200_CALL);
 #undef MCTSB200_CALL
+}
+int32_t mctsb200_root_stats(mctsb200_ctx* ctx, int64_t root_i, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q, int64_t* total_n) {
+    return root_stats_any(ctx, root_i, -1, n_children, action_idx, n, q, total_n);
+}
+int32_t mctsb200_root_stats_n(mctsb200_ctx* ctx, int64_t root_i, int64_t capacity, int32_t* n_children, int32_t* action_idx, int64_t* n, double* q,
+                              int64_t* total_n) {
+    if (capacity < 0) return fail(MCTSB200_ERR_INVALID_ARG, "capacity must be >= 0");
+    return root_stats_any(ctx, root_i, capacity, n_children, action_idx, n, q, total_n);
 }
 
 int32_t mctsb200_tree_sizes_query(mctsb200_ctx* ctx, int64_t root_i, mctsb200_tree_sizes* sizes) {

@@ -1,6 +1,7 @@
-"""Small plans through every kernel family, meant to be run under `compute-sanitizer --tool memcheck` (scripts/gpu_sanitize.sh):
+"""Small plans through every kernel family, meant to be run under `compute-sanitizer --tool memcheck python scripts/sanitize_small.py`:
 the lane-per-tree UCT and DPW kernels, the tile kernel (built-in MountainCar, every tile width), a run-time plugin (NVRTC-compiled
-tile kernel, unbounded branching), kept trees, the episode driver, tree export."""
+tile kernel, unbounded branching), continuous action spaces (built-in model and plugin; kept trees until their room is used up), kept trees of hashed
+models, _vis_stats, the episode driver, tree export."""
 import os
 import sys
 
@@ -44,5 +45,33 @@ for _ in range(3):
 p.run_episodes(gridworld_roots(40), 4, 3)
 m.solve(m.DPWSolver(n_iterations=40, depth=10, rng=10), noisy, ctx=ctx).run_episodes(mountaincar_roots(12), 3, 3)
 print("episodes done")
+# continuous action spaces: action-node table + arena, every tile width, kept trees up to MCTSB200_ERR_CAPACITY, episodes
+box, cp = m.GaussianBox(drift=0.2, cost=1.0, var=(0.05, 0.1, 0.02)), m.ContinuousPendulum()
+box_roots = [(0.0, 0.0, 0.0), (1.5, -2.0, 0.5), (-3.0, 3.0, -1.0)]
+for lanes in (0, 1, 4, 32):
+    plan(m.DPWSolver(n_iterations=150, depth=8, rng=11), box, box_roots, lanes)
+    plan(m.DPWSolver(n_iterations=150, depth=8, rng=12, check_repeat_action=False, check_repeat_state=False), box, box_roots, lanes)
+    plan(m.DPWSolver(n_iterations=150, depth=8, rng=13, estimate_value=m.RolloutEstimator(m.PluginPolicy(100), max_depth=12)), cp, [(0.02, 0.0), (-0.1, 0.05)], lanes)
+for mdp, roots in ((box, box_roots), (cp, [(0.02, 0.0), (-0.1, 0.05)])):
+    ctx.clear_trees()
+    try:
+        for call in range(6):
+            plan(m.DPWSolver(n_iterations=60, depth=6, rng=20 + call, keep_tree=True, keep_tree_calls=3), mdp, roots)
+        raise SystemExit("kept trees never ran out of room")
+    except m.MCTSB200Error as e:
+        assert e.status == m.abi.ERR_CAPACITY, e
+    ctx.clear_trees()
+    m.solve(m.DPWSolver(n_iterations=40, depth=6, rng=30, keep_tree=True), mdp, ctx=ctx).run_episodes(roots, 4, 3)
+print("continuous actions done")
+# kept trees of a hashed model, _vis_stats
+ctx.clear_trees()
+for call in range(3):
+    plan(m.DPWSolver(n_iterations=60, depth=12, rng=40 + call, keep_tree=True), mc, mountaincar_roots(6))
+ctx.clear_trees()
+plan(m.MCTSSolver(n_iterations=80, depth=10, exploration_constant=5.0, rng=50, enable_tree_vis=True), gw, gridworld_roots(12))
+ctx.tree_vis_stats(3)
+plan(m.MCTSSolver(n_iterations=80, depth=10, exploration_constant=3.0, rng=51, enable_tree_vis=True), mc, mountaincar_roots(5))
+ctx.tree_vis_stats(2)
+print("kept hashed trees / vis stats done")
 ctx.close()
 print("sanitize_small OK")

@@ -445,6 +445,30 @@ def test_emu_box_actions_episodes(emu_ctx, oracle, keep):
     assert st.n_simulations == 60 * 10 * 5
 
 
+def test_emu_box_root_stats_state_their_capacity(emu_ctx):
+    """A root over a continuous action space has as many children as the search gave it: mctsb200_root_stats ("buffers hold n_actions
+    entries") only answers the count there, mctsb200_root_stats_n writes at most `capacity` entries."""
+    mdp = m.GaussianBox()
+    cfg, keep = m.build_cfg(m.DPWSolver(n_iterations=300, depth=4, rng=1), mdp)
+    emu_ctx.configure(mdp.mdp_id, mdp.params())
+    emu_ctx.plan(cfg, mdp.mdp_id, mdp.encode_states(BOX_ROOTS[:2]))
+    lib, h = emu_ctx.lib, emu_ctx._h
+    nch, tot = C.c_int32(), C.c_int64()
+    assert lib.mctsb200_root_stats(h, 1, C.byref(nch), None, None, None, C.byref(tot)) == m.abi.OK and nch.value > 16
+    q = np.full(nch.value + 8, -7.0)
+    assert lib.mctsb200_root_stats(h, 1, C.byref(nch), None, None, q.ctypes.data_as(C.c_void_p), C.byref(tot)) == m.abi.ERR_UNSUPPORTED
+    assert lib.mctsb200_root_stats_n(h, 1, 5, C.byref(nch), None, None, q.ctypes.data_as(C.c_void_p), C.byref(tot)) == m.abi.OK
+    assert (q[5:] == -7.0).all() and (q[:5] != -7.0).all()
+    full = emu_ctx.root_stats(1)
+    assert len(full["q"]) == nch.value and np.array_equal(full["q"][:5], q[:5]) and len(emu_ctx.root_stats(1, 3)["n"]) == 3
+    # a finite action set through the same entry point
+    gw = m.SimpleGridWorld()
+    cfg2, keep2 = m.build_cfg(m.MCTSSolver(n_iterations=30, depth=5, rng=1), gw)
+    emu_ctx.configure(gw.mdp_id, gw.params())
+    emu_ctx.plan(cfg2, gw.mdp_id, gw.encode_states([(2, 2)]))
+    assert len(emu_ctx.root_stats(0)["q"]) == 4 and len(emu_ctx.root_stats(0, 2)["q"]) == 2
+
+
 def test_emu_box_actions_refuses_what_cannot_work(emu_ctx):
     mdp = m.GaussianBox()
     emu_ctx.configure(mdp.mdp_id, mdp.params())
