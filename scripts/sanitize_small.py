@@ -1,4 +1,6 @@
-"""Small plans through every kernel family, meant to be run under `compute-sanitizer --tool memcheck python scripts/sanitize_small.py`:
+"""Small plans through every kernel family: on the GPU box `python scripts/sanitize_small.py` (under compute-sanitizer where the pool
+allows it), here `python scripts/sanitize_small.py --emu <host-emulation library>` under AddressSanitizer (scripts/asan_emu.sh; run-time
+plugins are device-only and skipped there):
 the lane-per-tree UCT and DPW kernels, the tile kernel (built-in MountainCar, every tile width), a run-time plugin (NVRTC-compiled
 tile kernel, unbounded branching), continuous action spaces (built-in model and plugin; kept trees until their room is used up), kept trees of hashed
 models, _vis_stats, the episode driver, tree export."""
@@ -11,8 +13,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import mcts_jl_b200 as m
 from mcts_jl_b200.workloads import gridworld_roots, mountaincar_roots
 
-ctx = m.Context(0)
-gw, mc, noisy = m.SimpleGridWorld(), m.MountainCar(), m.NoisyMountainCar()
+EMU = sys.argv[2] if len(sys.argv) > 2 and sys.argv[1] == "--emu" else None
+ctx = m.Context(0, lib_path=EMU) if EMU else m.Context(0)
+gw, mc = m.SimpleGridWorld(), m.MountainCar()
+noisy = None if EMU else m.NoisyMountainCar()
 
 
 def plan(solver, mdp, roots, lanes=0, export=True):
@@ -34,7 +38,7 @@ for lanes in (1, 2, 4, 8, 16, 32):
     plan(m.MCTSSolver(n_iterations=60, depth=20, exploration_constant=3.0, rng=4), mc, mountaincar_roots(9), lanes)
     plan(m.DPWSolver(n_iterations=60, depth=10, rng=5), gw, gridworld_roots(9), lanes)  # tile kernel on the dense-state model
 print("tile widths done")
-for lanes in (0, 1, 8):
+for lanes in (0, 1, 8) if noisy else ():
     plan(m.DPWSolver(n_iterations=120, depth=20, rng=6), noisy, mountaincar_roots(9), lanes)
     plan(m.DPWSolver(n_iterations=80, depth=20, rng=7, check_repeat_state=False), noisy, mountaincar_roots(9), lanes)
     plan(m.MCTSSolver(n_iterations=80, depth=20, exploration_constant=3.0, rng=8), noisy, mountaincar_roots(9), lanes)
@@ -43,16 +47,20 @@ p = m.solve(m.MCTSSolver(n_iterations=40, depth=10, exploration_constant=5.0, re
 for _ in range(3):
     p.action_batch(gridworld_roots(40))
 p.run_episodes(gridworld_roots(40), 4, 3)
-m.solve(m.DPWSolver(n_iterations=40, depth=10, rng=10), noisy, ctx=ctx).run_episodes(mountaincar_roots(12), 3, 3)
+m.solve(m.DPWSolver(n_iterations=40, depth=10, rng=10), noisy or mc, ctx=ctx).run_episodes(mountaincar_roots(12), 3, 3)
+p.action_root_parallel((1, 1), 37)
 print("episodes done")
 # continuous action spaces: action-node table + arena, every tile width, kept trees up to MCTSB200_ERR_CAPACITY, episodes
-box, cp = m.GaussianBox(drift=0.2, cost=1.0, var=(0.05, 0.1, 0.02)), m.ContinuousPendulum()
+box, cp = m.GaussianBox(drift=0.2, cost=1.0, var=(0.05, 0.1, 0.02)), None if EMU else m.ContinuousPendulum()
 box_roots = [(0.0, 0.0, 0.0), (1.5, -2.0, 0.5), (-3.0, 3.0, -1.0)]
 for lanes in (0, 1, 4, 32):
     plan(m.DPWSolver(n_iterations=150, depth=8, rng=11), box, box_roots, lanes)
     plan(m.DPWSolver(n_iterations=150, depth=8, rng=12, check_repeat_action=False, check_repeat_state=False), box, box_roots, lanes)
-    plan(m.DPWSolver(n_iterations=150, depth=8, rng=13, estimate_value=m.RolloutEstimator(m.PluginPolicy(100), max_depth=12)), cp, [(0.02, 0.0), (-0.1, 0.05)], lanes)
+    if cp:
+        plan(m.DPWSolver(n_iterations=150, depth=8, rng=13, estimate_value=m.RolloutEstimator(m.PluginPolicy(100), max_depth=12)), cp, [(0.02, 0.0), (-0.1, 0.05)], lanes)
 for mdp, roots in ((box, box_roots), (cp, [(0.02, 0.0), (-0.1, 0.05)])):
+    if mdp is None:
+        continue
     ctx.clear_trees()
     try:
         for call in range(6):

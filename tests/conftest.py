@@ -54,6 +54,8 @@ def oracle_libm():
 @pytest.fixture(scope="session")
 def emu_lib_path():
     """Host emulation build of the library sources (tests only; see tests/emu/cuda_shim.h)."""
+    if os.environ.get("MCTSB200_EMU_LIB"):  # another build of the emulation (scripts/asan_emu.sh: the AddressSanitizer one)
+        return os.environ["MCTSB200_EMU_LIB"]
     res = subprocess.run(["make", "-C", EMU_DIR], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     return EMU_LIB
