@@ -158,6 +158,10 @@ typedef struct {
                                      tree's _vis_stats (src/vanilla.jl:268-270, 328-334), for D3Tree(::MCTSTree); vanilla UCT on
                                      models with bounded branching (max_branch >= 1) only                                */
     int32_t reserved1;
+    const int32_t* next_action_table; /* DPWSolver.next_action as a state-only function f(mdp, s, snode) (src/action_gen.jl:14,
+                                     test/options.jl:50), tabulated by the host over a dense state space: the action index action
+                                     widening proposes at a state, [n_states]; draws no random number. NULL = RandomActionGenerator
+                                     (src/action_gen.jl:11-13). Host pointer; dense-state MDPs only */
 } mctsb200_solver_cfg;
 
 /* Work counters of one plan call (sums over all trees of the call). "Simulation" = one iteration of
@@ -233,7 +237,7 @@ int32_t mctsb200_mdp_configure(mctsb200_ctx* ctx, int32_t mdp_id, const void* po
  * room for keep_tree_calls calls. */
 int32_t mctsb200_mdp_register(const char* name, const char* cuda_source, const char* plugin_struct, int32_t state_doubles,
                               int32_t n_actions, int32_t max_branch, int32_t* mdp_id_out);
-/* The same for a CONTINUOUS action space (actions(mdp) = a Box of `action_doubles` float64 coordinates, 1 or 2; the reference's
+/* The same for a CONTINUOUS action space (actions(mdp) = a Box of `action_doubles` float64 coordinates, 1 to 4; the reference's
  * test/discussion_514.jl with a model of the caller's own): the struct defines is_terminal, next_action (the action DPW's action
  * widening proposes: next_action(gen, mdp, s, snode), src/dpw.jl:98 -- for the default RandomActionGenerator a draw from the Box,
  * src/action_gen.jl:11-13), gen(params, s, a, rng, sp, r) with `a` the action vector, and policy_action for rollout policies

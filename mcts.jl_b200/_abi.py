@@ -112,6 +112,7 @@ class SolverCfg(C.Structure):
         ("policy_table", C.POINTER(C.c_int32)),
         ("enable_tree_vis", C.c_int32),
         ("reserved1", C.c_int32),
+        ("next_action_table", C.POINTER(C.c_int32)),
     ]
 
 

@@ -119,7 +119,7 @@ struct mctsb200_ctx {
 
     Storage st;
     DevBuf counters, log_tab, sqrtlog_tab, rsqrt_tab, nmin_state, init_q, init_n, value_tab, io_roots, io_action, io_bestq, io_status, sums;
-    DevBuf order, order_bins, policy_tab, nmin_action_tab;
+    DevBuf order, order_bins, policy_tab, nmin_action_tab, next_action_tab;
     double gw_reward_max = 0.0;
     bool gw_fast_det = false;
     // host hooks run between launches (mctsb200_set_progress_callback / mctsb200_set_timer)
@@ -604,6 +604,17 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
             CUDA_TRY(cudaMemcpy(ctx->policy_tab.p, pol.data(), pol.size(), cudaMemcpyHostToDevice));
             d.policy_table = (const unsigned char*)ctx->policy_tab.p;
         }
+    }
+    if (cfg->next_action_table && cfg->kind == MCTSB200_KIND_DPW && cfg->enable_action_pw) {
+        if (!M::kDense || dense <= 0) return fail(MCTSB200_ERR_UNSUPPORTED, "a tabulated next_action needs a dense-state MDP");
+        std::vector<unsigned char> tab((size_t)dense);
+        for (int i = 0; i < dense; ++i) {
+            if (cfg->next_action_table[i] < 0 || cfg->next_action_table[i] >= A) return fail(MCTSB200_ERR_INVALID_ARG, "next_action_table entry %d out of range", i);
+            tab[(size_t)i] = (unsigned char)cfg->next_action_table[i];
+        }
+        CUDA_TRY(ctx->next_action_tab.ensure(tab.size()));
+        CUDA_TRY(cudaMemcpy(ctx->next_action_tab.p, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+        d.next_action_table = (const unsigned char*)ctx->next_action_tab.p;
     }
     if (cfg->init_q_table) {
         const size_t bytes = sizeof(double) * (size_t)dense * A;
@@ -1889,10 +1900,14 @@ using Custom43 = CustomDev<4, 3>;
 using Custom44 = CustomDev<4, 4>;
 using CustomBox21 = CustomBoxDev<2, 1>;
 using CustomBox22 = CustomBoxDev<2, 2>;
+using CustomBox23 = CustomBoxDev<2, 3>;
+using CustomBox24 = CustomBoxDev<2, 4>;
 using CustomBox41 = CustomBoxDev<4, 1>;
 using CustomBox42 = CustomBoxDev<4, 2>;
+using CustomBox43 = CustomBoxDev<4, 3>;
+using CustomBox44 = CustomBoxDev<4, 4>;
 bool plugin_shape_ok(int sd, int a) { return (sd == 2 || sd == 4) && a >= 2 && a <= 4; }
-bool plugin_box_shape_ok(int sd, int ad) { return (sd == 2 || sd == 4) && (ad == 1 || ad == 2); }
+bool plugin_box_shape_ok(int sd, int ad) { return (sd == 2 || sd == 4) && ad >= 1 && ad <= 4; }
 #define MCTSB200_FOR_PLUGIN(ctx, mdp_id, CALL)                                                              \
     if ((mdp_id) >= MCTSB200_MDP_PLUGIN_BASE) {                                                             \
         const mctsb200_rt::PluginInfo* pi__ = mctsb200_rt::plugin_info((mdp_id) - MCTSB200_MDP_PLUGIN_BASE); \
@@ -1904,6 +1919,10 @@ bool plugin_box_shape_ok(int sd, int ad) { return (sd == 2 || sd == 4) && (ad ==
                 case 220: return CALL(CustomBox22);                                                         \
                 case 140: return CALL(CustomBox41);                                                         \
                 case 240: return CALL(CustomBox42);                                                         \
+                case 320: return CALL(CustomBox23);                                                         \
+                case 420: return CALL(CustomBox24);                                                         \
+                case 340: return CALL(CustomBox43);                                                         \
+                case 440: return CALL(CustomBox44);                                                         \
                 case 22: return CALL(Custom22);                                                             \
                 case 23: return CALL(Custom23);                                                             \
                 case 24: return CALL(Custom24);                                                             \
@@ -1983,7 +2002,7 @@ int32_t mctsb200_ctx_destroy(mctsb200_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->gw_reward, &c->gw_term, &c->st.hdr, &c->st.rows, &c->st.rows_fast, &c->st.trans_fast, &c->st.aux, &c->st.trans, &c->st.map, &c->st.path, &c->st.plog, &c->st.anodes, &c->st.action_vec, &c->st.vis, &c->nmin_action_tab, &c->counters,
                       &c->log_tab, &c->sqrtlog_tab, &c->rsqrt_tab, &c->nmin_state, &c->init_q, &c->init_n, &c->value_tab, &c->io_roots, &c->io_action, &c->io_bestq, &c->io_status,
-                      &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->gw_fast,
+                      &c->sums, &c->order, &c->order_bins, &c->policy_tab, &c->next_action_tab, &c->gw_fast,
                       &c->ep_states, &c->ep_disc, &c->ep_ret, &c->ep_steps, &c->ep_active, &c->ep_count};
     for (DevBuf* b : bufs) b->release();
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -2155,7 +2174,7 @@ int32_t mctsb200_mdp_register_continuous(const char* name, const char* cuda_sour
     if (!std::strcmp(name, "SimpleGridWorld") || !std::strcmp(name, "MountainCar") || !std::strcmp(name, "GaussianBox"))
         return fail(MCTSB200_ERR_INVALID_ARG, "'%s' is a built-in MDP", name);
     if (!plugin_box_shape_ok(state_doubles, action_doubles))
-        return fail(MCTSB200_ERR_UNSUPPORTED, "plugin shape (%d state doubles, %d action doubles) is not available: state_doubles 2 or 4, action_doubles 1 or 2",
+        return fail(MCTSB200_ERR_UNSUPPORTED, "plugin shape (%d state doubles, %d action doubles) is not available: state_doubles 2 or 4, action_doubles 1 to 4",
                     state_doubles, action_doubles);
     mctsb200_rt::PluginInfo info;
     info.name = name;

@@ -242,6 +242,7 @@ struct DevCfg {
     const double* rsqrt_tab;     // device: 1/sqrt(n) for n < rsqrt_tab_n     (fast-path score)
     const int* nmin_state;       // device: min n[sanode] for which n_a_children == len may widen
     const unsigned char* policy_table;  // device, may be null: tabulated state-only rollout policy [dense index] (uct_fast.cuh)
+    const unsigned char* next_action_table;  // device, may be null: DPW's next_action as a state-only function [dense index]
     int log_tab_n;
     int rsqrt_tab_n;
     int nmin_state_n;

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
         const int TERM = ft.term;
         const double gamma = M::discount(args.mdp), eps = cfg.rollout_eps, c_ucb = cfg.c;
         const bool apw = cfg.enable_action_pw != 0, spw = cfg.enable_state_pw != 0;
+        const unsigned char* const natab = cfg.next_action_table;
         // min n[sanode] for which an action node with 1..4 distinct successors may widen (src/dpw.jl:121); kept in registers
         const int nmin_s1 = 1 < cfg.nmin_state_n ? __ldg(cfg.nmin_state + 1) : 0x7fffffff;
         const int nmin_s2 = 2 < cfg.nmin_state_n ? __ldg(cfg.nmin_state + 2) : 0x7fffffff;
@@ -195,7 +196,13 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                     if (apw) {
                         // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action[len]
                         if (N >= cfg.nmin_action[nchild]) {
-                            if (nchild == A) {
+                            if (natab) {  // next_action(f::Function, ...) = f(mdp, s, snode), tabulated over the states: no draw
+                                const int act = (int)natab[cell];
+                                bool present = false;
+#pragma unroll
+                                for (int t = 0; t < A; ++t) present |= t < nchild && dpw_label(k[t].tag) == act;
+                                if (!present) add_child(act);
+                            } else if (nchild == A) {
                                 skip_word();  // next_action(::RandomActionGenerator) draws, but every action is a child already
                             } else {
                                 const int act = (int)__umulhi(next_word(), (uint32_t)A);

@@ -861,10 +861,15 @@ struct Search {
 #endif
                     // next_action(::RandomActionGenerator) always draws; a node that owns every action cannot gain one (check_repeat_action
                     // is always on here, see capi.cu), so the word is consumed unread
+                    bool tabulated = false;
+                    if constexpr (M::kDense) tabulated = a.cfg.next_action_table != nullptr;
                     if (nchild == A) {
-                        rng.skip();
+                        if (!tabulated) rng.skip();
                     } else {
-                        const int act = rng.uniform_int(A);
+                        // next_action(f::Function, mdp, s, snode) = f(mdp, s, snode) (src/action_gen.jl:14), tabulated: no draw
+                        int act;
+                        if (tabulated) act = (int)a.cfg.next_action_table[M::dense_index(a.mdp, s)];
+                        else act = rng.uniform_int(A);
                         bool present = false;
                         const uint32_t pk = R.packed;
 #pragma unroll

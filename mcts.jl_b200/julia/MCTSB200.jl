@@ -50,6 +50,7 @@ struct SolverCfg                       # mctsb200_solver_cfg
     seed::UInt64
     init_q_table::Ptr{Float64}; init_n_table::Ptr{Int64}; value_table::Ptr{Float64}; policy_table::Ptr{Int32}
     enable_tree_vis::Int32; reserved1::Int32
+    next_action_table::Ptr{Int32}      # DPW's next_action as a state-only function, tabulated (NULL = RandomActionGenerator)
 end
 
 mutable struct PlanStats               # mctsb200_plan_stats
@@ -177,18 +178,30 @@ function cfg_from(s::MCTSSolver, mdp)
     cfg = SolverCfg(sizeof(SolverCfg), KIND_UCT, s.n_iterations, s.depth, 1, s.exploration_constant, s.max_time,
                     0.0, 0.0, 0.0, 0.0, 0, 0, 1, 1, s.reuse_tree, 0, numeric(s.init_Q, "init_Q"), numeric(s.init_N, "init_N"),
                     ek, pol, ec, par, rmd, 0, eps, seed_of(s.rng), C_NULL, C_NULL, C_NULL, tab === nothing ? C_NULL : pointer(tab),
-                    s.enable_tree_vis, 0)   # enable_tree_vis: _vis_stats recorded on the device (src/vanilla.jl:268-270)
+                    s.enable_tree_vis, 0, C_NULL)   # enable_tree_vis: _vis_stats recorded on the device (src/vanilla.jl:268-270)
     return cfg, tab
 end
 function cfg_from(s::DPWSolver, mdp)
     s.show_progress && unsupported("`show_progress`")
-    s.next_action isa MCTS.RandomActionGenerator || unsupported("a custom `next_action`")
+    # next_action(f::Function, mdp, s, snode) = f(mdp, s, snode) (src/action_gen.jl:14; test/options.jl:50): a function that looks at the
+    # state only is a table over a dense state space (snode is passed as `nothing`: a generator that inspects the node is refused)
+    natab = nothing
+    if !(s.next_action isa MCTS.RandomActionGenerator)
+        n = n_dense_states(mdp)
+        (s.next_action isa Function && n > 0) || unsupported("a custom `next_action` object, or one on an MDP without a dense state index")
+        natab = try
+            Int32[action_index(mdp, s.next_action(mdp, dense_state(mdp, i), nothing)) for i in 0:n-1]
+        catch
+            unsupported("a `next_action` that inspects the tree node")
+        end
+    end
     ek, ec, pol, par, rmd, eps, tab = rollout_fields(s.estimate_value, mdp)
     cfg = SolverCfg(sizeof(SolverCfg), KIND_DPW, s.n_iterations, s.depth, 1, s.exploration_constant, s.max_time,
                     s.k_action, s.alpha_action, s.k_state, s.alpha_state, s.enable_action_pw, s.enable_state_pw,
                     s.check_repeat_state, s.check_repeat_action, s.keep_tree, 0, numeric(s.init_Q, "init_Q"), numeric(s.init_N, "init_N"),
-                    ek, pol, ec, par, rmd, 0, eps, seed_of(s.rng), C_NULL, C_NULL, C_NULL, tab === nothing ? C_NULL : pointer(tab), 0, 0)
-    return cfg, tab
+                    ek, pol, ec, par, rmd, 0, eps, seed_of(s.rng), C_NULL, C_NULL, C_NULL, tab === nothing ? C_NULL : pointer(tab), 0, 0,
+                    natab === nothing ? C_NULL : pointer(natab))
+    return cfg, (tab, natab)
 end
 
 # ---- planners --------------------------------------------------------------------------------------------

@@ -142,7 +142,7 @@ class DPWSolver:
     estimate_value: Any = field(default_factory=RolloutEstimator)
     init_Q: Any = 0.0
     init_N: Any = 0
-    next_action: Any = None  # None = RandomActionGenerator(rng)
+    next_action: Any = None  # None = RandomActionGenerator(rng); f(mdp, s, snode) looking at s only: tabulated (dense-state MDPs)
     default_action: Any = field(default_factory=ExceptionRethrow)
     reset_callback: Optional[Callable] = None
     show_progress: bool = False
@@ -203,7 +203,19 @@ def build_cfg(solver, mdp) -> tuple[abi.SolverCfg, list]:
         if solver.show_progress:
             raise _unsupported("`show_progress`")
         if solver.next_action is not None:
-            raise _unsupported("a custom `next_action` (only RandomActionGenerator)")
+            # next_action(f::Function, mdp, s, snode) = f(mdp, s, snode) (src/action_gen.jl:14; test/options.jl:50 `(mdp, s, snode)->:up`):
+            # a host function cannot run inside the search, but one that looks at the state only is a table over a dense state space
+            if not callable(solver.next_action):
+                raise TypeError("next_action must be callable as f(mdp, s, snode)")  # the reference's MethodError for `next_action="bad"`
+            if not getattr(mdp, "dense", False) or getattr(mdp, "action_width", 0):
+                raise _unsupported("a custom `next_action` on an MDP without a dense state index (write it into the device plugin's next_action)")
+            try:
+                tab = np.ascontiguousarray([mdp.action_index(solver.next_action(mdp, mdp.state_from_index(i), None)) for i in range(mdp.n_states())],
+                                           dtype=np.int32)
+            except (AttributeError, TypeError) as e:
+                raise _unsupported(f"a `next_action` that inspects the tree node (snode is not available on the host: {e})")
+            keep.append(tab)
+            cfg.next_action_table = tab.ctypes.data_as(C.POINTER(C.c_int32))
         cfg.k_action, cfg.alpha_action = float(solver.k_action), float(solver.alpha_action)
         cfg.k_state, cfg.alpha_state = float(solver.k_state), float(solver.alpha_state)
         cfg.enable_action_pw = int(bool(solver.enable_action_pw))

@@ -934,7 +934,17 @@ struct DPWPlanner {
         // action progressive widening
         if (cfg.enable_action_pw) {
             if ((double)children[snode - 1].size() <= cfg.k_action * std::pow((double)total_n[snode - 1], cfg.alpha_action)) {
-                const Act a = mdp.next_action(s, *rng);  // next_action(::RandomActionGenerator) = rand(rng, actions(mdp, s))
+                Act a;
+                bool tabulated = false;
+                if constexpr (M::kActionDoubles == 0) {
+                    // next_action(f::Function, mdp, s, snode) = f(mdp, s, snode) (src/action_gen.jl:14; test/options.jl:50) for a state-only f,
+                    // tabulated over the dense state space: draws nothing
+                    if (cfg.next_action_table && mdp.state_index(s) >= 0) {
+                        a = cfg.next_action_table[mdp.state_index(s)];
+                        tabulated = true;
+                    }
+                }
+                if (!tabulated) a = mdp.next_action(s, *rng);  // next_action(::RandomActionGenerator) = rand(rng, actions(mdp, s))
                 if (!cfg.check_repeat_action || !a_lookup.count({snode, M::action_key(a)})) {
                     const int64_t n0 = hooks.init_N(s, a);
                     insert_action_node(snode, a, n0, hooks.init_Q(s, a), cfg.check_repeat_action != 0);

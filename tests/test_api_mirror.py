@@ -60,9 +60,20 @@ def test_option_matrix_like_options_jl(ctx):
     # launches (tested below)
     _, info = m.solve(m.MCTSSolver(n_iterations=30, depth=5, enable_tree_vis=True), GW, ctx=ctx).action_info((1, 1))
     assert sum(info["tree"]._vis_stats.values()) >= 30
-    for kw in (dict(reset_callback=lambda mdp, s: None), dict(show_progress=True), dict(next_action=lambda *a: "up")):
+    for kw in (dict(reset_callback=lambda mdp, s: None), dict(show_progress=True)):
         with pytest.raises(m.MCTSB200Error):
             m.solve(m.DPWSolver(**kw), GW, ctx=ctx)
+    # next_action=(mdp, s, snode)->:up (test/options.jl:50): a generator that looks at the state only is tabulated; every state node then
+    # owns the one action it proposes
+    p = m.solve(m.DPWSolver(n_iterations=60, depth=5, exploration_constant=5.0, next_action=lambda mdp, s, snode: "up"), GW, ctx=ctx)
+    a, info = p.action_info((3, 3), tree_in_info=True)
+    assert a == "up" and set(int(x) for x in info["tree"].a_labels) == {GW.action_index("up")}
+    with pytest.raises(TypeError):  # test/options.jl:52: next_action="bad" is a MethodError
+        m.solve(m.DPWSolver(next_action="bad"), GW, ctx=ctx)
+    with pytest.raises(m.MCTSB200Error):  # the node itself is not available to a host function
+        m.solve(m.DPWSolver(next_action=lambda mdp, s, snode: snode.tree), GW, ctx=ctx)
+    with pytest.raises(m.MCTSB200Error):  # no dense state index to tabulate over
+        m.solve(m.DPWSolver(next_action=lambda mdp, s, snode: 1.0), m.MountainCar(), ctx=ctx)
     # RolloutEstimator(x -> :up) (test/options.jl:29): a state-only function is tabulated over the dense state space
     assert m.solve(m.MCTSSolver(n_iterations=20, depth=5, estimate_value=m.RolloutEstimator(lambda s: "up")), GW, ctx=ctx).action((1, 1)) in GW.actions
     with pytest.raises(m.MCTSB200Error):  # ... which a hashed-state model does not have

@@ -633,6 +633,13 @@ def test_plugin_continuous_actions_refusals(gpu_ctx):
 
 
 @pytest.mark.parametrize("fast", ["1", "0"])
+def test_next_action_as_a_state_only_function(gpu_ctx, oracle, monkeypatch, fast):
+    from test_host_emu_parity import test_emu_next_action_as_a_state_only_function as body
+
+    body(gpu_ctx, oracle, monkeypatch, fast)
+
+
+@pytest.mark.parametrize("fast", ["1", "0"])
 def test_function_policy_is_a_table_on_the_device(gpu_ctx, oracle, monkeypatch, fast):
     from test_host_emu_parity import test_emu_function_policy_is_a_table_on_the_device as body
 

@@ -408,6 +408,23 @@ def test_emu_box_actions_option_matrix(emu_ctx, oracle, opts):
     assert all(mdp.action_in_space(a) for a in v)
 
 
+@pytest.mark.parametrize("fast", ["1", "0"])
+def test_emu_next_action_as_a_state_only_function(emu_ctx, oracle, monkeypatch, fast):
+    """DPWSolver(next_action=(mdp, s, snode)->:up) (test/options.jl:50; src/action_gen.jl:14): tabulated over the dense state space, the
+    action widening proposes table[s] and draws no random number. Lane-per-tree and tile kernel against the oracle."""
+    monkeypatch.setenv("MCTSB200_FAST", fast)
+    roots = gridworld_roots(24)
+    gens = (lambda mdp, s, snode: "up",
+            lambda mdp, s, snode: ("right" if s[0] < 9 else "up") if (s[0] + s[1]) % 3 else "left")  # (the terminal state is (-1, -1))
+    for gen in gens:
+        for kw in (dict(), dict(k_action=2.0, alpha_action=0.3, init_Q=1.5, init_N=2), dict(estimate_value=0.0, enable_state_pw=False)):
+            s = m.DPWSolver(n_iterations=80, depth=8, exploration_constant=4.0, rng=12, next_action=gen, **kw)
+            _, _, _, st = run_both(emu_ctx, oracle, s, GW, roots, compare_trees=range(0, 24, 5))
+            assert st.kernel_variant == int(fast) or kw  # (the lane-per-tree kernel takes rollout estimates only)
+    t = emu_ctx.tree_export(0)
+    assert (np.diff(t["child_offsets"]) <= 1).all()  # one proposal per state: at most one child
+
+
 def _box_kept_trees(ctx, orc, mdp, roots, lanes=None):
     """keep_tree over a continuous action space (src/dpw.jl:31-37): a 4-call sequence in which every root moves on to a successor its
     own tree already holds (the second state node: the first successor the search generated), trees compared after every call."""

@@ -69,7 +69,7 @@ def test_argument_checks():
 
 def test_continuous_action_plugins_compile():
     """mctsb200_mdp_register_continuous: actions(mdp) = a Box (test/discussion_514.jl) for a model the caller brings. The DPW program
-    compiles at registration, for every host shape (2 / 4 state doubles x 1 / 2 action doubles); the interface is checked there."""
+    compiles at registration, for the host shapes 2 / 4 state doubles x 1 ... 4 action doubles; the interface is checked there."""
     from mcts_jl_b200._lib import register_mdp_continuous
 
     cp = m.ContinuousPendulum()
@@ -89,7 +89,9 @@ def test_continuous_action_plugins_compile():
            register_mdp_continuous("CP42", wide.replace("rng.uniform01()));\n    }", "rng.uniform01()));\n        a[1] = rng.uniform01();\n    }", 1)
                                    .replace("        a[0] = u;\n", "        a[0] = u;\n        a[1] = 0.0;\n"), "ContinuousPendulum", 4, 2)}
     assert len(ids) == 3 and a not in ids
-    for sd, ad in [(2, 3), (3, 1), (2, 0), (8, 2)]:
+    three = two.replace("        a[1] = rng.uniform01();\n", "        a[1] = rng.uniform01();\n        a[2] = rng.uniform01();\n").replace("        a[1] = 0.0;\n", "        a[1] = 0.0;\n        a[2] = 0.0;\n")
+    assert register_mdp_continuous("CP23", three, "ContinuousPendulum", 2, 3) not in ids | {a}
+    for sd, ad in [(2, 5), (3, 1), (2, 0), (8, 2)]:
         with pytest.raises(m.MCTSB200Error) as e:
             register_mdp_continuous("ShapeC", cp.source, "ContinuousPendulum", sd, ad)
         assert e.value.status == abi.ERR_UNSUPPORTED
