@@ -837,6 +837,7 @@ int fast_variant(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, long long pr
         // (iteration, level) tags of the children: 24 bits of iteration for UCT, 16 for DPW
         if (cfg->depth > 254 || cfg->n_iterations >= (KIND == MCTSB200_KIND_UCT ? (1LL << 24) - 1 : (1LL << 16) - 1)) return -1;
         if (KIND == MCTSB200_KIND_DPW && !(cfg->check_repeat_state && cfg->check_repeat_action)) return -1;  // unmerged nodes: tile kernel
+        if (KIND == MCTSB200_KIND_DPW && cfg->next_action_table) return -1;  // a tabulated next_action: tile kernel
         (void)prior_visits;  // (visit counts beyond the UCB tables take the exact path inside the kernels)
         if (fast_smem_bytes<M>(MdpAccess<M>::params(ctx), std::max(cfg->depth, 1), 64) > kFastSmemLimit) return -1;
         switch (cfg->rollout_policy) {
@@ -993,7 +994,8 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             launches += 3;
         }
     }
-    if ((fast >= 0 || G == 1) && !args.order && !cfg->keep_tree && root_stride == 1 && n_trees < (1LL << 30)) {
+    // (root_stride 0 = an ensemble of one root, mctsb200_plan_root_parallel: the lanes do not run in lockstep either)
+    if ((fast >= 0 || G == 1) && !args.order && !cfg->keep_tree && n_trees < (1LL << 30)) {
         // lanes that do not run in lockstep: spread the trees over more warps while one wave of blocks still holds them all
         int spread = 1;
         const char* ev = std::getenv("MCTSB200_SPREAD");
@@ -1005,8 +1007,12 @@ int32_t run_search(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, const type
             if (cfg->rollouts_per_leaf == 1 && n_trees * 32 <= (long long)tile_occupancy<M, KIND>(ctx, 1, smem1) * kBlockThreads * ctx->sm_count) spread = 32;
         } else if (!MdpAccess<M>::lockstep(ctx, cfg)) {
             // (measured on B200: pays up to about 8 warps per SM, config 3 +2.5 %, 4096 DPW roots +24 %; beyond that the wider
-            // footprint in L1/L2 eats the gain)
-            for (int s2 = 2; s2 <= 8; s2 *= 2)
+            // footprint in L1/L2 eats the gain). A warp's iteration lasts as long as the longest descent plus the longest rollout
+            // plus the longest backup among its lanes; with one or two trees per warp that sum shrinks to the tree's own -- for
+            // vanilla UCT down to one tree per warp (1 184 trees: 14.5 ms against 18.4 ms at four per warp), not for DPW
+            // (profiles/r2_experiments.md)
+            const int max_spread = KIND == MCTSB200_KIND_UCT ? 32 : 8;
+            for (int s2 = 2; s2 <= max_spread; s2 *= 2)
                 if ((n_trees * s2 + 31) / 32 <= (long long)ctx->sm_count * 8) spread = s2;
         }
         if (spread == 2 || spread == 4 || spread == 8 || spread == 16 || spread == 32) {

@@ -2,7 +2,8 @@
 // cells), the DPW counterpart of uct_fast.cuh: one lane per tree, model tables in shared memory, direct-indexed
 // interleaved rows, load-free backup. Same algorithm, arithmetic and results as search_kernel<M, DPW, 1>
 // (search.cuh); it applies when states and actions are merged (check_repeat_state, check_repeat_action: the
-// reference's defaults), one rollout per leaf, c > 0.
+// reference's defaults), one rollout per leaf, c > 0, next_action = RandomActionGenerator (a tabulated generator costs this
+// kernel 1.4 % even when absent: the tile kernel takes those calls).
 //
 // Reference lines restated: simulate src/dpw.jl:80-154 (action widening :94-114, state widening :119-141),
 // best_sanode_UCB :179-199, insert_state_node!/insert_action_node! src/dpw_types.jl:162-186,
@@ -109,7 +110,6 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
         const int TERM = ft.term;
         const double gamma = M::discount(args.mdp), eps = cfg.rollout_eps, c_ucb = cfg.c;
         const bool apw = cfg.enable_action_pw != 0, spw = cfg.enable_state_pw != 0;
-        const unsigned char* const natab = cfg.next_action_table;
         // min n[sanode] for which an action node with 1..4 distinct successors may widen (src/dpw.jl:121); kept in registers
         const int nmin_s1 = 1 < cfg.nmin_state_n ? __ldg(cfg.nmin_state + 1) : 0x7fffffff;
         const int nmin_s2 = 2 < cfg.nmin_state_n ? __ldg(cfg.nmin_state + 2) : 0x7fffffff;
@@ -196,13 +196,7 @@ __global__ void __launch_bounds__(kFastMaxThreads, 1) dpw_fast_kernel(const __gr
                     if (apw) {
                         // length(children) <= k_action * total_n^alpha_action  <=>  total_n >= nmin_action[len]
                         if (N >= cfg.nmin_action[nchild]) {
-                            if (natab) {  // next_action(f::Function, ...) = f(mdp, s, snode), tabulated over the states: no draw
-                                const int act = (int)natab[cell];
-                                bool present = false;
-#pragma unroll
-                                for (int t = 0; t < A; ++t) present |= t < nchild && dpw_label(k[t].tag) == act;
-                                if (!present) add_child(act);
-                            } else if (nchild == A) {
+                            if (nchild == A) {
                                 skip_word();  // next_action(::RandomActionGenerator) draws, but every action is a child already
                             } else {
                                 const int act = (int)__umulhi(next_word(), (uint32_t)A);

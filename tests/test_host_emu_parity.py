@@ -411,7 +411,7 @@ def test_emu_box_actions_option_matrix(emu_ctx, oracle, opts):
 @pytest.mark.parametrize("fast", ["1", "0"])
 def test_emu_next_action_as_a_state_only_function(emu_ctx, oracle, monkeypatch, fast):
     """DPWSolver(next_action=(mdp, s, snode)->:up) (test/options.jl:50; src/action_gen.jl:14): tabulated over the dense state space, the
-    action widening proposes table[s] and draws no random number. Lane-per-tree and tile kernel against the oracle."""
+    action widening proposes table[s] and draws no random number. Against the oracle."""
     monkeypatch.setenv("MCTSB200_FAST", fast)
     roots = gridworld_roots(24)
     gens = (lambda mdp, s, snode: "up",
@@ -420,7 +420,7 @@ def test_emu_next_action_as_a_state_only_function(emu_ctx, oracle, monkeypatch, 
         for kw in (dict(), dict(k_action=2.0, alpha_action=0.3, init_Q=1.5, init_N=2), dict(estimate_value=0.0, enable_state_pw=False)):
             s = m.DPWSolver(n_iterations=80, depth=8, exploration_constant=4.0, rng=12, next_action=gen, **kw)
             _, _, _, st = run_both(emu_ctx, oracle, s, GW, roots, compare_trees=range(0, 24, 5))
-            assert st.kernel_variant == int(fast) or kw  # (the lane-per-tree kernel takes rollout estimates only)
+            assert st.kernel_variant == 0  # (the tile kernel takes these calls whatever MCTSB200_FAST says)
     t = emu_ctx.tree_export(0)
     assert (np.diff(t["child_offsets"]) <= 1).all()  # one proposal per state: at most one child
 
