@@ -102,7 +102,9 @@ def plan_sharded(ctx: Context, solver, mdp, states: Sequence, rank: Optional[int
 def plan_root_parallel(ctx: Context, solver, mdp, state, n_trees_total: int, rank: Optional[int] = None,
                        world: Optional[int] = None, device=None):
     """Root-parallel decision for ONE root: `n_trees_total` trees of `solver.n_iterations` iterations each, split
-    across ranks; one allreduce(sum) of 2*|A| doubles. Returns (action_idx, best_q, q_per_action, sum_n, stats)."""
+    across ranks; one allreduce(sum) of 5*|A|+1 int64 words (exact integer partial sums: the result does not depend on the number of
+    ranks) -- inside the library over its NCCL communicator after `attach_comm`, else over the process group. Returns
+    (action_idx, best_q, q_per_action, sum_n, stats)."""
     import torch
 
     dist = _dist()
