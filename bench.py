@@ -426,7 +426,8 @@ def main():
         # ---- the other workloads, N = 1 -----------------------------------------------------------------------------------
         if world == 1:
             others = {}
-            for name in ("config2-uct-gridworld-deterministic", "config2-uct-gridworld-stochastic", "config3-dpw-gridworld", "config4-dpw-mountaincar"):
+            for name in ("config2-uct-gridworld-deterministic", "config2-uct-gridworld-stochastic", "config3-dpw-gridworld", "config4-dpw-mountaincar",
+                         "box-dpw-continuous-actions"):
                 b = Batch(name)
                 r, _ = measure(b, max(1, min(args.steps, 3)), 1)
                 r["config"] = config_of(name, b.n, 1)
@@ -443,7 +444,8 @@ def main():
                                   ("config2-uct-gridworld-deterministic", line["workloads"]["config2-uct-gridworld-deterministic"]),
                                   ("config2-uct-gridworld-stochastic", line["workloads"]["config2-uct-gridworld-stochastic"]),
                                   ("config3-dpw-gridworld", line["workloads"]["config3-dpw-gridworld"]),
-                                  ("config4-dpw-mountaincar", line["workloads"]["config4-dpw-mountaincar"])):
+                                  ("config4-dpw-mountaincar", line["workloads"]["config4-dpw-mountaincar"]),
+                                  ("box-dpw-continuous-actions", line["workloads"]["box-dpw-continuous-actions"])):
                     dst["cpu_baseline"] = cpu_sample(name, seconds_target=6.0, single_seconds=2.0)
         except Exception as ex:  # the baseline must never break the GPU line
             line.setdefault("cpu_baseline", {"error": str(ex)})
