@@ -120,7 +120,9 @@ enum {
 typedef struct {
     int32_t struct_size;          /* = sizeof(mctsb200_solver_cfg), ABI guard                      */
     int32_t kind;                 /* MCTSB200_KIND_*                                               */
-    int64_t n_iterations;
+    int64_t n_iterations;         /* (a max_time search runs at most min(2^24 - 2, 2 * 10^9 / depth) of them.) Visit counts are 32-bit on the device (the reference's are Int64): a
+                                     call whose bound -- visits already in kept trees + n_iterations * depth -- passes 2 * 10^9
+                                     is refused with MCTSB200_ERR_CAPACITY (clear_tree! and start over), never wrapped         */
     int32_t depth;
     int32_t rollouts_per_leaf;    /* 1 = reference semantics; K>1 averages K rollouts per leaf     */
     double exploration_constant;  /* >= 0                                                          */
