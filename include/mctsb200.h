@@ -114,9 +114,10 @@ enum {
 #define MCTSB200_PLUGIN_PARAM_BYTES 256
 
 /* Flat mirror of MCTSSolver (src/vanilla.jl:28-62) and DPWSolver (src/dpw_types.jl:45-100).
- * Fields that hold host closures in the reference (callback, timer, reset_callback, show_progress,
- * Function/object-valued init_Q/init_N/estimate_value/next_action) have no representation here: the
- * host glue must refuse them (MCTSB200_ERR_UNSUPPORTED) -- there is no CPU fallback. */
+ * Fields that hold host closures in the reference have no representation here. What runs BETWEEN launches is a host hook (callback,
+ * show_progress: mctsb200_set_progress_callback; timer: mctsb200_set_timer); what looks at a state of a dense-state MDP only is a table
+ * the host fills (init_q_table, init_n_table, value_table, policy_table, next_action_table); everything else (reset_callback,
+ * closures over hashed states or tree nodes) the host glue must refuse (MCTSB200_ERR_UNSUPPORTED) -- there is no CPU fallback. */
 typedef struct {
     int32_t struct_size;          /* = sizeof(mctsb200_solver_cfg), ABI guard                      */
     int32_t kind;                 /* MCTSB200_KIND_*                                               */

@@ -182,7 +182,6 @@ function cfg_from(s::MCTSSolver, mdp)
     return cfg, tab
 end
 function cfg_from(s::DPWSolver, mdp)
-    s.show_progress && unsupported("`show_progress`")
     # next_action(f::Function, mdp, s, snode) = f(mdp, s, snode) (src/action_gen.jl:14; test/options.jl:50): a function that looks at the
     # state only is a table over a dense state space (snode is passed as `nothing`: a generator that inspects the node is refused)
     natab = nothing
@@ -298,14 +297,19 @@ end
 # trades fidelity for fewer launches. The planner is passed through the user pointer.
 function _progress_thunk(user::Ptr{Cvoid}, done::Int64, total::Int64)::Int32
     p = unsafe_pointer_to_objref(user)::B200Planner
-    p.solver.callback(p, Int(done))
+    if p.solver isa MCTSSolver
+        p.solver.callback(p, Int(done))
+    else   # DPWSolver.show_progress (src/dpw.jl:45-53: a ProgressMeter advanced per iteration), as a coarse host hook
+        print(stderr, "\rMCTS (DPW) ", done, "/", total, " iterations", done >= total ? "\n" : "")
+    end
     return Int32(0)
 end
 _timer_thunk(user::Ptr{Cvoid})::Float64 = (unsafe_pointer_to_objref(user)::B200Planner).solver.timer()
 function install_hooks!(p::B200Planner; every::Integer = 1)   # p must be a mutable struct kept alive (GC.@preserve) during plan
-    if p.solver isa MCTSSolver
+    if p.solver isa MCTSSolver || p.solver.show_progress
+        step = p.solver isa MCTSSolver ? every : max(1, p.solver.n_iterations ÷ 20)
         check(ccall((:mctsb200_set_progress_callback, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64), p.ctx.h,
-                    @cfunction(_progress_thunk, Int32, (Ptr{Cvoid}, Int64, Int64)), pointer_from_objref(p), every))
+                    @cfunction(_progress_thunk, Int32, (Ptr{Cvoid}, Int64, Int64)), pointer_from_objref(p), step))
     end
     check(ccall((:mctsb200_set_timer, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), p.ctx.h,
                 @cfunction(_timer_thunk, Float64, (Ptr{Cvoid},)), pointer_from_objref(p)))

@@ -200,8 +200,6 @@ def build_cfg(solver, mdp) -> tuple[abi.SolverCfg, list]:
     if is_dpw:
         if solver.reset_callback is not None:
             raise _unsupported("`reset_callback`")
-        if solver.show_progress:
-            raise _unsupported("`show_progress`")
         if solver.next_action is not None:
             # next_action(f::Function, mdp, s, snode) = f(mdp, s, snode) (src/action_gen.jl:14; test/options.jl:50 `(mdp, s, snode)->:up`):
             # a host function cannot run inside the search, but one that looks at the state only is a table over a dense state space
@@ -377,13 +375,24 @@ class _Planner:
         roots = self.mdp.encode_states(states)
         self._roots = [self.mdp.decode_state(r) for r in roots]
         cb = getattr(self.solver, "callback", None)
+        if cb is None and getattr(self.solver, "show_progress", False):
+            # DPWSolver.show_progress (src/dpw.jl:45-53: a ProgressMeter advanced once per iteration): a host hook between launches,
+            # about twenty updates per search
+            import sys
+
+            def cb(_planner, done, total=int(cfg.n_iterations)):
+                sys.stderr.write(f"\rMCTS (DPW) {done}/{total} iterations")
+                if done >= total:
+                    sys.stderr.write("\n")
+                sys.stderr.flush()
         if cb is not None:  # callback(planner, iteration) (src/vanilla.jl:231); planner.tree is live inside it
             def progress(done, _total):
                 self.tree = TreeView(self, 0)
                 cb(self, done)
                 return False
 
-            self.ctx.set_progress_callback(progress, max(1, int(self.solver.callback_every)))
+            every = int(getattr(self.solver, "callback_every", 0)) or max(1, int(cfg.n_iterations) // 20)
+            self.ctx.set_progress_callback(progress, max(1, every))
         if self.solver.timer is not None:
             self.ctx.set_timer(self.solver.timer)
         try:

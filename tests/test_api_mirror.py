@@ -41,7 +41,7 @@ def test_readme_usage(ctx):
     assert planner.action((1, 2)) in ("up", "down", "left", "right")
 
 
-def test_option_matrix_like_options_jl(ctx):
+def test_option_matrix_like_options_jl(ctx, capsys):
     """test/options.jl: every device-expressible form of init_Q / init_N / estimate_value runs for both solvers;
     a String is a MethodError (TypeError here); host closures without a device form are refused."""
     for S in (m.MCTSSolver, m.DPWSolver):
@@ -60,9 +60,14 @@ def test_option_matrix_like_options_jl(ctx):
     # launches (tested below)
     _, info = m.solve(m.MCTSSolver(n_iterations=30, depth=5, enable_tree_vis=True), GW, ctx=ctx).action_info((1, 1))
     assert sum(info["tree"]._vis_stats.values()) >= 30
-    for kw in (dict(reset_callback=lambda mdp, s: None), dict(show_progress=True)):
-        with pytest.raises(m.MCTSB200Error):
-            m.solve(m.DPWSolver(**kw), GW, ctx=ctx)
+    with pytest.raises(m.MCTSB200Error):
+        m.solve(m.DPWSolver(reset_callback=lambda mdp, s: None), GW, ctx=ctx)
+    # show_progress (src/dpw.jl:45-53) is a host hook between launches: the same tree as without it
+    base_dpw = dict(n_iterations=60, depth=5, exploration_constant=5.0, rng=4)
+    a_quiet, i_quiet = m.solve(m.DPWSolver(**base_dpw), GW, ctx=ctx).action_info((2, 2))
+    a_loud, i_loud = m.solve(m.DPWSolver(show_progress=True, **base_dpw), GW, ctx=ctx).action_info((2, 2))
+    assert a_quiet == a_loud and i_quiet["best_Q"] == i_loud["best_Q"]
+    assert "60/60 iterations" in capsys.readouterr().err
     # next_action=(mdp, s, snode)->:up (test/options.jl:50): a generator that looks at the state only is tabulated; every state node then
     # owns the one action it proposes
     p = m.solve(m.DPWSolver(n_iterations=60, depth=5, exploration_constant=5.0, next_action=lambda mdp, s, snode: "up"), GW, ctx=ctx)
