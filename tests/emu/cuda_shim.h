@@ -92,7 +92,8 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSucces
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
 static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = (size_t)8 << 30; return cudaSuccess; }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// (cudaMalloc aligns to 256 bytes; the kernels' 32-byte aligned row types rely on it)
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::aligned_alloc(256, (n ? n : 1) + 255 & ~(size_t)255); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return cudaSuccess; }
