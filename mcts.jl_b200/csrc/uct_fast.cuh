@@ -50,7 +50,10 @@ __device__ __forceinline__ unsigned __smid() {
 #endif
 
 constexpr int kFastMaxThreads = 512;
-constexpr int kFastTab = 2048;  // entries of sqrt(log N) and 1/sqrt(n) staged in shared memory
+#ifndef MCTSB200_FAST_TAB
+#define MCTSB200_FAST_TAB 2048
+#endif
+constexpr int kFastTab = MCTSB200_FAST_TAB;  // entries of sqrt(log N) and 1/sqrt(n) staged in shared memory
 enum { FAST_POLICY_RANDOM = 0, FAST_POLICY_CONSTANT = 1, FAST_POLICY_TABLE = 2 };
 enum { FAST_MODE_PLAIN = 0, FAST_MODE_AHEAD = 1, FAST_MODE_DET = 2 };
 
