@@ -28,6 +28,31 @@
 #define MCTSB200_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+#if !defined(MCTSB200_HOST_EMU) && !defined(__CUDACC_RTC__)
+#include <cstdlib>
+// Shared memory and L1 share the SM's 256 KB. Left to itself the driver gives a kernel with a large dynamic request the maximum
+// carve-out (L1: 28 KB); these kernels want every KB of L1 their block leaves over (32 768 roots: 29.2 -> 27.8 ms,
+// profiles/r2_experiments.md), so the launchers of the ONE-BLOCK-PER-SM kernels (uct_fast, dpw_fast) ask for the smallest carve-out
+// that holds the block. Not for the tile kernel: its small blocks share an SM, and a carve-out sized for one of them leaves room
+// for one of them (config 4: 445 -> 612 ms, a second wave of blocks); the driver's default is right there.
+// MCTSB200_CARVEOUT=<percent> overrides (experiments).
+namespace mctsb200 {
+template <class K>
+inline void prefer_smallest_carveout(K kernel, size_t dynamic_smem) {
+    static const int max_smem = [] {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        return v > 0 ? v : 228 * 1024;
+    }();
+    int pct = (int)(((dynamic_smem + 2048) * 100 + (size_t)max_smem - 1) / (size_t)max_smem);
+    if (const char* ev = std::getenv("MCTSB200_CARVEOUT"))
+        if (ev[0]) pct = std::atoi(ev);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+}
+}  // namespace mctsb200
+#endif
+
 #define MCTSB200_MAX_ACTIONS_PER_ROW 7
 
 namespace mctsb200 {

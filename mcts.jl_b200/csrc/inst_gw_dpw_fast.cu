@@ -9,6 +9,7 @@ static int32_t launch_dpw_fast_one(const KernelArgs<M>& args, int grid, int bloc
     auto kernel = dpw_fast_kernel<M, POLICY>;
 #ifndef MCTSB200_HOST_EMU
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MCTSB200_ERR_CUDA;
+    prefer_smallest_carveout(kernel, smem);
 #endif
     MCTSB200_LAUNCH(kernel, (unsigned)grid, (unsigned)block, smem, stream, args);
     return MCTSB200_OK;

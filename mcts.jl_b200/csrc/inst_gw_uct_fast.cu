@@ -9,6 +9,7 @@ static int32_t launch_fast_one(const KernelArgs<M>& args, int grid, int block, s
     auto kernel = uct_fast_kernel<M, POLICY, MODE>;
 #ifndef MCTSB200_HOST_EMU
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MCTSB200_ERR_CUDA;
+    prefer_smallest_carveout(kernel, smem);
 #endif
     MCTSB200_LAUNCH(kernel, (unsigned)grid, (unsigned)block, smem, stream, args);
     return MCTSB200_OK;

@@ -32,6 +32,7 @@
 // Reference lines restated: simulate src/vanilla.jl:240-276, insert_node! :292-307, best_sanode_UCB :354-386,
 // estimate_value(::SolvedRolloutEstimator) src/domain_knowledge.jl:65-73 + the POMDPTools RolloutSimulator loop.
 #pragma once
+#include <cstdlib>
 #ifdef MCTSB200_PHASE_TIMING
 #include <cstdio>
 #endif
@@ -54,6 +55,7 @@ constexpr int kFastMaxThreads = 512;
 #define MCTSB200_FAST_TAB 2048
 #endif
 constexpr int kFastTab = MCTSB200_FAST_TAB;  // entries of sqrt(log N) and 1/sqrt(n) staged in shared memory
+
 enum { FAST_POLICY_RANDOM = 0, FAST_POLICY_CONSTANT = 1, FAST_POLICY_TABLE = 2 };
 enum { FAST_MODE_PLAIN = 0, FAST_MODE_AHEAD = 1, FAST_MODE_DET = 2 };
 
