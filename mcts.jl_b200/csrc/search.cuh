@@ -24,6 +24,9 @@
 
 namespace mctsb200 {
 
+#ifndef MCTSB200_BOX_SCAN_U
+#define MCTSB200_BOX_SCAN_U 8  // children a lane has in flight in the scans of continuous-action trees
+#endif
 constexpr int kBlockThreads = 128;
 // Two ideas that looked free and measured slower on B200 (config 4, profiles/r2e_*: 465 ms without either, 477 ms with the widening
 // thresholds hoisted into registers, 520 ms with 1024-entry UCB table heads in shared memory -- the 16 KB per block come out of the
@@ -151,6 +154,26 @@ __device__ __forceinline__ void load_now(const T* p, T& out) {
 #endif
     }
     memcpy(&out, w, sizeof(T));
+#endif
+}
+
+// small loads that are issued where they are written (the children scans of continuous-action trees request several children's
+// indices, then their nodes, before looking at any of them: four L2 round trips overlap instead of queueing)
+__device__ __forceinline__ int ld_int_now(const int* p) {
+#ifdef MCTSB200_HOST_EMU
+    return *p;
+#else
+    int v;
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void ld_2u64_now(const void* p, unsigned long long& lo, unsigned long long& hi) {
+#ifdef MCTSB200_HOST_EMU
+    lo = reinterpret_cast<const unsigned long long*>(p)[0];
+    hi = reinterpret_cast<const unsigned long long*>(p)[1];
+#else
+    asm volatile("ld.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
 #endif
 }
 
@@ -1093,12 +1116,24 @@ struct Search {
                 M::next_action(a.mdp, s, rng, act);  // next_action(::RandomActionGenerator): always draws
                 bool present = false;
                 if (a.cfg.check_repeat_action) {  // haskey(tree.a_lookup, (snode, a)): isequal on the vector = bitwise
-                    for (int j = tile.lane; j < nchild; j += G) {
-                        const BoxANode* c = an + plog[cbase + j];
-                        bool eq = true;
+                    constexpr int U = MCTSB200_BOX_SCAN_U;  // children per lane and trip: their indices, then their labels, are requested together
+                    for (int j0 = tile.lane; j0 < nchild; j0 += U * G) {
+                        int id[U];
+                        unsigned long long lab[U][4];
 #pragma unroll
-                        for (int i = 0; i < AD; ++i) eq = eq && __double_as_longlong(c->a[i]) == __double_as_longlong(act.v[i]);
-                        present = present || eq;
+                        for (int u = 0; u < U; ++u) id[u] = ld_int_now(plog + cbase + (j0 + u * G < nchild ? j0 + u * G : j0));
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            ld_2u64_now(an[id[u]].a, lab[u][0], lab[u][1]);
+                            if constexpr (AD > 2) ld_2u64_now(an[id[u]].a + 2, lab[u][2], lab[u][3]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            bool eq = j0 + u * G < nchild;
+#pragma unroll
+                            for (int i = 0; i < AD; ++i) eq = eq && lab[u][i] == (unsigned long long)__double_as_longlong(act.v[i]);
+                            present = present || eq;
+                        }
                     }
                     present = tile.any(present);
                 }
@@ -1148,16 +1183,30 @@ struct Search {
             const double ltn = log_n(total_n);
             double best = -CUDART_INF;
             int best_j = kNone;
-            for (int j = tile.lane; j < nchild; j += G) {
-                const BoxANode* ch = an + plog[cbase + j];
-                const double2 qn = *reinterpret_cast<const double2*>(ch);  // (q, n | nac)
-                const int nn = __double2loint(qn.y);
-                double ucb;
-                if ((ltn <= 0.0 && nn == 0) || c == 0.0) ucb = qn.x;
-                else ucb = DM_ADD(qn.x, DM_MUL(c, DM_SQRT(DM_DIV(ltn, i2d(nn)))));
-                if (ucb > best) {
-                    best = ucb;
-                    best_j = j;
+            {
+                constexpr int U = MCTSB200_BOX_SCAN_U;  // as in the repeat check: several children's (q, n) in flight per lane
+                for (int j0 = tile.lane; j0 < nchild; j0 += U * G) {
+                    int id[U];
+                    unsigned long long qb[U], nb[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) id[u] = ld_int_now(plog + cbase + (j0 + u * G < nchild ? j0 + u * G : j0));
+#pragma unroll
+                    for (int u = 0; u < U; ++u) ld_2u64_now(an + id[u], qb[u], nb[u]);  // (q, n | nac)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int j = j0 + u * G;
+                        if (j < nchild) {
+                            const double q = __longlong_as_double((long long)qb[u]);
+                            const int nn = (int)(unsigned)nb[u];
+                            double ucb;
+                            if ((ltn <= 0.0 && nn == 0) || c == 0.0) ucb = q;
+                            else ucb = DM_ADD(q, DM_MUL(c, DM_SQRT(DM_DIV(ltn, i2d(nn)))));
+                            if (ucb > best) {  // (children of a lane are taken in increasing j: the first maximum)
+                                best = ucb;
+                                best_j = j;
+                            }
+                        }
+                    }
                 }
             }
             tile.argmax(best, best_j);
