@@ -84,6 +84,9 @@ def test_fuzz_gridworld(ctx, oracle, seed, monkeypatch):
     for call in range(3 if kept else 1):
         run_both(ctx, oracle, solver, mdp, roots, base=int(rng.integers(0, 1000)) if not kept else 5,
                  compare_trees=range(0, len(roots), max(1, len(roots) // 4)))
+        if getattr(solver, "enable_tree_vis", False):  # tree._vis_stats (src/vanilla.jl:328-334)
+            for i in range(0, len(roots), max(1, len(roots) // 3)):
+                assert ctx.tree_vis_stats(i) == oracle.tree_vis_stats(i)
         # an episode-like move: every root steps to a neighbouring cell (kept trees continue, or start a new root node)
         roots = [(min(max(x + int(rng.integers(-1, 2)), 1), mdp.size[0]), min(max(y + int(rng.integers(-1, 2)), 1), mdp.size[1])) for x, y in roots]
     ctx.clear_trees()
@@ -140,3 +143,69 @@ def test_fuzz_episodes(ctx, oracle, seed):
         solver.enable_tree_vis = False
     starts = [s for s in _random_roots(rng, mdp, int(rng.integers(1, 30)))]
     run_episodes_both(ctx, oracle, solver, mdp, starts, max_steps=int(rng.integers(1, 6)), env_seed=int(rng.integers(0, 1000)), base=int(rng.integers(0, 50)))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_root_parallel(ctx, oracle, seed):
+    """mctsb200_plan_root_parallel: an ensemble of trees of ONE root, per-action sums of N and N*Q -- the exact integer words summed in
+    any split and order give the oracle's doubles."""
+    rng = np.random.default_rng(3000 + seed)
+    mdp = _random_gridworld(rng) if rng.random() < 0.7 else m.MountainCar()
+    dense = isinstance(mdp, m.SimpleGridWorld)
+    solver = m.MCTSSolver(n_iterations=int(rng.integers(1, 150)), depth=int(rng.integers(1, 14)), rng=int(rng.integers(0, 2**31)),
+                          exploration_constant=float(rng.choice([0.5, 5.0])), estimate_value=_random_estimate(rng, mdp, dense))
+    root = _random_roots(rng, mdp, 1)[0] if dense else (float(rng.uniform(-1.0, 0.4)), float(rng.uniform(-0.05, 0.05)))
+    n_trees, base = int(rng.integers(1, 60)), int(rng.integers(0, 100))
+    cfg, keep = m.build_cfg(solver, mdp)
+    ctx.configure(mdp.mdp_id, mdp.params())
+    oracle.configure(mdp.mdp_id, mdp.params())
+    r = mdp.encode_states([root])
+    n1, nq1, _ = ctx.plan_root_parallel(cfg, mdp.mdp_id, r, n_trees, tree_index_base=base)
+    n2, nq2, _ = oracle.plan_root_parallel(cfg, mdp.mdp_id, r, n_trees, tree_index_base=base, n_threads=3)
+    assert np.array_equal(n1, n2) and np.array_equal(nq1.view(np.int64), nq2.view(np.int64))
+    # any split of the ensemble, merged through the integer words, gives the same bits
+    cut = int(rng.integers(0, n_trees + 1))
+    words = np.zeros(5 * len(n1) + 1, dtype=np.int64)
+    for lo, hi in ((0, cut), (cut, n_trees)):
+        if hi > lo:
+            ctx.plan_root_parallel(cfg, mdp.mdp_id, r, hi - lo, tree_index_base=base + lo)
+            words = words + ctx.root_sums_words()
+    n3, nq3 = ctx.root_sums_merge(words, len(n1))
+    assert np.array_equal(n3, n1) and np.array_equal(nq3.view(np.int64), nq1.view(np.int64))
+    del keep
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_plugins(gpu_ctx, oracle, seed):
+    """The run-time plugins (NVRTC-compiled tile kernel; device only) under random DPW / UCT options against their oracle restatements."""
+    from test_host_emu_parity import _run_box_both
+
+    rng = np.random.default_rng(11000 + seed)
+    which = int(rng.integers(0, 3))
+    roots = [(float(rng.uniform(-0.2, 0.2)), float(rng.uniform(-0.1, 0.1))) for _ in range(int(rng.integers(1, 10)))]
+    gpu_ctx.clear_trees()
+    oracle.clear_trees()
+    lanes = int(rng.choice([1, 4, 8])) if rng.random() < 0.5 else None
+    if which == 2:
+        mdp = m.ContinuousPendulum(noise=float(rng.choice([2.0, 10.0])), effort=float(rng.choice([0.0, 1e-4])))
+        solver = m.DPWSolver(n_iterations=int(rng.integers(1, 250)), depth=int(rng.integers(1, 10)), rng=int(rng.integers(0, 2**31)),
+                             exploration_constant=float(rng.choice([0.0, 2.0, 10.0])), k_action=float(rng.choice([2.0, 8.0])),
+                             alpha_action=float(rng.choice([0.25, 0.5])), alpha_state=float(rng.choice([0.125, 0.5])),
+                             check_repeat_action=bool(rng.random() < 0.7), check_repeat_state=bool(rng.random() < 0.7),
+                             keep_tree=bool(rng.random() < 0.4), keep_tree_calls=3,
+                             estimate_value=m.RolloutEstimator(m.PluginPolicy(100) if rng.random() < 0.5 else m.RandomSolver(), max_depth=int(rng.choice([-1, 6]))))
+        for call in range(2 if solver.keep_tree else 1):
+            _run_box_both(gpu_ctx, oracle, solver, mdp, roots, base=2, lanes=lanes)
+    else:
+        mdp = m.NoisyMountainCar() if which == 0 else m.InvertedPendulum()
+        if which == 0:
+            roots = [(float(rng.uniform(-1.1, 0.4)), float(rng.uniform(-0.05, 0.05))) for _ in roots]
+        solver = _random_solver(rng, mdp, dense=False)
+        if isinstance(solver, m.MCTSSolver):
+            solver.enable_tree_vis = False  # (unbounded branching: _vis_stats needs max_branch >= 1)
+        kept = getattr(solver, "keep_tree", False) or getattr(solver, "reuse_tree", False)
+        for call in range(2 if kept else 1):
+            run_both(gpu_ctx, oracle, solver, mdp, roots, base=3, lanes=lanes, literal=True)
+    gpu_ctx.clear_trees()
+    oracle.clear_trees()
