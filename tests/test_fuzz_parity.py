@@ -3,11 +3,16 @@ random models, solver options and call sequences -- every field of every compare
 seeds, so a failure names a reproducible case. The hand-written matrices of test_host_emu_parity.py / test_gpu_parity.py cover the
 options one at a time; this covers their combinations (and combinations are where the dispatch between the three kernel families,
 the kept-tree sizing and the table-driven hooks meet)."""
+import os
+
 import numpy as np
 import pytest
 
 import mcts_jl_b200 as m
 from helpers import run_both, run_episodes_both
+
+
+SCALE = int(os.environ.get("MCTSB200_FUZZ_SCALE", "1"))  # MCTSB200_FUZZ_SCALE=10: ten times as many cases (stress runs)
 
 
 @pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
@@ -70,7 +75,7 @@ def _random_roots(rng, mdp, n):
     return [cells[int(i)] for i in rng.integers(0, len(cells), size=n)]
 
 
-@pytest.mark.parametrize("seed", range(200))
+@pytest.mark.parametrize("seed", range(200 * SCALE))
 def test_fuzz_gridworld(ctx, oracle, seed, monkeypatch):
     rng = np.random.default_rng(1000 + seed)
     if rng.random() < 0.3:
@@ -93,7 +98,7 @@ def test_fuzz_gridworld(ctx, oracle, seed, monkeypatch):
     oracle.clear_trees()
 
 
-@pytest.mark.parametrize("seed", range(60))
+@pytest.mark.parametrize("seed", range(60 * SCALE))
 def test_fuzz_mountaincar(ctx, oracle, seed):
     rng = np.random.default_rng(5000 + seed)
     mdp = m.MountainCar()
@@ -111,7 +116,7 @@ def test_fuzz_mountaincar(ctx, oracle, seed):
     oracle.clear_trees()
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(40 * SCALE))
 def test_fuzz_box(ctx, oracle, seed):
     from test_host_emu_parity import _run_box_both
 
@@ -134,7 +139,7 @@ def test_fuzz_box(ctx, oracle, seed):
     oracle.clear_trees()
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(40 * SCALE))
 def test_fuzz_episodes(ctx, oracle, seed):
     rng = np.random.default_rng(7000 + seed)
     mdp = _random_gridworld(rng)
@@ -145,7 +150,7 @@ def test_fuzz_episodes(ctx, oracle, seed):
     run_episodes_both(ctx, oracle, solver, mdp, starts, max_steps=int(rng.integers(1, 6)), env_seed=int(rng.integers(0, 1000)), base=int(rng.integers(0, 50)))
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(40 * SCALE))
 def test_fuzz_root_parallel(ctx, oracle, seed):
     """mctsb200_plan_root_parallel: an ensemble of trees of ONE root, per-action sums of N and N*Q -- the exact integer words summed in
     any split and order give the oracle's doubles."""
@@ -176,7 +181,7 @@ def test_fuzz_root_parallel(ctx, oracle, seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(16 * SCALE))
 def test_fuzz_plugins(gpu_ctx, oracle, seed):
     """The run-time plugins (NVRTC-compiled tile kernel; device only) under random DPW / UCT options against their oracle restatements."""
     from test_host_emu_parity import _run_box_both
