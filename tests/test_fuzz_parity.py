@@ -217,3 +217,44 @@ def test_fuzz_plugins(gpu_ctx, oracle, seed):
             run_both(gpu_ctx, oracle, solver, mdp, roots, base=3, lanes=lanes, literal=True)
     gpu_ctx.clear_trees()
     oracle.clear_trees()
+
+
+@pytest.mark.parametrize("seed", range(20 * SCALE))
+def test_fuzz_multi_device_ctx(emu_lib_path, seed):
+    """mctsb200_ctx_create_multi: the same calls on a ctx over several "devices" (the emulator's one device, twice or three times)
+    return what a single-device ctx returns -- plans, exported trees wherever they live, episodes, root-parallel sums."""
+    rng = np.random.default_rng(13000 + seed)
+    mdp = _random_gridworld(rng) if rng.random() < 0.7 else m.MountainCar()
+    dense = isinstance(mdp, m.SimpleGridWorld)
+    solver = _random_solver(rng, mdp, dense)
+    for attr in ("keep_tree", "reuse_tree"):  # (kept trees pin tree i to its device: covered by the single-device cases)
+        if hasattr(solver, attr):
+            setattr(solver, attr, False)
+    n = int(rng.integers(1, 30))
+    roots = _random_roots(rng, mdp, n) if dense else [(float(rng.uniform(-1.0, 0.4)), float(rng.uniform(-0.05, 0.05))) for _ in range(n)]
+    one = m.Context(0, lib_path=emu_lib_path)
+    many = m.Context([0] * int(rng.integers(2, 4)), lib_path=emu_lib_path)
+    cfg, keep = m.build_cfg(solver, mdp)
+    r = mdp.encode_states(roots)
+    base = int(rng.integers(0, 100))
+    for c in (one, many):
+        c.configure(mdp.mdp_id, mdp.params())
+    a1, q1, s1, _ = one.plan(cfg, mdp.mdp_id, r, base, want_status=True)
+    a2, q2, s2, _ = many.plan(cfg, mdp.mdp_id, r, base, want_status=True)
+    assert np.array_equal(a1, a2) and np.array_equal(q1.view(np.int64), q2.view(np.int64)) and np.array_equal(s1, s2)
+    for i in range(0, n, max(1, n // 4)):
+        t1, t2 = one.tree_export(i, mdp.state_dtype, mdp.state_width), many.tree_export(i, mdp.state_dtype, mdp.state_width)
+        assert all(np.array_equal(t1[k].view(np.uint8), t2[k].view(np.uint8)) for k in t1)
+    if getattr(solver, "enable_tree_vis", False):
+        solver.enable_tree_vis = False
+        cfg, keep = m.build_cfg(solver, mdp)
+    e1 = one.run_episodes(cfg, mdp.mdp_id, r, 3, 17, base)
+    e2 = many.run_episodes(cfg, mdp.mdp_id, r, 3, 17, base)
+    assert all(np.array_equal(np.asarray(x).view(np.uint8), np.asarray(y).view(np.uint8)) for x, y in zip(e1[:3], e2[:3]))
+    if isinstance(solver, m.MCTSSolver):
+        p1 = one.plan_root_parallel(cfg, mdp.mdp_id, r[:1], 11, tree_index_base=base)
+        p2 = many.plan_root_parallel(cfg, mdp.mdp_id, r[:1], 11, tree_index_base=base)
+        assert np.array_equal(p1[0], p2[0]) and np.array_equal(p1[1].view(np.int64), p2[1].view(np.int64))
+    one.close()
+    many.close()
+    del keep
