@@ -58,6 +58,10 @@ def _random_solver(rng, mdp, dense=True):
     elif dense and rng.random() < 0.2:
         common["init_Q"] = lambda mdp_, s, a: 0.125 * (s[0] - s[1]) + (1.0 if a == "up" else 0.0)  # Function-valued -> tables
         common["init_N"] = lambda mdp_, s, a: (s[0] + s[1]) % 3
+    if rng.random() < 0.15 and isinstance(common["estimate_value"], m.RolloutEstimator):
+        common["rollouts_per_leaf"] = int(rng.choice([2, 3, 8]))  # leaf-parallel rollouts, averaged in stream order
+    if rng.random() < 0.25:
+        common["lanes_per_tree"] = int(rng.choice([1, 2, 4, 8, 16, 32]))  # tile width (results do not depend on it)
     if rng.random() < 0.5:
         return m.MCTSSolver(reuse_tree=bool(rng.random() < 0.4), enable_tree_vis=bool(rng.random() < 0.2), **common)
     kw = dict(k_action=float(rng.choice([1.0, 4.0, 10.0])), alpha_action=float(rng.choice([0.1, 0.5, 0.8])),
