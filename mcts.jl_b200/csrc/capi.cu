@@ -679,9 +679,9 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
         if constexpr (M::kActionDoubles > 0) {
             // a continuous action space: a state node may own as many children as the widening rule allows (one more per visit at most)
             std::vector<int> na;
-            // (a kept tree brings the children of earlier calls: the table runs to the visit bound, which includes them, and ends at
-            // the first length no visit count below that bound allows)
-            const long long max_len = std::min<long long>(bound, (1 << 20) - 2);
+            // (a kept tree brings the children of earlier calls -- at most one per earlier visit; the table ends at the first length
+            // no visit count below the bound allows)
+            const long long max_len = std::min<long long>(prior_visits + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1, (1 << 20) - 2);
             for (long long len = 0; len <= max_len; ++len) {
                 const int v = nmin_for(cfg->k_action, cfg->alpha_action, (int)len, bound);
                 na.push_back(v);
@@ -693,9 +693,13 @@ int32_t build_dev_cfg(mctsb200_ctx* ctx, const mctsb200_solver_cfg* cfg, DevCfg&
             d.nmin_action_n = (int)na.size();
         }
         std::vector<int> ns;
-        // n_a_children never exceeds the model's branching (merged states) nor the visits of its action node -- those of earlier
-        // calls included when the tree is kept (`bound`); the loop ends at the first length no visit count below the bound allows
-        const long long need_len = cfg->check_repeat_state ? std::min<long long>(MdpAccess<M>::max_branch(ctx), bound) : bound;
+        // n_a_children never exceeds the model's branching (merged states) nor the pushes to its action node: one per visit, and an
+        // unmerged tree visits a node at most once per iteration. A kept tree brings the pushes of earlier calls (prior_visits: found
+        // by the randomised test -- a table sized for one call made kept unmerged trees stop widening). The loop ends at the first
+        // length no visit count below the bound allows.
+        const long long need_len = cfg->check_repeat_state
+                                       ? std::min<long long>(MdpAccess<M>::max_branch(ctx), prior_visits + cfg->n_iterations * (long long)std::max(cfg->depth, 1) + 1)
+                                       : prior_visits + cfg->n_iterations + 1;
         const long long max_len = std::min<long long>(need_len, (1 << 20) - 2);
         for (long long len = 0; len <= max_len; ++len) {
             const int v = nmin_for(cfg->k_state, cfg->alpha_state, (int)len, bound);

@@ -255,6 +255,30 @@ def test_emu_kept_trees_of_hashed_models(emu_ctx, oracle, kind):
     oracle.clear_trees()
 
 
+def test_emu_kept_unmerged_trees_keep_widening(emu_ctx, oracle):
+    """Found by tests/test_fuzz_parity.py: with check_repeat_state = false every transition makes a node, so n_a_children of a kept
+    tree's action node grows call after call -- past the length of a widening-threshold table sized for ONE call, where the search
+    silently stopped widening. Three calls on a terminate_from root (every action ends the episode: all visits go to one action node
+    per call), against the oracle; and a long unmerged search whose visit bound exceeds 2^20 still gets its table."""
+    gw = m.SimpleGridWorld(size=(8, 5), rewards={(5, 4): 10.0, (1, 2): 3.0}, terminate_from={(5, 4), (1, 2)})
+    s = m.DPWSolver(n_iterations=41, depth=15, exploration_constant=0.0, k_action=4.0, alpha_action=0.8, check_repeat_state=False, keep_tree=True,
+                    keep_tree_calls=4, init_N=0, rng=7)
+    emu_ctx.clear_trees()
+    oracle.clear_trees()
+    for _ in range(3):
+        run_both(emu_ctx, oracle, s, gw, [(5, 4), (1, 2), (4, 4)])
+    # one new (terminal) state node per iteration in every call; the second call also makes a second root node: the first call's root
+    # was inserted with maintain_s_lookup = check_repeat_state = false (src/dpw.jl:40), so the kept tree cannot find it (src/dpw.jl:33)
+    assert emu_ctx.tree_export(0)["total_n"].shape[0] == 42 + 42 + 41
+    emu_ctx.clear_trees()
+    oracle.clear_trees()
+    big = m.DPWSolver(n_iterations=60000, depth=20, k_state=10.0, alpha_state=1.0, check_repeat_state=False, estimate_value=0.0, rng=1)
+    cfg, keep = m.build_cfg(big, gw)
+    emu_ctx.configure(gw.mdp_id, gw.params())
+    emu_ctx.plan(cfg, gw.mdp_id, gw.encode_states([(5, 4)]))  # (60 000 one-level iterations)
+    assert emu_ctx.tree_export(0)["total_n"].shape[0] == 60001
+
+
 def test_emu_kept_trees_report_capacity_when_their_room_is_used_up(emu_ctx):
     mc = m.MountainCar()
     emu_ctx.clear_trees()
