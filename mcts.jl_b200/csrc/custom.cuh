@@ -135,6 +135,7 @@ struct CustomBoxDev {
     static constexpr bool kCustom = true;
     static constexpr int kStateDoubles = SD;
     static constexpr int kActionDoubles = AD;
+    static constexpr bool kCoopGen = false;  // (a plugin's gen runs on every lane of a tile)
     static_assert(AD >= 1 && AD <= 4, "an action node's label holds up to four doubles (BoxANode)");
 
     struct AbiState { double v[SD]; };

@@ -378,6 +378,34 @@ struct GaussianBoxDev {
         sp.v[3] = s.v[3];
         r = DM_SUB(0.0, DM_MUL(p.cost, ss));
     }
+    // The same on a tile of G >= 2 lanes (which all run the same stream: search.cuh). The two Box-Muller pairs are the same
+    // functions on different arguments, so even lanes take the first pair and odd lanes the second: one det_log, one square root, one
+    // det_cos and one det_sin pass instead of two / two / two / one -- the same rounded operations on the same operands, hence the
+    // same bits as gen(); the three deviates come back by shuffle.
+    static constexpr bool kCoopGen = true;
+    template <class TileT>
+    __device__ __forceinline__ static void gen_coop(const TileT& tile, const Params& p, const State& s, const Action& a, Stream& rng, State& sp,
+                                                    double& r) {
+        const double two_pi = 6.283185307179586;
+        const double u1a = DM_MUL(DM_ADD((double)rng.next(), 1.0), 1.0 / 4294967296.0), u2a = rng.uniform01();
+        const double u1b = DM_MUL(DM_ADD((double)rng.next(), 1.0), 1.0 / 4294967296.0), u2b = rng.uniform01();
+        const bool second = (tile.lane & 1) != 0;
+        const double rad = DM_SQRT(DM_MUL(-2.0, det_log(second ? u1b : u1a))), ang = DM_MUL(two_pi, second ? u2b : u2a);
+        const double zc = DM_MUL(rad, det_cos(ang));  // z0 on even lanes, z2 on odd ones
+        const double zs = DM_MUL(rad, det_sin(ang));  // z1 on even lanes
+        const double z[3] = {tile.bcast(zc, 0), tile.bcast(zs, 0), tile.bcast(zc, 1)};
+        double ss = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double x = s.v[i];
+            if (i < kActionDoubles) x = DM_ADD(x, DM_MUL(p.drift, a.v[i]));
+            x = DM_ADD(x, DM_MUL(p.sd[i], z[i]));
+            sp.v[i] = x;
+            ss = DM_ADD(ss, DM_MUL(x, x));
+        }
+        sp.v[3] = s.v[3];
+        r = DM_SUB(0.0, DM_MUL(p.cost, ss));
+    }
 };
 
 }  // namespace mctsb200

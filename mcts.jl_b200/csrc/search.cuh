@@ -334,7 +334,9 @@ struct Search {
             if constexpr (M::kActionDoubles > 0) {  // RandomPolicy on a continuous action space: rand(rng, actions(mdp, s))
                 typename M::Action act;
                 M::policy_action(a.mdp, a.cfg.policy, a.cfg.pparam, s, rs, act);
-                M::gen(a.mdp, s, act, rs, sp, r);
+                // (these models run one rollout per leaf: every lane of the tile is here, with the same stream)
+                if constexpr (G >= 2 && M::kCoopGen) M::gen_coop(tile, a.mdp, s, act, rs, sp, r);
+                else M::gen(a.mdp, s, act, rs, sp, r);
             } else {
                 int act;
                 if (M::kDense && a.cfg.policy == MCTSB200_POLICY_TABLE) act = (int)a.cfg.policy_table[M::dense_index(a.mdp, s)];  // FunctionPolicy(f), tabulated
@@ -1229,7 +1231,8 @@ struct Search {
                 widen = AN.n >= need;
             }
             if (widen) {
-                M::gen(a.mdp, s, act, rng, sp, r);
+                if constexpr (G >= 2 && M::kCoopGen) M::gen_coop(tile, a.mdp, s, act, rng, sp, r);
+                else M::gen(a.mdp, s, act, rng, sp, r);
                 spnode = a.cfg.check_repeat_state ? map_lookup(sp) : -1;
                 if (spnode < 0) {
                     spnode = dpw_insert_state(sp, a.cfg.maintain_lookup != 0);
