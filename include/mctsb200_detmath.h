@@ -201,4 +201,31 @@ MCTSB200_HD double det_sincos_impl(double x, int want_sin) {
     }
 }
 
+/* Both at once: det_sin(x) and det_cos(x) bit for bit (one reduction, both kernels evaluated on every call and the quadrant applied
+ * by selection) -- for callers that need the pair, and for SIMT code whose lanes would otherwise split over the quadrant switch. */
+MCTSB200_HD void det_sincos(double x, double* s_out, double* c_out) {
+    const double INV_PIO2 = dm_from_bits(0x3fe45f306dc9c883ULL);
+    const double PIO2_1 = dm_from_bits(0x3ff921fb54400000ULL);
+    const double PIO2_2 = dm_from_bits(0x3dd0b4611a600000ULL);
+    const double PIO2_2T = dm_from_bits(0x3ba3198a2e037073ULL);
+    const uint64_t ax = dm_bits(x) & 0x7fffffffffffffffULL;
+    if (ax > 0x4130000000000000ULL) {
+        *s_out = *c_out = dm_from_bits(0x7ff8000000000000ULL);
+        return;
+    }
+    const double fn = floor(DM_ADD(DM_MUL(x, INV_PIO2), 0.5));
+    const int n = (int)fn;
+    const double t = DM_SUB(x, DM_MUL(fn, PIO2_1));
+    const double w1 = DM_MUL(fn, PIO2_2);
+    const double r = DM_SUB(t, w1);
+    const double w = DM_SUB(DM_MUL(fn, PIO2_2T), DM_SUB(DM_SUB(t, r), w1));
+    const double y0 = DM_SUB(r, w);
+    const double y1 = DM_SUB(DM_SUB(r, y0), w);
+    const double kc = dm_kernel_cos(y0, y1), ks = dm_kernel_sin(y0, y1);
+    const double nkc = DM_SUB(0.0, kc), nks = DM_SUB(0.0, ks);
+    const int q = n & 3;
+    *c_out = q == 0 ? kc : q == 1 ? nks : q == 2 ? nkc : ks;  /* det_cos's switch                    */
+    *s_out = q == 0 ? ks : q == 1 ? kc : q == 2 ? nks : nkc;  /* det_sin's: the same, one quadrant back */
+}
+
 #endif /* MCTSB200_DETMATH_H */

@@ -359,8 +359,10 @@ struct GaussianBoxDev {
         {
             const double u1 = DM_MUL(DM_ADD((double)rng.next(), 1.0), 1.0 / 4294967296.0), u2 = rng.uniform01();
             const double rad = DM_SQRT(DM_MUL(-2.0, det_log(u1))), ang = DM_MUL(two_pi, u2);
-            z[0] = DM_MUL(rad, det_cos(ang));
-            z[1] = DM_MUL(rad, det_sin(ang));
+            double sn, cs;
+            det_sincos(ang, &sn, &cs);  // (= det_sin(ang), det_cos(ang) with one reduction)
+            z[0] = DM_MUL(rad, cs);
+            z[1] = DM_MUL(rad, sn);
         }
         {
             const double u1 = DM_MUL(DM_ADD((double)rng.next(), 1.0), 1.0 / 4294967296.0), u2 = rng.uniform01();
@@ -391,8 +393,10 @@ struct GaussianBoxDev {
         const double u1b = DM_MUL(DM_ADD((double)rng.next(), 1.0), 1.0 / 4294967296.0), u2b = rng.uniform01();
         const bool second = (tile.lane & 1) != 0;
         const double rad = DM_SQRT(DM_MUL(-2.0, det_log(second ? u1b : u1a))), ang = DM_MUL(two_pi, second ? u2b : u2a);
-        const double zc = DM_MUL(rad, det_cos(ang));  // z0 on even lanes, z2 on odd ones
-        const double zs = DM_MUL(rad, det_sin(ang));  // z1 on even lanes
+        double sn, cs;
+        det_sincos(ang, &sn, &cs);               // (no quadrant branch for the lanes to split over)
+        const double zc = DM_MUL(rad, cs);       // z0 on even lanes, z2 on odd ones
+        const double zs = DM_MUL(rad, sn);       // z1 on even lanes
         const double z[3] = {tile.bcast(zc, 0), tile.bcast(zs, 0), tile.bcast(zc, 1)};
         double ss = 0.0;
 #pragma unroll

@@ -24,7 +24,9 @@ struct ContinuousPendulum {
     __device__ static void gen(const Params& p, const double* s, const double* a, mctsb200::Stream& rng, double* sp, double& r) {
         const double th = s[0], w = s[1];
         const double u = DM_ADD(a[0], DM_MUL(DM_SUB(rng.uniform01(), 0.5), p.noise));
-        const double sn = det_sin(th), cs = det_cos(th), s2 = det_sin(DM_MUL(2.0, th));
+        double sn, cs;
+        det_sincos(th, &sn, &cs);  // (= det_sin(th), det_cos(th): one reduction, no quadrant branch for the lanes of a warp to split over)
+        const double s2 = det_sin(DM_MUL(2.0, th));
         const double aml = DM_MUL(DM_MUL(p.alpha, p.m), p.l);
         const double num = DM_SUB(DM_SUB(DM_MUL(p.g, sn), DM_MUL(DM_MUL(DM_MUL(aml, DM_MUL(w, w)), s2), 0.5)), DM_MUL(DM_MUL(p.alpha, cs), u));
         const double den = DM_SUB(DM_MUL(4.0 / 3.0, p.l), DM_MUL(DM_MUL(p.alpha, p.l), DM_MUL(cs, cs)));
