@@ -18,6 +18,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef MCTSB200_MC_COS_NB
+#define MCTSB200_MC_COS_NB 0  // 1: MountainCar's cosine without the quadrant branch (experiment, profiles/r2_experiments.md)
+#endif
+
 namespace mctsb200 {
 
 // ---------------------------------------------------------------------------------------------
@@ -274,7 +278,13 @@ struct MountainCarDev {
     // v' = clamp(v + a*0.001 + cos(3x)*-0.0025, -0.07, 0.07); x' = x + v'; inelastic wall at -1.2
     __device__ __forceinline__ static void gen(const Params& p, const State& s, int ai, Stream&, State& sp, double& r) {
         const double push = ai == 0 ? -0.001 : (ai == 1 ? 0.0 : 0.001);  // a * 0.001 for a in (-1., 0., 1.): exact
+#if MCTSB200_MC_COS_NB
+        double sn_, cs_;
+        det_sincos(DM_MUL(3.0, s.x), &sn_, &cs_);  // experiment: no quadrant branch (both kernels always)
+        double v_ = DM_ADD(DM_ADD(s.v, push), DM_MUL(cs_, -0.0025));
+#else
         double v_ = DM_ADD(DM_ADD(s.v, push), DM_MUL(det_cos(DM_MUL(3.0, s.x)), -0.0025));
+#endif
         v_ = v_ > 0.07 ? 0.07 : (v_ < -0.07 ? -0.07 : v_);  // clamp (two compares: FP64 min/max are multi-instruction sequences)
         double x_ = DM_ADD(s.x, v_);
         if (x_ < -1.2) {
