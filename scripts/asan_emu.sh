@@ -7,5 +7,5 @@ make -C tests/emu libmctsb200_emu_asan.so > /dev/null
 export MCTSB200_EMU_LIB=$PWD/tests/emu/libmctsb200_emu_asan.so
 ASAN=$(${ASAN_CXX:-/usr/bin/g++} -print-file-name=libasan.so)
 export LD_PRELOAD=$(readlink -f "$ASAN") ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1
-python -m pytest tests/test_host_emu_parity.py tests/test_api_mirror.py tests/test_distributed_gloo.py -x -q -m "not gpu" -p no:cacheprovider
+python -m pytest tests/test_host_emu_parity.py tests/test_api_mirror.py tests/test_distributed_gloo.py tests/test_fuzz_parity.py -x -q -m "not gpu" -p no:cacheprovider
 python scripts/sanitize_small.py --emu "$MCTSB200_EMU_LIB"
