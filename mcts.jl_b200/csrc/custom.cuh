@@ -16,7 +16,7 @@
 // value table; tests/test_gpu_parity.py::test_plugin_params_may_carry_device_pointers).
 // `a` is the 0-based index into actions(mdp); random numbers come from `rng.next()` (32-bit words of the tree's Philox
 // stream), `rng.uniform_int(n)`, `rng.uniform01()`. The source sees everything search.cuh sees (DM_ADD / DM_MUL /
-// det_cos / det_log for reproducible arithmetic). The library compiles search_kernel<CustomDev<SD, A>, KIND, G> around
+// det_log / det_cos / det_sin / det_sincos for reproducible arithmetic). The library compiles search_kernel<CustomDev<SD, A>, KIND, G> around
 // it with NVRTC for sm_100a -- the same tile kernel the built-in MountainCar runs -- and launches the result; nothing of
 // a plugin ever runs on the host (north star: no CPU fallback).
 //
